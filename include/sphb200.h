@@ -1,0 +1,213 @@
+/* sphb200.h -- C ABI of the B200-native JAX-SPH per-step engine (libsphb200.so).
+ *
+ * Everything a host binding (the jax.ffi shim in csrc/ffi_shim.cc, the ctypes
+ * loader in jax_sph_b200/_lib.py) needs.  Plain C: POD structs, raw pointers,
+ * sizes, a cudaStream_t passed as void*.  No torch / jax types.
+ *
+ * The reference (tumaer/jax-sph) has NO native interface for this path -- it is
+ * pure Python/JAX -- so each entry point names the Python callable it replaces
+ * (citations relative to the reference tree):
+ *
+ *   sphb200_neighbor_list   <- jax_sph/partition.py:492-571  neighbor_list(...).allocate/.update
+ *                              (jax_sph/jax_md/partition.py:914-983, Sparse format, .idx)
+ *   sphb200_forward         <- jax_sph/solver.py:702-951     WCSPH.forward_wrapper()(state, neighbors)
+ *   sphb200_advance         <- jax_sph/integrator.py:22-56   si_euler(...).advance(dt, state, neighbors)
+ *                              (+ the case bc_fn / g_ext_fn in table form, cases/*.py)
+ *   sphb200_engine_*        <- jax_sph/simulate.py:110-134   the step loop, state resident in HBM
+ *
+ * Conventions
+ *   - All functions return 0 on success or a negative SPHB200_E* code; they never
+ *     abort, throw or print.  sphb200_strerror() gives the text.
+ *   - Device work is enqueued on the caller's stream; nothing synchronises the
+ *     device unless documented ("sync").  Run-time conditions (neighbour-list
+ *     overflow, staging overflow) are reported through a device-side error word
+ *     (bits below), mirroring PartitionErrorCode (jax_md/partition.py:434-457).
+ *   - Arrays use the reference layouts: vector fields are (N, dim) row-major
+ *     float32, scalar fields (N,) float32, tag (N,) int32.
+ *   - float32 only: the reference's float64 mode is not offered (documented drift
+ *     bound instead); a float64 request fails with SPHB200_EDTYPE.
+ *   - Re-entrant: no global mutable state; one engine per stream/device.
+ */
+#ifndef SPHB200_H_
+#define SPHB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHB200_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+#define SPHB200_OK 0
+#define SPHB200_EINVAL (-1)   /* bad argument / inconsistent config            */
+#define SPHB200_ENOMEM (-2)   /* cudaMalloc failed or workspace too small      */
+#define SPHB200_ECUDA (-3)    /* a CUDA runtime call failed                    */
+#define SPHB200_EDTYPE (-4)   /* unsupported dtype (float64)                   */
+#define SPHB200_EUNSUP (-5)   /* unsupported variant (e.g. DELTA solver)       */
+#define SPHB200_ENODEV (-6)   /* no CUDA device / not an sm_100 device         */
+
+/* ---- device-side error word (sphb200_engine_error) ---------------------- */
+#define SPHB200_ERR_NEIGHBOR_OVERFLOW (1u << 0) /* == PartitionErrorCode.NEIGHBOR_LIST_OVERFLOW */
+#define SPHB200_ERR_CELL_OVERFLOW (1u << 1)     /* == PartitionErrorCode.CELL_LIST_OVERFLOW     */
+#define SPHB200_ERR_STAGE_OVERFLOW (1u << 2)    /* one stencil row exceeds the staging buffer   */
+#define SPHB200_ERR_NONFINITE (1u << 3)         /* non-finite position met while hashing        */
+
+/* ---- enums --------------------------------------------------------------- */
+enum { SPHB200_SOLVER_SPH = 0, SPHB200_SOLVER_RIE = 1 };  /* solver.py:639-640 (DELTA: unsupported) */
+enum { SPHB200_KERNEL_QSK = 0, SPHB200_KERNEL_WC2K = 1 }; /* kernel.py:51-103                        */
+enum { SPHB200_EOS_TAIT = 0, SPHB200_EOS_RIEMANN = 1 };   /* eos.py:20-57                            */
+
+/* solver flags (WCSPH ctor booleans, solver.py:616-637) */
+#define SPHB200_F_BC_TRICK (1u << 0)        /* is_bc_trick        */
+#define SPHB200_F_RHO_EVOL (1u << 1)        /* is_rho_evol        */
+#define SPHB200_F_RHO_RENORM (1u << 2)      /* is_rho_renorm      */
+#define SPHB200_F_FREE_SLIP (1u << 3)       /* is_free_slip       */
+#define SPHB200_F_HEAT (1u << 4)            /* is_heat_conduction */
+
+/* tags, utils.py:22-32 */
+enum {
+  SPHB200_TAG_PAD = -1,
+  SPHB200_TAG_FLUID = 0,
+  SPHB200_TAG_SOLID_WALL = 1,
+  SPHB200_TAG_MOVING_WALL = 2,
+  SPHB200_TAG_DIRICHLET_WALL = 3
+};
+
+/* external force g_ext_fn(r) in table form (cases/tgv.py:53, db.py:129-132, pf.py/ht.py band) */
+enum { SPHB200_G_NONE = 0, SPHB200_G_CONST = 1, SPHB200_G_BAND = 2, SPHB200_G_ARRAY = 3 };
+
+/* case bc_fn in table form: per tag, which fields are overwritten after forward
+ * (cases/db.py:134-142, cf.py:143-160, pf.py, ht.py:154-187) */
+#define SPHB200_BC_SET_U (1u << 0)
+#define SPHB200_BC_SET_V (1u << 1)
+#define SPHB200_BC_ZERO_DUDT (1u << 2)
+#define SPHB200_BC_ZERO_DVDT (1u << 3)
+#define SPHB200_BC_SET_P (1u << 4)
+#define SPHB200_BC_SET_T (1u << 5)
+#define SPHB200_BC_ZERO_DTDT (1u << 6)
+
+typedef struct sphb200_bc_rule {
+  uint32_t flags; /* SPHB200_BC_* */
+  float u[3];
+  float v[3];
+  float p;
+  float T;
+} sphb200_bc_rule;
+
+/* ---- configuration -------------------------------------------------------
+ * Mirrors the WCSPH constructor (solver.py:616-637), the EoS objects
+ * (eos.py), si_euler's tvf (integrator.py:8-10), space.periodic(side=box)
+ * (case_setup.py:133) and the table form of the case callables.  Physical
+ * parameters are doubles and are rounded to float32 exactly where the
+ * reference's weakly-typed Python scalars are. */
+typedef struct sphb200_config {
+  uint32_t struct_size; /* = sizeof(sphb200_config), ABI check */
+  int32_t dim;          /* 2 or 3 */
+  int32_t solver;       /* SPHB200_SOLVER_* */
+  int32_t kernel;       /* SPHB200_KERNEL_* */
+  int32_t eos;          /* SPHB200_EOS_*    */
+  uint32_t flags;       /* SPHB200_F_*      */
+  double box[3];        /* periodic box sides (box[2] ignored in 2D) */
+  double dx;            /* particle spacing                          */
+  double h;             /* smoothing length = h_fac * dx             */
+  double dt;            /* WCSPH.dt: rho / T integration inside forward */
+  double tvf;           /* si_euler tvf                               */
+  double c_ref;         /* RIE limiter                                */
+  double eta_limiter;   /* RIE, -1 = off                              */
+  double artificial_alpha;
+  double p_ref, rho_ref, p_bg, gamma; /* TaitEoS                      */
+  double u_ref;                       /* RIEMANNEoS                   */
+  /* g_ext table */
+  int32_t g_mode;   /* SPHB200_G_* */
+  int32_t g_axis;   /* BAND: coordinate axis tested */
+  double g[3];      /* CONST / BAND value */
+  double g_lo, g_hi; /* BAND: g applied where lo < r[axis] < hi */
+  /* bc table, indexed by tag 0..3 */
+  sphb200_bc_rule bc[4];
+  int32_t bc_inflow_on;  /* ht.py:159-161: fluid with r.x < x  -> T = T_in, dTdt = 0 */
+  float bc_inflow_x, bc_inflow_T;
+  int32_t bc_outflow_on; /* ht.py:182-185: fluid with r.x > x  -> dTdt = 0           */
+  float bc_outflow_x;
+  /* tuning (0 = automatic) */
+  int32_t cell_sub[3]; /* cells per cutoff along each axis (1 or 2)  */
+  int32_t tile[3];     /* tile size in cells                         */
+  int32_t threads;     /* sweep block size                           */
+  int32_t list_cap;    /* per-thread pair-list capacity              */
+  int32_t stage_cap;   /* staged particles per block (0 = auto)      */
+  int32_t reserved[8];
+} sphb200_config;
+
+/* State dict of the reference (solver.py:930-947), device or host pointers.
+ * Optional members may be NULL: nw (zeros), T (ones), dTdt, kappa, Cp, drhodt (zeros). */
+typedef struct sphb200_state {
+  float *r, *u, *v, *dudt, *dvdt, *nw;                          /* (N, dim) */
+  float *rho, *p, *drhodt, *mass, *eta, *T, *dTdt, *kappa, *Cp; /* (N,)     */
+  int32_t *tag;                                                 /* (N,)     */
+  float *g_ext; /* (N, dim), only read when g_mode == SPHB200_G_ARRAY */
+} sphb200_state;
+
+typedef struct sphb200_engine sphb200_engine;
+
+/* step flags */
+#define SPHB200_STEP_INTEGRATE (1u << 0) /* si_euler kick+drift before forward (advance); unset = forward only */
+#define SPHB200_STEP_BC (1u << 1)        /* apply the bc table after forward                                  */
+
+/* ---- library ------------------------------------------------------------- */
+int sphb200_abi_version(void);
+const char *sphb200_strerror(int code);
+void sphb200_config_default(sphb200_config *cfg);
+
+/* ---- resident engine (state stays cell-sorted in HBM between steps) ------ */
+/* Bytes of device memory an engine for n particles needs. */
+int sphb200_engine_bytes(const sphb200_config *cfg, int64_t n, size_t *bytes);
+/* Allocates its own arena with cudaMalloc on the current device. */
+int sphb200_engine_create(const sphb200_config *cfg, int64_t n, sphb200_engine **out);
+/* Places the engine in caller-owned device memory (>= sphb200_engine_bytes). */
+int sphb200_engine_create_in(const sphb200_config *cfg, int64_t n, void *workspace,
+                             size_t workspace_bytes, sphb200_engine **out);
+int sphb200_engine_destroy(sphb200_engine *e);
+/* Copy a state in reference layout into the engine (on_host: pointers are host memory). */
+int sphb200_engine_upload(sphb200_engine *e, const sphb200_state *s, int on_host, void *stream);
+/* nsteps x advance(dt) (integrator.py:22-56) or forward only, per `flags`. */
+int sphb200_engine_step(sphb200_engine *e, double dt, int nsteps, uint32_t flags, void *stream);
+/* Write the state back in the ORIGINAL particle order (index-stable API). NULL members are skipped. */
+int sphb200_engine_download(sphb200_engine *e, sphb200_state *out, int on_host, void *stream);
+/* sync: read and clear the device error word. */
+int sphb200_engine_error(sphb200_engine *e, uint32_t *code, void *stream);
+/* Sparse neighbour list of the CURRENT resident positions in original indices:
+ * idx is (2, capacity) int32 on the device, row 0 receiver, row 1 sender, sorted
+ * by (sender, receiver), padded with N (jax_md/partition.py:885-909).  count
+ * (device int64, may be NULL) receives the number of edges found; overflow sets
+ * SPHB200_ERR_NEIGHBOR_OVERFLOW. */
+int sphb200_engine_neighbor_list(sphb200_engine *e, int32_t *idx, int64_t capacity,
+                                 int mask_self, int64_t *count, void *stream);
+/* sync: kinetic energy 0.5*sum(m u.u) (utils.py:128-133) and max |u| (utils.py:136-166). */
+int sphb200_engine_stats(sphb200_engine *e, double *ekin, double *u_max, void *stream);
+/* Kernel launches issued by this engine so far (bench.py's gpu_launches). */
+int64_t sphb200_engine_launches(const sphb200_engine *e);
+/* Sweep timing: CUDA-event ms of the last step's passes: [0] integrate+hash, [1] sort/reorder,
+ * [2] density sweep, [3] wall sweep, [4] force sweep, [5] total.  Enabled by sphb200_engine_profile(e, 1). sync. */
+int sphb200_engine_profile(sphb200_engine *e, int enable);
+int sphb200_engine_last_times(sphb200_engine *e, float ms[8]);
+/* cell-grid facts for reports: ncells[3], sub[3], tile[3], threads, list_cap, stage_cap(A,B,C). */
+int sphb200_engine_plan(const sphb200_engine *e, int32_t out[16]);
+
+/* ---- stateless entry points (device pointers, caller-owned workspace) ----- */
+int sphb200_workspace_bytes(const sphb200_config *cfg, int64_t n, size_t *bytes);
+int sphb200_neighbor_list(const sphb200_config *cfg, int64_t n, const float *r, int32_t *idx,
+                          int64_t capacity, int mask_self, int64_t *count, uint32_t *err,
+                          void *workspace, size_t workspace_bytes, void *stream);
+int sphb200_forward(const sphb200_config *cfg, int64_t n, const sphb200_state *in,
+                    sphb200_state *out, uint32_t *err, void *workspace, size_t workspace_bytes,
+                    void *stream);
+int sphb200_advance(const sphb200_config *cfg, int64_t n, double dt, const sphb200_state *in,
+                    sphb200_state *out, uint32_t *err, void *workspace, size_t workspace_bytes,
+                    void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHB200_H_ */

@@ -1,0 +1,266 @@
+// cells.cuh -- integrate + hash, cell table, stable reorder, pack / unpack.
+//
+// Replaces, per step: integrator.py:26-30 (kick, drift, periodic wrap), the cell
+// hash + argsort + scatter of jax_md/partition.py:367-393 and the occupancy
+// bookkeeping of :401-403.  The sort is a one-digit radix (counting) sort with
+// radix = number of cells, made stable by an in-cell rank fix, so particle order
+// inside a cell is the order of the previous frame -- deterministic sums.
+//
+// All passes are HBM-bound streaming kernels: one particle per thread, float4
+// accesses, grid = ceil(N / 256).
+#pragma once
+#include "common.cuh"
+
+namespace sphb200 {
+
+// K1: integrate (optionally), hash, histogram.  Reads pt, um, du, dv (64 B),
+// writes key + arrival rank (8 B); cell counters live in L2.
+template <int DIM>
+__global__ void __launch_bounds__(256) k_hash(int n, Grid g, Kick k, const float4* __restrict__ pt,
+                                              const float4* __restrict__ um,
+                                              const float4* __restrict__ du,
+                                              const float4* __restrict__ dv, int* __restrict__ key,
+                                              int* __restrict__ rnk, int* __restrict__ count,
+                                              unsigned* __restrict__ err) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  float4 a = pt[p];
+  float r[3] = {a.x, a.y, a.z};
+  if (k.on) {
+    float4 b = um[p];
+    float u[3] = {b.x, b.y, b.z}, v[3];
+    integrate_one<DIM>(k, g, r, u, v, du[p], dv[p]);
+  }
+  bool finite = isfinite(r[0]) && isfinite(r[1]) && (DIM == 2 || isfinite(r[2]));
+  if (!finite) {
+    atomicOr(err, SPHB200_ERR_NONFINITE);
+    r[0] = r[1] = r[2] = 0.0f;
+  }
+  int c[3];
+  int cell = cell_of<DIM>(g, r, c);
+  key[p] = cell;
+  rnk[p] = atomicAdd(&count[cell], 1);
+}
+
+// K2: exclusive scan of the cell histogram -> cell_start[0..C].  Three small
+// launches (C <= a few million): block sums, scan of block sums, final scan.
+constexpr int SCAN_TPB = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_TPB * SCAN_ITEMS;
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(FULL_MASK, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// inclusive block scan of one value per thread; returns inclusive value, total in *total
+__device__ __forceinline__ int block_incl_scan(int v, int* sh /* >= 32 ints */, int* total) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int inc = warp_incl_scan(v, lane);
+  if (lane == 31) sh[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int s = lane < nw ? sh[lane] : 0;
+    s = warp_incl_scan(s, lane);
+    sh[lane] = s;
+  }
+  __syncthreads();
+  int off = w > 0 ? sh[w - 1] : 0;
+  *total = sh[nw - 1];
+  __syncthreads();
+  return inc + off;
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_partial(int c, const int* __restrict__ count,
+                                                           int* __restrict__ bsum) {
+  __shared__ int sh[32];
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) s += (base + i < c) ? count[base + i] : 0;
+  int tot;
+  block_incl_scan(s, sh, &tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of bsum[0..nb) in place (nb arbitrary)
+__global__ void __launch_bounds__(1024) k_scan_bsum(int nb, int* __restrict__ bsum) {
+  __shared__ int sh[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int v = i < nb ? bsum[i] : 0;
+    int tot;
+    int inc = block_incl_scan(v, sh, &tot);
+    int carry = carry_s;
+    if (i < nb) bsum[i] = carry + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_final(int c, int n, int* __restrict__ count,
+                                                         const int* __restrict__ bsum,
+                                                         int* __restrict__ start,
+                                                         int* __restrict__ maxocc) {
+  __shared__ int sh[32];
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int s = 0, mx = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    v[i] = (base + i < c) ? count[base + i] : 0;
+    s += v[i];
+    mx = max(mx, v[i]);
+  }
+  int tot;
+  int inc = block_incl_scan(s, sh, &tot);
+  int run = bsum[blockIdx.x] + inc - s;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < c) {
+      start[base + i] = run;
+      count[base + i] = 0;  // ready for the next step's histogram
+    }
+    run += v[i];
+  }
+  if (base <= c && c < base + SCAN_ITEMS) start[c] = n;
+  mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 16));
+  mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 8));
+  mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 4));
+  mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 2));
+  mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 1));
+  if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(maxocc, mx);
+}
+
+// K3: slot (arrival order) -> source index.
+__global__ void __launch_bounds__(256) k_scatter_src(int n, const int* __restrict__ key,
+                                                     const int* __restrict__ rnk,
+                                                     const int* __restrict__ start,
+                                                     int* __restrict__ src) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  src[start[key[p]] + rnk[p]] = p;
+}
+
+// K4: stable in-cell rank + integrate + gather the whole frame into the new
+// (cell-sorted) frame.  One thread per arrival slot.
+struct ReorderOpt {
+  int heat, has_nw, has_ge;
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_reorder(int n, Grid g, Kick k, ReorderOpt o, Frame a,
+                                                 Frame b, const int* __restrict__ key,
+                                                 const int* __restrict__ start,
+                                                 const int* __restrict__ src) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int p = src[s];
+  int cell = key[p];
+  int lo = start[cell], hi = start[cell + 1];
+  int rank = 0;
+  for (int t = lo; t < hi; ++t) rank += (__ldg(&src[t]) < p);
+  int f = lo + rank;
+
+  float4 pt = a.pt[p], um = a.um[p], vv = a.vv[p], du = a.du[p];
+  float r[3] = {pt.x, pt.y, pt.z}, u[3] = {um.x, um.y, um.z}, v[3] = {vv.x, vv.y, vv.z};
+  if (k.on) integrate_one<DIM>(k, g, r, u, v, du, a.dv[p]);
+  b.pt[f] = make_float4(r[0], r[1], r[2], pt.w);
+  b.um[f] = make_float4(u[0], u[1], u[2], um.w);
+  b.vv[f] = make_float4(v[0], v[1], v[2], vv.w);
+  b.st[f] = a.st[p];
+  b.du[f] = make_float4(0.f, 0.f, 0.f, du.w);  // drhodt passes through when not evolved
+  b.id[f] = a.id[p];
+  if (o.heat) b.kc[f] = a.kc[p];
+  if (o.has_nw) b.nw[f] = a.nw[p];
+  if (o.has_ge) b.ge[f] = a.ge[p];
+}
+
+// ---------------------------------------------------------------------------
+// pack: reference layout -> frame (identity order); unpack: frame -> reference
+// layout in ORIGINAL order (scatter through id).
+struct StatePtrs {
+  const float *r, *u, *v, *dudt, *dvdt, *nw, *rho, *p, *drhodt, *mass, *eta, *T, *dTdt, *kappa,
+      *Cp, *g_ext;
+  const int* tag;
+};
+struct StateOut {
+  float *r, *u, *v, *dudt, *dvdt, *nw, *rho, *p, *drhodt, *mass, *eta, *T, *dTdt, *kappa, *Cp;
+  int* tag;
+};
+
+template <int DIM>
+__device__ __forceinline__ float4 load_vec(const float* a, int p, float w) {
+  if (a == nullptr) return make_float4(0.f, 0.f, 0.f, w);
+  if (DIM == 2) {
+    float2 t = reinterpret_cast<const float2*>(a)[p];
+    return make_float4(t.x, t.y, 0.f, w);
+  }
+  return make_float4(a[3 * p], a[3 * p + 1], a[3 * p + 2], w);
+}
+
+template <int DIM>
+__device__ __forceinline__ void store_vec(float* a, int p, float4 q) {
+  if (a == nullptr) return;
+  if (DIM == 2) {
+    reinterpret_cast<float2*>(a)[p] = make_float2(q.x, q.y);
+  } else {
+    a[3 * p] = q.x; a[3 * p + 1] = q.y; a[3 * p + 2] = q.z;
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_pack(int n, StatePtrs s, Frame f, int* __restrict__ wallcount) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int tag = s.tag ? s.tag[p] : 0;
+  f.pt[p] = load_vec<DIM>(s.r, p, __int_as_float(tag));
+  f.um[p] = load_vec<DIM>(s.u, p, s.mass ? s.mass[p] : 1.0f);
+  f.vv[p] = load_vec<DIM>(s.v, p, s.eta ? s.eta[p] : 0.0f);
+  f.st[p] = make_float4(s.rho ? s.rho[p] : 1.0f, s.p ? s.p[p] : 0.0f, s.T ? s.T[p] : 1.0f,
+                        s.dTdt ? s.dTdt[p] : 0.0f);
+  f.du[p] = load_vec<DIM>(s.dudt, p, s.drhodt ? s.drhodt[p] : 0.0f);
+  f.dv[p] = load_vec<DIM>(s.dvdt, p, 0.0f);
+  if (f.kc) f.kc[p] = make_float2(s.kappa ? s.kappa[p] : 0.0f, s.Cp ? s.Cp[p] : 0.0f);
+  if (f.nw) f.nw[p] = load_vec<DIM>(s.nw, p, 0.0f);
+  if (f.ge) f.ge[p] = load_vec<DIM>(s.g_ext, p, 0.0f);
+  f.id[p] = p;
+  if (is_wall_tag(tag)) atomicAdd(wallcount, 1);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_unpack(int n, Frame f, StateOut o) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int p = f.id[s];
+  float4 pt = f.pt[s], um = f.um[s], vv = f.vv[s], st = f.st[s], du = f.du[s], dv = f.dv[s];
+  store_vec<DIM>(o.r, p, pt);
+  store_vec<DIM>(o.u, p, um);
+  store_vec<DIM>(o.v, p, vv);
+  store_vec<DIM>(o.dudt, p, du);
+  store_vec<DIM>(o.dvdt, p, dv);
+  if (o.tag) o.tag[p] = __float_as_int(pt.w);
+  if (o.mass) o.mass[p] = um.w;
+  if (o.eta) o.eta[p] = vv.w;
+  if (o.rho) o.rho[p] = st.x;
+  if (o.p) o.p[p] = st.y;
+  if (o.T) o.T[p] = st.z;
+  if (o.dTdt) o.dTdt[p] = st.w;
+  if (o.drhodt) o.drhodt[p] = du.w;
+  if (f.kc) {
+    float2 kc = f.kc[s];
+    if (o.kappa) o.kappa[p] = kc.x;
+    if (o.Cp) o.Cp[p] = kc.y;
+  }
+  if (o.nw && f.nw) store_vec<DIM>(o.nw, p, f.nw[s]);
+}
+
+}  // namespace sphb200

@@ -1,0 +1,233 @@
+// common.cuh -- shared device structs and bit-faithful arithmetic helpers.
+//
+// sm_100a only.  Everything here is new code; comments cite the reference
+// expressions whose *values* the helpers reproduce (paths relative to the
+// reference tree).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sphb200.h"
+
+namespace sphb200 {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+// ---------------------------------------------------------------------------
+// Resident particle frame: cell-sorted, float4-packed so that every pass moves
+// 16-byte vectors (coalesced LDG.128 / STG.128 and LDS.128 when staged).
+//   pt = (x, y, z, tag-bits)        um = (ux, uy, uz, mass)
+//   vv = (vx, vy, vz, eta)          st = (rho, p, T, dTdt)
+//   du = (dudt xyz, drhodt)         dv = (dvdt xyz, unused)
+//   kc = (kappa, Cp)                nw = (nw xyz, 0)        ut = (u_tilde xyz, 0)  [RIE walls]
+//   ge = (g_ext xyz, 0)  [only g_mode == ARRAY]             id = original particle index
+struct Frame {
+  float4 *pt, *um, *vv, *st, *du, *dv, *nw, *ut, *ge;
+  float2 *kc;
+  int *id;
+};
+
+// Cell grid + stencil/tiling plan (host-computed, passed by value).
+struct Grid {
+  int n[3];      // cells per axis (n[2] = 1 in 2D)
+  int S[3];      // stencil half width in cells
+  int W[3];      // per-particle window length  = min(2S+1, n)
+  int T[3];      // tile size in cells
+  int nt[3];     // tiles per axis
+  int ncells;
+  int exact_all; // small-box mode: no fast reject, window covers the whole axis
+  float inv_cell[3];
+  float box[3], half[3];
+  float c2;      // f32(cutoff)^2 rounded to f32  (jax_md/partition.py:820-822)
+  float c2_hi;   // fast-reject threshold  (> c2, covers rounding of the fast path)
+  float c2_lo;   // below this the pair is inside for every rounding
+};
+
+// Derived float32 constants, rounded where the reference rounds them.
+struct Consts {
+  int dim, solver, kernel, eos;
+  uint32_t flags;
+  float eps;        // finfo(float32).eps, solver.py:21
+  float ooh;        // f32(1/h)               kernel.py:55
+  float sigma;      // f32(sigma)             kernel.py:56-62 / :80-86
+  float sigma_ooh;  // f32(sigma) * f32(1/h)  (jax.grad of w)
+  float dt_s;       // f32(WCSPH.dt)
+  float p_ref, rho_ref, p_bg, gamma, inv_gamma, c100;
+  float p_bg_tvf;   // eos.p_fn(0), solver.py:802
+  float c_ref, eta_lim;
+  int use_lim;
+  float av_coef;    // f32(alpha * h_ab * c_ab), solver.py:413-415
+  float av_eps;     // f32(0.01 * h_ab^2)
+  int g_mode, g_axis;
+  float g[3], g_lo, g_hi;
+  sphb200_bc_rule bc[4];
+  int inflow_on, outflow_on;
+  float inflow_x, inflow_T, outflow_x;
+  int any_walls;    // 0 when no particle carries a wall tag (host-known hint)
+};
+
+// Per-launch switches of the sweep policies (phys.cuh).
+struct Extra {
+  float4* st_out;  // destination of the (rho, p, T, dTdt) quad (ping-pong, see engine.cu)
+  int nq;          // quads staged per particle
+  int q_v, q_h, q_nw, q_ut;  // optional staged quads (force sweep), -1 = absent
+  int utilde;      // RIE & bc_trick & !free_slip: write u_tilde
+  int wallT;       // RIE & bc_trick & heat: Shepard wall temperature
+  int finalT;      // this sweep integrates T (no wall sweep follows)
+  int heat, av, bc_on, free_slip, bc_trick;
+  // neighbour-list materialiser
+  int* nl_counts;
+  const int* nl_offsets;
+  int* nl_idx;
+  long long nl_capacity;
+  int nl_mask_self, nl_fill, nl_n;
+};
+
+// ---------------------------------------------------------------------------
+// jnp.mod(t, side) for float32 (fmod + sign fix-up toward the divisor), the
+// arithmetic of space.py:181 and :209.  fmodf is exact, so the only rounding is
+// the fix-up add, exactly as in XLA / NumPy.
+__device__ __forceinline__ float mod_side(float t, float side) {
+  float m;
+  if (t >= 0.0f && t < side) {
+    m = t;
+  } else if (t >= side && t < 2.0f * side) {
+    m = __fsub_rn(t, side);  // exact (Sterbenz)
+  } else if (t < 0.0f && t > -side) {
+    m = __fadd_rn(t, side);  // fmod(t, side) == t, then + side
+  } else {
+    m = fmodf(t, side);
+    if (m != 0.0f && (m < 0.0f)) m = __fadd_rn(m, side);
+  }
+  return m;
+}
+
+// space.py:170-181  periodic_displacement(side, a - b)
+__device__ __forceinline__ float disp1(float a, float b, float half, float side) {
+  float d = __fsub_rn(a, b);
+  float t = __fadd_rn(d, half);
+  return __fsub_rn(mod_side(t, side), half);
+}
+
+// space.py:184-192 sum of squares, left to right, no FMA contraction.
+template <int DIM>
+__device__ __forceinline__ float sumsq(const float (&d)[3]) {
+  float acc = __fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1]));
+  if (DIM == 3) acc = __fadd_rn(acc, __fmul_rn(d[2], d[2]));
+  return acc;
+}
+
+// integrator.py:26-30 + space.py:207-209 for one particle; used by the hashing
+// pass and again by the reorder pass, so both see bit-identical positions.
+struct Kick {
+  float dt;  // f32(dt)
+  float c2;  // f32(f32(tvf*0.5) * f32(dt))
+  int on;
+};
+
+template <int DIM>
+__device__ __forceinline__ void integrate_one(const Kick k, const Grid& g, float (&r)[3],
+                                              float (&u)[3], float (&v)[3], const float4 du,
+                                              const float4 dv) {
+  if (!k.on) return;
+  const float a[3] = {du.x, du.y, du.z};
+  const float b[3] = {dv.x, dv.y, dv.z};
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    u[d] = __fadd_rn(u[d], __fmul_rn(k.dt, a[d]));
+    v[d] = __fadd_rn(u[d], __fmul_rn(k.c2, b[d]));
+    float t = __fadd_rn(r[d], __fmul_rn(k.dt, v[d]));
+    r[d] = mod_side(t, g.box[d]);
+  }
+}
+
+// Cell coordinates of a position (clamped; the reference truncates
+// position / cell_size, jax_md/partition.py:367).
+template <int DIM>
+__device__ __forceinline__ int cell_of(const Grid& g, const float (&r)[3], int (&c)[3]) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (d < DIM) {
+      int ci = (int)(r[d] * g.inv_cell[d]);
+      ci = ci < 0 ? 0 : (ci >= g.n[d] ? g.n[d] - 1 : ci);
+      c[d] = ci;
+    } else {
+      c[d] = 0;
+    }
+  }
+  return (c[2] * g.n[1] + c[1]) * g.n[0] + c[0];
+}
+
+// ---------------------------------------------------------------------------
+// Smoothing kernels, evaluated inline (kernel.py:51-103).  x^5 = ((x^2)^2)*x as
+// lax.integer_pow lowers it.
+template <int KERN>
+__device__ __forceinline__ float kernel_w(const Consts& c, float r) {
+  float q = r * c.ooh;
+  if (KERN == SPHB200_KERNEL_QSK) {
+    float q1 = fmaxf(0.0f, 1.0f - q), q2 = fmaxf(0.0f, 2.0f - q), q3 = fmaxf(0.0f, 3.0f - q);
+    float a1 = q1 * q1, a2 = q2 * q2, a3 = q3 * q3;
+    float p1 = (a1 * a1) * q1, p2 = (a2 * a2) * q2, p3 = (a3 * a3) * q3;
+    return c.sigma * ((p3 - 6.0f * p2) + 15.0f * p1);
+  } else {
+    float q1 = fmaxf(0.0f, 1.0f - 0.5f * q);
+    float a = q1 * q1;
+    return c.sigma * ((a * a) * (2.0f * q + 1.0f));
+  }
+}
+
+template <int KERN>
+__device__ __forceinline__ float kernel_gw(const Consts& c, float r) {
+  float q = r * c.ooh;
+  if (KERN == SPHB200_KERNEL_QSK) {
+    float q1 = fmaxf(0.0f, 1.0f - q), q2 = fmaxf(0.0f, 2.0f - q), q3 = fmaxf(0.0f, 3.0f - q);
+    float a1 = q1 * q1, a2 = q2 * q2, a3 = q3 * q3;
+    float poly = (-5.0f * (a3 * a3) + 30.0f * (a2 * a2)) - 75.0f * (a1 * a1);
+    return c.sigma_ooh * poly;
+  } else {
+    float q1 = fmaxf(0.0f, 1.0f - 0.5f * q);
+    return c.sigma_ooh * ((-5.0f * q) * ((q1 * q1) * q1));
+  }
+}
+
+// eos.py:33-38 / :53-57
+__device__ __forceinline__ float eos_p(const Consts& c, float rho) {
+  if (c.eos == SPHB200_EOS_TAIT) {
+    float x = rho / c.rho_ref;
+    if (c.gamma != 1.0f) x = powf(x, c.gamma);
+    return c.p_ref * (x - 1.0f) + c.p_bg;
+  }
+  return c.c100 * (rho - c.rho_ref) + c.p_bg;
+}
+
+__device__ __forceinline__ float eos_rho(const Consts& c, float p) {
+  if (c.eos == SPHB200_EOS_TAIT) {
+    float x = ((p + c.p_ref) - c.p_bg) / c.p_ref;
+    if (c.gamma != 1.0f) x = powf(x, c.inv_gamma);
+    return c.rho_ref * x;
+  }
+  return (p - c.p_bg) / c.c100 + c.rho_ref;
+}
+
+// g_ext_fn(r) in table form.
+template <int DIM>
+__device__ __forceinline__ void g_ext_of(const Consts& c, const Frame& f, int p,
+                                         const float (&r)[3], float (&g)[3]) {
+  g[0] = g[1] = g[2] = 0.0f;
+  if (c.g_mode == SPHB200_G_CONST) {
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) g[d] = c.g[d];
+  } else if (c.g_mode == SPHB200_G_BAND) {
+    float x = r[c.g_axis];
+    bool in = (x < c.g_hi) && (x > c.g_lo);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) g[d] = in ? c.g[d] : 0.0f;
+  } else if (c.g_mode == SPHB200_G_ARRAY) {
+    float4 q = f.ge[p];
+    g[0] = q.x; g[1] = q.y; g[2] = q.z;
+  }
+}
+
+__device__ __forceinline__ bool is_wall_tag(int tag) { return tag >= 1 && tag <= 3; }
+
+}  // namespace sphb200

@@ -1,0 +1,959 @@
+// engine.cu -- host side of libsphb200.so: planning, arena, launches, C ABI.
+//
+// The per-step pipeline (one call of si_euler.advance, integrator.py:22-56):
+//   k_hash        kick + drift + wrap (recomputed, not stored) -> cell key, arrival rank, histogram
+//   k_scan_*      cell histogram -> cell_start table
+//   k_scatter_src arrival slot -> source index
+//   k_reorder     stable in-cell rank, kick + drift + wrap, gather into the new cell-sorted frame
+//   k_sweep<PhysDensity>  [k_sweep<PhysRenorm>]  [k_sweep<PhysWall>]  k_sweep<PhysForce>  [k_bc]
+// The state never leaves HBM between steps; the original particle order is
+// restored only by k_unpack (download).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "cells.cuh"
+#include "common.cuh"
+#include "phys.cuh"
+#include "sweep.cuh"
+
+using namespace sphb200;
+
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t _e = (call);                       \
+    if (_e != cudaSuccess) return SPHB200_ECUDA;   \
+  } while (0)
+
+namespace {
+
+constexpr size_t ALIGN = 256;
+inline size_t up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
+
+struct SweepPlan {
+  int nq, cap;
+  size_t smem;
+};
+
+}  // namespace
+
+struct sphb200_engine {
+  sphb200_config cfg;
+  int n, dim;
+  Grid grid;
+  Consts consts;
+  char* arena;
+  size_t arena_bytes;
+  bool own_arena;
+  Frame fr[2];
+  int cur;
+  bool cells_valid;
+  int *key, *rnk, *src, *count, *start, *bsum, *maxocc, *wallcount, *nl_counts;
+  unsigned* err;
+  double* stats;  // [ekin, umax]
+  int nscan_blocks;
+  int tpb, lcap;
+  SweepPlan planA, planR, planW, planC, planN;
+  bool has_kc, has_nw, has_ut, has_ge;
+  int64_t launches;
+  bool profile;
+  cudaEvent_t ev[8];
+  float times[8];
+  // host staging for on_host upload / download
+  char* hstage;
+  size_t hstage_bytes;
+  int max_smem;
+  bool needs_zero;
+};
+
+namespace {
+
+double kernel_cutoff(const sphb200_config& c) {
+  return (c.kernel == SPHB200_KERNEL_QSK ? 3.0 : 2.0) * c.h;
+}
+
+int validate(const sphb200_config* c, int64_t n) {
+  if (!c || c->struct_size != sizeof(sphb200_config)) return SPHB200_EINVAL;
+  if (c->dim != 2 && c->dim != 3) return SPHB200_EINVAL;
+  if (n <= 0 || n > 2000000000LL) return SPHB200_EINVAL;
+  if (c->solver != SPHB200_SOLVER_SPH && c->solver != SPHB200_SOLVER_RIE) return SPHB200_EUNSUP;
+  if (c->kernel != SPHB200_KERNEL_QSK && c->kernel != SPHB200_KERNEL_WC2K) return SPHB200_EUNSUP;
+  if (c->eos != SPHB200_EOS_TAIT && c->eos != SPHB200_EOS_RIEMANN) return SPHB200_EINVAL;
+  if (!(c->h > 0) || !(c->dx > 0)) return SPHB200_EINVAL;
+  for (int a = 0; a < c->dim; ++a)
+    if (!(c->box[a] > 0)) return SPHB200_EINVAL;
+  if (c->g_mode < 0 || c->g_mode > 3) return SPHB200_EINVAL;
+  if (c->g_mode == SPHB200_G_BAND && (c->g_axis < 0 || c->g_axis >= c->dim)) return SPHB200_EINVAL;
+  return SPHB200_OK;
+}
+
+// Cell grid, stencil and tiling (host).
+void plan_grid(const sphb200_config& c, Grid& g, int tpb) {
+  const double cutoff = kernel_cutoff(c);
+  double pop = 1.0;
+  g.exact_all = 0;
+  g.ncells = 1;
+  for (int a = 0; a < 3; ++a) {
+    if (a < c.dim) {
+      int sub = c.cell_sub[a] > 0 ? c.cell_sub[a] : 1;
+      if (sub > 4) sub = 4;
+      int n = (int)floor(c.box[a] * sub / (cutoff * 1.001));
+      if (n < 1) n = 1;
+      g.n[a] = n;
+      g.S[a] = sub;
+      g.W[a] = (n >= 2 * sub + 1) ? 2 * sub + 1 : n;
+      if (n < 2 * sub + 1) g.exact_all = 1;
+      g.inv_cell[a] = (float)(n / c.box[a]);
+      g.box[a] = (float)c.box[a];
+      g.half[a] = g.box[a] * 0.5f;
+      pop *= (c.box[a] / n) / c.dx;
+    } else {
+      g.n[a] = 1; g.S[a] = 0; g.W[a] = 1;
+      g.inv_cell[a] = 0.f; g.box[a] = 1.f; g.half[a] = 0.5f;
+    }
+    g.ncells *= g.n[a];
+  }
+  // tile: T1 = T2 = sub (so a tile is about one cutoff wide across), T0 fills the block
+  for (int a = 1; a < 3; ++a) {
+    int t = c.tile[a] > 0 ? c.tile[a] : (a < c.dim ? g.S[a] : 1);
+    if (t > g.n[a]) t = g.n[a];
+    g.T[a] = t;
+  }
+  while (g.T[1] * g.T[2] > MAX_RUNS) (g.T[2] > 1 ? g.T[2] : g.T[1])--;
+  int t0 = c.tile[0] > 0 ? c.tile[0] : (int)floor(0.9 * tpb / (pop * g.T[1] * g.T[2]) + 0.5);
+  if (t0 < 1) t0 = 1;
+  if (t0 > g.n[0]) t0 = g.n[0];
+  // MAX_SOFF bound on staged (row, cell) entries
+  auto entries = [&](int t) {
+    int rows = 1;
+    for (int a = 1; a < 3; ++a)
+      rows *= (g.n[a] >= 2 * g.S[a] + 1) ? g.T[a] + 2 * g.S[a] : g.n[a];
+    int nxs = (g.n[0] >= 2 * g.S[0] + 1) ? t + 2 * g.S[0] : g.n[0];
+    return rows * nxs;
+  };
+  while (t0 > 1 && entries(t0) > MAX_SOFF) --t0;
+  g.T[0] = t0;
+  for (int a = 0; a < 3; ++a) g.nt[a] = (g.n[a] + g.T[a] - 1) / g.T[a];
+
+  const float cf = (float)cutoff;
+  g.c2 = cf * cf;  // float32 product, jax_md/partition.py:820-822
+  if (g.exact_all) {
+    g.c2_hi = INFINITY;
+    g.c2_lo = -1.0f;
+  } else {
+    double side = 0;
+    for (int a = 0; a < c.dim; ++a) side = fmax(side, c.box[a]);
+    const double errd = 16.0 * 1.1920929e-7 * side * sqrt((double)c.dim);
+    const double chi = cutoff + errd, clo = fmax(0.0, cutoff - errd);
+    g.c2_hi = (float)(chi * chi * (1.0 + 1e-6));
+    g.c2_lo = (float)(clo * clo * (1.0 - 1e-6));
+  }
+}
+
+void plan_consts(const sphb200_config& c, Consts& k) {
+  memset(&k, 0, sizeof(k));
+  k.dim = c.dim; k.solver = c.solver; k.kernel = c.kernel; k.eos = c.eos; k.flags = c.flags;
+  k.eps = 1.1920928955078125e-07f;
+  const double ooh = 1.0 / c.h;
+  double sigma;
+  if (c.kernel == SPHB200_KERNEL_QSK)
+    sigma = c.dim == 2 ? 7.0 / 478.0 / M_PI * ooh * ooh : 3.0 / 359.0 / M_PI * ooh * ooh * ooh;
+  else
+    sigma = c.dim == 2 ? 7.0 / 4.0 / M_PI * ooh * ooh : 21.0 / 16.0 / M_PI * ooh * ooh * ooh;
+  k.ooh = (float)ooh;
+  k.sigma = (float)sigma;
+  k.sigma_ooh = k.sigma * k.ooh;
+  k.dt_s = (float)c.dt;
+  k.p_ref = (float)c.p_ref; k.rho_ref = (float)c.rho_ref; k.p_bg = (float)c.p_bg;
+  k.gamma = (float)c.gamma;
+  k.inv_gamma = (float)(1.0 / c.gamma);
+  k.c100 = (float)(100.0 * c.u_ref * c.u_ref);
+  if (c.eos == SPHB200_EOS_TAIT) {
+    // p_fn(0) = p_ref * ((0/rho_ref)^gamma - 1) + p_bg in float32
+    k.p_bg_tvf = k.p_ref * (0.0f - 1.0f) + k.p_bg;
+  } else {
+    k.p_bg_tvf = k.c100 * (0.0f - k.rho_ref) + k.p_bg;
+  }
+  k.c_ref = (float)c.c_ref;
+  k.use_lim = !(c.eta_limiter == -1.0);
+  k.eta_lim = (float)c.eta_limiter;
+  k.av_coef = (float)(c.artificial_alpha * c.dx * 10.0);  // h_ab = dx, c_ab = 10 * 1.0
+  k.av_eps = (float)(0.01 * c.dx * c.dx);
+  k.g_mode = c.g_mode; k.g_axis = c.g_axis;
+  for (int a = 0; a < 3; ++a) k.g[a] = (float)c.g[a];
+  k.g_lo = (float)c.g_lo; k.g_hi = (float)c.g_hi;
+  for (int t = 0; t < 4; ++t) k.bc[t] = c.bc[t];
+  k.inflow_on = c.bc_inflow_on; k.inflow_x = c.bc_inflow_x; k.inflow_T = c.bc_inflow_T;
+  k.outflow_on = c.bc_outflow_on; k.outflow_x = c.bc_outflow_x;
+  k.any_walls = 1;
+}
+
+bool bc_table_on(const sphb200_config& c) {
+  for (int t = 0; t < 4; ++t)
+    if (c.bc[t].flags) return true;
+  return c.bc_inflow_on || c.bc_outflow_on;
+}
+
+struct Layout {
+  size_t frame[2][12];
+  size_t key, rnk, src, count, start, bsum, maxocc, wallcount, err, stats, nl_counts, ut;
+  size_t total;
+};
+
+void feature_flags(const sphb200_config& c, bool& kc, bool& nw, bool& ut, bool& ge) {
+  kc = (c.flags & SPHB200_F_HEAT) != 0;
+  nw = (c.solver == SPHB200_SOLVER_RIE) || (c.flags & SPHB200_F_FREE_SLIP);
+  ut = (c.solver == SPHB200_SOLVER_RIE) && (c.flags & SPHB200_F_BC_TRICK) &&
+       !(c.flags & SPHB200_F_FREE_SLIP);
+  ge = c.g_mode == SPHB200_G_ARRAY;
+}
+
+void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, Layout& L) {
+  bool kc, nw, ut, ge;
+  feature_flags(c, kc, nw, ut, ge);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += up(bytes);
+    return o;
+  };
+  for (int f = 0; f < 2; ++f) {
+    for (int q = 0; q < 6; ++q) L.frame[f][q] = take((size_t)n * 16);  // pt um vv st du dv
+    L.frame[f][6] = take((size_t)n * 4);                              // id
+    L.frame[f][7] = kc ? take((size_t)n * 8) : (size_t)-1;
+    L.frame[f][8] = nw ? take((size_t)n * 16) : (size_t)-1;
+    L.frame[f][9] = ge ? take((size_t)n * 16) : (size_t)-1;
+  }
+  L.ut = ut ? take((size_t)n * 16) : (size_t)-1;
+  L.key = take((size_t)n * 4);
+  L.rnk = take((size_t)n * 4);
+  L.src = take((size_t)n * 4);
+  L.nl_counts = take(((size_t)n + 1) * 4);
+  L.count = take((size_t)g.ncells * 4);
+  L.start = take(((size_t)g.ncells + 1) * 4);
+  size_t nb = ((size_t)(n > g.ncells ? n : g.ncells) + SCAN_TILE - 1) / SCAN_TILE + 1;
+  L.bsum = take(nb * 4);
+  L.maxocc = take(4);
+  L.wallcount = take(4);
+  L.err = take(4);
+  L.stats = take(16);
+  L.total = off;
+}
+
+SweepPlan plan_sweep(const sphb200_engine* e, int nq) {
+  const Grid& g = e->grid;
+  const sphb200_config& c = e->cfg;
+  double pop = 1.0;
+  for (int a = 0; a < c.dim; ++a) pop *= (c.box[a] / g.n[a]) / c.dx;
+  int rows = 1;
+  for (int a = 1; a < 3; ++a) rows *= (g.n[a] >= 2 * g.S[a] + 1) ? g.T[a] + 2 * g.S[a] : g.n[a];
+  int nxs = (g.n[0] >= 2 * g.S[0] + 1) ? g.T[0] + 2 * g.S[0] : g.n[0];
+  long long want = (long long)(rows * (double)nxs * pop * 1.3) + 64;
+  if (c.stage_cap > 0) want = c.stage_cap;
+  if (want > e->n + 32) want = e->n + 32;  // never more than (a few images of) everything
+  size_t fixed = sweep_smem_bytes(nq, 0, e->lcap, e->tpb);
+  long long fit = ((long long)e->max_smem - (long long)fixed) / (16LL * nq);
+  if (want > fit) want = fit;
+  if (want > 65535) want = 65535;
+  want = want / 32 * 32;
+  if (want < 32) want = 32;
+  SweepPlan p;
+  p.nq = nq;
+  p.cap = (int)want;
+  p.smem = sweep_smem_bytes(nq, p.cap, e->lcap, e->tpb);
+  return p;
+}
+
+template <class K>
+int launch_sweep(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f, const Extra& ex,
+                 cudaStream_t st) {
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
+  SweepDims sd{sp.cap, e->lcap, ex.nq};
+  const int blocks = e->grid.nt[0] * e->grid.nt[1] * e->grid.nt[2];
+  kern<<<blocks, e->tpb, sp.smem, st>>>(e->grid, e->consts, f, e->start, sd, ex, e->err);
+  e->launches++;
+  CK(cudaGetLastError());
+  return SPHB200_OK;
+}
+
+Extra make_extra() {
+  Extra ex;
+  memset(&ex, 0, sizeof(ex));
+  ex.q_v = ex.q_h = ex.q_nw = ex.q_ut = -1;
+  ex.nq = 1;
+  return ex;
+}
+
+#define DISPATCH_DK(e, CALL)                                                   \
+  do {                                                                         \
+    if ((e)->dim == 2) {                                                       \
+      if ((e)->cfg.kernel == SPHB200_KERNEL_QSK) { CALL(2, SPHB200_KERNEL_QSK); } \
+      else { CALL(2, SPHB200_KERNEL_WC2K); }                                   \
+    } else {                                                                   \
+      if ((e)->cfg.kernel == SPHB200_KERNEL_QSK) { CALL(3, SPHB200_KERNEL_QSK); } \
+      else { CALL(3, SPHB200_KERNEL_WC2K); }                                   \
+    }                                                                          \
+  } while (0)
+
+void swap_st(sphb200_engine* e) {
+  float4* t = e->fr[0].st;
+  e->fr[0].st = e->fr[1].st;
+  e->fr[1].st = t;
+}
+
+int build_cells(sphb200_engine* e, const Kick& k, cudaStream_t st) {
+  const int n = e->n;
+  const int nb = (n + 255) / 256;
+  Frame& A = e->fr[e->cur];
+  Frame& B = e->fr[1 - e->cur];
+  if (e->dim == 2)
+    k_hash<2><<<nb, 256, 0, st>>>(n, e->grid, k, A.pt, A.um, A.du, A.dv, e->key, e->rnk, e->count, e->err);
+  else
+    k_hash<3><<<nb, 256, 0, st>>>(n, e->grid, k, A.pt, A.um, A.du, A.dv, e->key, e->rnk, e->count, e->err);
+  const int c = e->grid.ncells;
+  const int sb = (c + SCAN_TILE) / SCAN_TILE;  // covers index c itself (start[c] = n)
+  k_scan_partial<<<sb, SCAN_TPB, 0, st>>>(c, e->count, e->bsum);
+  k_scan_bsum<<<1, 1024, 0, st>>>(sb, e->bsum);
+  k_scan_final<<<sb, SCAN_TPB, 0, st>>>(c, n, e->count, e->bsum, e->start, e->maxocc);
+  k_scatter_src<<<nb, 256, 0, st>>>(n, e->key, e->rnk, e->start, e->src);
+  ReorderOpt o{e->has_kc ? 1 : 0, e->has_nw ? 1 : 0, e->has_ge ? 1 : 0};
+  if (e->dim == 2)
+    k_reorder<2><<<nb, 256, 0, st>>>(n, e->grid, k, o, A, B, e->key, e->start, e->src);
+  else
+    k_reorder<3><<<nb, 256, 0, st>>>(n, e->grid, k, o, A, B, e->key, e->start, e->src);
+  e->launches += 6;
+  CK(cudaGetLastError());
+  e->cur ^= 1;
+  e->cells_valid = true;
+  return SPHB200_OK;
+}
+
+int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st) {
+  const sphb200_config& c = e->cfg;
+  const bool bc_trick = c.flags & SPHB200_F_BC_TRICK, evol = c.flags & SPHB200_F_RHO_EVOL,
+             renorm = c.flags & SPHB200_F_RHO_RENORM, free_slip = c.flags & SPHB200_F_FREE_SLIP,
+             heat = c.flags & SPHB200_F_HEAT;
+  const bool rie = c.solver == SPHB200_SOLVER_RIE;
+  const bool wall_sweep = bc_trick && !rie;
+  int rc;
+  // ---- density -------------------------------------------------------------
+  {
+    Extra ex = make_extra();
+    ex.utilde = e->has_ut;
+    ex.wallT = rie && bc_trick && heat;
+    ex.finalT = heat && !wall_sweep;
+    ex.heat = heat;
+    Frame& F = e->fr[e->cur];
+    ex.st_out = e->fr[1 - e->cur].st;
+    const bool extras = ex.utilde || ex.wallT;
+    if (!evol) {
+      SweepPlan sp = extras ? e->planW : e->planA;  // 3 quads fit in the 4-quad plan
+      ex.nq = extras ? 3 : 1;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_SUM>>, sp, F, ex, st)
+      DISPATCH_DK(e, CALL);
+#undef CALL
+    } else if (!rie) {
+      SweepPlan sp = e->planR;
+      ex.nq = 2;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_EVOL_SPH>>, sp, F, ex, st)
+      DISPATCH_DK(e, CALL);
+#undef CALL
+    } else {
+      SweepPlan sp = e->planW;
+      ex.nq = 4;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_EVOL_RIE>>, sp, F, ex, st)
+      DISPATCH_DK(e, CALL);
+#undef CALL
+    }
+    if (rc) return rc;
+    swap_st(e);
+  }
+  if (e->profile) cudaEventRecord(e->ev[3], st);
+  if (evol && renorm) {
+    Extra ex = make_extra();
+    ex.nq = 2;
+    Frame& F = e->fr[e->cur];
+    ex.st_out = e->fr[1 - e->cur].st;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysRenorm<D, K>>, e->planR, F, ex, st)
+    DISPATCH_DK(e, CALL);
+#undef CALL
+    if (rc) return rc;
+    swap_st(e);
+  }
+  // ---- generalized wall boundary condition ---------------------------------
+  if (wall_sweep) {
+    Extra ex = make_extra();
+    ex.nq = 4;
+    ex.heat = heat;
+    ex.free_slip = free_slip;
+    Frame& F = e->fr[e->cur];
+    ex.st_out = e->fr[1 - e->cur].st;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysWall<D, K>>, e->planW, F, ex, st)
+    DISPATCH_DK(e, CALL);
+#undef CALL
+    if (rc) return rc;
+    swap_st(e);
+  }
+  if (e->profile) cudaEventRecord(e->ev[4], st);
+  // ---- force -----------------------------------------------------------------
+  {
+    Extra ex = make_extra();
+    int nq = 3;
+    if (!rie && !v_is_u) ex.q_v = nq++;
+    if (heat) ex.q_h = nq++;
+    if (rie) {
+      ex.q_nw = nq++;
+      if (e->has_ut) ex.q_ut = nq++;
+    }
+    ex.nq = nq;
+    ex.heat = heat;
+    ex.av = c.artificial_alpha != 0.0;
+    ex.bc_on = (flags & SPHB200_STEP_BC) && bc_table_on(c);
+    ex.free_slip = free_slip;
+    ex.bc_trick = bc_trick;
+    SweepPlan sp = plan_sweep(e, nq);
+    Frame& F = e->fr[e->cur];
+    if (!rie) {
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH>>, sp, F, ex, st)
+      DISPATCH_DK(e, CALL);
+#undef CALL
+    } else {
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_RIE>>, sp, F, ex, st)
+      DISPATCH_DK(e, CALL);
+#undef CALL
+    }
+    if (rc) return rc;
+    if (ex.bc_on) {
+      const int nb = (e->n + 255) / 256;
+      if (e->dim == 2) k_bc<2><<<nb, 256, 0, st>>>(e->n, e->consts, F);
+      else k_bc<3><<<nb, 256, 0, st>>>(e->n, e->consts, F);
+      e->launches++;
+      CK(cudaGetLastError());
+    }
+  }
+  return SPHB200_OK;
+}
+
+__global__ void k_fill(int* a, long long n, int v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+
+// exclusive scan of counts[0..n) (original order) using the cell-scan kernels;
+// total edge count -> *count64, overflow -> err
+__global__ void k_nl_total(int n, const int* offs_last, const int* counts, long long capacity,
+                           long long* count64, unsigned* err) {
+  long long tot = (long long)(unsigned)offs_last[n - 1] + counts[n - 1];
+  if (count64) *count64 = tot;
+  if (tot > capacity) atomicOr(err, SPHB200_ERR_NEIGHBOR_OVERFLOW);
+}
+
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_final_keep(int c, const int* __restrict__ count,
+                                                              const int* __restrict__ bsum,
+                                                              int* __restrict__ start) {
+  __shared__ int sh[32];
+  int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    v[i] = (base + i < c) ? count[base + i] : 0;
+    s += v[i];
+  }
+  int tot;
+  int inc = block_incl_scan(s, sh, &tot);
+  int run = bsum[blockIdx.x] + inc - s;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < c) start[base + i] = run;
+    run += v[i];
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_stats(int n, Frame f, double* out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double ek = 0.0;
+  float um = 0.f;
+  if (p < n) {
+    float4 u = f.um[p];
+    float s = u.x * u.x + u.y * u.y + (DIM == 3 ? u.z * u.z : 0.f);
+    ek = 0.5 * (double)u.w * (double)s;
+    um = sqrtf(s);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ek += __shfl_xor_sync(FULL_MASK, ek, o);
+    um = fmaxf(um, __shfl_xor_sync(FULL_MASK, um, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&out[0], ek);
+    atomicMax(reinterpret_cast<unsigned long long*>(&out[1]),
+              (unsigned long long)__double_as_longlong((double)um));
+  }
+}
+
+int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* ws, size_t ws_bytes,
+                bool own) {
+  e->cfg = *cfg;
+  e->n = (int)n;
+  e->dim = cfg->dim;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  int maxs = 0;
+  CK(cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  e->max_smem = maxs - 1024;
+  e->tpb = cfg->threads > 0 ? (cfg->threads + 31) / 32 * 32 : 128;
+  if (e->tpb > 256) e->tpb = 256;
+  e->lcap = cfg->list_cap > 0 ? cfg->list_cap : 96;
+  if (e->lcap < SWEEP_CHUNK) e->lcap = SWEEP_CHUNK;
+  plan_grid(*cfg, e->grid, e->tpb);
+  plan_consts(*cfg, e->consts);
+  feature_flags(*cfg, e->has_kc, e->has_nw, e->has_ut, e->has_ge);
+  Layout L;
+  plan_layout(*cfg, n, e->grid, L);
+  if (ws_bytes < L.total) return SPHB200_ENOMEM;
+  e->arena = (char*)ws;
+  e->arena_bytes = L.total;
+  e->own_arena = own;
+  for (int f = 0; f < 2; ++f) {
+    Frame& F = e->fr[f];
+    memset(&F, 0, sizeof(F));
+    F.pt = (float4*)(e->arena + L.frame[f][0]);
+    F.um = (float4*)(e->arena + L.frame[f][1]);
+    F.vv = (float4*)(e->arena + L.frame[f][2]);
+    F.st = (float4*)(e->arena + L.frame[f][3]);
+    F.du = (float4*)(e->arena + L.frame[f][4]);
+    F.dv = (float4*)(e->arena + L.frame[f][5]);
+    F.id = (int*)(e->arena + L.frame[f][6]);
+    F.kc = e->has_kc ? (float2*)(e->arena + L.frame[f][7]) : nullptr;
+    F.nw = e->has_nw ? (float4*)(e->arena + L.frame[f][8]) : nullptr;
+    F.ge = e->has_ge ? (float4*)(e->arena + L.frame[f][9]) : nullptr;
+    F.ut = e->has_ut ? (float4*)(e->arena + L.ut) : nullptr;
+  }
+  e->key = (int*)(e->arena + L.key);
+  e->rnk = (int*)(e->arena + L.rnk);
+  e->src = (int*)(e->arena + L.src);
+  e->nl_counts = (int*)(e->arena + L.nl_counts);
+  e->count = (int*)(e->arena + L.count);
+  e->start = (int*)(e->arena + L.start);
+  e->bsum = (int*)(e->arena + L.bsum);
+  e->maxocc = (int*)(e->arena + L.maxocc);
+  e->wallcount = (int*)(e->arena + L.wallcount);
+  e->err = (unsigned*)(e->arena + L.err);
+  e->stats = (double*)(e->arena + L.stats);
+  e->cur = 0;
+  e->cells_valid = false;
+  e->launches = 0;
+  e->profile = false;
+  e->hstage = nullptr;
+  e->hstage_bytes = 0;
+  memset(e->times, 0, sizeof(e->times));
+  e->planA = plan_sweep(e, 1);
+  e->planR = plan_sweep(e, 2);
+  e->planW = plan_sweep(e, 4);
+  e->planC = plan_sweep(e, 4);
+  e->planN = plan_sweep(e, 2);
+  e->needs_zero = true;  // control words are zeroed on the first upload's stream
+  return SPHB200_OK;
+}
+
+// device-side staging of a reference-layout state for host pointers
+struct HostStage {
+  sphb200_state dev;
+};
+
+size_t state_floats(int dim) { return (size_t)(7 * dim + 10); }
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int sphb200_abi_version(void) { return SPHB200_ABI_VERSION; }
+
+const char* sphb200_strerror(int code) {
+  switch (code) {
+    case SPHB200_OK: return "ok";
+    case SPHB200_EINVAL: return "invalid argument or inconsistent configuration";
+    case SPHB200_ENOMEM: return "out of device memory or workspace too small";
+    case SPHB200_ECUDA: return "CUDA runtime error";
+    case SPHB200_EDTYPE: return "unsupported dtype (float32 only)";
+    case SPHB200_EUNSUP: return "unsupported solver/kernel variant";
+    case SPHB200_ENODEV: return "no usable CUDA device";
+    default: return "unknown error";
+  }
+}
+
+void sphb200_config_default(sphb200_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->struct_size = sizeof(*c);
+  c->dim = 3;
+  c->solver = SPHB200_SOLVER_SPH;
+  c->kernel = SPHB200_KERNEL_QSK;
+  c->eos = SPHB200_EOS_TAIT;
+  c->box[0] = c->box[1] = c->box[2] = 1.0;
+  c->dx = 0.05; c->h = 0.05; c->dt = 0.0;
+  c->c_ref = 10.0; c->eta_limiter = 3.0;
+  c->p_ref = 100.0; c->rho_ref = 1.0; c->gamma = 1.0; c->u_ref = 1.0;
+}
+
+int sphb200_engine_bytes(const sphb200_config* cfg, int64_t n, size_t* bytes) {
+  int rc = validate(cfg, n);
+  if (rc) return rc;
+  if (!bytes) return SPHB200_EINVAL;
+  Grid g;
+  plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : 128);
+  Layout L;
+  plan_layout(*cfg, n, g, L);
+  *bytes = L.total;
+  return SPHB200_OK;
+}
+
+int sphb200_workspace_bytes(const sphb200_config* cfg, int64_t n, size_t* bytes) {
+  return sphb200_engine_bytes(cfg, n, bytes);
+}
+
+int sphb200_engine_create_in(const sphb200_config* cfg, int64_t n, void* ws, size_t ws_bytes,
+                             sphb200_engine** out) {
+  int rc = validate(cfg, n);
+  if (rc) return rc;
+  if (!ws || !out) return SPHB200_EINVAL;
+  sphb200_engine* e = new (std::nothrow) sphb200_engine();
+  if (!e) return SPHB200_ENOMEM;
+  rc = init_engine(e, cfg, n, ws, ws_bytes, false);
+  if (rc) {
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return SPHB200_OK;
+}
+
+int sphb200_engine_create(const sphb200_config* cfg, int64_t n, sphb200_engine** out) {
+  int rc = validate(cfg, n);
+  if (rc) return rc;
+  if (!out) return SPHB200_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SPHB200_ENODEV;
+  size_t bytes = 0;
+  rc = sphb200_engine_bytes(cfg, n, &bytes);
+  if (rc) return rc;
+  void* ws = nullptr;
+  if (cudaMalloc(&ws, bytes) != cudaSuccess) return SPHB200_ENOMEM;
+  sphb200_engine* e = new (std::nothrow) sphb200_engine();
+  if (!e) {
+    cudaFree(ws);
+    return SPHB200_ENOMEM;
+  }
+  rc = init_engine(e, cfg, n, ws, bytes, true);
+  if (rc) {
+    cudaFree(ws);
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return SPHB200_OK;
+}
+
+int sphb200_engine_destroy(sphb200_engine* e) {
+  if (!e) return SPHB200_EINVAL;
+  if (e->profile)
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(e->ev[i]);
+  if (e->hstage) cudaFree(e->hstage);
+  if (e->own_arena) cudaFree(e->arena);
+  delete e;
+  return SPHB200_OK;
+}
+
+static int ensure_hstage(sphb200_engine* e) {
+  size_t need = up((size_t)e->n * 4) * state_floats(e->dim);
+  if (e->hstage && e->hstage_bytes >= need) return SPHB200_OK;
+  if (e->hstage) cudaFree(e->hstage);
+  e->hstage = nullptr;
+  if (cudaMalloc((void**)&e->hstage, need) != cudaSuccess) return SPHB200_ENOMEM;
+  e->hstage_bytes = need;
+  return SPHB200_OK;
+}
+
+int sphb200_engine_upload(sphb200_engine* e, const sphb200_state* s, int on_host, void* stream) {
+  if (!e || !s || !s->r) return SPHB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = e->n, d = e->dim;
+  sphb200_state dv = *s;
+  if (on_host) {
+    int rc = ensure_hstage(e);
+    if (rc) return rc;
+    char* base = e->hstage;
+    size_t off = 0;
+    auto stage = [&](const void* h, size_t words) -> void* {
+      if (!h) return nullptr;
+      void* dptr = base + off;
+      off += up(words * 4) ;
+      cudaMemcpyAsync(dptr, h, words * 4, cudaMemcpyHostToDevice, st);
+      return dptr;
+    };
+    const size_t nv = (size_t)n * d, ns = (size_t)n;
+    dv.r = (float*)stage(s->r, nv); dv.u = (float*)stage(s->u, nv); dv.v = (float*)stage(s->v, nv);
+    dv.dudt = (float*)stage(s->dudt, nv); dv.dvdt = (float*)stage(s->dvdt, nv);
+    dv.nw = e->has_nw ? (float*)stage(s->nw, nv) : nullptr;
+    dv.rho = (float*)stage(s->rho, ns); dv.p = (float*)stage(s->p, ns);
+    dv.drhodt = (float*)stage(s->drhodt, ns); dv.mass = (float*)stage(s->mass, ns);
+    dv.eta = (float*)stage(s->eta, ns); dv.T = (float*)stage(s->T, ns);
+    dv.dTdt = (float*)stage(s->dTdt, ns);
+    dv.kappa = e->has_kc ? (float*)stage(s->kappa, ns) : nullptr;
+    dv.Cp = e->has_kc ? (float*)stage(s->Cp, ns) : nullptr;
+    dv.tag = (int32_t*)stage(s->tag, ns);
+    dv.g_ext = e->has_ge ? (float*)stage(s->g_ext, nv) : nullptr;
+    CK(cudaGetLastError());
+  }
+  StatePtrs sp{dv.r, dv.u, dv.v, dv.dudt, dv.dvdt, dv.nw, dv.rho, dv.p, dv.drhodt, dv.mass,
+               dv.eta, dv.T, dv.dTdt, dv.kappa, dv.Cp, dv.g_ext, dv.tag};
+  if (e->has_ge && !dv.g_ext) return SPHB200_EINVAL;
+  e->cur = 0;
+  e->cells_valid = false;
+  if (e->needs_zero) {
+    CK(cudaMemsetAsync(e->count, 0, (size_t)e->grid.ncells * 4, st));
+    CK(cudaMemsetAsync(e->maxocc, 0, 4, st));
+    CK(cudaMemsetAsync(e->err, 0, 4, st));
+    e->needs_zero = false;
+  }
+  CK(cudaMemsetAsync(e->wallcount, 0, 4, st));
+  const int nb = (n + 255) / 256;
+  if (d == 2) k_pack<2><<<nb, 256, 0, st>>>(n, sp, e->fr[0], e->wallcount);
+  else k_pack<3><<<nb, 256, 0, st>>>(n, sp, e->fr[0], e->wallcount);
+  e->launches++;
+  CK(cudaGetLastError());
+  return SPHB200_OK;
+}
+
+int sphb200_engine_download(sphb200_engine* e, sphb200_state* out, int on_host, void* stream) {
+  if (!e || !out) return SPHB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = e->n, d = e->dim;
+  sphb200_state dv = *out;
+  struct Back { void* h; void* dptr; size_t bytes; } back[16];
+  int nback = 0;
+  if (on_host) {
+    int rc = ensure_hstage(e);
+    if (rc) return rc;
+    char* base = e->hstage;
+    size_t off = 0;
+    auto stage = [&](void* h, size_t words) -> void* {
+      if (!h) return nullptr;
+      void* dptr = base + off;
+      off += up(words * 4);
+      back[nback++] = Back{h, dptr, words * 4};
+      return dptr;
+    };
+    const size_t nv = (size_t)n * d, ns = (size_t)n;
+    dv.r = (float*)stage(out->r, nv); dv.u = (float*)stage(out->u, nv); dv.v = (float*)stage(out->v, nv);
+    dv.dudt = (float*)stage(out->dudt, nv); dv.dvdt = (float*)stage(out->dvdt, nv);
+    dv.nw = e->has_nw ? (float*)stage(out->nw, nv) : nullptr;
+    dv.rho = (float*)stage(out->rho, ns); dv.p = (float*)stage(out->p, ns);
+    dv.drhodt = (float*)stage(out->drhodt, ns); dv.mass = (float*)stage(out->mass, ns);
+    dv.eta = (float*)stage(out->eta, ns); dv.T = (float*)stage(out->T, ns);
+    dv.dTdt = (float*)stage(out->dTdt, ns);
+    dv.kappa = e->has_kc ? (float*)stage(out->kappa, ns) : nullptr;
+    dv.Cp = e->has_kc ? (float*)stage(out->Cp, ns) : nullptr;
+    dv.tag = (int32_t*)stage(out->tag, ns);
+  }
+  StateOut so{dv.r, dv.u, dv.v, dv.dudt, dv.dvdt, dv.nw, dv.rho, dv.p, dv.drhodt, dv.mass,
+              dv.eta, dv.T, dv.dTdt, dv.kappa, dv.Cp, dv.tag};
+  const int nb = (n + 255) / 256;
+  if (d == 2) k_unpack<2><<<nb, 256, 0, st>>>(n, e->fr[e->cur], so);
+  else k_unpack<3><<<nb, 256, 0, st>>>(n, e->fr[e->cur], so);
+  e->launches++;
+  CK(cudaGetLastError());
+  for (int i = 0; i < nback; ++i)
+    CK(cudaMemcpyAsync(back[i].h, back[i].dptr, back[i].bytes, cudaMemcpyDeviceToHost, st));
+  return SPHB200_OK;
+}
+
+int sphb200_engine_step(sphb200_engine* e, double dt, int nsteps, uint32_t flags, void* stream) {
+  if (!e || nsteps < 0) return SPHB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  Kick k;
+  k.dt = (float)dt;
+  k.c2 = (float)(e->cfg.tvf * 0.5) * (float)dt;
+  k.on = (flags & SPHB200_STEP_INTEGRATE) ? 1 : 0;
+  const bool v_is_u = k.on && e->cfg.tvf == 0.0;
+  for (int s = 0; s < nsteps; ++s) {
+    if (e->profile) cudaEventRecord(e->ev[0], st);
+    int rc = build_cells(e, k, st);
+    if (rc) return rc;
+    if (e->profile) cudaEventRecord(e->ev[2], st);
+    rc = run_forward(e, flags, v_is_u, st);
+    if (rc) return rc;
+    if (e->profile) cudaEventRecord(e->ev[5], st);
+  }
+  return SPHB200_OK;
+}
+
+int sphb200_engine_error(sphb200_engine* e, uint32_t* code, void* stream) {
+  if (!e || !code) return SPHB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned h = 0;
+  CK(cudaMemcpyAsync(&h, e->err, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemsetAsync(e->err, 0, 4, st));
+  CK(cudaStreamSynchronize(st));
+  *code = h;
+  return SPHB200_OK;
+}
+
+int sphb200_engine_neighbor_list(sphb200_engine* e, int32_t* idx, int64_t capacity, int mask_self,
+                                 int64_t* count, void* stream) {
+  if (!e || !idx || capacity < 0 || capacity >= 2147483647LL) return SPHB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!e->cells_valid) {
+    Kick k{0.f, 0.f, 0};
+    int rc = build_cells(e, k, st);
+    if (rc) return rc;
+  }
+  const int n = e->n;
+  int rc = 0;
+  Frame& F = e->fr[e->cur];
+  Extra ex = make_extra();
+  ex.nq = 2;
+  ex.nl_counts = e->nl_counts;
+  ex.nl_mask_self = mask_self;
+  ex.nl_n = n;
+  ex.nl_idx = idx;
+  ex.nl_capacity = capacity;
+  ex.nl_fill = 0;
+  if (e->dim == 2) rc = launch_sweep(e, k_sweep<2, PhysNeighbors<2>>, e->planN, F, ex, st);
+  else rc = launch_sweep(e, k_sweep<3, PhysNeighbors<3>>, e->planN, F, ex, st);
+  if (rc) return rc;
+  // exclusive scan of the per-sender counts (original order) -> offsets (reuse rnk as scratch)
+  const int sb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  k_scan_partial<<<sb, SCAN_TPB, 0, st>>>(n, e->nl_counts, e->bsum);
+  k_scan_bsum<<<1, 1024, 0, st>>>(sb, e->bsum);
+  k_scan_final_keep<<<sb, SCAN_TPB, 0, st>>>(n, e->nl_counts, e->bsum, e->rnk);
+  k_nl_total<<<1, 1, 0, st>>>(n, e->rnk, e->nl_counts, capacity, (long long*)count, e->err);
+  const long long tot = 2 * capacity;
+  if (tot > 0) k_fill<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(idx, tot, n);
+  e->launches += 5;
+  ex.nl_fill = 1;
+  ex.nl_offsets = e->rnk;
+  if (e->dim == 2) rc = launch_sweep(e, k_sweep<2, PhysNeighbors<2>>, e->planN, F, ex, st);
+  else rc = launch_sweep(e, k_sweep<3, PhysNeighbors<3>>, e->planN, F, ex, st);
+  CK(cudaGetLastError());
+  return rc;
+}
+
+int sphb200_engine_stats(sphb200_engine* e, double* ekin, double* u_max, void* stream) {
+  if (!e) return SPHB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(e->stats, 0, 16, st));
+  const int nb = (e->n + 255) / 256;
+  if (e->dim == 2) k_stats<2><<<nb, 256, 0, st>>>(e->n, e->fr[e->cur], e->stats);
+  else k_stats<3><<<nb, 256, 0, st>>>(e->n, e->fr[e->cur], e->stats);
+  e->launches++;
+  double h[2];
+  CK(cudaMemcpyAsync(h, e->stats, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (ekin) *ekin = h[0];
+  if (u_max) *u_max = h[1];
+  return SPHB200_OK;
+}
+
+int64_t sphb200_engine_launches(const sphb200_engine* e) { return e ? e->launches : -1; }
+
+int sphb200_engine_profile(sphb200_engine* e, int enable) {
+  if (!e) return SPHB200_EINVAL;
+  if (enable && !e->profile) {
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&e->ev[i]));
+    e->profile = true;
+  } else if (!enable && e->profile) {
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(e->ev[i]);
+    e->profile = false;
+  }
+  return SPHB200_OK;
+}
+
+int sphb200_engine_last_times(sphb200_engine* e, float ms[8]) {
+  if (!e || !ms || !e->profile) return SPHB200_EINVAL;
+  CK(cudaEventSynchronize(e->ev[5]));
+  memset(ms, 0, 8 * sizeof(float));
+  // ev0 start, ev2 cells done, ev3 density done, ev4 wall done, ev5 force done
+  CK(cudaEventElapsedTime(&ms[1], e->ev[0], e->ev[2]));
+  CK(cudaEventElapsedTime(&ms[2], e->ev[2], e->ev[3]));
+  CK(cudaEventElapsedTime(&ms[3], e->ev[3], e->ev[4]));
+  CK(cudaEventElapsedTime(&ms[4], e->ev[4], e->ev[5]));
+  CK(cudaEventElapsedTime(&ms[5], e->ev[0], e->ev[5]));
+  return SPHB200_OK;
+}
+
+int sphb200_engine_plan(const sphb200_engine* e, int32_t out[16]) {
+  if (!e || !out) return SPHB200_EINVAL;
+  for (int a = 0; a < 3; ++a) {
+    out[a] = e->grid.n[a];
+    out[3 + a] = e->grid.S[a];
+    out[6 + a] = e->grid.T[a];
+  }
+  out[9] = e->tpb;
+  out[10] = e->lcap;
+  out[11] = e->planA.cap;
+  out[12] = e->planW.cap;
+  out[13] = e->planC.cap;
+  out[14] = e->grid.exact_all;
+  out[15] = e->grid.ncells;
+  return SPHB200_OK;
+}
+
+// ---- stateless entry points -------------------------------------------------
+static int with_engine(const sphb200_config* cfg, int64_t n, void* ws, size_t ws_bytes,
+                       sphb200_engine** e) {
+  return sphb200_engine_create_in(cfg, n, ws, ws_bytes, e);
+}
+
+int sphb200_neighbor_list(const sphb200_config* cfg, int64_t n, const float* r, int32_t* idx,
+                          int64_t capacity, int mask_self, int64_t* count, uint32_t* err,
+                          void* ws, size_t ws_bytes, void* stream) {
+  if (!r) return SPHB200_EINVAL;
+  sphb200_engine* e = nullptr;
+  int rc = with_engine(cfg, n, ws, ws_bytes, &e);
+  if (rc) return rc;
+  sphb200_state s;
+  memset(&s, 0, sizeof(s));
+  s.r = const_cast<float*>(r);
+  rc = sphb200_engine_upload(e, &s, 0, stream);
+  if (!rc) rc = sphb200_engine_neighbor_list(e, idx, capacity, mask_self, count, stream);
+  if (!rc && err)
+    rc = cudaMemcpyAsync(err, e->err, 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) == cudaSuccess
+             ? SPHB200_OK : SPHB200_ECUDA;
+  sphb200_engine_destroy(e);
+  return rc;
+}
+
+static int stateless_step(const sphb200_config* cfg, int64_t n, double dt, uint32_t flags,
+                          const sphb200_state* in, sphb200_state* out, uint32_t* err, void* ws,
+                          size_t ws_bytes, void* stream) {
+  if (!in || !out) return SPHB200_EINVAL;
+  sphb200_engine* e = nullptr;
+  int rc = with_engine(cfg, n, ws, ws_bytes, &e);
+  if (rc) return rc;
+  rc = sphb200_engine_upload(e, in, 0, stream);
+  if (!rc) rc = sphb200_engine_step(e, dt, 1, flags, stream);
+  if (!rc) rc = sphb200_engine_download(e, out, 0, stream);
+  if (!rc && err)
+    rc = cudaMemcpyAsync(err, e->err, 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) == cudaSuccess
+             ? SPHB200_OK : SPHB200_ECUDA;
+  sphb200_engine_destroy(e);
+  return rc;
+}
+
+int sphb200_forward(const sphb200_config* cfg, int64_t n, const sphb200_state* in,
+                    sphb200_state* out, uint32_t* err, void* ws, size_t ws_bytes, void* stream) {
+  return stateless_step(cfg, n, 0.0, 0u, in, out, err, ws, ws_bytes, stream);
+}
+
+int sphb200_advance(const sphb200_config* cfg, int64_t n, double dt, const sphb200_state* in,
+                    sphb200_state* out, uint32_t* err, void* ws, size_t ws_bytes, void* stream) {
+  return stateless_step(cfg, n, dt, SPHB200_STEP_INTEGRATE | SPHB200_STEP_BC, in, out, err, ws,
+                        ws_bytes, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,542 @@
+// phys.cuh -- pair physics policies for k_sweep (see sweep.cuh).
+//
+// Each policy restates, for ONE receiver particle i and ONE neighbour j, the
+// per-edge expressions of the reference and what its segment_sum accumulates;
+// finish() is the per-particle epilogue.  Citations: jax_sph/solver.py.
+//
+//   PhysDensity   :750-802  density summation / continuity (SPH) / Riemann continuity,
+//                           EoS; RIE wall helpers u_tilde (:547-552) and heat_bc (:556-565)
+//   PhysRenorm    :167-173  Shepard density renormalisation
+//   PhysWall      :450-528  generalized wall boundary condition (SPH)
+//   PhysForce     :221-256 standard acceleration, :199-213 TVF, :316-401 Riemann,
+//                 :404-428 artificial viscosity, :591-610 heat conduction,
+//                 integrator.py:54 case bc_fn (table form, dudt/dvdt/dTdt part)
+//   PhysNeighbors jax_md/partition.py:885-909  sparse list materialiser (parity / drop-in .idx)
+#pragma once
+#include "common.cuh"
+
+namespace sphb200 {
+
+
+__device__ __forceinline__ float dot3(const float (&a)[3], const float (&b)[3], int dim) {
+  float s = a[0] * b[0] + a[1] * b[1];
+  if (dim == 3) s += a[2] * b[2];
+  return s;
+}
+
+// ---------------------------------------------------------------------------
+enum { DENS_SUM = 0, DENS_EVOL_SPH = 1, DENS_EVOL_RIE = 2 };
+
+template <int DIM, int KERN, int MODE>
+struct PhysDensity {
+  static constexpr int NQ = 4;
+  static constexpr bool SENDER_VIEW = false;
+  struct Own {
+    float u[3], g[3];
+    float rho, p, T, dTdt, mass;
+    int tag;
+  };
+  struct Acc {
+    float s;            // sum w  |  continuity sum
+    float swf, sT;      // RIE wall helpers
+    float su[3];
+  };
+  __device__ static void load_stage(const Consts& c, const Frame& f, const Extra& ex, int gp,
+                                    float4 (&q)[NQ]) {
+    q[0] = f.pt[gp];
+    if (MODE == DENS_SUM) {
+      if (ex.nq > 1) {
+        q[1] = f.um[gp];
+        q[2] = f.st[gp];
+      }
+    } else if (MODE == DENS_EVOL_SPH) {
+      float4 um = f.um[gp], st = f.st[gp];
+      q[1] = make_float4(um.x, um.y, um.z, um.w / st.x);  // (mass / rho)[j], solver.py:26
+    } else {
+      q[1] = f.um[gp];
+      q[2] = f.st[gp];
+      q[3] = f.nw ? f.nw[gp] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __device__ static void load_own(const Consts& c, const Frame& f, const Extra& ex, int p,
+                                  float4 pt, Own& o) {
+    float4 um = f.um[p], st = f.st[p];
+    o.u[0] = um.x; o.u[1] = um.y; o.u[2] = um.z;
+    o.mass = um.w;
+    o.rho = st.x; o.p = st.y; o.T = st.z; o.dTdt = st.w;
+    o.tag = __float_as_int(pt.w);
+    if (MODE == DENS_EVOL_RIE) {
+      float r[3] = {pt.x, pt.y, pt.z};
+      g_ext_of<DIM>(c, f, p, r, o.g);
+    }
+  }
+  __device__ static bool active(const Consts&, const Own&) { return true; }
+  __device__ static void init(Acc& a) {
+    a.s = 0.f; a.swf = 0.f; a.sT = 0.f;
+    a.su[0] = a.su[1] = a.su[2] = 0.f;
+  }
+  __device__ static void pair(const Consts& c, const Extra& ex, const Own& o, Acc& a,
+                              const float4* sq, int cap, int j, float4 pj, const float (&dr)[3],
+                              float d2) {
+    const float dist = sqrtf(d2);
+    const int tag_j = __float_as_int(pj.w);
+    if (MODE == DENS_SUM || ex.utilde || ex.wallT) {
+      const float w = kernel_w<KERN>(c, dist);
+      if (MODE == DENS_SUM) a.s += w;
+      if (ex.utilde || ex.wallT) {
+        if (tag_j == SPHB200_TAG_FLUID) {
+          const float4 uj = sq[cap + j];
+          const float4 sj = sq[2 * cap + j];
+          a.swf += w;
+          a.su[0] += w * uj.x; a.su[1] += w * uj.y; a.su[2] += w * uj.z;
+          a.sT += w * sj.z;
+        }
+      }
+    }
+    if (MODE == DENS_EVOL_SPH) {
+      const float4 uj = sq[cap + j];
+      const float gw = kernel_gw<KERN>(c, dist);
+      const float den = dist + c.eps;
+      float s = (o.u[0] - uj.x) * (gw * (dr[0] / den)) + (o.u[1] - uj.y) * (gw * (dr[1] / den));
+      if (DIM == 3) s += (o.u[2] - uj.z) * (gw * (dr[2] / den));
+      a.s += uj.w * s;
+    }
+    if (MODE == DENS_EVOL_RIE) {
+      const float4 uj4 = sq[cap + j], sj = sq[2 * cap + j], nj4 = sq[3 * cap + j];
+      const float uj[3] = {uj4.x, uj4.y, uj4.z}, nwj[3] = {nj4.x, nj4.y, nj4.z};
+      const float gw = kernel_gw<KERN>(c, dist);
+      const float den = dist + c.eps;
+      float e[3] = {dr[0] / den, dr[1] / den, DIM == 3 ? dr[2] / den : 0.f};
+      float kg[3] = {gw * e[0], gw * e[1], gw * e[2]};
+      const bool is_w = is_wall_tag(tag_j);
+      float ne[3] = {-e[0], -e[1], -e[2]}, nn[3] = {-nwj[0], -nwj[1], -nwj[2]};
+      float ndr[3] = {-dr[0], -dr[1], -dr[2]};
+      const float u_L = is_w ? dot3(o.u, nn, DIM) : dot3(o.u, ne, DIM);
+      const float p_L = o.p, rho_L = o.rho;
+      const float u_R = is_w ? (-u_L + 2.0f * dot3(uj, nwj, DIM)) : dot3(uj, ne, DIM);
+      const float p_R = is_w ? (p_L + rho_L * dot3(o.g, ndr, DIM)) : sj.y;
+      const float rho_R = is_w ? eos_rho(c, p_R) : sj.x;
+      const float U_avg = (u_L + u_R) / 2.0f;
+      const float rho_avg = (rho_L + rho_R) / 2.0f;
+      const float U_star = U_avg + 0.5f * (p_L - p_R) / (rho_avg * c.c_ref);
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) {
+        const float v_avg = (o.u[k] + uj[k]) / 2.0f;
+        const float v_star = U_star * ne[k] + (v_avg - U_avg * ne[k]);
+        s += (o.u[k] - v_star) * kg[k];
+      }
+      a.s += 2.0f * o.rho * uj4.w / sj.x * s;
+    }
+  }
+  __device__ static void finish(const Consts& c, const Frame& f, const Extra& ex, int p,
+                                const Own& o, const Acc& a) {
+    float rho, drhodt = 0.f;
+    if (MODE == DENS_SUM) {
+      const float rho_ = o.mass * a.s;
+      rho = (o.tag == SPHB200_TAG_FLUID) ? rho_ : o.rho;  // solver.py:795-796
+    } else if (MODE == DENS_EVOL_SPH) {
+      drhodt = o.rho * a.s;           // :28
+      rho = o.rho + c.dt_s * drhodt;  // :29
+    } else {
+      drhodt = a.s * ((o.tag == SPHB200_TAG_FLUID) ? 1.0f : 0.0f);  // :789
+      rho = o.rho + c.dt_s * drhodt;                             // :790
+    }
+    const float pnew = eos_p(c, rho);  // :801
+    float T = o.T;
+    if (ex.wallT && (o.tag == SPHB200_TAG_SOLID_WALL || o.tag == SPHB200_TAG_MOVING_WALL))
+      T = a.sT / (a.swf + c.eps);  // :556-565
+    if (ex.finalT) T = T + c.dt_s * o.dTdt;  // :834
+    ex.st_out[p] = make_float4(rho, pnew, T, o.dTdt);
+    if (MODE != DENS_SUM) reinterpret_cast<float*>(&f.du[p])[3] = drhodt;
+    if (ex.utilde) {
+      const float den = a.swf + c.eps;  // :547-552
+      f.ut[p] = make_float4(a.su[0] / den, a.su[1] / den, a.su[2] / den, 0.f);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+template <int DIM, int KERN>
+struct PhysRenorm {
+  static constexpr int NQ = 2;
+  static constexpr bool SENDER_VIEW = false;
+  struct Own {
+    float4 st;
+  };
+  struct Acc {
+    float num, den;
+  };
+  __device__ static void load_stage(const Consts&, const Frame& f, const Extra&, int gp,
+                                    float4 (&q)[NQ]) {
+    q[0] = f.pt[gp];
+    const float m = f.um[gp].w, rho = f.st[gp].x;
+    q[1] = make_float4(m, m / rho, 0.f, 0.f);
+  }
+  __device__ static void load_own(const Consts&, const Frame& f, const Extra&, int p, float4,
+                                  Own& o) {
+    o.st = f.st[p];
+  }
+  __device__ static bool active(const Consts&, const Own&) { return true; }
+  __device__ static void init(Acc& a) { a.num = a.den = 0.f; }
+  __device__ static void pair(const Consts& c, const Extra&, const Own&, Acc& a, const float4* sq,
+                              int cap, int j, float4, const float (&)[3], float d2) {
+    const float w = kernel_w<KERN>(c, sqrtf(d2));
+    const float4 mj = sq[cap + j];
+    a.num += mj.x * w;
+    a.den += mj.y * w;
+  }
+  __device__ static void finish(const Consts& c, const Frame&, const Extra& ex, int p,
+                                const Own& o, const Acc& a) {
+    const float den = a.den > 1.0f ? 1.0f : a.den;
+    const float rho = a.num / den;
+    ex.st_out[p] = make_float4(rho, eos_p(c, rho), o.st.z, o.st.w);
+  }
+};
+
+// ---------------------------------------------------------------------------
+template <int DIM, int KERN>
+struct PhysWall {
+  static constexpr int NQ = 4;
+  static constexpr bool SENDER_VIEW = false;
+  struct Own {
+    float u[3], v[3], g[3], nw[3];
+    float4 st;
+    float mass, eta;
+    int tag;
+  };
+  struct Acc {
+    float sw, sp, sT;
+    float su[3], sv[3], srr[3];
+  };
+  __device__ static void load_stage(const Consts&, const Frame& f, const Extra&, int gp,
+                                    float4 (&q)[NQ]) {
+    q[0] = f.pt[gp];
+    q[1] = f.um[gp];
+    q[2] = f.vv[gp];
+    q[3] = f.st[gp];
+  }
+  __device__ static void load_own(const Consts& c, const Frame& f, const Extra& ex, int p,
+                                  float4 pt, Own& o) {
+    float4 um = f.um[p], vv = f.vv[p];
+    o.u[0] = um.x; o.u[1] = um.y; o.u[2] = um.z; o.mass = um.w;
+    o.v[0] = vv.x; o.v[1] = vv.y; o.v[2] = vv.z; o.eta = vv.w;
+    o.st = f.st[p];
+    o.tag = __float_as_int(pt.w);
+    float r[3] = {pt.x, pt.y, pt.z};
+    g_ext_of<DIM>(c, f, p, r, o.g);
+    o.nw[0] = o.nw[1] = o.nw[2] = 0.f;
+    if (ex.free_slip && f.nw) {
+      float4 n = f.nw[p];
+      o.nw[0] = n.x; o.nw[1] = n.y; o.nw[2] = n.z;
+    }
+  }
+  // only wall particles need the Shepard sums (everything else is discarded by the
+  // jnp.where(mask_bc, ...) of solver.py:461,485,514)
+  __device__ static bool active(const Consts&, const Own& o) { return is_wall_tag(o.tag); }
+  __device__ static void init(Acc& a) {
+    a.sw = a.sp = a.sT = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a.su[k] = a.sv[k] = a.srr[k] = 0.f;
+  }
+  __device__ static void pair(const Consts& c, const Extra&, const Own&, Acc& a, const float4* sq,
+                              int cap, int j, float4 pj, const float (&dr)[3], float d2) {
+    if (__float_as_int(pj.w) != SPHB200_TAG_FLUID) return;  // w * mask_j_s_fluid == 0
+    const float w = kernel_w<KERN>(c, sqrtf(d2));
+    const float4 uj = sq[cap + j], vj = sq[2 * cap + j], sj = sq[3 * cap + j];
+    a.sw += w;
+    a.su[0] += w * uj.x; a.su[1] += w * uj.y; a.su[2] += w * uj.z;
+    a.sv[0] += w * vj.x; a.sv[1] += w * vj.y; a.sv[2] += w * vj.z;
+    a.sp += w * sj.y;
+    const float rw = sj.x * w;
+    a.srr[0] += rw * dr[0]; a.srr[1] += rw * dr[1]; a.srr[2] += rw * dr[2];
+    a.sT += w * sj.z;
+  }
+  __device__ static void finish(const Consts& c, const Frame& f, const Extra& ex, int p,
+                                const Own& o, const Acc& a) {
+    const bool wall = is_wall_tag(o.tag);
+    float p_new = o.st.y, T = o.st.z;
+    if (wall) {
+      const float den = a.sw + c.eps;
+      float uw[3], vw[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        uw[k] = a.su[k] / den;
+        vw[k] = a.sv[k] / den;
+      }
+      if (ex.free_slip) {  // :464-486, wall_inner_normals = -nw
+        float win[3] = {-o.nw[0], -o.nw[1], -o.nw[2]};
+        float su = dot3(uw, win, DIM), sv = dot3(vw, win, DIM);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          uw[k] = win[k] * su;
+          vw[k] = win[k] * sv;
+        }
+      }
+      f.um[p] = make_float4(2.0f * o.u[0] - uw[0], 2.0f * o.u[1] - uw[1],
+                            DIM == 3 ? 2.0f * o.u[2] - uw[2] : 0.f, o.mass);
+      f.vv[p] = make_float4(2.0f * o.v[0] - vw[0], 2.0f * o.v[1] - vw[1],
+                            DIM == 3 ? 2.0f * o.v[2] - vw[2] : 0.f, o.eta);
+      const float p_ext = dot3(o.g, a.srr, DIM);  // :509-511
+      p_new = (a.sp + p_ext) / den;               // :513
+      if (ex.heat && (o.tag == SPHB200_TAG_SOLID_WALL || o.tag == SPHB200_TAG_MOVING_WALL))
+        T = a.sT / den;  // :518-526
+    }
+    const float rho = eos_rho(c, p_new);  // :516, every particle
+    if (ex.heat) T = T + c.dt_s * o.st.w;  // :834
+    ex.st_out[p] = make_float4(rho, p_new, T, o.st.w);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Force sweep.  Staged quads: 0 (x,y,z,tag) 1 (u, rho) 2 (p, eta, mass, (m/rho)^2)
+// [q_v] (v, 0)  [q_h] (T, kappa, 0, 0)  [q_nw] (nw, 0)  [q_ut] (u_tilde, 0)
+template <int DIM, int KERN, int SOLVER>
+struct PhysForce {
+  static constexpr int NQ = 7;
+  static constexpr bool SENDER_VIEW = false;
+  struct Own {
+    float u[3], v[3], g[3];
+    float rho, p, eta, mass, V2, T, kappa, Cp;
+    int tag;
+  };
+  struct Acc {
+    float a[3], tv[3], av[3];
+    float dT;
+  };
+  __device__ static void load_stage(const Consts&, const Frame& f, const Extra& ex, int gp,
+                                    float4 (&q)[NQ]) {
+    const float4 um = f.um[gp], st = f.st[gp], vv = f.vv[gp];
+    q[0] = f.pt[gp];
+    q[1] = make_float4(um.x, um.y, um.z, st.x);
+    const float vol = um.w / st.x;
+    q[2] = make_float4(st.y, vv.w, um.w, vol * vol);
+    if (ex.q_v >= 0) q[ex.q_v] = vv;
+    if (ex.q_h >= 0) q[ex.q_h] = make_float4(st.z, f.kc[gp].x, 0.f, 0.f);
+    if (ex.q_nw >= 0) q[ex.q_nw] = f.nw ? f.nw[gp] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ex.q_ut >= 0) q[ex.q_ut] = f.ut[gp];
+  }
+  __device__ static void load_own(const Consts& c, const Frame& f, const Extra& ex, int p,
+                                  float4 pt, Own& o) {
+    const float4 um = f.um[p], st = f.st[p], vv = f.vv[p];
+    o.u[0] = um.x; o.u[1] = um.y; o.u[2] = um.z; o.mass = um.w;
+    o.v[0] = vv.x; o.v[1] = vv.y; o.v[2] = vv.z; o.eta = vv.w;
+    o.rho = st.x; o.p = st.y; o.T = st.z;
+    const float vol = um.w / st.x;
+    o.V2 = vol * vol;
+    o.tag = __float_as_int(pt.w);
+    o.kappa = 0.f; o.Cp = 1.f;
+    if (ex.heat) {
+      float2 kc = f.kc[p];
+      o.kappa = kc.x; o.Cp = kc.y;
+    }
+    float r[3] = {pt.x, pt.y, pt.z};
+    g_ext_of<DIM>(c, f, p, r, o.g);
+  }
+  __device__ static bool active(const Consts&, const Own&) { return true; }
+  __device__ static void init(Acc& a) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a.a[k] = a.tv[k] = a.av[k] = 0.f;
+    a.dT = 0.f;
+  }
+  __device__ static void pair(const Consts& c, const Extra& ex, const Own& o, Acc& a,
+                              const float4* sq, int cap, int j, float4 pj, const float (&dr)[3],
+                              float d2) {
+    const float4 q1 = sq[cap + j], q2 = sq[2 * cap + j];
+    const float uj[3] = {q1.x, q1.y, q1.z};
+    const float rho_j = q1.w, p_j = q2.x, eta_j = q2.y, m_j = q2.z, V2_j = q2.w;
+    const int tag_j = __float_as_int(pj.w);
+    const float dist = sqrtf(d2);
+    const float gw = kernel_gw<KERN>(c, dist);
+    const float den = dist + c.eps;
+    const float wv = (o.V2 + V2_j) / o.mass;                                 // :205 / :247
+    const float cc = wv * gw / den;                                          // :206 / :248
+    const float eta_ij = 2.0f * o.eta * eta_j / (o.eta + eta_j + c.eps);    // :243
+    // transport-velocity acceleration, always computed (:912-921)
+    const float ct = cc * 1.0f * c.p_bg_tvf;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) a.tv[k] += ct * dr[k];
+
+    if (SOLVER == SPHB200_SOLVER_SPH) {
+      const float p_ij = (rho_j * o.p + o.rho * p_j) / (o.rho + rho_j);  // :244
+      float si = 0.f, sj = 0.f;
+      if (ex.q_v >= 0) {
+        const float4 vj = sq[ex.q_v * cap + j];
+        const float dvi[3] = {o.v[0] - o.u[0], o.v[1] - o.u[1], o.v[2] - o.u[2]};
+        const float dvj[3] = {vj.x - uj[0], vj.y - uj[1], vj.z - uj[2]};
+        si = dot3(dvi, dr, DIM);
+        sj = dot3(dvj, dr, DIM);
+      }
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) {
+        const float A = ((o.rho * o.u[k]) * si + (rho_j * uj[k]) * sj) / 2.0f;  // :250-251
+        a.a[k] += cc * ((-p_ij * dr[k] + A) + eta_ij * (o.u[k] - uj[k]));       // :254
+      }
+    } else {
+      float e[3] = {dr[0] / den, dr[1] / den, DIM == 3 ? dr[2] / den : 0.f};
+      float ne[3] = {-e[0], -e[1], -e[2]};
+      const bool is_w = is_wall_tag(tag_j);
+      float nwj[3] = {0.f, 0.f, 0.f}, ud[3] = {uj[0], uj[1], uj[2]};
+      if (is_w && ex.q_nw >= 0) {
+        const float4 n4 = sq[ex.q_nw * cap + j];
+        nwj[0] = n4.x; nwj[1] = n4.y; nwj[2] = n4.z;
+      }
+      if (is_w && ex.q_ut >= 0) {
+        const float4 t4 = sq[ex.q_ut * cap + j];
+        ud[0] = 2.0f * uj[0] - t4.x; ud[1] = 2.0f * uj[1] - t4.y; ud[2] = 2.0f * uj[2] - t4.z;
+      }
+      float nn[3] = {-nwj[0], -nwj[1], -nwj[2]}, ndr[3] = {-dr[0], -dr[1], -dr[2]};
+      const float u_L = is_w ? dot3(o.u, nn, DIM) : dot3(o.u, ne, DIM);  // :346-350
+      const float p_L = o.p, rho_L = o.rho;
+      const float u_R = is_w ? (-u_L + 2.0f * dot3(uj, nwj, DIM)) : dot3(uj, ne, DIM);
+      const float p_R = is_w ? (p_L + rho_L * dot3(o.g, ndr, DIM)) : p_j;
+      const float rho_R = is_w ? eos_rho(c, p_R) : rho_j;
+      const float P_avg = (p_L + p_R) / 2.0f;
+      const float rho_avg = (rho_L + rho_R) / 2.0f;
+      float beta = c.c_ref;  // :574-588
+      if (c.use_lim) beta = fminf(c.eta_lim * fmaxf(u_L - u_R, 0.0f), c.c_ref);
+      const float P_star = P_avg + 0.5f * rho_avg * (u_L - u_R) * beta;  // :371
+      const float rr = o.rho * rho_j;
+      const float c9 = -2.0f * m_j * (P_star / rr);                      // :374
+      const float c6 = 2.0f * m_j * eta_ij / rr;                         // :380-386
+      float mask = 1.0f;
+      if (ex.bc_trick && ex.free_slip) mask = (o.tag == SPHB200_TAG_FLUID) ? 1.0f : 0.0f;
+      const float gm = gw * mask;
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) {
+        const float vij = is_w ? (o.u[k] - ud[k]) : (o.u[k] - uj[k]);
+        a.a[k] += c9 * (gw * e[k]) + (c6 * vij / den) * gm;
+      }
+    }
+    if (ex.av) {  // :404-428
+      if (o.tag == SPHB200_TAG_FLUID && tag_j == SPHB200_TAG_FLUID) {
+        const float rho_ab = (o.rho + rho_j) / 2.0f;
+        const float du[3] = {o.u[0] - uj[0], o.u[1] - uj[1], o.u[2] - uj[2]};
+        const float num = (m_j * c.av_coef) * dot3(du, dr, DIM);
+        const float dd = rho_ab * (dist * dist + c.av_eps);
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) a.av[k] += num * (gw * (dr[k] / den)) / dd;
+      }
+    }
+    if (ex.heat) {  // :591-610
+      const float4 hj = sq[ex.q_h * cap + j];
+      const float eff = (o.kappa * hj.y) / (o.kappa + hj.y);
+      float rk = 0.f;
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) rk += dr[k] * (gw * (dr[k] / den));
+      const float F = rk / (dist * dist + c.eps);
+      a.dT += (4.0f * m_j * eff * (o.T - hj.x) * F) / (o.Cp * o.rho * rho_j);
+    }
+  }
+  __device__ static void finish(const Consts& c, const Frame& f, const Extra& ex, int p,
+                                const Own& o, const Acc& a) {
+    float du[3], dv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float s = a.a[k];
+      if (ex.av) s = s + a.av[k];  // :925-928
+      du[k] = s + o.g[k];          // :936
+      dv[k] = a.tv[k];
+    }
+    float dTdt = a.dT;
+    // case bc_fn, derivative part (u, v, p, T are patched by k_bc after the sweep)
+    if (ex.bc_on && o.tag >= 0 && o.tag <= 3) {
+      const uint32_t fl = c.bc[o.tag].flags;
+      if (fl & SPHB200_BC_ZERO_DUDT) du[0] = du[1] = du[2] = 0.f;
+      if (fl & SPHB200_BC_ZERO_DVDT) dv[0] = dv[1] = dv[2] = 0.f;
+      if (fl & SPHB200_BC_ZERO_DTDT) dTdt = 0.f;
+      if (o.tag == SPHB200_TAG_FLUID) {
+        const float x = f.pt[p].x;
+        if (c.inflow_on && x < c.inflow_x) dTdt = 0.f;
+        if (c.outflow_on && x > c.outflow_x) dTdt = 0.f;
+      }
+    }
+    const float drhodt = f.du[p].w;
+    f.du[p] = make_float4(du[0], du[1], DIM == 3 ? du[2] : 0.f, drhodt);
+    f.dv[p] = make_float4(dv[0], dv[1], DIM == 3 ? dv[2] : 0.f, 0.f);
+    if (ex.heat) reinterpret_cast<float*>(&f.st[p])[3] = dTdt;
+  }
+};
+
+// bc_fn, value part: u, v, p, T overwritten per tag (after the force sweep has
+// consumed the wall values the solver computed).
+template <int DIM>
+__global__ void __launch_bounds__(256) k_bc(int n, Consts c, Frame f) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const float4 pt = f.pt[p];
+  const int tag = __float_as_int(pt.w);
+  if (tag < 0 || tag > 3) return;
+  const sphb200_bc_rule r = c.bc[tag];
+  if (r.flags & SPHB200_BC_SET_U) {
+    float4 q = f.um[p];
+    f.um[p] = make_float4(r.u[0], r.u[1], DIM == 3 ? r.u[2] : 0.f, q.w);
+  }
+  if (r.flags & SPHB200_BC_SET_V) {
+    float4 q = f.vv[p];
+    f.vv[p] = make_float4(r.v[0], r.v[1], DIM == 3 ? r.v[2] : 0.f, q.w);
+  }
+  const bool inflow = c.inflow_on && tag == SPHB200_TAG_FLUID && pt.x < c.inflow_x;
+  if ((r.flags & (SPHB200_BC_SET_P | SPHB200_BC_SET_T)) || inflow) {
+    float4 q = f.st[p];
+    if (inflow) q.z = c.inflow_T;
+    if (r.flags & SPHB200_BC_SET_P) q.y = r.p;
+    if (r.flags & SPHB200_BC_SET_T) q.z = r.T;
+    f.st[p] = q;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Sparse neighbour list in original indices.  The thread's own particle is the
+// SENDER (row 1); receivers (row 0) are written ascending.  Two launches: count,
+// then (after an exclusive scan over senders in original order) fill.
+template <int DIM>
+struct PhysNeighbors {
+  static constexpr int NQ = 2;
+  static constexpr bool SENDER_VIEW = true;
+  struct Own {
+    int id;
+    long long off;
+  };
+  struct Acc {
+    int n;
+  };
+  __device__ static void load_stage(const Consts&, const Frame& f, const Extra&, int gp,
+                                    float4 (&q)[NQ]) {
+    q[0] = f.pt[gp];
+    q[1] = make_float4(__int_as_float(f.id[gp]), 0.f, 0.f, 0.f);
+  }
+  __device__ static void load_own(const Consts&, const Frame& f, const Extra& ex, int p, float4,
+                                  Own& o) {
+    o.id = f.id[p];
+    o.off = ex.nl_fill ? (long long)(unsigned)ex.nl_offsets[o.id] : 0;
+  }
+  __device__ static bool active(const Consts&, const Own&) { return true; }
+  __device__ static void init(Acc& a) { a.n = 0; }
+  __device__ static void pair(const Consts&, const Extra& ex, const Own& o, Acc& a,
+                              const float4* sq, int cap, int j, float4, const float (&)[3], float) {
+    const int jid = __float_as_int(sq[cap + j].x);
+    if (ex.nl_mask_self && jid == o.id) return;
+    if (ex.nl_fill) {
+      // insertion into the ascending run [off, off + n) of row 0
+      long long pos = o.off + a.n;
+      if (pos < ex.nl_capacity) {
+        int* row0 = ex.nl_idx;
+        long long k = pos;
+        while (k > o.off && row0[k - 1] > jid) {
+          row0[k] = row0[k - 1];
+          --k;
+        }
+        row0[k] = jid;
+        ex.nl_idx[ex.nl_capacity + pos] = o.id;
+      }
+    }
+    ++a.n;
+  }
+  __device__ static void finish(const Consts&, const Frame&, const Extra& ex, int, const Own& o,
+                                const Acc& a) {
+    if (!ex.nl_fill) ex.nl_counts[o.id] = a.n;
+  }
+};
+
+}  // namespace sphb200

@@ -1,0 +1,279 @@
+// sweep.cuh -- the list-free pairwise sweep over cell-sorted particles.
+//
+// Replaces the reference's candidate gather + prune + E-sized gathers +
+// segment_sum chains (jax_md/partition.py:832-909, solver.py:722-731 and every
+// ops.segment_sum in solver.py:750-928) by one kernel template.
+//
+// One thread block owns a tile of T[0] x T[1] x T[2] cells.  It
+//   1. stages the particles of the tile's stencil (tile + S cells each side)
+//      into shared memory with coalesced float4 loads, NQ quads per particle;
+//   2. phase 1: every thread walks ITS OWN (2S+1)^d window of the staged cells
+//      with a cheap squared-distance test (no periodic fold: the image shift is
+//      applied once per row/segment to the thread's own coordinates) and appends
+//      the survivors' staged indices to a per-thread uint16 list in shared memory;
+//   3. phase 2: every thread consumes its list -- all lanes busy with real
+//      neighbours -- re-deriving the displacement with the reference's exact
+//      float32 arithmetic (space.py:170-181) and, inside the rounding band
+//      around the cutoff, the reference's membership metric d(r_j, r_i) < cutoff^2
+//      (jax_md/partition.py:897), so the neighbour SET is the reference's, bit for bit.
+// The physics (what is accumulated per pair, what is written per particle) is a
+// policy class P, see phys.cuh.
+#pragma once
+#include "common.cuh"
+
+namespace sphb200 {
+
+constexpr int MAX_RUNS = 16;     // T[1]*T[2] upper bound
+constexpr int MAX_SOFF = 1023;   // staged (row, cell) entries upper bound
+constexpr int SWEEP_CHUNK = 32;  // phase-1 candidates between list-room checks
+
+struct SweepDims {
+  int cap;   // staged particles per block
+  int lcap;  // list entries per thread (>= SWEEP_CHUNK)
+  int nq;    // quads staged per particle (<= P::NQ)
+};
+
+__host__ __device__ inline size_t sweep_smem_bytes(int nq, int cap, int lcap, int tpb) {
+  return (size_t)nq * cap * 16 + (size_t)lcap * tpb * 2 + (MAX_SOFF + 1 + 2 * MAX_RUNS + 2) * 4;
+}
+
+__device__ __forceinline__ int wrap_cell(int u, int n) {
+  int m = u % n;
+  return m < 0 ? m + n : m;
+}
+__device__ __forceinline__ int floor_div(int u, int n) { return (u >= 0) ? (u / n) : -((-u + n - 1) / n); }
+
+template <int DIM, class P>
+__global__ void __launch_bounds__(256) k_sweep(const Grid g, const Consts c, const Frame f,
+                                               const int* __restrict__ cs, const SweepDims sd,
+                                               const Extra ex,
+                                               unsigned* __restrict__ err) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int TPB = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = TPB >> 5;
+  float4* sq = reinterpret_cast<float4*>(smem_raw);
+  unsigned short* list = reinterpret_cast<unsigned short*>(sq + (size_t)sd.nq * sd.cap);
+  int* soff = reinterpret_cast<int*>(list + (size_t)sd.lcap * TPB);
+  int* own_off = soff + (MAX_SOFF + 1);
+  int* own_start = own_off + (MAX_RUNS + 1);
+
+  // ---- tile geometry (uniform) -------------------------------------------
+  int b = blockIdx.x;
+  const int tx = b % g.nt[0];
+  b /= g.nt[0];
+  const int ty = b % g.nt[1];
+  const int tz = b / g.nt[1];
+  int c0[3] = {tx * g.T[0], ty * g.T[1], tz * g.T[2]};
+  int no[3], sa0[3], slen[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    no[a] = min(g.T[a], g.n[a] - c0[a]);
+    if (g.n[a] >= 2 * g.S[a] + 1) {
+      sa0[a] = c0[a] - g.S[a];
+      slen[a] = no[a] + 2 * g.S[a];
+    } else {
+      sa0[a] = 0;
+      slen[a] = g.n[a];
+    }
+  }
+  const int nxs = slen[0];
+  const int nrows = slen[1] * slen[2];
+  const int E = nrows * nxs;
+  const int nruns = no[1] * no[2];
+
+  if (tid < nruns) {
+    int ry = tid % no[1], rz = tid / no[1];
+    int cell = ((c0[2] + rz) * g.n[1] + (c0[1] + ry)) * g.n[0] + c0[0];
+    int s = cs[cell];
+    own_start[tid] = s;
+    own_off[tid + 1] = cs[cell + no[0]] - s;
+  }
+  for (int e = tid; e < E; e += TPB) {
+    int k = e % nxs, row = e / nxs;
+    int ry = row % slen[1], rz = row / slen[1];
+    int cell = (wrap_cell(sa0[2] + rz, g.n[2]) * g.n[1] + wrap_cell(sa0[1] + ry, g.n[1])) * g.n[0] +
+               wrap_cell(sa0[0] + k, g.n[0]);
+    soff[e] = cs[cell + 1] - cs[cell];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // exclusive scan of soff[0..E) in place, soff[E] = total
+    int carry = 0;
+    for (int base = 0; base < E; base += 32) {
+      int i = base + lane;
+      int v = i < E ? soff[i] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(FULL_MASK, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (i < E) soff[i] = carry + inc - v;
+      carry += __shfl_sync(FULL_MASK, inc, 31);
+    }
+    if (lane == 0) {
+      soff[E] = carry;
+      int acc = 0;
+      own_off[0] = 0;
+      for (int r = 0; r < nruns; ++r) {
+        acc += own_off[r + 1];
+        own_off[r + 1] = acc;
+      }
+    }
+  }
+  __syncthreads();
+  const int tile_n = own_off[nruns];
+  if (tile_n == 0) return;
+  const int total_staged = soff[E];
+  const bool single_group = total_staged <= sd.cap;
+
+  for (int ib = 0; ib < tile_n; ib += TPB) {
+    // ---- own particle ------------------------------------------------------
+    const int t = ib + tid;
+    const bool have = t < tile_n;
+    int p = 0;
+    if (have) {
+      int r = 0;
+      while (t >= own_off[r + 1]) ++r;
+      p = own_start[r] + (t - own_off[r]);
+    }
+    typename P::Own own;
+    typename P::Acc acc;
+    float ri[3] = {0.f, 0.f, 0.f};
+    int ci[3] = {0, 0, 0};
+    bool act = false;
+    if (have) {
+      float4 q = f.pt[p];
+      ri[0] = q.x; ri[1] = q.y; ri[2] = q.z;
+      cell_of<DIM>(g, ri, ci);
+      P::load_own(c, f, ex, p, q, own);
+      act = P::active(c, own);
+    }
+    P::init(acc);
+    // window origin in staged coordinates
+    int w0[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) w0[a] = (g.n[a] >= 2 * g.S[a] + 1) ? (ci[a] - g.S[a] - sa0[a]) : 0;
+
+    int cnt = 0;
+    auto consume = [&]() {
+      for (int k = 0; k < cnt; ++k) {
+        const int j = list[k * TPB + tid];
+        const float4 pj = sq[j];
+        float dr[3];
+        dr[0] = disp1(ri[0], pj.x, g.half[0], g.box[0]);
+        dr[1] = disp1(ri[1], pj.y, g.half[1], g.box[1]);
+        dr[2] = (DIM == 3) ? disp1(ri[2], pj.z, g.half[2], g.box[2]) : 0.0f;
+        const float d2 = sumsq<DIM>(dr);
+        if (d2 > g.c2_lo) {
+          // rounding band: the reference decides membership on d(r_sender, r_receiver)
+          float m[3];
+          if (P::SENDER_VIEW) {
+            m[0] = dr[0]; m[1] = dr[1]; m[2] = dr[2];
+          } else {
+            m[0] = disp1(pj.x, ri[0], g.half[0], g.box[0]);
+            m[1] = disp1(pj.y, ri[1], g.half[1], g.box[1]);
+            m[2] = (DIM == 3) ? disp1(pj.z, ri[2], g.half[2], g.box[2]) : 0.0f;
+          }
+          if (!(sumsq<DIM>(m) < g.c2)) continue;
+        }
+        P::pair(c, ex, own, acc, sq, sd.cap, j, pj, dr, d2);
+      }
+      cnt = 0;
+    };
+
+    // ---- row groups ----------------------------------------------------------
+    int row_a = 0;
+    while (row_a < nrows) {
+      const int base = soff[row_a * nxs];
+      int row_b = row_a;
+      while (row_b < nrows && soff[(row_b + 1) * nxs] - base <= sd.cap) ++row_b;
+      bool skip = false;
+      if (row_b == row_a) {  // one stencil row alone exceeds the staging buffer
+        if (tid == 0) atomicOr(err, SPHB200_ERR_STAGE_OVERFLOW);
+        row_b = row_a + 1;
+        skip = true;
+      }
+      if (!skip && !(single_group && ib > 0)) {
+        if (ib > 0 || row_a > 0) __syncthreads();  // previous readers done
+        const int njobs = (row_b - row_a) * 3;
+        for (int job = warp; job < njobs; job += nwarps) {
+          const int row = row_a + job / 3;
+          const int seg = job % 3 - 1;
+          int k0 = max(0, seg * g.n[0] - sa0[0]);
+          int k1 = min(nxs, (seg + 1) * g.n[0] - sa0[0]);
+          if (k0 >= k1) continue;
+          const int ry = row % slen[1], rz = row / slen[1];
+          const int rowcell =
+              (wrap_cell(sa0[2] + rz, g.n[2]) * g.n[1] + wrap_cell(sa0[1] + ry, g.n[1])) * g.n[0];
+          const int gstart = cs[rowcell + (sa0[0] + k0 - seg * g.n[0])];
+          const int dst = soff[row * nxs + k0] - base;
+          const int len = soff[row * nxs + k1] - soff[row * nxs + k0];
+          for (int m = lane; m < len; m += 32) {
+            float4 q[P::NQ];
+            P::load_stage(c, f, ex, gstart + m, q);
+#pragma unroll
+            for (int qq = 0; qq < P::NQ; ++qq)
+              if (qq < sd.nq) sq[(size_t)qq * sd.cap + dst + m] = q[qq];
+          }
+        }
+        __syncthreads();
+      }
+      if (!skip) {
+        for (int row = row_a; row < row_b; ++row) {
+          const int ry = row % slen[1], rz = row / slen[1];
+          const bool inwin = act && ry >= w0[1] && ry < w0[1] + g.W[1] && rz >= w0[2] &&
+                             rz < w0[2] + g.W[2];
+          const float ys = ri[1] - (float)floor_div(sa0[1] + ry, g.n[1]) * g.box[1];
+          const float zs = ri[2] - (float)floor_div(sa0[2] + rz, g.n[2]) * g.box[2];
+          const int ka = w0[0], kb = w0[0] + g.W[0];
+          int ks = kb;
+          const int kz = -sa0[0], kn = g.n[0] - sa0[0];
+          if (ka < kz && kz < kb) ks = kz;
+          else if (ka < kn && kn < kb) ks = kn;
+#pragma unroll 1
+          for (int sgm = 0; sgm < 2; ++sgm) {
+            const int kk0 = sgm == 0 ? ka : ks, kk1 = sgm == 0 ? ks : kb;
+            int ja = 0, jb = 0;
+            float xs = ri[0];
+            if (inwin && kk0 < kk1) {
+              ja = soff[row * nxs + kk0] - base;
+              jb = soff[row * nxs + kk1] - base;
+              xs = ri[0] - (float)floor_div(sa0[0] + kk0, g.n[0]) * g.box[0];
+            }
+            int j = ja;
+            for (;;) {
+              const int rem = jb - j;
+              const bool more = rem > 0;
+              if (!__any_sync(FULL_MASK, more)) break;
+              const int want = more ? min(rem, SWEEP_CHUNK) : 0;
+              if (__any_sync(FULL_MASK, want > sd.lcap - cnt)) {
+                consume();
+                continue;
+              }
+              const int e = j + want;
+              for (; j < e; ++j) {
+                const float4 pj = sq[j];
+                const float dx = xs - pj.x, dy = ys - pj.y;
+                float d2 = dx * dx + dy * dy;
+                if (DIM == 3) {
+                  const float dz = zs - pj.z;
+                  d2 += dz * dz;
+                }
+                if (d2 < g.c2_hi) {
+                  list[cnt * TPB + tid] = (unsigned short)j;
+                  ++cnt;
+                }
+              }
+            }
+          }
+        }
+        consume();
+      }
+      row_a = row_b;
+    }
+    if (have) P::finish(c, f, ex, p, own, acc);
+  }
+}
+
+}  // namespace sphb200

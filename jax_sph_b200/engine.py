@@ -1,0 +1,288 @@
+"""Resident B200 engine: the step loop of jax_sph/simulate.py:110-134 with the
+particle state kept cell-sorted in HBM.
+
+`Engine` is a thin, typed wrapper over the C ABI (include/sphb200.h); torch is
+used only for device memory and streams.  States are dicts with the reference's
+keys (jax_sph/solver.py:930-947): torch CUDA tensors or NumPy arrays.
+"""
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib
+
+STATE_KEYS = _lib.VECTOR_FIELDS + _lib.SCALAR_FIELDS + ("tag",)
+
+
+def make_config(
+    dim, box, dx, dt, *, solver="SPH", kernel="QSK", h_fac=1.0, tvf=0.0, eos=None,
+    p_ref=None, rho_ref=1.0, p_bg=0.0, gamma=1.0, u_ref=1.0, c_ref=10.0, eta_limiter=3.0,
+    is_bc_trick=False, is_rho_evol=False, is_rho_renorm=False, is_free_slip=False,
+    is_heat_conduction=False, artificial_alpha=0.0, g_ext_spec=None, bc_table=None,
+    cell_sub=None, tile=None, threads=0, list_cap=0, stage_cap=0, g_ext_array=False,
+):
+    """Build a `sphb200_config` from the WCSPH constructor arguments
+    (jax_sph/solver.py:616-637) plus the table forms of the case callables."""
+    if solver not in _lib.SOLVER:
+        raise _lib.Sphb200Error(f"solver {solver!r} is not supported (SPH, RIE)")
+    if kernel not in _lib.KERNEL:
+        raise _lib.Sphb200Error(f"kernel {kernel!r} is not supported (QSK, WC2K)")
+    cfg = _lib.default_config()
+    cfg.dim = dim
+    cfg.solver = _lib.SOLVER[solver]
+    cfg.kernel = _lib.KERNEL[kernel]
+    if eos is None:
+        eos = "RIEMANN" if solver == "RIE" else "TAIT"
+    cfg.eos = _lib.EOS_RIEMANN if eos == "RIEMANN" else _lib.EOS_TAIT
+    box = np.asarray(box, dtype=np.float64).reshape(-1)
+    if box.size == 1:
+        box = np.repeat(box, dim)
+    for a in range(dim):
+        cfg.box[a] = float(box[a])
+    cfg.dx = dx
+    cfg.h = h_fac * dx
+    cfg.dt = dt
+    cfg.tvf = tvf
+    cfg.c_ref = c_ref
+    cfg.eta_limiter = eta_limiter
+    cfg.artificial_alpha = artificial_alpha
+    cfg.p_ref = p_ref if p_ref is not None else rho_ref * c_ref**2 / gamma
+    cfg.rho_ref, cfg.p_bg, cfg.gamma, cfg.u_ref = rho_ref, p_bg, gamma, u_ref
+    cfg.flags = ((_lib.F_BC_TRICK if is_bc_trick else 0) | (_lib.F_RHO_EVOL if is_rho_evol else 0)
+                 | (_lib.F_RHO_RENORM if is_rho_renorm else 0)
+                 | (_lib.F_FREE_SLIP if is_free_slip else 0)
+                 | (_lib.F_HEAT if is_heat_conduction else 0))
+    spec = g_ext_spec or {"mode": "none"}
+    if g_ext_array:
+        cfg.g_mode = _lib.G_ARRAY
+    elif spec["mode"] == "const":
+        cfg.g_mode = _lib.G_CONST
+        for a in range(3):
+            cfg.g[a] = spec["g"][a]
+    elif spec["mode"] == "band":
+        cfg.g_mode = _lib.G_BAND
+        cfg.g_axis = spec["axis"]
+        cfg.g_lo, cfg.g_hi = spec["lo"], spec["hi"]
+        for a in range(3):
+            cfg.g[a] = spec["g"][a]
+    else:
+        cfg.g_mode = _lib.G_NONE
+    if bc_table:
+        for tag, rule in bc_table.get("tags", {}).items():
+            r = cfg.bc[int(tag)]
+            fl = 0
+            if "u" in rule:
+                fl |= _lib.BC_SET_U
+                for a in range(3):
+                    r.u[a] = rule["u"][a]
+            if "v" in rule:
+                fl |= _lib.BC_SET_V
+                for a in range(3):
+                    r.v[a] = rule["v"][a]
+            if rule.get("zero_dudt"):
+                fl |= _lib.BC_ZERO_DUDT
+            if rule.get("zero_dvdt"):
+                fl |= _lib.BC_ZERO_DVDT
+            if "p" in rule:
+                fl |= _lib.BC_SET_P
+                r.p = rule["p"]
+            if "T" in rule:
+                fl |= _lib.BC_SET_T
+                r.T = rule["T"]
+            if rule.get("zero_dTdt"):
+                fl |= _lib.BC_ZERO_DTDT
+            r.flags = fl
+        if bc_table.get("inflow_x"):
+            cfg.bc_inflow_on = 1
+            cfg.bc_inflow_x = bc_table["inflow_x"]["x"]
+            cfg.bc_inflow_T = bc_table["inflow_x"]["T"]
+        if bc_table.get("outflow_x"):
+            cfg.bc_outflow_on = 1
+            cfg.bc_outflow_x = bc_table["outflow_x"]["x"]
+    for name, val in (("cell_sub", cell_sub), ("tile", tile)):
+        if val is not None:
+            arr = getattr(cfg, name)
+            for a in range(3):
+                arr[a] = int(val[a]) if a < len(val) else 0
+    cfg.threads, cfg.list_cap, cfg.stage_cap = threads, list_cap, stage_cap
+    return cfg
+
+
+def config_from_setup(setup, **tuning):
+    """`setup` is anything exposing the fields of the reference's
+    SimulationSetup / WCSPH call (jax_sph/simulate.py:49-69): used by tests and
+    bench with the oracle's case objects -- only plain attributes are read."""
+    return make_config(
+        setup.dim, setup.box_size, setup.dx, setup.dt, solver=setup.solver, kernel=setup.kernel,
+        h_fac=setup.h_factor, tvf=setup.tvf, p_ref=setup.p_ref, rho_ref=setup.rho_ref,
+        p_bg=setup.p_bg, gamma=setup.gamma, u_ref=setup.u_ref, c_ref=setup.c_ref,
+        eta_limiter=setup.eta_limiter, is_bc_trick=setup.is_bc_trick,
+        is_rho_evol=setup.density_evolution, is_rho_renorm=setup.density_renormalize,
+        is_free_slip=setup.free_slip, is_heat_conduction=setup.heat_conduction,
+        artificial_alpha=setup.artificial_alpha, g_ext_spec=setup.g_ext_spec,
+        bc_table=setup.bc_table, **tuning)
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _stream_ptr():
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One engine = one particle system resident on the current CUDA device."""
+
+    def __init__(self, cfg, n: int):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.Sphb200Error("no CUDA device: the engine has no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.n = int(n)
+        self.dim = int(cfg.dim)
+        nbytes = C.c_size_t()
+        _lib.check(self.lib.sphb200_engine_bytes(C.byref(cfg), self.n, C.byref(nbytes)))
+        # torch owns the arena (caching allocator, freed with the object)
+        self._arena = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+        self._h = C.c_void_p()
+        _lib.check(self.lib.sphb200_engine_create_in(
+            C.byref(cfg), self.n, C.c_void_p(self._arena.data_ptr()), nbytes.value,
+            C.byref(self._h)))
+        self.arena_bytes = nbytes.value
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.sphb200_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- marshalling -----------------------------------------------------------
+    def _state_struct(self, state: Dict, writable: bool):
+        """dict -> (sphb200_state, on_host).  Arrays must be float32/int32 and contiguous."""
+        torch = _torch()
+        st = _lib.State()
+        on_host = None
+        keep = []
+        for k in STATE_KEYS + ("g_ext",):
+            a = state.get(k)
+            if a is None:
+                continue
+            want_int = k == "tag"
+            if isinstance(a, np.ndarray):
+                host = True
+                if a.dtype == np.float64:
+                    raise _lib.Sphb200Error(f"state[{k!r}] is float64: float32 only (SPHB200_EDTYPE)")
+                want = np.int32 if want_int else np.float32
+                if a.dtype != want or not a.flags.c_contiguous:
+                    if writable:
+                        raise _lib.Sphb200Error(f"output state[{k!r}] must be contiguous {want}")
+                    a = np.ascontiguousarray(a, dtype=want)
+                ptr = a.ctypes.data
+            else:
+                host = not a.is_cuda
+                if a.dtype == torch.float64:
+                    raise _lib.Sphb200Error(f"state[{k!r}] is float64: float32 only (SPHB200_EDTYPE)")
+                want = torch.int32 if want_int else torch.float32
+                if a.dtype != want or not a.is_contiguous():
+                    if writable:
+                        raise _lib.Sphb200Error(f"output state[{k!r}] must be contiguous {want}")
+                    a = a.to(want).contiguous()
+                ptr = a.data_ptr()
+            n_expected = self.n * (self.dim if k in _lib.VECTOR_FIELDS + ("g_ext",) else 1)
+            if a.size if isinstance(a, np.ndarray) else a.numel():
+                pass
+            count = a.size if isinstance(a, np.ndarray) else a.numel()
+            if count != n_expected:
+                raise _lib.Sphb200Error(f"state[{k!r}] has {count} elements, expected {n_expected}")
+            if on_host is None:
+                on_host = host
+            elif on_host != host:
+                raise _lib.Sphb200Error("state mixes host and device arrays")
+            keep.append(a)
+            setattr(st, k, ptr)
+        return st, bool(on_host), keep
+
+    # -- API -------------------------------------------------------------------
+    def upload(self, state: Dict):
+        st, on_host, keep = self._state_struct(state, writable=False)
+        self._keep = keep
+        _lib.check(self.lib.sphb200_engine_upload(self._h, C.byref(st), int(on_host), _stream_ptr()))
+
+    def step(self, dt: float, nsteps: int = 1, integrate: bool = True, bc: bool = True):
+        flags = (_lib.STEP_INTEGRATE if integrate else 0) | (_lib.STEP_BC if bc else 0)
+        _lib.check(self.lib.sphb200_engine_step(self._h, float(dt), int(nsteps), flags, _stream_ptr()))
+
+    def download(self, out: Optional[Dict] = None, keys=None, host: bool = False):
+        """State in the original particle order.  `out` may hold preallocated arrays."""
+        torch = _torch()
+        if out is None:
+            out = {}
+            keys = keys or STATE_KEYS
+            for k in keys:
+                if k == "nw" and not (self.cfg.solver == 1 or self.cfg.flags & _lib.F_FREE_SLIP):
+                    continue
+                if k in ("kappa", "Cp") and not self.cfg.flags & _lib.F_HEAT:
+                    continue
+                shape = (self.n, self.dim) if k in _lib.VECTOR_FIELDS else (self.n,)
+                dt = torch.int32 if k == "tag" else torch.float32
+                if host:
+                    out[k] = torch.empty(shape, dtype=dt, pin_memory=True)
+                else:
+                    out[k] = torch.empty(shape, dtype=dt, device="cuda")
+        st, on_host, keep = self._state_struct(out, writable=True)
+        _lib.check(self.lib.sphb200_engine_download(self._h, C.byref(st), int(on_host), _stream_ptr()))
+        if on_host:
+            torch.cuda.current_stream().synchronize()
+        return out
+
+    def error(self) -> int:
+        code = C.c_uint32()
+        _lib.check(self.lib.sphb200_engine_error(self._h, C.byref(code), _stream_ptr()))
+        return code.value
+
+    def neighbor_list(self, capacity: int, mask_self: bool = False):
+        """(idx[2, capacity] int32 cuda tensor, edge count)."""
+        torch = _torch()
+        idx = torch.empty((2, capacity), dtype=torch.int32, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        _lib.check(self.lib.sphb200_engine_neighbor_list(
+            self._h, C.c_void_p(idx.data_ptr()), int(capacity), int(mask_self),
+            C.c_void_p(cnt.data_ptr()), _stream_ptr()))
+        return idx, int(cnt.item())
+
+    def stats(self):
+        ek, um = C.c_double(), C.c_double()
+        _lib.check(self.lib.sphb200_engine_stats(self._h, C.byref(ek), C.byref(um), _stream_ptr()))
+        return ek.value, um.value
+
+    def launches(self) -> int:
+        return int(self.lib.sphb200_engine_launches(self._h))
+
+    def profile(self, on: bool = True):
+        _lib.check(self.lib.sphb200_engine_profile(self._h, int(on)))
+
+    def last_times(self):
+        ms = (C.c_float * 8)()
+        _lib.check(self.lib.sphb200_engine_last_times(self._h, C.byref(ms)))
+        return dict(cells=ms[1], density=ms[2], wall=ms[3], force=ms[4], total=ms[5])
+
+    def plan(self):
+        out = (C.c_int32 * 16)()
+        _lib.check(self.lib.sphb200_engine_plan(self._h, C.byref(out)))
+        v = list(out)
+        return dict(cells=v[0:3], sub=v[3:6], tile=v[6:9], threads=v[9], list_cap=v[10],
+                    stage_cap=dict(density=v[11], wall=v[12], force=v[13]), exact_all=v[14],
+                    ncells=v[15])
