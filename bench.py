@@ -1,0 +1,348 @@
+"""bench.py -- particle-updates/s of the JAX-SPH per-step hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU reference arm)
+
+Workload at N=1: BASELINE.json configs[3], the 3D Taylor-Green vortex of
+validation/tgv3d.sh (SPH, tvf=1, viscosity 0.02, Quintic kernel) on a 256^3
+lattice = 16 777 216 particles, float32, synthetic lattice initialisation.
+One "step" = one advance(dt) (integrator.py:22-56): kick + drift + wrap,
+neighbour-structure rebuild, density sweep + EoS, force sweep.
+
+Prints ONE JSON line (rank 0).  `value` times the resident engine (state in
+HBM); `e2e` times the same step through the public host-buffer API with the
+full state copied host->device before and device->host after every step.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle-updates/sec"
+UNIT = "particle-updates/s"
+
+# algorithmic HBM bytes per particle-step (float32, 3D / 2D), DESIGN.md section 4
+BYTES = {
+    3: dict(cells=64 + 8 + 12 + 16 + 76 + 84, density=16 + 16, force=64 + 32, step=0),
+    2: dict(cells=64 + 8 + 12 + 16 + 76 + 84, density=16 + 16, force=64 + 32, step=0),
+}
+# useful flops per directed in-range edge, SURVEY.md section 8d
+FLOPS_EDGE = {3: dict(density=58 + 1, force=58 + 103 + 16), 2: dict(density=50 + 1, force=50 + 63 + 14)}
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal non-tensor FP32 FMA peak
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        try:
+            self.proc.terminate()
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4)
+                          if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_setup(workload, nx):
+    from oracle import cases
+
+    if workload == "tgv3d":
+        return cases.make_case("tgv", dim=3, dx=2 * np.pi / nx, dtype=np.float32, tvf=1.0,
+                               viscosity=0.02)
+    if workload == "tgv2d":
+        return cases.make_case("tgv", dim=2, dx=1.0 / nx, dtype=np.float32, tvf=1.0)
+    raise ValueError(workload)
+
+
+def lattice_state(workload, nx):
+    """Synthetic lattice initial state WITHOUT importing the oracle (product path):
+    particles at (i + 0.5) dx, TGV velocity field (cases/tgv.py:37-51), rho = 1."""
+    if workload == "tgv3d":
+        dim, box = 3, 2 * np.pi
+    else:
+        dim, box = 2, 1.0
+    dx = box / nx
+    ax = ((np.arange(nx, dtype=np.float32) + np.float32(0.5)) * np.float32(dx)).astype(np.float32)
+    if dim == 3:
+        # utils.py:49-54 meshgrid(indexing="xy") ravel order
+        X, Y, Z = np.meshgrid(ax, ax, ax, indexing="xy")
+        r = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+        x, y, z = r[:, 0], r[:, 1], r[:, 2]
+        u = np.stack([np.sin(x) * np.cos(y) * np.cos(z), -np.cos(x) * np.sin(y) * np.cos(z),
+                      np.zeros_like(x)], axis=1).astype(np.float32)
+        viscosity, u_ref = 0.02, 1.0
+    else:
+        X, Y = np.meshgrid(ax, ax, indexing="xy")
+        r = np.stack([X.ravel(), Y.ravel()], axis=1)
+        x, y = r[:, 0], r[:, 1]
+        tp = np.float32(2 * np.pi)
+        u = np.stack([-np.cos(tp * x) * np.sin(tp * y), np.sin(tp * x) * np.cos(tp * y)],
+                     axis=1).astype(np.float32)
+        viscosity, u_ref = 0.01, 1.0
+    n = len(r)
+    c_ref = 10.0 * u_ref
+    # case_setup.py:94-97 (CFL 0.25)
+    dt = float(min(0.25 * dx / (c_ref + u_ref), 0.25 * dx * dx / viscosity))
+    ones = np.ones(n, dtype=np.float32)
+    state = dict(r=np.ascontiguousarray(r, dtype=np.float32), u=u, v=u.copy(),
+                 dudt=np.zeros_like(u), dvdt=np.zeros_like(u), rho=ones.copy(),
+                 p=np.zeros(n, dtype=np.float32), drhodt=np.zeros(n, dtype=np.float32),
+                 mass=ones * np.float32(dx**dim), eta=ones * np.float32(viscosity),
+                 T=ones.copy(), dTdt=np.zeros(n, dtype=np.float32),
+                 tag=np.zeros(n, dtype=np.int32))
+    meta = dict(dim=dim, box=[box] * dim, dx=dx, dt=dt, viscosity=viscosity, c_ref=c_ref,
+                p_ref=c_ref**2, tvf=1.0)
+    return state, meta
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from jax_sph_b200 import Engine, make_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    state, meta = lattice_state(args.workload, args.nx)
+    n = len(state["r"])
+    dim = meta["dim"]
+    cfg = make_config(dim, meta["box"], meta["dx"], meta["dt"], tvf=meta["tvf"],
+                      c_ref=meta["c_ref"], p_ref=meta["p_ref"],
+                      cell_sub=[args.sub] * dim if args.sub else None,
+                      threads=args.threads, list_cap=args.list_cap,
+                      tile=[args.tile_x, 0, 0] if args.tile_x else None)
+    eng = Engine(cfg, n)
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in state.items()}
+    eng.upload(pinned)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.step(meta["dt"], args.warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = eng.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    eng.step(meta["dt"], args.steps)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launches() - l0
+    clocks = sampler.finish()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    err = eng.error()
+
+    # per-pass CUDA-event times (same stream, separate loop of the same steps)
+    eng.profile(True)
+    acc = {}
+    for _ in range(args.steps):
+        eng.step(meta["dt"], 1)
+        for k, v in eng.last_times().items():
+            acc[k] = acc.get(k, 0.0) + v / args.steps
+    eng.profile(False)
+
+    # end to end through the host-buffer API: H2D state, advance, D2H state, every step
+    out = eng.download(host=True)
+    host_in = {k: out[k] for k in out}
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    bytes_in = sum(v.numel() * v.element_size() for v in host_in.values())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.upload(host_in)
+        eng.step(meta["dt"], 1)
+        eng.download(out=host_in)  # synchronises the stream
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    if rank != 0:
+        return
+    peaks, which = measured_peaks()
+    per_step_ms = ms / args.steps
+    value = world * n * args.steps / (ms * 1e-3)
+    edges = 93 if dim == 3 else 25  # directed in-range edges per lattice particle incl. self
+    f_ms = acc.get("force", 0.0)
+    f_bytes = BYTES[dim]["force"] * n
+    f_flops = FLOPS_EDGE[dim]["force"] * edges * n
+    roof = {
+        "kernel": "k_sweep<PhysForce> (force sweep)", "bound": "hbm",
+        "achieved": f_bytes / (f_ms * 1e-3) / 1e9 if f_ms else None,
+        "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": which,
+        "frac": (f_bytes / (f_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if f_ms else None,
+        "traffic": None, "ms": f_ms,
+        "note": "FP32-pipe bound, not HBM bound: see fp32",
+        "fp32": {"achieved_tflops": f_flops / (f_ms * 1e-3) / 1e12 if f_ms else None,
+                 "peak_tflops_nominal": FP32_PEAK_TFLOPS,
+                 "frac": (f_flops / (f_ms * 1e-3) / 1e12) / FP32_PEAK_TFLOPS if f_ms else None},
+        "passes_ms": acc,
+    }
+    cpu = cpu_baseline(args, bounded=True)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload} nx={args.nx} N={n} SPH tvf=1 QSK (BASELINE configs[3])",
+                   "particles_per_gpu": n, "parallelism": "1 engine per GPU" if world == 1 else
+                   f"{world} independent periodic boxes (replicas, no halo exchange yet)",
+                   "l2_policy": "state (>1.8 GB) larger than L2", "plan": eng.plan()},
+        "clocks": clocks, "gpu_launches": int(launches), "device_error_word": err,
+        "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": UNIT,
+                "h2d_bytes_per_step": int(bytes_in), "d2h_bytes_per_step": int(bytes_in),
+                "steps": e2e_steps,
+                "what": "Engine.upload(pinned host state) + step + download(host) every step"},
+        "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline(args, bounded=True):
+    """The NumPy oracle (port of the reference algorithm) on the host cores, on a
+    bounded sample of the same workload."""
+    from oracle import cases, integrator
+
+    nx = args.cpu_nx
+    if args.workload == "tgv3d":
+        setup = cases.make_case("tgv", dim=3, dx=2 * np.pi / nx, dtype=np.float32, tvf=1.0,
+                                viscosity=0.02)
+    else:
+        setup = cases.make_case("tgv", dim=2, dx=1.0 / nx, dtype=np.float32, tvf=1.0)
+    n = len(setup.state["r"])
+    steps = args.cpu_steps
+    integrator.simulate(setup, 1, fast_segment_sum=True)
+    t0 = time.perf_counter()
+    integrator.simulate(setup, steps, fast_segment_sum=True)
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{args.workload} nx={nx} N={n}, {steps} steps, NumPy restatement of the "
+                      "reference edge-list algorithm (jax is not installable here), "
+                      f"{dt:.1f} s wall, host has {os.cpu_count()} cores"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cases, integrator
+
+    nx = args.cpu_nx
+    if args.workload == "tgv3d":
+        setup = cases.make_case("tgv", dim=3, dx=2 * np.pi / nx, dtype=np.float32, tvf=1.0,
+                                viscosity=0.02)
+    else:
+        setup = cases.make_case("tgv", dim=2, dx=1.0 / nx, dtype=np.float32, tvf=1.0)
+    n = len(setup.state["r"])
+    sub = max(1, args.cpu_steps // 4)
+    for _ in range(min(args.warmup, 1)):
+        integrator.simulate(setup, 1, fast_segment_sum=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        integrator.simulate(setup, sub, fast_segment_sum=True)
+    dt = time.perf_counter() - t0
+    value = n * sub * args.steps / dt
+    sample = (f"{args.workload} nx={nx} N={n}: each bench step = {sub} advance() calls of the NumPy "
+              "port of the reference algorithm (jax/jaxlib absent, reference not runnable)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload} (bounded sample nx={nx} N={n})"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="tgv3d", choices=["tgv3d", "tgv2d"])
+    ap.add_argument("--nx", type=int, default=256)
+    ap.add_argument("--cpu-nx", type=int, default=32)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--sub", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--list-cap", type=int, default=0)
+    ap.add_argument("--tile-x", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

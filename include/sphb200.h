@@ -54,6 +54,8 @@ extern "C" {
 #define SPHB200_ERR_CELL_OVERFLOW (1u << 1)     /* == PartitionErrorCode.CELL_LIST_OVERFLOW     */
 #define SPHB200_ERR_STAGE_OVERFLOW (1u << 2)    /* one stencil row exceeds the staging buffer   */
 #define SPHB200_ERR_NONFINITE (1u << 3)         /* non-finite position met while hashing        */
+#define SPHB200_ERR_OUTSIDE_BOX (1u << 4)       /* a position outside [0, box]: the periodic    *
+                                                 * fold assumes shift_fn-wrapped positions       */
 
 /* ---- enums --------------------------------------------------------------- */
 enum { SPHB200_SOLVER_SPH = 0, SPHB200_SOLVER_RIE = 1 };  /* solver.py:639-640 (DELTA: unsupported) */

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsphb200.so")
 ABI_VERSION = 1
 OK, EINVAL, ENOMEM, ECUDA, EDTYPE, EUNSUP, ENODEV = 0, -1, -2, -3, -4, -5, -6
 ERR_NEIGHBOR_OVERFLOW, ERR_CELL_OVERFLOW, ERR_STAGE_OVERFLOW, ERR_NONFINITE = 1, 2, 4, 8
+ERR_OUTSIDE_BOX = 16
 SOLVER = {"SPH": 0, "RIE": 1}
 KERNEL = {"QSK": 0, "WC2K": 1}
 EOS_TAIT, EOS_RIEMANN = 0, 1

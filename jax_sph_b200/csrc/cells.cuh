@@ -36,6 +36,9 @@ __global__ void __launch_bounds__(256) k_hash(int n, Grid g, Kick k, const float
     atomicOr(err, SPHB200_ERR_NONFINITE);
     r[0] = r[1] = r[2] = 0.0f;
   }
+  bool inside = r[0] >= 0.f && r[0] <= g.box[0] && r[1] >= 0.f && r[1] <= g.box[1] &&
+                (DIM == 2 || (r[2] >= 0.f && r[2] <= g.box[2]));
+  if (!inside) atomicOr(err, SPHB200_ERR_OUTSIDE_BOX);
   int c[3];
   int cell = cell_of<DIM>(g, r, c);
   key[p] = cell;

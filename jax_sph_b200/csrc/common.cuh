@@ -103,10 +103,22 @@ __device__ __forceinline__ float mod_side(float t, float side) {
 }
 
 // space.py:170-181  periodic_displacement(side, a - b)
+// Both positions lie in [0, side] (k_hash checks and flags SPHB200_ERR_OUTSIDE_BOX
+// otherwise), so t = d + half is in (-side/2, 3 side/2) and jnp.mod reduces to two
+// selects: t - side is exact (Sterbenz), t + side rounds exactly as the fix-up add.
 __device__ __forceinline__ float disp1(float a, float b, float half, float side) {
-  float d = __fsub_rn(a, b);
-  float t = __fadd_rn(d, half);
-  return __fsub_rn(mod_side(t, side), half);
+  const float d = __fsub_rn(a, b);
+  const float t = __fadd_rn(d, half);
+  float m = t;
+  if (t >= side) m = __fsub_rn(t, side);
+  if (t < 0.0f) m = __fadd_rn(t, side);
+  return __fsub_rn(m, half);
+}
+
+// Same value when the minimum image is known to be the direct difference
+// (|d| < half, no periodic wrap between the two particles): 0 <= t < side.
+__device__ __forceinline__ float disp1_nowrap(float a, float b, float half) {
+  return __fsub_rn(__fadd_rn(__fsub_rn(a, b), half), half);
 }
 
 // space.py:184-192 sum of squares, left to right, no FMA contraction.
@@ -189,6 +201,19 @@ __device__ __forceinline__ float kernel_gw(const Consts& c, float r) {
     return c.sigma_ooh * ((-5.0f * q) * ((q1 * q1) * q1));
   }
 }
+
+// Pair-level division / square root.  Default: hardware reciprocal / rsqrt
+// (<= 2 ulp), well inside the float32 summation-order noise of the sweeps
+// (DESIGN.md section 6); -DSPHB200_PRECISE restores IEEE operations.
+#ifdef SPHB200_PRECISE
+__device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
+__device__ __forceinline__ float frcp(float a) { return 1.0f / a; }
+__device__ __forceinline__ float fsqrt(float a) { return sqrtf(a); }
+#else
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float frcp(float a) { return __fdividef(1.0f, a); }
+__device__ __forceinline__ float fsqrt(float a) { return a > 0.0f ? a * rsqrtf(a) : 0.0f; }
+#endif
 
 // eos.py:33-38 / :53-57
 __device__ __forceinline__ float eos_p(const Consts& c, float rho) {

@@ -287,15 +287,15 @@ Extra make_extra() {
   return ex;
 }
 
-#define DISPATCH_DK(e, CALL)                                                   \
-  do {                                                                         \
-    if ((e)->dim == 2) {                                                       \
-      if ((e)->cfg.kernel == SPHB200_KERNEL_QSK) { CALL(2, SPHB200_KERNEL_QSK); } \
-      else { CALL(2, SPHB200_KERNEL_WC2K); }                                   \
-    } else {                                                                   \
-      if ((e)->cfg.kernel == SPHB200_KERNEL_QSK) { CALL(3, SPHB200_KERNEL_QSK); } \
-      else { CALL(3, SPHB200_KERNEL_WC2K); }                                   \
-    }                                                                          \
+#define DISPATCH_DK(e, CALL)                                                       \
+  do {                                                                             \
+    if ((e)->dim == 2) {                                                           \
+      if ((e)->cfg.kernel == SPHB200_KERNEL_QSK) { CALL(2, SPHB200_KERNEL_QSK); }  \
+      else { CALL(2, SPHB200_KERNEL_WC2K); }                                       \
+    } else {                                                                       \
+      if ((e)->cfg.kernel == SPHB200_KERNEL_QSK) { CALL(3, SPHB200_KERNEL_QSK); }  \
+      else { CALL(3, SPHB200_KERNEL_WC2K); }                                       \
+    }                                                                              \
   } while (0)
 
 void swap_st(sphb200_engine* e) {
@@ -417,11 +417,22 @@ int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st)
     SweepPlan sp = plan_sweep(e, nq);
     Frame& F = e->fr[e->cur];
     if (!rie) {
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH>>, sp, F, ex, st)
-      DISPATCH_DK(e, CALL);
+      const int feat = (heat || ex.av) ? FORCE_GENERIC : (v_is_u ? FORCE_PLAIN : FORCE_TVF);
+      if (feat == FORCE_PLAIN) {
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>>, sp, F, ex, st)
+        DISPATCH_DK(e, CALL);
 #undef CALL
+      } else if (feat == FORCE_TVF) {
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF>>, sp, F, ex, st)
+        DISPATCH_DK(e, CALL);
+#undef CALL
+      } else {
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_GENERIC>>, sp, F, ex, st)
+        DISPATCH_DK(e, CALL);
+#undef CALL
+      }
     } else {
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_RIE>>, sp, F, ex, st)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_RIE, FORCE_GENERIC>>, sp, F, ex, st)
       DISPATCH_DK(e, CALL);
 #undef CALL
     }
@@ -506,7 +517,7 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   CK(cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   e->max_smem = maxs - 1024;
   e->tpb = cfg->threads > 0 ? (cfg->threads + 31) / 32 * 32 : 128;
-  if (e->tpb > 256) e->tpb = 256;
+  if (e->tpb > 512) e->tpb = 512;
   e->lcap = cfg->list_cap > 0 ? cfg->list_cap : 96;
   if (e->lcap < SWEEP_CHUNK) e->lcap = SWEEP_CHUNK;
   plan_grid(*cfg, e->grid, e->tpb);

@@ -12,11 +12,13 @@
 //                 :404-428 artificial viscosity, :591-610 heat conduction,
 //                 integrator.py:54 case bc_fn (table form, dudt/dvdt/dTdt part)
 //   PhysNeighbors jax_md/partition.py:885-909  sparse list materialiser (parity / drop-in .idx)
+//
+// Registers held across the pair loop are kept to what pair() reads; finish()
+// re-reads the rest of the particle from global memory.
 #pragma once
 #include "common.cuh"
 
 namespace sphb200 {
-
 
 __device__ __forceinline__ float dot3(const float (&a)[3], const float (&b)[3], int dim) {
   float s = a[0] * b[0] + a[1] * b[1];
@@ -29,43 +31,43 @@ enum { DENS_SUM = 0, DENS_EVOL_SPH = 1, DENS_EVOL_RIE = 2 };
 
 template <int DIM, int KERN, int MODE>
 struct PhysDensity {
-  static constexpr int NQ = 4;
+  static constexpr int MINB = (MODE == DENS_EVOL_RIE) ? 1 : 2;
   static constexpr bool SENDER_VIEW = false;
   struct Own {
     float u[3], g[3];
-    float rho, p, T, dTdt, mass;
-    int tag;
+    float rho, p;
   };
   struct Acc {
-    float s;            // sum w  |  continuity sum
-    float swf, sT;      // RIE wall helpers
+    float s;        // sum w  |  continuity sum
+    float swf, sT;  // RIE wall helpers
     float su[3];
   };
-  __device__ static void load_stage(const Consts& c, const Frame& f, const Extra& ex, int gp,
-                                    float4 (&q)[NQ]) {
-    q[0] = f.pt[gp];
+  __device__ static void stage(const Consts& c, const Frame& f, const Extra& ex, int gp,
+                               float4* sq, int cap, int d) {
+    sq[d] = f.pt[gp];
     if (MODE == DENS_SUM) {
       if (ex.nq > 1) {
-        q[1] = f.um[gp];
-        q[2] = f.st[gp];
+        sq[cap + d] = f.um[gp];
+        sq[2 * cap + d] = f.st[gp];
       }
     } else if (MODE == DENS_EVOL_SPH) {
       float4 um = f.um[gp], st = f.st[gp];
-      q[1] = make_float4(um.x, um.y, um.z, um.w / st.x);  // (mass / rho)[j], solver.py:26
+      sq[cap + d] = make_float4(um.x, um.y, um.z, um.w / st.x);  // (mass / rho)[j], solver.py:26
     } else {
-      q[1] = f.um[gp];
-      q[2] = f.st[gp];
-      q[3] = f.nw ? f.nw[gp] : make_float4(0.f, 0.f, 0.f, 0.f);
+      sq[cap + d] = f.um[gp];
+      sq[2 * cap + d] = f.st[gp];
+      sq[3 * cap + d] = f.nw ? f.nw[gp] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   __device__ static void load_own(const Consts& c, const Frame& f, const Extra& ex, int p,
                                   float4 pt, Own& o) {
-    float4 um = f.um[p], st = f.st[p];
-    o.u[0] = um.x; o.u[1] = um.y; o.u[2] = um.z;
-    o.mass = um.w;
-    o.rho = st.x; o.p = st.y; o.T = st.z; o.dTdt = st.w;
-    o.tag = __float_as_int(pt.w);
+    if (MODE != DENS_SUM) {
+      float4 um = f.um[p];
+      o.u[0] = um.x; o.u[1] = um.y; o.u[2] = um.z;
+    }
     if (MODE == DENS_EVOL_RIE) {
+      float4 st = f.st[p];
+      o.rho = st.x; o.p = st.y;
       float r[3] = {pt.x, pt.y, pt.z};
       g_ext_of<DIM>(c, f, p, r, o.g);
     }
@@ -78,7 +80,7 @@ struct PhysDensity {
   __device__ static void pair(const Consts& c, const Extra& ex, const Own& o, Acc& a,
                               const float4* sq, int cap, int j, float4 pj, const float (&dr)[3],
                               float d2) {
-    const float dist = sqrtf(d2);
+    const float dist = fsqrt(d2);
     const int tag_j = __float_as_int(pj.w);
     if (MODE == DENS_SUM || ex.utilde || ex.wallT) {
       const float w = kernel_w<KERN>(c, dist);
@@ -96,17 +98,17 @@ struct PhysDensity {
     if (MODE == DENS_EVOL_SPH) {
       const float4 uj = sq[cap + j];
       const float gw = kernel_gw<KERN>(c, dist);
-      const float den = dist + c.eps;
-      float s = (o.u[0] - uj.x) * (gw * (dr[0] / den)) + (o.u[1] - uj.y) * (gw * (dr[1] / den));
-      if (DIM == 3) s += (o.u[2] - uj.z) * (gw * (dr[2] / den));
+      const float id = frcp(dist + c.eps);
+      float s = (o.u[0] - uj.x) * (gw * (dr[0] * id)) + (o.u[1] - uj.y) * (gw * (dr[1] * id));
+      if (DIM == 3) s += (o.u[2] - uj.z) * (gw * (dr[2] * id));
       a.s += uj.w * s;
     }
     if (MODE == DENS_EVOL_RIE) {
       const float4 uj4 = sq[cap + j], sj = sq[2 * cap + j], nj4 = sq[3 * cap + j];
       const float uj[3] = {uj4.x, uj4.y, uj4.z}, nwj[3] = {nj4.x, nj4.y, nj4.z};
       const float gw = kernel_gw<KERN>(c, dist);
-      const float den = dist + c.eps;
-      float e[3] = {dr[0] / den, dr[1] / den, DIM == 3 ? dr[2] / den : 0.f};
+      const float id = frcp(dist + c.eps);
+      float e[3] = {dr[0] * id, dr[1] * id, DIM == 3 ? dr[2] * id : 0.f};
       float kg[3] = {gw * e[0], gw * e[1], gw * e[2]};
       const bool is_w = is_wall_tag(tag_j);
       float ne[3] = {-e[0], -e[1], -e[2]}, nn[3] = {-nwj[0], -nwj[1], -nwj[2]};
@@ -118,7 +120,7 @@ struct PhysDensity {
       const float rho_R = is_w ? eos_rho(c, p_R) : sj.x;
       const float U_avg = (u_L + u_R) / 2.0f;
       const float rho_avg = (rho_L + rho_R) / 2.0f;
-      const float U_star = U_avg + 0.5f * (p_L - p_R) / (rho_avg * c.c_ref);
+      const float U_star = U_avg + fdiv(0.5f * (p_L - p_R), rho_avg * c.c_ref);
       float s = 0.f;
 #pragma unroll
       for (int k = 0; k < DIM; ++k) {
@@ -126,28 +128,30 @@ struct PhysDensity {
         const float v_star = U_star * ne[k] + (v_avg - U_avg * ne[k]);
         s += (o.u[k] - v_star) * kg[k];
       }
-      a.s += 2.0f * o.rho * uj4.w / sj.x * s;
+      a.s += fdiv(2.0f * o.rho * uj4.w, sj.x) * s;
     }
   }
   __device__ static void finish(const Consts& c, const Frame& f, const Extra& ex, int p,
-                                const Own& o, const Acc& a) {
+                                const Own&, const Acc& a) {
+    const float4 st = f.st[p];
+    const int tag = __float_as_int(f.pt[p].w);
     float rho, drhodt = 0.f;
     if (MODE == DENS_SUM) {
-      const float rho_ = o.mass * a.s;
-      rho = (o.tag == SPHB200_TAG_FLUID) ? rho_ : o.rho;  // solver.py:795-796
+      const float rho_ = f.um[p].w * a.s;
+      rho = (tag == SPHB200_TAG_FLUID) ? rho_ : st.x;  // solver.py:795-796
     } else if (MODE == DENS_EVOL_SPH) {
-      drhodt = o.rho * a.s;           // :28
-      rho = o.rho + c.dt_s * drhodt;  // :29
+      drhodt = st.x * a.s;           // :28
+      rho = st.x + c.dt_s * drhodt;  // :29
     } else {
-      drhodt = a.s * ((o.tag == SPHB200_TAG_FLUID) ? 1.0f : 0.0f);  // :789
-      rho = o.rho + c.dt_s * drhodt;                             // :790
+      drhodt = a.s * ((tag == SPHB200_TAG_FLUID) ? 1.0f : 0.0f);  // :789
+      rho = st.x + c.dt_s * drhodt;                               // :790
     }
     const float pnew = eos_p(c, rho);  // :801
-    float T = o.T;
-    if (ex.wallT && (o.tag == SPHB200_TAG_SOLID_WALL || o.tag == SPHB200_TAG_MOVING_WALL))
+    float T = st.z;
+    if (ex.wallT && (tag == SPHB200_TAG_SOLID_WALL || tag == SPHB200_TAG_MOVING_WALL))
       T = a.sT / (a.swf + c.eps);  // :556-565
-    if (ex.finalT) T = T + c.dt_s * o.dTdt;  // :834
-    ex.st_out[p] = make_float4(rho, pnew, T, o.dTdt);
+    if (ex.finalT) T = T + c.dt_s * st.w;  // :834
+    ex.st_out[p] = make_float4(rho, pnew, T, st.w);
     if (MODE != DENS_SUM) reinterpret_cast<float*>(&f.du[p])[3] = drhodt;
     if (ex.utilde) {
       const float den = a.swf + c.eps;  // :547-552
@@ -159,77 +163,59 @@ struct PhysDensity {
 // ---------------------------------------------------------------------------
 template <int DIM, int KERN>
 struct PhysRenorm {
-  static constexpr int NQ = 2;
+  static constexpr int MINB = 2;
   static constexpr bool SENDER_VIEW = false;
-  struct Own {
-    float4 st;
-  };
+  struct Own {};
   struct Acc {
     float num, den;
   };
-  __device__ static void load_stage(const Consts&, const Frame& f, const Extra&, int gp,
-                                    float4 (&q)[NQ]) {
-    q[0] = f.pt[gp];
+  __device__ static void stage(const Consts&, const Frame& f, const Extra&, int gp, float4* sq,
+                               int cap, int d) {
+    sq[d] = f.pt[gp];
     const float m = f.um[gp].w, rho = f.st[gp].x;
-    q[1] = make_float4(m, m / rho, 0.f, 0.f);
+    sq[cap + d] = make_float4(m, m / rho, 0.f, 0.f);
   }
-  __device__ static void load_own(const Consts&, const Frame& f, const Extra&, int p, float4,
-                                  Own& o) {
-    o.st = f.st[p];
-  }
+  __device__ static void load_own(const Consts&, const Frame&, const Extra&, int, float4, Own&) {}
   __device__ static bool active(const Consts&, const Own&) { return true; }
   __device__ static void init(Acc& a) { a.num = a.den = 0.f; }
   __device__ static void pair(const Consts& c, const Extra&, const Own&, Acc& a, const float4* sq,
                               int cap, int j, float4, const float (&)[3], float d2) {
-    const float w = kernel_w<KERN>(c, sqrtf(d2));
+    const float w = kernel_w<KERN>(c, fsqrt(d2));
     const float4 mj = sq[cap + j];
     a.num += mj.x * w;
     a.den += mj.y * w;
   }
-  __device__ static void finish(const Consts& c, const Frame&, const Extra& ex, int p,
-                                const Own& o, const Acc& a) {
+  __device__ static void finish(const Consts& c, const Frame& f, const Extra& ex, int p,
+                                const Own&, const Acc& a) {
+    const float4 st = f.st[p];
     const float den = a.den > 1.0f ? 1.0f : a.den;
     const float rho = a.num / den;
-    ex.st_out[p] = make_float4(rho, eos_p(c, rho), o.st.z, o.st.w);
+    ex.st_out[p] = make_float4(rho, eos_p(c, rho), st.z, st.w);
   }
 };
 
 // ---------------------------------------------------------------------------
 template <int DIM, int KERN>
 struct PhysWall {
-  static constexpr int NQ = 4;
+  static constexpr int MINB = 1;
   static constexpr bool SENDER_VIEW = false;
   struct Own {
-    float u[3], v[3], g[3], nw[3];
-    float4 st;
-    float mass, eta;
     int tag;
   };
   struct Acc {
     float sw, sp, sT;
     float su[3], sv[3], srr[3];
   };
-  __device__ static void load_stage(const Consts&, const Frame& f, const Extra&, int gp,
-                                    float4 (&q)[NQ]) {
-    q[0] = f.pt[gp];
-    q[1] = f.um[gp];
-    q[2] = f.vv[gp];
-    q[3] = f.st[gp];
+  __device__ static void stage(const Consts&, const Frame& f, const Extra&, int gp, float4* sq,
+                               int cap, int d) {
+    sq[d] = f.pt[gp];
+    sq[cap + d] = f.um[gp];
+    sq[2 * cap + d] = f.vv[gp];
+    sq[3 * cap + d] = f.st[gp];
   }
-  __device__ static void load_own(const Consts& c, const Frame& f, const Extra& ex, int p,
-                                  float4 pt, Own& o) {
-    float4 um = f.um[p], vv = f.vv[p];
-    o.u[0] = um.x; o.u[1] = um.y; o.u[2] = um.z; o.mass = um.w;
-    o.v[0] = vv.x; o.v[1] = vv.y; o.v[2] = vv.z; o.eta = vv.w;
-    o.st = f.st[p];
+  __device__ static void load_own(const Consts&, const Frame&, const Extra&, int, float4 pt,
+                                  Own& o) {
     o.tag = __float_as_int(pt.w);
-    float r[3] = {pt.x, pt.y, pt.z};
-    g_ext_of<DIM>(c, f, p, r, o.g);
-    o.nw[0] = o.nw[1] = o.nw[2] = 0.f;
-    if (ex.free_slip && f.nw) {
-      float4 n = f.nw[p];
-      o.nw[0] = n.x; o.nw[1] = n.y; o.nw[2] = n.z;
-    }
   }
   // only wall particles need the Shepard sums (everything else is discarded by the
   // jnp.where(mask_bc, ...) of solver.py:461,485,514)
@@ -242,7 +228,7 @@ struct PhysWall {
   __device__ static void pair(const Consts& c, const Extra&, const Own&, Acc& a, const float4* sq,
                               int cap, int j, float4 pj, const float (&dr)[3], float d2) {
     if (__float_as_int(pj.w) != SPHB200_TAG_FLUID) return;  // w * mask_j_s_fluid == 0
-    const float w = kernel_w<KERN>(c, sqrtf(d2));
+    const float w = kernel_w<KERN>(c, fsqrt(d2));
     const float4 uj = sq[cap + j], vj = sq[2 * cap + j], sj = sq[3 * cap + j];
     a.sw += w;
     a.su[0] += w * uj.x; a.su[1] += w * uj.y; a.su[2] += w * uj.z;
@@ -255,8 +241,13 @@ struct PhysWall {
   __device__ static void finish(const Consts& c, const Frame& f, const Extra& ex, int p,
                                 const Own& o, const Acc& a) {
     const bool wall = is_wall_tag(o.tag);
-    float p_new = o.st.y, T = o.st.z;
+    const float4 st = f.st[p];
+    float p_new = st.y, T = st.z;
     if (wall) {
+      const float4 pt = f.pt[p], um = f.um[p], vv = f.vv[p];
+      const float u[3] = {um.x, um.y, um.z}, v[3] = {vv.x, vv.y, vv.z};
+      float r[3] = {pt.x, pt.y, pt.z}, g[3];
+      g_ext_of<DIM>(c, f, p, r, g);
       const float den = a.sw + c.eps;
       float uw[3], vw[3];
 #pragma unroll
@@ -265,7 +256,8 @@ struct PhysWall {
         vw[k] = a.sv[k] / den;
       }
       if (ex.free_slip) {  // :464-486, wall_inner_normals = -nw
-        float win[3] = {-o.nw[0], -o.nw[1], -o.nw[2]};
+        float4 n = f.nw ? f.nw[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float win[3] = {-n.x, -n.y, -n.z};
         float su = dot3(uw, win, DIM), sv = dot3(vw, win, DIM);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -273,65 +265,81 @@ struct PhysWall {
           vw[k] = win[k] * sv;
         }
       }
-      f.um[p] = make_float4(2.0f * o.u[0] - uw[0], 2.0f * o.u[1] - uw[1],
-                            DIM == 3 ? 2.0f * o.u[2] - uw[2] : 0.f, o.mass);
-      f.vv[p] = make_float4(2.0f * o.v[0] - vw[0], 2.0f * o.v[1] - vw[1],
-                            DIM == 3 ? 2.0f * o.v[2] - vw[2] : 0.f, o.eta);
-      const float p_ext = dot3(o.g, a.srr, DIM);  // :509-511
-      p_new = (a.sp + p_ext) / den;               // :513
+      f.um[p] = make_float4(2.0f * u[0] - uw[0], 2.0f * u[1] - uw[1],
+                            DIM == 3 ? 2.0f * u[2] - uw[2] : 0.f, um.w);
+      f.vv[p] = make_float4(2.0f * v[0] - vw[0], 2.0f * v[1] - vw[1],
+                            DIM == 3 ? 2.0f * v[2] - vw[2] : 0.f, vv.w);
+      const float p_ext = dot3(g, a.srr, DIM);  // :509-511
+      p_new = (a.sp + p_ext) / den;             // :513
       if (ex.heat && (o.tag == SPHB200_TAG_SOLID_WALL || o.tag == SPHB200_TAG_MOVING_WALL))
         T = a.sT / den;  // :518-526
     }
     const float rho = eos_rho(c, p_new);  // :516, every particle
-    if (ex.heat) T = T + c.dt_s * o.st.w;  // :834
-    ex.st_out[p] = make_float4(rho, p_new, T, o.st.w);
+    if (ex.heat) T = T + c.dt_s * st.w;   // :834
+    ex.st_out[p] = make_float4(rho, p_new, T, st.w);
   }
 };
 
 // ---------------------------------------------------------------------------
 // Force sweep.  Staged quads: 0 (x,y,z,tag) 1 (u, rho) 2 (p, eta, mass, (m/rho)^2)
 // [q_v] (v, 0)  [q_h] (T, kappa, 0, 0)  [q_nw] (nw, 0)  [q_ut] (u_tilde, 0)
-template <int DIM, int KERN, int SOLVER>
+// FEAT: compile-time specialisation of the two headline variants; GENERIC reads
+// the switches from Extra at run time.
+enum { FORCE_PLAIN = 0, FORCE_TVF = 1, FORCE_GENERIC = 2 };
+
+template <int DIM, int KERN, int SOLVER, int FEAT>
 struct PhysForce {
-  static constexpr int NQ = 7;
+  static constexpr int MINB = 1;
   static constexpr bool SENDER_VIEW = false;
   struct Own {
-    float u[3], v[3], g[3];
-    float rho, p, eta, mass, V2, T, kappa, Cp;
+    float u[3], dvu[3], g[3];
+    float rho, p, eta, inv_m, V2, T, kappa, Cp;
     int tag;
   };
   struct Acc {
     float a[3], tv[3], av[3];
     float dT;
   };
-  __device__ static void load_stage(const Consts&, const Frame& f, const Extra& ex, int gp,
-                                    float4 (&q)[NQ]) {
+  __device__ static int qv(const Extra& ex) {
+    return FEAT == FORCE_PLAIN ? -1 : (FEAT == FORCE_TVF ? 3 : ex.q_v);
+  }
+  __device__ static void stage(const Consts&, const Frame& f, const Extra& ex, int gp, float4* sq,
+                               int cap, int d) {
     const float4 um = f.um[gp], st = f.st[gp], vv = f.vv[gp];
-    q[0] = f.pt[gp];
-    q[1] = make_float4(um.x, um.y, um.z, st.x);
+    sq[d] = f.pt[gp];
+    sq[cap + d] = make_float4(um.x, um.y, um.z, st.x);
     const float vol = um.w / st.x;
-    q[2] = make_float4(st.y, vv.w, um.w, vol * vol);
-    if (ex.q_v >= 0) q[ex.q_v] = vv;
-    if (ex.q_h >= 0) q[ex.q_h] = make_float4(st.z, f.kc[gp].x, 0.f, 0.f);
-    if (ex.q_nw >= 0) q[ex.q_nw] = f.nw ? f.nw[gp] : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ex.q_ut >= 0) q[ex.q_ut] = f.ut[gp];
+    sq[2 * cap + d] = make_float4(st.y, vv.w, um.w, vol * vol);
+    if (qv(ex) >= 0) sq[qv(ex) * cap + d] = make_float4(vv.x - um.x, vv.y - um.y, vv.z - um.z, 0.f);
+    if (FEAT == FORCE_GENERIC) {
+      if (ex.q_h >= 0) sq[ex.q_h * cap + d] = make_float4(st.z, f.kc[gp].x, 0.f, 0.f);
+      if (ex.q_nw >= 0) sq[ex.q_nw * cap + d] = f.nw ? f.nw[gp] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ex.q_ut >= 0) sq[ex.q_ut * cap + d] = f.ut[gp];
+    }
   }
   __device__ static void load_own(const Consts& c, const Frame& f, const Extra& ex, int p,
                                   float4 pt, Own& o) {
     const float4 um = f.um[p], st = f.st[p], vv = f.vv[p];
-    o.u[0] = um.x; o.u[1] = um.y; o.u[2] = um.z; o.mass = um.w;
-    o.v[0] = vv.x; o.v[1] = vv.y; o.v[2] = vv.z; o.eta = vv.w;
+    o.u[0] = um.x; o.u[1] = um.y; o.u[2] = um.z;
+    o.dvu[0] = vv.x - um.x; o.dvu[1] = vv.y - um.y; o.dvu[2] = vv.z - um.z;
+    o.eta = vv.w;
     o.rho = st.x; o.p = st.y; o.T = st.z;
     const float vol = um.w / st.x;
     o.V2 = vol * vol;
+    o.inv_m = 1.0f / um.w;
     o.tag = __float_as_int(pt.w);
     o.kappa = 0.f; o.Cp = 1.f;
-    if (ex.heat) {
-      float2 kc = f.kc[p];
-      o.kappa = kc.x; o.Cp = kc.y;
+    o.g[0] = o.g[1] = o.g[2] = 0.f;
+    if (FEAT == FORCE_GENERIC) {
+      if (ex.heat) {
+        float2 kc = f.kc[p];
+        o.kappa = kc.x; o.Cp = kc.y;
+      }
+      if (SOLVER == SPHB200_SOLVER_RIE) {
+        float r[3] = {pt.x, pt.y, pt.z};
+        g_ext_of<DIM>(c, f, p, r, o.g);
+      }
     }
-    float r[3] = {pt.x, pt.y, pt.z};
-    g_ext_of<DIM>(c, f, p, r, o.g);
   }
   __device__ static bool active(const Consts&, const Own&) { return true; }
   __device__ static void init(Acc& a) {
@@ -346,34 +354,33 @@ struct PhysForce {
     const float uj[3] = {q1.x, q1.y, q1.z};
     const float rho_j = q1.w, p_j = q2.x, eta_j = q2.y, m_j = q2.z, V2_j = q2.w;
     const int tag_j = __float_as_int(pj.w);
-    const float dist = sqrtf(d2);
+    const float dist = fsqrt(d2);
     const float gw = kernel_gw<KERN>(c, dist);
-    const float den = dist + c.eps;
-    const float wv = (o.V2 + V2_j) / o.mass;                                 // :205 / :247
-    const float cc = wv * gw / den;                                          // :206 / :248
-    const float eta_ij = 2.0f * o.eta * eta_j / (o.eta + eta_j + c.eps);    // :243
+    const float id = frcp(dist + c.eps);
+    const float wv = (o.V2 + V2_j) * o.inv_m;                                // :205 / :247
+    const float cc = wv * gw * id;                                           // :206 / :248
+    const float eta_ij = fdiv(2.0f * o.eta * eta_j, o.eta + eta_j + c.eps);  // :243
     // transport-velocity acceleration, always computed (:912-921)
-    const float ct = cc * 1.0f * c.p_bg_tvf;
+    const float ct = cc * c.p_bg_tvf;
 #pragma unroll
     for (int k = 0; k < DIM; ++k) a.tv[k] += ct * dr[k];
 
     if (SOLVER == SPHB200_SOLVER_SPH) {
-      const float p_ij = (rho_j * o.p + o.rho * p_j) / (o.rho + rho_j);  // :244
+      const float p_ij = fdiv(rho_j * o.p + o.rho * p_j, o.rho + rho_j);  // :244
       float si = 0.f, sj = 0.f;
-      if (ex.q_v >= 0) {
-        const float4 vj = sq[ex.q_v * cap + j];
-        const float dvi[3] = {o.v[0] - o.u[0], o.v[1] - o.u[1], o.v[2] - o.u[2]};
-        const float dvj[3] = {vj.x - uj[0], vj.y - uj[1], vj.z - uj[2]};
-        si = dot3(dvi, dr, DIM);
+      if (qv(ex) >= 0) {
+        const float4 dj = sq[qv(ex) * cap + j];
+        const float dvj[3] = {dj.x, dj.y, dj.z};
+        si = dot3(o.dvu, dr, DIM);
         sj = dot3(dvj, dr, DIM);
       }
 #pragma unroll
       for (int k = 0; k < DIM; ++k) {
-        const float A = ((o.rho * o.u[k]) * si + (rho_j * uj[k]) * sj) / 2.0f;  // :250-251
+        const float A = ((o.rho * o.u[k]) * si + (rho_j * uj[k]) * sj) * 0.5f;  // :250-251
         a.a[k] += cc * ((-p_ij * dr[k] + A) + eta_ij * (o.u[k] - uj[k]));       // :254
       }
     } else {
-      float e[3] = {dr[0] / den, dr[1] / den, DIM == 3 ? dr[2] / den : 0.f};
+      float e[3] = {dr[0] * id, dr[1] * id, DIM == 3 ? dr[2] * id : 0.f};
       float ne[3] = {-e[0], -e[1], -e[2]};
       const bool is_w = is_wall_tag(tag_j);
       float nwj[3] = {0.f, 0.f, 0.f}, ud[3] = {uj[0], uj[1], uj[2]};
@@ -396,46 +403,51 @@ struct PhysForce {
       float beta = c.c_ref;  // :574-588
       if (c.use_lim) beta = fminf(c.eta_lim * fmaxf(u_L - u_R, 0.0f), c.c_ref);
       const float P_star = P_avg + 0.5f * rho_avg * (u_L - u_R) * beta;  // :371
-      const float rr = o.rho * rho_j;
-      const float c9 = -2.0f * m_j * (P_star / rr);                      // :374
-      const float c6 = 2.0f * m_j * eta_ij / rr;                         // :380-386
+      const float irr = frcp(o.rho * rho_j);
+      const float c9 = -2.0f * m_j * (P_star * irr);  // :374
+      const float c6 = 2.0f * m_j * eta_ij * irr;     // :380-386
       float mask = 1.0f;
       if (ex.bc_trick && ex.free_slip) mask = (o.tag == SPHB200_TAG_FLUID) ? 1.0f : 0.0f;
       const float gm = gw * mask;
 #pragma unroll
       for (int k = 0; k < DIM; ++k) {
         const float vij = is_w ? (o.u[k] - ud[k]) : (o.u[k] - uj[k]);
-        a.a[k] += c9 * (gw * e[k]) + (c6 * vij / den) * gm;
+        a.a[k] += c9 * (gw * e[k]) + (c6 * vij * id) * gm;
       }
     }
-    if (ex.av) {  // :404-428
-      if (o.tag == SPHB200_TAG_FLUID && tag_j == SPHB200_TAG_FLUID) {
-        const float rho_ab = (o.rho + rho_j) / 2.0f;
-        const float du[3] = {o.u[0] - uj[0], o.u[1] - uj[1], o.u[2] - uj[2]};
-        const float num = (m_j * c.av_coef) * dot3(du, dr, DIM);
-        const float dd = rho_ab * (dist * dist + c.av_eps);
+    if (FEAT == FORCE_GENERIC) {
+      if (ex.av) {  // :404-428
+        if (o.tag == SPHB200_TAG_FLUID && tag_j == SPHB200_TAG_FLUID) {
+          const float rho_ab = (o.rho + rho_j) / 2.0f;
+          const float du[3] = {o.u[0] - uj[0], o.u[1] - uj[1], o.u[2] - uj[2]};
+          const float num = (m_j * c.av_coef) * dot3(du, dr, DIM);
+          const float idd = frcp(rho_ab * (dist * dist + c.av_eps));
 #pragma unroll
-        for (int k = 0; k < DIM; ++k) a.av[k] += num * (gw * (dr[k] / den)) / dd;
+          for (int k = 0; k < DIM; ++k) a.av[k] += num * (gw * (dr[k] * id)) * idd;
+        }
       }
-    }
-    if (ex.heat) {  // :591-610
-      const float4 hj = sq[ex.q_h * cap + j];
-      const float eff = (o.kappa * hj.y) / (o.kappa + hj.y);
-      float rk = 0.f;
+      if (ex.heat) {  // :591-610
+        const float4 hj = sq[ex.q_h * cap + j];
+        const float eff = fdiv(o.kappa * hj.y, o.kappa + hj.y);
+        float rk = 0.f;
 #pragma unroll
-      for (int k = 0; k < DIM; ++k) rk += dr[k] * (gw * (dr[k] / den));
-      const float F = rk / (dist * dist + c.eps);
-      a.dT += (4.0f * m_j * eff * (o.T - hj.x) * F) / (o.Cp * o.rho * rho_j);
+        for (int k = 0; k < DIM; ++k) rk += dr[k] * (gw * (dr[k] * id));
+        const float F = fdiv(rk, dist * dist + c.eps);
+        a.dT += fdiv(4.0f * m_j * eff * (o.T - hj.x) * F, o.Cp * o.rho * rho_j);
+      }
     }
   }
   __device__ static void finish(const Consts& c, const Frame& f, const Extra& ex, int p,
                                 const Own& o, const Acc& a) {
+    const float4 pt = f.pt[p];
+    float r[3] = {pt.x, pt.y, pt.z}, g[3];
+    g_ext_of<DIM>(c, f, p, r, g);
     float du[3], dv[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       float s = a.a[k];
-      if (ex.av) s = s + a.av[k];  // :925-928
-      du[k] = s + o.g[k];          // :936
+      if (FEAT == FORCE_GENERIC && ex.av) s = s + a.av[k];  // :925-928
+      du[k] = s + g[k];                                     // :936
       dv[k] = a.tv[k];
     }
     float dTdt = a.dT;
@@ -446,15 +458,14 @@ struct PhysForce {
       if (fl & SPHB200_BC_ZERO_DVDT) dv[0] = dv[1] = dv[2] = 0.f;
       if (fl & SPHB200_BC_ZERO_DTDT) dTdt = 0.f;
       if (o.tag == SPHB200_TAG_FLUID) {
-        const float x = f.pt[p].x;
-        if (c.inflow_on && x < c.inflow_x) dTdt = 0.f;
-        if (c.outflow_on && x > c.outflow_x) dTdt = 0.f;
+        if (c.inflow_on && pt.x < c.inflow_x) dTdt = 0.f;
+        if (c.outflow_on && pt.x > c.outflow_x) dTdt = 0.f;
       }
     }
     const float drhodt = f.du[p].w;
     f.du[p] = make_float4(du[0], du[1], DIM == 3 ? du[2] : 0.f, drhodt);
     f.dv[p] = make_float4(dv[0], dv[1], DIM == 3 ? dv[2] : 0.f, 0.f);
-    if (ex.heat) reinterpret_cast<float*>(&f.st[p])[3] = dTdt;
+    if (FEAT == FORCE_GENERIC && ex.heat) reinterpret_cast<float*>(&f.st[p])[3] = dTdt;
   }
 };
 
@@ -492,7 +503,7 @@ __global__ void __launch_bounds__(256) k_bc(int n, Consts c, Frame f) {
 // then (after an exclusive scan over senders in original order) fill.
 template <int DIM>
 struct PhysNeighbors {
-  static constexpr int NQ = 2;
+  static constexpr int MINB = 2;
   static constexpr bool SENDER_VIEW = true;
   struct Own {
     int id;
@@ -501,10 +512,10 @@ struct PhysNeighbors {
   struct Acc {
     int n;
   };
-  __device__ static void load_stage(const Consts&, const Frame& f, const Extra&, int gp,
-                                    float4 (&q)[NQ]) {
-    q[0] = f.pt[gp];
-    q[1] = make_float4(__int_as_float(f.id[gp]), 0.f, 0.f, 0.f);
+  __device__ static void stage(const Consts&, const Frame& f, const Extra&, int gp, float4* sq,
+                               int cap, int d) {
+    sq[d] = f.pt[gp];
+    sq[cap + d] = make_float4(__int_as_float(f.id[gp]), 0.f, 0.f, 0.f);
   }
   __device__ static void load_own(const Consts&, const Frame& f, const Extra& ex, int p, float4,
                                   Own& o) {

@@ -6,7 +6,7 @@
 //
 // One thread block owns a tile of T[0] x T[1] x T[2] cells.  It
 //   1. stages the particles of the tile's stencil (tile + S cells each side)
-//      into shared memory with coalesced float4 loads, NQ quads per particle;
+//      into shared memory with coalesced float4 loads, nq quads per particle;
 //   2. phase 1: every thread walks ITS OWN (2S+1)^d window of the staged cells
 //      with a cheap squared-distance test (no periodic fold: the image shift is
 //      applied once per row/segment to the thread's own coordinates) and appends
@@ -16,8 +16,9 @@
 //      float32 arithmetic (space.py:170-181) and, inside the rounding band
 //      around the cutoff, the reference's membership metric d(r_j, r_i) < cutoff^2
 //      (jax_md/partition.py:897), so the neighbour SET is the reference's, bit for bit.
-// The physics (what is accumulated per pair, what is written per particle) is a
-// policy class P, see phys.cuh.
+// Phase 1 and phase 2 each exist at exactly one code site (the hot loops must
+// stay inside the instruction cache).  The physics (what is accumulated per
+// pair, what is written per particle) is a policy class P, see phys.cuh.
 #pragma once
 #include "common.cuh"
 
@@ -25,29 +26,27 @@ namespace sphb200 {
 
 constexpr int MAX_RUNS = 16;     // T[1]*T[2] upper bound
 constexpr int MAX_SOFF = 1023;   // staged (row, cell) entries upper bound
-constexpr int SWEEP_CHUNK = 32;  // phase-1 candidates between list-room checks
+constexpr int SWEEP_CHUNK = 16;  // phase-1 candidates between list-room checks
+constexpr int SWEEP_MAXT = 512;  // largest block size the kernels are compiled for
 
 struct SweepDims {
   int cap;   // staged particles per block
   int lcap;  // list entries per thread (>= SWEEP_CHUNK)
-  int nq;    // quads staged per particle (<= P::NQ)
+  int nq;    // quads staged per particle
 };
 
 __host__ __device__ inline size_t sweep_smem_bytes(int nq, int cap, int lcap, int tpb) {
   return (size_t)nq * cap * 16 + (size_t)lcap * tpb * 2 + (MAX_SOFF + 1 + 2 * MAX_RUNS + 2) * 4;
 }
 
-__device__ __forceinline__ int wrap_cell(int u, int n) {
-  int m = u % n;
-  return m < 0 ? m + n : m;
-}
-__device__ __forceinline__ int floor_div(int u, int n) { return (u >= 0) ? (u / n) : -((-u + n - 1) / n); }
+// unwrapped cell index u in [-n, 2n)  ->  periodic image count / wrapped index
+__device__ __forceinline__ int wrap_count(int u, int n) { return u < 0 ? -1 : (u >= n ? 1 : 0); }
+__device__ __forceinline__ int wrap_cell(int u, int n) { return u < 0 ? u + n : (u >= n ? u - n : u); }
 
 template <int DIM, class P>
-__global__ void __launch_bounds__(256) k_sweep(const Grid g, const Consts c, const Frame f,
-                                               const int* __restrict__ cs, const SweepDims sd,
-                                               const Extra ex,
-                                               unsigned* __restrict__ err) {
+__global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
+    k_sweep(const Grid g, const Consts c, const Frame f, const int* __restrict__ cs,
+            const SweepDims sd, const Extra ex, unsigned* __restrict__ err) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int TPB = blockDim.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = TPB >> 5;
@@ -65,6 +64,7 @@ __global__ void __launch_bounds__(256) k_sweep(const Grid g, const Consts c, con
   const int tz = b / g.nt[1];
   int c0[3] = {tx * g.T[0], ty * g.T[1], tz * g.T[2]};
   int no[3], sa0[3], slen[3];
+  bool interior = true;  // no periodic image inside this tile's stencil
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     no[a] = min(g.T[a], g.n[a] - c0[a]);
@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(256) k_sweep(const Grid g, const Consts c, con
       sa0[a] = 0;
       slen[a] = g.n[a];
     }
+    interior = interior && (a >= DIM || (sa0[a] >= 0 && sa0[a] + slen[a] <= g.n[a] &&
+                                         g.n[a] >= 2 * g.S[a] + 2));
   }
+  if (g.exact_all) interior = false;
   const int nxs = slen[0];
   const int nrows = slen[1] * slen[2];
   const int E = nrows * nxs;
@@ -126,6 +129,8 @@ __global__ void __launch_bounds__(256) k_sweep(const Grid g, const Consts c, con
   if (tile_n == 0) return;
   const int total_staged = soff[E];
   const bool single_group = total_staged <= sd.cap;
+  const int kz = -sa0[0], kn = g.n[0] - sa0[0];  // staged x index of unwrapped cells 0 and n
+  const int nit = 2 * g.W[1] * g.W[2];
 
   for (int ib = 0; ib < tile_n; ib += TPB) {
     // ---- own particle ------------------------------------------------------
@@ -154,40 +159,24 @@ __global__ void __launch_bounds__(256) k_sweep(const Grid g, const Consts c, con
     int w0[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) w0[a] = (g.n[a] >= 2 * g.S[a] + 1) ? (ci[a] - g.S[a] - sa0[a]) : 0;
+    // x window, split where the periodic image changes
+    const int ka = w0[0], kb = w0[0] + g.W[0];
+    int ks = kb;
+    if (ka < kz && kz < kb) ks = kz;
+    else if (ka < kn && kn < kb) ks = kn;
+    const float xs0 = ri[0] - (float)wrap_count(sa0[0] + ka, g.n[0]) * g.box[0];
+    const float xs1 = ri[0] - (float)wrap_count(sa0[0] + ks, g.n[0]) * g.box[0];
 
-    int cnt = 0;
-    auto consume = [&]() {
-      for (int k = 0; k < cnt; ++k) {
-        const int j = list[k * TPB + tid];
-        const float4 pj = sq[j];
-        float dr[3];
-        dr[0] = disp1(ri[0], pj.x, g.half[0], g.box[0]);
-        dr[1] = disp1(ri[1], pj.y, g.half[1], g.box[1]);
-        dr[2] = (DIM == 3) ? disp1(ri[2], pj.z, g.half[2], g.box[2]) : 0.0f;
-        const float d2 = sumsq<DIM>(dr);
-        if (d2 > g.c2_lo) {
-          // rounding band: the reference decides membership on d(r_sender, r_receiver)
-          float m[3];
-          if (P::SENDER_VIEW) {
-            m[0] = dr[0]; m[1] = dr[1]; m[2] = dr[2];
-          } else {
-            m[0] = disp1(pj.x, ri[0], g.half[0], g.box[0]);
-            m[1] = disp1(pj.y, ri[1], g.half[1], g.box[1]);
-            m[2] = (DIM == 3) ? disp1(pj.z, ri[2], g.half[2], g.box[2]) : 0.0f;
-          }
-          if (!(sumsq<DIM>(m) < g.c2)) continue;
-        }
-        P::pair(c, ex, own, acc, sq, sd.cap, j, pj, dr, d2);
-      }
-      cnt = 0;
-    };
-
-    // ---- row groups ----------------------------------------------------------
+    // ---- row groups (one group unless the stencil exceeds the staging buffer) ----
     int row_a = 0;
     while (row_a < nrows) {
       const int base = soff[row_a * nxs];
       int row_b = row_a;
-      while (row_b < nrows && soff[(row_b + 1) * nxs] - base <= sd.cap) ++row_b;
+      if (single_group) {
+        row_b = nrows;
+      } else {
+        while (row_b < nrows && soff[(row_b + 1) * nxs] - base <= sd.cap) ++row_b;
+      }
       bool skip = false;
       if (row_b == row_a) {  // one stencil row alone exceeds the staging buffer
         if (tid == 0) atomicOr(err, SPHB200_ERR_STAGE_OVERFLOW);
@@ -209,66 +198,102 @@ __global__ void __launch_bounds__(256) k_sweep(const Grid g, const Consts c, con
           const int gstart = cs[rowcell + (sa0[0] + k0 - seg * g.n[0])];
           const int dst = soff[row * nxs + k0] - base;
           const int len = soff[row * nxs + k1] - soff[row * nxs + k0];
-          for (int m = lane; m < len; m += 32) {
-            float4 q[P::NQ];
-            P::load_stage(c, f, ex, gstart + m, q);
-#pragma unroll
-            for (int qq = 0; qq < P::NQ; ++qq)
-              if (qq < sd.nq) sq[(size_t)qq * sd.cap + dst + m] = q[qq];
-          }
+          for (int m = lane; m < len; m += 32) P::stage(c, f, ex, gstart + m, sq, sd.cap, dst + m);
         }
         __syncthreads();
       }
       if (!skip) {
-        for (int row = row_a; row < row_b; ++row) {
-          const int ry = row % slen[1], rz = row / slen[1];
-          const bool inwin = act && ry >= w0[1] && ry < w0[1] + g.W[1] && rz >= w0[2] &&
-                             rz < w0[2] + g.W[2];
-          const float ys = ri[1] - (float)floor_div(sa0[1] + ry, g.n[1]) * g.box[1];
-          const float zs = ri[2] - (float)floor_div(sa0[2] + rz, g.n[2]) * g.box[2];
-          const int ka = w0[0], kb = w0[0] + g.W[0];
-          int ks = kb;
-          const int kz = -sa0[0], kn = g.n[0] - sa0[0];
-          if (ka < kz && kz < kb) ks = kz;
-          else if (ka < kn && kn < kb) ks = kn;
-#pragma unroll 1
-          for (int sgm = 0; sgm < 2; ++sgm) {
-            const int kk0 = sgm == 0 ? ka : ks, kk1 = sgm == 0 ? ks : kb;
-            int ja = 0, jb = 0;
-            float xs = ri[0];
-            if (inwin && kk0 < kk1) {
-              ja = soff[row * nxs + kk0] - base;
-              jb = soff[row * nxs + kk1] - base;
-              xs = ri[0] - (float)floor_div(sa0[0] + kk0, g.n[0]) * g.box[0];
-            }
-            int j = ja;
-            for (;;) {
-              const int rem = jb - j;
-              const bool more = rem > 0;
-              if (!__any_sync(FULL_MASK, more)) break;
-              const int want = more ? min(rem, SWEEP_CHUNK) : 0;
-              if (__any_sync(FULL_MASK, want > sd.lcap - cnt)) {
-                consume();
-                continue;
+        // Walk the thread's window as 2 * W1 * W2 (row, x-segment) pieces.  All lanes
+        // advance through the pieces together; a warp-wide vote switches to phase 2
+        // whenever some lane's list cannot take the next chunk.
+        int it = -1, wy = -1, wz = 0, cnt = 0;
+        int j = 0, jb = 0, row = 0;
+        bool inwin = false;
+        float xs = 0.f, ys = 0.f, zs = 0.f;
+        for (;;) {
+          bool fin = false;
+          // ---------------- phase 1: cheap reject, append survivors ----------------
+          for (;;) {
+            const int rem = jb - j;
+            if (!__any_sync(FULL_MASK, rem > 0)) {
+              if (++it >= nit) {
+                fin = true;
+                break;
               }
-              const int e = j + want;
-              for (; j < e; ++j) {
-                const float4 pj = sq[j];
-                const float dx = xs - pj.x, dy = ys - pj.y;
-                float d2 = dx * dx + dy * dy;
-                if (DIM == 3) {
-                  const float dz = zs - pj.z;
-                  d2 += dz * dz;
+              const int sgm = it & 1;
+              if (sgm == 0) {
+                if (++wy == g.W[1]) {
+                  wy = 0;
+                  ++wz;
                 }
-                if (d2 < g.c2_hi) {
-                  list[cnt * TPB + tid] = (unsigned short)j;
-                  ++cnt;
-                }
+                const int ry = w0[1] + wy, rz = w0[2] + wz;
+                row = rz * slen[1] + ry;
+                inwin = act && row >= row_a && row < row_b;
+                ys = ri[1] - (float)wrap_count(sa0[1] + ry, g.n[1]) * g.box[1];
+                zs = ri[2] - (float)wrap_count(sa0[2] + rz, g.n[2]) * g.box[2];
+              }
+              const int kk0 = sgm == 0 ? ka : ks, kk1 = sgm == 0 ? ks : kb;
+              j = jb = 0;
+              if (inwin && kk0 < kk1) {
+                j = soff[row * nxs + kk0] - base;
+                jb = soff[row * nxs + kk1] - base;
+              }
+              xs = sgm == 0 ? xs0 : xs1;
+              continue;
+            }
+            const int want = rem > 0 ? min(rem, SWEEP_CHUNK) : 0;
+            if (__any_sync(FULL_MASK, want > sd.lcap - cnt)) break;  // flush first
+            const int e = j + want;
+            unsigned short* lp = list + cnt * TPB + tid;
+#pragma unroll 4
+            for (; j < e; ++j) {
+              const float4 pj = sq[j];
+              const float dx = xs - pj.x, dy = ys - pj.y;
+              float d2 = dx * dx + dy * dy;
+              if (DIM == 3) {
+                const float dz = zs - pj.z;
+                d2 += dz * dz;
+              }
+              if (d2 < g.c2_hi) {
+                *lp = (unsigned short)j;
+                lp += TPB;
+                ++cnt;
               }
             }
           }
+          // ---------------- phase 2: real neighbours, exact arithmetic ----------------
+#pragma unroll 1
+          for (int k = 0; k < cnt; ++k) {
+            const int jn = list[k * TPB + tid];
+            const float4 pj = sq[jn];
+            float dr[3];
+            if (interior) {
+              dr[0] = disp1_nowrap(ri[0], pj.x, g.half[0]);
+              dr[1] = disp1_nowrap(ri[1], pj.y, g.half[1]);
+              dr[2] = (DIM == 3) ? disp1_nowrap(ri[2], pj.z, g.half[2]) : 0.0f;
+            } else {
+              dr[0] = disp1(ri[0], pj.x, g.half[0], g.box[0]);
+              dr[1] = disp1(ri[1], pj.y, g.half[1], g.box[1]);
+              dr[2] = (DIM == 3) ? disp1(ri[2], pj.z, g.half[2], g.box[2]) : 0.0f;
+            }
+            const float d2 = sumsq<DIM>(dr);
+            if (d2 > g.c2_lo) {
+              // rounding band: the reference decides membership on d(r_sender, r_receiver)
+              float m[3];
+              if (P::SENDER_VIEW) {
+                m[0] = dr[0]; m[1] = dr[1]; m[2] = dr[2];
+              } else {
+                m[0] = disp1(pj.x, ri[0], g.half[0], g.box[0]);
+                m[1] = disp1(pj.y, ri[1], g.half[1], g.box[1]);
+                m[2] = (DIM == 3) ? disp1(pj.z, ri[2], g.half[2], g.box[2]) : 0.0f;
+              }
+              if (!(sumsq<DIM>(m) < g.c2)) continue;
+            }
+            P::pair(c, ex, own, acc, sq, sd.cap, jn, pj, dr, d2);
+          }
+          cnt = 0;
+          if (fin) break;
         }
-        consume();
       }
       row_a = row_b;
     }
