@@ -122,6 +122,8 @@ typedef struct sphb200_config {
   double artificial_alpha;
   double p_ref, rho_ref, p_bg, gamma; /* TaitEoS                      */
   double u_ref;                       /* RIEMANNEoS                   */
+  double r_cutoff; /* neighbour cutoff; 0 = kernel support (3h QSK, 2h WC2K, kernel.py:64,88).
+                    * Set explicitly only by the neighbor_list drop-in (partition.py:492-507). */
   /* g_ext table */
   int32_t g_mode;   /* SPHB200_G_* */
   int32_t g_axis;   /* BAND: coordinate axis tested */
@@ -183,7 +185,7 @@ int sphb200_engine_error(sphb200_engine *e, uint32_t *code, void *stream);
  * idx is (2, capacity) int32 on the device, row 0 receiver, row 1 sender, sorted
  * by (sender, receiver), padded with N (jax_md/partition.py:885-909).  count
  * (device int64, may be NULL) receives the number of edges found; overflow sets
- * SPHB200_ERR_NEIGHBOR_OVERFLOW. */
+ * SPHB200_ERR_NEIGHBOR_OVERFLOW.  idx == NULL with capacity 0 only counts. */
 int sphb200_engine_neighbor_list(sphb200_engine *e, int32_t *idx, int64_t capacity,
                                  int mask_self, int64_t *count, void *stream);
 /* sync: kinetic energy 0.5*sum(m u.u) (utils.py:128-133) and max |u| (utils.py:136-166). */

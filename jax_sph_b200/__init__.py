@@ -11,7 +11,7 @@ All compute goes through the C ABI of ``libsphb200.so`` (include/sphb200.h,
 hand-written sm_100a CUDA); there is no CPU or PyTorch fallback.
 """
 
-from . import _lib  # noqa: F401
+from . import _lib, eos, integrator, partition, solver, space  # noqa: F401
 from .engine import Engine, config_from_setup, make_config  # noqa: F401
 
 __all__ = ["Engine", "make_config", "config_from_setup"]

@@ -42,7 +42,7 @@ class Config(C.Structure):
         ("tvf", C.c_double), ("c_ref", C.c_double), ("eta_limiter", C.c_double),
         ("artificial_alpha", C.c_double),
         ("p_ref", C.c_double), ("rho_ref", C.c_double), ("p_bg", C.c_double),
-        ("gamma", C.c_double), ("u_ref", C.c_double),
+        ("gamma", C.c_double), ("u_ref", C.c_double), ("r_cutoff", C.c_double),
         ("g_mode", C.c_int32), ("g_axis", C.c_int32), ("g", C.c_double * 3),
         ("g_lo", C.c_double), ("g_hi", C.c_double),
         ("bc", BcRule * 4),

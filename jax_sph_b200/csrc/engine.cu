@@ -31,6 +31,7 @@ using namespace sphb200;
 namespace {
 
 constexpr size_t ALIGN = 256;
+constexpr int DEFAULT_TPB = 512;  // tuned on B200, profiles/ (tune logs)
 inline size_t up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
 
 struct SweepPlan {
@@ -72,6 +73,7 @@ struct sphb200_engine {
 namespace {
 
 double kernel_cutoff(const sphb200_config& c) {
+  if (c.r_cutoff > 0.0) return c.r_cutoff;
   return (c.kernel == SPHB200_KERNEL_QSK ? 3.0 : 2.0) * c.h;
 }
 
@@ -98,7 +100,7 @@ void plan_grid(const sphb200_config& c, Grid& g, int tpb) {
   g.ncells = 1;
   for (int a = 0; a < 3; ++a) {
     if (a < c.dim) {
-      int sub = c.cell_sub[a] > 0 ? c.cell_sub[a] : 1;
+      int sub = c.cell_sub[a] > 0 ? c.cell_sub[a] : 2;  // cells of half a cutoff by default
       if (sub > 4) sub = 4;
       int n = (int)floor(c.box[a] * sub / (cutoff * 1.001));
       if (n < 1) n = 1;
@@ -118,12 +120,12 @@ void plan_grid(const sphb200_config& c, Grid& g, int tpb) {
   }
   // tile: T1 = T2 = sub (so a tile is about one cutoff wide across), T0 fills the block
   for (int a = 1; a < 3; ++a) {
-    int t = c.tile[a] > 0 ? c.tile[a] : (a < c.dim ? g.S[a] : 1);
+    int t = c.tile[a] > 0 ? c.tile[a] : (a < c.dim ? 2 * g.S[a] : 1);
     if (t > g.n[a]) t = g.n[a];
     g.T[a] = t;
   }
   while (g.T[1] * g.T[2] > MAX_RUNS) (g.T[2] > 1 ? g.T[2] : g.T[1])--;
-  int t0 = c.tile[0] > 0 ? c.tile[0] : (int)floor(0.9 * tpb / (pop * g.T[1] * g.T[2]) + 0.5);
+  int t0 = c.tile[0] > 0 ? c.tile[0] : (int)floor(0.86 * tpb / (pop * g.T[1] * g.T[2]) + 0.5);
   if (t0 < 1) t0 = 1;
   if (t0 > g.n[0]) t0 = g.n[0];
   // MAX_SOFF bound on staged (row, cell) entries
@@ -516,9 +518,9 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   int maxs = 0;
   CK(cudaDeviceGetAttribute(&maxs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   e->max_smem = maxs - 1024;
-  e->tpb = cfg->threads > 0 ? (cfg->threads + 31) / 32 * 32 : 128;
+  e->tpb = cfg->threads > 0 ? (cfg->threads + 31) / 32 * 32 : DEFAULT_TPB;
   if (e->tpb > 512) e->tpb = 512;
-  e->lcap = cfg->list_cap > 0 ? cfg->list_cap : 96;
+  e->lcap = cfg->list_cap > 0 ? cfg->list_cap : 32;
   if (e->lcap < SWEEP_CHUNK) e->lcap = SWEEP_CHUNK;
   plan_grid(*cfg, e->grid, e->tpb);
   plan_consts(*cfg, e->consts);
@@ -616,7 +618,7 @@ int sphb200_engine_bytes(const sphb200_config* cfg, int64_t n, size_t* bytes) {
   if (rc) return rc;
   if (!bytes) return SPHB200_EINVAL;
   Grid g;
-  plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : 128);
+  plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : DEFAULT_TPB);
   Layout L;
   plan_layout(*cfg, n, g, L);
   *bytes = L.total;
@@ -816,7 +818,8 @@ int sphb200_engine_error(sphb200_engine* e, uint32_t* code, void* stream) {
 
 int sphb200_engine_neighbor_list(sphb200_engine* e, int32_t* idx, int64_t capacity, int mask_self,
                                  int64_t* count, void* stream) {
-  if (!e || !idx || capacity < 0 || capacity >= 2147483647LL) return SPHB200_EINVAL;
+  if (!e || capacity < 0 || capacity >= 2147483647LL) return SPHB200_EINVAL;
+  if (!idx && capacity != 0) return SPHB200_EINVAL;  // idx == NULL: count only
   cudaStream_t st = (cudaStream_t)stream;
   if (!e->cells_valid) {
     Kick k{0.f, 0.f, 0};
@@ -842,10 +845,16 @@ int sphb200_engine_neighbor_list(sphb200_engine* e, int32_t* idx, int64_t capaci
   k_scan_partial<<<sb, SCAN_TPB, 0, st>>>(n, e->nl_counts, e->bsum);
   k_scan_bsum<<<1, 1024, 0, st>>>(sb, e->bsum);
   k_scan_final_keep<<<sb, SCAN_TPB, 0, st>>>(n, e->nl_counts, e->bsum, e->rnk);
-  k_nl_total<<<1, 1, 0, st>>>(n, e->rnk, e->nl_counts, capacity, (long long*)count, e->err);
+  k_nl_total<<<1, 1, 0, st>>>(n, e->rnk, e->nl_counts, idx ? capacity : (1LL << 62),
+                              (long long*)count, e->err);
+  e->launches += 4;
+  if (!idx) {
+    CK(cudaGetLastError());
+    return SPHB200_OK;
+  }
   const long long tot = 2 * capacity;
   if (tot > 0) k_fill<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(idx, tot, n);
-  e->launches += 5;
+  e->launches += 1;
   ex.nl_fill = 1;
   ex.nl_offsets = e->rnk;
   if (e->dim == 2) rc = launch_sweep(e, k_sweep<2, PhysNeighbors<2>>, e->planN, F, ex, st);

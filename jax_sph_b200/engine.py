@@ -22,6 +22,7 @@ def make_config(
     is_bc_trick=False, is_rho_evol=False, is_rho_renorm=False, is_free_slip=False,
     is_heat_conduction=False, artificial_alpha=0.0, g_ext_spec=None, bc_table=None,
     cell_sub=None, tile=None, threads=0, list_cap=0, stage_cap=0, g_ext_array=False,
+    r_cutoff=0.0,
 ):
     """Build a `sphb200_config` from the WCSPH constructor arguments
     (jax_sph/solver.py:616-637) plus the table forms of the case callables."""
@@ -107,6 +108,7 @@ def make_config(
             for a in range(3):
                 arr[a] = int(val[a]) if a < len(val) else 0
     cfg.threads, cfg.list_cap, cfg.stage_cap = threads, list_cap, stage_cap
+    cfg.r_cutoff = float(r_cutoff)
     return cfg
 
 
@@ -254,13 +256,13 @@ class Engine:
         return code.value
 
     def neighbor_list(self, capacity: int, mask_self: bool = False):
-        """(idx[2, capacity] int32 cuda tensor, edge count)."""
+        """(idx[2, capacity] int32 cuda tensor, edge count); capacity 0 = count only."""
         torch = _torch()
-        idx = torch.empty((2, capacity), dtype=torch.int32, device="cuda")
+        idx = torch.empty((2, capacity), dtype=torch.int32, device="cuda") if capacity else None
         cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
         _lib.check(self.lib.sphb200_engine_neighbor_list(
-            self._h, C.c_void_p(idx.data_ptr()), int(capacity), int(mask_self),
-            C.c_void_p(cnt.data_ptr()), _stream_ptr()))
+            self._h, C.c_void_p(idx.data_ptr() if capacity else None), int(capacity),
+            int(mask_self), C.c_void_p(cnt.data_ptr()), _stream_ptr()))
         return idx, int(cnt.item())
 
     def stats(self):

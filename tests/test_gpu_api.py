@@ -1,0 +1,180 @@
+"""GPU tests of the drop-in boundary: the mirrors of the reference's Python API
+(partition.neighbor_list, solver.WCSPH, integrator.si_euler), the stateless
+C-ABI entry points the jax.ffi shim binds, determinism and error behaviour."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests._util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(**kw):
+    from oracle import cases
+
+    return cases.make_case(dtype=np.float32, **kw)
+
+
+def _to_cuda(state):
+    import torch
+
+    return {k: torch.as_tensor(v, device="cuda") for k, v in state.items()}
+
+
+def test_reference_call_sequence_with_mirrors():
+    """The call sequence of jax_sph/simulate.py:49-93,117 written against the mirrors."""
+    from jax_sph_b200 import eos, integrator, partition, solver, space
+    from oracle import integrator as oint
+
+    setup = _case(case="db", dim=2, dx=0.05)
+    displacement_fn, shift_fn = space.periodic(side=setup.box_size)
+    eos_obj = eos.TaitEoS(setup.p_ref, setup.rho_ref, setup.p_bg, setup.gamma)
+    model = solver.WCSPH(
+        displacement_fn, eos_obj, setup.g_ext_fn, setup.dx, setup.dim, setup.dt, setup.c_ref,
+        setup.eta_limiter, 0.0, 0.0, setup.solver, setup.kernel, setup.h_factor,
+        setup.is_bc_trick, setup.density_evolution, setup.artificial_alpha, setup.free_slip,
+        setup.density_renormalize, setup.heat_conduction, g_ext_spec=setup.g_ext_spec)
+    forward = model.forward_wrapper()
+    nfns = partition.neighbor_list(displacement_fn, setup.box_size, model._kernel_fn.cutoff,
+                                   mask_self=False)
+    state = _to_cuda(setup.state)
+    neighbors = nfns.allocate(state["r"])
+    advance = integrator.si_euler(setup.tvf, forward, shift_fn, integrator.BcTable(setup.bc_table))
+    for _ in range(3):
+        state, neighbors = advance(setup.dt, state, neighbors)
+        assert not neighbors.did_buffer_overflow  # simulate.py:120
+    ref = oint.simulate(setup, 3)
+    for k in ("r", "u", "v", "rho", "p", "dudt", "dvdt"):
+        assert_close(k, state[k].cpu().numpy(), ref[k], setup, factor=3.0, what="mirror advance")
+    assert set(ref) <= set(state), "state dict keys (solver.py:930-947)"
+
+
+def test_forward_mirror_with_python_g_ext():
+    """WCSPH.forward with an arbitrary g_ext_fn callable (evaluated outside, passed as array)."""
+    import torch
+
+    from jax_sph_b200 import eos, solver, space
+    from oracle import integrator as oint
+    from oracle.solver import WCSPH as OracleWCSPH
+
+    setup = _case(case="pf", dim=2, dx=0.04)
+    displacement_fn, _ = space.periodic(side=setup.box_size)
+
+    def g_ext_fn(r):  # torch version of cases/pf.py external force
+        return torch.as_tensor(setup.g_ext_fn(r.cpu().numpy()), device=r.device)
+
+    model = solver.WCSPH(displacement_fn, eos.TaitEoS(setup.p_ref, setup.rho_ref, setup.p_bg, 1.0),
+                         g_ext_fn, setup.dx, 2, setup.dt, setup.c_ref, solver="SPH", kernel="QSK",
+                         is_bc_trick=True)
+    got = model.forward_wrapper()(_to_cuda(setup.state), None)
+    osolver = OracleWCSPH(setup.displacement_fn, setup.eos, setup.g_ext_fn, setup.dx, 2, setup.dt,
+                          setup.c_ref, is_bc_trick=True, dtype=np.float32)
+    nfn = oint.make_neighbors_fn(setup.box_size, osolver._kernel_fn.cutoff)
+    ref = osolver.forward({k: v.copy() for k, v in setup.state.items()}, nfn(setup.state["r"]))
+    for k in ("rho", "p", "u", "v", "dudt", "dvdt"):
+        assert_close(k, got[k].cpu().numpy(), ref[k], setup, what="forward mirror")
+
+
+def test_stateless_advance_equals_resident_engine_bitwise():
+    import torch
+
+    from jax_sph_b200 import Engine, _lib, config_from_setup
+
+    setup = _case(case="tgv", dim=3, dx=2 * np.pi / 14, tvf=1.0, viscosity=0.02)
+    n = len(setup.state["r"])
+    cfg = config_from_setup(setup)
+    eng = Engine(cfg, n)
+    eng.upload(setup.state)
+    eng.step(setup.dt, 1)
+    ref = eng.download()
+    lib = _lib.load()
+    nbytes = C.c_size_t()
+    _lib.check(lib.sphb200_workspace_bytes(C.byref(cfg), n, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+    dev = _to_cuda(setup.state)
+    out = {k: torch.empty_like(v) for k, v in dev.items()}
+    sin, sout = _lib.State(), _lib.State()
+    for k in dev:
+        setattr(sin, k, dev[k].data_ptr())
+        setattr(sout, k, out[k].data_ptr())
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(lib.sphb200_advance(
+        C.byref(cfg), n, float(setup.dt), C.byref(sin), C.byref(sout), C.c_void_p(err.data_ptr()),
+        C.c_void_p(ws.data_ptr()), nbytes.value,
+        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    for k in ("r", "u", "v", "rho", "p", "dudt", "dvdt", "tag", "mass"):
+        assert torch.equal(out[k], ref[k]), k
+
+
+def test_determinism_and_host_pointer_path():
+    import torch
+
+    from jax_sph_b200 import Engine, config_from_setup
+
+    setup = _case(case="ht", dim=2, dx=0.02)
+    n = len(setup.state["r"])
+    runs = []
+    for host in (False, True, False):
+        eng = Engine(config_from_setup(setup), n)
+        eng.upload(setup.state if host else _to_cuda(setup.state))
+        eng.step(setup.dt, 7)
+        got = eng.download(host=host)
+        runs.append({k: (v.numpy() if host else v.cpu().numpy()) for k, v in got.items()})
+        assert eng.error() == 0
+    for k in runs[0]:
+        assert np.array_equal(runs[0][k], runs[1][k]), f"host vs device path differ in {k}"
+        assert np.array_equal(runs[0][k], runs[2][k]), f"run-to-run difference in {k}"
+    torch.cuda.synchronize()
+
+
+def test_particle_order_does_not_matter():
+    from jax_sph_b200 import Engine, config_from_setup
+
+    setup = _case(case="tgv", dim=2, dx=0.02, tvf=1.0)
+    n = len(setup.state["r"])
+    perm = np.random.default_rng(5).permutation(n)
+    eng = Engine(config_from_setup(setup), n)
+    eng.upload(setup.state)
+    eng.step(setup.dt, 3)
+    a = eng.download(host=True)
+    eng.upload({k: np.ascontiguousarray(v[perm]) for k, v in setup.state.items()})
+    eng.step(setup.dt, 3)
+    b = eng.download(host=True)
+    for k in ("r", "u", "rho", "p", "dudt"):
+        assert_close(k, b[k].numpy(), a[k].numpy()[perm], setup, factor=2.0, what="permuted input")
+
+
+def test_error_behaviour():
+    import torch
+
+    from jax_sph_b200 import Engine, _lib, config_from_setup, make_config
+
+    setup = _case(case="tgv", dim=2, dx=0.05)
+    n = len(setup.state["r"])
+    eng = Engine(config_from_setup(setup), n)
+    with pytest.raises(_lib.Sphb200Error, match="float64"):
+        eng.upload({k: v.astype(np.float64) if v.dtype == np.float32 else v
+                    for k, v in setup.state.items()})
+    with pytest.raises(_lib.Sphb200Error, match="elements"):
+        eng.upload({"r": setup.state["r"][:-1]})
+    with pytest.raises(_lib.Sphb200Error, match="not supported"):
+        make_config(2, [1.0, 1.0], 0.05, 0.0, solver="DELTA")
+    with pytest.raises(_lib.Sphb200Error, match="not supported"):
+        make_config(2, [1.0, 1.0], 0.05, 0.0, kernel="GK")
+    # positions outside the periodic box are reported through the device error word
+    bad = dict(setup.state)
+    bad["r"] = bad["r"].copy()
+    bad["r"][0, 0] = 1.5
+    eng.upload(bad)
+    eng.step(0.0, 1, integrate=False)
+    assert eng.error() & _lib.ERR_OUTSIDE_BOX
+    bad["r"][0, 0] = np.nan
+    eng.upload(bad)
+    eng.step(0.0, 1, integrate=False)
+    assert eng.error() & _lib.ERR_NONFINITE
+    torch.cuda.synchronize()

@@ -1,0 +1,110 @@
+"""CPU tests of the host-side logic: config marshalling and the table forms of
+the case callables (bc_fn / g_ext_fn) that the fused CUDA epilogue consumes."""
+
+import numpy as np
+import pytest
+
+from oracle import cases
+from oracle.solver import DIRICHLET_WALL, FLUID, MOVING_WALL, SOLID_WALL
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__ as g
+
+    g.build()
+
+
+def apply_bc_table(table, state, dim):
+    """NumPy statement of what k_sweep<PhysForce>::finish + k_bc do with the table."""
+    s = {k: v.copy() for k, v in state.items()}
+    for tag, rule in table["tags"].items():
+        m = s["tag"] == tag
+        if "u" in rule:
+            s["u"][m] = np.asarray(rule["u"][:dim], dtype=s["u"].dtype)
+        if "v" in rule:
+            s["v"][m] = np.asarray(rule["v"][:dim], dtype=s["v"].dtype)
+        if rule.get("zero_dudt"):
+            s["dudt"][m] = 0
+        if rule.get("zero_dvdt"):
+            s["dvdt"][m] = 0
+        if "p" in rule:
+            s["p"][m] = rule["p"]
+        if "T" in rule:
+            s["T"][m] = rule["T"]
+        if rule.get("zero_dTdt"):
+            s["dTdt"][m] = 0
+    fluid = s["tag"] == FLUID
+    if table.get("inflow_x"):
+        m = fluid & (s["r"][:, 0] < np.float32(table["inflow_x"]["x"]))
+        s["T"][m] = table["inflow_x"]["T"]
+        s["dTdt"][m] = 0
+    if table.get("outflow_x"):
+        m = fluid & (s["r"][:, 0] > np.float32(table["outflow_x"]["x"]))
+        s["dTdt"][m] = 0
+    return s
+
+
+@pytest.mark.parametrize("case,dim", [("tgv", 2), ("db", 2), ("pf", 2), ("cf", 2), ("ht", 2), ("ht", 3)])
+def test_bc_table_equals_case_callable(case, dim):
+    setup = cases.make_case(case, dim=dim, dx=0.05, dtype=np.float32)
+    rng = np.random.default_rng(1)
+    state = {k: (rng.standard_normal(v.shape).astype(v.dtype) if v.dtype == np.float32 else v.copy())
+             for k, v in setup.state.items()}
+    state["r"] = setup.state["r"].copy()
+    want = setup.bc_fn({k: v.copy() for k, v in state.items()})
+    got = apply_bc_table(setup.bc_table, state, dim)
+    for k in want:
+        assert np.array_equal(want[k], got[k]), f"{case}: table != bc_fn for {k}"
+
+
+@pytest.mark.parametrize("case,dim", [("tgv", 3), ("db", 2), ("pf", 2), ("ht", 3)])
+def test_g_ext_spec_equals_case_callable(case, dim):
+    setup = cases.make_case(case, dim=dim, dx=0.05, dtype=np.float32)
+    r = setup.state["r"]
+    want = setup.g_ext_fn(r)
+    spec = setup.g_ext_spec
+    got = np.zeros_like(r)
+    if spec["mode"] == "const":
+        got[:] = np.asarray(spec["g"][:dim], dtype=np.float32)
+    elif spec["mode"] == "band":
+        x = r[:, spec["axis"]]
+        m = (x < np.float32(spec["hi"])) & (x > np.float32(spec["lo"]))
+        got[m] = np.asarray(spec["g"][:dim], dtype=np.float32)
+    assert np.array_equal(want.astype(np.float32), got)
+
+
+def test_config_from_setup_fields():
+    from jax_sph_b200 import _lib, config_from_setup
+
+    setup = cases.make_case("ht", dim=3, dx=0.05, dtype=np.float32)
+    cfg = config_from_setup(setup)
+    assert cfg.dim == 3 and cfg.solver == 0 and cfg.kernel == 0 and cfg.eos == _lib.EOS_TAIT
+    assert cfg.flags == _lib.F_BC_TRICK | _lib.F_HEAT
+    assert list(cfg.box) == pytest.approx(list(setup.box_size))
+    assert cfg.h == setup.dx and cfg.dt == setup.dt and cfg.p_bg == pytest.approx(0.05 * setup.p_ref)
+    assert cfg.g_mode == _lib.G_BAND and cfg.g_axis == 1 and cfg.g[0] == pytest.approx(2.3)
+    assert cfg.bc[SOLID_WALL].flags & _lib.BC_SET_T and cfg.bc[DIRICHLET_WALL].T == pytest.approx(1.23)
+    assert cfg.bc[MOVING_WALL].flags == 0 and cfg.bc_inflow_on == 1 and cfg.bc_outflow_on == 1
+    rie = cases.make_case("tgv", dim=2, dx=0.05, dtype=np.float32, solver="RIE", density_evolution=True)
+    cfg = config_from_setup(rie, cell_sub=[1, 1], tile=[4, 1], threads=128)
+    assert cfg.solver == 1 and cfg.eos == _lib.EOS_RIEMANN and cfg.flags == _lib.F_RHO_EVOL
+    assert list(cfg.cell_sub) == [1, 1, 0] and list(cfg.tile) == [4, 1, 0] and cfg.threads == 128
+
+
+def test_engine_bytes_scale_with_features():
+    import ctypes as C
+
+    from jax_sph_b200 import _lib, config_from_setup
+
+    lib = _lib.load()
+
+    def nbytes(setup, n=100000):
+        b = C.c_size_t()
+        _lib.check(lib.sphb200_engine_bytes(C.byref(config_from_setup(setup)), n, C.byref(b)))
+        return b.value
+
+    plain = nbytes(cases.make_case("tgv", dim=3, dx=0.2, dtype=np.float32))
+    heat = nbytes(cases.make_case("ht", dim=3, dx=0.05, dtype=np.float32))
+    assert 200 * 100000 < plain < 260 * 100000  # ~212 B / particle + cell tables
+    assert heat > plain  # kappa / Cp carried only when heat conduction is on
