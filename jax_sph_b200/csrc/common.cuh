@@ -202,18 +202,20 @@ __device__ __forceinline__ float kernel_gw(const Consts& c, float r) {
   }
 }
 
-// Pair-level division / square root.  Default: hardware reciprocal / rsqrt
-// (<= 2 ulp), well inside the float32 summation-order noise of the sweeps
-// (DESIGN.md section 6); -DSPHB200_PRECISE restores IEEE operations.
+// Pair-level division: hardware reciprocal (<= 2 ulp), well inside the float32
+// summation-order noise of the sweeps; -DSPHB200_PRECISE
+// restores IEEE division.  The distance keeps the IEEE square root: near the edge
+// of the kernel support w ~ (3 - q)^5 amplifies a 2-ulp error of q by 5 / (3 - q),
+// which the Shepard wall averages of solver.py:505-526 (sum w T / (sum w + EPS))
+// expose for wall particles whose only fluid neighbours sit at the cutoff.
 #ifdef SPHB200_PRECISE
 __device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
 __device__ __forceinline__ float frcp(float a) { return 1.0f / a; }
-__device__ __forceinline__ float fsqrt(float a) { return sqrtf(a); }
 #else
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ float frcp(float a) { return __fdividef(1.0f, a); }
-__device__ __forceinline__ float fsqrt(float a) { return a > 0.0f ? a * rsqrtf(a) : 0.0f; }
 #endif
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
 
 // eos.py:33-38 / :53-57
 __device__ __forceinline__ float eos_p(const Consts& c, float rho) {

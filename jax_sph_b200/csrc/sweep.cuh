@@ -167,30 +167,38 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
     const float xs0 = ri[0] - (float)wrap_count(sa0[0] + ka, g.n[0]) * g.box[0];
     const float xs1 = ri[0] - (float)wrap_count(sa0[0] + ks, g.n[0]) * g.box[0];
 
-    // ---- row groups (one group unless the stencil exceeds the staging buffer) ----
-    int row_a = 0;
-    while (row_a < nrows) {
-      const int base = soff[row_a * nxs];
-      int row_b = row_a;
-      if (single_group) {
-        row_b = nrows;
-      } else {
-        while (row_b < nrows && soff[(row_b + 1) * nxs] - base <= sd.cap) ++row_b;
+    // ---- staging groups: maximal runs [e_a, e_b) of consecutive (row, cell) entries that
+    //      fit the staging buffer (one group unless the stencil is unusually crowded) ----
+    int e_a = 0;
+    while (e_a < E) {
+      const int base = soff[e_a];
+      int e_b = E;
+      if (!single_group) {
+        int lo = e_a, hi = E;  // largest e_b with soff[e_b] - base <= cap (soff is monotone)
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (soff[mid] - base <= sd.cap) lo = mid;
+          else hi = mid - 1;
+        }
+        e_b = lo;
       }
       bool skip = false;
-      if (row_b == row_a) {  // one stencil row alone exceeds the staging buffer
+      if (e_b == e_a) {  // one cell alone exceeds the staging buffer
         if (tid == 0) atomicOr(err, SPHB200_ERR_STAGE_OVERFLOW);
-        row_b = row_a + 1;
+        e_b = e_a + 1;
         skip = true;
       }
       if (!skip && !(single_group && ib > 0)) {
-        if (ib > 0 || row_a > 0) __syncthreads();  // previous readers done
-        const int njobs = (row_b - row_a) * 3;
+        if (ib > 0 || e_a > 0) __syncthreads();  // previous readers done
+        const int r_first = e_a / nxs, r_last = (e_b - 1) / nxs;
+        const int njobs = (r_last - r_first + 1) * 3;
         for (int job = warp; job < njobs; job += nwarps) {
-          const int row = row_a + job / 3;
+          const int row = r_first + job / 3;
           const int seg = job % 3 - 1;
-          int k0 = max(0, seg * g.n[0] - sa0[0]);
-          int k1 = min(nxs, (seg + 1) * g.n[0] - sa0[0]);
+          const int klo = row == r_first ? e_a - row * nxs : 0;
+          const int khi = row == r_last ? e_b - row * nxs : nxs;
+          int k0 = max(klo, seg * g.n[0] - sa0[0]);
+          int k1 = min(khi, (seg + 1) * g.n[0] - sa0[0]);
           if (k0 >= k1) continue;
           const int ry = row % slen[1], rz = row / slen[1];
           const int rowcell =
@@ -228,15 +236,18 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
                 }
                 const int ry = w0[1] + wy, rz = w0[2] + wz;
                 row = rz * slen[1] + ry;
-                inwin = act && row >= row_a && row < row_b;
+                inwin = act;
                 ys = ri[1] - (float)wrap_count(sa0[1] + ry, g.n[1]) * g.box[1];
                 zs = ri[2] - (float)wrap_count(sa0[2] + rz, g.n[2]) * g.box[2];
               }
               const int kk0 = sgm == 0 ? ka : ks, kk1 = sgm == 0 ? ks : kb;
               j = jb = 0;
               if (inwin && kk0 < kk1) {
-                j = soff[row * nxs + kk0] - base;
-                jb = soff[row * nxs + kk1] - base;
+                const int ea = max(row * nxs + kk0, e_a), eb = min(row * nxs + kk1, e_b);
+                if (ea < eb) {
+                  j = soff[ea] - base;
+                  jb = soff[eb] - base;
+                }
               }
               xs = sgm == 0 ? xs0 : xs1;
               continue;
@@ -295,7 +306,7 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
           if (fin) break;
         }
       }
-      row_a = row_b;
+      e_a = e_b;
     }
     if (have) P::finish(c, f, ex, p, own, acc);
   }

@@ -34,13 +34,17 @@ def floors(setup):
     dx, rho0 = setup.dx, setup.rho_ref
     p_bg_tvf = abs(-setup.p_ref + setup.p_bg) if setup.solver != "RIE" else abs(
         -100 * setup.u_ref**2 * rho0 + setup.p_bg)
+    acc = max(setup.p_ref, p_bg_tvf) / (rho0 * dx)
     return {
         "p": setup.p_ref if setup.solver != "RIE" else 100 * setup.u_ref**2 * rho0,
         "dudt": setup.p_ref / (rho0 * dx),
         "dvdt": p_bg_tvf / (rho0 * dx),
         "drhodt": rho0 * setup.c_ref / dx * 1e-2,
         "dTdt": 1e-2 / dx,
-        "r": float(np.max(setup.box_size)) * 1e-2,
+        # one step of the acceleration floor: u += dt dudt, r += dt v
+        "u": setup.dt * acc,
+        "v": setup.dt * acc,
+        "r": float(np.max(setup.box_size)) * 1e-2 + setup.dt**2 * acc,
     }
 
 

@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from tests._util import assert_close
+from _util import assert_close
 
 pytestmark = pytest.mark.gpu
 
@@ -21,7 +21,7 @@ def _case(**kw):
 def _to_cuda(state):
     import torch
 
-    return {k: torch.as_tensor(v, device="cuda") for k, v in state.items()}
+    return {k: torch.as_tensor(np.ascontiguousarray(v), device="cuda") for k, v in state.items()}
 
 
 def test_reference_call_sequence_with_mirrors():

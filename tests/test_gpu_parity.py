@@ -11,7 +11,7 @@ Wendland C2 and a moving wall.  Tolerances: tests/_util.py.
 import numpy as np
 import pytest
 
-from tests._util import assert_close, drift_ok, load_golden
+from _util import assert_close, drift_ok, load_golden
 
 pytestmark = pytest.mark.gpu
 
