@@ -141,7 +141,9 @@ typedef struct sphb200_config {
   int32_t threads;     /* sweep block size                           */
   int32_t list_cap;    /* per-thread pair-list capacity              */
   int32_t stage_cap;   /* staged particles per block (0 = auto)      */
-  int32_t reserved[8];
+  int32_t nl_cap;      /* row length of the per-step neighbour lists shared by the sweeps of one
+                        * forward(): 0 = auto (1.3 x the uniform-fluid neighbour count), -1 = off */
+  int32_t reserved[7];
 } sphb200_config;
 
 /* State dict of the reference (solver.py:930-947), device or host pointers.

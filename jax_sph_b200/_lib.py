@@ -49,7 +49,8 @@ class Config(C.Structure):
         ("bc_inflow_on", C.c_int32), ("bc_inflow_x", C.c_float), ("bc_inflow_T", C.c_float),
         ("bc_outflow_on", C.c_int32), ("bc_outflow_x", C.c_float),
         ("cell_sub", C.c_int32 * 3), ("tile", C.c_int32 * 3), ("threads", C.c_int32),
-        ("list_cap", C.c_int32), ("stage_cap", C.c_int32), ("reserved", C.c_int32 * 8),
+        ("list_cap", C.c_int32), ("stage_cap", C.c_int32), ("nl_cap", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 

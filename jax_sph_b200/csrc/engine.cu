@@ -53,6 +53,11 @@ struct sphb200_engine {
   int cur;
   bool cells_valid;
   int *key, *rnk, *src, *count, *start, *bsum, *maxocc, *wallcount, *nl_counts;
+  // per-step neighbour lists shared by the sweeps of one forward() (sweep.cuh, NList)
+  unsigned short* pl_list;
+  int* pl_cnt;
+  unsigned char* pl_ok;
+  int pl_lmax;
   unsigned* err;
   double* stats;  // [ekin, umax]
   int nscan_blocks;
@@ -202,6 +207,8 @@ bool bc_table_on(const sphb200_config& c) {
 struct Layout {
   size_t frame[2][12];
   size_t key, rnk, src, count, start, bsum, maxocc, wallcount, err, stats, nl_counts, ut;
+  size_t pl_list, pl_cnt, pl_ok;
+  int pl_lmax;
   size_t total;
 };
 
@@ -211,6 +218,18 @@ void feature_flags(const sphb200_config& c, bool& kc, bool& nw, bool& ut, bool& 
   ut = (c.solver == SPHB200_SOLVER_RIE) && (c.flags & SPHB200_F_BC_TRICK) &&
        !(c.flags & SPHB200_F_FREE_SLIP);
   ge = c.g_mode == SPHB200_G_ARRAY;
+}
+
+// Row length of the per-step neighbour lists: 1.3 x the expected number of
+// neighbours of a particle in a uniform fluid (+8), a multiple of 8; 0 = lists off.
+int plan_lmax(const sphb200_config& c) {
+  if (c.nl_cap < 0) return 0;
+  if (c.nl_cap > 0) return (c.nl_cap + 7) / 8 * 8;
+  const double q = kernel_cutoff(c) / c.dx;
+  const double expect = c.dim == 2 ? M_PI * q * q : 4.0 / 3.0 * M_PI * q * q * q;
+  int lmax = ((int)(1.3 * expect) + 8 + 7) / 8 * 8;
+  if (lmax > 1024) lmax = 0;  // very wide kernels: not worth the memory
+  return lmax;
 }
 
 void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, Layout& L) {
@@ -242,6 +261,14 @@ void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, Layout& L) {
   L.wallcount = take(4);
   L.err = take(4);
   L.stats = take(16);
+  L.pl_lmax = plan_lmax(c);
+  if (L.pl_lmax > 0) {
+    L.pl_list = take((size_t)n * L.pl_lmax * 2);
+    L.pl_cnt = take((size_t)n * 4);
+    L.pl_ok = take((size_t)g.nt[0] * g.nt[1] * g.nt[2]);
+  } else {
+    L.pl_list = L.pl_cnt = L.pl_ok = (size_t)-1;
+  }
   L.total = off;
 }
 
@@ -271,11 +298,11 @@ SweepPlan plan_sweep(const sphb200_engine* e, int nq) {
 
 template <class K>
 int launch_sweep(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f, const Extra& ex,
-                 cudaStream_t st) {
+                 cudaStream_t st, const NList& nl = NList{nullptr, nullptr, nullptr, 0, 0}) {
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
   SweepDims sd{sp.cap, e->lcap, ex.nq};
   const int blocks = e->grid.nt[0] * e->grid.nt[1] * e->grid.nt[2];
-  kern<<<blocks, e->tpb, sp.smem, st>>>(e->grid, e->consts, f, e->start, sd, ex, e->err);
+  kern<<<blocks, e->tpb, sp.smem, st>>>(e->grid, e->consts, f, e->start, sd, ex, e->err, nl);
   e->launches++;
   CK(cudaGetLastError());
   return SPHB200_OK;
@@ -341,6 +368,23 @@ int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st)
   const bool rie = c.solver == SPHB200_SOLVER_RIE;
   const bool wall_sweep = bc_trick && !rie;
   int rc;
+  // quads staged by the force sweep (decides its staging capacity)
+  int force_nq = 3;
+  const int fq_v = (!rie && !v_is_u) ? force_nq++ : -1;
+  const int fq_h = heat ? force_nq++ : -1;
+  const int fq_nw = rie ? force_nq++ : -1;
+  const int fq_ut = (rie && e->has_ut) ? force_nq++ : -1;
+  const SweepPlan planF = plan_sweep(e, force_nq);
+  const bool dens_extras = e->has_ut || (rie && bc_trick && heat);
+  const SweepPlan planD = !evol ? (dens_extras ? e->planW : e->planA) : (!rie ? e->planR : e->planW);
+  // neighbour lists: built by the density sweep, consumed by every later sweep of this step
+  NList nl{e->pl_list, e->pl_cnt, e->pl_ok, e->pl_lmax, 0};
+  {
+    int mc = planD.cap < planF.cap ? planD.cap : planF.cap;
+    if (evol && renorm && e->planR.cap < mc) mc = e->planR.cap;
+    if (wall_sweep && e->planW.cap < mc) mc = e->planW.cap;
+    nl.min_cap = mc;
+  }
   // ---- density -------------------------------------------------------------
   {
     Extra ex = make_extra();
@@ -350,23 +394,26 @@ int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st)
     ex.heat = heat;
     Frame& F = e->fr[e->cur];
     ex.st_out = e->fr[1 - e->cur].st;
-    const bool extras = ex.utilde || ex.wallT;
     if (!evol) {
-      SweepPlan sp = extras ? e->planW : e->planA;  // 3 quads fit in the 4-quad plan
-      ex.nq = extras ? 3 : 1;
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_SUM>>, sp, F, ex, st)
-      DISPATCH_DK(e, CALL);
+      if (dens_extras) {
+        ex.nq = 3;  // 3 quads fit in the 4-quad plan
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_SUM_X>, LIST_BUILD>, planD, F, ex, st, nl)
+        DISPATCH_DK(e, CALL);
 #undef CALL
+      } else {
+        ex.nq = 1;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_SUM>, LIST_BUILD>, planD, F, ex, st, nl)
+        DISPATCH_DK(e, CALL);
+#undef CALL
+      }
     } else if (!rie) {
-      SweepPlan sp = e->planR;
       ex.nq = 2;
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_EVOL_SPH>>, sp, F, ex, st)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_EVOL_SPH>, LIST_BUILD>, planD, F, ex, st, nl)
       DISPATCH_DK(e, CALL);
 #undef CALL
     } else {
-      SweepPlan sp = e->planW;
       ex.nq = 4;
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_EVOL_RIE>>, sp, F, ex, st)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_EVOL_RIE>, LIST_BUILD>, planD, F, ex, st, nl)
       DISPATCH_DK(e, CALL);
 #undef CALL
     }
@@ -379,7 +426,7 @@ int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st)
     ex.nq = 2;
     Frame& F = e->fr[e->cur];
     ex.st_out = e->fr[1 - e->cur].st;
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysRenorm<D, K>>, e->planR, F, ex, st)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysRenorm<D, K>, LIST_CONSUME>, e->planR, F, ex, st, nl)
     DISPATCH_DK(e, CALL);
 #undef CALL
     if (rc) return rc;
@@ -393,7 +440,7 @@ int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st)
     ex.free_slip = free_slip;
     Frame& F = e->fr[e->cur];
     ex.st_out = e->fr[1 - e->cur].st;
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysWall<D, K>>, e->planW, F, ex, st)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysWall<D, K>, LIST_CONSUME>, e->planW, F, ex, st, nl)
     DISPATCH_DK(e, CALL);
 #undef CALL
     if (rc) return rc;
@@ -403,38 +450,32 @@ int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st)
   // ---- force -----------------------------------------------------------------
   {
     Extra ex = make_extra();
-    int nq = 3;
-    if (!rie && !v_is_u) ex.q_v = nq++;
-    if (heat) ex.q_h = nq++;
-    if (rie) {
-      ex.q_nw = nq++;
-      if (e->has_ut) ex.q_ut = nq++;
-    }
-    ex.nq = nq;
+    ex.q_v = fq_v; ex.q_h = fq_h; ex.q_nw = fq_nw; ex.q_ut = fq_ut;
+    ex.nq = force_nq;
     ex.heat = heat;
     ex.av = c.artificial_alpha != 0.0;
     ex.bc_on = (flags & SPHB200_STEP_BC) && bc_table_on(c);
     ex.free_slip = free_slip;
     ex.bc_trick = bc_trick;
-    SweepPlan sp = plan_sweep(e, nq);
+    const SweepPlan& sp = planF;
     Frame& F = e->fr[e->cur];
     if (!rie) {
       const int feat = (heat || ex.av) ? FORCE_GENERIC : (v_is_u ? FORCE_PLAIN : FORCE_TVF);
       if (feat == FORCE_PLAIN) {
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>>, sp, F, ex, st)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>, LIST_CONSUME>, sp, F, ex, st, nl)
         DISPATCH_DK(e, CALL);
 #undef CALL
       } else if (feat == FORCE_TVF) {
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF>>, sp, F, ex, st)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF>, LIST_CONSUME>, sp, F, ex, st, nl)
         DISPATCH_DK(e, CALL);
 #undef CALL
       } else {
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_GENERIC>>, sp, F, ex, st)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_GENERIC>, LIST_CONSUME>, sp, F, ex, st, nl)
         DISPATCH_DK(e, CALL);
 #undef CALL
       }
     } else {
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_RIE, FORCE_GENERIC>>, sp, F, ex, st)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_RIE, FORCE_GENERIC>, LIST_CONSUME>, sp, F, ex, st, nl)
       DISPATCH_DK(e, CALL);
 #undef CALL
     }
@@ -557,6 +598,10 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->wallcount = (int*)(e->arena + L.wallcount);
   e->err = (unsigned*)(e->arena + L.err);
   e->stats = (double*)(e->arena + L.stats);
+  e->pl_lmax = L.pl_lmax;
+  e->pl_list = L.pl_lmax ? (unsigned short*)(e->arena + L.pl_list) : nullptr;
+  e->pl_cnt = L.pl_lmax ? (int*)(e->arena + L.pl_cnt) : nullptr;
+  e->pl_ok = L.pl_lmax ? (unsigned char*)(e->arena + L.pl_ok) : nullptr;
   e->cur = 0;
   e->cells_valid = false;
   e->launches = 0;

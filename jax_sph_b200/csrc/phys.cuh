@@ -27,12 +27,16 @@ __device__ __forceinline__ float dot3(const float (&a)[3], const float (&b)[3], 
 }
 
 // ---------------------------------------------------------------------------
-enum { DENS_SUM = 0, DENS_EVOL_SPH = 1, DENS_EVOL_RIE = 2 };
+// DENS_SUM_X: summation plus the RIE wall helpers (u_tilde, wall temperature); the helpers
+// are compiled out of DENS_SUM / DENS_EVOL_SPH, which never need them.
+enum { DENS_SUM = 0, DENS_EVOL_SPH = 1, DENS_EVOL_RIE = 2, DENS_SUM_X = 3 };
 
 template <int DIM, int KERN, int MODE>
 struct PhysDensity {
   static constexpr int MINB = (MODE == DENS_EVOL_RIE) ? 1 : 2;
   static constexpr bool SENDER_VIEW = false;
+  static constexpr bool SUM = MODE == DENS_SUM || MODE == DENS_SUM_X;
+  static constexpr bool XTRA = MODE == DENS_SUM_X || MODE == DENS_EVOL_RIE;
   struct Own {
     float u[3], g[3];
     float rho, p;
@@ -46,10 +50,9 @@ struct PhysDensity {
                                float4* sq, int cap, int d) {
     sq[d] = f.pt[gp];
     if (MODE == DENS_SUM) {
-      if (ex.nq > 1) {
-        sq[cap + d] = f.um[gp];
-        sq[2 * cap + d] = f.st[gp];
-      }
+    } else if (MODE == DENS_SUM_X) {
+      sq[cap + d] = f.um[gp];
+      sq[2 * cap + d] = f.st[gp];
     } else if (MODE == DENS_EVOL_SPH) {
       float4 um = f.um[gp], st = f.st[gp];
       sq[cap + d] = make_float4(um.x, um.y, um.z, um.w / st.x);  // (mass / rho)[j], solver.py:26
@@ -61,7 +64,7 @@ struct PhysDensity {
   }
   __device__ static void load_own(const Consts& c, const Frame& f, const Extra& ex, int p,
                                   float4 pt, Own& o) {
-    if (MODE != DENS_SUM) {
+    if (!SUM) {
       float4 um = f.um[p];
       o.u[0] = um.x; o.u[1] = um.y; o.u[2] = um.z;
     }
@@ -82,10 +85,10 @@ struct PhysDensity {
                               float d2) {
     const float dist = fsqrt(d2);
     const int tag_j = __float_as_int(pj.w);
-    if (MODE == DENS_SUM || ex.utilde || ex.wallT) {
+    if (SUM || (XTRA && (ex.utilde || ex.wallT))) {
       const float w = kernel_w<KERN>(c, dist);
-      if (MODE == DENS_SUM) a.s += w;
-      if (ex.utilde || ex.wallT) {
+      if (SUM) a.s += w;
+      if (XTRA && (ex.utilde || ex.wallT)) {
         if (tag_j == SPHB200_TAG_FLUID) {
           const float4 uj = sq[cap + j];
           const float4 sj = sq[2 * cap + j];
@@ -136,7 +139,7 @@ struct PhysDensity {
     const float4 st = f.st[p];
     const int tag = __float_as_int(f.pt[p].w);
     float rho, drhodt = 0.f;
-    if (MODE == DENS_SUM) {
+    if (SUM) {
       const float rho_ = f.um[p].w * a.s;
       rho = (tag == SPHB200_TAG_FLUID) ? rho_ : st.x;  // solver.py:795-796
     } else if (MODE == DENS_EVOL_SPH) {
@@ -148,12 +151,12 @@ struct PhysDensity {
     }
     const float pnew = eos_p(c, rho);  // :801
     float T = st.z;
-    if (ex.wallT && (tag == SPHB200_TAG_SOLID_WALL || tag == SPHB200_TAG_MOVING_WALL))
+    if (XTRA && ex.wallT && (tag == SPHB200_TAG_SOLID_WALL || tag == SPHB200_TAG_MOVING_WALL))
       T = a.sT / (a.swf + c.eps);  // :556-565
     if (ex.finalT) T = T + c.dt_s * st.w;  // :834
     ex.st_out[p] = make_float4(rho, pnew, T, st.w);
-    if (MODE != DENS_SUM) reinterpret_cast<float*>(&f.du[p])[3] = drhodt;
-    if (ex.utilde) {
+    if (!SUM) reinterpret_cast<float*>(&f.du[p])[3] = drhodt;
+    if (XTRA && ex.utilde) {
       const float den = a.swf + c.eps;  // :547-552
       f.ut[p] = make_float4(a.su[0] / den, a.su[1] / den, a.su[2] / den, 0.f);
     }

@@ -35,6 +35,25 @@ struct SweepDims {
   int nq;    // quads staged per particle
 };
 
+// Per-step neighbour lists in HBM, shared by all sweeps of one forward():
+// the first sweep (density) BUILDS them from its phase-2 survivors, the later
+// sweeps (renorm / wall / force) CONSUME them and skip the search altogether.
+// Entries are STAGED indices (uint16): every sweep of a step stages a tile's
+// stencil in the same order, so the index means the same particle everywhere.
+// A particle's row is lmax entries, written in 16-byte chunks of 8.  A tile
+// whose stencil does not fit one staging group, or that holds a particle with
+// more than lmax neighbours, is marked not-ok and its consumers search on
+// their own (the list is an accelerator, never a correctness dependency).
+struct NList {
+  unsigned short* list;  // [n][lmax], nullptr = lists off
+  int* cnt;              // [n] neighbours stored for the particle
+  unsigned char* ok;     // [tiles]
+  int lmax;              // multiple of 8
+  int min_cap;           // smallest staging capacity among the step's sweeps
+};
+
+enum { LIST_NONE = 0, LIST_BUILD = 1, LIST_CONSUME = 2 };
+
 __host__ __device__ inline size_t sweep_smem_bytes(int nq, int cap, int lcap, int tpb) {
   return (size_t)nq * cap * 16 + (size_t)lcap * tpb * 2 + (MAX_SOFF + 1 + 2 * MAX_RUNS + 2) * 4;
 }
@@ -43,10 +62,10 @@ __host__ __device__ inline size_t sweep_smem_bytes(int nq, int cap, int lcap, in
 __device__ __forceinline__ int wrap_count(int u, int n) { return u < 0 ? -1 : (u >= n ? 1 : 0); }
 __device__ __forceinline__ int wrap_cell(int u, int n) { return u < 0 ? u + n : (u >= n ? u - n : u); }
 
-template <int DIM, class P>
+template <int DIM, class P, int LM = LIST_NONE>
 __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
     k_sweep(const Grid g, const Consts c, const Frame f, const int* __restrict__ cs,
-            const SweepDims sd, const Extra ex, unsigned* __restrict__ err) {
+            const SweepDims sd, const Extra ex, unsigned* __restrict__ err, const NList nl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int TPB = blockDim.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = TPB >> 5;
@@ -132,6 +151,15 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
   const int kz = -sa0[0], kn = g.n[0] - sa0[0];  // staged x index of unwrapped cells 0 and n
   const int nit = 2 * g.W[1] * g.W[2];
 
+  // neighbour-list mode of this block (uniform over the block, see NList)
+  __shared__ int s_bad;
+  bool nl_build = false, nl_use = false;
+  if (LM == LIST_BUILD) {
+    nl_build = nl.list != nullptr && total_staged <= nl.min_cap;
+    if (tid == 0) s_bad = nl_build ? 0 : 1;  // ordered before any other write by the staging barrier
+  }
+  if (LM == LIST_CONSUME) nl_use = nl.list != nullptr && nl.ok[blockIdx.x] != 0;
+
   for (int ib = 0; ib < tile_n; ib += TPB) {
     // ---- own particle ------------------------------------------------------
     const int t = ib + tid;
@@ -155,6 +183,7 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
       act = P::active(c, own);
     }
     P::init(acc);
+    int gk = 0, carry = 0;  // LIST_BUILD: entries already in HBM / survivors waiting in the column
     // window origin in staged coordinates
     int w0[3];
 #pragma unroll
@@ -210,7 +239,38 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
         }
         __syncthreads();
       }
-      if (!skip) {
+      if (!skip && LM == LIST_CONSUME && nl_use) {
+        // ---------------- list consumer: the neighbours were found by this step's density
+        // sweep; all lanes step through their rows together, every lane on a real pair ----
+        const int nn = (have && act) ? nl.cnt[p] : 0;
+        const uint4* lrow = reinterpret_cast<const uint4*>(nl.list + (size_t)p * nl.lmax);
+        uint4 cur = make_uint4(0u, 0u, 0u, 0u), nxt = cur;
+        if (nn > 0) nxt = __ldg(lrow);
+#pragma unroll 1
+        for (int k = 0; k < nn; ++k) {
+          if ((k & 7) == 0) {
+            cur = nxt;
+            if (k + 8 < nn) nxt = __ldg(lrow + (k >> 3) + 1);
+          }
+          const int jn = (int)(cur.x & 0xffffu);
+          cur.x = __funnelshift_r(cur.x, cur.y, 16);
+          cur.y = __funnelshift_r(cur.y, cur.z, 16);
+          cur.z = __funnelshift_r(cur.z, cur.w, 16);
+          cur.w >>= 16;
+          const float4 pj = sq[jn];
+          float dr[3];
+          if (interior) {
+            dr[0] = disp1_nowrap(ri[0], pj.x, g.half[0]);
+            dr[1] = disp1_nowrap(ri[1], pj.y, g.half[1]);
+            dr[2] = (DIM == 3) ? disp1_nowrap(ri[2], pj.z, g.half[2]) : 0.0f;
+          } else {
+            dr[0] = disp1(ri[0], pj.x, g.half[0], g.box[0]);
+            dr[1] = disp1(ri[1], pj.y, g.half[1], g.box[1]);
+            dr[2] = (DIM == 3) ? disp1(ri[2], pj.z, g.half[2], g.box[2]) : 0.0f;
+          }
+          P::pair(c, ex, own, acc, sq, sd.cap, jn, pj, dr, sumsq<DIM>(dr));
+        }
+      } else if (!skip) {
         // Walk the thread's window as 2 * W1 * W2 (row, x-segment) pieces.  All lanes
         // advance through the pieces together; a warp-wide vote switches to phase 2
         // whenever some lane's list cannot take the next chunk.
@@ -273,8 +333,9 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
             }
           }
           // ---------------- phase 2: real neighbours, exact arithmetic ----------------
+          int m = carry;
 #pragma unroll 1
-          for (int k = 0; k < cnt; ++k) {
+          for (int k = carry; k < cnt; ++k) {
             const int jn = list[k * TPB + tid];
             const float4 pj = sq[jn];
             float dr[3];
@@ -290,25 +351,72 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
             const float d2 = sumsq<DIM>(dr);
             if (d2 > g.c2_lo) {
               // rounding band: the reference decides membership on d(r_sender, r_receiver)
-              float m[3];
+              float mm[3];
               if (P::SENDER_VIEW) {
-                m[0] = dr[0]; m[1] = dr[1]; m[2] = dr[2];
+                mm[0] = dr[0]; mm[1] = dr[1]; mm[2] = dr[2];
               } else {
-                m[0] = disp1(pj.x, ri[0], g.half[0], g.box[0]);
-                m[1] = disp1(pj.y, ri[1], g.half[1], g.box[1]);
-                m[2] = (DIM == 3) ? disp1(pj.z, ri[2], g.half[2], g.box[2]) : 0.0f;
+                mm[0] = disp1(pj.x, ri[0], g.half[0], g.box[0]);
+                mm[1] = disp1(pj.y, ri[1], g.half[1], g.box[1]);
+                mm[2] = (DIM == 3) ? disp1(pj.z, ri[2], g.half[2], g.box[2]) : 0.0f;
               }
-              if (!(sumsq<DIM>(m) < g.c2)) continue;
+              if (!(sumsq<DIM>(mm) < g.c2)) continue;
+            }
+            if (LM == LIST_BUILD && nl_build) {  // keep the survivor, compacted in place (m <= k)
+              list[m * TPB + tid] = (unsigned short)jn;
+              ++m;
             }
             P::pair(c, ex, own, acc, sq, sd.cap, jn, pj, dr, d2);
           }
-          cnt = 0;
+          if (LM == LIST_BUILD && nl_build) {
+            // survivors [0, m) of the column -> HBM in chunks of 8; the remainder waits
+            unsigned short* col = list + tid;
+            int w = 0;
+            for (; m - w >= 8; w += 8) {
+              uint4 v;
+              v.x = (unsigned)col[(w + 0) * TPB] | ((unsigned)col[(w + 1) * TPB] << 16);
+              v.y = (unsigned)col[(w + 2) * TPB] | ((unsigned)col[(w + 3) * TPB] << 16);
+              v.z = (unsigned)col[(w + 4) * TPB] | ((unsigned)col[(w + 5) * TPB] << 16);
+              v.w = (unsigned)col[(w + 6) * TPB] | ((unsigned)col[(w + 7) * TPB] << 16);
+              if (gk + 8 <= nl.lmax)
+                *reinterpret_cast<uint4*>(nl.list + (size_t)p * nl.lmax + gk) = v;
+              else
+                s_bad = 1;
+              gk += 8;
+            }
+            const int r = m - w;
+            if (w > 0)
+              for (int i = 0; i < r; ++i) col[i * TPB] = col[(w + i) * TPB];
+            carry = r;
+            cnt = r;
+          } else {
+            cnt = 0;
+          }
           if (fin) break;
+        }
+        if (LM == LIST_BUILD && nl_build && have) {
+          // tail chunk (its unused slots are never read: cnt says how many are real)
+          if (carry > 0) {
+            const unsigned short* col = list + tid;
+            unsigned e8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e8[i] = i < carry ? (unsigned)col[i * TPB] : 0u;
+            if (gk + 8 <= nl.lmax)
+              *reinterpret_cast<uint4*>(nl.list + (size_t)p * nl.lmax + gk) =
+                  make_uint4(e8[0] | (e8[1] << 16), e8[2] | (e8[3] << 16), e8[4] | (e8[5] << 16),
+                             e8[6] | (e8[7] << 16));
+            else
+              s_bad = 1;
+          }
+          nl.cnt[p] = gk + carry;
         }
       }
       e_a = e_b;
     }
     if (have) P::finish(c, f, ex, p, own, acc);
+  }
+  if (LM == LIST_BUILD && nl.list != nullptr) {
+    __syncthreads();
+    if (tid == 0) nl.ok[blockIdx.x] = s_bad ? 0 : 1;
   }
 }
 

@@ -21,7 +21,7 @@ def make_config(
     p_ref=None, rho_ref=1.0, p_bg=0.0, gamma=1.0, u_ref=1.0, c_ref=10.0, eta_limiter=3.0,
     is_bc_trick=False, is_rho_evol=False, is_rho_renorm=False, is_free_slip=False,
     is_heat_conduction=False, artificial_alpha=0.0, g_ext_spec=None, bc_table=None,
-    cell_sub=None, tile=None, threads=0, list_cap=0, stage_cap=0, g_ext_array=False,
+    cell_sub=None, tile=None, threads=0, list_cap=0, stage_cap=0, nl_cap=0, g_ext_array=False,
     r_cutoff=0.0,
 ):
     """Build a `sphb200_config` from the WCSPH constructor arguments
@@ -108,6 +108,7 @@ def make_config(
             for a in range(3):
                 arr[a] = int(val[a]) if a < len(val) else 0
     cfg.threads, cfg.list_cap, cfg.stage_cap = threads, list_cap, stage_cap
+    cfg.nl_cap = nl_cap
     cfg.r_cutoff = float(r_cutoff)
     return cfg
 

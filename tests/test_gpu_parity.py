@@ -26,7 +26,11 @@ GOLDEN_CASES = {
 }
 FWD_KEYS = ("rho", "p", "u", "v", "dudt", "dvdt", "drhodt", "T", "dTdt")
 ADV_KEYS = ("r", "u", "v", "rho", "p", "T", "dudt", "dvdt")
-PLANS = {"default": {}, "coarse_cells": dict(cell_sub=[1, 1, 1], threads=128, list_cap=96)}
+# default: per-step neighbour lists built by the density sweep and consumed by the later sweeps;
+# no_lists: every sweep searches on its own; tiny_lists: rows of 16 overflow, so every tile falls
+# back to its own search (the list is an accelerator, never a correctness dependency)
+PLANS = {"default": {}, "coarse_cells": dict(cell_sub=[1, 1, 1], threads=128, list_cap=96),
+         "no_lists": dict(nl_cap=-1), "tiny_lists": dict(nl_cap=16)}
 
 
 def _setup(name):

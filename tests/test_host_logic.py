@@ -99,12 +99,16 @@ def test_engine_bytes_scale_with_features():
 
     lib = _lib.load()
 
-    def nbytes(setup, n=100000):
+    def nbytes(setup, n=100000, **tuning):
         b = C.c_size_t()
-        _lib.check(lib.sphb200_engine_bytes(C.byref(config_from_setup(setup)), n, C.byref(b)))
+        _lib.check(lib.sphb200_engine_bytes(C.byref(config_from_setup(setup, **tuning)), n, C.byref(b)))
         return b.value
 
-    plain = nbytes(cases.make_case("tgv", dim=3, dx=0.2, dtype=np.float32))
-    heat = nbytes(cases.make_case("ht", dim=3, dx=0.05, dtype=np.float32))
+    tgv = cases.make_case("tgv", dim=3, dx=0.2, dtype=np.float32)
+    plain = nbytes(tgv, nl_cap=-1)
+    heat = nbytes(cases.make_case("ht", dim=3, dx=0.05, dtype=np.float32), nl_cap=-1)
     assert 200 * 100000 < plain < 260 * 100000  # ~212 B / particle + cell tables
     assert heat > plain  # kappa / Cp carried only when heat conduction is on
+    # per-step neighbour lists: rows of 1.3 x 113 + 8 -> 160 uint16 entries + a count per particle
+    lists = nbytes(tgv) - plain
+    assert 160 * 2 * 100000 <= lists < (160 * 2 + 4 + 1) * 100000 + 4096
