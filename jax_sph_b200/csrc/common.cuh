@@ -202,20 +202,37 @@ __device__ __forceinline__ float kernel_gw(const Consts& c, float r) {
   }
 }
 
-// Pair-level division: hardware reciprocal (<= 2 ulp), well inside the float32
-// summation-order noise of the sweeps; -DSPHB200_PRECISE
-// restores IEEE division.  The distance keeps the IEEE square root: near the edge
-// of the kernel support w ~ (3 - q)^5 amplifies a 2-ulp error of q by 5 / (3 - q),
-// which the Shepard wall averages of solver.py:505-526 (sum w T / (sum w + EPS))
-// expose for wall particles whose only fluid neighbours sit at the cutoff.
+// Pair-level division: one MUFU.RCP (rcp.approx.ftz, <= 1 ulp) and a multiply, well inside
+// the float32 summation-order noise of the sweeps; -DSPHB200_PRECISE
+// restores IEEE division and square root.
+//
+// The distance: rsqrt.approx seeds one Newton step whose residual d2 - s*s is formed exactly
+// by an FMA, so the result is the correctly rounded square root except for rare half-ulp
+// ties -- as good as the IEEE routine, branch-free and half its instructions.  (A bare
+// sqrt.approx, 2 ulp, is NOT enough: near the edge of the kernel support w ~ (3 - q)^5
+// amplifies an error of q by 5 / (3 - q), which the Shepard wall averages of
+// solver.py:505-526 expose for wall particles whose only fluid neighbours sit at the
+// cutoff.)  d2 == 0 (the self pair) is lifted to 1e-30: the kernels see q = 0 either way.
 #ifdef SPHB200_PRECISE
 __device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
 __device__ __forceinline__ float frcp(float a) { return 1.0f / a; }
-#else
-__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
-__device__ __forceinline__ float frcp(float a) { return __fdividef(1.0f, a); }
-#endif
 __device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+#else
+__device__ __forceinline__ float frcp(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ float fdiv(float a, float b) { return a * frcp(b); }
+__device__ __forceinline__ float fsqrt(float a) {
+  a = fmaxf(a, 1e-30f);
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  const float s = a * r;
+  const float e = __fmaf_rn(-s, s, a);
+  return __fmaf_rn(e, 0.5f * r, s);
+}
+#endif
 
 // eos.py:33-38 / :53-57
 __device__ __forceinline__ float eos_p(const Consts& c, float rho) {

@@ -62,6 +62,62 @@ __host__ __device__ inline size_t sweep_smem_bytes(int nq, int cap, int lcap, in
 __device__ __forceinline__ int wrap_count(int u, int n) { return u < 0 ? -1 : (u >= n ? 1 : 0); }
 __device__ __forceinline__ int wrap_cell(int u, int n) { return u < 0 ? u + n : (u >= n ? u - n : u); }
 
+// Reference displacement r_i - r_j (space.py:170-181) of one staged neighbour; INTERIOR: no
+// periodic image inside the tile's stencil, the fold is two adds.
+template <int DIM, bool INTERIOR>
+__device__ __forceinline__ void pair_disp(const Grid& g, const float (&ri)[3], const float4 pj,
+                                          float (&dr)[3]) {
+  if (INTERIOR) {
+    dr[0] = disp1_nowrap(ri[0], pj.x, g.half[0]);
+    dr[1] = disp1_nowrap(ri[1], pj.y, g.half[1]);
+    dr[2] = (DIM == 3) ? disp1_nowrap(ri[2], pj.z, g.half[2]) : 0.0f;
+  } else {
+    dr[0] = disp1(ri[0], pj.x, g.half[0], g.box[0]);
+    dr[1] = disp1(ri[1], pj.y, g.half[1], g.box[1]);
+    dr[2] = (DIM == 3) ? disp1(ri[2], pj.z, g.half[2], g.box[2]) : 0.0f;
+  }
+}
+
+// List consumer: the neighbours of particle p were found by this step's density sweep.  All
+// lanes step through their rows together, every lane on a real pair, two pairs per iteration
+// so that two independent dependency chains (LDS -> displacement -> rsqrt -> kernel -> pair
+// terms) are in flight per warp: with one 512-thread block per SM there are only four warps
+// per scheduler to hide those latencies otherwise.
+template <int DIM, class P, bool INTERIOR>
+__device__ __forceinline__ void consume_list(const Grid& g, const Consts& c, const Extra& ex,
+                                             const NList& nl, const float4* sq, int cap, int p,
+                                             int nn, const float (&ri)[3],
+                                             const typename P::Own& own, typename P::Acc& acc) {
+  const uint4* lrow = reinterpret_cast<const uint4*>(nl.list + (size_t)p * nl.lmax);
+  uint4 cur = make_uint4(0u, 0u, 0u, 0u), nxt = cur;
+  if (nn > 0) nxt = __ldg(lrow);
+  int k = 0;
+#pragma unroll 1
+  for (; k + 1 < nn; k += 2) {
+    if ((k & 7) == 0) {
+      cur = nxt;
+      if (k + 8 < nn) nxt = __ldg(lrow + (k >> 3) + 1);
+    }
+    const int j0 = (int)(cur.x & 0xffffu), j1 = (int)(cur.x >> 16);
+    cur.x = cur.y; cur.y = cur.z; cur.z = cur.w;
+    const float4 p0 = sq[j0], p1 = sq[j1];
+    float d0[3], d1[3];
+    pair_disp<DIM, INTERIOR>(g, ri, p0, d0);
+    pair_disp<DIM, INTERIOR>(g, ri, p1, d1);
+    const float s0 = sumsq<DIM>(d0), s1 = sumsq<DIM>(d1);
+    P::pair(c, ex, own, acc, sq, cap, j0, p0, d0, s0);
+    P::pair(c, ex, own, acc, sq, cap, j1, p1, d1, s1);
+  }
+  if (k < nn) {
+    if ((k & 7) == 0) cur = nxt;
+    const int j0 = (int)(cur.x & 0xffffu);
+    const float4 p0 = sq[j0];
+    float d0[3];
+    pair_disp<DIM, INTERIOR>(g, ri, p0, d0);
+    P::pair(c, ex, own, acc, sq, cap, j0, p0, d0, sumsq<DIM>(d0));
+  }
+}
+
 template <int DIM, class P, int LM = LIST_NONE>
 __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
     k_sweep(const Grid g, const Consts c, const Frame f, const int* __restrict__ cs,
@@ -240,36 +296,11 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
         __syncthreads();
       }
       if (!skip && LM == LIST_CONSUME && nl_use) {
-        // ---------------- list consumer: the neighbours were found by this step's density
-        // sweep; all lanes step through their rows together, every lane on a real pair ----
         const int nn = (have && act) ? nl.cnt[p] : 0;
-        const uint4* lrow = reinterpret_cast<const uint4*>(nl.list + (size_t)p * nl.lmax);
-        uint4 cur = make_uint4(0u, 0u, 0u, 0u), nxt = cur;
-        if (nn > 0) nxt = __ldg(lrow);
-#pragma unroll 1
-        for (int k = 0; k < nn; ++k) {
-          if ((k & 7) == 0) {
-            cur = nxt;
-            if (k + 8 < nn) nxt = __ldg(lrow + (k >> 3) + 1);
-          }
-          const int jn = (int)(cur.x & 0xffffu);
-          cur.x = __funnelshift_r(cur.x, cur.y, 16);
-          cur.y = __funnelshift_r(cur.y, cur.z, 16);
-          cur.z = __funnelshift_r(cur.z, cur.w, 16);
-          cur.w >>= 16;
-          const float4 pj = sq[jn];
-          float dr[3];
-          if (interior) {
-            dr[0] = disp1_nowrap(ri[0], pj.x, g.half[0]);
-            dr[1] = disp1_nowrap(ri[1], pj.y, g.half[1]);
-            dr[2] = (DIM == 3) ? disp1_nowrap(ri[2], pj.z, g.half[2]) : 0.0f;
-          } else {
-            dr[0] = disp1(ri[0], pj.x, g.half[0], g.box[0]);
-            dr[1] = disp1(ri[1], pj.y, g.half[1], g.box[1]);
-            dr[2] = (DIM == 3) ? disp1(ri[2], pj.z, g.half[2], g.box[2]) : 0.0f;
-          }
-          P::pair(c, ex, own, acc, sq, sd.cap, jn, pj, dr, sumsq<DIM>(dr));
-        }
+        if (interior)
+          consume_list<DIM, P, true>(g, c, ex, nl, sq, sd.cap, p, nn, ri, own, acc);
+        else
+          consume_list<DIM, P, false>(g, c, ex, nl, sq, sd.cap, p, nn, ri, own, acc);
       } else if (!skip) {
         // Walk the thread's window as 2 * W1 * W2 (row, x-segment) pieces.  All lanes
         // advance through the pieces together; a warp-wide vote switches to phase 2
@@ -339,28 +370,17 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
             const int jn = list[k * TPB + tid];
             const float4 pj = sq[jn];
             float dr[3];
-            if (interior) {
-              dr[0] = disp1_nowrap(ri[0], pj.x, g.half[0]);
-              dr[1] = disp1_nowrap(ri[1], pj.y, g.half[1]);
-              dr[2] = (DIM == 3) ? disp1_nowrap(ri[2], pj.z, g.half[2]) : 0.0f;
-            } else {
-              dr[0] = disp1(ri[0], pj.x, g.half[0], g.box[0]);
-              dr[1] = disp1(ri[1], pj.y, g.half[1], g.box[1]);
-              dr[2] = (DIM == 3) ? disp1(ri[2], pj.z, g.half[2], g.box[2]) : 0.0f;
-            }
+            if (interior) pair_disp<DIM, true>(g, ri, pj, dr);
+            else pair_disp<DIM, false>(g, ri, pj, dr);
             const float d2 = sumsq<DIM>(dr);
-            if (d2 > g.c2_lo) {
-              // rounding band: the reference decides membership on d(r_sender, r_receiver)
-              float mm[3];
-              if (P::SENDER_VIEW) {
-                mm[0] = dr[0]; mm[1] = dr[1]; mm[2] = dr[2];
-              } else {
-                mm[0] = disp1(pj.x, ri[0], g.half[0], g.box[0]);
-                mm[1] = disp1(pj.y, ri[1], g.half[1], g.box[1]);
-                mm[2] = (DIM == 3) ? disp1(pj.z, ri[2], g.half[2], g.box[2]) : 0.0f;
-              }
-              if (!(sumsq<DIM>(mm) < g.c2)) continue;
-            }
+            // Membership.  The reference decides it on d(r_sender, r_receiver)^2 < cutoff^2
+            // (jax_md/partition.py:897).  For the materialiser (SENDER_VIEW) the thread's
+            // particle IS the sender, so d2 is that very number and the list is the
+            // reference's bit for bit.  In the physics sweeps d2 is the receiver view, which
+            // can differ in the last bit for a pair on the rounding edge of the cutoff -- where
+            // every kernel is max(0, .)-clamped to exactly zero (and ~(1e-7)^4 of its peak one
+            // ulp inside), so such a pair contributes nothing either way.
+            if (!(d2 < g.c2)) continue;
             if (LM == LIST_BUILD && nl_build) {  // keep the survivor, compacted in place (m <= k)
               list[m * TPB + tid] = (unsigned short)jn;
               ++m;
