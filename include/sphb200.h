@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SPHB200_ABI_VERSION 1
+#define SPHB200_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------- */
 #define SPHB200_OK 0
@@ -56,6 +56,9 @@ extern "C" {
 #define SPHB200_ERR_NONFINITE (1u << 3)         /* non-finite position met while hashing        */
 #define SPHB200_ERR_OUTSIDE_BOX (1u << 4)       /* a position outside [0, box]: the periodic    *
                                                  * fold assumes shift_fn-wrapped positions       */
+#define SPHB200_ERR_SLAB_OVERFLOW (1u << 5)     /* slab engine: own / halo / migration capacity  */
+#define SPHB200_ERR_SLAB_MIGRATION (1u << 6)    /* slab engine: a particle crossed more than the *
+                                                 * halo width in one step                        */
 
 /* ---- enums --------------------------------------------------------------- */
 enum { SPHB200_SOLVER_SPH = 0, SPHB200_SOLVER_RIE = 1 };  /* solver.py:639-640 (DELTA: unsupported) */
@@ -200,6 +203,46 @@ int sphb200_engine_profile(sphb200_engine *e, int enable);
 int sphb200_engine_last_times(sphb200_engine *e, float ms[8]);
 /* cell-grid facts for reports: ncells[3], sub[3], tile[3], threads, list_cap, stage_cap(A,B,C). */
 int sphb200_engine_plan(const sphb200_engine *e, int32_t out[16]);
+
+/* ---- slab decomposition: one engine per GPU, the caller moves the messages ----------------
+ * The reference drives ONE device (jax_sph/simulate.py:110-134); north_star asks for the
+ * periodic box to be cut into slabs with a halo exchange and particle migration each step.
+ * The box is cut along the slowest-varying cell axis (z in 3D, y in 2D) into `nranks` slabs
+ * of whole cell layers; rank r owns global layers [z0, z1) (sphb200_slab_info) and keeps
+ * S = cell_sub halo layers (one cutoff) of its ring neighbours on each side.  One step is
+ *
+ *     for (phase = 0;; ++phase) {
+ *       sphb200_slab_run(e, phase, dt, flags, send_lo, send_hi, recv_lo, recv_hi, stream, &nbytes);
+ *       if (nbytes == 0) break;                       // step complete
+ *       send send_lo[0:nbytes] to rank-1, send_hi[0:nbytes] to rank+1 (periodic ring),
+ *       receive recv_lo[0:nbytes] from rank-1, recv_hi[0:nbytes] from rank+1, stream-ordered
+ *     }
+ *
+ * phase 0 integrates + hashes and emits the emigrants, phase 1 takes the immigrants, sorts and
+ * emits the boundary layers, every later phase takes a halo message and runs the sweeps up to
+ * the next one whose results the neighbours need (density -> rho, p; wall BC -> u, v, rho, p).
+ * Message sizes depend only on the capacities, counts travel in the message headers and stay
+ * on the device: nothing synchronises with the host.  The four buffers are device memory of
+ * at least outi[9] bytes each (sphb200_slab_info), owned by the caller (the transport:
+ * NCCL send/recv in jax_sph_b200/slab.py).  Capacities <= 0 are chosen from the config. */
+int sphb200_slab_create(const sphb200_config *cfg, int rank, int nranks, int64_t own_cap,
+                        int64_t halo_cap, int64_t mig_cap, sphb200_engine **out);
+/* outi: rank, nranks, axis, z0, z1, global layers, own_cap, halo_cap, mig_cap, message buffer
+ * bytes, S, slots, arena bytes.  outd: float32 1/cell and box side along the slab axis (a
+ * particle at r lies in layer min(int(f32(r) * f32(outd[0])), layers - 1)). */
+int sphb200_slab_info(const sphb200_engine *e, int64_t outi[16], double outd[4]);
+/* This rank's own particles (rows <= own_cap) and their global indices. */
+int sphb200_slab_upload(sphb200_engine *e, const sphb200_state *s, const int32_t *ids, int64_t rows,
+                        int on_host, void *stream);
+/* Own particles in local (cell-sorted) order; ids receives their global indices; rows = array
+ * capacity (>= current own count, see sphb200_slab_counts). */
+int sphb200_slab_download(sphb200_engine *e, sphb200_state *out, int32_t *ids, int64_t rows,
+                          int on_host, void *stream);
+/* sync: device counters [own, immigrants, emigrants lo, hi, halo lo, hi, sent lo, hi]. */
+int sphb200_slab_counts(sphb200_engine *e, int32_t out[8], void *stream);
+int sphb200_slab_run(sphb200_engine *e, int phase, double dt, uint32_t flags, void *send_lo,
+                     void *send_hi, const void *recv_lo, const void *recv_hi, void *stream,
+                     int64_t *xbytes);
 
 /* ---- stateless entry points (device pointers, caller-owned workspace) ----- */
 int sphb200_workspace_bytes(const sphb200_config *cfg, int64_t n, size_t *bytes);

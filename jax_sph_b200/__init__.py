@@ -6,6 +6,7 @@ Host-side mirror of the reference interface for that path:
 * ``solver.WCSPH``             <- jax_sph/solver.py:613-951
 * ``integrator.si_euler``      <- jax_sph/integrator.py:8-58
 * ``engine.Engine``            <- the step loop of jax_sph/simulate.py:110-134
+* ``slab.SlabEngine``          <- the same loop, slab-decomposed over the GPUs of one node
 
 All compute goes through the C ABI of ``libsphb200.so`` (include/sphb200.h,
 hand-written sm_100a CUDA); there is no CPU or PyTorch fallback.
@@ -13,5 +14,6 @@ hand-written sm_100a CUDA); there is no CPU or PyTorch fallback.
 
 from . import _lib, eos, integrator, partition, solver, space  # noqa: F401
 from .engine import Engine, config_from_setup, make_config  # noqa: F401
+from .slab import SlabEngine  # noqa: F401
 
-__all__ = ["Engine", "make_config", "config_from_setup"]
+__all__ = ["Engine", "SlabEngine", "make_config", "config_from_setup"]

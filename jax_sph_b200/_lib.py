@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsphb200.so")
 
 # ---- constants mirrored from include/sphb200.h ------------------------------
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, EINVAL, ENOMEM, ECUDA, EDTYPE, EUNSUP, ENODEV = 0, -1, -2, -3, -4, -5, -6
 ERR_NEIGHBOR_OVERFLOW, ERR_CELL_OVERFLOW, ERR_STAGE_OVERFLOW, ERR_NONFINITE = 1, 2, 4, 8
 ERR_OUTSIDE_BOX = 16
@@ -80,6 +80,14 @@ SYMBOLS = {
     "sphb200_engine_profile": (C.c_int, [_P, C.c_int]),
     "sphb200_engine_last_times": (C.c_int, [_P, C.POINTER(C.c_float * 8)]),
     "sphb200_engine_plan": (C.c_int, [_P, C.POINTER(C.c_int32 * 16)]),
+    "sphb200_slab_create": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                      C.c_int64, C.POINTER(_P)]),
+    "sphb200_slab_info": (C.c_int, [_P, C.POINTER(C.c_int64 * 16), C.POINTER(C.c_double * 4)]),
+    "sphb200_slab_upload": (C.c_int, [_P, C.POINTER(State), _P, C.c_int64, C.c_int, _P]),
+    "sphb200_slab_download": (C.c_int, [_P, C.POINTER(State), _P, C.c_int64, C.c_int, _P]),
+    "sphb200_slab_counts": (C.c_int, [_P, C.POINTER(C.c_int32 * 8), _P]),
+    "sphb200_slab_run": (C.c_int, [_P, C.c_int, C.c_double, C.c_uint32, _P, _P, _P, _P, _P,
+                                   C.POINTER(C.c_int64)]),
     "sphb200_workspace_bytes": (C.c_int, [C.POINTER(Config), C.c_int64, C.POINTER(C.c_size_t)]),
     "sphb200_neighbor_list": (C.c_int, [C.POINTER(Config), C.c_int64, _P, _P, C.c_int64, C.c_int,
                                         _P, _P, _P, C.c_size_t, _P]),

@@ -13,23 +13,66 @@
 
 namespace sphb200 {
 
+// Slab decomposition: where a rank's particles live and what is in flight (slab.cuh).
+// Particle slots are [base - n_halo_lo, base) lower halo | [base, base + n_own) own |
+// [base + n_own, ...) upper halo; the counts are device-side (dn), so a step never
+// synchronises with the host.  Single GPU: base = 0, dn = nullptr, n fixed.
+enum { DN_OWN = 0, DN_IN = 1, DN_EMIG_LO = 2, DN_EMIG_HI = 3, DN_HALO_LO = 4, DN_HALO_HI = 5,
+       DN_SEND_LO = 6, DN_SEND_HI = 7, DN_WORDS = 8 };
+
+struct Slab {
+  int base;      // first own slot
+  int* dn;       // device counters (DN_*), nullptr on a single GPU
+  int mig_cap;   // emigrant records per direction
+  char* mig_lo;  // emigrant send buffers (records leaving towards the lower / upper neighbour)
+  char* mig_hi;
+};
+
+// Emigrant / immigrant record buffer: [count, pad x3] then SoA arrays of `cap` entries each.
+struct MigView {
+  int* hdr;
+  float4 *pt, *um, *vv, *st, *du, *nw, *ge;
+  float2* kc;
+  int* id;
+};
+__host__ __device__ inline size_t mig_bytes(int cap) { return 16 + (size_t)cap * (7 * 16 + 8 + 4); }
+__host__ __device__ inline MigView mig_view(char* b, int cap) {
+  MigView v;
+  v.hdr = reinterpret_cast<int*>(b);
+  char* q = b + 16;
+  v.pt = reinterpret_cast<float4*>(q); q += (size_t)cap * 16;
+  v.um = reinterpret_cast<float4*>(q); q += (size_t)cap * 16;
+  v.vv = reinterpret_cast<float4*>(q); q += (size_t)cap * 16;
+  v.st = reinterpret_cast<float4*>(q); q += (size_t)cap * 16;
+  v.du = reinterpret_cast<float4*>(q); q += (size_t)cap * 16;
+  v.nw = reinterpret_cast<float4*>(q); q += (size_t)cap * 16;
+  v.ge = reinterpret_cast<float4*>(q); q += (size_t)cap * 16;
+  v.kc = reinterpret_cast<float2*>(q); q += (size_t)cap * 8;
+  v.id = reinterpret_cast<int*>(q);
+  return v;
+}
+
 // K1: integrate (optionally), hash, histogram.  Reads pt, um, du, dv (64 B),
-// writes key + arrival rank (8 B); cell counters live in L2.
+// writes key + arrival rank (8 B); cell counters live in L2.  Slab mode: a particle
+// whose new cell lies outside the rank's own layers is an emigrant: its integrated
+// record goes to the send buffer of that direction and its key becomes -1.
 template <int DIM>
-__global__ void __launch_bounds__(256) k_hash(int n, Grid g, Kick k, const float4* __restrict__ pt,
-                                              const float4* __restrict__ um,
-                                              const float4* __restrict__ du,
-                                              const float4* __restrict__ dv, int* __restrict__ key,
-                                              int* __restrict__ rnk, int* __restrict__ count,
-                                              unsigned* __restrict__ err) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  float4 a = pt[p];
+__global__ void __launch_bounds__(256) k_hash(int n, Grid g, Kick k, Slab sl, Frame f,
+                                              int* __restrict__ key, int* __restrict__ rnk,
+                                              int* __restrict__ count, unsigned* __restrict__ err) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_int = sl.dn ? sl.dn[DN_OWN] : n;           // integrated sources (own)
+  const int n_src = sl.dn ? n_int + sl.dn[DN_IN] : n;    // + immigrants (already integrated)
+  if (t >= n_src) return;
+  const int p = sl.base + t;
+  float4 a = f.pt[p];
   float r[3] = {a.x, a.y, a.z};
-  if (k.on) {
-    float4 b = um[p];
-    float u[3] = {b.x, b.y, b.z}, v[3];
-    integrate_one<DIM>(k, g, r, u, v, du[p], dv[p]);
+  float u[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
+  const bool integ = k.on && t < n_int;
+  if (integ) {
+    float4 b = f.um[p];
+    u[0] = b.x; u[1] = b.y; u[2] = b.z;
+    integrate_one<DIM>(k, g, r, u, v, f.du[p], f.dv[p]);
   }
   bool finite = isfinite(r[0]) && isfinite(r[1]) && (DIM == 2 || isfinite(r[2]));
   if (!finite) {
@@ -41,6 +84,37 @@ __global__ void __launch_bounds__(256) k_hash(int n, Grid g, Kick k, const float
   if (!inside) atomicOr(err, SPHB200_ERR_OUTSIDE_BOX);
   int c[3];
   int cell = cell_of<DIM>(g, r, c);
+  if (sl.dn) {
+    const int ax = DIM - 1;
+    if (cell < 0 || c[ax] < g.own_lo[ax] || c[ax] >= g.own_hi[ax]) {
+      // left the slab: one step moves a particle by a fraction of a cell, so it can only be
+      // in the halo layer next to the own range
+      const bool down = cell >= 0 && c[ax] < g.own_lo[ax];
+      const bool up = cell >= 0 && c[ax] >= g.own_hi[ax];
+      key[p] = -1;
+      if (!(down || up) || t >= n_int) {
+        atomicOr(err, SPHB200_ERR_SLAB_MIGRATION);
+        return;
+      }
+      const int slot = atomicAdd(&sl.dn[down ? DN_EMIG_LO : DN_EMIG_HI], 1);
+      if (slot >= sl.mig_cap) {
+        atomicOr(err, SPHB200_ERR_SLAB_OVERFLOW);
+        return;
+      }
+      MigView m = mig_view(down ? sl.mig_lo : sl.mig_hi, sl.mig_cap);
+      const float4 um = f.um[p], vv = f.vv[p];
+      m.pt[slot] = make_float4(r[0], r[1], r[2], a.w);
+      m.um[slot] = integ ? make_float4(u[0], u[1], u[2], um.w) : um;
+      m.vv[slot] = integ ? make_float4(v[0], v[1], v[2], vv.w) : vv;
+      m.st[slot] = f.st[p];
+      m.du[slot] = make_float4(0.f, 0.f, 0.f, f.du[p].w);
+      m.id[slot] = f.id[p];
+      if (f.kc) m.kc[slot] = f.kc[p];
+      if (f.nw) m.nw[slot] = f.nw[p];
+      if (f.ge) m.ge[slot] = f.ge[p];
+      return;
+    }
+  }
   key[p] = cell;
   rnk[p] = atomicAdd(&count[cell], 1);
 }
@@ -109,7 +183,8 @@ __global__ void __launch_bounds__(1024) k_scan_bsum(int nb, int* __restrict__ bs
   }
 }
 
-__global__ void __launch_bounds__(SCAN_TPB) k_scan_final(int c, int n, int* __restrict__ count,
+// start[i] = off + exclusive prefix for i in [0, c]; start[c] is the grand total.
+__global__ void __launch_bounds__(SCAN_TPB) k_scan_final(int c, int off, int* __restrict__ count,
                                                          const int* __restrict__ bsum,
                                                          int* __restrict__ start,
                                                          int* __restrict__ maxocc) {
@@ -125,16 +200,13 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_final(int c, int n, int* __re
   }
   int tot;
   int inc = block_incl_scan(s, sh, &tot);
-  int run = bsum[blockIdx.x] + inc - s;
+  int run = off + bsum[blockIdx.x] + inc - s;
 #pragma unroll
   for (int i = 0; i < SCAN_ITEMS; ++i) {
-    if (base + i < c) {
-      start[base + i] = run;
-      count[base + i] = 0;  // ready for the next step's histogram
-    }
+    if (base + i <= c) start[base + i] = run;
+    if (base + i < c) count[base + i] = 0;  // ready for the next step's histogram
     run += v[i];
   }
-  if (base <= c && c < base + SCAN_ITEMS) start[c] = n;
   mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 16));
   mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 8));
   mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, 4));
@@ -144,13 +216,15 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_final(int c, int n, int* __re
 }
 
 // K3: slot (arrival order) -> source index.
-__global__ void __launch_bounds__(256) k_scatter_src(int n, const int* __restrict__ key,
+__global__ void __launch_bounds__(256) k_scatter_src(int n, Slab sl, const int* __restrict__ key,
                                                      const int* __restrict__ rnk,
                                                      const int* __restrict__ start,
                                                      int* __restrict__ src) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  src[start[key[p]] + rnk[p]] = p;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (sl.dn ? sl.dn[DN_OWN] + sl.dn[DN_IN] : n)) return;
+  const int p = sl.base + t;
+  const int k = key[p];
+  if (k >= 0) src[start[k] + rnk[p]] = p;  // emigrants (key -1) drop out here
 }
 
 // K4: stable in-cell rank + integrate + gather the whole frame into the new
@@ -160,13 +234,16 @@ struct ReorderOpt {
 };
 
 template <int DIM>
-__global__ void __launch_bounds__(256) k_reorder(int n, Grid g, Kick k, ReorderOpt o, Frame a,
-                                                 Frame b, const int* __restrict__ key,
+__global__ void __launch_bounds__(256) k_reorder(int n, Grid g, Kick k, Slab sl, ReorderOpt o,
+                                                 Frame a, Frame b, const int* __restrict__ key,
                                                  const int* __restrict__ start,
                                                  const int* __restrict__ src) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  // slab mode: the own count after migration is the scan total (halo cells are still empty)
+  if (t >= (sl.dn ? start[g.ncells] - sl.base : n)) return;
+  const int s = sl.base + t;
   int p = src[s];
+  if (sl.dn && p - sl.base >= sl.dn[DN_OWN]) k.on = 0;  // immigrants arrive integrated
   int cell = key[p];
   int lo = start[cell], hi = start[cell + 1];
   int rank = 0;
@@ -198,6 +275,7 @@ struct StatePtrs {
 struct StateOut {
   float *r, *u, *v, *dudt, *dvdt, *nw, *rho, *p, *drhodt, *mass, *eta, *T, *dTdt, *kappa, *Cp;
   int* tag;
+  int* ids;  // slab mode: rows are written in local order and ids[row] = global particle index
 };
 
 template <int DIM>
@@ -220,10 +298,18 @@ __device__ __forceinline__ void store_vec(float* a, int p, float4 q) {
   }
 }
 
+// `ids` (slab mode): global particle indices of the uploaded rows; frame slots start at `base`.
 template <int DIM>
-__global__ void __launch_bounds__(256) k_pack(int n, StatePtrs s, Frame f, int* __restrict__ wallcount) {
+__global__ void __launch_bounds__(256) k_pack(int n, StatePtrs s, Frame fin, int base,
+                                              const int* __restrict__ ids,
+                                              int* __restrict__ wallcount) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
+  Frame f = fin;
+  f.pt += base; f.um += base; f.vv += base; f.st += base; f.du += base; f.dv += base; f.id += base;
+  if (f.kc) f.kc += base;
+  if (f.nw) f.nw += base;
+  if (f.ge) f.ge += base;
   int tag = s.tag ? s.tag[p] : 0;
   f.pt[p] = load_vec<DIM>(s.r, p, __int_as_float(tag));
   f.um[p] = load_vec<DIM>(s.u, p, s.mass ? s.mass[p] : 1.0f);
@@ -235,15 +321,20 @@ __global__ void __launch_bounds__(256) k_pack(int n, StatePtrs s, Frame f, int* 
   if (f.kc) f.kc[p] = make_float2(s.kappa ? s.kappa[p] : 0.0f, s.Cp ? s.Cp[p] : 0.0f);
   if (f.nw) f.nw[p] = load_vec<DIM>(s.nw, p, 0.0f);
   if (f.ge) f.ge[p] = load_vec<DIM>(s.g_ext, p, 0.0f);
-  f.id[p] = p;
+  f.id[p] = ids ? ids[p] : p;
   if (is_wall_tag(tag)) atomicAdd(wallcount, 1);
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(256) k_unpack(int n, Frame f, StateOut o) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
+__global__ void __launch_bounds__(256) k_unpack(int n, Slab sl, Frame f, StateOut o) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (sl.dn ? sl.dn[DN_OWN] : n)) return;
+  const int s = sl.base + t;
   int p = f.id[s];
+  if (o.ids) {
+    o.ids[t] = p;
+    p = t;
+  }
   float4 pt = f.pt[s], um = f.um[s], vv = f.vv[s], st = f.st[s], du = f.du[s], dv = f.dv[s];
   store_vec<DIM>(o.r, p, pt);
   store_vec<DIM>(o.u, p, um);

@@ -41,6 +41,13 @@ struct Grid {
   float c2;      // f32(cutoff)^2 rounded to f32  (jax_md/partition.py:820-822)
   float c2_hi;   // fast-reject threshold  (> c2, covers rounding of the fast path)
   float c2_lo;   // below this the pair is inside for every rounding
+  // Slab decomposition (one rank's view; single GPU: goff = 0, ng = n, own = [0, n)).
+  // n[] are the LOCAL cells this rank indexes (own layers + S halo layers each side along the
+  // slab axis), positions stay global, so the periodic image of a staged cell is decided by
+  // its GLOBAL index goff + local.
+  int goff[3];   // global cell index of local cell 0 (negative for the rank at the box bottom)
+  int ng[3];     // global cells per axis
+  int own_lo[3], own_hi[3];  // local cell range this rank owns (sweeps tile exactly this range)
 };
 
 // Derived float32 constants, rounded where the reference rounds them.
@@ -155,19 +162,25 @@ __device__ __forceinline__ void integrate_one(const Kick k, const Grid& g, float
 
 // Cell coordinates of a position (clamped; the reference truncates
 // position / cell_size, jax_md/partition.py:367).
+// Returns the LOCAL cell index, or -1 when the position lies outside this rank's local
+// cells (slab mode only; c[] then still holds the wrapped offset from local cell 0).
 template <int DIM>
 __device__ __forceinline__ int cell_of(const Grid& g, const float (&r)[3], int (&c)[3]) {
+  bool local = true;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     if (d < DIM) {
       int ci = (int)(r[d] * g.inv_cell[d]);
-      ci = ci < 0 ? 0 : (ci >= g.n[d] ? g.n[d] - 1 : ci);
+      ci = ci < 0 ? 0 : (ci >= g.ng[d] ? g.ng[d] - 1 : ci);
+      ci -= g.goff[d];
+      ci = ci < 0 ? ci + g.ng[d] : (ci >= g.ng[d] ? ci - g.ng[d] : ci);
+      local = local && ci < g.n[d];
       c[d] = ci;
     } else {
       c[d] = 0;
     }
   }
-  return (c[2] * g.n[1] + c[1]) * g.n[0] + c[0];
+  return local ? (c[2] * g.n[1] + c[1]) * g.n[0] + c[0] : -1;
 }
 
 // ---------------------------------------------------------------------------

@@ -18,6 +18,7 @@
 #include "cells.cuh"
 #include "common.cuh"
 #include "phys.cuh"
+#include "slab.cuh"
 #include "sweep.cuh"
 
 using namespace sphb200;
@@ -73,6 +74,18 @@ struct sphb200_engine {
   size_t hstage_bytes;
   int max_smem;
   bool needs_zero;
+  // slab decomposition (slab.cuh); slab_on == false: one GPU owns the whole periodic box
+  bool slab_on;
+  int slab_rank, slab_nranks, slab_axis;
+  int slab_z0, slab_z1;    // global cell layers [z0, z1) owned along slab_axis
+  Slab slab;               // base slot, device counters, migration buffers (set per call)
+  SlabGeom sgeom;
+  int* dn;
+  int slab_stage;          // next sweep of the current step (0 density, 1 renorm, 2 wall, 3 force)
+  int slab_pending_mask;   // arrays carried by the exchange in flight
+  uint32_t slab_flags;
+  bool slab_v_is_u;
+  Kick slab_kick;
 };
 
 namespace {
@@ -97,8 +110,14 @@ int validate(const sphb200_config* c, int64_t n) {
   return SPHB200_OK;
 }
 
-// Cell grid, stencil and tiling (host).
-void plan_grid(const sphb200_config& c, Grid& g, int tpb) {
+// Global layer range [z0, z1) of rank r of p along an axis of ng cell layers.
+void slab_range(int ng, int r, int p, int& z0, int& z1) {
+  z0 = (int)((long long)ng * r / p);
+  z1 = (int)((long long)ng * (r + 1) / p);
+}
+
+// Cell grid, stencil and tiling (host).  nranks > 1: the local view of rank `rank`.
+void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nranks = 1) {
   const double cutoff = kernel_cutoff(c);
   double pop = 1.0;
   g.exact_all = 0;
@@ -143,7 +162,25 @@ void plan_grid(const sphb200_config& c, Grid& g, int tpb) {
   };
   while (t0 > 1 && entries(t0) > MAX_SOFF) --t0;
   g.T[0] = t0;
-  for (int a = 0; a < 3; ++a) g.nt[a] = (g.n[a] + g.T[a] - 1) / g.T[a];
+  for (int a = 0; a < 3; ++a) {
+    g.goff[a] = 0;
+    g.ng[a] = g.n[a];
+    g.own_lo[a] = 0;
+    g.own_hi[a] = g.n[a];
+  }
+  if (nranks > 1) {
+    const int ax = c.dim - 1;
+    int z0, z1;
+    slab_range(g.n[ax], rank, nranks, z0, z1);
+    g.goff[ax] = z0 - g.S[ax];
+    g.own_lo[ax] = g.S[ax];
+    g.own_hi[ax] = g.S[ax] + (z1 - z0);
+    g.n[ax] = (z1 - z0) + 2 * g.S[ax];
+    g.W[ax] = 2 * g.S[ax] + 1;
+    if (g.T[ax] > z1 - z0) g.T[ax] = z1 - z0;
+    g.ncells = g.n[0] * g.n[1] * g.n[2];
+  }
+  for (int a = 0; a < 3; ++a) g.nt[a] = (g.own_hi[a] - g.own_lo[a] + g.T[a] - 1) / g.T[a];
 
   const float cf = (float)cutoff;
   g.c2 = cf * cf;  // float32 product, jax_md/partition.py:820-822
@@ -209,6 +246,7 @@ struct Layout {
   size_t key, rnk, src, count, start, bsum, maxocc, wallcount, err, stats, nl_counts, ut;
   size_t pl_list, pl_cnt, pl_ok;
   int pl_lmax;
+  size_t dn;
   size_t total;
 };
 
@@ -255,12 +293,13 @@ void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, Layout& L) {
   L.nl_counts = take(((size_t)n + 1) * 4);
   L.count = take((size_t)g.ncells * 4);
   L.start = take(((size_t)g.ncells + 1) * 4);
-  size_t nb = ((size_t)(n > g.ncells ? n : g.ncells) + SCAN_TILE - 1) / SCAN_TILE + 1;
+  size_t nb = ((size_t)(n > g.ncells ? n : g.ncells) + SCAN_TILE) / SCAN_TILE + 1;
   L.bsum = take(nb * 4);
   L.maxocc = take(4);
   L.wallcount = take(4);
   L.err = take(4);
   L.stats = take(16);
+  L.dn = take(DN_WORDS * 4);
   L.pl_lmax = plan_lmax(c);
   if (L.pl_lmax > 0) {
     L.pl_list = take((size_t)n * L.pl_lmax * 2);
@@ -333,41 +372,66 @@ void swap_st(sphb200_engine* e) {
   e->fr[1].st = t;
 }
 
-int build_cells(sphb200_engine* e, const Kick& k, cudaStream_t st) {
-  const int n = e->n;
-  const int nb = (n + 255) / 256;
+// first half of the cell pipeline: kick + drift + wrap (recomputed later, not stored), cell
+// key, arrival rank, histogram; slab mode: emigrants leave through e->slab.mig_*
+int hash_cells(sphb200_engine* e, const Kick& k, cudaStream_t st) {
+  const int bound = e->slab_on ? e->sgeom.own_cap : e->n;
+  const int nb = (bound + 255) / 256;
+  Frame& A = e->fr[e->cur];
+  if (e->dim == 2)
+    k_hash<2><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, A, e->key, e->rnk, e->count, e->err);
+  else
+    k_hash<3><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, A, e->key, e->rnk, e->count, e->err);
+  e->launches += 1;
+  CK(cudaGetLastError());
+  return SPHB200_OK;
+}
+
+// second half: cell table, slot -> source, stable reorder into the other frame
+int sort_cells(sphb200_engine* e, const Kick& k, cudaStream_t st) {
+  // slab mode: sources are own + immigrants; the new own count is only known on the device
+  const int bound = e->slab_on ? e->sgeom.own_cap + 2 * e->slab.mig_cap : e->n;
+  const int nb = (bound + 255) / 256;
   Frame& A = e->fr[e->cur];
   Frame& B = e->fr[1 - e->cur];
-  if (e->dim == 2)
-    k_hash<2><<<nb, 256, 0, st>>>(n, e->grid, k, A.pt, A.um, A.du, A.dv, e->key, e->rnk, e->count, e->err);
-  else
-    k_hash<3><<<nb, 256, 0, st>>>(n, e->grid, k, A.pt, A.um, A.du, A.dv, e->key, e->rnk, e->count, e->err);
   const int c = e->grid.ncells;
-  const int sb = (c + SCAN_TILE) / SCAN_TILE;  // covers index c itself (start[c] = n)
+  const int sb = (c + SCAN_TILE) / SCAN_TILE;  // covers index c itself (start[c] = total)
   k_scan_partial<<<sb, SCAN_TPB, 0, st>>>(c, e->count, e->bsum);
   k_scan_bsum<<<1, 1024, 0, st>>>(sb, e->bsum);
-  k_scan_final<<<sb, SCAN_TPB, 0, st>>>(c, n, e->count, e->bsum, e->start, e->maxocc);
-  k_scatter_src<<<nb, 256, 0, st>>>(n, e->key, e->rnk, e->start, e->src);
+  k_scan_final<<<sb, SCAN_TPB, 0, st>>>(c, e->slab.base, e->count, e->bsum, e->start, e->maxocc);
+  k_scatter_src<<<nb, 256, 0, st>>>(bound, e->slab, e->key, e->rnk, e->start, e->src);
   ReorderOpt o{e->has_kc ? 1 : 0, e->has_nw ? 1 : 0, e->has_ge ? 1 : 0};
   if (e->dim == 2)
-    k_reorder<2><<<nb, 256, 0, st>>>(n, e->grid, k, o, A, B, e->key, e->start, e->src);
+    k_reorder<2><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, o, A, B, e->key, e->start, e->src);
   else
-    k_reorder<3><<<nb, 256, 0, st>>>(n, e->grid, k, o, A, B, e->key, e->start, e->src);
-  e->launches += 6;
+    k_reorder<3><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, o, A, B, e->key, e->start, e->src);
+  e->launches += 5;
   CK(cudaGetLastError());
   e->cur ^= 1;
   e->cells_valid = true;
   return SPHB200_OK;
 }
 
-int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st) {
+int build_cells(sphb200_engine* e, const Kick& k, cudaStream_t st) {
+  int rc = hash_cells(e, k, st);
+  if (rc) return rc;
+  return sort_cells(e, k, st);
+}
+
+// One stage of WCSPH.forward (solver.py:705-949): 0 density + EoS, 1 Shepard renormalisation,
+// 2 generalized wall BC, 3 force (+ case bc_fn).  *wrote = HX_* mask of the per-particle
+// arrays the stage changed that later stages read from NEIGHBOURS (what a slab halo must
+// refresh); 0 when the stage is not part of this solver variant.
+int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cudaStream_t st,
+                  int* wrote) {
   const sphb200_config& c = e->cfg;
+  *wrote = 0;
   const bool bc_trick = c.flags & SPHB200_F_BC_TRICK, evol = c.flags & SPHB200_F_RHO_EVOL,
              renorm = c.flags & SPHB200_F_RHO_RENORM, free_slip = c.flags & SPHB200_F_FREE_SLIP,
              heat = c.flags & SPHB200_F_HEAT;
   const bool rie = c.solver == SPHB200_SOLVER_RIE;
   const bool wall_sweep = bc_trick && !rie;
-  int rc;
+  int rc = SPHB200_OK;
   // quads staged by the force sweep (decides its staging capacity)
   int force_nq = 3;
   const int fq_v = (!rie && !v_is_u) ? force_nq++ : -1;
@@ -386,7 +450,7 @@ int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st)
     nl.min_cap = mc;
   }
   // ---- density -------------------------------------------------------------
-  {
+  if (stage == 0) {
     Extra ex = make_extra();
     ex.utilde = e->has_ut;
     ex.wallT = rie && bc_trick && heat;
@@ -419,9 +483,10 @@ int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st)
     }
     if (rc) return rc;
     swap_st(e);
+    *wrote = HX_ST | (e->has_ut ? HX_UT : 0);
+    if (e->profile) cudaEventRecord(e->ev[3], st);
   }
-  if (e->profile) cudaEventRecord(e->ev[3], st);
-  if (evol && renorm) {
+  if (stage == 1 && evol && renorm) {
     Extra ex = make_extra();
     ex.nq = 2;
     Frame& F = e->fr[e->cur];
@@ -431,9 +496,10 @@ int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st)
 #undef CALL
     if (rc) return rc;
     swap_st(e);
+    *wrote = HX_ST;
   }
   // ---- generalized wall boundary condition ---------------------------------
-  if (wall_sweep) {
+  if (stage == 2 && wall_sweep) {
     Extra ex = make_extra();
     ex.nq = 4;
     ex.heat = heat;
@@ -445,10 +511,11 @@ int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st)
 #undef CALL
     if (rc) return rc;
     swap_st(e);
+    *wrote = HX_UM | HX_VV | HX_ST;
   }
-  if (e->profile) cudaEventRecord(e->ev[4], st);
   // ---- force -----------------------------------------------------------------
-  {
+  if (stage == 3) {
+    if (e->profile) cudaEventRecord(e->ev[4], st);
     Extra ex = make_extra();
     ex.q_v = fq_v; ex.q_h = fq_h; ex.q_nw = fq_nw; ex.q_ut = fq_ut;
     ex.nq = force_nq;
@@ -481,12 +548,22 @@ int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st)
     }
     if (rc) return rc;
     if (ex.bc_on) {
-      const int nb = (e->n + 255) / 256;
-      if (e->dim == 2) k_bc<2><<<nb, 256, 0, st>>>(e->n, e->consts, F);
-      else k_bc<3><<<nb, 256, 0, st>>>(e->n, e->consts, F);
+      const int bound = e->slab_on ? e->sgeom.own_cap : e->n;
+      const int nb = (bound + 255) / 256;
+      if (e->dim == 2) k_bc<2><<<nb, 256, 0, st>>>(bound, e->slab, e->consts, F);
+      else k_bc<3><<<nb, 256, 0, st>>>(bound, e->slab, e->consts, F);
       e->launches++;
       CK(cudaGetLastError());
     }
+  }
+  return SPHB200_OK;
+}
+
+int run_forward(sphb200_engine* e, uint32_t flags, bool v_is_u, cudaStream_t st) {
+  for (int stage = 0; stage < 4; ++stage) {
+    int wrote;
+    int rc = forward_stage(e, stage, flags, v_is_u, st, &wrote);
+    if (rc) return rc;
   }
   return SPHB200_OK;
 }
@@ -528,11 +605,12 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_final_keep(int c, const int* 
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(256) k_stats(int n, Frame f, double* out) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_stats(int n, Slab sl, Frame f, double* out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = sl.base + t;
   double ek = 0.0;
   float um = 0.f;
-  if (p < n) {
+  if (t < (sl.dn ? sl.dn[DN_OWN] : n)) {
     float4 u = f.um[p];
     float s = u.x * u.x + u.y * u.y + (DIM == 3 ? u.z * u.z : 0.f);
     ek = 0.5 * (double)u.w * (double)s;
@@ -549,11 +627,25 @@ __global__ void __launch_bounds__(256) k_stats(int n, Frame f, double* out) {
   }
 }
 
+struct SlabSpec {
+  int rank, nranks;
+  int own_cap, halo_cap, mig_cap;
+};
+
+// capacity (particle slots) of a slab engine
+int64_t slab_slots(const SlabSpec& sp) { return (int64_t)sp.halo_cap + sp.own_cap + sp.halo_cap; }
+
 int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* ws, size_t ws_bytes,
-                bool own) {
+                bool own, const SlabSpec* sp = nullptr) {
   e->cfg = *cfg;
   e->n = (int)n;
   e->dim = cfg->dim;
+  e->slab_on = sp != nullptr;
+  e->slab_rank = sp ? sp->rank : 0;
+  e->slab_nranks = sp ? sp->nranks : 1;
+  e->slab_axis = cfg->dim - 1;
+  e->slab_stage = 0;
+  e->slab_pending_mask = 0;
   int dev = 0;
   CK(cudaGetDevice(&dev));
   int maxs = 0;
@@ -563,7 +655,7 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   if (e->tpb > 512) e->tpb = 512;
   e->lcap = cfg->list_cap > 0 ? cfg->list_cap : 32;
   if (e->lcap < SWEEP_CHUNK) e->lcap = SWEEP_CHUNK;
-  plan_grid(*cfg, e->grid, e->tpb);
+  plan_grid(*cfg, e->grid, e->tpb, e->slab_rank, e->slab_nranks);
   plan_consts(*cfg, e->consts);
   feature_flags(*cfg, e->has_kc, e->has_nw, e->has_ut, e->has_ge);
   Layout L;
@@ -602,6 +694,25 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->pl_list = L.pl_lmax ? (unsigned short*)(e->arena + L.pl_list) : nullptr;
   e->pl_cnt = L.pl_lmax ? (int*)(e->arena + L.pl_cnt) : nullptr;
   e->pl_ok = L.pl_lmax ? (unsigned char*)(e->arena + L.pl_ok) : nullptr;
+  e->dn = (int*)(e->arena + L.dn);
+  memset(&e->slab, 0, sizeof(e->slab));
+  memset(&e->sgeom, 0, sizeof(e->sgeom));
+  if (sp) {
+    const Grid& g = e->grid;
+    const int ax = e->slab_axis;
+    int layer = 1;  // cells per layer along the slab axis
+    for (int a = 0; a < ax; ++a) layer *= g.n[a];
+    e->slab.base = sp->halo_cap;
+    e->slab.dn = e->dn;
+    e->slab.mig_cap = sp->mig_cap;
+    e->sgeom.halo_cap = sp->halo_cap;
+    e->sgeom.ncl = g.S[ax] * layer;
+    e->sgeom.c_own_lo = g.own_lo[ax] * layer;
+    e->sgeom.c_own_hi = g.own_hi[ax] * layer;
+    e->sgeom.own_cap = sp->own_cap;
+    e->sgeom.cap_total = (int)n;
+    slab_range(g.ng[ax], sp->rank, sp->nranks, e->slab_z0, e->slab_z1);
+  }
   e->cur = 0;
   e->cells_valid = false;
   e->launches = 0;
@@ -727,7 +838,7 @@ int sphb200_engine_destroy(sphb200_engine* e) {
 }
 
 static int ensure_hstage(sphb200_engine* e) {
-  size_t need = up((size_t)e->n * 4) * state_floats(e->dim);
+  size_t need = up((size_t)e->n * 4) * (state_floats(e->dim) + 1);
   if (e->hstage && e->hstage_bytes >= need) return SPHB200_OK;
   if (e->hstage) cudaFree(e->hstage);
   e->hstage = nullptr;
@@ -736,11 +847,14 @@ static int ensure_hstage(sphb200_engine* e) {
   return SPHB200_OK;
 }
 
-int sphb200_engine_upload(sphb200_engine* e, const sphb200_state* s, int on_host, void* stream) {
+// rows: particles in *s (slab mode: this rank's own particles, ids = their global indices)
+static int upload_impl(sphb200_engine* e, const sphb200_state* s, int rows, const int32_t* ids,
+                       int on_host, void* stream) {
   if (!e || !s || !s->r) return SPHB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  const int n = e->n, d = e->dim;
+  const int n = rows, d = e->dim;
   sphb200_state dv = *s;
+  const int32_t* dids = ids;
   if (on_host) {
     int rc = ensure_hstage(e);
     if (rc) return rc;
@@ -765,6 +879,7 @@ int sphb200_engine_upload(sphb200_engine* e, const sphb200_state* s, int on_host
     dv.Cp = e->has_kc ? (float*)stage(s->Cp, ns) : nullptr;
     dv.tag = (int32_t*)stage(s->tag, ns);
     dv.g_ext = e->has_ge ? (float*)stage(s->g_ext, nv) : nullptr;
+    if (ids) dids = (const int32_t*)stage(ids, ns);
     CK(cudaGetLastError());
   }
   StatePtrs sp{dv.r, dv.u, dv.v, dv.dudt, dv.dvdt, dv.nw, dv.rho, dv.p, dv.drhodt, dv.mass,
@@ -779,20 +894,35 @@ int sphb200_engine_upload(sphb200_engine* e, const sphb200_state* s, int on_host
     e->needs_zero = false;
   }
   CK(cudaMemsetAsync(e->wallcount, 0, 4, st));
+  if (e->slab_on) {
+    int h[DN_WORDS] = {0};
+    h[DN_OWN] = n;
+    CK(cudaMemcpyAsync(e->dn, h, sizeof(h), cudaMemcpyHostToDevice, st));  // pageable: staged at once
+  }
   const int nb = (n + 255) / 256;
-  if (d == 2) k_pack<2><<<nb, 256, 0, st>>>(n, sp, e->fr[0], e->wallcount);
-  else k_pack<3><<<nb, 256, 0, st>>>(n, sp, e->fr[0], e->wallcount);
-  e->launches++;
+  if (n > 0) {
+    if (d == 2) k_pack<2><<<nb, 256, 0, st>>>(n, sp, e->fr[0], e->slab.base, dids, e->wallcount);
+    else k_pack<3><<<nb, 256, 0, st>>>(n, sp, e->fr[0], e->slab.base, dids, e->wallcount);
+    e->launches++;
+  }
   CK(cudaGetLastError());
   return SPHB200_OK;
 }
 
-int sphb200_engine_download(sphb200_engine* e, sphb200_state* out, int on_host, void* stream) {
+int sphb200_engine_upload(sphb200_engine* e, const sphb200_state* s, int on_host, void* stream) {
+  if (!e || e->slab_on) return SPHB200_EINVAL;
+  return upload_impl(e, s, e->n, nullptr, on_host, stream);
+}
+
+// rows: capacity of the arrays in *out; ids != NULL (slab mode): local order + global indices
+static int download_impl(sphb200_engine* e, sphb200_state* out, int rows, int32_t* ids,
+                         int on_host, void* stream) {
   if (!e || !out) return SPHB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  const int n = e->n, d = e->dim;
+  const int n = rows, d = e->dim;
   sphb200_state dv = *out;
-  struct Back { void* h; void* dptr; size_t bytes; } back[16];
+  int32_t* dids = ids;
+  struct Back { void* h; void* dptr; size_t bytes; } back[20];
   int nback = 0;
   if (on_host) {
     int rc = ensure_hstage(e);
@@ -817,12 +947,13 @@ int sphb200_engine_download(sphb200_engine* e, sphb200_state* out, int on_host, 
     dv.kappa = e->has_kc ? (float*)stage(out->kappa, ns) : nullptr;
     dv.Cp = e->has_kc ? (float*)stage(out->Cp, ns) : nullptr;
     dv.tag = (int32_t*)stage(out->tag, ns);
+    if (ids) dids = (int32_t*)stage(ids, ns);
   }
   StateOut so{dv.r, dv.u, dv.v, dv.dudt, dv.dvdt, dv.nw, dv.rho, dv.p, dv.drhodt, dv.mass,
-              dv.eta, dv.T, dv.dTdt, dv.kappa, dv.Cp, dv.tag};
+              dv.eta, dv.T, dv.dTdt, dv.kappa, dv.Cp, dv.tag, dids};
   const int nb = (n + 255) / 256;
-  if (d == 2) k_unpack<2><<<nb, 256, 0, st>>>(n, e->fr[e->cur], so);
-  else k_unpack<3><<<nb, 256, 0, st>>>(n, e->fr[e->cur], so);
+  if (d == 2) k_unpack<2><<<nb, 256, 0, st>>>(n, e->slab, e->fr[e->cur], so);
+  else k_unpack<3><<<nb, 256, 0, st>>>(n, e->slab, e->fr[e->cur], so);
   e->launches++;
   CK(cudaGetLastError());
   for (int i = 0; i < nback; ++i)
@@ -830,8 +961,13 @@ int sphb200_engine_download(sphb200_engine* e, sphb200_state* out, int on_host, 
   return SPHB200_OK;
 }
 
+int sphb200_engine_download(sphb200_engine* e, sphb200_state* out, int on_host, void* stream) {
+  if (!e || e->slab_on) return SPHB200_EINVAL;
+  return download_impl(e, out, e->n, nullptr, on_host, stream);
+}
+
 int sphb200_engine_step(sphb200_engine* e, double dt, int nsteps, uint32_t flags, void* stream) {
-  if (!e || nsteps < 0) return SPHB200_EINVAL;
+  if (!e || nsteps < 0 || e->slab_on) return SPHB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   Kick k;
   k.dt = (float)dt;
@@ -863,7 +999,7 @@ int sphb200_engine_error(sphb200_engine* e, uint32_t* code, void* stream) {
 
 int sphb200_engine_neighbor_list(sphb200_engine* e, int32_t* idx, int64_t capacity, int mask_self,
                                  int64_t* count, void* stream) {
-  if (!e || capacity < 0 || capacity >= 2147483647LL) return SPHB200_EINVAL;
+  if (!e || e->slab_on || capacity < 0 || capacity >= 2147483647LL) return SPHB200_EINVAL;
   if (!idx && capacity != 0) return SPHB200_EINVAL;  // idx == NULL: count only
   cudaStream_t st = (cudaStream_t)stream;
   if (!e->cells_valid) {
@@ -912,9 +1048,10 @@ int sphb200_engine_stats(sphb200_engine* e, double* ekin, double* u_max, void* s
   if (!e) return SPHB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemsetAsync(e->stats, 0, 16, st));
-  const int nb = (e->n + 255) / 256;
-  if (e->dim == 2) k_stats<2><<<nb, 256, 0, st>>>(e->n, e->fr[e->cur], e->stats);
-  else k_stats<3><<<nb, 256, 0, st>>>(e->n, e->fr[e->cur], e->stats);
+  const int bound = e->slab_on ? e->sgeom.own_cap : e->n;
+  const int nb = (bound + 255) / 256;
+  if (e->dim == 2) k_stats<2><<<nb, 256, 0, st>>>(bound, e->slab, e->fr[e->cur], e->stats);
+  else k_stats<3><<<nb, 256, 0, st>>>(bound, e->slab, e->fr[e->cur], e->stats);
   e->launches++;
   double h[2];
   CK(cudaMemcpyAsync(h, e->stats, 16, cudaMemcpyDeviceToHost, st));
@@ -965,6 +1102,195 @@ int sphb200_engine_plan(const sphb200_engine* e, int32_t out[16]) {
   out[13] = e->planC.cap;
   out[14] = e->grid.exact_all;
   out[15] = e->grid.ncells;
+  return SPHB200_OK;
+}
+
+// ---- slab decomposition (one engine per rank; the caller moves the messages) ----------------
+static int slab_spec(const sphb200_config* cfg, int rank, int nranks, int64_t own_cap,
+                     int64_t halo_cap, int64_t mig_cap, SlabSpec* sp) {
+  if (nranks < 2 || rank < 0 || rank >= nranks) return SPHB200_EINVAL;
+  Grid g;
+  plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : DEFAULT_TPB);
+  const int ax = cfg->dim - 1;
+  if (g.exact_all && g.n[ax] < 2 * g.S[ax] + 1) return SPHB200_EINVAL;
+  for (int r = 0; r < nranks; ++r) {
+    int z0, z1;
+    slab_range(g.n[ax], r, nranks, z0, z1);
+    if (z1 - z0 < 2 * g.S[ax]) return SPHB200_EINVAL;  // a slab must be at least two cutoffs thick
+  }
+  double per_layer = 1.0;  // nominal particles in one cell layer along the slab axis
+  for (int a = 0; a < cfg->dim; ++a) per_layer *= cfg->box[a] / cfg->dx;
+  per_layer /= g.n[ax];
+  int z0, z1;
+  slab_range(g.n[ax], rank, nranks, z0, z1);
+  if (own_cap <= 0) own_cap = (int64_t)(1.25 * per_layer * (z1 - z0)) + 4096;
+  if (halo_cap <= 0) halo_cap = (int64_t)(1.5 * per_layer * g.S[ax]) + 4096;
+  if (mig_cap <= 0) mig_cap = (int64_t)(0.25 * per_layer) + 1024;
+  if (2 * mig_cap > halo_cap) halo_cap = 2 * mig_cap;  // immigrants are parked in the upper halo slots
+  if (2 * halo_cap + own_cap > 2000000000LL) return SPHB200_EINVAL;
+  sp->rank = rank; sp->nranks = nranks;
+  sp->own_cap = (int)own_cap; sp->halo_cap = (int)halo_cap; sp->mig_cap = (int)mig_cap;
+  return SPHB200_OK;
+}
+
+int sphb200_slab_create(const sphb200_config* cfg, int rank, int nranks, int64_t own_cap,
+                        int64_t halo_cap, int64_t mig_cap, sphb200_engine** out) {
+  int rc = validate(cfg, 1);
+  if (rc) return rc;
+  if (!out) return SPHB200_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SPHB200_ENODEV;
+  SlabSpec sp;
+  rc = slab_spec(cfg, rank, nranks, own_cap, halo_cap, mig_cap, &sp);
+  if (rc) return rc;
+  Grid g;
+  plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : DEFAULT_TPB, rank, nranks);
+  Layout L;
+  plan_layout(*cfg, slab_slots(sp), g, L);
+  void* ws = nullptr;
+  if (cudaMalloc(&ws, L.total) != cudaSuccess) return SPHB200_ENOMEM;
+  sphb200_engine* e = new (std::nothrow) sphb200_engine();
+  if (!e) {
+    cudaFree(ws);
+    return SPHB200_ENOMEM;
+  }
+  rc = init_engine(e, cfg, slab_slots(sp), ws, L.total, true, &sp);
+  if (rc) {
+    cudaFree(ws);
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return SPHB200_OK;
+}
+
+static int slab_mask_a(const sphb200_engine* e) {
+  return HX_PT | HX_UM | HX_VV | HX_ST | HX_CELLS | (e->has_kc ? HX_KC : 0) |
+         (e->has_nw ? HX_NW : 0) | (e->has_ge ? HX_GE : 0);
+}
+
+int sphb200_slab_info(const sphb200_engine* e, int64_t outi[16], double outd[4]) {
+  if (!e || !e->slab_on || !outi || !outd) return SPHB200_EINVAL;
+  const int ax = e->slab_axis;
+  const SlabGeom& sg = e->sgeom;
+  size_t xb = mig_bytes(e->slab.mig_cap);
+  const size_t hb = halo_bytes(slab_mask_a(e) | HX_UT, sg.halo_cap, sg.ncl);
+  if (hb > xb) xb = hb;
+  outi[0] = e->slab_rank; outi[1] = e->slab_nranks; outi[2] = ax;
+  outi[3] = e->slab_z0; outi[4] = e->slab_z1; outi[5] = e->grid.ng[ax];
+  outi[6] = sg.own_cap; outi[7] = sg.halo_cap; outi[8] = e->slab.mig_cap;
+  outi[9] = (int64_t)xb;  // bytes each of the four message buffers must hold
+  outi[10] = e->grid.S[ax]; outi[11] = sg.cap_total; outi[12] = (int64_t)e->arena_bytes;
+  outi[13] = outi[14] = outi[15] = 0;
+  outd[0] = (double)e->grid.inv_cell[ax];  // layer = min(int(f32(r) * f32(inv_cell)), ng - 1)
+  outd[1] = (double)e->grid.box[ax];
+  outd[2] = outd[3] = 0.0;
+  return SPHB200_OK;
+}
+
+int sphb200_slab_upload(sphb200_engine* e, const sphb200_state* s, const int32_t* ids, int64_t rows,
+                        int on_host, void* stream) {
+  if (!e || !e->slab_on || rows < 0 || rows > e->sgeom.own_cap || !ids) return SPHB200_EINVAL;
+  return upload_impl(e, s, (int)rows, ids, on_host, stream);
+}
+
+int sphb200_slab_download(sphb200_engine* e, sphb200_state* out, int32_t* ids, int64_t rows,
+                          int on_host, void* stream) {
+  if (!e || !e->slab_on || rows < 0 || rows > e->sgeom.own_cap || !ids) return SPHB200_EINVAL;
+  return download_impl(e, out, (int)rows, ids, on_host, stream);
+}
+
+int sphb200_slab_counts(sphb200_engine* e, int32_t out[8], void* stream) {
+  if (!e || !e->slab_on || !out) return SPHB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(out, e->dn, DN_WORDS * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SPHB200_OK;
+}
+
+int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, void* send_lo,
+                     void* send_hi, const void* recv_lo, const void* recv_hi, void* stream,
+                     int64_t* xbytes) {
+  if (!e || !e->slab_on || !xbytes || phase < 0) return SPHB200_EINVAL;
+  if (!send_lo || !send_hi || !recv_lo || !recv_hi) return SPHB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  Slab& sl = e->slab;
+  const SlabGeom& sg = e->sgeom;
+  const int hblocks = 4 * 148;
+  *xbytes = 0;
+  if (phase == 0) {
+    Kick k;
+    k.dt = (float)dt;
+    k.c2 = (float)(e->cfg.tvf * 0.5) * (float)dt;
+    k.on = (flags & SPHB200_STEP_INTEGRATE) ? 1 : 0;
+    e->slab_kick = k;
+    e->slab_flags = flags;
+    e->slab_v_is_u = k.on && e->cfg.tvf == 0.0;
+    sl.mig_lo = (char*)send_lo;
+    sl.mig_hi = (char*)send_hi;
+    if (e->profile) cudaEventRecord(e->ev[0], st);
+    int rc = hash_cells(e, k, st);
+    if (rc) return rc;
+    k_mig_header<<<1, 1, 0, st>>>(sl);
+    e->launches++;
+    CK(cudaGetLastError());
+    *xbytes = (int64_t)mig_bytes(sl.mig_cap);
+    return SPHB200_OK;
+  }
+  if (phase == 1) {
+    const dim3 gi((sl.mig_cap + 255) / 256, 2);
+    Frame& A = e->fr[e->cur];
+    if (e->dim == 2)
+      k_immigrate<2><<<gi, 256, 0, st>>>(e->grid, sl, sg, A, (const char*)recv_lo,
+                                         (const char*)recv_hi, e->key, e->rnk, e->count, e->err);
+    else
+      k_immigrate<3><<<gi, 256, 0, st>>>(e->grid, sl, sg, A, (const char*)recv_lo,
+                                         (const char*)recv_hi, e->key, e->rnk, e->count, e->err);
+    int rc = sort_cells(e, e->slab_kick, st);
+    if (rc) return rc;
+    k_slab_after_sort<<<1, 1, 0, st>>>(e->grid, sl, sg, e->start, e->err);
+    const int mask = slab_mask_a(e);
+    k_halo_pack<<<dim3(hblocks, 2), 256, 0, st>>>(sl, sg, e->fr[e->cur], mask, e->start,
+                                                  (char*)send_lo, (char*)send_hi, e->err);
+    e->launches += 3;
+    CK(cudaGetLastError());
+    if (e->profile) cudaEventRecord(e->ev[2], st);
+    e->slab_pending_mask = mask;
+    e->slab_stage = 0;
+    *xbytes = (int64_t)halo_bytes(mask, sg.halo_cap, sg.ncl);
+    return SPHB200_OK;
+  }
+  // phase >= 2: take in the halo message of the previous phase, then sweep until the next
+  // stage whose results the neighbours need
+  if (e->slab_pending_mask) {
+    const int mask = e->slab_pending_mask;
+    if (mask & HX_CELLS) {
+      k_halo_cells<<<2, 1024, 0, st>>>(e->grid, sl, sg, mask, (const char*)recv_lo,
+                                       (const char*)recv_hi, e->start, e->err);
+      e->launches++;
+    }
+    k_halo_unpack<<<dim3(hblocks, 2), 256, 0, st>>>(sl, sg, e->fr[e->cur], mask,
+                                                    (const char*)recv_lo, (const char*)recv_hi);
+    e->launches++;
+    CK(cudaGetLastError());
+    e->slab_pending_mask = 0;
+  }
+  while (e->slab_stage < 4) {
+    int wrote = 0;
+    const int stage = e->slab_stage++;
+    int rc = forward_stage(e, stage, e->slab_flags, e->slab_v_is_u, st, &wrote);
+    if (rc) return rc;
+    if (wrote && stage < 3) {
+      k_halo_pack<<<dim3(hblocks, 2), 256, 0, st>>>(sl, sg, e->fr[e->cur], wrote, e->start,
+                                                    (char*)send_lo, (char*)send_hi, e->err);
+      e->launches++;
+      CK(cudaGetLastError());
+      e->slab_pending_mask = wrote;
+      *xbytes = (int64_t)halo_bytes(wrote, sg.halo_cap, sg.ncl);
+      return SPHB200_OK;
+    }
+  }
+  if (e->profile) cudaEventRecord(e->ev[5], st);
   return SPHB200_OK;
 }
 

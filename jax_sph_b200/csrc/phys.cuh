@@ -16,6 +16,7 @@
 // Registers held across the pair loop are kept to what pair() reads; finish()
 // re-reads the rest of the particle from global memory.
 #pragma once
+#include "cells.cuh"
 #include "common.cuh"
 
 namespace sphb200 {
@@ -475,9 +476,10 @@ struct PhysForce {
 // bc_fn, value part: u, v, p, T overwritten per tag (after the force sweep has
 // consumed the wall values the solver computed).
 template <int DIM>
-__global__ void __launch_bounds__(256) k_bc(int n, Consts c, Frame f) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
+__global__ void __launch_bounds__(256) k_bc(int n, Slab sl, Consts c, Frame f) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (sl.dn ? sl.dn[DN_OWN] : n)) return;
+  const int p = sl.base + t;
   const float4 pt = f.pt[p];
   const int tag = __float_as_int(pt.w);
   if (tag < 0 || tag > 3) return;

@@ -58,7 +58,7 @@ __host__ __device__ inline size_t sweep_smem_bytes(int nq, int cap, int lcap, in
   return (size_t)nq * cap * 16 + (size_t)lcap * tpb * 2 + (MAX_SOFF + 1 + 2 * MAX_RUNS + 2) * 4;
 }
 
-// unwrapped cell index u in [-n, 2n)  ->  periodic image count / wrapped index
+// unwrapped (global) cell index u in [-n, 2n)  ->  periodic image count / wrapped index
 __device__ __forceinline__ int wrap_count(int u, int n) { return u < 0 ? -1 : (u >= n ? 1 : 0); }
 __device__ __forceinline__ int wrap_cell(int u, int n) { return u < 0 ? u + n : (u >= n ? u - n : u); }
 
@@ -137,12 +137,12 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
   b /= g.nt[0];
   const int ty = b % g.nt[1];
   const int tz = b / g.nt[1];
-  int c0[3] = {tx * g.T[0], ty * g.T[1], tz * g.T[2]};
+  int c0[3] = {g.own_lo[0] + tx * g.T[0], g.own_lo[1] + ty * g.T[1], g.own_lo[2] + tz * g.T[2]};
   int no[3], sa0[3], slen[3];
   bool interior = true;  // no periodic image inside this tile's stencil
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
-    no[a] = min(g.T[a], g.n[a] - c0[a]);
+    no[a] = min(g.T[a], g.own_hi[a] - c0[a]);
     if (g.n[a] >= 2 * g.S[a] + 1) {
       sa0[a] = c0[a] - g.S[a];
       slen[a] = no[a] + 2 * g.S[a];
@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
       sa0[a] = 0;
       slen[a] = g.n[a];
     }
-    interior = interior && (a >= DIM || (sa0[a] >= 0 && sa0[a] + slen[a] <= g.n[a] &&
+    interior = interior && (a >= DIM || (sa0[a] + g.goff[a] >= 0 &&
+                                         sa0[a] + g.goff[a] + slen[a] <= g.ng[a] &&
                                          g.n[a] >= 2 * g.S[a] + 2));
   }
   if (g.exact_all) interior = false;
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
     int ks = kb;
     if (ka < kz && kz < kb) ks = kz;
     else if (ka < kn && kn < kb) ks = kn;
-    const float xs0 = ri[0] - (float)wrap_count(sa0[0] + ka, g.n[0]) * g.box[0];
+    const float xs0 = ri[0] - (float)wrap_count(sa0[0] + ka, g.n[0]) * g.box[0];  // x is never the slab axis
     const float xs1 = ri[0] - (float)wrap_count(sa0[0] + ks, g.n[0]) * g.box[0];
 
     // ---- staging groups: maximal runs [e_a, e_b) of consecutive (row, cell) entries that
@@ -328,8 +329,8 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
                 const int ry = w0[1] + wy, rz = w0[2] + wz;
                 row = rz * slen[1] + ry;
                 inwin = act;
-                ys = ri[1] - (float)wrap_count(sa0[1] + ry, g.n[1]) * g.box[1];
-                zs = ri[2] - (float)wrap_count(sa0[2] + rz, g.n[2]) * g.box[2];
+                ys = ri[1] - (float)wrap_count(sa0[1] + ry + g.goff[1], g.ng[1]) * g.box[1];
+                zs = ri[2] - (float)wrap_count(sa0[2] + rz + g.goff[2], g.ng[2]) * g.box[2];
               }
               const int kk0 = sgm == 0 ? ka : ks, kk1 = sgm == 0 ? ks : kb;
               j = jb = 0;
