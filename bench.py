@@ -100,25 +100,44 @@ def make_setup(workload, nx):
     raise ValueError(workload)
 
 
-def lattice_state(workload, nx):
+def lattice_meta(workload, nx):
+    dim, box = (3, 2 * np.pi) if workload == "tgv3d" else (2, 1.0)
+    dx = box / nx
+    viscosity, u_ref = (0.02, 1.0) if dim == 3 else (0.01, 1.0)
+    c_ref = 10.0 * u_ref
+    # case_setup.py:94-97 (CFL 0.25)
+    dt = float(min(0.25 * dx / (c_ref + u_ref), 0.25 * dx * dx / viscosity))
+    return dict(dim=dim, box=[box] * dim, dx=dx, dt=dt, viscosity=viscosity, c_ref=c_ref,
+                p_ref=c_ref**2, tvf=1.0)
+
+
+def lattice_state(workload, nx, planes=None):
     """Synthetic lattice initial state WITHOUT importing the oracle (product path):
-    particles at (i + 0.5) dx, TGV velocity field (cases/tgv.py:37-51), rho = 1."""
+    particles at (i + 0.5) dx, TGV velocity field (cases/tgv.py:37-51), rho = 1.
+    `planes`: boolean mask over the lattice planes along the last axis (a rank's slab);
+    the state then also carries `ids`, the particles' indices in the full lattice."""
     if workload == "tgv3d":
         dim, box = 3, 2 * np.pi
     else:
         dim, box = 2, 1.0
     dx = box / nx
     ax = ((np.arange(nx, dtype=np.float32) + np.float32(0.5)) * np.float32(dx)).astype(np.float32)
+    last = ax if planes is None else ax[planes]
+    kk = np.arange(nx) if planes is None else np.nonzero(planes)[0]
     if dim == 3:
         # utils.py:49-54 meshgrid(indexing="xy") ravel order
-        X, Y, Z = np.meshgrid(ax, ax, ax, indexing="xy")
+        X, Y, Z = np.meshgrid(ax, ax, last, indexing="xy")
+        IX, IY, IK = np.meshgrid(np.arange(nx), np.arange(nx), kk, indexing="xy")
+        ids = ((IY.ravel() * nx + IX.ravel()) * nx + IK.ravel()).astype(np.int32)
         r = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
         x, y, z = r[:, 0], r[:, 1], r[:, 2]
         u = np.stack([np.sin(x) * np.cos(y) * np.cos(z), -np.cos(x) * np.sin(y) * np.cos(z),
                       np.zeros_like(x)], axis=1).astype(np.float32)
         viscosity, u_ref = 0.02, 1.0
     else:
-        X, Y = np.meshgrid(ax, ax, indexing="xy")
+        X, Y = np.meshgrid(ax, last, indexing="xy")
+        IX, IK = np.meshgrid(np.arange(nx), kk, indexing="xy")
+        ids = (IK.ravel() * nx + IX.ravel()).astype(np.int32)
         r = np.stack([X.ravel(), Y.ravel()], axis=1)
         x, y = r[:, 0], r[:, 1]
         tp = np.float32(2 * np.pi)
@@ -138,6 +157,8 @@ def lattice_state(workload, nx):
                  tag=np.zeros(n, dtype=np.int32))
     meta = dict(dim=dim, box=[box] * dim, dx=dx, dt=dt, viscosity=viscosity, c_ref=c_ref,
                 p_ref=c_ref**2, tvf=1.0)
+    if planes is not None:
+        state["ids"] = ids
     return state, meta
 
 
@@ -155,6 +176,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return run_slab(args, world, rank, local)
 
     state, meta = lattice_state(args.workload, args.nx)
     n = len(state["r"])
@@ -258,6 +280,150 @@ def run_ours(args):
                 "steps": e2e_steps,
                 "what": "Engine.upload(pinned host state) + step + download(host) every step"},
         "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def run_slab(args, world, rank, local):
+    """N > 1: the SAME box (strong scaling) cut into `world` slabs along the last axis, one
+    rank per GPU, halo exchange + particle migration every step over NCCL (slab.py)."""
+    import torch
+    import torch.distributed as dist
+
+    from jax_sph_b200 import SlabEngine, make_config
+    from jax_sph_b200.slab import layer_of
+
+    # NCCL prints its version banner on fd 1: keep stdout for the one JSON line
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    meta = lattice_meta(args.workload, args.nx)
+    dim, nx = meta["dim"], args.nx
+    n_total = nx**dim
+    cfg = make_config(dim, meta["box"], meta["dx"], meta["dt"], tvf=meta["tvf"],
+                      c_ref=meta["c_ref"], p_ref=meta["p_ref"],
+                      cell_sub=[args.sub] * dim if args.sub else None,
+                      threads=args.threads, list_cap=args.list_cap,
+                      tile=[args.tile_x, 0, 0] if args.tile_x else None)
+    eng = SlabEngine(cfg)
+    ax = ((np.arange(nx, dtype=np.float32) + np.float32(0.5)) * np.float32(meta["dx"])).astype(np.float32)
+    lay = layer_of(ax, eng.inv_cell, eng.layers)
+    state, _ = lattice_state(args.workload, nx, planes=(lay >= eng.z0) & (lay < eng.z1))
+    ids = state.pop("ids")
+    n_own0 = len(ids)
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in state.items()}
+    ids_t = torch.from_numpy(ids).pin_memory()
+    eng.upload(pinned, ids_t)
+    torch.cuda.synchronize()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    eng.step(meta["dt"], args.warmup)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    l0, x0 = eng.launches(), eng.bytes_exchanged
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    t_host0 = time.perf_counter()
+    eng.step(meta["dt"], args.steps)
+    t_host = time.perf_counter() - t_host0
+    e1.record()
+    barrier()
+    ms = reduce_max(e0.elapsed_time(e1))
+    launches = eng.launches() - l0
+    xbytes = (eng.bytes_exchanged - x0) / args.steps
+    clocks = sampler.finish()
+    err = eng.error()
+    counts = eng.counts()
+    tot = torch.tensor([counts["own"]], device="cuda", dtype=torch.int64)
+    dist.all_reduce(tot)
+
+    eng.profile(True)
+    acc = {}
+    for _ in range(args.steps):
+        eng.step(meta["dt"], 1)
+        for k, v in eng.last_times().items():
+            acc[k] = acc.get(k, 0.0) + v / args.steps
+    eng.profile(False)
+    # stream time of each exchange (includes waiting for the neighbour to reach its send)
+    eng.time_exchanges = True
+    barrier()
+    eng.step(meta["dt"], args.steps)
+    xt = eng.exchange_times()
+    eng.time_exchanges = False
+
+    # end to end: this rank's slab host -> device, one advance (with its exchanges), device -> host
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    host_in, ids_h = eng.download()
+    bytes_in = sum(v.numel() * v.element_size() for v in host_in.values()) + ids_h.numel() * 4
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.upload(host_in, ids_h)
+        eng.step(meta["dt"], 1)
+        host_in, ids_h = eng.download()
+    barrier()
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    bytes_all = torch.tensor([bytes_in], device="cuda", dtype=torch.int64)
+    dist.all_reduce(bytes_all)
+    barrier()
+    dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+
+    if rank != 0:
+        return
+    peaks, which = measured_peaks()
+    edges = 93 if dim == 3 else 25
+    f_ms = acc.get("force", 0.0)
+    n_loc = counts["own"]
+    f_bytes = BYTES[dim]["force"] * n_loc
+    f_flops = FLOPS_EDGE[dim]["force"] * edges * n_loc
+    roof = {
+        "kernel": "k_sweep<PhysForce> (force sweep), rank 0's slab", "bound": "hbm",
+        "achieved": f_bytes / (f_ms * 1e-3) / 1e9 if f_ms else None,
+        "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": which,
+        "frac": (f_bytes / (f_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if f_ms else None,
+        "traffic": None, "ms": f_ms, "note": "FP32-issue bound, not HBM bound: see fp32",
+        "fp32": {"achieved_tflops": f_flops / (f_ms * 1e-3) / 1e12 if f_ms else None,
+                 "peak_tflops_nominal": FP32_PEAK_TFLOPS,
+                 "frac": (f_flops / (f_ms * 1e-3) / 1e12) / FP32_PEAK_TFLOPS if f_ms else None},
+        "passes_ms": acc,
+    }
+    line = {
+        "metric": METRIC, "value": n_total * args.steps / (ms * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload} nx={nx} N={n_total} SPH tvf=1 QSK (BASELINE configs[3])",
+                   "particles_per_gpu": n_own0, "particles_total_after_run": int(tot.item()),
+                   "parallelism": f"slab{world}: 1-D slabs of cell layers along axis {eng.axis}, "
+                                  f"halo (one cutoff) + migration every step, NCCL send/recv ring",
+                   "slab": {"layers": [eng.z0, eng.z1], "of": eng.layers, "own_cap": eng.own_cap,
+                            "halo_cap": eng.halo_cap, "mig_cap": eng.mig_cap,
+                            "message_bytes_per_step_per_rank": int(xbytes),
+                            "host_enqueue_ms_per_step": t_host / args.steps * 1e3,
+                            "exchange_ms_bytes_by_phase": {str(k): [round(v[0], 4), v[1]] for k, v in xt.items()},
+                            "counts": counts},
+                   "l2_policy": "per-rank state larger than L2" if n_own0 * 212 > 126e6 else
+                                "per-rank state fits L2 (strong scaling of the named size)"},
+        "clocks": clocks, "gpu_launches": int(launches), "device_error_word": err,
+        "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": UNIT,
+                "h2d_bytes_per_step": int(bytes_all.item()), "d2h_bytes_per_step": int(bytes_all.item()),
+                "steps": e2e_steps,
+                "what": "per rank: SlabEngine.upload(own slab, host) + step (with exchanges) + download(host), every step"},
+        "roofline": roof,
+        "cpu_baseline": {"value": None, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": "reported at N=1 only"},
     }
     print(json.dumps(line))
 

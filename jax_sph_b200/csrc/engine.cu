@@ -315,7 +315,7 @@ SweepPlan plan_sweep(const sphb200_engine* e, int nq) {
   const Grid& g = e->grid;
   const sphb200_config& c = e->cfg;
   double pop = 1.0;
-  for (int a = 0; a < c.dim; ++a) pop *= (c.box[a] / g.n[a]) / c.dx;
+  for (int a = 0; a < c.dim; ++a) pop *= (c.box[a] / g.ng[a]) / c.dx;  // global cells: n[] is the slab-local view
   int rows = 1;
   for (int a = 1; a < 3; ++a) rows *= (g.n[a] >= 2 * g.S[a] + 1) ? g.T[a] + 2 * g.S[a] : g.n[a];
   int nxs = (g.n[0] >= 2 * g.S[0] + 1) ? g.T[0] + 2 * g.S[0] : g.n[0];

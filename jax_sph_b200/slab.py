@@ -102,6 +102,9 @@ class SlabEngine:
                      for k in ("send_lo", "send_hi", "recv_lo", "recv_hi")}
         self.bytes_exchanged = 0
         self._keep = []
+        self._pinned = {}
+        self.time_exchanges = False  # CUDA events around every exchange (bench diagnostics)
+        self._xev = []
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -175,11 +178,29 @@ class SlabEngine:
         if on_host:
             torch.cuda.current_stream().synchronize()
 
-    def _exchange(self, nbytes: int):
+    def _exchange(self, nbytes: int, phase: int = 0):
         b = self._buf
+        if self.time_exchanges:
+            torch = _torch()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         ring_exchange(b["send_lo"][:nbytes], b["send_hi"][:nbytes], b["recv_lo"][:nbytes],
                       b["recv_hi"][:nbytes], self.rank, self.nranks, self.group)
+        if self.time_exchanges:
+            e1.record()
+            self._xev.append((phase, nbytes, e0, e1))
         self.bytes_exchanged += 2 * nbytes
+
+    def exchange_times(self):
+        """{phase: (mean ms on the stream incl. waiting for the neighbour, bytes per message)}."""
+        _torch().cuda.synchronize()
+        acc = {}
+        for phase, nb, e0, e1 in self._xev:
+            a = acc.setdefault(phase, [0.0, 0, nb])
+            a[0] += e0.elapsed_time(e1)
+            a[1] += 1
+        self._xev = []
+        return {ph: (a[0] / a[1], a[2]) for ph, a in acc.items()}
 
     def run_phase(self, phase: int, dt: float, flags: int) -> int:
         """Enqueue one phase of the step; returns the bytes of the send buffers the ring
@@ -200,7 +221,7 @@ class SlabEngine:
                 nb = self.run_phase(phase, dt, flags)
                 if nb == 0:
                     break
-                self._exchange(nb)
+                self._exchange(nb, phase)
                 phase += 1
 
     def counts(self) -> Dict[str, int]:
@@ -213,15 +234,22 @@ class SlabEngine:
         torch = _torch()
         rows = self.counts()["own"]
         out = {}
+        # pinned staging is allocated once at capacity (cudaHostAlloc is slow) and handed out as
+        # views: the arrays of the previous download are overwritten by the next one
+        pool = self._pinned
         for k in keys or STATE_KEYS:
             if k == "nw" and not (self.cfg.solver == 1 or self.cfg.flags & _lib.F_FREE_SLIP):
                 continue
             if k in ("kappa", "Cp") and not self.cfg.flags & _lib.F_HEAT:
                 continue
-            shape = (rows, self.dim) if k in _lib.VECTOR_FIELDS else (rows,)
-            out[k] = torch.empty(shape, dtype=torch.int32 if k == "tag" else torch.float32,
-                                 pin_memory=True)
-        ids = torch.empty(rows, dtype=torch.int32, pin_memory=True)
+            width = self.dim if k in _lib.VECTOR_FIELDS else 1
+            if k not in pool:
+                pool[k] = torch.empty(self.own_cap * width, pin_memory=True,
+                                      dtype=torch.int32 if k == "tag" else torch.float32)
+            out[k] = pool[k][:rows * width].view((rows, self.dim) if width > 1 else (rows,))
+        if "ids" not in pool:
+            pool["ids"] = torch.empty(self.own_cap, dtype=torch.int32, pin_memory=True)
+        ids = pool["ids"][:rows]
         st, on_host, _ = self._state_struct(out, rows)
         _lib.check(self.lib.sphb200_slab_download(self._h, C.byref(st), C.c_void_p(ids.data_ptr()),
                                                   rows, 1, _stream_ptr()))
@@ -249,9 +277,10 @@ class SlabEngine:
             return int(code.value)
         import torch.distributed as dist
 
-        t = torch.tensor([code.value], dtype=torch.int32, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.BOR, group=self.group)
-        return int(t.item())
+        # NCCL has no bitwise OR: reduce the 32 bits separately with MAX
+        bits = torch.tensor([(code.value >> i) & 1 for i in range(32)], dtype=torch.int32, device="cuda")
+        dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=self.group)
+        return sum(int(v) << i for i, v in enumerate(bits.tolist()))
 
     def stats(self, reduce: bool = True):
         """Kinetic energy (sum) and max |u| (max) over the ranks (utils.py:128-166)."""
