@@ -36,7 +36,7 @@ constexpr int DEFAULT_TPB = 512;  // tuned on B200, profiles/ (tune logs)
 inline size_t up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
 
 struct SweepPlan {
-  int nq, cap;
+  int nq, cap, lcap;
   size_t smem;
 };
 
@@ -311,7 +311,10 @@ void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, Layout& L) {
   L.total = off;
 }
 
-SweepPlan plan_sweep(const sphb200_engine* e, int nq) {
+// lcap: per-thread pair-list entries in shared memory.  The sweeps that search (density =
+// list builder, the materialiser) want it long -- fewer, more even flushes; a list consumer
+// only searches in its fall-back path, so it gets the minimum and the staging buffer the rest.
+SweepPlan plan_sweep(const sphb200_engine* e, int nq, int lcap) {
   const Grid& g = e->grid;
   const sphb200_config& c = e->cfg;
   double pop = 1.0;
@@ -322,8 +325,13 @@ SweepPlan plan_sweep(const sphb200_engine* e, int nq) {
   long long want = (long long)(rows * (double)nxs * pop * 1.3) + 64;
   if (c.stage_cap > 0) want = c.stage_cap;
   if (want > e->n + 32) want = e->n + 32;  // never more than (a few images of) everything
-  size_t fixed = sweep_smem_bytes(nq, 0, e->lcap, e->tpb);
+  size_t fixed = sweep_smem_bytes(nq, 0, lcap, e->tpb);
   long long fit = ((long long)e->max_smem - (long long)fixed) / (16LL * nq);
+  while (fit < want && lcap > 24) {  // the staging buffer comes first: a stencil that does not
+    lcap -= 8;                       // fit is swept in several groups and gets no shared lists
+    fixed = sweep_smem_bytes(nq, 0, lcap, e->tpb);
+    fit = ((long long)e->max_smem - (long long)fixed) / (16LL * nq);
+  }
   if (want > fit) want = fit;
   if (want > 65535) want = 65535;
   want = want / 32 * 32;
@@ -331,7 +339,8 @@ SweepPlan plan_sweep(const sphb200_engine* e, int nq) {
   SweepPlan p;
   p.nq = nq;
   p.cap = (int)want;
-  p.smem = sweep_smem_bytes(nq, p.cap, e->lcap, e->tpb);
+  p.lcap = lcap;
+  p.smem = sweep_smem_bytes(nq, p.cap, lcap, e->tpb);
   return p;
 }
 
@@ -339,7 +348,7 @@ template <class K>
 int launch_sweep(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f, const Extra& ex,
                  cudaStream_t st, const NList& nl = NList{nullptr, nullptr, nullptr, 0, 0}) {
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
-  SweepDims sd{sp.cap, e->lcap, ex.nq};
+  SweepDims sd{sp.cap, sp.lcap, ex.nq};
   const int blocks = e->grid.nt[0] * e->grid.nt[1] * e->grid.nt[2];
   kern<<<blocks, e->tpb, sp.smem, st>>>(e->grid, e->consts, f, e->start, sd, ex, e->err, nl);
   e->launches++;
@@ -438,7 +447,8 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
   const int fq_h = heat ? force_nq++ : -1;
   const int fq_nw = rie ? force_nq++ : -1;
   const int fq_ut = (rie && e->has_ut) ? force_nq++ : -1;
-  const SweepPlan planF = plan_sweep(e, force_nq);
+  const SweepPlan planF =
+      plan_sweep(e, force_nq, e->pl_lmax > 0 ? (e->lcap < 24 ? e->lcap : 24) : e->lcap);
   const bool dens_extras = e->has_ut || (rie && bc_trick && heat);
   const SweepPlan planD = !evol ? (dens_extras ? e->planW : e->planA) : (!rie ? e->planR : e->planW);
   // neighbour lists: built by the density sweep, consumed by every later sweep of this step
@@ -446,7 +456,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
   {
     int mc = planD.cap < planF.cap ? planD.cap : planF.cap;
     if (evol && renorm && e->planR.cap < mc) mc = e->planR.cap;
-    if (wall_sweep && e->planW.cap < mc) mc = e->planW.cap;
+    if (wall_sweep && e->planC.cap < mc) mc = e->planC.cap;
     nl.min_cap = mc;
   }
   // ---- density -------------------------------------------------------------
@@ -506,7 +516,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
     ex.free_slip = free_slip;
     Frame& F = e->fr[e->cur];
     ex.st_out = e->fr[1 - e->cur].st;
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysWall<D, K>, LIST_CONSUME>, e->planW, F, ex, st, nl)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysWall<D, K>, LIST_CONSUME>, e->planC, F, ex, st, nl)
     DISPATCH_DK(e, CALL);
 #undef CALL
     if (rc) return rc;
@@ -653,7 +663,7 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->max_smem = maxs - 1024;
   e->tpb = cfg->threads > 0 ? (cfg->threads + 31) / 32 * 32 : DEFAULT_TPB;
   if (e->tpb > 512) e->tpb = 512;
-  e->lcap = cfg->list_cap > 0 ? cfg->list_cap : 32;
+  e->lcap = cfg->list_cap > 0 ? cfg->list_cap : 48;  // tuned on B200 (profiles/, tune logs)
   if (e->lcap < SWEEP_CHUNK) e->lcap = SWEEP_CHUNK;
   plan_grid(*cfg, e->grid, e->tpb, e->slab_rank, e->slab_nranks);
   plan_consts(*cfg, e->consts);
@@ -720,11 +730,11 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->hstage = nullptr;
   e->hstage_bytes = 0;
   memset(e->times, 0, sizeof(e->times));
-  e->planA = plan_sweep(e, 1);
-  e->planR = plan_sweep(e, 2);
-  e->planW = plan_sweep(e, 4);
-  e->planC = plan_sweep(e, 4);
-  e->planN = plan_sweep(e, 2);
+  e->planA = plan_sweep(e, 1, e->lcap);
+  e->planR = plan_sweep(e, 2, e->lcap);
+  e->planW = plan_sweep(e, 4, e->lcap);
+  e->planC = plan_sweep(e, 4, 24);  // wall sweep: a list consumer
+  e->planN = plan_sweep(e, 2, e->lcap);
   e->needs_zero = true;  // control words are zeroed on the first upload's stream
   return SPHB200_OK;
 }
