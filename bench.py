@@ -32,13 +32,25 @@ METRIC = "particle-updates/sec"
 UNIT = "particle-updates/s"
 
 # algorithmic HBM bytes per particle-step (float32, 3D / 2D), DESIGN.md section 4
+# (state quads + the particle's neighbour-list row: 93 / 25 entries in chunks of 8 x 2 B + count)
 BYTES = {
-    3: dict(cells=64 + 8 + 12 + 16 + 76 + 84, density=16 + 16, force=64 + 32, step=0),
-    2: dict(cells=64 + 8 + 12 + 16 + 76 + 84, density=16 + 16, force=64 + 32, step=0),
+    3: dict(cells=276, density=64 + 196, force=112 + 196),
+    2: dict(cells=276, density=64 + 68, force=112 + 68),
 }
 # useful flops per directed in-range edge, SURVEY.md section 8d
 FLOPS_EDGE = {3: dict(density=58 + 1, force=58 + 103 + 16), 2: dict(density=50 + 1, force=50 + 63 + 14)}
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal non-tensor FP32 FMA peak
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep, from the committed
+    ncu capture of this workload (profiles/r01_traffic.json); None when absent."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -258,8 +270,8 @@ def run_ours(args):
         "achieved": f_bytes / (f_ms * 1e-3) / 1e9 if f_ms else None,
         "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": which,
         "frac": (f_bytes / (f_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if f_ms else None,
-        "traffic": None, "ms": f_ms,
-        "note": "FP32-pipe bound, not HBM bound: see fp32",
+        "traffic": ncu_traffic("force"), "ms": f_ms,
+        "note": "bound by shared-memory wavefronts and FP32/ALU issue, not by HBM: see fp32",
         "fp32": {"achieved_tflops": f_flops / (f_ms * 1e-3) / 1e12 if f_ms else None,
                  "peak_tflops_nominal": FP32_PEAK_TFLOPS,
                  "frac": (f_flops / (f_ms * 1e-3) / 1e12) / FP32_PEAK_TFLOPS if f_ms else None},
