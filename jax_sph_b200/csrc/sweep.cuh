@@ -252,6 +252,9 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
     else if (ka < kn && kn < kb) ks = kn;
     const float xs0 = ri[0] - (float)wrap_count(sa0[0] + ka, g.n[0]) * g.box[0];  // x is never the slab axis
     const float xs1 = ri[0] - (float)wrap_count(sa0[0] + ks, g.n[0]) * g.box[0];
+    // the second x segment exists only where the window crosses the periodic seam: elsewhere
+    // (all lanes of the warp agree) the row loop visits first segments only
+    const int it_step = __any_sync(FULL_MASK, have && ks < kb) ? 1 : 2;
 
     // ---- staging groups: maximal runs [e_a, e_b) of consecutive (row, cell) entries that
     //      fit the staging buffer (one group unless the stencil is unusually crowded) ----
@@ -316,7 +319,8 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
           for (;;) {
             const int rem = jb - j;
             if (!__any_sync(FULL_MASK, rem > 0)) {
-              if (++it >= nit) {
+              it = it < 0 ? 0 : it + it_step;
+              if (it >= nit) {
                 fin = true;
                 break;
               }
