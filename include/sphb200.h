@@ -193,6 +193,16 @@ int sphb200_engine_error(sphb200_engine *e, uint32_t *code, void *stream);
  * SPHB200_ERR_NEIGHBOR_OVERFLOW.  idx == NULL with capacity 0 only counts. */
 int sphb200_engine_neighbor_list(sphb200_engine *e, int32_t *idx, int64_t capacity,
                                  int mask_self, int64_t *count, void *stream);
+/* Wall-normal recomputation, the integrator's `nw_fn` (jax_sph/integrator.py:33-34;
+ * compute_nws_jax_wrapper, jax_sph/utils.py:197-277; enabled by case_setup.py:209-218 when a
+ * MOVING_WALL exists and the solver reads normals).  layer: HOST array (n_layer, dim) float32,
+ * the one-layer discretisation `wall_part_fn(dx / 5, 1) - offset / n_walls / 5`; offset: HOST
+ * (dim) float32 subtracted from the wall positions; cutoff = dx * n_walls * sqrt(2) * 1.01.
+ * From then on every integrating step rewrites nw after the drift: each wall particle gets
+ * disp(closest layer particle, particle) / (dist + EPS), all other particles zero.
+ * n_layer = 0 switches it off (normals stay what upload() provided).  sync (copies). */
+int sphb200_engine_set_wall_layer(sphb200_engine *e, const float *layer, int n_layer,
+                                  const float *offset, double cutoff);
 /* sync: kinetic energy 0.5*sum(m u.u) (utils.py:128-133) and max |u| (utils.py:136-166). */
 int sphb200_engine_stats(sphb200_engine *e, double *ekin, double *u_max, void *stream);
 /* Kernel launches issued by this engine so far (bench.py's gpu_launches). */

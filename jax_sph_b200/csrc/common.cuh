@@ -77,6 +77,7 @@ struct Consts {
 struct Extra {
   float4* st_out;  // destination of the (rho, p, T, dTdt) quad (ping-pong, see engine.cu)
   int nq;          // quads staged per particle
+  int sb;          // bytes staged per particle when the policy stages a compact record, else 0
   int q_v, q_h, q_nw, q_ut;  // optional staged quads (force sweep), -1 = absent
   int utilde;      // RIE & bc_trick & !free_slip: write u_tilde
   int wallT;       // RIE & bc_trick & heat: Shepard wall temperature

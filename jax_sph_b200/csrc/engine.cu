@@ -36,7 +36,7 @@ constexpr int DEFAULT_TPB = 512;  // tuned on B200, profiles/ (tune logs)
 inline size_t up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
 
 struct SweepPlan {
-  int nq, cap, lcap;
+  int sb, cap, lcap;  // bytes staged per particle, staged particles, list entries per thread
   size_t smem;
 };
 
@@ -86,6 +86,12 @@ struct sphb200_engine {
   uint32_t slab_flags;
   bool slab_v_is_u;
   Kick slab_kick;
+  // wall-normal recomputation for moving walls (utils.py:197-277): the static one-layer
+  // discretisation of the wall surface; wl_n == 0: normals are an input that never changes
+  float4* wl_pts;
+  int wl_n;
+  float wl_off[3];
+  float wl_c2;
 };
 
 namespace {
@@ -314,7 +320,11 @@ void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, Layout& L) {
 // lcap: per-thread pair-list entries in shared memory.  The sweeps that search (density =
 // list builder, the materialiser) want it long -- fewer, more even flushes; a list consumer
 // only searches in its fall-back path, so it gets the minimum and the staging buffer the rest.
-SweepPlan plan_sweep(const sphb200_engine* e, int nq, int lcap) {
+SweepPlan plan_sweep_bytes(const sphb200_engine* e, int sb, int lcap);
+SweepPlan plan_sweep(const sphb200_engine* e, int nq, int lcap) { return plan_sweep_bytes(e, 16 * nq, lcap); }
+// sb: bytes staged per particle (a multiple of 4; capacities are multiples of 32 particles, so
+// whatever follows the staging buffer stays 16-byte aligned)
+SweepPlan plan_sweep_bytes(const sphb200_engine* e, int sb, int lcap) {
   const Grid& g = e->grid;
   const sphb200_config& c = e->cfg;
   double pop = 1.0;
@@ -325,22 +335,22 @@ SweepPlan plan_sweep(const sphb200_engine* e, int nq, int lcap) {
   long long want = (long long)(rows * (double)nxs * pop * 1.3) + 64;
   if (c.stage_cap > 0) want = c.stage_cap;
   if (want > e->n + 32) want = e->n + 32;  // never more than (a few images of) everything
-  size_t fixed = sweep_smem_bytes(nq, 0, lcap, e->tpb);
-  long long fit = ((long long)e->max_smem - (long long)fixed) / (16LL * nq);
+  size_t fixed = sweep_smem_bytes(sb, 0, lcap, e->tpb);
+  long long fit = ((long long)e->max_smem - (long long)fixed) / (long long)sb;
   while (fit < want && lcap > 24) {  // the staging buffer comes first: a stencil that does not
     lcap -= 8;                       // fit is swept in several groups and gets no shared lists
-    fixed = sweep_smem_bytes(nq, 0, lcap, e->tpb);
-    fit = ((long long)e->max_smem - (long long)fixed) / (16LL * nq);
+    fixed = sweep_smem_bytes(sb, 0, lcap, e->tpb);
+    fit = ((long long)e->max_smem - (long long)fixed) / (long long)sb;
   }
   if (want > fit) want = fit;
   if (want > 65535) want = 65535;
   want = want / 32 * 32;
   if (want < 32) want = 32;
   SweepPlan p;
-  p.nq = nq;
+  p.sb = sb;
   p.cap = (int)want;
   p.lcap = lcap;
-  p.smem = sweep_smem_bytes(nq, p.cap, lcap, e->tpb);
+  p.smem = sweep_smem_bytes(sb, p.cap, lcap, e->tpb);
   return p;
 }
 
@@ -348,7 +358,10 @@ template <class K>
 int launch_sweep(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f, const Extra& ex,
                  cudaStream_t st, const NList& nl = NList{nullptr, nullptr, nullptr, 0, 0}) {
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
-  SweepDims sd{sp.cap, sp.lcap, ex.nq};
+  // a sweep may stage fewer bytes than its plan was sized for, never more
+  const int sb = ex.sb > 0 ? ex.sb : 16 * ex.nq;
+  if (sb > sp.sb) return SPHB200_EINVAL;
+  SweepDims sd{sp.cap, sp.lcap, sb};
   const int blocks = e->grid.nt[0] * e->grid.nt[1] * e->grid.nt[2];
   kern<<<blocks, e->tpb, sp.smem, st>>>(e->grid, e->consts, f, e->start, sd, ex, e->err, nl);
   e->launches++;
@@ -379,6 +392,48 @@ void swap_st(sphb200_engine* e) {
   float4* t = e->fr[0].st;
   e->fr[0].st = e->fr[1].st;
   e->fr[1].st = t;
+}
+
+// nw_fn of the integrator (integrator.py:33-34, compute_nws_jax_wrapper utils.py:197-277):
+// every wall particle takes the direction to the closest particle of the wall-surface layer
+// among those within the list cutoff; everything else gets a zero normal.  The layer is a
+// few thousand points (5 per dx of wall length), scanned linearly by each wall particle --
+// the case that needs this (a MOVING_WALL with free-slip or Riemann walls) is the 2D/3D
+// Couette channel, O(walls x layer) is a fraction of one sweep there.  Reference quirk kept:
+// layer particle 0 is never matched (`idx > len(r_walls)`, utils.py:252).
+template <int DIM>
+__global__ void __launch_bounds__(256)
+    k_wall_normals(int n, Grid g, Slab sl, Consts c, Frame f, const float4* __restrict__ layer,
+                   int nl, float ox, float oy, float oz, float c2) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (sl.dn ? sl.dn[DN_OWN] : n)) return;
+  const int p = sl.base + t;
+  const float4 pt = f.pt[p];
+  float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (is_wall_tag(__float_as_int(pt.w))) {
+    const float rw[3] = {__fsub_rn(pt.x, ox), __fsub_rn(pt.y, oy), __fsub_rn(pt.z, oz)};
+    float best = __int_as_float(0x7f800000), bd[3] = {0.f, 0.f, 0.f};
+    for (int j = 1; j < nl; ++j) {
+      const float4 q = __ldg(layer + j);
+      float d[3];
+      d[0] = __fsub_rn(mod_side(__fadd_rn(__fsub_rn(q.x, rw[0]), g.half[0]), g.box[0]), g.half[0]);
+      d[1] = __fsub_rn(mod_side(__fadd_rn(__fsub_rn(q.y, rw[1]), g.half[1]), g.box[1]), g.half[1]);
+      d[2] = DIM == 3
+                 ? __fsub_rn(mod_side(__fadd_rn(__fsub_rn(q.z, rw[2]), g.half[2]), g.box[2]), g.half[2])
+                 : 0.f;
+      const float d2 = sumsq<DIM>(d);
+      if (d2 < c2 && d2 < best) {  // first minimum wins, like argmin
+        best = d2;
+        bd[0] = d[0]; bd[1] = d[1]; bd[2] = d[2];
+      }
+    }
+    if (best < __int_as_float(0x7f800000)) {
+      const float den = __fadd_rn(best > 0.f ? __fsqrt_rn(best) : 0.f, c.eps);
+      out = make_float4(__fdiv_rn(bd[0], den), __fdiv_rn(bd[1], den),
+                        DIM == 3 ? __fdiv_rn(bd[2], den) : 0.f, 0.f);
+    }
+  }
+  f.nw[p] = out;
 }
 
 // first half of the cell pipeline: kick + drift + wrap (recomputed later, not stored), cell
@@ -418,6 +473,20 @@ int sort_cells(sphb200_engine* e, const Kick& k, cudaStream_t st) {
   CK(cudaGetLastError());
   e->cur ^= 1;
   e->cells_valid = true;
+  if (e->wl_n > 0 && e->has_nw && k.on) {  // integrator.py:33-34: nw = nw_fn(r) after the drift
+    const int wb = e->slab_on ? e->sgeom.own_cap : e->n;
+    Frame& F = e->fr[e->cur];
+    if (e->dim == 2)
+      k_wall_normals<2><<<(wb + 255) / 256, 256, 0, st>>>(wb, e->grid, e->slab, e->consts, F, e->wl_pts,
+                                                        e->wl_n, e->wl_off[0], e->wl_off[1],
+                                                        e->wl_off[2], e->wl_c2);
+    else
+      k_wall_normals<3><<<(wb + 255) / 256, 256, 0, st>>>(wb, e->grid, e->slab, e->consts, F, e->wl_pts,
+                                                        e->wl_n, e->wl_off[0], e->wl_off[1],
+                                                        e->wl_off[2], e->wl_c2);
+    e->launches++;
+    CK(cudaGetLastError());
+  }
   return SPHB200_OK;
 }
 
@@ -447,8 +516,13 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
   const int fq_h = heat ? force_nq++ : -1;
   const int fq_nw = rie ? force_nq++ : -1;
   const int fq_ut = (rie && e->has_ut) ? force_nq++ : -1;
+  // the two headline SPH variants stage a compact record (phys.cuh, PhysForce)
+  const bool av_on = c.artificial_alpha != 0.0;
+  const int force_feat = (heat || av_on) ? FORCE_GENERIC : (v_is_u ? FORCE_PLAIN : FORCE_TVF);
+  const int force_sb = (rie || force_feat == FORCE_GENERIC) ? 16 * force_nq
+                                                           : (force_feat == FORCE_TVF ? 52 : 40);
   const SweepPlan planF =
-      plan_sweep(e, force_nq, e->pl_lmax > 0 ? (e->lcap < 24 ? e->lcap : 24) : e->lcap);
+      plan_sweep_bytes(e, force_sb, e->pl_lmax > 0 ? (e->lcap < 24 ? e->lcap : 24) : e->lcap);
   const bool dens_extras = e->has_ut || (rie && bc_trick && heat);
   const SweepPlan planD = !evol ? (dens_extras ? e->planW : e->planA) : (!rie ? e->planR : e->planW);
   // neighbour lists: built by the density sweep, consumed by every later sweep of this step
@@ -529,15 +603,16 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
     Extra ex = make_extra();
     ex.q_v = fq_v; ex.q_h = fq_h; ex.q_nw = fq_nw; ex.q_ut = fq_ut;
     ex.nq = force_nq;
+    ex.sb = force_sb;
     ex.heat = heat;
-    ex.av = c.artificial_alpha != 0.0;
+    ex.av = av_on;
     ex.bc_on = (flags & SPHB200_STEP_BC) && bc_table_on(c);
     ex.free_slip = free_slip;
     ex.bc_trick = bc_trick;
     const SweepPlan& sp = planF;
     Frame& F = e->fr[e->cur];
     if (!rie) {
-      const int feat = (heat || ex.av) ? FORCE_GENERIC : (v_is_u ? FORCE_PLAIN : FORCE_TVF);
+      const int feat = force_feat;
       if (feat == FORCE_PLAIN) {
 #define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>, LIST_CONSUME>, sp, F, ex, st, nl)
         DISPATCH_DK(e, CALL);
@@ -842,8 +917,35 @@ int sphb200_engine_destroy(sphb200_engine* e) {
   if (e->profile)
     for (int i = 0; i < 8; ++i) cudaEventDestroy(e->ev[i]);
   if (e->hstage) cudaFree(e->hstage);
+  if (e->wl_pts) cudaFree(e->wl_pts);
   if (e->own_arena) cudaFree(e->arena);
   delete e;
+  return SPHB200_OK;
+}
+
+int sphb200_engine_set_wall_layer(sphb200_engine* e, const float* layer, int n_layer,
+                                  const float* offset, double cutoff) {
+  if (!e || n_layer < 0 || (n_layer > 0 && (!layer || !offset || !(cutoff > 0.0)))) return SPHB200_EINVAL;
+  if (n_layer > 0 && !e->has_nw) return SPHB200_EINVAL;  // this solver variant reads no normals
+  if (e->wl_pts) cudaFree(e->wl_pts);
+  e->wl_pts = nullptr;
+  e->wl_n = 0;
+  if (n_layer == 0) return SPHB200_OK;
+  float4* h = new (std::nothrow) float4[n_layer];
+  if (!h) return SPHB200_ENOMEM;
+  for (int i = 0; i < n_layer; ++i)
+    h[i] = make_float4(layer[(size_t)i * e->dim], layer[(size_t)i * e->dim + 1],
+                       e->dim == 3 ? layer[(size_t)i * e->dim + 2] : 0.f, 0.f);
+  int rc = SPHB200_OK;
+  if (cudaMalloc((void**)&e->wl_pts, (size_t)n_layer * sizeof(float4)) != cudaSuccess) rc = SPHB200_ENOMEM;
+  else if (cudaMemcpy(e->wl_pts, h, (size_t)n_layer * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess)
+    rc = SPHB200_ECUDA;
+  delete[] h;
+  if (rc) return rc;
+  e->wl_n = n_layer;
+  for (int a = 0; a < 3; ++a) e->wl_off[a] = a < e->dim ? offset[a] : 0.f;
+  const float c = (float)cutoff;  // weak-typed scalar squared in float32 (jax_md/partition.py:820-821)
+  e->wl_c2 = c * c;
   return SPHB200_OK;
 }
 

@@ -285,10 +285,21 @@ struct PhysWall {
 };
 
 // ---------------------------------------------------------------------------
-// Force sweep.  Staged quads: 0 (x,y,z,tag) 1 (u, rho) 2 (p, eta, mass, (m/rho)^2)
-// [q_v] (v, 0)  [q_h] (T, kappa, 0, 0)  [q_nw] (nw, 0)  [q_ut] (u_tilde, 0)
+// Force sweep.  Staged per particle (GENERIC / RIE): quads 0 (x,y,z,tag) 1 (u, rho)
+// 2 (p, eta, mass, (m/rho)^2) [q_v] (rho/2 (v - u), 0)  [q_h] (T, kappa, 0, 0)  [q_nw] (nw, 0)
+// [q_ut] (u_tilde, 0).  The two headline variants stage a COMPACT record -- the sweep is bound
+// by shared-memory wavefronts of these random 16-byte gathers, so every byte counts:
+//   FORCE_TVF   quads 0 (x,y,z,rho) 1 (u, p) 2 (rho/2 (v - u), (m/rho)^2) + float column eta  (52 B)
+//   FORCE_PLAIN quads 0 (x,y,z,rho) 1 (u, p)     + float2 column (eta, (m/rho)^2)            (40 B)
 // FEAT: compile-time specialisation of the two headline variants; GENERIC reads
 // the switches from Extra at run time.
+//
+// Standard acceleration (solver.py:221-256) per pair, with c = ((m_i/rho_i)^2 + (m_j/rho_j)^2)/m_i
+// * grad_w / (d + EPS):
+//     a_i += c (-p_ij r + 1/2 (A_i + A_j) r + eta_ij u_ij),   A = rho u (x) (v - u)
+// is accumulated as  a_i += -(c p_ij) r + (c eta_ij) u_ij + (c (rho_j/2 (v_j-u_j)).r) u_j  and the
+// A_i term is factored out of the sum: 1/2 rho_i u_i ((v_i-u_i) . sum_j c r); sum_j c r is the
+// transport-velocity sum the sweep keeps anyway (dvdt = p_bg sum_j c r, solver.py:199-213).
 enum { FORCE_PLAIN = 0, FORCE_TVF = 1, FORCE_GENERIC = 2 };
 
 template <int DIM, int KERN, int SOLVER, int FEAT>
@@ -297,24 +308,44 @@ struct PhysForce {
   static constexpr bool SENDER_VIEW = false;
   struct Own {
     float u[3], dvu[3], g[3];
-    float rho, p, eta, inv_m, V2, T, kappa, Cp;
+    float rho, p, eta, eta2, inv_m, V2, T, kappa, Cp;
     int tag;
   };
   struct Acc {
     float a[3], tv[3], av[3];
     float dT;
   };
-  __device__ static int qv(const Extra& ex) {
-    return FEAT == FORCE_PLAIN ? -1 : (FEAT == FORCE_TVF ? 3 : ex.q_v);
+  static constexpr bool COMPACT = SOLVER == SPHB200_SOLVER_SPH && FEAT != FORCE_GENERIC;
+  static constexpr int CQ = FEAT == FORCE_TVF ? 3 : 2;  // quads of the compact record
+  // bytes staged per particle (engine.cu sizes the staging buffer with it)
+  __host__ __device__ static int stage_bytes(int nq_generic) {
+    return COMPACT ? (FEAT == FORCE_TVF ? 52 : 40) : 16 * nq_generic;
   }
+  __device__ static int qv(const Extra& ex) { return ex.q_v; }
   __device__ static void stage(const Consts&, const Frame& f, const Extra& ex, int gp, float4* sq,
                                int cap, int d) {
-    const float4 um = f.um[gp], st = f.st[gp], vv = f.vv[gp];
-    sq[d] = f.pt[gp];
-    sq[cap + d] = make_float4(um.x, um.y, um.z, st.x);
+    const float4 pt = f.pt[gp], um = f.um[gp], st = f.st[gp], vv = f.vv[gp];
     const float vol = um.w / st.x;
+    if (COMPACT) {
+      sq[d] = make_float4(pt.x, pt.y, pt.z, st.x);
+      sq[cap + d] = make_float4(um.x, um.y, um.z, st.y);
+      if (FEAT == FORCE_TVF) {
+        const float hr = 0.5f * st.x;
+        sq[2 * cap + d] = make_float4(hr * (vv.x - um.x), hr * (vv.y - um.y), hr * (vv.z - um.z),
+                                      vol * vol);
+        reinterpret_cast<float*>(sq + 3 * cap)[d] = vv.w;
+      } else {
+        reinterpret_cast<float2*>(sq + 2 * cap)[d] = make_float2(vv.w, vol * vol);
+      }
+      return;
+    }
+    sq[d] = pt;
+    sq[cap + d] = make_float4(um.x, um.y, um.z, st.x);
     sq[2 * cap + d] = make_float4(st.y, vv.w, um.w, vol * vol);
-    if (qv(ex) >= 0) sq[qv(ex) * cap + d] = make_float4(vv.x - um.x, vv.y - um.y, vv.z - um.z, 0.f);
+    if (qv(ex) >= 0) {
+      const float hr = 0.5f * st.x;
+      sq[qv(ex) * cap + d] = make_float4(hr * (vv.x - um.x), hr * (vv.y - um.y), hr * (vv.z - um.z), 0.f);
+    }
     if (FEAT == FORCE_GENERIC) {
       if (ex.q_h >= 0) sq[ex.q_h * cap + d] = make_float4(st.z, f.kc[gp].x, 0.f, 0.f);
       if (ex.q_nw >= 0) sq[ex.q_nw * cap + d] = f.nw ? f.nw[gp] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -327,6 +358,7 @@ struct PhysForce {
     o.u[0] = um.x; o.u[1] = um.y; o.u[2] = um.z;
     o.dvu[0] = vv.x - um.x; o.dvu[1] = vv.y - um.y; o.dvu[2] = vv.z - um.z;
     o.eta = vv.w;
+    o.eta2 = 2.0f * vv.w;
     o.rho = st.x; o.p = st.y; o.T = st.z;
     const float vol = um.w / st.x;
     o.V2 = vol * vol;
@@ -354,34 +386,56 @@ struct PhysForce {
   __device__ static void pair(const Consts& c, const Extra& ex, const Own& o, Acc& a,
                               const float4* sq, int cap, int j, float4 pj, const float (&dr)[3],
                               float d2) {
-    const float4 q1 = sq[cap + j], q2 = sq[2 * cap + j];
+    const float4 q1 = sq[cap + j];
     const float uj[3] = {q1.x, q1.y, q1.z};
-    const float rho_j = q1.w, p_j = q2.x, eta_j = q2.y, m_j = q2.z, V2_j = q2.w;
-    const int tag_j = __float_as_int(pj.w);
+    float rho_j, p_j, eta_j, m_j = 0.f, V2_j;
+    float hdv[3] = {0.f, 0.f, 0.f};  // rho_j / 2 (v_j - u_j)
+    bool have_dv = false;
+    int tag_j = SPHB200_TAG_FLUID;
+    if (COMPACT) {
+      rho_j = pj.w;
+      p_j = q1.w;
+      if (FEAT == FORCE_TVF) {
+        const float4 q2 = sq[2 * cap + j];
+        hdv[0] = q2.x; hdv[1] = q2.y; hdv[2] = q2.z;
+        V2_j = q2.w;
+        eta_j = reinterpret_cast<const float*>(sq + 3 * cap)[j];
+        have_dv = true;
+      } else {
+        const float2 ev = reinterpret_cast<const float2*>(sq + 2 * cap)[j];
+        eta_j = ev.x;
+        V2_j = ev.y;
+      }
+    } else {
+      const float4 q2 = sq[2 * cap + j];
+      rho_j = q1.w; p_j = q2.x; eta_j = q2.y; m_j = q2.z; V2_j = q2.w;
+      tag_j = __float_as_int(pj.w);
+      if (SOLVER == SPHB200_SOLVER_SPH && qv(ex) >= 0) {
+        const float4 dj = sq[qv(ex) * cap + j];
+        hdv[0] = dj.x; hdv[1] = dj.y; hdv[2] = dj.z;
+        have_dv = true;
+      }
+    }
     const float dist = fsqrt(d2);
     const float gw = kernel_gw<KERN>(c, dist);
     const float id = frcp(dist + c.eps);
-    const float wv = (o.V2 + V2_j) * o.inv_m;                                // :205 / :247
-    const float cc = wv * gw * id;                                           // :206 / :248
-    const float eta_ij = fdiv(2.0f * o.eta * eta_j, o.eta + eta_j + c.eps);  // :243
-    // transport-velocity acceleration, always computed (:912-921)
-    const float ct = cc * c.p_bg_tvf;
+    const float wv = (o.V2 + V2_j) * o.inv_m;                        // :205 / :247
+    const float cc = wv * gw * id;                                   // :206 / :248
+    const float eta_ij = fdiv(o.eta2 * eta_j, o.eta + eta_j + c.eps);  // :243
+    // sum_j c r: the transport-velocity acceleration / p_bg, always computed (:912-921)
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) a.tv[k] += ct * dr[k];
+    for (int k = 0; k < DIM; ++k) a.tv[k] = fmaf(cc, dr[k], a.tv[k]);
 
     if (SOLVER == SPHB200_SOLVER_SPH) {
       const float p_ij = fdiv(rho_j * o.p + o.rho * p_j, o.rho + rho_j);  // :244
-      float si = 0.f, sj = 0.f;
-      if (qv(ex) >= 0) {
-        const float4 dj = sq[qv(ex) * cap + j];
-        const float dvj[3] = {dj.x, dj.y, dj.z};
-        si = dot3(o.dvu, dr, DIM);
-        sj = dot3(dvj, dr, DIM);
-      }
+      const float cp = cc * p_ij, ce = cc * eta_ij;
+      float cj = 0.f;
+      if (have_dv) cj = cc * dot3(hdv, dr, DIM);  // c (A_j r)_k = cj u_j[k]   (:250-251)
 #pragma unroll
       for (int k = 0; k < DIM; ++k) {
-        const float A = ((o.rho * o.u[k]) * si + (rho_j * uj[k]) * sj) * 0.5f;  // :250-251
-        a.a[k] += cc * ((-p_ij * dr[k] + A) + eta_ij * (o.u[k] - uj[k]));       // :254
+        float t = fmaf(-cp, dr[k], a.a[k]);       // -c p_ij r
+        t = fmaf(ce, o.u[k] - uj[k], t);          // c eta_ij u_ij
+        a.a[k] = have_dv ? fmaf(cj, uj[k], t) : t;
       }
     } else {
       float e[3] = {dr[0] * id, dr[1] * id, DIM == 3 ? dr[2] * id : 0.f};
@@ -447,12 +501,17 @@ struct PhysForce {
     float r[3] = {pt.x, pt.y, pt.z}, g[3];
     g_ext_of<DIM>(c, f, p, r, g);
     float du[3], dv[3];
+    // A_i term of the standard acceleration, factored out of the pair sum (see the header)
+    float ai = 0.f;
+    if (SOLVER == SPHB200_SOLVER_SPH && (COMPACT ? FEAT == FORCE_TVF : qv(ex) >= 0))
+      ai = 0.5f * o.rho * dot3(o.dvu, a.tv, DIM);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       float s = a.a[k];
+      if (SOLVER == SPHB200_SOLVER_SPH) s = fmaf(ai, o.u[k], s);
       if (FEAT == FORCE_GENERIC && ex.av) s = s + a.av[k];  // :925-928
       du[k] = s + g[k];                                     // :936
-      dv[k] = a.tv[k];
+      dv[k] = a.tv[k] * c.p_bg_tvf;                         // :205-211
     }
     float dTdt = a.dT;
     // case bc_fn, derivative part (u, v, p, T are patched by k_bc after the sweep)

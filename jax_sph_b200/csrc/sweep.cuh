@@ -32,7 +32,7 @@ constexpr int SWEEP_MAXT = 512;  // largest block size the kernels are compiled 
 struct SweepDims {
   int cap;   // staged particles per block
   int lcap;  // list entries per thread (>= SWEEP_CHUNK)
-  int nq;    // quads staged per particle
+  int sb;    // bytes staged per particle (16 per quad + scalar columns, see phys.cuh)
 };
 
 // Per-step neighbour lists in HBM, shared by all sweeps of one forward():
@@ -54,8 +54,8 @@ struct NList {
 
 enum { LIST_NONE = 0, LIST_BUILD = 1, LIST_CONSUME = 2 };
 
-__host__ __device__ inline size_t sweep_smem_bytes(int nq, int cap, int lcap, int tpb) {
-  return (size_t)nq * cap * 16 + (size_t)lcap * tpb * 2 + (MAX_SOFF + 1 + 2 * MAX_RUNS + 2) * 4;
+__host__ __device__ inline size_t sweep_smem_bytes(int sb, int cap, int lcap, int tpb) {
+  return (size_t)sb * cap + (size_t)lcap * tpb * 2 + (MAX_SOFF + 1 + 2 * MAX_RUNS + 2) * 4;
 }
 
 // unwrapped (global) cell index u in [-n, 2n)  ->  periodic image count / wrapped index
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
   const int TPB = blockDim.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = TPB >> 5;
   float4* sq = reinterpret_cast<float4*>(smem_raw);
-  unsigned short* list = reinterpret_cast<unsigned short*>(sq + (size_t)sd.nq * sd.cap);
+  unsigned short* list = reinterpret_cast<unsigned short*>(smem_raw + (size_t)sd.sb * sd.cap);
   int* soff = reinterpret_cast<int*>(list + (size_t)sd.lcap * TPB);
   int* own_off = soff + (MAX_SOFF + 1);
   int* own_start = own_off + (MAX_RUNS + 1);

@@ -22,7 +22,7 @@ def make_config(
     is_bc_trick=False, is_rho_evol=False, is_rho_renorm=False, is_free_slip=False,
     is_heat_conduction=False, artificial_alpha=0.0, g_ext_spec=None, bc_table=None,
     cell_sub=None, tile=None, threads=0, list_cap=0, stage_cap=0, nl_cap=0, g_ext_array=False,
-    r_cutoff=0.0,
+    r_cutoff=0.0, wall_layer=None,
 ):
     """Build a `sphb200_config` from the WCSPH constructor arguments
     (jax_sph/solver.py:616-637) plus the table forms of the case callables."""
@@ -110,6 +110,8 @@ def make_config(
     cfg.threads, cfg.list_cap, cfg.stage_cap = threads, list_cap, stage_cap
     cfg.nl_cap = nl_cap
     cfg.r_cutoff = float(r_cutoff)
+    # not part of the C struct: Engine / SlabEngine hand it to sphb200_engine_set_wall_layer
+    cfg.wall_layer = wall_layer
     return cfg
 
 
@@ -125,7 +127,15 @@ def config_from_setup(setup, **tuning):
         is_rho_evol=setup.density_evolution, is_rho_renorm=setup.density_renormalize,
         is_free_slip=setup.free_slip, is_heat_conduction=setup.heat_conduction,
         artificial_alpha=setup.artificial_alpha, g_ext_spec=setup.g_ext_spec,
-        bc_table=setup.bc_table, **tuning)
+        bc_table=setup.bc_table, wall_layer=getattr(setup, "nw_spec", None), **tuning)
+
+
+def set_wall_layer(lib, handle, dim, layer, offset, cutoff):
+    layer = np.ascontiguousarray(np.asarray(layer, dtype=np.float32).reshape(-1, dim))
+    offset = np.ascontiguousarray(np.asarray(offset, dtype=np.float32).reshape(dim))
+    _lib.check(lib.sphb200_engine_set_wall_layer(
+        handle, layer.ctypes.data_as(C.c_void_p), int(len(layer)),
+        offset.ctypes.data_as(C.c_void_p), float(cutoff)))
 
 
 def _torch():
@@ -160,6 +170,8 @@ class Engine:
             C.byref(self._h)))
         self.arena_bytes = nbytes.value
         self._keep = []
+        if getattr(cfg, "wall_layer", None):
+            self.set_wall_layer(**cfg.wall_layer)
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -265,6 +277,12 @@ class Engine:
             self._h, C.c_void_p(idx.data_ptr() if capacity else None), int(capacity),
             int(mask_self), C.c_void_p(cnt.data_ptr()), _stream_ptr()))
         return idx, int(cnt.item())
+
+    def set_wall_layer(self, layer, offset, cutoff):
+        """The integrator's `nw_fn` (jax_sph/integrator.py:33-34, utils.py:197-277): from now on
+        every integrating step recomputes the wall normals from this one-layer discretisation
+        of the wall surface (`layer` (n, dim), `offset` (dim,), list cutoff)."""
+        set_wall_layer(self.lib, self._h, self.dim, layer, offset, cutoff)
 
     def stats(self):
         ek, um = C.c_double(), C.c_double()

@@ -104,6 +104,10 @@ class SlabEngine:
         self._keep = []
         self._pinned = {}
         self.time_exchanges = False  # CUDA events around every exchange (bench diagnostics)
+        if getattr(cfg, "wall_layer", None):  # the integrator's nw_fn, see Engine.set_wall_layer
+            from .engine import set_wall_layer
+
+            set_wall_layer(self.lib, self._h, self.dim, **cfg.wall_layer)
         self._xev = []
 
     def close(self):

@@ -99,6 +99,8 @@ class Setup:
     n_walls: int = 3
     bc_table: dict = field(default_factory=dict)
     g_ext_spec: dict = field(default_factory=dict)
+    nw_fn: Optional[Callable] = None  # case_setup.py:218
+    nw_spec: Optional[dict] = None
 
 
 def _dt_cfl(dx, u_ref, c_ref, viscosity, g_mag, rho_ref, cfl, eps):
@@ -126,6 +128,43 @@ def _compute_nws_scipy(r, tag, dx, n_walls, offset_vec, wall_part_fn, eps):
     nw = np.zeros_like(r)
     nw[is_w] = nw_walls.astype(r.dtype)
     return nw
+
+
+def make_nw_fn(state0, dx, n_walls, offset_vec, box_size, wall_part_fn, dtype):
+    """compute_nws_jax_wrapper (utils.py:197-277): wall normals recomputed every step when a
+    MOVING_WALL exists (case_setup.py:209-218, integrator.py:33-34).  For every wall particle
+    the closest particle of a 5x finer one-layer discretisation of the wall surface, among
+    those within dx * n_walls * sqrt(2) * 1.01 (the Dense neighbour list of :227-238), gives
+    nw = disp(layer, wall) / (dist + EPS) in the position dtype.  Reference quirk kept:
+    ``mask_to_layer = idx > len(r_walls)`` (:252) never matches the FIRST layer particle."""
+    dtype = np.dtype(dtype)
+    t = dtype.type
+    eps = t(np.finfo(dtype).eps)
+    tag = state0["tag"]
+    is_w = np.isin(tag, WALL_TAGS)
+    off = np.asarray(offset_vec).astype(dtype)
+    layer = (wall_part_fn(dx / 5, 1).astype(dtype) - (np.asarray(offset_vec) / n_walls / 5).astype(dtype))
+    cutoff = dx * n_walls * 2.0**0.5 * 1.01
+    c2 = t(t(cutoff) * t(cutoff))  # weak-typed scalar squared in the position dtype
+    side = np.asarray(box_size).astype(dtype)
+
+    def nw_fn(r):
+        r_walls = (r[is_w] - off).astype(dtype)
+        dr = space.periodic_displacement(side, (layer[None, :, :] - r_walls[:, None, :]).astype(dtype))
+        d2 = space.square_distance(dr)
+        dist = space.distance(dr)
+        ok = d2 < c2
+        ok[:, 0] = False  # :252, idx > len(r_walls)
+        dist = np.where(ok, dist, np.inf).astype(dtype)
+        k = np.argmin(dist, axis=1)
+        rows = np.arange(len(r_walls))
+        with np.errstate(invalid="ignore"):
+            nw_walls = dr[rows, k] / (dist[rows, k] + eps)[:, None]
+        nw = np.zeros_like(r)
+        nw[is_w] = nw_walls.astype(dtype)
+        return nw
+
+    return nw_fn
 
 
 def make_case(
@@ -397,7 +436,19 @@ def make_case(
 
     state = bc_fn(state)  # case_setup.py:202
 
+    # case_setup.py:209-218: recompute the wall normals every step when a wall moves
+    nw_fn, nw_spec = None, None
+    if is_nw and (tag == MOVING_WALL).any():
+        nw_fn = make_nw_fn(state, dx, n_walls, offset_vec, box, wall_part_fn, dtype)
+        # the same three inputs in the form the CUDA engine takes (sphb200_engine_set_wall_layer)
+        nw_spec = dict(
+            layer=(wall_part_fn(dx / 5, 1).astype(dtype)
+                   - (np.asarray(offset_vec) / n_walls / 5).astype(dtype)).astype(np.float32),
+            offset=np.asarray(offset_vec, dtype=np.float32),
+            cutoff=dx * n_walls * 2.0**0.5 * 1.01)
+
     return Setup(
+        nw_fn=nw_fn, nw_spec=nw_spec,
         name=case, dim=dim, dx=dx, dt=dt, dtype=dtype, box_size=box, state=state, eos=eos,
         c_ref=c_ref, p_ref=p_ref, p_bg=p_bg, g_ext_fn=g_ext_fn, bc_fn=bc_fn,
         displacement_fn=displacement_fn, shift_fn=shift_fn, solver=solver, kernel=kernel,

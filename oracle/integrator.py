@@ -51,7 +51,8 @@ def simulate(case, n_steps, dtype=None, faithful_nl=False, fast_segment_sum=Fals
         fast_segment_sum=fast_segment_sum,
     )
     nfn = make_neighbors_fn(setup.box_size, solver._kernel_fn.cutoff, faithful=faithful_nl)
-    advance = si_euler(setup.tvf, solver.forward, setup.shift_fn, setup.bc_fn, None)
+    advance = si_euler(setup.tvf, solver.forward, setup.shift_fn, setup.bc_fn,
+                       getattr(setup, "nw_fn", None))
     state = {k: np.array(v, copy=True) for k, v in setup.state.items()}
     for step in range(n_steps):
         state, _ = advance(setup.dt, state, nfn)

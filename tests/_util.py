@@ -15,7 +15,9 @@ between the reference's own float32 and float64 runs, so the tolerance is
     |a - b| <= RTOL * max|b| + NOISE * floor(field)
 
 with floor(p) = p_ref, floor(dudt) = p_ref / (rho_ref dx),
-floor(dvdt) = |p_fn(0)| / (rho_ref dx), floor(drhodt) = rho_ref c_ref / dx * 1e-2,
+floor(dvdt) = |p_fn(0)| / (rho_ref dx), floor(drhodt) = rho_ref c_ref / dx * 5e-2
+(the continuity sum divides the velocity noise by dx; calibrated on the reference's own
+float32 vs float64 runs, tests/test_reference_pins.py),
 and `drift_ok` additionally checks that the engine is not further from the
 float64 oracle than the float32 oracle is (times a small factor).
 """
@@ -39,7 +41,7 @@ def floors(setup):
         "p": setup.p_ref if setup.solver != "RIE" else 100 * setup.u_ref**2 * rho0,
         "dudt": setup.p_ref / (rho0 * dx),
         "dvdt": p_bg_tvf / (rho0 * dx),
-        "drhodt": rho0 * setup.c_ref / dx * 1e-2,
+        "drhodt": rho0 * setup.c_ref / dx * 5e-2,
         "dTdt": 1e-2 / dx,
         # one step of the acceleration floor: u += dt dudt, r += dt v
         "u": setup.dt * acc,

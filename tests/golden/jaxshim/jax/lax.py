@@ -6,7 +6,16 @@ from ._core import T, to_dtype
 
 
 def stop_gradient(x):
-    return tree_util.tree_map(lambda t: t.detach() if isinstance(t, _torch.Tensor) else t, x)
+    # like every lax primitive, stop_gradient turns a Python scalar into a (weakly typed)
+    # array of the default dtype: jax_md's `cutoff ** 2` (jax_md/partition.py:820-821) is
+    # therefore evaluated in float32 when x64 is off, not in Python double precision
+    def one(t):
+        if isinstance(t, _torch.Tensor):
+            return t.detach()
+        if isinstance(t, (float, int)) and not isinstance(t, bool):
+            return T(t)
+        return t
+    return tree_util.tree_map(one, x)
 
 
 def iota(dtype, size):
