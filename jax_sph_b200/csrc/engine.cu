@@ -155,7 +155,7 @@ void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nran
     g.T[a] = t;
   }
   while (g.T[1] * g.T[2] > MAX_RUNS) (g.T[2] > 1 ? g.T[2] : g.T[1])--;
-  int t0 = c.tile[0] > 0 ? c.tile[0] : (int)floor(0.86 * tpb / (pop * g.T[1] * g.T[2]) + 0.5);
+  int t0 = c.tile[0] > 0 ? c.tile[0] : (int)floor(0.93 * tpb / (pop * g.T[1] * g.T[2]) + 0.5);
   if (t0 < 1) t0 = 1;
   if (t0 > g.n[0]) t0 = g.n[0];
   // MAX_SOFF bound on staged (row, cell) entries

@@ -28,6 +28,8 @@ constexpr int MAX_RUNS = 16;     // T[1]*T[2] upper bound
 constexpr int MAX_SOFF = 1023;   // staged (row, cell) entries upper bound
 constexpr int SWEEP_CHUNK = 16;  // phase-1 candidates between list-room checks
 constexpr int SWEEP_MAXT = 512;  // largest block size the kernels are compiled for
+constexpr int LS = SWEEP_MAXT;   // row stride of the per-thread lists: a compile-time constant, so
+                                 // that the append in the phase-1 loop is one immediate add
 
 struct SweepDims {
   int cap;   // staged particles per block
@@ -55,7 +57,8 @@ struct NList {
 enum { LIST_NONE = 0, LIST_BUILD = 1, LIST_CONSUME = 2 };
 
 __host__ __device__ inline size_t sweep_smem_bytes(int sb, int cap, int lcap, int tpb) {
-  return (size_t)sb * cap + (size_t)lcap * tpb * 2 + (MAX_SOFF + 1 + 2 * MAX_RUNS + 2) * 4;
+  (void)tpb;
+  return (size_t)sb * cap + (size_t)lcap * LS * 2 + (MAX_SOFF + 1 + 2 * MAX_RUNS + 2) * 4;
 }
 
 // unwrapped (global) cell index u in [-n, 2n)  ->  periodic image count / wrapped index
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = TPB >> 5;
   float4* sq = reinterpret_cast<float4*>(smem_raw);
   unsigned short* list = reinterpret_cast<unsigned short*>(smem_raw + (size_t)sd.sb * sd.cap);
-  int* soff = reinterpret_cast<int*>(list + (size_t)sd.lcap * TPB);
+  int* soff = reinterpret_cast<int*>(list + (size_t)sd.lcap * LS);
   int* own_off = soff + (MAX_SOFF + 1);
   int* own_start = own_off + (MAX_RUNS + 1);
 
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
             const int want = rem > 0 ? min(rem, SWEEP_CHUNK) : 0;
             if (__any_sync(FULL_MASK, want > sd.lcap - cnt)) break;  // flush first
             const int e = j + want;
-            unsigned short* lp = list + cnt * TPB + tid;
+            int lo = cnt * LS + tid;  // tid < LS: lo / LS is the entry count at any time
 #pragma unroll 4
             for (; j < e; ++j) {
               const float4 pj = sq[j];
@@ -362,17 +365,17 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
                 d2 += dz * dz;
               }
               if (d2 < g.c2_hi) {
-                *lp = (unsigned short)j;
-                lp += TPB;
-                ++cnt;
+                list[lo] = (unsigned short)j;
+                lo += LS;
               }
             }
+            cnt = lo / LS;
           }
           // ---------------- phase 2: real neighbours, exact arithmetic ----------------
           int m = carry;
 #pragma unroll 1
           for (int k = carry; k < cnt; ++k) {
-            const int jn = list[k * TPB + tid];
+            const int jn = list[k * LS + tid];
             const float4 pj = sq[jn];
             float dr[3];
             if (interior) pair_disp<DIM, true>(g, ri, pj, dr);
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
             // ulp inside), so such a pair contributes nothing either way.
             if (!(d2 < g.c2)) continue;
             if (LM == LIST_BUILD && nl_build) {  // keep the survivor, compacted in place (m <= k)
-              list[m * TPB + tid] = (unsigned short)jn;
+              list[m * LS + tid] = (unsigned short)jn;
               ++m;
             }
             P::pair(c, ex, own, acc, sq, sd.cap, jn, pj, dr, d2);
@@ -398,10 +401,10 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
             int w = 0;
             for (; m - w >= 8; w += 8) {
               uint4 v;
-              v.x = (unsigned)col[(w + 0) * TPB] | ((unsigned)col[(w + 1) * TPB] << 16);
-              v.y = (unsigned)col[(w + 2) * TPB] | ((unsigned)col[(w + 3) * TPB] << 16);
-              v.z = (unsigned)col[(w + 4) * TPB] | ((unsigned)col[(w + 5) * TPB] << 16);
-              v.w = (unsigned)col[(w + 6) * TPB] | ((unsigned)col[(w + 7) * TPB] << 16);
+              v.x = (unsigned)col[(w + 0) * LS] | ((unsigned)col[(w + 1) * LS] << 16);
+              v.y = (unsigned)col[(w + 2) * LS] | ((unsigned)col[(w + 3) * LS] << 16);
+              v.z = (unsigned)col[(w + 4) * LS] | ((unsigned)col[(w + 5) * LS] << 16);
+              v.w = (unsigned)col[(w + 6) * LS] | ((unsigned)col[(w + 7) * LS] << 16);
               if (gk + 8 <= nl.lmax)
                 *reinterpret_cast<uint4*>(nl.list + (size_t)p * nl.lmax + gk) = v;
               else
@@ -410,7 +413,7 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
             }
             const int r = m - w;
             if (w > 0)
-              for (int i = 0; i < r; ++i) col[i * TPB] = col[(w + i) * TPB];
+              for (int i = 0; i < r; ++i) col[i * LS] = col[(w + i) * LS];
             carry = r;
             cnt = r;
           } else {
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
             const unsigned short* col = list + tid;
             unsigned e8[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) e8[i] = i < carry ? (unsigned)col[i * TPB] : 0u;
+            for (int i = 0; i < 8; ++i) e8[i] = i < carry ? (unsigned)col[i * LS] : 0u;
             if (gk + 8 <= nl.lmax)
               *reinterpret_cast<uint4*>(nl.list + (size_t)p * nl.lmax + gk) =
                   make_uint4(e8[0] | (e8[1] << 16), e8[2] | (e8[3] << 16), e8[4] | (e8[5] << 16),
