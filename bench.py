@@ -61,6 +61,46 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def roofline_of(acc, dim, n, edges, peaks, which):
+    """`roofline` object: the DOMINANT kernel of the step (largest CUDA-event time) against
+    the HBM roofline as the contract asks, with its FP32 figure (the sweeps are issue-bound,
+    DESIGN.md section 3) and the same numbers for the other sweep under `kernels`."""
+    names = {"density": "k_sweep<PhysDensity, LIST_BUILD> (density sweep + neighbour-list builder)",
+             "force": "k_sweep<PhysForce, LIST_CONSUME> (force sweep)"}
+    per = {}
+    for k in ("density", "force"):
+        ms = acc.get(k, 0.0)
+        if not ms:
+            continue
+        gbs = BYTES[dim][k] * n / (ms * 1e-3) / 1e9
+        tf = FLOPS_EDGE[dim][k] * edges * n / (ms * 1e-3) / 1e12
+        per[k] = {"kernel": names[k], "ms": ms, "achieved": gbs, "frac": gbs / peaks["hbm_gbs"],
+                  "traffic": ncu_traffic(k),
+                  "fp32": {"achieved_tflops": tf, "peak_tflops_nominal": FP32_PEAK_TFLOPS,
+                           "frac": tf / FP32_PEAK_TFLOPS}}
+    if not per:
+        return {"kernel": None, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": None, "traffic": None, "passes_ms": acc}
+    top = max(per, key=lambda k: per[k]["ms"])
+    c_ms = acc.get("cells", 0.0)
+    roof = {
+        "kernel": per[top]["kernel"], "bound": "hbm", "achieved": per[top]["achieved"],
+        "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": which, "frac": per[top]["frac"],
+        "traffic": per[top]["traffic"], "ms": per[top]["ms"],
+        "note": "the sweeps are bound by FP32/ALU issue and shared-memory wavefronts, not by HBM "
+                "(20 flop per algorithmic byte, ridge at 11): see fp32 and DESIGN.md section 3; "
+                "the HBM-bound passes are under cells",
+        "fp32": per[top]["fp32"], "kernels": per,
+        "cells": {"kernel": "k_hash + scan + k_scatter_src + k_reorder (integrate, sort, reorder)",
+                  "ms": c_ms,
+                  "achieved": BYTES[dim]["cells"] * n / (c_ms * 1e-3) / 1e9 if c_ms else None,
+                  "frac": BYTES[dim]["cells"] * n / (c_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]
+                  if c_ms else None},
+        "passes_ms": acc,
+    }
+    return roof
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -187,8 +227,12 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner through C stdio on fd 1 when the communicator is
+        # created (eagerly, with device_id): keep stdout for the one JSON line
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        return run_slab(args, world, rank, local)
+        return run_slab(args, world, rank, local, saved_stdout)
 
     state, meta = lattice_state(args.workload, args.nx)
     n = len(state["r"])
@@ -238,17 +282,19 @@ def run_ours(args):
             acc[k] = acc.get(k, 0.0) + v / args.steps
     eng.profile(False)
 
-    # end to end through the host-buffer API: H2D state, advance, D2H state, every step
+    # end to end through the host-buffer API, every step: Engine.advance_host = H2D of the state
+    # entries this solver variant reads, advance, D2H of the entries it writes (the others pass
+    # through advance() untouched and stay the caller's arrays, as in the reference)
     out = eng.download(host=True)
     host_in = {k: out[k] for k in out}
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    bytes_in = sum(v.numel() * v.element_size() for v in host_in.values())
+    read, written = eng.live_fields()
+    bytes_in = sum(host_in[k].numel() * host_in[k].element_size() for k in read)
+    bytes_out = sum(host_in[k].numel() * host_in[k].element_size() for k in written)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.upload(host_in)
-        eng.step(meta["dt"], 1)
-        eng.download(out=host_in)  # synchronises the stream
+        host_in = eng.advance_host(meta["dt"], host_in)  # download synchronises the stream
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -262,21 +308,7 @@ def run_ours(args):
     per_step_ms = ms / args.steps
     value = world * n * args.steps / (ms * 1e-3)
     edges = 93 if dim == 3 else 25  # directed in-range edges per lattice particle incl. self
-    f_ms = acc.get("force", 0.0)
-    f_bytes = BYTES[dim]["force"] * n
-    f_flops = FLOPS_EDGE[dim]["force"] * edges * n
-    roof = {
-        "kernel": "k_sweep<PhysForce> (force sweep)", "bound": "hbm",
-        "achieved": f_bytes / (f_ms * 1e-3) / 1e9 if f_ms else None,
-        "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": which,
-        "frac": (f_bytes / (f_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if f_ms else None,
-        "traffic": ncu_traffic("force"), "ms": f_ms,
-        "note": "bound by shared-memory wavefronts and FP32/ALU issue, not by HBM: see fp32",
-        "fp32": {"achieved_tflops": f_flops / (f_ms * 1e-3) / 1e12 if f_ms else None,
-                 "peak_tflops_nominal": FP32_PEAK_TFLOPS,
-                 "frac": (f_flops / (f_ms * 1e-3) / 1e12) / FP32_PEAK_TFLOPS if f_ms else None},
-        "passes_ms": acc,
-    }
+    roof = roofline_of(acc, dim, n, edges, peaks, which)
     cpu = cpu_baseline(args, bounded=True)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -288,15 +320,17 @@ def run_ours(args):
                    "l2_policy": "state (>1.8 GB) larger than L2", "plan": eng.plan()},
         "clocks": clocks, "gpu_launches": int(launches), "device_error_word": err,
         "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": UNIT,
-                "h2d_bytes_per_step": int(bytes_in), "d2h_bytes_per_step": int(bytes_in),
+                "h2d_bytes_per_step": int(bytes_in), "d2h_bytes_per_step": int(bytes_out),
                 "steps": e2e_steps,
-                "what": "Engine.upload(pinned host state) + step + download(host) every step"},
+                "what": "Engine.advance_host(dt, pinned host state) every step: H2D of the "
+                        f"entries advance() reads ({','.join(read)}), one step, D2H of the "
+                        f"entries it writes ({','.join(written)})"},
         "roofline": roof, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
 
 
-def run_slab(args, world, rank, local):
+def run_slab(args, world, rank, local, saved_stdout):
     """N > 1: the SAME box (strong scaling) cut into `world` slabs along the last axis, one
     rank per GPU, halo exchange + particle migration every step over NCCL (slab.py)."""
     import torch
@@ -305,9 +339,6 @@ def run_slab(args, world, rank, local):
     from jax_sph_b200 import SlabEngine, make_config
     from jax_sph_b200.slab import layer_of
 
-    # NCCL prints its version banner on fd 1: keep stdout for the one JSON line
-    saved_stdout = os.dup(1)
-    os.dup2(2, 1)
     meta = lattice_meta(args.workload, args.nx)
     dim, nx = meta["dim"], args.nx
     n_total = nx**dim
@@ -390,27 +421,22 @@ def run_slab(args, world, rank, local):
     barrier()
     dist.destroy_process_group()
     sys.stdout.flush()
+    try:  # flush C stdio (the NCCL banner) while fd 1 still points at stderr
+        import ctypes
+
+        ctypes.CDLL(None).fflush(None)
+    except Exception:
+        pass
     os.dup2(saved_stdout, 1)
 
     if rank != 0:
         return
     peaks, which = measured_peaks()
     edges = 93 if dim == 3 else 25
-    f_ms = acc.get("force", 0.0)
     n_loc = counts["own"]
-    f_bytes = BYTES[dim]["force"] * n_loc
-    f_flops = FLOPS_EDGE[dim]["force"] * edges * n_loc
-    roof = {
-        "kernel": "k_sweep<PhysForce> (force sweep), rank 0's slab", "bound": "hbm",
-        "achieved": f_bytes / (f_ms * 1e-3) / 1e9 if f_ms else None,
-        "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": which,
-        "frac": (f_bytes / (f_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if f_ms else None,
-        "traffic": None, "ms": f_ms, "note": "FP32-issue bound, not HBM bound: see fp32",
-        "fp32": {"achieved_tflops": f_flops / (f_ms * 1e-3) / 1e12 if f_ms else None,
-                 "peak_tflops_nominal": FP32_PEAK_TFLOPS,
-                 "frac": (f_flops / (f_ms * 1e-3) / 1e12) / FP32_PEAK_TFLOPS if f_ms else None},
-        "passes_ms": acc,
-    }
+    roof = roofline_of(acc, dim, n_loc, edges, peaks, which)  # rank 0's slab
+    roof["kernel"] = str(roof["kernel"]) + ", rank 0's slab"
+    roof["traffic"] = None  # the ncu capture is of the single-GPU launch
     line = {
         "metric": METRIC, "value": n_total * args.steps / (ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -263,6 +263,43 @@ class Engine:
             torch.cuda.current_stream().synchronize()
         return out
 
+    def live_fields(self):
+        """(read, written): the state entries one `advance(dt, state, neighbors)`
+        (jax_sph/integrator.py:22-56 + jax_sph/solver.py:705-949) of THIS solver variant reads
+        and the ones it changes.  Everything else passes through the reference's advance()
+        untouched (`v` is overwritten before it is read, integrator.py:27; `p` is recomputed
+        from rho, solver.py:801, and only the Riemann continuity equation reads the incoming
+        one, :773-791; `drhodt` is an output of the evolution variants only; T / dTdt / kappa /
+        Cp matter with heat conduction only, :832-849; `nw` with free-slip or Riemann walls)."""
+        f = self.cfg.flags
+        rie = self.cfg.solver == _lib.SOLVER["RIE"]
+        evol, heat = bool(f & _lib.F_RHO_EVOL), bool(f & _lib.F_HEAT)
+        has_nw = rie or bool(f & _lib.F_FREE_SLIP)
+        read = ["r", "u", "dudt", "dvdt", "tag", "mass", "eta", "rho"]
+        read += ["p"] if (rie and evol) else []
+        read += ["T", "dTdt", "kappa", "Cp"] if heat else []
+        read += ["nw"] if has_nw else []
+        written = ["r", "u", "v", "dudt", "dvdt", "rho", "p"]
+        written += ["drhodt"] if evol else []
+        written += ["T", "dTdt"] if heat else []
+        written += ["nw"] if (has_nw and getattr(self.cfg, "wall_layer", None)) else []
+        return tuple(read), tuple(written)
+
+    def advance_host(self, dt: float, state: Dict, out: Optional[Dict] = None):
+        """`advance(dt, state, neighbors)` on HOST buffers, the call a reference user makes with
+        host-resident state: copies host->device the entries this variant reads, runs one
+        step, copies device->host the entries it writes (into `out` when given, else into
+        `state`'s own arrays) and returns the full state dict -- the untouched entries are the
+        caller's arrays, exactly what the reference's advance() returns for them."""
+        read, written = self.live_fields()
+        self.upload({k: state[k] for k in read})
+        self.step(dt, 1)
+        dst = out if out is not None else state
+        self.download(out={k: dst[k] for k in written})
+        res = dict(state)
+        res.update({k: dst[k] for k in written})
+        return res
+
     def error(self) -> int:
         code = C.c_uint32()
         _lib.check(self.lib.sphb200_engine_error(self._h, C.byref(code), _stream_ptr()))

@@ -2,6 +2,7 @@
 
     python tests/golden/make_reference_golden.py            # all cases, both dtypes
     python tests/golden/make_reference_golden.py --only tgv2d_sph
+    python tests/golden/make_reference_golden.py --long     # 200-step trajectories
 
 jax / jaxlib cannot be installed in the build container (no network, not in the
 wheelhouse), so the reference package under /root/reference is imported as it
@@ -84,6 +85,31 @@ CASES = {
 }
 
 
+# north_star: "tolerance-matched 200-step trajectories for every listed case".  The same cases at
+# sizes the stand-in steps through in minutes; only state0 and the final state are stored
+# (tests/golden/ref200_<case>.npz).
+LONG_STEPS = 200
+LONG_CASES = {
+    "tgv2d_sph": (["config=cases/tgv.yaml", "solver.name=SPH", "solver.tvf=0.0", "case.dx=0.04",
+                   "case.r0_noise_factor=0.25"],
+                  dict(case="tgv", dim=2, dx=0.04)),
+    "tgv2d_tvf": (["config=cases/tgv.yaml", "solver.tvf=1.0", "case.dx=0.04",
+                   "case.r0_noise_factor=0.25"],
+                  dict(case="tgv", dim=2, dx=0.04, tvf=1.0)),
+    "tgv2d_rie": (["config=cases/tgv.yaml", "solver.name=RIE", "solver.density_evolution=True",
+                   "case.dx=0.04", "case.r0_noise_factor=0.25"],
+                  dict(case="tgv", dim=2, dx=0.04, solver="RIE", density_evolution=True)),
+    "tgv3d_tvf": (["config=cases/tgv.yaml", "case.dim=3", "case.dx=0.6283185307179586",
+                   "case.viscosity=0.02", "solver.tvf=1.0", "case.r0_noise_factor=0.25"],
+                  dict(case="tgv", dim=3, dx=0.6283185307179586, tvf=1.0, viscosity=0.02)),
+    "db2d": (["config=cases/db.yaml", "case.dx=0.08", "solver.dt=null"],
+             dict(case="db", dim=2, dx=0.08)),
+    "ht2d": (["config=cases/ht.yaml", "case.dx=0.04"], dict(case="ht", dim=2, dx=0.04)),
+    "cf2d": (["config=cases/cf.yaml", "case.dx=0.05", "solver.dt=null"],
+             dict(case="cf", dim=2, dx=0.05)),
+}
+
+
 def canonical_pairs(idx, n):
     """(2, E) padded edge list -> sorted int64 keys sender * n + receiver (padding dropped)."""
     recv, send = np.asarray(idx[0], dtype=np.int64), np.asarray(idx[1], dtype=np.int64)
@@ -105,7 +131,7 @@ def unpack_pairs(counts, recv):
     return send * n + recv.astype(np.int64)
 
 
-def run_case(name, x64):
+def run_case(name, x64, long=False):
     """Executed in a child process: one case, one dtype, through the reference's own code."""
     sys.path.insert(0, os.path.join(HERE, "jaxshim"))
     sys.path.insert(0, REF)
@@ -123,7 +149,8 @@ def run_case(name, x64):
     from jax_sph.solver import WCSPH
     from jax_sph.utils import Tag
 
-    cli, _ = CASES[name]
+    cli, _ = (LONG_CASES if long else CASES)[name]
+    nsteps = LONG_STEPS if long else NSTEPS
     cli_args = OmegaConf.from_dotlist(cli + ["dtype=" + ("float64" if x64 else "float32")])
     cfg = refmain.load_embedded_configs(cli_args)
 
@@ -167,9 +194,13 @@ def run_case(name, x64):
     state0 = {k: np.array(v) for k, v in state.items()}
     _state, _nbrs = advance(0.0, state0, neighbors)
     assert not bool(_nbrs.did_buffer_overflow)
-    snap("forward", _state)
+    if not long:
+        snap("forward", _state)
+    else:
+        # simulate.py:110-111 discards this call: the loop starts from the initial state
+        del out[f"pairs_{tag}_counts"], out[f"pairs_{tag}_recv"]
     # simulate.py:114-131 without IO
-    for step in range(NSTEPS):
+    for step in range(nsteps):
         state_, neighbors_ = advance(cfg.solver.dt, state, neighbors)
         if bool(neighbors_.did_buffer_overflow):
             neighbors = neighbor_fn.allocate(state["r"], num_particles=num_particles)
@@ -177,8 +208,9 @@ def run_case(name, x64):
         else:
             state, neighbors = state_, neighbors_
     snap("advance", state)
-    keys = canonical_pairs(np.array(neighbors.idx), n)
-    out[f"pairs_end_{tag}_counts"], out[f"pairs_end_{tag}_recv"] = pack_pairs(keys, n)
+    if not long:
+        keys = canonical_pairs(np.array(neighbors.idx), n)
+        out[f"pairs_end_{tag}_counts"], out[f"pairs_end_{tag}_recv"] = pack_pairs(keys, n)
 
     meta = dict(
         dt=float(cfg.solver.dt), dx=float(cfg.case.dx), dim=int(cfg.case.dim),
@@ -187,32 +219,34 @@ def run_case(name, x64):
         solver=str(cfg.solver.name), tvf=float(cfg.solver.tvf), kernel=str(cfg.kernel.name),
         h_factor=float(cfg.kernel.h_factor), cutoff=float(solver._kernel_fn.cutoff),
         p_ref=float(getattr(eos_fn, "p_ref", 0.0)), p_bg=float(eos_fn.p_bg),
-        eos=type(eos_fn).__name__, nsteps=NSTEPS, n=n, pbc=[bool(b) for b in cfg.case.pbc],
+        eos=type(eos_fn).__name__, nsteps=nsteps, n=n, pbc=[bool(b) for b in cfg.case.pbc],
         cli=cli)
     out[f"meta_{tag}"] = np.array(json.dumps(meta))
-    np.savez(os.path.join(HERE, f"_tmp_{name}_{tag}.npz"), **out)
+    np.savez(os.path.join(HERE, f"_tmp_{'long_' if long else ''}{name}_{tag}.npz"), **out)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", nargs="*")
     ap.add_argument("--child", nargs=2, metavar=("CASE", "X64"))
+    ap.add_argument("--long", action="store_true", help="the 200-step trajectories (ref200_*.npz)")
     a = ap.parse_args()
     if a.child:
-        run_case(a.child[0], int(a.child[1]))
+        run_case(a.child[0], int(a.child[1]), long=a.long)
         return
-    for name, (cli, kw) in CASES.items():
+    for name, (cli, kw) in (LONG_CASES if a.long else CASES).items():
         if a.only and name not in a.only:
             continue
         merged = {"make_case_kwargs": np.array(json.dumps(kw))}
         for x64 in (0, 1):
             subprocess.run([sys.executable, "-W", "ignore", os.path.abspath(__file__), "--child",
-                            name, str(x64)], check=True, stdout=subprocess.DEVNULL)
-            tmp = os.path.join(HERE, f"_tmp_{name}_{'f64' if x64 else 'f32'}.npz")
+                            name, str(x64)] + (["--long"] if a.long else []), check=True,
+                           stdout=subprocess.DEVNULL)
+            tmp = os.path.join(HERE, f"_tmp_{'long_' if a.long else ''}{name}_{'f64' if x64 else 'f32'}.npz")
             with np.load(tmp) as z:
                 merged.update({k: z[k] for k in z.files})
             os.remove(tmp)
-        path = os.path.join(HERE, f"ref_{name}.npz")
+        path = os.path.join(HERE, f"{'ref200' if a.long else 'ref'}_{name}.npz")
         np.savez_compressed(path, **merged)
         print(name, int(json.loads(str(merged["meta_f32"]))["n"]), "particles ->",
               os.path.getsize(path) // 1024, "KiB", flush=True)

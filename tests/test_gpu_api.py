@@ -178,3 +178,37 @@ def test_error_behaviour():
     eng.step(0.0, 1, integrate=False)
     assert eng.error() & _lib.ERR_NONFINITE
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(case="tgv", dim=3, dx=2 * np.pi / 12, tvf=1.0, viscosity=0.02),
+    dict(case="tgv", dim=2, dx=0.04, solver="RIE", density_evolution=True),
+    dict(case="db", dim=2, dx=0.05),
+    dict(case="ht", dim=2, dx=0.04),
+    dict(case="cf", dim=2, dx=0.05, free_slip=True),
+])
+def test_advance_host_moves_only_live_fields(kw):
+    """Engine.advance_host copies only what this solver variant reads / writes and still returns
+    what the full upload + step + download path returns, bit for bit; the entries advance()
+    never touches come back as the caller's own arrays with their original content."""
+    from jax_sph_b200 import Engine, config_from_setup
+
+    setup = _case(**kw)
+    n = len(setup.state["r"])
+    full = Engine(config_from_setup(setup), n)
+    full.upload(setup.state)
+    full.step(setup.dt, 3)
+    want = {k: v.numpy() for k, v in full.download(host=True).items()}
+    eng = Engine(config_from_setup(setup), n)
+    read, written = eng.live_fields()
+    assert set(written) <= set(want) and "v" not in read and "drhodt" not in read
+    state = {k: np.ascontiguousarray(v.copy()) for k, v in setup.state.items()}
+    orig = {k: v.copy() for k, v in state.items()}
+    for _ in range(3):
+        state = eng.advance_host(setup.dt, state)
+    assert eng.error() == 0
+    for k in want:
+        if k in written:
+            assert np.array_equal(state[k], want[k]), f"{k} differs from the full-copy path"
+        else:
+            assert np.array_equal(state[k], orig[k]) and np.array_equal(want[k], orig[k]), k

@@ -112,3 +112,38 @@ def test_advance_20_steps_matches_reference(name):
         # 20 steps let the per-step float32 noise accumulate: allow sqrt(20) ~ 5 units
         assert_close(k, g, z[f"advance_f32_{k}"], setup, factor=5.0, what=f"{name} advance")
         drift_ok(k, g, z[f"advance_f32_{k}"], z[f"advance_f64_{k}"], setup, factor=3.0)
+
+
+# ---- 200-step trajectories (north_star: "tolerance-matched 200-step trajectories") ----------
+LONG_NAMES = sorted(os.path.basename(p)[7:-4] for p in glob.glob(os.path.join(GOLDEN, "ref200_*.npz")))
+
+
+def test_long_goldens_present():
+    assert len(LONG_NAMES) >= 6
+
+
+@pytest.mark.parametrize("name", LONG_NAMES)
+def test_200_step_trajectory_matches_reference(name):
+    """The loop of simulate.py:114-131 for 200 steps from the reference's state0: engine vs the
+    reference's float32 run (15 tolerance units: per-step float32 noise accumulates) and the
+    drift bound against its float64 run."""
+    from oracle import cases
+
+    z = np.load(os.path.join(GOLDEN, f"ref200_{name}.npz"))
+    kw = json.loads(str(z["make_case_kwargs"]))
+    meta = json.loads(str(z["meta_f32"]))
+    setup = cases.make_case(dtype=np.float32, **kw)
+    setup.state = {k: np.array(z[f"state0_f32_{k}"]) for k in setup.state}
+    eng = _engine(setup)
+    eng.upload(setup.state)
+    eng.step(meta["dt"], meta["nsteps"])
+    got = eng.download(host=True)
+    assert eng.error() == 0
+    for k in ("r", "u", "v", "rho", "T"):
+        g = got[k].numpy()
+        assert_close(k, g, z[f"advance_f32_{k}"], setup, factor=15.0, what=f"{name} 200 steps")
+        drift_ok(k, g, z[f"advance_f32_{k}"], z[f"advance_f64_{k}"], setup, factor=3.0)
+    ek = 0.5 * float((got["mass"].numpy()[:, None] * got["u"].numpy() ** 2).sum())
+    ref_u, ref_m = z["advance_f32_u"], z["state0_f32_mass"]
+    ek_ref = 0.5 * float((ref_m[:, None] * ref_u ** 2).sum())
+    assert abs(ek - ek_ref) <= 2e-5 * max(ek_ref, 1e-30), "kinetic energy after 200 steps"

@@ -177,3 +177,39 @@ def test_forward_and_advance_f32_match_reference(name):
     adv, _ = oracle_run(setup, meta["nsteps"], meta["dt"])
     for k in OUT_KEYS:
         assert_close(k, adv[k], z[f"advance_f32_{k}"], setup, factor=5.0, what=f"{name} advance")
+
+
+# ---- 200-step trajectories (north_star: "tolerance-matched 200-step trajectories") ----------
+LONG_NAMES = sorted(os.path.basename(p)[7:-4] for p in glob.glob(os.path.join(GOLDEN, "ref200_*.npz")))
+
+
+def load_long(name, tag):
+    from oracle import cases
+
+    z = np.load(os.path.join(GOLDEN, f"ref200_{name}.npz"))
+    kw = json.loads(str(z["make_case_kwargs"]))
+    meta = json.loads(str(z[f"meta_{tag}"]))
+    setup = cases.make_case(dtype=np.float32 if tag == "f32" else np.float64, **kw)
+    setup.state = {k: np.array(z[f"state0_{tag}_{k}"]) for k in setup.state}
+    assert abs(setup.dt - meta["dt"]) <= 1e-12 * meta["dt"]
+    return z, setup, meta
+
+
+def test_long_goldens_present():
+    assert len(LONG_NAMES) >= 6, "tests/golden/ref200_*.npz missing (make_reference_golden.py --long)"
+
+
+@pytest.mark.parametrize("name", LONG_NAMES)
+def test_200_steps_match_reference(name):
+    """Oracle vs the reference's own 200-step run: float64 to 1e-6 relative (rounding-order
+    differences grow along the trajectory), float32 within the trajectory tolerance."""
+    z, setup, meta = load_long(name, "f64")
+    adv, _ = oracle_run(setup, meta["nsteps"], meta["dt"])
+    for k in OUT_KEYS:
+        ref = z[f"advance_f64_{k}"]
+        tol = 1e-6 * max(float(np.abs(ref).max()), 1e-300) + 1e-6 * assert_tol(k, ref, setup)
+        assert max_err(adv[k], ref) <= tol, (name, k, max_err(adv[k], ref), tol)
+    z, setup, meta = load_long(name, "f32")
+    adv, _ = oracle_run(setup, meta["nsteps"], meta["dt"])
+    for k in ("r", "u", "v", "rho", "T"):
+        assert_close(k, adv[k], z[f"advance_f32_{k}"], setup, factor=15.0, what=f"{name} 200 steps")
