@@ -189,8 +189,10 @@ def test_error_behaviour():
 ])
 def test_advance_host_moves_only_live_fields(kw):
     """Engine.advance_host copies only what this solver variant reads / writes and still returns
-    what the full upload + step + download path returns, bit for bit; the entries advance()
-    never touches come back as the caller's own arrays with their original content."""
+    what the full upload + step + download path returns (to rounding: re-uploading every step
+    restarts the in-cell order from the original particle order, so sums run in another
+    order than in the resident run); the entries advance() never touches come back as the
+    caller's own arrays with their original content."""
     from jax_sph_b200 import Engine, config_from_setup
 
     setup = _case(**kw)
@@ -209,6 +211,6 @@ def test_advance_host_moves_only_live_fields(kw):
     assert eng.error() == 0
     for k in want:
         if k in written:
-            assert np.array_equal(state[k], want[k]), f"{k} differs from the full-copy path"
+            assert_close(k, state[k], want[k], setup, factor=3.0, what="advance_host vs resident")
         else:
             assert np.array_equal(state[k], orig[k]) and np.array_equal(want[k], orig[k]), k
