@@ -46,7 +46,7 @@ extern "C" {
 #define SPHB200_ENOMEM (-2)   /* cudaMalloc failed or workspace too small      */
 #define SPHB200_ECUDA (-3)    /* a CUDA runtime call failed                    */
 #define SPHB200_EDTYPE (-4)   /* unsupported dtype (float64)                   */
-#define SPHB200_EUNSUP (-5)   /* unsupported variant (e.g. DELTA solver)       */
+#define SPHB200_EUNSUP (-5)   /* unsupported variant (e.g. DELTA + density evolution) */
 #define SPHB200_ENODEV (-6)   /* no CUDA device / not an sm_100 device         */
 
 /* ---- device-side error word (sphb200_engine_error) ---------------------- */
@@ -61,7 +61,10 @@ extern "C" {
                                                  * halo width in one step                        */
 
 /* ---- enums --------------------------------------------------------------- */
-enum { SPHB200_SOLVER_SPH = 0, SPHB200_SOLVER_RIE = 1 };  /* solver.py:639-640 (DELTA: unsupported) */
+/* solver.py:666-686.  DELTA (Marrone et al. 2011): the velocity diffusion of
+ * acceleration_delta_fn (solver.py:259-313) is built; its density diffusion
+ * (rho_evol_fn_delta, solver.py:33-105: SPHB200_F_RHO_EVOL with DELTA) returns SPHB200_EUNSUP. */
+enum { SPHB200_SOLVER_SPH = 0, SPHB200_SOLVER_RIE = 1, SPHB200_SOLVER_DELTA = 2 };
 enum { SPHB200_KERNEL_QSK = 0, SPHB200_KERNEL_WC2K = 1 }; /* kernel.py:51-103                        */
 enum { SPHB200_EOS_TAIT = 0, SPHB200_EOS_RIEMANN = 1 };   /* eos.py:20-57                            */
 
@@ -146,7 +149,9 @@ typedef struct sphb200_config {
   int32_t stage_cap;   /* staged particles per block (0 = auto)      */
   int32_t nl_cap;      /* row length of the per-step neighbour lists shared by the sweeps of one
                         * forward(): 0 = auto (1.3 x the uniform-fluid neighbour count), -1 = off */
-  int32_t reserved[7];
+  float diff_delta;    /* DELTA: solver.py:623, defaults.py:97 */
+  float diff_alpha;    /* DELTA: solver.py:624, defaults.py:99 */
+  int32_t reserved[5];
 } sphb200_config;
 
 /* State dict of the reference (solver.py:930-947), device or host pointers.

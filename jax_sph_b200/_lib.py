@@ -16,7 +16,7 @@ ABI_VERSION = 2
 OK, EINVAL, ENOMEM, ECUDA, EDTYPE, EUNSUP, ENODEV = 0, -1, -2, -3, -4, -5, -6
 ERR_NEIGHBOR_OVERFLOW, ERR_CELL_OVERFLOW, ERR_STAGE_OVERFLOW, ERR_NONFINITE = 1, 2, 4, 8
 ERR_OUTSIDE_BOX = 16
-SOLVER = {"SPH": 0, "RIE": 1}
+SOLVER = {"SPH": 0, "RIE": 1, "DELTA": 2}
 KERNEL = {"QSK": 0, "WC2K": 1}
 EOS_TAIT, EOS_RIEMANN = 0, 1
 F_BC_TRICK, F_RHO_EVOL, F_RHO_RENORM, F_FREE_SLIP, F_HEAT = 1, 2, 4, 8, 16
@@ -50,7 +50,7 @@ class Config(C.Structure):
         ("bc_outflow_on", C.c_int32), ("bc_outflow_x", C.c_float),
         ("cell_sub", C.c_int32 * 3), ("tile", C.c_int32 * 3), ("threads", C.c_int32),
         ("list_cap", C.c_int32), ("stage_cap", C.c_int32), ("nl_cap", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("diff_delta", C.c_float), ("diff_alpha", C.c_float), ("reserved", C.c_int32 * 5),
     ]
 
 

@@ -65,6 +65,7 @@ struct Consts {
   int use_lim;
   float av_coef;    // f32(alpha * h_ab * c_ab), solver.py:413-415
   float av_eps;     // f32(0.01 * h_ab^2)
+  float delta_coef; // DELTA: f32(alpha * support * c_ref * rho_ref), solver.py:303-308
   int g_mode, g_axis;
   float g[3], g_lo, g_hi;
   sphb200_bc_rule bc[4];
@@ -83,6 +84,7 @@ struct Extra {
   int wallT;       // RIE & bc_trick & heat: Shepard wall temperature
   int finalT;      // this sweep integrates T (no wall sweep follows)
   int heat, av, bc_on, free_slip, bc_trick;
+  int delta;       // DELTA solver: velocity diffusion term of acceleration_delta_fn
   // neighbour-list materialiser
   int* nl_counts;
   const int* nl_offsets;

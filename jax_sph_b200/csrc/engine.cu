@@ -105,7 +105,11 @@ int validate(const sphb200_config* c, int64_t n) {
   if (!c || c->struct_size != sizeof(sphb200_config)) return SPHB200_EINVAL;
   if (c->dim != 2 && c->dim != 3) return SPHB200_EINVAL;
   if (n <= 0 || n > 2000000000LL) return SPHB200_EINVAL;
-  if (c->solver != SPHB200_SOLVER_SPH && c->solver != SPHB200_SOLVER_RIE) return SPHB200_EUNSUP;
+  if (c->solver != SPHB200_SOLVER_SPH && c->solver != SPHB200_SOLVER_RIE &&
+      c->solver != SPHB200_SOLVER_DELTA)
+    return SPHB200_EUNSUP;
+  // DELTA: the density diffusion of rho_evol_fn_delta (solver.py:33-105) is not built yet
+  if (c->solver == SPHB200_SOLVER_DELTA && (c->flags & SPHB200_F_RHO_EVOL)) return SPHB200_EUNSUP;
   if (c->kernel != SPHB200_KERNEL_QSK && c->kernel != SPHB200_KERNEL_WC2K) return SPHB200_EUNSUP;
   if (c->eos != SPHB200_EOS_TAIT && c->eos != SPHB200_EOS_RIEMANN) return SPHB200_EINVAL;
   if (!(c->h > 0) || !(c->dx > 0)) return SPHB200_EINVAL;
@@ -232,6 +236,7 @@ void plan_consts(const sphb200_config& c, Consts& k) {
   k.eta_lim = (float)c.eta_limiter;
   k.av_coef = (float)(c.artificial_alpha * c.dx * 10.0);  // h_ab = dx, c_ab = 10 * 1.0
   k.av_eps = (float)(0.01 * c.dx * c.dx);
+  k.delta_coef = (float)c.diff_alpha * (float)c.h * (float)c.c_ref * (float)c.rho_ref;
   k.g_mode = c.g_mode; k.g_axis = c.g_axis;
   for (int a = 0; a < 3; ++a) k.g[a] = (float)c.g[a];
   k.g_lo = (float)c.g_lo; k.g_hi = (float)c.g_hi;
@@ -518,7 +523,9 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
   const int fq_ut = (rie && e->has_ut) ? force_nq++ : -1;
   // the two headline SPH variants stage a compact record (phys.cuh, PhysForce)
   const bool av_on = c.artificial_alpha != 0.0;
-  const int force_feat = (heat || av_on) ? FORCE_GENERIC : (v_is_u ? FORCE_PLAIN : FORCE_TVF);
+  const bool delta_on = c.solver == SPHB200_SOLVER_DELTA;
+  const int force_feat =
+      (heat || av_on || delta_on) ? FORCE_GENERIC : (v_is_u ? FORCE_PLAIN : FORCE_TVF);
   const int force_sb = (rie || force_feat == FORCE_GENERIC) ? 16 * force_nq
                                                            : (force_feat == FORCE_TVF ? 52 : 40);
   const SweepPlan planF =
@@ -606,6 +613,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
     ex.sb = force_sb;
     ex.heat = heat;
     ex.av = av_on;
+    ex.delta = delta_on;
     ex.bc_on = (flags & SPHB200_STEP_BC) && bc_table_on(c);
     ex.free_slip = free_slip;
     ex.bc_trick = bc_trick;

@@ -474,6 +474,16 @@ struct PhysForce {
       }
     }
     if (FEAT == FORCE_GENERIC) {
+      if (SOLVER == SPHB200_SOLVER_SPH && ex.delta) {  // acceleration_delta_fn, solver.py:297-311
+        if (tag_j == SPHB200_TAG_FLUID) {
+          const float du[3] = {o.u[0] - uj[0], o.u[1] - uj[1], o.u[2] - uj[2]};
+          const float idd = frcp((dist + c.eps) * (dist + c.eps));
+          const float pi_ij = dot3(du, dr, DIM) * idd;  // dot(u_j - u_i, -r_ij) / (d + EPS)^2
+          const float s = fdiv(m_j, rho_j) * pi_ij * c.delta_coef * fdiv(1.0f, o.rho);
+#pragma unroll
+          for (int k = 0; k < DIM; ++k) a.av[k] += s * (gw * (dr[k] * id));
+        }
+      }
       if (ex.av) {  // :404-428
         if (o.tag == SPHB200_TAG_FLUID && tag_j == SPHB200_TAG_FLUID) {
           const float rho_ab = (o.rho + rho_j) / 2.0f;
@@ -509,7 +519,7 @@ struct PhysForce {
     for (int k = 0; k < 3; ++k) {
       float s = a.a[k];
       if (SOLVER == SPHB200_SOLVER_SPH) s = fmaf(ai, o.u[k], s);
-      if (FEAT == FORCE_GENERIC && ex.av) s = s + a.av[k];  // :925-928
+      if (FEAT == FORCE_GENERIC && (ex.av || ex.delta)) s = s + a.av[k];  // :925-928 / :311
       du[k] = s + g[k];                                     // :936
       dv[k] = a.tv[k] * c.p_bg_tvf;                         // :205-211
     }

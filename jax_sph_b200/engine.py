@@ -22,12 +22,12 @@ def make_config(
     is_bc_trick=False, is_rho_evol=False, is_rho_renorm=False, is_free_slip=False,
     is_heat_conduction=False, artificial_alpha=0.0, g_ext_spec=None, bc_table=None,
     cell_sub=None, tile=None, threads=0, list_cap=0, stage_cap=0, nl_cap=0, g_ext_array=False,
-    r_cutoff=0.0, wall_layer=None,
+    r_cutoff=0.0, wall_layer=None, diff_delta=0.1, diff_alpha=0.01,
 ):
     """Build a `sphb200_config` from the WCSPH constructor arguments
     (jax_sph/solver.py:616-637) plus the table forms of the case callables."""
     if solver not in _lib.SOLVER:
-        raise _lib.Sphb200Error(f"solver {solver!r} is not supported (SPH, RIE)")
+        raise _lib.Sphb200Error(f"solver {solver!r} is not supported (SPH, RIE, DELTA)")
     if kernel not in _lib.KERNEL:
         raise _lib.Sphb200Error(f"kernel {kernel!r} is not supported (QSK, WC2K)")
     cfg = _lib.default_config()
@@ -110,6 +110,7 @@ def make_config(
     cfg.threads, cfg.list_cap, cfg.stage_cap = threads, list_cap, stage_cap
     cfg.nl_cap = nl_cap
     cfg.r_cutoff = float(r_cutoff)
+    cfg.diff_delta, cfg.diff_alpha = float(diff_delta), float(diff_alpha)
     # not part of the C struct: Engine / SlabEngine hand it to sphb200_engine_set_wall_layer
     cfg.wall_layer = wall_layer
     return cfg
@@ -127,7 +128,9 @@ def config_from_setup(setup, **tuning):
         is_rho_evol=setup.density_evolution, is_rho_renorm=setup.density_renormalize,
         is_free_slip=setup.free_slip, is_heat_conduction=setup.heat_conduction,
         artificial_alpha=setup.artificial_alpha, g_ext_spec=setup.g_ext_spec,
-        bc_table=setup.bc_table, wall_layer=getattr(setup, "nw_spec", None), **tuning)
+        bc_table=setup.bc_table, wall_layer=getattr(setup, "nw_spec", None),
+        diff_delta=getattr(setup, "diff_delta", 0.1), diff_alpha=getattr(setup, "diff_alpha", 0.01),
+        **tuning)
 
 
 def set_wall_layer(lib, handle, dim, layer, offset, cutoff):

@@ -36,8 +36,11 @@ class WCSPH:
         is_rho_renorm: bool = False, is_heat_conduction: bool = False,
         g_ext_spec=None, bc_table=None, tvf: float = 0.0,
     ):
-        if solver == "DELTA":
-            raise _lib.Sphb200Error("solver 'DELTA' is outside the hot-path scope (SPHB200_EUNSUP)")
+        if solver == "DELTA" and is_rho_evol:
+            # rho_evol_fn_delta (jax_sph/solver.py:33-105) is not built yet; DELTA with density
+            # summation (what the reference's own tests run, tests/test_pf2d.py:107) is
+            raise _lib.Sphb200Error(
+                "solver 'DELTA' with density_evolution is not supported (SPHB200_EUNSUP)")
         side = getattr(displacement_fn, "side", None)
         if side is None:
             raise _lib.Sphb200Error("displacement_fn must come from jax_sph_b200.space.periodic")
@@ -53,7 +56,7 @@ class WCSPH:
             eta_limiter=eta_limiter, is_bc_trick=is_bc_trick, is_rho_evol=is_rho_evol,
             is_rho_renorm=is_rho_renorm, is_free_slip=is_free_slip,
             is_heat_conduction=is_heat_conduction, artificial_alpha=artificial_alpha,
-            bc_table=bc_table)
+            bc_table=bc_table, diff_delta=diff_delta, diff_alpha=diff_alpha)
         self._box = np.asarray(side, dtype=np.float64)
         # g_ext: table form when given (runs inside the kernels), else g_ext_fn(r) per call
         self._g_spec = g_ext_spec

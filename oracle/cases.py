@@ -100,6 +100,8 @@ class Setup:
     bc_table: dict = field(default_factory=dict)
     g_ext_spec: dict = field(default_factory=dict)
     nw_fn: Optional[Callable] = None  # case_setup.py:218
+    diff_delta: float = 0.1  # defaults.py:97
+    diff_alpha: float = 0.01  # defaults.py:99
     nw_spec: Optional[dict] = None
 
 
@@ -197,6 +199,9 @@ def make_case(
     Cp_ref: Optional[float] = None,
     T_ref: float = 1.0,
     box_override=None,
+    gamma: float = 1.0,
+    diff_delta: float = 0.1,
+    diff_alpha: float = 0.01,
 ) -> Setup:
     """Build a Setup the way ``SimulationSetup.initialize`` does for ``cases/<case>.yaml``."""
     dtype = np.dtype(dtype)
@@ -233,7 +238,7 @@ def make_case(
     Cp_ref = pick(Cp_ref, "Cp_ref", 0.0)
     sp = dict(yaml.get("special", {}))
     sp.update(special or {})
-    rho_ref, gamma, c_ref_factor = 1.0, 1.0, 10.0
+    rho_ref, c_ref_factor = 1.0, 10.0  # defaults.py:119-127 (gamma: eos.gamma)
     eps = float(np.finfo(dtype).eps)
 
     c_ref = c_ref_factor * u_ref  # case_setup.py:83
@@ -448,7 +453,7 @@ def make_case(
             cutoff=dx * n_walls * 2.0**0.5 * 1.01)
 
     return Setup(
-        nw_fn=nw_fn, nw_spec=nw_spec,
+        nw_fn=nw_fn, nw_spec=nw_spec, diff_delta=diff_delta, diff_alpha=diff_alpha,
         name=case, dim=dim, dx=dx, dt=dt, dtype=dtype, box_size=box, state=state, eos=eos,
         c_ref=c_ref, p_ref=p_ref, p_bg=p_bg, g_ext_fn=g_ext_fn, bc_fn=bc_fn,
         displacement_fn=displacement_fn, shift_fn=shift_fn, solver=solver, kernel=kernel,

@@ -45,7 +45,7 @@ def simulate(case, n_steps, dtype=None, faithful_nl=False, fast_segment_sum=Fals
     setup = case
     solver = WCSPH(
         setup.displacement_fn, setup.eos, setup.g_ext_fn, setup.dx, setup.dim, setup.dt,
-        setup.c_ref, setup.eta_limiter, 0.0, 0.0, setup.solver, setup.kernel, setup.h_factor,
+        setup.c_ref, setup.eta_limiter, setup.diff_delta, setup.diff_alpha, setup.solver, setup.kernel, setup.h_factor,
         setup.is_bc_trick, setup.density_evolution, setup.artificial_alpha, setup.free_slip,
         setup.density_renormalize, setup.heat_conduction, dtype=setup.dtype,
         fast_segment_sum=fast_segment_sum,

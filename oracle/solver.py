@@ -1,7 +1,8 @@
 """WCSPH.forward on an explicit edge list (oracle; test infrastructure only).
 
-Line-by-line NumPy restatement of jax_sph/solver.py for solver in {SPH, RIE}
-(DELTA is outside the hot-path scope):
+Line-by-line NumPy restatement of jax_sph/solver.py for solver in {SPH, RIE, DELTA}
+(DELTA is SURVEY.md section 8 row a19, "next": rho_evol_fn_delta solver.py:33-105,
+acceleration_delta_fn solver.py:259-313):
 
 * EPS                      solver.py:21
 * rho_evol_fn              solver.py:24-30
@@ -68,8 +69,11 @@ class WCSPH:
         dtype=np.float64,
         fast_segment_sum=False,
     ):
-        if solver not in ("SPH", "RIE"):
-            raise NotImplementedError("oracle covers SPH and RIE (hot-path scope)")
+        if solver not in ("SPH", "RIE", "DELTA"):
+            raise NotImplementedError("oracle covers SPH, RIE and DELTA")
+        self.diff_delta = diff_delta
+        self.diff_alpha = diff_alpha
+        self.h = h_fac * dx  # `support` of the DELTA wrappers (solver.py:678, :683)
         self.displacement_fn = displacement_fn
         self.eos = eos
         self.g_ext_fn = g_ext_fn
@@ -164,6 +168,12 @@ class WCSPH:
             rho = rho + dt_s * drhodt  # :29
             if self.is_rho_renorm:
                 rho = self._rho_renorm(rho, mass, i_s, j_s, w_dist, N)
+        elif self.is_rho_evol and self.solver == "DELTA":  # :757-771
+            rho, drhodt = self._rho_evol_delta(
+                rho, mass, dr_i_j, dist, u, i_s, j_s, dt_s, N, fluid_mask[j_s]
+            )
+            if self.is_rho_renorm:
+                rho = self._rho_renorm(rho, mass, i_s, j_s, w_dist, N)
         elif self.is_rho_evol and self.solver == "RIE":
             temp = self._rho_evol_riemann(
                 e_s, rho[i_s], rho[j_s], mass[j_s], u[i_s], u[j_s], p[i_s], p[j_s],
@@ -181,7 +191,7 @@ class WCSPH:
         background_pressure_tvf = self.eos.p_fn(np.zeros_like(p))  # :802
 
         # wall boundary conditions :806-828
-        if self.is_bc_trick and self.solver == "SPH":
+        if self.is_bc_trick and self.solver in ("SPH", "DELTA"):  # :806
             p, rho, u, v, temperature = self._gwbc(
                 temperature, rho, tag, u, v, p, g_ext, i_s, j_s, w_dist, dr_i_j, nw, N
             )
@@ -217,6 +227,13 @@ class WCSPH:
             out = self._acceleration_standard(
                 dr_i_j, dist, rho[i_s], rho[j_s], u[i_s], u[j_s], v[i_s], v[j_s],
                 mass[i_s], mass[j_s], eta[i_s], eta[j_s], p[i_s], p[j_s],
+            )
+        elif self.solver == "DELTA":  # :871-888
+            out = self._acceleration_standard(
+                dr_i_j, dist, rho[i_s], rho[j_s], u[i_s], u[j_s], v[i_s], v[j_s],
+                mass[i_s], mass[j_s], eta[i_s], eta[j_s], p[i_s], p[j_s],
+            ) + self._acceleration_delta_diff(
+                dr_i_j, dist, rho[i_s], rho[j_s], u[i_s], u[j_s], mass[j_s], fluid_mask[j_s]
             )
         else:
             out = self._acceleration_riemann(
@@ -352,6 +369,49 @@ class WCSPH:
         ) / t(2)
         u_ij = u_i - u_j
         return c[:, None] * (-p_ij[:, None] * r_ij + A_r + eta_ij[:, None] * u_ij)
+
+    def _acceleration_delta_diff(self, r_ij, d_ij, rho_i, rho_j, u_i, u_j, m_j, fluidmask_j):
+        """The Delta-SPH velocity diffusion of acceleration_delta_fn, solver.py:297-311 (a_eq_8,
+        :280-295, is the standard acceleration)."""
+        t = self.dtype.type
+        EPS = self.EPS
+        e_ij = r_ij / (d_ij + EPS)[:, None]
+        kernel_grad = self._kernel_fn.grad_w(d_ij)[:, None] * e_ij
+        V_j = m_j / rho_j
+        pi_ij = self._dot(u_j - u_i, -r_ij) / (d_ij + EPS) ** 2
+        rho_ref = t(self.eos.rho_ref)
+        # V_j * pi_ij * kernel_grad * alpha * support * c_ref * rho_ref / rho_i * fluidmask_j
+        out = (V_j * pi_ij)[:, None] * kernel_grad
+        out = out * t(self.diff_alpha) * t(self.h) * t(self.c_ref) * rho_ref
+        return out / rho_i[:, None] * fluidmask_j[:, None]
+
+    def _rho_evol_delta(self, rho, mass, r_ij, d_ij, u, i_s, j_s, dt, N, fluidmask_j):
+        """rho_evol_fn_delta, solver.py:36-103 (Marrone et al. 2011)."""
+        t = self.dtype.type
+        EPS = self.EPS
+        seg = self._seg
+        d = r_ij.shape[1]
+        e_ab = r_ij / (d_ij + EPS)[:, None]  # :42
+        kernel_grad = self._kernel_fn.grad_w(d_ij)[:, None] * e_ab  # :43
+        V_i, V_j = (mass / rho)[i_s], (mass / rho)[j_s]  # :44-45
+        # :52-57  L = inv(sum tensordot(-r_ab, kernel_grad * V_b))
+        temp = (-r_ij)[:, :, None] * (kernel_grad * V_j[:, None])[:, None, :]
+        L_mati = np.linalg.inv(seg(temp.reshape(len(i_s), d * d), i_s, N).reshape(N, d, d))
+        temp = (r_ij)[:, :, None] * (kernel_grad * V_i[:, None])[:, None, :]
+        L_matj = np.linalg.inv(seg(temp.reshape(len(i_s), d * d), j_s, N).reshape(N, d, d))
+        # :59-65
+        gi = np.einsum("eab,eb->ea", L_mati[i_s], kernel_grad * V_j[:, None])
+        rho_grad_term_i = seg((rho[j_s] - rho[i_s])[:, None] * gi, i_s, N)
+        gj = np.einsum("eab,eb->ea", L_matj[j_s], -kernel_grad * V_i[:, None])
+        rho_grad_term_j = seg((rho[i_s] - rho[j_s])[:, None] * gj, i_s, N)
+        # :67-93
+        rho_term = (t(2) * (rho[j_s] - rho[i_s]))[:, None] * (-r_ij) / ((d_ij + EPS) ** 2)[:, None]
+        psi_ij = rho_term - rho_grad_term_i[i_s] - rho_grad_term_j[j_s]
+        diff_term = seg(self._dot(psi_ij, kernel_grad) * V_j * fluidmask_j, i_s, N)
+        # :95-103
+        cont = seg(self._dot(u[i_s] - u[j_s], kernel_grad) * V_j, i_s, N)
+        drhodt = rho * cont + t(self.c_ref) * t(self.diff_delta) * t(self.h) * diff_term
+        return (rho + dt * drhodt).astype(self.dtype), drhodt.astype(self.dtype)
 
     def _acceleration_tvf(self, r_ij, d_ij, rho_i, rho_j, m_i, m_j, p_bg_i):
         """solver.py:202-211."""

@@ -82,6 +82,19 @@ CASES = {
                       dict(case="cf", dim=2, dx=0.04, free_slip=True)),
     "pf2d": (["config=cases/pf.yaml", "case.dx=0.04", "solver.dt=null"],
              dict(case="pf", dim=2, dx=0.04)),
+    # Delta-SPH: reference tests/test_pf2d.py:107, test_cf2d.py:111
+    # (summation density + velocity diffusion) and validation/db2d.sh:8 (density diffusion,
+    # gamma = 7)
+    "pf2d_delta": (["config=cases/pf.yaml", "case.dx=0.04", "solver.dt=null", "solver.name=DELTA"],
+                   dict(case="pf", dim=2, dx=0.04, solver="DELTA")),
+    "cf2d_delta": (["config=cases/cf.yaml", "case.dx=0.04", "solver.dt=null", "solver.name=DELTA"],
+                   dict(case="cf", dim=2, dx=0.04, solver="DELTA")),
+    "db2d_delta": (["config=cases/db.yaml", "case.dx=0.05", "solver.dt=null", "solver.name=DELTA",
+                    "eos.gamma=7.0", "solver.artificial_alpha=0.0"],
+                   dict(case="db", dim=2, dx=0.05, solver="DELTA", gamma=7.0, artificial_alpha=0.0)),
+    "tgv2d_delta": (["config=cases/tgv.yaml", "case.dx=0.04", "solver.name=DELTA",
+                     "solver.density_evolution=True", "case.r0_noise_factor=0.25"],
+                    dict(case="tgv", dim=2, dx=0.04, solver="DELTA", density_evolution=True)),
 }
 
 

@@ -34,7 +34,7 @@ def test_reference_call_sequence_with_mirrors():
     eos_obj = eos.TaitEoS(setup.p_ref, setup.rho_ref, setup.p_bg, setup.gamma)
     model = solver.WCSPH(
         displacement_fn, eos_obj, setup.g_ext_fn, setup.dx, setup.dim, setup.dt, setup.c_ref,
-        setup.eta_limiter, 0.0, 0.0, setup.solver, setup.kernel, setup.h_factor,
+        setup.eta_limiter, setup.diff_delta, setup.diff_alpha, setup.solver, setup.kernel, setup.h_factor,
         setup.is_bc_trick, setup.density_evolution, setup.artificial_alpha, setup.free_slip,
         setup.density_renormalize, setup.heat_conduction, g_ext_spec=setup.g_ext_spec)
     forward = model.forward_wrapper()
@@ -163,7 +163,9 @@ def test_error_behaviour():
     with pytest.raises(_lib.Sphb200Error, match="elements"):
         eng.upload({"r": setup.state["r"][:-1]})
     with pytest.raises(_lib.Sphb200Error, match="not supported"):
-        make_config(2, [1.0, 1.0], 0.05, 0.0, solver="DELTA")
+        make_config(2, [1.0, 1.0], 0.05, 0.0, solver="GSPH")
+    with pytest.raises(_lib.Sphb200Error, match="unsupported"):  # DELTA density diffusion
+        Engine(make_config(2, [1.0, 1.0], 0.05, 0.0, solver="DELTA", is_rho_evol=True), 16)
     with pytest.raises(_lib.Sphb200Error, match="not supported"):
         make_config(2, [1.0, 1.0], 0.05, 0.0, kernel="GK")
     # positions outside the periodic box are reported through the device error word

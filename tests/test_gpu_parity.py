@@ -130,7 +130,7 @@ def test_variants_vs_oracle(kw):
 
     setup = cases.make_case(dtype=np.float32, **kw)
     solver = WCSPH(setup.displacement_fn, setup.eos, setup.g_ext_fn, setup.dx, setup.dim, setup.dt,
-                   setup.c_ref, setup.eta_limiter, 0.0, 0.0, setup.solver, setup.kernel,
+                   setup.c_ref, setup.eta_limiter, setup.diff_delta, setup.diff_alpha, setup.solver, setup.kernel,
                    setup.h_factor, setup.is_bc_trick, setup.density_evolution,
                    setup.artificial_alpha, setup.free_slip, setup.density_renormalize,
                    setup.heat_conduction, dtype=np.float32)
