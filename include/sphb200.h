@@ -61,9 +61,10 @@ extern "C" {
                                                  * halo width in one step                        */
 
 /* ---- enums --------------------------------------------------------------- */
-/* solver.py:666-686.  DELTA (Marrone et al. 2011): the velocity diffusion of
- * acceleration_delta_fn (solver.py:259-313) is built; its density diffusion
- * (rho_evol_fn_delta, solver.py:33-105: SPHB200_F_RHO_EVOL with DELTA) returns SPHB200_EUNSUP. */
+/* solver.py:666-686.  DELTA (Marrone et al. 2011): velocity diffusion of acceleration_delta_fn
+ * (solver.py:259-313) and, with SPHB200_F_RHO_EVOL, the renormalised density diffusion of
+ * rho_evol_fn_delta (solver.py:33-105); the latter on the single-GPU engine only
+ * (sphb200_slab_create returns SPHB200_EUNSUP for it). */
 enum { SPHB200_SOLVER_SPH = 0, SPHB200_SOLVER_RIE = 1, SPHB200_SOLVER_DELTA = 2 };
 enum { SPHB200_KERNEL_QSK = 0, SPHB200_KERNEL_WC2K = 1 }; /* kernel.py:51-103                        */
 enum { SPHB200_EOS_TAIT = 0, SPHB200_EOS_RIEMANN = 1 };   /* eos.py:20-57                            */

@@ -23,6 +23,7 @@ constexpr unsigned FULL_MASK = 0xffffffffu;
 //   ge = (g_ext xyz, 0)  [only g_mode == ARRAY]             id = original particle index
 struct Frame {
   float4 *pt, *um, *vv, *st, *du, *dv, *nw, *ut, *ge;
+  float4 *dl, *dg;  // Delta-SPH density diffusion: renormalisation matrix rows [3n], gradient terms [2n]
   float2 *kc;
   int *id;
 };
@@ -66,6 +67,7 @@ struct Consts {
   float av_coef;    // f32(alpha * h_ab * c_ab), solver.py:413-415
   float av_eps;     // f32(0.01 * h_ab^2)
   float delta_coef; // DELTA: f32(alpha * support * c_ref * rho_ref), solver.py:303-308
+  float delta_rho;  // DELTA: f32(c_ref * delta * support), solver.py:100
   int g_mode, g_axis;
   float g[3], g_lo, g_hi;
   sphb200_bc_rule bc[4];

@@ -108,8 +108,7 @@ int validate(const sphb200_config* c, int64_t n) {
   if (c->solver != SPHB200_SOLVER_SPH && c->solver != SPHB200_SOLVER_RIE &&
       c->solver != SPHB200_SOLVER_DELTA)
     return SPHB200_EUNSUP;
-  // DELTA: the density diffusion of rho_evol_fn_delta (solver.py:33-105) is not built yet
-  if (c->solver == SPHB200_SOLVER_DELTA && (c->flags & SPHB200_F_RHO_EVOL)) return SPHB200_EUNSUP;
+
   if (c->kernel != SPHB200_KERNEL_QSK && c->kernel != SPHB200_KERNEL_WC2K) return SPHB200_EUNSUP;
   if (c->eos != SPHB200_EOS_TAIT && c->eos != SPHB200_EOS_RIEMANN) return SPHB200_EINVAL;
   if (!(c->h > 0) || !(c->dx > 0)) return SPHB200_EINVAL;
@@ -237,6 +236,7 @@ void plan_consts(const sphb200_config& c, Consts& k) {
   k.av_coef = (float)(c.artificial_alpha * c.dx * 10.0);  // h_ab = dx, c_ab = 10 * 1.0
   k.av_eps = (float)(0.01 * c.dx * c.dx);
   k.delta_coef = (float)c.diff_alpha * (float)c.h * (float)c.c_ref * (float)c.rho_ref;
+  k.delta_rho = (float)c.c_ref * (float)c.diff_delta * (float)c.h;
   k.g_mode = c.g_mode; k.g_axis = c.g_axis;
   for (int a = 0; a < 3; ++a) k.g[a] = (float)c.g[a];
   k.g_lo = (float)c.g_lo; k.g_hi = (float)c.g_hi;
@@ -256,6 +256,7 @@ struct Layout {
   size_t frame[2][12];
   size_t key, rnk, src, count, start, bsum, maxocc, wallcount, err, stats, nl_counts, ut;
   size_t pl_list, pl_cnt, pl_ok;
+  size_t dl, dg;  // Delta-SPH density diffusion (PhysDelta)
   int pl_lmax;
   size_t dn;
   size_t total;
@@ -298,6 +299,9 @@ void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, Layout& L) {
     L.frame[f][9] = ge ? take((size_t)n * 16) : (size_t)-1;
   }
   L.ut = ut ? take((size_t)n * 16) : (size_t)-1;
+  const bool delta_evol = c.solver == SPHB200_SOLVER_DELTA && (c.flags & SPHB200_F_RHO_EVOL);
+  L.dl = delta_evol ? take((size_t)n * 48) : (size_t)-1;
+  L.dg = delta_evol ? take((size_t)n * 32) : (size_t)-1;
   L.key = take((size_t)n * 4);
   L.rnk = take((size_t)n * 4);
   L.src = take((size_t)n * 4);
@@ -534,8 +538,13 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
   const SweepPlan planD = !evol ? (dens_extras ? e->planW : e->planA) : (!rie ? e->planR : e->planW);
   // neighbour lists: built by the density sweep, consumed by every later sweep of this step
   NList nl{e->pl_list, e->pl_cnt, e->pl_ok, e->pl_lmax, 0};
+  const SweepPlan planG = plan_sweep(e, e->dim == 3 ? 5 : 3, 24);  // PhysDelta<1>
   {
     int mc = planD.cap < planF.cap ? planD.cap : planF.cap;
+    if (delta_on && evol) {
+      if (planG.cap < mc) mc = planG.cap;
+      if (e->planC.cap < mc) mc = e->planC.cap;
+    }
     if (evol && renorm && e->planR.cap < mc) mc = e->planR.cap;
     if (wall_sweep && e->planC.cap < mc) mc = e->planC.cap;
     nl.min_cap = mc;
@@ -561,6 +570,22 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
         DISPATCH_DK(e, CALL);
 #undef CALL
       }
+    } else if (delta_on) {
+      // rho_evol_fn_delta (solver.py:36-103): L matrices (list builder), gradient terms, update
+      ex.nq = 2;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDelta<D, K, 0>, LIST_BUILD>, planD, F, ex, st, nl)
+      DISPATCH_DK(e, CALL);
+#undef CALL
+      if (rc) return rc;
+      ex.nq = e->dim == 3 ? 5 : 3;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDelta<D, K, 1>, LIST_CONSUME>, planG, F, ex, st, nl)
+      DISPATCH_DK(e, CALL);
+#undef CALL
+      if (rc) return rc;
+      ex.nq = 4;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDelta<D, K, 2>, LIST_CONSUME>, e->planC, F, ex, st, nl)
+      DISPATCH_DK(e, CALL);
+#undef CALL
     } else if (!rie) {
       ex.nq = 2;
 #define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_EVOL_SPH>, LIST_BUILD>, planD, F, ex, st, nl)
@@ -771,6 +796,8 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
     F.nw = e->has_nw ? (float4*)(e->arena + L.frame[f][8]) : nullptr;
     F.ge = e->has_ge ? (float4*)(e->arena + L.frame[f][9]) : nullptr;
     F.ut = e->has_ut ? (float4*)(e->arena + L.ut) : nullptr;
+    F.dl = L.dl != (size_t)-1 ? (float4*)(e->arena + L.dl) : nullptr;
+    F.dg = L.dg != (size_t)-1 ? (float4*)(e->arena + L.dg) : nullptr;
   }
   e->key = (int*)(e->arena + L.key);
   e->rnk = (int*)(e->arena + L.rnk);
@@ -1258,6 +1285,8 @@ int sphb200_slab_create(const sphb200_config* cfg, int rank, int nranks, int64_t
   int rc = validate(cfg, 1);
   if (rc) return rc;
   if (!out) return SPHB200_EINVAL;
+  // the Delta-SPH density diffusion needs two more halo refreshes (L, gradient terms): next
+  if (cfg->solver == SPHB200_SOLVER_DELTA && (cfg->flags & SPHB200_F_RHO_EVOL)) return SPHB200_EUNSUP;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SPHB200_ENODEV;
   SlabSpec sp;

@@ -7,6 +7,7 @@
 //   PhysDensity   :750-802  density summation / continuity (SPH) / Riemann continuity,
 //                           EoS; RIE wall helpers u_tilde (:547-552) and heat_bc (:556-565)
 //   PhysRenorm    :167-173  Shepard density renormalisation
+//   PhysDelta     :33-105   Delta-SPH density evolution (renormalised density diffusion)
 //   PhysWall      :450-528  generalized wall boundary condition (SPH)
 //   PhysForce     :221-256 standard acceleration, :199-213 TVF, :316-401 Riemann,
 //                 :404-428 artificial viscosity, :591-610 heat conduction,
@@ -160,6 +161,182 @@ struct PhysDensity {
     if (XTRA && ex.utilde) {
       const float den = a.swf + c.eps;  // :547-552
       f.ut[p] = make_float4(a.su[0] / den, a.su[1] / den, a.su[2] / den, 0.f);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Delta-SPH density evolution, rho_evol_fn_delta (solver.py:36-103, Marrone et al. 2011), as
+// three sweeps over the same neighbour lists:
+//   STEP 0 (list builder)  M_i = sum_j (-r_ij) (x) (grad W_ij V_j),  L_i = inv(M_i)      :52-55
+//   STEP 1                 G_i = sum_j (rho_j - rho_i) L_i (grad W_ij V_j)               :59-62
+//                          H_i = sum_j (rho_i - rho_j) L_j (grad W_ij V_i)               :63-65
+//                          (the reference builds L_matj = inv(sum over senders), which is
+//                          -L_j for the symmetric edge list; the two signs cancel)
+//   STEP 2                 psi_ij = 2 (rho_j - rho_i)(-r_ij)/(d+EPS)^2 - G_i - H_j       :77-79
+//                          drhodt = rho_i sum_j (u_i-u_j).grad W_ij V_j
+//                                   + c_ref delta h sum_j psi_ij.grad W_ij V_j [j fluid]  :80-101
+//                          rho += dt drhodt, p = eos(rho)                                :102, :801
+// All three read the INCOMING rho; only STEP 2 writes (into the other frame's st).
+template <int DIM, int KERN, int STEP>
+struct PhysDelta {
+  static constexpr int MINB = 1;
+  static constexpr bool SENDER_VIEW = false;
+  static constexpr int LQ = DIM == 3 ? 3 : 1;  // quads of one staged L matrix
+  struct Own {
+    float rho, V;
+    float u[3], G[3];
+    float L[9];
+  };
+  struct Acc {
+    float m[9];  // STEP 0: M;  STEP 1: G (0..2), H (3..5);  STEP 2: diff (0), cont (1)
+  };
+  __host__ __device__ static int nq() { return STEP == 0 ? 2 : (STEP == 1 ? 2 + LQ : 4); }
+  __device__ static void stage(const Consts&, const Frame& f, const Extra&, int gp, float4* sq,
+                               int cap, int d) {
+    sq[d] = f.pt[gp];
+    const float4 um = f.um[gp], st = f.st[gp];
+    sq[cap + d] = make_float4(um.w / st.x, st.x, 0.f, 0.f);  // V_j = m_j / rho_j (:44-45), rho_j
+    if (STEP == 1) {
+      if (DIM == 3) {
+        sq[2 * cap + d] = f.dl[3 * gp];
+        sq[3 * cap + d] = f.dl[3 * gp + 1];
+        sq[4 * cap + d] = f.dl[3 * gp + 2];
+      } else {
+        sq[2 * cap + d] = f.dl[3 * gp];
+      }
+    }
+    if (STEP == 2) {
+      sq[2 * cap + d] = um;
+      sq[3 * cap + d] = f.dg[2 * gp + 1];
+    }
+  }
+  __device__ static void load_own(const Consts&, const Frame& f, const Extra&, int p, float4,
+                                  Own& o) {
+    const float4 um = f.um[p], st = f.st[p];
+    o.rho = st.x;
+    o.V = um.w / st.x;
+    o.u[0] = um.x; o.u[1] = um.y; o.u[2] = um.z;
+    if (STEP == 1) {
+      const float4 a = f.dl[3 * p];
+      if (DIM == 3) {
+        const float4 b = f.dl[3 * p + 1], cc = f.dl[3 * p + 2];
+        o.L[0] = a.x; o.L[1] = a.y; o.L[2] = a.z;
+        o.L[3] = b.x; o.L[4] = b.y; o.L[5] = b.z;
+        o.L[6] = cc.x; o.L[7] = cc.y; o.L[8] = cc.z;
+      } else {
+        o.L[0] = a.x; o.L[1] = a.y; o.L[2] = a.z; o.L[3] = a.w;
+      }
+    }
+    if (STEP == 2) {
+      const float4 g = f.dg[2 * p];
+      o.G[0] = g.x; o.G[1] = g.y; o.G[2] = g.z;
+    }
+  }
+  __device__ static bool active(const Consts&, const Own&) { return true; }
+  __device__ static void init(Acc& a) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.m[k] = 0.f;
+  }
+  // y = L x for a row-major DIM x DIM matrix
+  __device__ static void matvec(const float* L, const float (&x)[3], float (&y)[3]) {
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) {
+      float s = L[a * DIM] * x[0] + L[a * DIM + 1] * x[1];
+      if (DIM == 3) s += L[a * DIM + 2] * x[2];
+      y[a] = s;
+    }
+    if (DIM == 2) y[2] = 0.f;
+  }
+  __device__ static void pair(const Consts& c, const Extra&, const Own& o, Acc& a,
+                              const float4* sq, int cap, int j, float4 pj, const float (&dr)[3],
+                              float d2) {
+    const float dist = fsqrt(d2);
+    const float gw = kernel_gw<KERN>(c, dist);
+    const float id = frcp(dist + c.eps);
+    const float4 q1 = sq[cap + j];
+    const float V_j = q1.x, rho_j = q1.y;
+    float kg[3] = {gw * (dr[0] * id), gw * (dr[1] * id), DIM == 3 ? gw * (dr[2] * id) : 0.f};  // :42-43
+    if (STEP == 0) {
+#pragma unroll
+      for (int r = 0; r < DIM; ++r)
+#pragma unroll
+        for (int s = 0; s < DIM; ++s) a.m[r * DIM + s] += (-dr[r]) * (kg[s] * V_j);  // :49-50
+    }
+    if (STEP == 1) {
+      float Lj[9];
+      const float4 l0 = sq[2 * cap + j];
+      if (DIM == 3) {
+        const float4 l1 = sq[3 * cap + j], l2 = sq[4 * cap + j];
+        Lj[0] = l0.x; Lj[1] = l0.y; Lj[2] = l0.z;
+        Lj[3] = l1.x; Lj[4] = l1.y; Lj[5] = l1.z;
+        Lj[6] = l2.x; Lj[7] = l2.y; Lj[8] = l2.z;
+      } else {
+        Lj[0] = l0.x; Lj[1] = l0.y; Lj[2] = l0.z; Lj[3] = l0.w;
+      }
+      const float xj[3] = {kg[0] * V_j, kg[1] * V_j, kg[2] * V_j};
+      const float xi[3] = {kg[0] * o.V, kg[1] * o.V, kg[2] * o.V};
+      float gi[3], hj[3];
+      matvec(o.L, xj, gi);
+      matvec(Lj, xi, hj);
+      const float dji = rho_j - o.rho, dij = o.rho - rho_j;
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) {
+        a.m[k] += dji * gi[k];      // :59-62
+        a.m[3 + k] += dij * hj[k];  // :63-65
+      }
+    }
+    if (STEP == 2) {
+      const float4 uj = sq[2 * cap + j], hj = sq[3 * cap + j];
+      const float idd = frcp((dist + c.eps) * (dist + c.eps));
+      const float two_d = 2.0f * (rho_j - o.rho);
+      const float H[3] = {hj.x, hj.y, hj.z};
+      const float du[3] = {o.u[0] - uj.x, o.u[1] - uj.y, o.u[2] - uj.z};
+      float psi_kg = 0.f, du_kg = 0.f;
+#pragma unroll
+      for (int k = 0; k < DIM; ++k) {
+        const float psi = (two_d * (-dr[k])) * idd - o.G[k] - H[k];  // :77-78
+        psi_kg += psi * kg[k];
+        du_kg += du[k] * kg[k];
+      }
+      const float fm = (__float_as_int(pj.w) == SPHB200_TAG_FLUID) ? 1.0f : 0.0f;
+      a.m[0] += psi_kg * V_j * fm;  // :79
+      a.m[1] += du_kg * V_j;        // :95-98
+    }
+  }
+  __device__ static void finish(const Consts& c, const Frame& f, const Extra& ex, int p,
+                                const Own& o, const Acc& a) {
+    if (STEP == 0) {
+      float L[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const float* m = a.m;
+      if (DIM == 2) {
+        const float idet = 1.0f / (m[0] * m[3] - m[1] * m[2]);
+        L[0] = m[3] * idet; L[1] = -m[1] * idet; L[2] = -m[2] * idet; L[3] = m[0] * idet;
+        f.dl[3 * p] = make_float4(L[0], L[1], L[2], L[3]);
+      } else {
+        const float c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8],
+                    c02 = m[3] * m[7] - m[4] * m[6];
+        const float idet = 1.0f / (m[0] * c00 + m[1] * c01 + m[2] * c02);
+        f.dl[3 * p] = make_float4(c00 * idet, (m[2] * m[7] - m[1] * m[8]) * idet,
+                                  (m[1] * m[5] - m[2] * m[4]) * idet, 0.f);
+        f.dl[3 * p + 1] = make_float4(c01 * idet, (m[0] * m[8] - m[2] * m[6]) * idet,
+                                      (m[2] * m[3] - m[0] * m[5]) * idet, 0.f);
+        f.dl[3 * p + 2] = make_float4(c02 * idet, (m[1] * m[6] - m[0] * m[7]) * idet,
+                                      (m[0] * m[4] - m[1] * m[3]) * idet, 0.f);
+      }
+    }
+    if (STEP == 1) {
+      f.dg[2 * p] = make_float4(a.m[0], a.m[1], a.m[2], 0.f);
+      f.dg[2 * p + 1] = make_float4(a.m[3], a.m[4], a.m[5], 0.f);
+    }
+    if (STEP == 2) {
+      const float4 st = f.st[p];
+      const float drhodt = st.x * a.m[1] + c.delta_rho * a.m[0];  // :99-101
+      const float rho = st.x + c.dt_s * drhodt;                   // :102
+      float T = st.z;
+      if (ex.finalT) T = T + c.dt_s * st.w;  // :834
+      ex.st_out[p] = make_float4(rho, eos_p(c, rho), T, st.w);
+      reinterpret_cast<float*>(&f.du[p])[3] = drhodt;
     }
   }
 };

@@ -36,11 +36,6 @@ class WCSPH:
         is_rho_renorm: bool = False, is_heat_conduction: bool = False,
         g_ext_spec=None, bc_table=None, tvf: float = 0.0,
     ):
-        if solver == "DELTA" and is_rho_evol:
-            # rho_evol_fn_delta (jax_sph/solver.py:33-105) is not built yet; DELTA with density
-            # summation (what the reference's own tests run, tests/test_pf2d.py:107) is
-            raise _lib.Sphb200Error(
-                "solver 'DELTA' with density_evolution is not supported (SPHB200_EUNSUP)")
         side = getattr(displacement_fn, "side", None)
         if side is None:
             raise _lib.Sphb200Error("displacement_fn must come from jax_sph_b200.space.periodic")

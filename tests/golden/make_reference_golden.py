@@ -92,6 +92,11 @@ CASES = {
     "db2d_delta": (["config=cases/db.yaml", "case.dx=0.05", "solver.dt=null", "solver.name=DELTA",
                     "eos.gamma=7.0", "solver.artificial_alpha=0.0"],
                    dict(case="db", dim=2, dx=0.05, solver="DELTA", gamma=7.0, artificial_alpha=0.0)),
+    "tgv3d_delta": (["config=cases/tgv.yaml", "case.dim=3", "case.dx=0.6283185307179586",
+                     "case.viscosity=0.02", "solver.name=DELTA", "solver.density_evolution=True",
+                     "case.r0_noise_factor=0.25"],
+                    dict(case="tgv", dim=3, dx=0.6283185307179586, viscosity=0.02, solver="DELTA",
+                         density_evolution=True)),
     "tgv2d_delta": (["config=cases/tgv.yaml", "case.dx=0.04", "solver.name=DELTA",
                      "solver.density_evolution=True", "case.r0_noise_factor=0.25"],
                     dict(case="tgv", dim=2, dx=0.04, solver="DELTA", density_evolution=True)),

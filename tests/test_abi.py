@@ -70,10 +70,11 @@ def test_argument_validation_is_host_side(lib):
     cfg.dim = 4
     assert so.sphb200_engine_bytes(C.byref(cfg), 10, C.byref(nbytes)) == lib.EINVAL
     cfg = lib.default_config()
-    cfg.solver = 2  # DELTA: velocity diffusion built, density diffusion (RHO_EVOL) not yet
+    cfg.solver = 2  # DELTA
     assert so.sphb200_engine_bytes(C.byref(cfg), 10, C.byref(nbytes)) == 0
-    cfg.flags |= lib.F_RHO_EVOL
-    assert so.sphb200_engine_bytes(C.byref(cfg), 10, C.byref(nbytes)) == lib.EUNSUP
+    plain = nbytes.value
+    cfg.flags |= lib.F_RHO_EVOL  # density diffusion keeps L matrices and gradient terms
+    assert so.sphb200_engine_bytes(C.byref(cfg), 10, C.byref(nbytes)) == 0 and nbytes.value > plain
     cfg = lib.default_config()
     cfg.solver = 3
     assert so.sphb200_engine_bytes(C.byref(cfg), 10, C.byref(nbytes)) == lib.EUNSUP

@@ -122,6 +122,9 @@ def test_200_step_trajectory_vs_oracle(name, kw):
     dict(case="db", dim=2, dx=0.05, density_renormalize=True),
     dict(case="cf", dim=2, dx=0.05, free_slip=True),
     dict(case="tgv", dim=3, dx=2 * np.pi / 12, kernel="WC2K", h_factor=1.3, tvf=1.0),
+    dict(case="tgv", dim=3, dx=2 * np.pi / 12, solver="DELTA", density_evolution=True),  # 3x3 L
+    dict(case="db", dim=2, dx=0.05, solver="DELTA", gamma=7.0, artificial_alpha=0.0,
+         density_renormalize=True),
 ])
 def test_variants_vs_oracle(kw):
     """Variants without a committed golden file: oracle evaluated on the fly."""

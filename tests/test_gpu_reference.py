@@ -47,10 +47,6 @@ def _load(name):
 def _engine(setup, **tuning):
     from jax_sph_b200 import Engine, config_from_setup
 
-    if setup.solver == "DELTA" and setup.density_evolution:
-        pytest.skip("DELTA density diffusion (rho_evol_fn_delta, solver.py:33-105) is the next "
-                    "row to build: the engine returns SPHB200_EUNSUP; the oracle is pinned")
-
     return Engine(config_from_setup(setup, **tuning), len(setup.state["r"]))
 
 
