@@ -66,7 +66,13 @@ extern "C" {
  * rho_evol_fn_delta (solver.py:33-105); the latter on the single-GPU engine only
  * (sphb200_slab_create returns SPHB200_EUNSUP for it). */
 enum { SPHB200_SOLVER_SPH = 0, SPHB200_SOLVER_RIE = 1, SPHB200_SOLVER_DELTA = 2 };
-enum { SPHB200_KERNEL_QSK = 0, SPHB200_KERNEL_WC2K = 1 }; /* kernel.py:51-103                        */
+/* kernel.py: Quintic :51-72, Wendland C2 :75-103 (compile-time specialised sweeps), and
+ * Cubic :26-48, Wendland C4 :106-134, C6 :137-165, Gaussian :168-182, SuperGaussian :185-201
+ * (one run-time-switched instance of every sweep). */
+enum {
+  SPHB200_KERNEL_QSK = 0, SPHB200_KERNEL_WC2K = 1, SPHB200_KERNEL_CSK = 2, SPHB200_KERNEL_WC4K = 3,
+  SPHB200_KERNEL_WC6K = 4, SPHB200_KERNEL_GK = 5, SPHB200_KERNEL_SGK = 6
+};
 enum { SPHB200_EOS_TAIT = 0, SPHB200_EOS_RIEMANN = 1 };   /* eos.py:20-57                            */
 
 /* solver flags (WCSPH ctor booleans, solver.py:616-637) */

@@ -17,7 +17,7 @@ OK, EINVAL, ENOMEM, ECUDA, EDTYPE, EUNSUP, ENODEV = 0, -1, -2, -3, -4, -5, -6
 ERR_NEIGHBOR_OVERFLOW, ERR_CELL_OVERFLOW, ERR_STAGE_OVERFLOW, ERR_NONFINITE = 1, 2, 4, 8
 ERR_OUTSIDE_BOX = 16
 SOLVER = {"SPH": 0, "RIE": 1, "DELTA": 2}
-KERNEL = {"QSK": 0, "WC2K": 1}
+KERNEL = {"QSK": 0, "WC2K": 1, "CSK": 2, "WC4K": 3, "WC6K": 4, "GK": 5, "SGK": 6}
 EOS_TAIT, EOS_RIEMANN = 0, 1
 F_BC_TRICK, F_RHO_EVOL, F_RHO_RENORM, F_FREE_SLIP, F_HEAT = 1, 2, 4, 8, 16
 G_NONE, G_CONST, G_BAND, G_ARRAY = 0, 1, 2, 3

@@ -191,6 +191,50 @@ __device__ __forceinline__ int cell_of(const Grid& g, const float (&r)[3], int (
 // ---------------------------------------------------------------------------
 // Smoothing kernels, evaluated inline (kernel.py:51-103).  x^5 = ((x^2)^2)*x as
 // lax.integer_pow lowers it.
+// Template slot of the run-time-switched kernels (every SPHB200_KERNEL_* other than QSK / WC2K)
+constexpr int KERN_ANY = 7;
+
+// The five kernels outside the headline pair, switched on c.kernel at run time.  which = 0: w,
+// which = 1: d w / d r as jax.grad differentiates the reference expressions (the jnp.where
+// masks of the Cubic / Gaussian kernels carry no gradient; d max(0, x) / dx = [x > 0]).
+__device__ __forceinline__ float kernel_any(const Consts& c, float q, int which) {
+  switch (c.kernel) {
+    case SPHB200_KERNEL_CSK: {  // kernel.py:40-48
+      const float c1 = (1.0f - q >= 0.0f) ? 1.0f : 0.0f;
+      const float c2 = (2.0f - q < 1.0f && 2.0f - q >= 0.0f) ? 1.0f : 0.0f;
+      const float t = 2.0f - q;
+      if (which == 0)
+        return (1.0f - 1.5f * (q * q) * (1.0f - q / 2.0f)) * c1 + (0.25f * ((t * t) * t)) * c2;
+      return (-3.0f * q + 2.25f * (q * q)) * c1 + (-0.75f * (t * t)) * c2;
+    }
+    case SPHB200_KERNEL_WC4K: {  // kernel.py:130-134: q1^6 (35/12 q^2 + 3 q + 1)
+      const float q1 = fmaxf(0.0f, 1.0f - 0.5f * q);
+      const float a2 = q1 * q1, a4 = a2 * a2;
+      const float poly = (35.0f / 12.0f) * (q * q) + 3.0f * q + 1.0f;
+      if (which == 0) return (a2 * a4) * poly;
+      return -3.0f * (q1 * a4) * poly + (a2 * a4) * ((35.0f / 6.0f) * q + 3.0f);
+    }
+    case SPHB200_KERNEL_WC6K: {  // kernel.py:161-165: q1^8 (4 q^3 + 6.25 q^2 + 4 q + 1)
+      const float q1 = fmaxf(0.0f, 1.0f - 0.5f * q);
+      const float a2 = q1 * q1, a4 = a2 * a2, a8 = a4 * a4;
+      const float poly = 4.0f * ((q * q) * q) + 6.25f * (q * q) + 4.0f * q + 1.0f;
+      if (which == 0) return a8 * poly;
+      return -4.0f * ((q1 * a2) * a4) * poly + a8 * (12.0f * (q * q) + 12.5f * q + 4.0f);
+    }
+    case SPHB200_KERNEL_GK: {  // kernel.py:178-182
+      const float m = (3.0f - q >= 0.0f) ? 1.0f : 0.0f;
+      const float e = expf(-(q * q));
+      return which == 0 ? m * e : m * ((-2.0f * q) * e);
+    }
+    default: {  // SPHB200_KERNEL_SGK, kernel.py:197-201
+      const float m = (3.0f - q >= 0.0f) ? 1.0f : 0.0f;
+      const float e = expf(-(q * q));
+      const float a = 0.5f * (float)c.dim + 1.0f;
+      return which == 0 ? m * e * (a - q * q) : m * ((-2.0f * q) * e) * (a + 1.0f - q * q);
+    }
+  }
+}
+
 template <int KERN>
 __device__ __forceinline__ float kernel_w(const Consts& c, float r) {
   float q = r * c.ooh;
@@ -199,10 +243,12 @@ __device__ __forceinline__ float kernel_w(const Consts& c, float r) {
     float a1 = q1 * q1, a2 = q2 * q2, a3 = q3 * q3;
     float p1 = (a1 * a1) * q1, p2 = (a2 * a2) * q2, p3 = (a3 * a3) * q3;
     return c.sigma * ((p3 - 6.0f * p2) + 15.0f * p1);
-  } else {
+  } else if (KERN == SPHB200_KERNEL_WC2K) {
     float q1 = fmaxf(0.0f, 1.0f - 0.5f * q);
     float a = q1 * q1;
     return c.sigma * ((a * a) * (2.0f * q + 1.0f));
+  } else {
+    return c.sigma * kernel_any(c, q, 0);
   }
 }
 
@@ -214,9 +260,11 @@ __device__ __forceinline__ float kernel_gw(const Consts& c, float r) {
     float a1 = q1 * q1, a2 = q2 * q2, a3 = q3 * q3;
     float poly = (-5.0f * (a3 * a3) + 30.0f * (a2 * a2)) - 75.0f * (a1 * a1);
     return c.sigma_ooh * poly;
-  } else {
+  } else if (KERN == SPHB200_KERNEL_WC2K) {
     float q1 = fmaxf(0.0f, 1.0f - 0.5f * q);
     return c.sigma_ooh * ((-5.0f * q) * ((q1 * q1) * q1));
+  } else {
+    return c.sigma_ooh * kernel_any(c, q, 1);
   }
 }
 

@@ -98,7 +98,9 @@ namespace {
 
 double kernel_cutoff(const sphb200_config& c) {
   if (c.r_cutoff > 0.0) return c.r_cutoff;
-  return (c.kernel == SPHB200_KERNEL_QSK ? 3.0 : 2.0) * c.h;
+  const bool wide = c.kernel == SPHB200_KERNEL_QSK || c.kernel == SPHB200_KERNEL_GK ||
+                    c.kernel == SPHB200_KERNEL_SGK;  // kernel.py:56, :172, :190: 3 h, else 2 h
+  return (wide ? 3.0 : 2.0) * c.h;
 }
 
 int validate(const sphb200_config* c, int64_t n) {
@@ -109,7 +111,7 @@ int validate(const sphb200_config* c, int64_t n) {
       c->solver != SPHB200_SOLVER_DELTA)
     return SPHB200_EUNSUP;
 
-  if (c->kernel != SPHB200_KERNEL_QSK && c->kernel != SPHB200_KERNEL_WC2K) return SPHB200_EUNSUP;
+  if (c->kernel < SPHB200_KERNEL_QSK || c->kernel > SPHB200_KERNEL_SGK) return SPHB200_EUNSUP;
   if (c->eos != SPHB200_EOS_TAIT && c->eos != SPHB200_EOS_RIEMANN) return SPHB200_EINVAL;
   if (!(c->h > 0) || !(c->dx > 0)) return SPHB200_EINVAL;
   for (int a = 0; a < c->dim; ++a)
@@ -212,10 +214,15 @@ void plan_consts(const sphb200_config& c, Consts& k) {
   k.eps = 1.1920928955078125e-07f;
   const double ooh = 1.0 / c.h;
   double sigma;
-  if (c.kernel == SPHB200_KERNEL_QSK)
-    sigma = c.dim == 2 ? 7.0 / 478.0 / M_PI * ooh * ooh : 3.0 / 359.0 / M_PI * ooh * ooh * ooh;
-  else
-    sigma = c.dim == 2 ? 7.0 / 4.0 / M_PI * ooh * ooh : 21.0 / 16.0 / M_PI * ooh * ooh * ooh;
+  const double oohd = c.dim == 2 ? ooh * ooh : ooh * ooh * ooh;
+  switch (c.kernel) {  // kernel.py: the _sigma of each class for dim 2 / 3
+    case SPHB200_KERNEL_QSK: sigma = (c.dim == 2 ? 7.0 / 478.0 : 3.0 / 359.0) / M_PI * oohd; break;
+    case SPHB200_KERNEL_WC2K: sigma = (c.dim == 2 ? 7.0 / 4.0 : 21.0 / 16.0) / M_PI * oohd; break;
+    case SPHB200_KERNEL_CSK: sigma = (c.dim == 2 ? 10.0 / 7.0 : 1.0) / M_PI * oohd; break;
+    case SPHB200_KERNEL_WC4K: sigma = (c.dim == 2 ? 9.0 / 4.0 : 495.0 / 256.0) / M_PI * oohd; break;
+    case SPHB200_KERNEL_WC6K: sigma = (c.dim == 2 ? 78.0 / 28.0 : 1365.0 / 512.0) / M_PI * oohd; break;
+    default: sigma = 1.0 / pow(M_PI, c.dim / 2.0) * oohd; break;  // GK, SGK
+  }
   k.ooh = (float)ooh;
   k.sigma = (float)sigma;
   k.sigma_ooh = k.sigma * k.ooh;
@@ -390,10 +397,12 @@ Extra make_extra() {
   do {                                                                             \
     if ((e)->dim == 2) {                                                           \
       if ((e)->cfg.kernel == SPHB200_KERNEL_QSK) { CALL(2, SPHB200_KERNEL_QSK); }  \
-      else { CALL(2, SPHB200_KERNEL_WC2K); }                                       \
+      else if ((e)->cfg.kernel == SPHB200_KERNEL_WC2K) { CALL(2, SPHB200_KERNEL_WC2K); } \
+      else { CALL(2, KERN_ANY); }                                                  \
     } else {                                                                       \
       if ((e)->cfg.kernel == SPHB200_KERNEL_QSK) { CALL(3, SPHB200_KERNEL_QSK); }  \
-      else { CALL(3, SPHB200_KERNEL_WC2K); }                                       \
+      else if ((e)->cfg.kernel == SPHB200_KERNEL_WC2K) { CALL(3, SPHB200_KERNEL_WC2K); } \
+      else { CALL(3, KERN_ANY); }                                                  \
     }                                                                              \
   } while (0)
 

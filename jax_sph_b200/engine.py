@@ -29,7 +29,7 @@ def make_config(
     if solver not in _lib.SOLVER:
         raise _lib.Sphb200Error(f"solver {solver!r} is not supported (SPH, RIE, DELTA)")
     if kernel not in _lib.KERNEL:
-        raise _lib.Sphb200Error(f"kernel {kernel!r} is not supported (QSK, WC2K)")
+        raise _lib.Sphb200Error(f"kernel {kernel!r} is not supported {tuple(_lib.KERNEL)}")
     cfg = _lib.default_config()
     cfg.dim = dim
     cfg.solver = _lib.SOLVER[solver]

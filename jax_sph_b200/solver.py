@@ -22,9 +22,9 @@ class _KernelInfo:
 
     def __init__(self, name, h):
         if name not in _lib.KERNEL:
-            raise _lib.Sphb200Error(f"kernel {name!r} is not supported (QSK, WC2K)")
+            raise _lib.Sphb200Error(f"kernel {name!r} is not supported {tuple(_lib.KERNEL)}")
         self.h = h
-        self.cutoff = (3.0 if name == "QSK" else 2.0) * h  # kernel.py:64, :88
+        self.cutoff = (3.0 if name in ("QSK", "GK", "SGK") else 2.0) * h  # kernel.py: cutoff
 
 
 class WCSPH:

@@ -2,7 +2,7 @@
 
 Restates jax_sph/kernel.py: QuinticKernel :51-72, WendlandC2Kernel :75-103 (the
 two on the hot path) plus Cubic :26-48, WendlandC4 :106-134, WendlandC6
-:137-165, Gaussian :168-182 so that the reference's tests/test_kernel.py can be
+:137-165, Gaussian :168-182, SuperGaussian :185-201 so that the reference's tests/test_kernel.py can be
 replayed against the oracle.  ``grad_w`` is the analytic derivative that
 ``jax.grad`` (kernel.py:20-23) produces; integer powers follow
 ``lax.integer_pow`` (repeated squaring).
@@ -129,18 +129,23 @@ class CubicKernel(_Base):
 
 
 class _WendlandHigh(_Base):
+    """w = sigma * max(0, 1 - q/2)^n * poly(q); grad_w is what jax.grad gives (kernel.py:20-23):
+    sigma / h * (-(n/2) q1^(n-1) poly + q1^n poly')."""
+
     _normalized_cutoff = 2.0
 
     def w(self, r):
         q = np.asarray(r, dtype=self.dtype) * self._c(self._one_over_h)
-        q1 = np.maximum(0.0, 1.0 - 0.5 * q)
-        return self._c(self._sigma) * (q1**self._n * self._poly(q))
+        q1 = np.maximum(self._c(0.0), self._c(1.0) - self._c(0.5) * q)
+        return self._c(self._sigma) * (_ipow(q1, self._n) * self._poly(q))
 
-    def grad_w(self, r, eps=1e-6):
-        r = np.asarray(r, dtype=np.float64)
-        return (self.w(r + eps * self.h) - self.w(np.maximum(r - eps * self.h, 0))) / (
-            (r + eps * self.h) - np.maximum(r - eps * self.h, 0)
-        )
+    def grad_w(self, r):
+        q = np.asarray(r, dtype=self.dtype) * self._c(self._one_over_h)
+        q1 = np.maximum(self._c(0.0), self._c(1.0) - self._c(0.5) * q)
+        inside = (q1 > 0).astype(self.dtype)  # d max(0, x)/dx
+        dq = (self._c(-0.5 * self._n) * _ipow(q1, self._n - 1) * inside * self._poly(q)
+              + _ipow(q1, self._n) * self._dpoly(q))
+        return self._c(self._sigma) * self._c(self._one_over_h) * dq
 
 
 class WendlandC4Kernel(_WendlandHigh):
@@ -157,7 +162,12 @@ class WendlandC4Kernel(_WendlandHigh):
     def _poly(self, q):
         if self.dim == 1:
             return 2.0 * q**2 + 2.5 * q + 1.0
-        return 35.0 / 12.0 * q**2 + 3 * q + 1.0
+        return self._c(35.0 / 12.0) * q**2 + 3 * q + 1.0
+
+    def _dpoly(self, q):
+        if self.dim == 1:
+            return 4.0 * q + 2.5
+        return self._c(35.0 / 6.0) * q + 3
 
 
 class WendlandC6Kernel(_WendlandHigh):
@@ -175,6 +185,11 @@ class WendlandC6Kernel(_WendlandHigh):
         if self.dim == 1:
             return 21.0 / 8.0 * q**3 + 19.0 / 4.0 * q**2 + 3.5 * q + 1.0
         return 4.0 * q**3 + 6.25 * q**2 + 4 * q + 1.0
+
+    def _dpoly(self, q):
+        if self.dim == 1:
+            return 63.0 / 8.0 * q**2 + 9.5 * q + 3.5
+        return 12.0 * q**2 + 12.5 * q + 4
 
 
 class GaussianKernel(_Base):
@@ -199,6 +214,27 @@ class GaussianKernel(_Base):
         )
 
 
+class SuperGaussianKernel(_Base):
+    """kernel.py:185-201: sigma [q <= 3] exp(-q^2) (dim/2 + 1 - q^2)."""
+
+    _normalized_cutoff = 3.0
+
+    def __init__(self, h, dim=3, dtype=np.float64):
+        super().__init__(h, dim, dtype)
+        self._sigma = 1.0 / np.pi ** (dim / 2) * self._one_over_h**dim
+
+    def w(self, r):
+        q = np.asarray(r, dtype=self.dtype) * self._c(self._one_over_h)
+        return (self._c(self._sigma) * (3 - q >= 0) * np.exp(-(q**2))
+                * (self._c(self.dim / 2 + 1) - q**2))
+
+    def grad_w(self, r):
+        q = np.asarray(r, dtype=self.dtype) * self._c(self._one_over_h)
+        # d/dq [e^{-q^2} (a - q^2)] = -2 q e^{-q^2} (a + 1 - q^2)
+        return (self._c(self._sigma) * self._c(self._one_over_h) * (3 - q >= 0) * (-2.0 * q)
+                * np.exp(-(q**2)) * (self._c(self.dim / 2 + 2) - q**2))
+
+
 KERNELS = {
     "CSK": CubicKernel,
     "QSK": QuinticKernel,
@@ -206,4 +242,5 @@ KERNELS = {
     "WC4K": WendlandC4Kernel,
     "WC6K": WendlandC6Kernel,
     "GK": GaussianKernel,
+    "SGK": SuperGaussianKernel,
 }

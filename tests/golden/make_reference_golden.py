@@ -92,6 +92,23 @@ CASES = {
     "db2d_delta": (["config=cases/db.yaml", "case.dx=0.05", "solver.dt=null", "solver.name=DELTA",
                     "eos.gamma=7.0", "solver.artificial_alpha=0.0"],
                    dict(case="db", dim=2, dx=0.05, solver="DELTA", gamma=7.0, artificial_alpha=0.0)),
+    # the five kernels outside QSK / WC2K (kernel.py:26-48, :106-201)
+    "tgv2d_csk": (["config=cases/tgv.yaml", "case.dx=0.04", "solver.tvf=1.0", "kernel.name=CSK",
+                   "kernel.h_factor=1.3", "case.r0_noise_factor=0.25"],
+                  dict(case="tgv", dim=2, dx=0.04, tvf=1.0, kernel="CSK", h_factor=1.3)),
+    "tgv2d_wc4k": (["config=cases/tgv.yaml", "case.dx=0.04", "solver.tvf=1.0", "kernel.name=WC4K",
+                    "kernel.h_factor=1.5", "case.r0_noise_factor=0.25"],
+                   dict(case="tgv", dim=2, dx=0.04, tvf=1.0, kernel="WC4K", h_factor=1.5)),
+    "tgv3d_wc6k": (["config=cases/tgv.yaml", "case.dim=3", "case.dx=0.6283185307179586",
+                    "case.viscosity=0.02", "solver.tvf=1.0", "kernel.name=WC6K",
+                    "kernel.h_factor=1.5", "case.r0_noise_factor=0.25"],
+                   dict(case="tgv", dim=3, dx=0.6283185307179586, viscosity=0.02, tvf=1.0,
+                        kernel="WC6K", h_factor=1.5)),
+    "tgv2d_gk": (["config=cases/tgv.yaml", "case.dx=0.04", "solver.name=RIE",
+                  "solver.density_evolution=True", "kernel.name=GK", "case.r0_noise_factor=0.25"],
+                 dict(case="tgv", dim=2, dx=0.04, solver="RIE", density_evolution=True, kernel="GK")),
+    "db2d_sgk": (["config=cases/db.yaml", "case.dx=0.05", "solver.dt=null", "kernel.name=SGK"],
+                 dict(case="db", dim=2, dx=0.05, kernel="SGK")),
     "tgv3d_delta": (["config=cases/tgv.yaml", "case.dim=3", "case.dx=0.6283185307179586",
                      "case.viscosity=0.02", "solver.name=DELTA", "solver.density_evolution=True",
                      "case.r0_noise_factor=0.25"],
@@ -147,6 +164,36 @@ def unpack_pairs(counts, recv):
     n = len(counts)
     send = np.repeat(np.arange(n, dtype=np.int64), counts)
     return send * n + recv.astype(np.int64)
+
+
+def run_kernels(x64):
+    """w(r) and grad_w(r) of every kernel class of jax_sph/kernel.py (vmapped as solver.py:726,730
+    does) on a grid that includes r = 0, the knots and the cutoff: tests/golden/ref_kernels.npz."""
+    sys.path.insert(0, os.path.join(HERE, "jaxshim"))
+    sys.path.insert(0, REF)
+    import jax
+
+    jax.config.update("jax_enable_x64", bool(x64))
+    import jax.numpy as jnp
+
+    from jax_sph import kernel as K
+
+    tag = "f64" if x64 else "f32"
+    h = 0.0123
+    out = {"h": np.float64(h)}
+    classes = dict(CSK=K.CubicKernel, QSK=K.QuinticKernel, WC2K=K.WendlandC2Kernel,
+                   WC4K=K.WendlandC4Kernel, WC6K=K.WendlandC6Kernel, GK=K.GaussianKernel,
+                   SGK=K.SuperGaussianKernel)
+    for name, cls in classes.items():
+        for dim in (2, 3):
+            k = cls(h=h, dim=dim)
+            q = np.concatenate([np.linspace(0.0, 3.3, 265), np.array([1.0, 2.0, 3.0])])
+            r = jnp.array(np.sort(q) * h)
+            out[f"{name}_{dim}_{tag}_r"] = np.array(r)
+            out[f"{name}_{dim}_{tag}_w"] = np.array(jax.vmap(k.w)(r))
+            out[f"{name}_{dim}_{tag}_gw"] = np.array(jax.vmap(k.grad_w)(r))
+            out[f"{name}_{dim}_cutoff"] = np.float64(k.cutoff)
+    np.savez(os.path.join(HERE, f"_tmp_kernels_{tag}.npz"), **out)
 
 
 def run_case(name, x64, long=False):
@@ -248,9 +295,25 @@ def main():
     ap.add_argument("--only", nargs="*")
     ap.add_argument("--child", nargs=2, metavar=("CASE", "X64"))
     ap.add_argument("--long", action="store_true", help="the 200-step trajectories (ref200_*.npz)")
+    ap.add_argument("--kernels", action="store_true", help="kernel tables (ref_kernels.npz)")
     a = ap.parse_args()
     if a.child:
-        run_case(a.child[0], int(a.child[1]), long=a.long)
+        if a.child[0] == "__kernels__":
+            run_kernels(int(a.child[1]))
+        else:
+            run_case(a.child[0], int(a.child[1]), long=a.long)
+        return
+    if a.kernels:
+        merged = {}
+        for x64 in (0, 1):
+            subprocess.run([sys.executable, "-W", "ignore", os.path.abspath(__file__), "--child",
+                            "__kernels__", str(x64)], check=True, stdout=subprocess.DEVNULL)
+            tmp = os.path.join(HERE, f"_tmp_kernels_{'f64' if x64 else 'f32'}.npz")
+            with np.load(tmp) as z:
+                merged.update({k: z[k] for k in z.files})
+            os.remove(tmp)
+        np.savez_compressed(os.path.join(HERE, "ref_kernels.npz"), **merged)
+        print("ref_kernels.npz", len(merged), "arrays")
         return
     for name, (cli, kw) in (LONG_CASES if a.long else CASES).items():
         if a.only and name not in a.only:

@@ -169,7 +169,7 @@ def test_error_behaviour():
 
         SlabEngine(make_config(2, [1.0, 1.0], 0.05, 0.0, solver="DELTA", is_rho_evol=True), 0, 2)
     with pytest.raises(_lib.Sphb200Error, match="not supported"):
-        make_config(2, [1.0, 1.0], 0.05, 0.0, kernel="GK")
+        make_config(2, [1.0, 1.0], 0.05, 0.0, kernel="M4")
     # positions outside the periodic box are reported through the device error word
     bad = dict(setup.state)
     bad["r"] = bad["r"].copy()

@@ -213,3 +213,23 @@ def test_200_steps_match_reference(name):
     adv, _ = oracle_run(setup, meta["nsteps"], meta["dt"])
     for k in ("r", "u", "v", "rho", "T"):
         assert_close(k, adv[k], z[f"advance_f32_{k}"], setup, factor=15.0, what=f"{name} 200 steps")
+
+
+# ---- kernel tables -------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["CSK", "QSK", "WC2K", "WC4K", "WC6K", "GK", "SGK"])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_kernels_match_reference_tables(name, dim):
+    """w(r) and jax.grad(w)(r) of every kernel class of jax_sph/kernel.py on a grid including
+    r = 0, the knots and the cutoff (tests/golden/ref_kernels.npz): the oracle's closed forms
+    agree to rounding in float64 and to 2e-6 of the peak in float32."""
+    from oracle import kernel as K
+
+    z = np.load(os.path.join(GOLDEN, "ref_kernels.npz"))
+    h = float(z["h"])
+    for tag, dt, tol in (("f64", np.float64, 1e-13), ("f32", np.float32, 2e-6)):
+        k = K.KERNELS[name](h=h, dim=dim, dtype=dt)
+        assert abs(k.cutoff - float(z[f"{name}_{dim}_cutoff"])) < 1e-15
+        r = z[f"{name}_{dim}_{tag}_r"]
+        for what, mine in (("w", k.w(r)), ("gw", k.grad_w(r))):
+            ref = z[f"{name}_{dim}_{tag}_{what}"]
+            assert max_err(mine, ref) <= tol * np.abs(ref).max(), (name, dim, tag, what)
