@@ -168,7 +168,7 @@ def unpack_pairs(counts, recv):
 
 def run_kernels(x64):
     """w(r) and grad_w(r) of every kernel class of jax_sph/kernel.py (vmapped as solver.py:726,730
-    does) on a grid that includes r = 0, the knots and the cutoff: tests/golden/ref_kernels.npz."""
+    does) on a grid that includes r = 0, the knots and the cutoff: tests/golden/kernel_tables.npz."""
     sys.path.insert(0, os.path.join(HERE, "jaxshim"))
     sys.path.insert(0, REF)
     import jax
@@ -295,7 +295,7 @@ def main():
     ap.add_argument("--only", nargs="*")
     ap.add_argument("--child", nargs=2, metavar=("CASE", "X64"))
     ap.add_argument("--long", action="store_true", help="the 200-step trajectories (ref200_*.npz)")
-    ap.add_argument("--kernels", action="store_true", help="kernel tables (ref_kernels.npz)")
+    ap.add_argument("--kernels", action="store_true", help="kernel tables (kernel_tables.npz)")
     a = ap.parse_args()
     if a.child:
         if a.child[0] == "__kernels__":
@@ -312,8 +312,8 @@ def main():
             with np.load(tmp) as z:
                 merged.update({k: z[k] for k in z.files})
             os.remove(tmp)
-        np.savez_compressed(os.path.join(HERE, "ref_kernels.npz"), **merged)
-        print("ref_kernels.npz", len(merged), "arrays")
+        np.savez_compressed(os.path.join(HERE, "kernel_tables.npz"), **merged)
+        print("kernel_tables.npz", len(merged), "arrays")
         return
     for name, (cli, kw) in (LONG_CASES if a.long else CASES).items():
         if a.only and name not in a.only:

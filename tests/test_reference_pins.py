@@ -220,11 +220,11 @@ def test_200_steps_match_reference(name):
 @pytest.mark.parametrize("dim", [2, 3])
 def test_kernels_match_reference_tables(name, dim):
     """w(r) and jax.grad(w)(r) of every kernel class of jax_sph/kernel.py on a grid including
-    r = 0, the knots and the cutoff (tests/golden/ref_kernels.npz): the oracle's closed forms
+    r = 0, the knots and the cutoff (tests/golden/kernel_tables.npz): the oracle's closed forms
     agree to rounding in float64 and to 2e-6 of the peak in float32."""
     from oracle import kernel as K
 
-    z = np.load(os.path.join(GOLDEN, "ref_kernels.npz"))
+    z = np.load(os.path.join(GOLDEN, "kernel_tables.npz"))
     h = float(z["h"])
     for tag, dt, tol in (("f64", np.float64, 1e-13), ("f32", np.float32, 2e-6)):
         k = K.KERNELS[name](h=h, dim=dim, dtype=dt)
