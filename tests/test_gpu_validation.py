@@ -78,3 +78,59 @@ def test_tgv3d_energy_curve_and_convergence():
     assert err[64] < 0.21, err  # measured 0.175
     assert err[32] < 0.29, err  # measured 0.246
     assert err[64] < err[32], err  # converges towards the reference curve
+
+
+# ---- the reference's own integration tests, replayed on the engine ---------------------------
+def _u_series_pf(y, t_, n_max=10):
+    """reference tests/test_pf2d.py:14-41 (transient Poiseuille profile)."""
+    eta, rho, u_max, d = 100.0, 1.0, 1.25, 1.0
+    nu = eta / rho
+    fx = -8 * nu * u_max / d**2
+    res = fx / (2 * nu) * y * (y - d)
+    for n in range(n_max):
+        base = np.pi * (2 * n + 1) / d
+        res = res + 4 * fx / (nu * base**3 * d) * np.sin(base * y) * np.exp(-(base**2) * nu * t_)
+    return res
+
+
+def _u_series_cf(y, t_, n_max=10):
+    """reference tests/test_cf2d.py:14-45 (transient Couette profile)."""
+    eta, rho, u_max, d = 100.0, 1.0, 1.25, 1.0
+    nu = eta / rho
+    res = u_max * y / d
+    for n in range(1, n_max):
+        base = np.pi * n / d
+        res = res + 2 * u_max / (n * np.pi) * (-1) ** n * np.sin(base * y) * np.exp(-(base**2) * nu * t_)
+    return res
+
+
+@pytest.mark.parametrize("tvf,solver", [(0.0, "SPH"), (1.0, "SPH"), (0.0, "RIE"), (0.0, "DELTA")])
+@pytest.mark.parametrize("case", ["pf", "cf"])
+def test_channel_flow_matches_analytical_solution(case, tvf, solver):
+    """reference tests/test_pf2d.py:106-115 and tests/test_cf2d.py:110-119, same parameters
+    (dx = 0.0333333, dt = 2e-6, t_end = 5e-3, probes at t = 5e-4, 1e-3, 5e-3, the same four
+    (tvf, solver) pairs, atol 1e-2), with the CUDA engine in place of `simulate()` and the
+    Shepard interpolation of `utils.sph_interpolator` (utils.py:299-443) on the downloaded state."""
+    from jax_sph_b200 import Engine, config_from_setup
+    from oracle import cases
+    from oracle.interp import interp_vel
+
+    dx, dt = 0.0333333, 0.000002
+    setup = cases.make_case(case, dim=2, dx=dx, dtype=np.float32, solver=solver, tvf=tvf, dt=dt)
+    eng = Engine(config_from_setup(setup), len(setup.state["r"]))
+    eng.upload(setup.state)
+    y_axis = np.linspace(0, 1, 21)
+    rs = 0.2 * np.ones([len(y_axis), 2])
+    rs[:, 1] = y_axis + 3 * dx
+    series = _u_series_pf if case == "pf" else _u_series_cf
+    done = 0
+    for tp in (0.0005, 0.001, 0.005):
+        # the reference writes frame k = the state before step k (simulate.py:115)
+        target = int(tp / dt)
+        eng.step(dt, target - done)
+        done = target
+        state = {k: v.numpy().astype(np.float64) if v.dtype.is_floating_point else v.numpy()
+                 for k, v in eng.download(host=True).items()}
+        got = interp_vel(state, setup.box_size, dx, 2, rs)
+        assert np.allclose(got, series(y_axis, tp), atol=1e-2), (case, solver, tvf, tp)
+    assert eng.error() == 0
