@@ -355,7 +355,25 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
             if (__any_sync(FULL_MASK, want > sd.lcap - cnt)) break;  // flush first
             const int e = j + want;
             int lo = cnt * LS + tid;  // tid < LS: lo / LS is the entry count at any time
-#pragma unroll 4
+            // four candidates per trip, loaded before the first append: the appends go to the
+            // same shared-memory window the candidates come from, so the compiler would
+            // otherwise keep every load behind the previous store (one LDS latency per candidate)
+            for (; j + 4 <= e; j += 4) {
+              const float4 p0 = sq[j], p1 = sq[j + 1], p2 = sq[j + 2], p3 = sq[j + 3];
+              float t0 = xs - p0.x, t1 = xs - p1.x, t2 = xs - p2.x, t3 = xs - p3.x;
+              float d0 = t0 * t0, d1 = t1 * t1, d2 = t2 * t2, d3 = t3 * t3;
+              t0 = ys - p0.y; t1 = ys - p1.y; t2 = ys - p2.y; t3 = ys - p3.y;
+              d0 += t0 * t0; d1 += t1 * t1; d2 += t2 * t2; d3 += t3 * t3;
+              if (DIM == 3) {
+                t0 = zs - p0.z; t1 = zs - p1.z; t2 = zs - p2.z; t3 = zs - p3.z;
+                d0 += t0 * t0; d1 += t1 * t1; d2 += t2 * t2; d3 += t3 * t3;
+              }
+              if (d0 < g.c2_hi) { list[lo] = (unsigned short)j; lo += LS; }
+              if (d1 < g.c2_hi) { list[lo] = (unsigned short)(j + 1); lo += LS; }
+              if (d2 < g.c2_hi) { list[lo] = (unsigned short)(j + 2); lo += LS; }
+              if (d3 < g.c2_hi) { list[lo] = (unsigned short)(j + 3); lo += LS; }
+            }
+#pragma unroll 1
             for (; j < e; ++j) {
               const float4 pj = sq[j];
               const float dx = xs - pj.x, dy = ys - pj.y;
@@ -373,8 +391,42 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
           }
           // ---------------- phase 2: real neighbours, exact arithmetic ----------------
           int m = carry;
+          int k = carry;
+          if (LM == LIST_BUILD) {
+            // the list builder takes two survivors per trip (both loaded before the first
+            // in-place compaction store, which the compiler must otherwise order against
+            // every later load): two independent LDS -> displacement -> kernel chains
 #pragma unroll 1
-          for (int k = carry; k < cnt; ++k) {
+            for (; k + 1 < cnt; k += 2) {
+              const int j0 = list[k * LS + tid], j1 = list[(k + 1) * LS + tid];
+              const float4 p0 = sq[j0], p1 = sq[j1];
+              float r0[3], r1[3];
+              if (interior) {
+                pair_disp<DIM, true>(g, ri, p0, r0);
+                pair_disp<DIM, true>(g, ri, p1, r1);
+              } else {
+                pair_disp<DIM, false>(g, ri, p0, r0);
+                pair_disp<DIM, false>(g, ri, p1, r1);
+              }
+              const float s0 = sumsq<DIM>(r0), s1 = sumsq<DIM>(r1);
+              if (s0 < g.c2) {  // membership: see the note in the loop below
+                if (nl_build) {
+                  list[m * LS + tid] = (unsigned short)j0;  // m <= k: never an unread entry
+                  ++m;
+                }
+                P::pair(c, ex, own, acc, sq, sd.cap, j0, p0, r0, s0);
+              }
+              if (s1 < g.c2) {
+                if (nl_build) {
+                  list[m * LS + tid] = (unsigned short)j1;
+                  ++m;
+                }
+                P::pair(c, ex, own, acc, sq, sd.cap, j1, p1, r1, s1);
+              }
+            }
+          }
+#pragma unroll 1
+          for (; k < cnt; ++k) {
             const int jn = list[k * LS + tid];
             const float4 pj = sq[jn];
             float dr[3];

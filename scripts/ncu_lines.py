@@ -1,6 +1,6 @@
 """Aggregate an ncu report's per-instruction counters by CUDA source line.
 
-  python scripts/ncu_lines.py gpurun_out/prof.ncu-rep [kernel-substring] [top]
+  python scripts/ncu_lines.py gpurun_out/prof.ncu-rep [kernel-substring] [top] [samples]
 
 Joins `ncu --page source --csv` (SASS rows with executed-instruction counts and
 stall samples) with `nvdisasm -g` line markers of the in-tree libsphb200.so.
@@ -45,6 +45,7 @@ def main():
     rep = sys.argv[1]
     want = sys.argv[2] if len(sys.argv) > 2 else ""
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    by_samples = len(sys.argv) > 4 and sys.argv[4] == "samples"  # order by stall samples
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True,
                          text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
@@ -83,7 +84,7 @@ def main():
             a[0] += n; a[1] += s; a[2] += t
             tot += n; tots += s
         print(f"== {b['name'][:110]}\n   matched {cand[:90]}\n   warp-inst {tot:,}  samples {tots:,}")
-        for (fn, ln), (n, s, t) in sorted(per.items(), key=lambda kv: -kv[1][0])[:top]:
+        for (fn, ln), (n, s, t) in sorted(per.items(), key=lambda kv: -kv[1][1 if by_samples else 0])[:top]:
             if fn not in srcs:
                 p = os.path.join(ROOT, "jax_sph_b200", "csrc", fn)
                 srcs[fn] = open(p).read().splitlines() if os.path.exists(p) else []
