@@ -231,7 +231,14 @@ def run_ours(args):
         # created (eagerly, with device_id): keep stdout for the one JSON line
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL's own streams at high priority: the halo exchanges run while the interior tile
+        # layers of the next sweep occupy the SMs on the engine's side stream (slab overlap)
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            pass
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
         return run_slab(args, world, rank, local, saved_stdout)
 
     state, meta = lattice_state(args.workload, args.nx)

@@ -49,6 +49,7 @@ struct Grid {
   int goff[3];   // global cell index of local cell 0 (negative for the rank at the box bottom)
   int ng[3];     // global cells per axis
   int own_lo[3], own_hi[3];  // local cell range this rank owns (sweeps tile exactly this range)
+  int block0;    // first tile of this launch (a sweep may be launched over a sub-range of tiles)
 };
 
 // Derived float32 constants, rounded where the reference rounds them.

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -86,6 +87,17 @@ struct sphb200_engine {
   uint32_t slab_flags;
   bool slab_v_is_u;
   Kick slab_kick;
+  // Slab overlap: while a halo message is in flight the INTERIOR tile layers of the next big
+  // sweep (density or force; tiles whose stencil touches no halo layer) run on a side stream.
+  // launch_lo/hi: tile-layer range (along the slab axis) of the sweep launches in progress,
+  // -1 = all tiles.
+  int launch_lo, launch_hi;
+  int part;            // 0: all tiles, 1: interior tile layers only, 2: boundary tile layers only
+  int int_lo, int_hi;  // interior tile layers [int_lo, int_hi) along the slab axis
+  cudaStream_t side;
+  cudaEvent_t ev_main, ev_side;
+  bool overlap;       // side stream and events exist (slab engines)
+  int pre_stage;      // stage whose interior tiles are already running on the side stream, -1
   // wall-normal recomputation for moving walls (utils.py:197-277): the static one-layer
   // discretisation of the wall surface; wl_n == 0: normals are an input that never changes
   float4* wl_pts;
@@ -378,9 +390,24 @@ int launch_sweep(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f,
   const int sb = ex.sb > 0 ? ex.sb : 16 * ex.nq;
   if (sb > sp.sb) return SPHB200_EINVAL;
   SweepDims sd{sp.cap, sp.lcap, sb};
-  const int blocks = e->grid.nt[0] * e->grid.nt[1] * e->grid.nt[2];
-  kern<<<blocks, e->tpb, sp.smem, st>>>(e->grid, e->consts, f, e->start, sd, ex, e->err, nl);
-  e->launches++;
+  const int all = e->grid.nt[0] * e->grid.nt[1] * e->grid.nt[2];
+  Grid g = e->grid;
+  // tile layers along the slab axis (the slowest tile index) covered by this launch
+  const int ax = e->dim - 1, nl_ax = g.nt[ax], per_layer = all / nl_ax;
+  int ranges[2][2] = {{0, nl_ax}, {0, 0}};
+  if (e->part == 1) {
+    ranges[0][0] = e->int_lo; ranges[0][1] = e->int_hi;
+  } else if (e->part == 2) {
+    ranges[0][0] = 0; ranges[0][1] = e->int_lo;
+    ranges[1][0] = e->int_hi; ranges[1][1] = nl_ax;
+  }
+  for (int r = 0; r < 2; ++r) {
+    const int blocks = (ranges[r][1] - ranges[r][0]) * per_layer;
+    if (blocks <= 0) continue;
+    g.block0 = ranges[r][0] * per_layer;
+    kern<<<blocks, e->tpb, sp.smem, st>>>(g, e->consts, f, e->start, sd, ex, e->err, nl);
+    e->launches++;
+  }
   CK(cudaGetLastError());
   return SPHB200_OK;
 }
@@ -518,10 +545,17 @@ int build_cells(sphb200_engine* e, const Kick& k, cudaStream_t st) {
 // 2 generalized wall BC, 3 force (+ case bc_fn).  *wrote = HX_* mask of the per-particle
 // arrays the stage changed that later stages read from NEIGHBOURS (what a slab halo must
 // refresh); 0 when the stage is not part of this solver variant.
+// part (slab overlap, stages 0 and 3 only): 1 = launch the interior tile layers and nothing else
+// (no swap, no bookkeeping: the boundary call finishes the stage), 2 = the boundary tile layers.
 int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cudaStream_t st,
-                  int* wrote) {
+                  int* wrote, int part = 0) {
   const sphb200_config& c = e->cfg;
   *wrote = 0;
+  struct PartGuard {  // launch_sweep reads e->part; always back to "all tiles" on return
+    sphb200_engine* e;
+    ~PartGuard() { e->part = 0; }
+  } part_guard{e};
+  e->part = part;
   const bool bc_trick = c.flags & SPHB200_F_BC_TRICK, evol = c.flags & SPHB200_F_RHO_EVOL,
              renorm = c.flags & SPHB200_F_RHO_RENORM, free_slip = c.flags & SPHB200_F_FREE_SLIP,
              heat = c.flags & SPHB200_F_HEAT;
@@ -607,6 +641,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
 #undef CALL
     }
     if (rc) return rc;
+    if (part == 1) return SPHB200_OK;
     swap_st(e);
     *wrote = HX_ST | (e->has_ut ? HX_UT : 0);
     if (e->profile) cudaEventRecord(e->ev[3], st);
@@ -640,7 +675,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
   }
   // ---- force -----------------------------------------------------------------
   if (stage == 3) {
-    if (e->profile) cudaEventRecord(e->ev[4], st);
+    if (e->profile && part != 1) cudaEventRecord(e->ev[4], st);
     Extra ex = make_extra();
     ex.q_v = fq_v; ex.q_h = fq_h; ex.q_nw = fq_nw; ex.q_ut = fq_ut;
     ex.nq = force_nq;
@@ -674,6 +709,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
 #undef CALL
     }
     if (rc) return rc;
+    if (part == 1) return SPHB200_OK;
     if (ex.bc_on) {
       const int bound = e->slab_on ? e->sgeom.own_cap : e->n;
       const int nb = (bound + 255) / 256;
@@ -773,6 +809,10 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->slab_axis = cfg->dim - 1;
   e->slab_stage = 0;
   e->slab_pending_mask = 0;
+  e->part = 0;
+  e->launch_lo = e->launch_hi = -1;
+  e->pre_stage = -1;
+  e->overlap = false;
   int dev = 0;
   CK(cudaGetDevice(&dev));
   int maxs = 0;
@@ -962,6 +1002,11 @@ int sphb200_engine_destroy(sphb200_engine* e) {
     for (int i = 0; i < 8; ++i) cudaEventDestroy(e->ev[i]);
   if (e->hstage) cudaFree(e->hstage);
   if (e->wl_pts) cudaFree(e->wl_pts);
+  if (e->overlap) {
+    cudaStreamDestroy(e->side);
+    cudaEventDestroy(e->ev_main);
+    cudaEventDestroy(e->ev_side);
+  }
   if (e->own_arena) cudaFree(e->arena);
   delete e;
   return SPHB200_OK;
@@ -1318,6 +1363,26 @@ int sphb200_slab_create(const sphb200_config* cfg, int rank, int nranks, int64_t
     delete e;
     return rc;
   }
+  // overlap of the halo exchanges with the interior tile layers (prelaunch_interior): tile
+  // layer t covers own cell layers [t T, (t + 1) T); its stencil stays inside the own layers
+  // iff t T >= S and (t + 1) T + S <= n_own
+  {
+    const Grid& gg = e->grid;
+    const int ax = e->dim - 1, T = gg.T[ax], S = gg.S[ax], nown = gg.own_hi[ax] - gg.own_lo[ax];
+    e->int_lo = (S + T - 1) / T;
+    e->int_hi = (nown - S) / T;
+    if (e->int_hi > gg.nt[ax]) e->int_hi = gg.nt[ax];
+    if (e->int_hi < e->int_lo) e->int_hi = e->int_lo;
+    const char* off = getenv("SPHB200_SLAB_OVERLAP");
+    if (!(off && off[0] == '0') && e->int_hi > e->int_lo &&
+        cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) == cudaSuccess) {
+      if (cudaEventCreateWithFlags(&e->ev_main, cudaEventDisableTiming) == cudaSuccess &&
+          cudaEventCreateWithFlags(&e->ev_side, cudaEventDisableTiming) == cudaSuccess)
+        e->overlap = true;
+      else
+        cudaStreamDestroy(e->side);
+    }
+  }
   *out = e;
   return SPHB200_OK;
 }
@@ -1363,6 +1428,36 @@ int sphb200_slab_counts(sphb200_engine* e, int32_t out[8], void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemcpyAsync(out, e->dn, DN_WORDS * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return SPHB200_OK;
+}
+
+// ---- slab overlap ---------------------------------------------------------------------------
+// The stage the next sweep launch belongs to (stages 1 and 2 exist only for some variants).
+static int next_effective_stage(const sphb200_engine* e, int from) {
+  const sphb200_config& c = e->cfg;
+  const bool evol = c.flags & SPHB200_F_RHO_EVOL, renorm = c.flags & SPHB200_F_RHO_RENORM;
+  const bool wall_sweep = (c.flags & SPHB200_F_BC_TRICK) && c.solver != SPHB200_SOLVER_RIE;
+  for (int s = from; s < 4; ++s) {
+    if (s == 1 && !(evol && renorm)) continue;
+    if (s == 2 && !wall_sweep) continue;
+    return s;
+  }
+  return 4;
+}
+
+// While the halo message just packed is in flight (the caller enqueues the exchange on `st`
+// after this returns), start the interior tile layers of stage `stage` (0 density, 3 force) on
+// the side stream: their stencils touch no halo layer, so they need nothing from the message.
+static int prelaunch_interior(sphb200_engine* e, int stage, cudaStream_t st) {
+  e->pre_stage = -1;
+  if (!e->overlap || (stage != 0 && stage != 3) || e->int_hi <= e->int_lo) return SPHB200_OK;
+  CK(cudaEventRecord(e->ev_main, st));
+  CK(cudaStreamWaitEvent(e->side, e->ev_main, 0));
+  int wrote = 0;
+  int rc = forward_stage(e, stage, e->slab_flags, e->slab_v_is_u, e->side, &wrote, 1);
+  if (rc) return rc;
+  CK(cudaEventRecord(e->ev_side, e->side));
+  e->pre_stage = stage;
   return SPHB200_OK;
 }
 
@@ -1416,7 +1511,7 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
     e->slab_pending_mask = mask;
     e->slab_stage = 0;
     *xbytes = (int64_t)halo_bytes(mask, sg.halo_cap, sg.ncl);
-    return SPHB200_OK;
+    return prelaunch_interior(e, next_effective_stage(e, 0), st);
   }
   // phase >= 2: take in the halo message of the previous phase, then sweep until the next
   // stage whose results the neighbours need
@@ -1436,7 +1531,13 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
   while (e->slab_stage < 4) {
     int wrote = 0;
     const int stage = e->slab_stage++;
-    int rc = forward_stage(e, stage, e->slab_flags, e->slab_v_is_u, st, &wrote);
+    int part = 0;
+    if (e->pre_stage == stage) {  // its interior tiles ran on the side stream during the exchange
+      CK(cudaStreamWaitEvent(st, e->ev_side, 0));
+      e->pre_stage = -1;
+      part = 2;
+    }
+    int rc = forward_stage(e, stage, e->slab_flags, e->slab_v_is_u, st, &wrote, part);
     if (rc) return rc;
     if (wrote && stage < 3) {
       k_halo_pack<<<dim3(hblocks, 2), 256, 0, st>>>(sl, sg, e->fr[e->cur], wrote, e->start,
@@ -1445,7 +1546,7 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
       CK(cudaGetLastError());
       e->slab_pending_mask = wrote;
       *xbytes = (int64_t)halo_bytes(wrote, sg.halo_cap, sg.ncl);
-      return SPHB200_OK;
+      return prelaunch_interior(e, next_effective_stage(e, stage + 1), st);
     }
   }
   if (e->profile) cudaEventRecord(e->ev[5], st);

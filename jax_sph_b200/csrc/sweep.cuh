@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
   int* own_start = own_off + (MAX_RUNS + 1);
 
   // ---- tile geometry (uniform) -------------------------------------------
-  int b = blockIdx.x;
+  int b = blockIdx.x + g.block0;
+  const int tile_id = b;
   const int tx = b % g.nt[0];
   b /= g.nt[0];
   const int ty = b % g.nt[1];
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
     nl_build = nl.list != nullptr && total_staged <= nl.min_cap;
     if (tid == 0) s_bad = nl_build ? 0 : 1;  // ordered before any other write by the staging barrier
   }
-  if (LM == LIST_CONSUME) nl_use = nl.list != nullptr && nl.ok[blockIdx.x] != 0;
+  if (LM == LIST_CONSUME) nl_use = nl.list != nullptr && nl.ok[tile_id] != 0;
 
   for (int ib = 0; ib < tile_n; ib += TPB) {
     // ---- own particle ------------------------------------------------------
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
   }
   if (LM == LIST_BUILD && nl.list != nullptr) {
     __syncthreads();
-    if (tid == 0) nl.ok[blockIdx.x] = s_bad ? 0 : 1;
+    if (tid == 0) nl.ok[tile_id] = s_bad ? 0 : 1;
   }
 }
 
