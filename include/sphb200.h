@@ -220,7 +220,9 @@ int sphb200_engine_stats(sphb200_engine *e, double *ekin, double *u_max, void *s
 /* Kernel launches issued by this engine so far (bench.py's gpu_launches). */
 int64_t sphb200_engine_launches(const sphb200_engine *e);
 /* Sweep timing: CUDA-event ms of the last step's passes: [0] integrate+hash, [1] sort/reorder,
- * [2] density sweep, [3] wall sweep, [4] force sweep, [5] total.  Enabled by sphb200_engine_profile(e, 1). sync. */
+ * [2] density sweep, [3] wall sweep, [4] force sweep, [5] total.  Enabled by sphb200_engine_profile(e, 1). sync.
+ * While enabled a slab engine does not overlap its exchanges with interior tiles (the passes are
+ * timed whole, on one stream). */
 int sphb200_engine_profile(sphb200_engine *e, int enable);
 int sphb200_engine_last_times(sphb200_engine *e, float ms[8]);
 /* cell-grid facts for reports: ncells[3], sub[3], tile[3], threads, list_cap, stage_cap(A,B,C). */

@@ -1450,7 +1450,9 @@ static int next_effective_stage(const sphb200_engine* e, int from) {
 // the side stream: their stencils touch no halo layer, so they need nothing from the message.
 static int prelaunch_interior(sphb200_engine* e, int stage, cudaStream_t st) {
   e->pre_stage = -1;
-  if (!e->overlap || (stage != 0 && stage != 3) || e->int_hi <= e->int_lo) return SPHB200_OK;
+  // per-pass event timing (sphb200_engine_profile) measures the sweeps whole, on one stream
+  if (!e->overlap || e->profile || (stage != 0 && stage != 3) || e->int_hi <= e->int_lo)
+    return SPHB200_OK;
   CK(cudaEventRecord(e->ev_main, st));
   CK(cudaStreamWaitEvent(e->side, e->ev_main, 0));
   int wrote = 0;
