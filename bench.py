@@ -152,7 +152,63 @@ def make_setup(workload, nx):
     raise ValueError(workload)
 
 
+def ht3d_meta(nx):
+    """BASELINE configs[4]: cases/ht.yaml with case.dim=3 (3D channel with a hot patch in the
+    bottom wall, cases/ht.py:29-187): box L x (H + 6 dx) x W = 1.0 x (0.2 + 6 dx) x 0.5,
+    dx = 1 / nx (nx = 855 -> 64.6 M particles), SPH + is_bc_trick + heat_conduction,
+    g_ext = 2.3 e_x between the walls, p_bg = 0.05 p_ref, kappa 7.313, Cp 305.27; bc_fn and
+    g_ext_fn in table form (what oracle/cases.py builds and tests/test_host_logic.py checks)."""
+    dx = 1.0 / nx
+    n_walls, g_mag, viscosity, u_ref = 3, 2.3, 0.01, 1.0
+    c_ref = 10.0 * u_ref
+    eps = float(np.finfo(np.float32).eps)
+    dt = float(min(0.25 * dx / (c_ref + u_ref), 0.25 * dx * dx / (viscosity + eps),
+                   0.25 * (dx / (g_mag + eps)) ** 0.5))  # case_setup.py:94-97
+    nxyz = [int(round(1.0 / dx)), int(round(0.2 / dx)) + 2 * n_walls, int(round(0.5 / dx))]
+    box = [1.0, 0.2 + 2 * n_walls * dx, 0.5]
+    zero = [0.0, 0.0, 0.0]
+    st = dict(u=zero, v=zero, zero_dudt=True, zero_dvdt=True, zero_dTdt=True)
+    bc_table = {"tags": {1: dict(st, T=1.0), 3: dict(st, T=1.23)},  # SOLID_WALL, DIRICHLET_WALL
+                "inflow_x": dict(x=float(n_walls * dx), T=1.0),
+                "outflow_x": dict(x=float(box[0] - n_walls * dx))}
+    g_ext_spec = {"mode": "band", "g": [g_mag, 0.0, 0.0], "axis": 1, "lo": float(n_walls * dx),
+                  "hi": float(box[1] - n_walls * dx)}
+    return dict(dim=3, box=box, dx=dx, dt=dt, viscosity=viscosity, c_ref=c_ref, p_ref=c_ref**2,
+                p_bg=0.05 * c_ref**2, tvf=0.0, nxyz=nxyz, n_walls=n_walls, kappa=7.313, Cp=305.27,
+                cfg_kwargs=dict(is_bc_trick=True, is_heat_conduction=True, p_bg=0.05 * c_ref**2,
+                                g_ext_spec=g_ext_spec, bc_table=bc_table))
+
+
+def ht3d_state(nx, planes=None):
+    """Lattice state of ht3d_meta(nx): walls (3 layers below and above) and fluid on one regular
+    lattice (i + 0.5) dx, tags SOLID_WALL / DIRICHLET_WALL (hot patch |x - 0.5| < 0.25 of the
+    bottom wall, ht.py:90-97) / FLUID, fluid at rest, T = 1 (no position noise: lattice input)."""
+    meta = ht3d_meta(nx)
+    dx, (n0, n1, n2), nw = np.float32(meta["dx"]), meta["nxyz"], meta["n_walls"]
+    kk = np.arange(n2) if planes is None else np.nonzero(planes)[0]
+    IX, IY, IK = np.meshgrid(np.arange(n0), np.arange(n1), kk, indexing="xy")
+    ix, iy, ik = IX.ravel(), IY.ravel(), IK.ravel()
+    r = np.stack([(ix + np.float32(0.5)) * dx, (iy + np.float32(0.5)) * dx,
+                  (ik + np.float32(0.5)) * dx], axis=1).astype(np.float32)
+    wall = (iy < nw) | (iy >= n1 - nw)
+    hot = (iy < nw) & (r[:, 0] < 0.5 + 0.25) & (r[:, 0] > 0.5 - 0.25)
+    tag = np.where(hot, 3, np.where(wall, 1, 0)).astype(np.int32)
+    n = len(r)
+    ones, zv = np.ones(n, dtype=np.float32), np.zeros((n, 3), dtype=np.float32)
+    state = dict(r=r, u=zv, v=zv.copy(), dudt=zv.copy(), dvdt=zv.copy(), rho=ones.copy(),
+                 p=ones * np.float32(meta["p_bg"]), drhodt=np.zeros(n, dtype=np.float32),
+                 mass=ones * np.float32(meta["dx"] ** 3), eta=ones * np.float32(meta["viscosity"]),
+                 T=np.where(hot, np.float32(1.23), np.float32(1.0)).astype(np.float32),  # bc_fn at setup
+                 dTdt=np.zeros(n, dtype=np.float32),
+                 kappa=ones * np.float32(meta["kappa"]), Cp=ones * np.float32(meta["Cp"]), tag=tag)
+    if planes is not None:
+        state["ids"] = ((iy * n0 + ix) * n2 + ik).astype(np.int32)
+    return state, meta
+
+
 def lattice_meta(workload, nx):
+    if workload == "ht3d":
+        return ht3d_meta(nx)
     dim, box = (3, 2 * np.pi) if workload == "tgv3d" else (2, 1.0)
     dx = box / nx
     viscosity, u_ref = (0.02, 1.0) if dim == 3 else (0.01, 1.0)
@@ -168,6 +224,8 @@ def lattice_state(workload, nx, planes=None):
     particles at (i + 0.5) dx, TGV velocity field (cases/tgv.py:37-51), rho = 1.
     `planes`: boolean mask over the lattice planes along the last axis (a rank's slab);
     the state then also carries `ids`, the particles' indices in the full lattice."""
+    if workload == "ht3d":
+        return ht3d_state(nx, planes)
     if workload == "tgv3d":
         dim, box = 3, 2 * np.pi
     else:
@@ -214,6 +272,25 @@ def lattice_state(workload, nx, planes=None):
     return state, meta
 
 
+def config_of(args, meta):
+    from jax_sph_b200 import make_config
+
+    dim = meta["dim"]
+    return make_config(dim, meta["box"], meta["dx"], meta["dt"], tvf=meta["tvf"],
+                       c_ref=meta["c_ref"], p_ref=meta["p_ref"],
+                       cell_sub=[args.sub] * dim if args.sub else None,
+                       threads=args.threads, list_cap=args.list_cap,
+                       tile=[args.tile_x, 0, 0] if args.tile_x else None,
+                       **meta.get("cfg_kwargs", {}))
+
+
+def workload_name(args, n):
+    if args.workload == "ht3d":
+        return (f"ht3d nx={args.nx} N={n} SPH bc_trick heat band-g QSK (BASELINE configs[4], "
+                "cases/ht.yaml case.dim=3)")
+    return f"{args.workload} nx={args.nx} N={n} SPH tvf=1 QSK (BASELINE configs[3])"
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -244,11 +321,7 @@ def run_ours(args):
     state, meta = lattice_state(args.workload, args.nx)
     n = len(state["r"])
     dim = meta["dim"]
-    cfg = make_config(dim, meta["box"], meta["dx"], meta["dt"], tvf=meta["tvf"],
-                      c_ref=meta["c_ref"], p_ref=meta["p_ref"],
-                      cell_sub=[args.sub] * dim if args.sub else None,
-                      threads=args.threads, list_cap=args.list_cap,
-                      tile=[args.tile_x, 0, 0] if args.tile_x else None)
+    cfg = config_of(args, meta)
     eng = Engine(cfg, n)
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in state.items()}
     eng.upload(pinned)
@@ -321,7 +394,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload} nx={args.nx} N={n} SPH tvf=1 QSK (BASELINE configs[3])",
+        "config": {"workload": workload_name(args, n),
                    "particles_per_gpu": n, "parallelism": "1 engine per GPU" if world == 1 else
                    f"{world} independent periodic boxes (replicas, no halo exchange yet)",
                    "l2_policy": "state (>1.8 GB) larger than L2", "plan": eng.plan()},
@@ -348,14 +421,11 @@ def run_slab(args, world, rank, local, saved_stdout):
 
     meta = lattice_meta(args.workload, args.nx)
     dim, nx = meta["dim"], args.nx
-    n_total = nx**dim
-    cfg = make_config(dim, meta["box"], meta["dx"], meta["dt"], tvf=meta["tvf"],
-                      c_ref=meta["c_ref"], p_ref=meta["p_ref"],
-                      cell_sub=[args.sub] * dim if args.sub else None,
-                      threads=args.threads, list_cap=args.list_cap,
-                      tile=[args.tile_x, 0, 0] if args.tile_x else None)
+    n_last = meta["nxyz"][-1] if "nxyz" in meta else nx  # lattice planes along the slab axis
+    n_total = int(np.prod(meta["nxyz"])) if "nxyz" in meta else nx**dim
+    cfg = config_of(args, meta)
     eng = SlabEngine(cfg)
-    ax = ((np.arange(nx, dtype=np.float32) + np.float32(0.5)) * np.float32(meta["dx"])).astype(np.float32)
+    ax = ((np.arange(n_last, dtype=np.float32) + np.float32(0.5)) * np.float32(meta["dx"])).astype(np.float32)
     lay = layer_of(ax, eng.inv_cell, eng.layers)
     state, _ = lattice_state(args.workload, nx, planes=(lay >= eng.z0) & (lay < eng.z1))
     ids = state.pop("ids")
@@ -449,7 +519,7 @@ def run_slab(args, world, rank, local, saved_stdout):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload} nx={nx} N={n_total} SPH tvf=1 QSK (BASELINE configs[3])",
+        "config": {"workload": workload_name(args, n_total),
                    "particles_per_gpu": n_own0, "particles_total_after_run": int(tot.item()),
                    "parallelism": f"slab{world}: 1-D slabs of cell layers along axis {eng.axis}, "
                                   f"halo (one cutoff) + migration every step, NCCL send/recv ring",
@@ -482,6 +552,8 @@ def cpu_baseline(args, bounded=True):
     if args.workload == "tgv3d":
         setup = cases.make_case("tgv", dim=3, dx=2 * np.pi / nx, dtype=np.float32, tvf=1.0,
                                 viscosity=0.02)
+    elif args.workload == "ht3d":
+        setup = cases.make_case("ht", dim=3, dx=1.0 / nx, dtype=np.float32)
     else:
         setup = cases.make_case("tgv", dim=2, dx=1.0 / nx, dtype=np.float32, tvf=1.0)
     n = len(setup.state["r"])
@@ -506,6 +578,8 @@ def run_reference(args):
     if args.workload == "tgv3d":
         setup = cases.make_case("tgv", dim=3, dx=2 * np.pi / nx, dtype=np.float32, tvf=1.0,
                                 viscosity=0.02)
+    elif args.workload == "ht3d":
+        setup = cases.make_case("ht", dim=3, dx=1.0 / nx, dtype=np.float32)
     else:
         setup = cases.make_case("tgv", dim=2, dx=1.0 / nx, dtype=np.float32, tvf=1.0)
     n = len(setup.state["r"])
@@ -538,7 +612,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="tgv3d", choices=["tgv3d", "tgv2d"])
+    ap.add_argument("--workload", default="tgv3d", choices=["tgv3d", "tgv2d", "ht3d"])
     ap.add_argument("--nx", type=int, default=256)
     ap.add_argument("--cpu-nx", type=int, default=32)
     ap.add_argument("--cpu-steps", type=int, default=3)

@@ -112,3 +112,35 @@ def test_engine_bytes_scale_with_features():
     # per-step neighbour lists: rows of 1.3 x 113 + 8 -> 160 uint16 entries + a count per particle
     lists = nbytes(tgv) - plain
     assert 160 * 2 * 100000 <= lists < (160 * 2 + 4 + 1) * 100000 + 4096
+
+
+def test_bench_ht3d_lattice_is_the_reference_case():
+    """bench.py's rank-local generator of BASELINE configs[4] (3D heated channel) produces the
+    particles, tags, fields, dt and bc / g_ext tables of the case setup (oracle.cases.make_case,
+    itself pinned against SimulationSetup.initialize by tests/test_reference_pins.py)."""
+    import bench
+    from oracle import cases
+
+    nx = 25
+    setup = cases.make_case("ht", dim=3, dx=1.0 / nx, dtype=np.float32, r0_noise_factor=0.0)
+    state, meta = bench.ht3d_state(nx)
+    assert len(state["r"]) == len(setup.state["r"]) == int(np.prod(meta["nxyz"]))
+    assert abs(meta["dt"] - setup.dt) <= 1e-12 * setup.dt
+    assert np.allclose(meta["box"], setup.box_size, rtol=1e-7)
+    assert meta["cfg_kwargs"]["bc_table"] == setup.bc_table
+    g1, g2 = meta["cfg_kwargs"]["g_ext_spec"], setup.g_ext_spec
+    assert g1["mode"] == g2["mode"] and g1["axis"] == g2["axis"] and np.allclose(g1["g"], g2["g"])
+    assert abs(g1["lo"] - g2["lo"]) < 1e-9 and abs(g1["hi"] - g2["hi"]) < 1e-9
+    assert abs(meta["p_bg"] - setup.p_bg) < 1e-12 and abs(meta["p_ref"] - setup.p_ref) < 1e-12
+
+    def order(r):  # same lattice, different enumeration order
+        q = np.rint(r * nx - 0.5).astype(np.int64)
+        return np.lexsort((q[:, 0], q[:, 1], q[:, 2]))
+
+    a, b = order(state["r"]), order(setup.state["r"])
+    for k in ("r", "tag", "u", "v", "rho", "p", "mass", "eta", "T", "kappa", "Cp", "dudt"):
+        x, y = state[k][a], setup.state[k][b]
+        assert np.allclose(x, y, rtol=0, atol=2e-7 * max(1.0, float(np.abs(y).max()))), k
+    # a slab's planes carry the ids of the full enumeration
+    sub, _ = bench.ht3d_state(nx, planes=np.arange(meta["nxyz"][2]) % 3 == 1)
+    assert len(np.unique(sub["ids"])) == len(sub["ids"]) < len(state["r"])
