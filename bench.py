@@ -166,6 +166,12 @@ def ht3d_meta(nx):
                    0.25 * (dx / (g_mag + eps)) ** 0.5))  # case_setup.py:94-97
     nxyz = [int(round(1.0 / dx)), int(round(0.2 / dx)) + 2 * n_walls, int(round(0.5 / dx))]
     box = [1.0, 0.2 + 2 * n_walls * dx, 0.5]
+    # (box / dx).round() of utils.py:51 must not put a lattice plane outside the periodic box
+    # (nx = 855: 0.5 / dx = 427.5 rounds to 428 planes, the last one at z > 0.5): such sizes are
+    # refused here instead of being reported later as SPHB200_ERR_OUTSIDE_BOX / _SLAB_OVERFLOW
+    if any(n * dx > b * (1 + 1e-9) for n, b in zip(nxyz, box)):
+        raise SystemExit(f"bench.py: ht3d nx={nx}: lattice {nxyz} does not fit the box {box}; "
+                         "pick nx with 0.5 * nx and 0.2 * nx away from half-integers (e.g. 854)")
     zero = [0.0, 0.0, 0.0]
     st = dict(u=zero, v=zero, zero_dudt=True, zero_dvdt=True, zero_dTdt=True)
     bc_table = {"tags": {1: dict(st, T=1.0), 3: dict(st, T=1.23)},  # SOLID_WALL, DIRICHLET_WALL
