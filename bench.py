@@ -169,7 +169,7 @@ def ht3d_meta(nx):
     # (box / dx).round() of utils.py:51 must not put a lattice plane outside the periodic box
     # (nx = 855: 0.5 / dx = 427.5 rounds to 428 planes, the last one at z > 0.5): such sizes are
     # refused here instead of being reported later as SPHB200_ERR_OUTSIDE_BOX / _SLAB_OVERFLOW
-    if any(n * dx > b * (1 + 1e-9) for n, b in zip(nxyz, box)):
+    if any((n - 0.5) * dx >= b * (1 - 1e-6) for n, b in zip(nxyz, box)):
         raise SystemExit(f"bench.py: ht3d nx={nx}: lattice {nxyz} does not fit the box {box}; "
                          "pick nx with 0.5 * nx and 0.2 * nx away from half-integers (e.g. 854)")
     zero = [0.0, 0.0, 0.0]
@@ -187,7 +187,8 @@ def ht3d_meta(nx):
 
 def ht3d_state(nx, planes=None):
     """Lattice state of ht3d_meta(nx): walls (3 layers below and above) and fluid on one regular
-    lattice (i + 0.5) dx, tags SOLID_WALL / DIRICHLET_WALL (hot patch |x - 0.5| < 0.25 of the
+    lattice (i + 0.5) dx (where H / dx is not an integer the reference leaves a sub-dx gap under
+    the top wall; the synthetic input keeps the lattice regular), tags SOLID_WALL / DIRICHLET_WALL (hot patch |x - 0.5| < 0.25 of the
     bottom wall, ht.py:90-97) / FLUID, fluid at rest, T = 1 (no position noise: lattice input)."""
     meta = ht3d_meta(nx)
     dx, (n0, n1, n2), nw = np.float32(meta["dx"]), meta["nxyz"], meta["n_walls"]
