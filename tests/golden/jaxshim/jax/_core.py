@@ -289,6 +289,30 @@ def install():
             return f
 
         setattr(torch.Tensor, name, make(orig, name))
+    # np.argsort(x) on an array object calls x.argsort(axis=..., kind=..., order=...): numpy's
+    # sort of a jax array is what the reference's tests rely on (stable for these sizes)
+    orig_argsort = torch.Tensor.argsort
+
+    def argsort(self, *a, axis=None, kind=None, order=None, stable=None, **kw):
+        if a or kw:
+            return orig_argsort(self, *a, stable=True, **kw)
+        return orig_argsort(self, dim=-1 if axis is None else axis, stable=True)
+
+    torch.Tensor.argsort = argsort
+    orig_transpose = torch.Tensor.transpose
+
+    def transpose(self, *axes):  # numpy / jax: x.transpose(1, 2, 0) or x.transpose((1, 2, 0))
+        if len(axes) == 1 and isinstance(axes[0], (tuple, list)):
+            axes = tuple(axes[0])
+        if len(axes) == 0:
+            return self.permute(*reversed(range(self.dim())))
+        if len(axes) == self.dim() and len(axes) != 2:
+            return self.permute(*axes)
+        if len(axes) == 2 and self.dim() == 2 and set(axes) == {0, 1}:
+            return self.permute(*axes)
+        return orig_transpose(self, *axes)
+
+    torch.Tensor.transpose = transpose
     orig_reshape = torch.Tensor.reshape
     torch.Tensor.ravel = lambda self: orig_reshape(self, -1)
     torch.Tensor.item_ = torch.Tensor.item
