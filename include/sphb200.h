@@ -63,8 +63,8 @@ extern "C" {
 /* ---- enums --------------------------------------------------------------- */
 /* solver.py:666-686.  DELTA (Marrone et al. 2011): velocity diffusion of acceleration_delta_fn
  * (solver.py:259-313) and, with SPHB200_F_RHO_EVOL, the renormalised density diffusion of
- * rho_evol_fn_delta (solver.py:33-105); the latter on the single-GPU engine only
- * (sphb200_slab_create returns SPHB200_EUNSUP for it). */
+ * rho_evol_fn_delta (solver.py:33-105; on a slab engine its three sweeps are separated by two
+ * more halo refreshes). */
 enum { SPHB200_SOLVER_SPH = 0, SPHB200_SOLVER_RIE = 1, SPHB200_SOLVER_DELTA = 2 };
 /* kernel.py: Quintic :51-72, Wendland C2 :75-103 (compile-time specialised sweeps), and
  * Cubic :26-48, Wendland C4 :106-134, C6 :137-165, Gaussian :168-182, SuperGaussian :185-201

@@ -23,7 +23,9 @@ constexpr unsigned FULL_MASK = 0xffffffffu;
 //   ge = (g_ext xyz, 0)  [only g_mode == ARRAY]             id = original particle index
 struct Frame {
   float4 *pt, *um, *vv, *st, *du, *dv, *nw, *ut, *ge;
-  float4 *dl, *dg;  // Delta-SPH density diffusion: renormalisation matrix rows [3n], gradient terms [2n]
+  // Delta-SPH density diffusion: rows of the renormalisation matrix L, gradient terms G (own
+  // use) and H (read from neighbours), one plane of n quads each
+  float4 *dl0, *dl1, *dl2, *dg0, *dg1;
   float2 *kc;
   int *id;
 };

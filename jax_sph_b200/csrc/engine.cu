@@ -98,6 +98,8 @@ struct sphb200_engine {
   cudaEvent_t ev_main, ev_side;
   bool overlap;       // side stream and events exist (slab engines)
   int pre_stage;      // stage whose interior tiles are already running on the side stream, -1
+  int delta_sub;      // slab engine, Delta-SPH density diffusion: next of its three sweeps
+  bool stage_more;    // forward_stage ran only part of the stage (another halo refresh first)
   // wall-normal recomputation for moving walls (utils.py:197-277): the static one-layer
   // discretisation of the wall surface; wl_n == 0: normals are an input that never changes
   float4* wl_pts;
@@ -614,21 +616,38 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
 #undef CALL
       }
     } else if (delta_on) {
-      // rho_evol_fn_delta (solver.py:36-103): L matrices (list builder), gradient terms, update
-      ex.nq = 2;
+      // rho_evol_fn_delta (solver.py:36-103): L matrices (list builder), gradient terms, update.
+      // A slab engine runs ONE of the three sweeps per call: the neighbours' L rows and H terms
+      // of the halo particles have to arrive in between (wrote = what to send next).
+      const int sub0 = e->slab_on ? e->delta_sub : 0, sub1 = e->slab_on ? e->delta_sub + 1 : 3;
+      for (int sub = sub0; sub < sub1 && !rc; ++sub) {
+        if (sub == 0) {
+          ex.nq = 2;
 #define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDelta<D, K, 0>, LIST_BUILD>, planD, F, ex, st, nl)
-      DISPATCH_DK(e, CALL);
+          DISPATCH_DK(e, CALL);
 #undef CALL
-      if (rc) return rc;
-      ex.nq = e->dim == 3 ? 5 : 3;
+        } else if (sub == 1) {
+          ex.nq = e->dim == 3 ? 5 : 3;
 #define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDelta<D, K, 1>, LIST_CONSUME>, planG, F, ex, st, nl)
-      DISPATCH_DK(e, CALL);
+          DISPATCH_DK(e, CALL);
 #undef CALL
-      if (rc) return rc;
-      ex.nq = 4;
+        } else {
+          ex.nq = 4;
 #define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDelta<D, K, 2>, LIST_CONSUME>, e->planC, F, ex, st, nl)
-      DISPATCH_DK(e, CALL);
+          DISPATCH_DK(e, CALL);
 #undef CALL
+        }
+      }
+      if (rc) return rc;
+      if (e->slab_on) {
+        if (e->delta_sub < 2) {
+          *wrote = e->delta_sub == 0 ? (HX_DL0 | (e->dim == 3 ? (HX_DL1 | HX_DL2) : 0)) : HX_DG1;
+          e->delta_sub++;
+          e->stage_more = true;
+          return SPHB200_OK;
+        }
+        e->delta_sub = 0;
+      }
     } else if (!rie) {
       ex.nq = 2;
 #define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_EVOL_SPH>, LIST_BUILD>, planD, F, ex, st, nl)
@@ -813,6 +832,8 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->launch_lo = e->launch_hi = -1;
   e->pre_stage = -1;
   e->overlap = false;
+  e->delta_sub = 0;
+  e->stage_more = false;
   int dev = 0;
   CK(cudaGetDevice(&dev));
   int maxs = 0;
@@ -845,8 +866,14 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
     F.nw = e->has_nw ? (float4*)(e->arena + L.frame[f][8]) : nullptr;
     F.ge = e->has_ge ? (float4*)(e->arena + L.frame[f][9]) : nullptr;
     F.ut = e->has_ut ? (float4*)(e->arena + L.ut) : nullptr;
-    F.dl = L.dl != (size_t)-1 ? (float4*)(e->arena + L.dl) : nullptr;
-    F.dg = L.dg != (size_t)-1 ? (float4*)(e->arena + L.dg) : nullptr;
+    F.dl0 = F.dl1 = F.dl2 = F.dg0 = F.dg1 = nullptr;
+    if (L.dl != (size_t)-1) {  // planes of n quads
+      F.dl0 = (float4*)(e->arena + L.dl);
+      F.dl1 = F.dl0 + n;
+      F.dl2 = F.dl1 + n;
+      F.dg0 = (float4*)(e->arena + L.dg);
+      F.dg1 = F.dg0 + n;
+    }
   }
   e->key = (int*)(e->arena + L.key);
   e->rnk = (int*)(e->arena + L.rnk);
@@ -1339,8 +1366,6 @@ int sphb200_slab_create(const sphb200_config* cfg, int rank, int nranks, int64_t
   int rc = validate(cfg, 1);
   if (rc) return rc;
   if (!out) return SPHB200_EINVAL;
-  // the Delta-SPH density diffusion needs two more halo refreshes (L, gradient terms): next
-  if (cfg->solver == SPHB200_SOLVER_DELTA && (cfg->flags & SPHB200_F_RHO_EVOL)) return SPHB200_EUNSUP;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SPHB200_ENODEV;
   SlabSpec sp;
@@ -1453,6 +1478,9 @@ static int prelaunch_interior(sphb200_engine* e, int stage, cudaStream_t st) {
   // per-pass event timing (sphb200_engine_profile) measures the sweeps whole, on one stream
   if (!e->overlap || e->profile || (stage != 0 && stage != 3) || e->int_hi <= e->int_lo)
     return SPHB200_OK;
+  // the three sweeps of the Delta-SPH density diffusion need their own halo refreshes
+  if (stage == 0 && e->cfg.solver == SPHB200_SOLVER_DELTA && (e->cfg.flags & SPHB200_F_RHO_EVOL))
+    return SPHB200_OK;
   CK(cudaEventRecord(e->ev_main, st));
   CK(cudaStreamWaitEvent(e->side, e->ev_main, 0));
   int wrote = 0;
@@ -1512,6 +1540,7 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
     if (e->profile) cudaEventRecord(e->ev[2], st);
     e->slab_pending_mask = mask;
     e->slab_stage = 0;
+    e->delta_sub = 0;
     *xbytes = (int64_t)halo_bytes(mask, sg.halo_cap, sg.ncl);
     return prelaunch_interior(e, next_effective_stage(e, 0), st);
   }
@@ -1532,7 +1561,8 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
   }
   while (e->slab_stage < 4) {
     int wrote = 0;
-    const int stage = e->slab_stage++;
+    const int stage = e->slab_stage;
+    e->stage_more = false;
     int part = 0;
     if (e->pre_stage == stage) {  // its interior tiles ran on the side stream during the exchange
       CK(cudaStreamWaitEvent(st, e->ev_side, 0));
@@ -1541,6 +1571,7 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
     }
     int rc = forward_stage(e, stage, e->slab_flags, e->slab_v_is_u, st, &wrote, part);
     if (rc) return rc;
+    if (!e->stage_more) e->slab_stage++;
     if (wrote && stage < 3) {
       k_halo_pack<<<dim3(hblocks, 2), 256, 0, st>>>(sl, sg, e->fr[e->cur], wrote, e->start,
                                                     (char*)send_lo, (char*)send_hi, e->err);
@@ -1548,7 +1579,7 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
       CK(cudaGetLastError());
       e->slab_pending_mask = wrote;
       *xbytes = (int64_t)halo_bytes(wrote, sg.halo_cap, sg.ncl);
-      return prelaunch_interior(e, next_effective_stage(e, stage + 1), st);
+      return prelaunch_interior(e, next_effective_stage(e, e->slab_stage), st);
     }
   }
   if (e->profile) cudaEventRecord(e->ev[5], st);

@@ -199,16 +199,16 @@ struct PhysDelta {
     sq[cap + d] = make_float4(um.w / st.x, st.x, 0.f, 0.f);  // V_j = m_j / rho_j (:44-45), rho_j
     if (STEP == 1) {
       if (DIM == 3) {
-        sq[2 * cap + d] = f.dl[3 * gp];
-        sq[3 * cap + d] = f.dl[3 * gp + 1];
-        sq[4 * cap + d] = f.dl[3 * gp + 2];
+        sq[2 * cap + d] = f.dl0[gp];
+        sq[3 * cap + d] = f.dl1[gp];
+        sq[4 * cap + d] = f.dl2[gp];
       } else {
-        sq[2 * cap + d] = f.dl[3 * gp];
+        sq[2 * cap + d] = f.dl0[gp];
       }
     }
     if (STEP == 2) {
       sq[2 * cap + d] = um;
-      sq[3 * cap + d] = f.dg[2 * gp + 1];
+      sq[3 * cap + d] = f.dg1[gp];
     }
   }
   __device__ static void load_own(const Consts&, const Frame& f, const Extra&, int p, float4,
@@ -218,9 +218,9 @@ struct PhysDelta {
     o.V = um.w / st.x;
     o.u[0] = um.x; o.u[1] = um.y; o.u[2] = um.z;
     if (STEP == 1) {
-      const float4 a = f.dl[3 * p];
+      const float4 a = f.dl0[p];
       if (DIM == 3) {
-        const float4 b = f.dl[3 * p + 1], cc = f.dl[3 * p + 2];
+        const float4 b = f.dl1[p], cc = f.dl2[p];
         o.L[0] = a.x; o.L[1] = a.y; o.L[2] = a.z;
         o.L[3] = b.x; o.L[4] = b.y; o.L[5] = b.z;
         o.L[6] = cc.x; o.L[7] = cc.y; o.L[8] = cc.z;
@@ -229,7 +229,7 @@ struct PhysDelta {
       }
     }
     if (STEP == 2) {
-      const float4 g = f.dg[2 * p];
+      const float4 g = f.dg0[p];
       o.G[0] = g.x; o.G[1] = g.y; o.G[2] = g.z;
     }
   }
@@ -312,22 +312,22 @@ struct PhysDelta {
       if (DIM == 2) {
         const float idet = 1.0f / (m[0] * m[3] - m[1] * m[2]);
         L[0] = m[3] * idet; L[1] = -m[1] * idet; L[2] = -m[2] * idet; L[3] = m[0] * idet;
-        f.dl[3 * p] = make_float4(L[0], L[1], L[2], L[3]);
+        f.dl0[p] = make_float4(L[0], L[1], L[2], L[3]);
       } else {
         const float c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8],
                     c02 = m[3] * m[7] - m[4] * m[6];
         const float idet = 1.0f / (m[0] * c00 + m[1] * c01 + m[2] * c02);
-        f.dl[3 * p] = make_float4(c00 * idet, (m[2] * m[7] - m[1] * m[8]) * idet,
+        f.dl0[p] = make_float4(c00 * idet, (m[2] * m[7] - m[1] * m[8]) * idet,
                                   (m[1] * m[5] - m[2] * m[4]) * idet, 0.f);
-        f.dl[3 * p + 1] = make_float4(c01 * idet, (m[0] * m[8] - m[2] * m[6]) * idet,
+        f.dl1[p] = make_float4(c01 * idet, (m[0] * m[8] - m[2] * m[6]) * idet,
                                       (m[2] * m[3] - m[0] * m[5]) * idet, 0.f);
-        f.dl[3 * p + 2] = make_float4(c02 * idet, (m[1] * m[6] - m[0] * m[7]) * idet,
+        f.dl2[p] = make_float4(c02 * idet, (m[1] * m[6] - m[0] * m[7]) * idet,
                                       (m[0] * m[4] - m[1] * m[3]) * idet, 0.f);
       }
     }
     if (STEP == 1) {
-      f.dg[2 * p] = make_float4(a.m[0], a.m[1], a.m[2], 0.f);
-      f.dg[2 * p + 1] = make_float4(a.m[3], a.m[4], a.m[5], 0.f);
+      f.dg0[p] = make_float4(a.m[0], a.m[1], a.m[2], 0.f);
+      f.dg1[p] = make_float4(a.m[3], a.m[4], a.m[5], 0.f);
     }
     if (STEP == 2) {
       const float4 st = f.st[p];

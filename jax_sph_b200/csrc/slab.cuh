@@ -24,21 +24,24 @@ namespace sphb200 {
 
 // which arrays a halo message carries
 enum {
-  HX_PT = 1, HX_UM = 2, HX_VV = 4, HX_ST = 8, HX_NW = 16, HX_GE = 32, HX_UT = 64, HX_KC = 128,
-  HX_CELLS = 256
+  HX_PT = 1, HX_UM = 2, HX_VV = 4, HX_ST = 8, HX_NW = 16, HX_GE = 32, HX_UT = 64,
+  HX_DL0 = 128, HX_DL1 = 256, HX_DL2 = 512,  // Delta-SPH renormalisation matrix rows
+  HX_DG1 = 1024,                              // Delta-SPH gradient term H (read from neighbours)
+  HX_KC = 2048, HX_CELLS = 4096
 };
+constexpr int HX_NQ = 11;  // quad arrays a message can carry (bits 0 .. HX_NQ-1)
 
 struct HaloView {
   int* hdr;     // [count, ...]
   int* cells;   // per-cell particle counts of the S layers (HX_CELLS)
-  float4* q[7]; // pt um vv st nw ge ut, nullptr when not carried
+  float4* q[HX_NQ]; // pt um vv st nw ge ut dl0 dl1 dl2 dg1, nullptr when not carried
   float2* kc;
 };
 
 __host__ __device__ inline size_t halo_bytes(int mask, int cap, int ncl) {
   size_t b = 16;
   if (mask & HX_CELLS) b += ((size_t)ncl * 4 + 15) / 16 * 16;
-  for (int i = 0; i < 7; ++i)
+  for (int i = 0; i < HX_NQ; ++i)
     if (mask & (1 << i)) b += (size_t)cap * 16;
   if (mask & HX_KC) b += (size_t)cap * 8;
   return b;
@@ -53,7 +56,7 @@ __host__ __device__ inline HaloView halo_view(char* b, int mask, int cap, int nc
     v.cells = reinterpret_cast<int*>(p);
     p += ((size_t)ncl * 4 + 15) / 16 * 16;
   }
-  for (int i = 0; i < 7; ++i) {
+  for (int i = 0; i < HX_NQ; ++i) {
     v.q[i] = nullptr;
     if (mask & (1 << i)) {
       v.q[i] = reinterpret_cast<float4*>(p);
@@ -72,7 +75,11 @@ __device__ __forceinline__ float4* frame_quad(const Frame& f, int i) {
     case 3: return f.st;
     case 4: return f.nw;
     case 5: return f.ge;
-    default: return f.ut;
+    case 6: return f.ut;
+    case 7: return f.dl0;
+    case 8: return f.dl1;
+    case 9: return f.dl2;
+    default: return f.dg1;
   }
 }
 
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(256) k_halo_pack(Slab sl, SlabGeom sg, Frame f
   if (mask & HX_CELLS)
     for (int j = tid; j < sg.ncl; j += nth) v.cells[j] = start[c0 + j + 1] - start[c0 + j];
 #pragma unroll
-  for (int a = 0; a < 7; ++a) {
+  for (int a = 0; a < HX_NQ; ++a) {
     if (!(mask & (1 << a))) continue;
     const float4* src = frame_quad(f, a) + s0;
     for (int i = tid; i < n; i += nth) v.q[a][i] = src[i];
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(256) k_halo_unpack(Slab sl, SlabGeom sg, Frame
   if (up && dst0 + n > sg.cap_total) return;  // flagged by k_halo_cells
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
 #pragma unroll
-  for (int a = 0; a < 7; ++a) {
+  for (int a = 0; a < HX_NQ; ++a) {
     if (!(mask & (1 << a))) continue;
     float4* dst = frame_quad(f, a) + dst0;
     for (int i = tid; i < n; i += nth) dst[i] = v.q[a][i];

@@ -164,10 +164,6 @@ def test_error_behaviour():
         eng.upload({"r": setup.state["r"][:-1]})
     with pytest.raises(_lib.Sphb200Error, match="not supported"):
         make_config(2, [1.0, 1.0], 0.05, 0.0, solver="GSPH")
-    with pytest.raises(_lib.Sphb200Error, match="unsupported"):  # DELTA density diffusion: no slabs yet
-        from jax_sph_b200 import SlabEngine
-
-        SlabEngine(make_config(2, [1.0, 1.0], 0.05, 0.0, solver="DELTA", is_rho_evol=True), 0, 2)
     with pytest.raises(_lib.Sphb200Error, match="not supported"):
         make_config(2, [1.0, 1.0], 0.05, 0.0, kernel="M4")
     # positions outside the periodic box are reported through the device error word

@@ -23,6 +23,11 @@ CASES = {
     "ht3d": (dict(case="ht", dim=3, dx=0.02), [2]),
     "cf2d_free_slip": (dict(case="cf", dim=2, dx=0.02, free_slip=True), [3]),
     "db2d_renorm": (dict(case="db", dim=2, dx=0.02, density_renormalize=True), [2]),
+    # Delta-SPH density diffusion: two more halo refreshes per step (L rows, gradient terms)
+    "tgv3d_delta": (dict(case="tgv", dim=3, dx=2 * np.pi / 24, solver="DELTA", density_evolution=True,
+                         viscosity=0.02), [2]),
+    "db2d_delta": (dict(case="db", dim=2, dx=0.02, solver="DELTA", gamma=7.0, artificial_alpha=0.0),
+                   [3]),
 }
 KEYS = ("r", "u", "v", "rho", "p", "T", "dudt", "dvdt", "drhodt", "dTdt")
 
