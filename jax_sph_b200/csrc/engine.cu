@@ -89,9 +89,6 @@ struct sphb200_engine {
   Kick slab_kick;
   // Slab overlap: while a halo message is in flight the INTERIOR tile layers of the next big
   // sweep (density or force; tiles whose stencil touches no halo layer) run on a side stream.
-  // launch_lo/hi: tile-layer range (along the slab axis) of the sweep launches in progress,
-  // -1 = all tiles.
-  int launch_lo, launch_hi;
   int part;            // 0: all tiles, 1: interior tile layers only, 2: boundary tile layers only
   int int_lo, int_hi;  // interior tile layers [int_lo, int_hi) along the slab axis
   cudaStream_t side;
@@ -829,7 +826,6 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->slab_stage = 0;
   e->slab_pending_mask = 0;
   e->part = 0;
-  e->launch_lo = e->launch_hi = -1;
   e->pre_stage = -1;
   e->overlap = false;
   e->delta_sub = 0;
