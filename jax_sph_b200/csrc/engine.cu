@@ -580,7 +580,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
   const SweepPlan planD = !evol ? (dens_extras ? e->planW : e->planA) : (!rie ? e->planR : e->planW);
   // neighbour lists: built by the density sweep, consumed by every later sweep of this step
   NList nl{e->pl_list, e->pl_cnt, e->pl_ok, e->pl_lmax, 0};
-  const SweepPlan planG = plan_sweep(e, e->dim == 3 ? 5 : 3, 24);  // PhysDelta<1>
+  const SweepPlan planG = plan_sweep(e, e->dim == 3 ? 4 : 2, 24);  // PhysDelta<1>
   {
     int mc = planD.cap < planF.cap ? planD.cap : planF.cap;
     if (delta_on && evol) {
@@ -619,17 +619,17 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
       const int sub0 = e->slab_on ? e->delta_sub : 0, sub1 = e->slab_on ? e->delta_sub + 1 : 3;
       for (int sub = sub0; sub < sub1 && !rc; ++sub) {
         if (sub == 0) {
-          ex.nq = 2;
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDelta<D, K, 0>, LIST_BUILD>, planD, F, ex, st, nl)
+          ex.nq = 1;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDelta<D, K, 0>, LIST_BUILD>, e->planA, F, ex, st, nl)
           DISPATCH_DK(e, CALL);
 #undef CALL
         } else if (sub == 1) {
-          ex.nq = e->dim == 3 ? 5 : 3;
+          ex.nq = e->dim == 3 ? 4 : 2;
 #define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDelta<D, K, 1>, LIST_CONSUME>, planG, F, ex, st, nl)
           DISPATCH_DK(e, CALL);
 #undef CALL
         } else {
-          ex.nq = 4;
+          ex.nq = 3;
 #define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDelta<D, K, 2>, LIST_CONSUME>, e->planC, F, ex, st, nl)
           DISPATCH_DK(e, CALL);
 #undef CALL

@@ -180,9 +180,14 @@ struct PhysDensity {
 // All three read the INCOMING rho; only STEP 2 writes (into the other frame's st).
 template <int DIM, int KERN, int STEP>
 struct PhysDelta {
-  static constexpr int MINB = 1;
+  static constexpr int MINB = STEP == 0 ? 2 : 1;
   static constexpr bool SENDER_VIEW = false;
-  static constexpr int LQ = DIM == 3 ? 3 : 1;  // quads of one staged L matrix
+  // Staged records, packed so that the stencil of a tile fits ONE staging group (a tile whose
+  // stencil does not fit gets no shared neighbour lists and every sweep searches on its own):
+  //   STEP 0           (x, y, z, V)                                                  16 B
+  //   STEP 1  3D       (x, y, z, V) (L00 L01 L02 rho) (L10 L11 L12 L20) (L21 L22 - -) 64 B
+  //           2D       (x, y, rho, V) (L00 L01 L10 L11)                               32 B
+  //   STEP 2           (x, y, z, tag) (u, V) (H, rho)                                 48 B
   struct Own {
     float rho, V;
     float u[3], G[3];
@@ -191,24 +196,30 @@ struct PhysDelta {
   struct Acc {
     float m[9];  // STEP 0: M;  STEP 1: G (0..2), H (3..5);  STEP 2: diff (0), cont (1)
   };
-  __host__ __device__ static int nq() { return STEP == 0 ? 2 : (STEP == 1 ? 2 + LQ : 4); }
+  __host__ __device__ static int nq() { return STEP == 0 ? 1 : (STEP == 1 ? (DIM == 3 ? 4 : 2) : 3); }
   __device__ static void stage(const Consts&, const Frame& f, const Extra&, int gp, float4* sq,
                                int cap, int d) {
-    sq[d] = f.pt[gp];
-    const float4 um = f.um[gp], st = f.st[gp];
-    sq[cap + d] = make_float4(um.w / st.x, st.x, 0.f, 0.f);  // V_j = m_j / rho_j (:44-45), rho_j
+    const float4 pt = f.pt[gp], um = f.um[gp], st = f.st[gp];
+    const float V = um.w / st.x;  // V_j = m_j / rho_j (:44-45)
+    if (STEP == 0) sq[d] = make_float4(pt.x, pt.y, pt.z, V);
     if (STEP == 1) {
+      const float4 l0 = f.dl0[gp];
       if (DIM == 3) {
-        sq[2 * cap + d] = f.dl0[gp];
-        sq[3 * cap + d] = f.dl1[gp];
-        sq[4 * cap + d] = f.dl2[gp];
+        const float4 l1 = f.dl1[gp], l2 = f.dl2[gp];
+        sq[d] = make_float4(pt.x, pt.y, pt.z, V);
+        sq[cap + d] = make_float4(l0.x, l0.y, l0.z, st.x);
+        sq[2 * cap + d] = make_float4(l1.x, l1.y, l1.z, l2.x);
+        sq[3 * cap + d] = make_float4(l2.y, l2.z, 0.f, 0.f);
       } else {
-        sq[2 * cap + d] = f.dl0[gp];
+        sq[d] = make_float4(pt.x, pt.y, st.x, V);  // the 2D sweeps never read the z slot
+        sq[cap + d] = l0;
       }
     }
     if (STEP == 2) {
-      sq[2 * cap + d] = um;
-      sq[3 * cap + d] = f.dg1[gp];
+      const float4 h = f.dg1[gp];
+      sq[d] = pt;
+      sq[cap + d] = make_float4(um.x, um.y, um.z, V);
+      sq[2 * cap + d] = make_float4(h.x, h.y, h.z, st.x);
     }
   }
   __device__ static void load_own(const Consts&, const Frame& f, const Extra&, int p, float4,
@@ -254,25 +265,27 @@ struct PhysDelta {
     const float dist = fsqrt(d2);
     const float gw = kernel_gw<KERN>(c, dist);
     const float id = frcp(dist + c.eps);
-    const float4 q1 = sq[cap + j];
-    const float V_j = q1.x, rho_j = q1.y;
     float kg[3] = {gw * (dr[0] * id), gw * (dr[1] * id), DIM == 3 ? gw * (dr[2] * id) : 0.f};  // :42-43
     if (STEP == 0) {
+      const float V_j = pj.w;
 #pragma unroll
       for (int r = 0; r < DIM; ++r)
 #pragma unroll
         for (int s = 0; s < DIM; ++s) a.m[r * DIM + s] += (-dr[r]) * (kg[s] * V_j);  // :49-50
     }
     if (STEP == 1) {
-      float Lj[9];
-      const float4 l0 = sq[2 * cap + j];
+      const float V_j = pj.w;
+      float Lj[9], rho_j;
+      const float4 l0 = sq[cap + j];
       if (DIM == 3) {
-        const float4 l1 = sq[3 * cap + j], l2 = sq[4 * cap + j];
+        const float4 l1 = sq[2 * cap + j], l2 = sq[3 * cap + j];
         Lj[0] = l0.x; Lj[1] = l0.y; Lj[2] = l0.z;
+        rho_j = l0.w;
         Lj[3] = l1.x; Lj[4] = l1.y; Lj[5] = l1.z;
-        Lj[6] = l2.x; Lj[7] = l2.y; Lj[8] = l2.z;
+        Lj[6] = l1.w; Lj[7] = l2.x; Lj[8] = l2.y;
       } else {
         Lj[0] = l0.x; Lj[1] = l0.y; Lj[2] = l0.z; Lj[3] = l0.w;
+        rho_j = pj.z;
       }
       const float xj[3] = {kg[0] * V_j, kg[1] * V_j, kg[2] * V_j};
       const float xi[3] = {kg[0] * o.V, kg[1] * o.V, kg[2] * o.V};
@@ -287,7 +300,8 @@ struct PhysDelta {
       }
     }
     if (STEP == 2) {
-      const float4 uj = sq[2 * cap + j], hj = sq[3 * cap + j];
+      const float4 uj = sq[cap + j], hj = sq[2 * cap + j];
+      const float V_j = uj.w, rho_j = hj.w;
       const float idd = frcp((dist + c.eps) * (dist + c.eps));
       const float two_d = 2.0f * (rho_j - o.rho);
       const float H[3] = {hj.x, hj.y, hj.z};

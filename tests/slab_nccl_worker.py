@@ -26,7 +26,10 @@ def main():
     nsteps = 40
     for kw in (dict(case="tgv", dim=2, dx=0.0125, tvf=1.0),
                dict(case="tgv", dim=3, dx=2 * np.pi / 32, tvf=1.0, viscosity=0.02),
-               dict(case="ht", dim=3, dx=0.02)):
+               dict(case="ht", dim=3, dx=0.02),
+               # Delta-SPH density diffusion: five exchanges per step
+               dict(case="tgv", dim=3, dx=2 * np.pi / 32, solver="DELTA", density_evolution=True,
+                    viscosity=0.02)):
         setup = cases.make_case(dtype=np.float32, **kw)
         n = len(setup.state["r"])
         eng = SlabEngine(config_from_setup(setup))
