@@ -138,6 +138,26 @@ void slab_range(int ng, int r, int p, int& z0, int& z1) {
   z1 = (int)((long long)ng * (r + 1) / p);
 }
 
+// Largest record (bytes per staged particle) any sweep of this solver variant stages: the
+// records of phys.cuh (PhysDensity / PhysDelta / PhysRenorm / PhysWall / PhysForce).
+int max_stage_bytes(const sphb200_config& c) {
+  const bool rie = c.solver == SPHB200_SOLVER_RIE, delta = c.solver == SPHB200_SOLVER_DELTA;
+  const bool bc_trick = c.flags & SPHB200_F_BC_TRICK, evol = c.flags & SPHB200_F_RHO_EVOL,
+             renorm = c.flags & SPHB200_F_RHO_RENORM, free_slip = c.flags & SPHB200_F_FREE_SLIP,
+             heat = c.flags & SPHB200_F_HEAT;
+  const bool has_ut = rie && bc_trick && !free_slip;
+  int m = !evol ? ((has_ut || (rie && bc_trick && heat)) ? 48 : 16)
+                : (delta ? (c.dim == 3 ? 64 : 48) : (!rie ? 32 : 64));
+  const int force_nq = 3 + ((!rie && c.tvf != 0.0) ? 1 : 0) + (heat ? 1 : 0) + (rie ? 1 : 0) +
+                       (has_ut ? 1 : 0);
+  const bool generic = rie || heat || c.artificial_alpha != 0.0 || delta;
+  const int force = generic ? 16 * force_nq : (c.tvf != 0.0 ? 52 : 40);
+  if (force > m) m = force;
+  if (bc_trick && !rie && 64 > m) m = 64;  // PhysWall
+  if (evol && renorm && 32 > m) m = 32;    // PhysRenorm
+  return m;
+}
+
 // Cell grid, stencil and tiling (host).  nranks > 1: the local view of rank `rank`.
 void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nranks = 1) {
   const double cutoff = kernel_cutoff(c);
@@ -183,6 +203,15 @@ void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nran
     return rows * nxs;
   };
   while (t0 > 1 && entries(t0) > MAX_SOFF) --t0;
+  if (c.tile[0] <= 0) {
+    // The step's shared neighbour lists need the tile's stencil to fit ONE staging group of the
+    // sweep with the largest record (sweep.cuh, NList): shorten the tile until the expected
+    // stencil population (+8 % for disorder) fits what 227 KB of shared memory hold next to the
+    // minimum per-thread lists.
+    const double fit = ((227.0 * 1024 - 1024) - (double)sweep_smem_bytes(0, 0, 24, tpb)) /
+                       max_stage_bytes(c);
+    while (t0 > 2 && entries(t0) * pop * 1.08 > fit) --t0;
+  }
   g.T[0] = t0;
   for (int a = 0; a < 3; ++a) {
     g.goff[a] = 0;

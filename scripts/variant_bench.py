@@ -17,6 +17,8 @@ VARIANTS = {
     "RIE+evol": dict(tvf=0.0, solver="RIE", is_rho_evol=True),
     "DELTA": dict(tvf=0.0, solver="DELTA"),
     "DELTA+evol": dict(tvf=0.0, solver="DELTA", is_rho_evol=True),
+    # 80-byte force record: the tile is shortened so that the shared neighbour lists survive
+    "SPH+tvf+heat": dict(tvf=1.0, is_heat_conduction=True),
 }
 
 
@@ -24,6 +26,8 @@ def main():
     for workload, nx in (("tgv2d", 1000), ("tgv3d", 160)):
         state, meta = lattice_state(workload, nx)
         n, dim = len(state["r"]), meta["dim"]
+        state["kappa"] = state["rho"] * 7.313
+        state["Cp"] = state["rho"] * 305.27
         pinned = {k: torch.from_numpy(v).pin_memory() for k, v in state.items()}
         for name, kw in VARIANTS.items():
             kw = dict(kw)
@@ -40,7 +44,7 @@ def main():
                 eng.step(meta["dt"], 1)
                 for k, v in eng.last_times().items():
                     acc[k] = acc.get(k, 0.0) + v / steps
-            print(f"{workload} N={n} {name:10s}: " + " ".join(f"{k}={v:.3f}" for k, v in acc.items())
+            print(f"{workload} N={n} {name:12s} tile={eng.plan()['tile']}: " + " ".join(f"{k}={v:.3f}" for k, v in acc.items())
                   + f" | {n / acc['total'] / 1e3:.1f} M upd/s err={eng.error()}", flush=True)
             eng.close()
             del eng
