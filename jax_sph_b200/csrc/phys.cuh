@@ -37,6 +37,8 @@ template <int DIM, int KERN, int MODE>
 struct PhysDensity {
   static constexpr int MINB = (MODE == DENS_EVOL_RIE) ? 1 : 2;
   static constexpr bool SENDER_VIEW = false;
+  // builder phase 2 takes two survivors per trip (sweep.cuh); heavy pair() bodies opt out
+  static constexpr bool PAIR2 = MODE != DENS_EVOL_RIE;
   static constexpr bool SUM = MODE == DENS_SUM || MODE == DENS_SUM_X;
   static constexpr bool XTRA = MODE == DENS_SUM_X || MODE == DENS_EVOL_RIE;
   struct Own {
@@ -182,6 +184,8 @@ template <int DIM, int KERN, int STEP>
 struct PhysDelta {
   static constexpr int MINB = STEP == 0 ? 2 : 1;
   static constexpr bool SENDER_VIEW = false;
+  // builder phase 2 takes two survivors per trip (sweep.cuh); heavy pair() bodies opt out
+  static constexpr bool PAIR2 = true;
   // Staged records, packed so that the stencil of a tile fits ONE staging group (a tile whose
   // stencil does not fit gets no shared neighbour lists and every sweep searches on its own):
   //   STEP 0           (x, y, z, V)                                                  16 B
@@ -360,6 +364,8 @@ template <int DIM, int KERN>
 struct PhysRenorm {
   static constexpr int MINB = 2;
   static constexpr bool SENDER_VIEW = false;
+  // builder phase 2 takes two survivors per trip (sweep.cuh); heavy pair() bodies opt out
+  static constexpr bool PAIR2 = true;
   struct Own {};
   struct Acc {
     float num, den;
@@ -394,6 +400,8 @@ template <int DIM, int KERN>
 struct PhysWall {
   static constexpr int MINB = 1;
   static constexpr bool SENDER_VIEW = false;
+  // builder phase 2 takes two survivors per trip (sweep.cuh); heavy pair() bodies opt out
+  static constexpr bool PAIR2 = true;
   struct Own {
     int tag;
   };
@@ -497,6 +505,8 @@ template <int DIM, int KERN, int SOLVER, int FEAT>
 struct PhysForce {
   static constexpr int MINB = 1;
   static constexpr bool SENDER_VIEW = false;
+  // builder phase 2 takes two survivors per trip (sweep.cuh); heavy pair() bodies opt out
+  static constexpr bool PAIR2 = true;
   struct Own {
     float u[3], dvu[3], g[3];
     float rho, p, eta, eta2, inv_m, V2, T, kappa, Cp;
@@ -770,6 +780,8 @@ template <int DIM>
 struct PhysNeighbors {
   static constexpr int MINB = 2;
   static constexpr bool SENDER_VIEW = true;
+  // builder phase 2 takes two survivors per trip (sweep.cuh); heavy pair() bodies opt out
+  static constexpr bool PAIR2 = true;
   struct Own {
     int id;
     long long off;

@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
           // ---------------- phase 2: real neighbours, exact arithmetic ----------------
           int m = carry;
           int k = carry;
-          if (LM == LIST_BUILD) {
+          if (LM == LIST_BUILD && P::PAIR2) {
             // the list builder takes two survivors per trip (both loaded before the first
             // in-place compaction store, which the compiler must otherwise order against
             // every later load): two independent LDS -> displacement -> kernel chains
