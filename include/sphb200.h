@@ -268,6 +268,40 @@ int sphb200_slab_run(sphb200_engine *e, int phase, double dt, uint32_t flags, vo
                      void *send_hi, const void *recv_lo, const void *recv_hi, void *stream,
                      int64_t *xbytes);
 
+/* ---- on-device case initialisation ----------
+ * Replaces the host-side lattice generators pos_init_cartesian_2d / _3d
+ * (jax_sph/utils.py:35-54), the velocity initialisation of cases/tgv.py:37-51 and the uniform
+ * field setup of SimulationSetup.initialize() (jax_sph/case_setup.py:152-181) for the
+ * regular-lattice cases: at 16-64 M particles the NumPy meshgrid / vstack and the host-to-device
+ * copy of the full state take seconds, the kernel a fraction of a millisecond.
+ *   row order   = np.meshgrid(range(n0), range(n1)[, range(n2)], indexing="xy") ravelled
+ *                 (utils.py:41,52): row = (iy * n0 + ix) * n2 + iz in 3D, iy * n0 + ix in 2D;
+ *   position    = (i + 0.5) * dx per axis, float32 (utils.py:42,53);
+ *   planes      = [k_lo, k_hi) of the LAST axis only (one rank's slab); rows are then counted
+ *                 within the slab and `ids` (optional) receives the full-lattice row of each;
+ *   walls       = the n_walls outer planes on both sides of wall_axis get SPHB200_TAG_SOLID_WALL;
+ *                 lower-wall particles with hot_lo < x < hot_hi get SPHB200_TAG_DIRICHLET_WALL and
+ *                 T_hot (cases/ht.py:90-97, :154-187); wall_axis = -1: no walls;
+ *   velocity    = u = v = the selected field evaluated at the position (fluid particles only). */
+enum { SPHB200_VEL_REST = 0, SPHB200_VEL_TGV2D = 1, SPHB200_VEL_TGV3D = 2 };
+
+typedef struct sphb200_lattice {
+  uint32_t struct_size; /* = sizeof(sphb200_lattice) */
+  int32_t dim;
+  int32_t n[3];       /* planes per axis = round(box / dx), utils.py:40,51 */
+  int32_t k_lo, k_hi; /* planes of the last axis; 0, n[dim - 1] = the whole lattice */
+  int32_t velocity;   /* SPHB200_VEL_* */
+  int32_t wall_axis, n_walls;
+  float hot_lo, hot_hi, T_hot;
+  float dx, rho, p, mass, eta, T, kappa, Cp; /* uniform fields, case_setup.py:152-181 */
+} sphb200_lattice;
+
+/* Rows sphb200_init_lattice writes (n0 * n1 * (k_hi - k_lo) in 3D), or a negative code. */
+int64_t sphb200_lattice_rows(const sphb200_lattice *l);
+/* Fill a state in the reference layout, DEVICE pointers; NULL members are skipped; dudt, dvdt,
+ * drhodt, dTdt, nw are zeroed.  `ids` (int32, device) may be NULL. */
+int sphb200_init_lattice(const sphb200_lattice *l, sphb200_state *out, int32_t *ids, void *stream);
+
 /* ---- stateless entry points (device pointers, caller-owned workspace) ----- */
 int sphb200_workspace_bytes(const sphb200_config *cfg, int64_t n, size_t *bytes);
 int sphb200_neighbor_list(const sphb200_config *cfg, int64_t n, const float *r, int32_t *idx,

@@ -24,6 +24,7 @@ G_NONE, G_CONST, G_BAND, G_ARRAY = 0, 1, 2, 3
 BC_SET_U, BC_SET_V, BC_ZERO_DUDT, BC_ZERO_DVDT, BC_SET_P, BC_SET_T, BC_ZERO_DTDT = (
     1, 2, 4, 8, 16, 32, 64)
 STEP_INTEGRATE, STEP_BC = 1, 2
+VEL_REST, VEL_TGV2D, VEL_TGV3D = 0, 1, 2
 
 VECTOR_FIELDS = ("r", "u", "v", "dudt", "dvdt", "nw")
 SCALAR_FIELDS = ("rho", "p", "drhodt", "mass", "eta", "T", "dTdt", "kappa", "Cp")
@@ -59,6 +60,17 @@ class State(C.Structure):
                 + [("tag", C.c_void_p), ("g_ext", C.c_void_p)])
 
 
+class Lattice(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("dim", C.c_int32), ("n", C.c_int32 * 3),
+        ("k_lo", C.c_int32), ("k_hi", C.c_int32), ("velocity", C.c_int32),
+        ("wall_axis", C.c_int32), ("n_walls", C.c_int32),
+        ("hot_lo", C.c_float), ("hot_hi", C.c_float), ("T_hot", C.c_float),
+        ("dx", C.c_float), ("rho", C.c_float), ("p", C.c_float), ("mass", C.c_float),
+        ("eta", C.c_float), ("T", C.c_float), ("kappa", C.c_float), ("Cp", C.c_float),
+    ]
+
+
 # every symbol include/sphb200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -89,6 +101,8 @@ SYMBOLS = {
     "sphb200_slab_counts": (C.c_int, [_P, C.POINTER(C.c_int32 * 8), _P]),
     "sphb200_slab_run": (C.c_int, [_P, C.c_int, C.c_double, C.c_uint32, _P, _P, _P, _P, _P,
                                    C.POINTER(C.c_int64)]),
+    "sphb200_lattice_rows": (C.c_int64, [C.POINTER(Lattice)]),
+    "sphb200_init_lattice": (C.c_int, [C.POINTER(Lattice), C.POINTER(State), _P, _P]),
     "sphb200_workspace_bytes": (C.c_int, [C.POINTER(Config), C.c_int64, C.POINTER(C.c_size_t)]),
     "sphb200_neighbor_list": (C.c_int, [C.POINTER(Config), C.c_int64, _P, _P, C.c_int64, C.c_int,
                                         _P, _P, _P, C.c_size_t, _P]),

@@ -1,0 +1,133 @@
+"""On-device case initialisation for the regular-lattice cases.
+
+Mirrors, with the output resident in HBM (torch CUDA tensors in the reference's layouts):
+
+* ``pos_init_cartesian_2d`` / ``pos_init_cartesian_3d``  <- jax_sph/utils.py:35-54
+* the field setup of ``SimulationSetup.initialize()``     <- jax_sph/case_setup.py:127-181
+  for lattice starts: TGV velocity fields (cases/tgv.py:37-51), channel walls along one
+  axis with the Dirichlet hot patch of cases/ht.py:90-97, uniform rho / p / mass / eta / T /
+  kappa / Cp.
+
+The reference builds these with NumPy ``meshgrid`` + ``vstack`` on the host and ships the
+whole state to the device; here one write-only kernel (csrc/init.cuh) fills the arrays, also
+per slab (``planes``) for the multi-GPU engine, so that a 64 M-particle start costs
+milliseconds.  Position noise (``case.r0_noise_factor``, jax.random) and relaxed starts
+(``case.r0_type == "relaxed"``, read from a state file) stay on the host side: out of scope.
+All compute goes through ``sphb200_init_lattice`` (include/sphb200.h); no CPU fallback.
+"""
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+_VEL = {"rest": _lib.VEL_REST, "tgv2d": _lib.VEL_TGV2D, "tgv3d": _lib.VEL_TGV3D}
+_KEYS = _lib.VECTOR_FIELDS + _lib.SCALAR_FIELDS + ("tag",)
+
+
+def lattice_shape(box_size, dx) -> Tuple[int, ...]:
+    """Planes per axis, `np.array((box_size / dx).round(), dtype=int)` (utils.py:40,51)."""
+    box = np.asarray(box_size, dtype=np.float64).reshape(-1)
+    return tuple(int(v) for v in np.array((box / dx).round(), dtype=int))
+
+
+def lattice_spec(box_size, dx, *, velocity="rest", wall_axis=-1, n_walls=0,
+                 hot: Optional[Sequence[float]] = None, T_hot=1.0, rho=1.0, p=0.0, mass=None,
+                 eta=0.0, T=1.0, kappa=0.0, Cp=0.0, planes: Optional[Tuple[int, int]] = None):
+    """`sphb200_lattice` for a box of `box_size` at spacing `dx`.  `planes` = (k_lo, k_hi)
+    restricts the last axis to one rank's slab; `hot` = (x_lo, x_hi) marks the Dirichlet patch
+    of the lower wall; `mass` defaults to rho * dx**dim (case_setup.py:100)."""
+    n = lattice_shape(box_size, dx)
+    dim = len(n)
+    if dim not in (2, 3):
+        raise _lib.Sphb200Error("box_size must have 2 or 3 entries")
+    if velocity not in _VEL:
+        raise _lib.Sphb200Error(f"velocity {velocity!r} is not one of {tuple(_VEL)}")
+    # a lattice plane at (n - 0.5) dx outside the periodic box would be reported by the engine as
+    # SPHB200_ERR_OUTSIDE_BOX on the first step; refuse it here, where the cause is visible
+    box = np.asarray(box_size, dtype=np.float64).reshape(-1)
+    for a in range(dim):
+        if (n[a] - 0.5) * dx >= box[a] * (1 - 1e-6):
+            raise _lib.Sphb200Error(
+                f"lattice {n} at dx={dx} does not fit the box {box.tolist()} (axis {a})")
+    lat = _lib.Lattice()
+    lat.struct_size = C.sizeof(_lib.Lattice)
+    lat.dim = dim
+    for a in range(3):
+        lat.n[a] = n[a] if a < dim else 1
+    lat.k_lo, lat.k_hi = (0, n[dim - 1]) if planes is None else (int(planes[0]), int(planes[1]))
+    lat.velocity = _VEL[velocity]
+    lat.wall_axis, lat.n_walls = int(wall_axis), int(n_walls)
+    lat.hot_lo, lat.hot_hi = (1.0, 0.0) if hot is None else (float(hot[0]), float(hot[1]))
+    lat.T_hot = T_hot
+    lat.dx, lat.rho, lat.p = dx, rho, p
+    lat.mass = rho * dx**dim if mass is None else mass
+    lat.eta, lat.T, lat.kappa, lat.Cp = eta, T, kappa, Cp
+    return lat
+
+
+def lattice_rows(lat) -> int:
+    rows = _lib.load().sphb200_lattice_rows(C.byref(lat))
+    if rows < 0:
+        _lib.check(int(rows))
+    return int(rows)
+
+
+def init_lattice(lat, keys: Sequence[str] = _KEYS, with_ids: bool = False) -> Dict:
+    """Fill a fresh state dict (torch CUDA tensors, reference layouts and row order) on the
+    current device and stream.  With `with_ids` the dict also carries `ids`, the row of each
+    particle in the full lattice (what SlabEngine.upload takes)."""
+    import torch
+
+    from .engine import _stream_ptr
+
+    lib = _lib.load()
+    rows = lattice_rows(lat)
+    if not torch.cuda.is_available():
+        raise _lib.Sphb200Error("init_lattice needs a CUDA device (there is no CPU fallback)")
+    st = _lib.State()
+    out = {}
+    for k in keys:
+        if k not in _KEYS:
+            raise _lib.Sphb200Error(f"unknown state key {k!r}")
+        shape = (rows, lat.dim) if k in _lib.VECTOR_FIELDS else (rows,)
+        out[k] = torch.empty(shape, dtype=torch.int32 if k == "tag" else torch.float32,
+                             device="cuda")
+        setattr(st, k, out[k].data_ptr() if rows else None)
+    ids = torch.empty(rows, dtype=torch.int32, device="cuda") if with_ids else None
+    _lib.check(lib.sphb200_init_lattice(
+        C.byref(lat), C.byref(st), C.c_void_p(ids.data_ptr() if (with_ids and rows) else None),
+        _stream_ptr()))
+    if with_ids:
+        out["ids"] = ids
+    return out
+
+
+def pos_init_cartesian_2d(box_size, dx):
+    """jax_sph/utils.py:35-46: particles at the centres of the Cartesian grid cells, (N, 2)."""
+    if len(np.asarray(box_size).reshape(-1)) != 2:
+        raise _lib.Sphb200Error("pos_init_cartesian_2d needs a 2-entry box_size")
+    return init_lattice(_bare_spec(box_size, dx), keys=("r",))["r"]
+
+
+def pos_init_cartesian_3d(box_size, dx):
+    """jax_sph/utils.py:49-54, (N, 3)."""
+    if len(np.asarray(box_size).reshape(-1)) != 3:
+        raise _lib.Sphb200Error("pos_init_cartesian_3d needs a 3-entry box_size")
+    return init_lattice(_bare_spec(box_size, dx), keys=("r",))["r"]
+
+
+def _bare_spec(box_size, dx):
+    # the reference's generators take any block size (wall blocks, utils.py:57-118): no box check
+    n = lattice_shape(box_size, dx)
+    lat = _lib.Lattice()
+    lat.struct_size = C.sizeof(_lib.Lattice)
+    lat.dim = len(n)
+    for a in range(3):
+        lat.n[a] = n[a] if a < len(n) else 1
+    lat.k_lo, lat.k_hi = 0, n[-1]
+    lat.wall_axis = -1
+    lat.dx = dx
+    return lat

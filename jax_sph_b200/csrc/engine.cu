@@ -18,6 +18,7 @@
 
 #include "cells.cuh"
 #include "common.cuh"
+#include "init.cuh"
 #include "phys.cuh"
 #include "slab.cuh"
 #include "sweep.cuh"
@@ -1311,6 +1312,56 @@ int sphb200_engine_stats(sphb200_engine* e, double* ekin, double* u_max, void* s
   CK(cudaStreamSynchronize(st));
   if (ekin) *ekin = h[0];
   if (u_max) *u_max = h[1];
+  return SPHB200_OK;
+}
+
+// ---- on-device case initialisation (row f1; kernel in init.cuh) ----------------------------
+int64_t sphb200_lattice_rows(const sphb200_lattice* l) {
+  if (!l || l->struct_size != sizeof(sphb200_lattice)) return SPHB200_EINVAL;
+  if (l->dim != 2 && l->dim != 3) return SPHB200_EINVAL;
+  for (int d = 0; d < l->dim; ++d)
+    if (l->n[d] <= 0) return SPHB200_EINVAL;
+  if (l->k_lo < 0 || l->k_hi < l->k_lo || l->k_hi > l->n[l->dim - 1]) return SPHB200_EINVAL;
+  if (l->wall_axis >= l->dim || (l->wall_axis >= 0 && l->n_walls < 0)) return SPHB200_EINVAL;
+  if (l->velocity < SPHB200_VEL_REST || l->velocity > SPHB200_VEL_TGV3D) return SPHB200_EINVAL;
+  if (l->velocity == SPHB200_VEL_TGV3D && l->dim != 3) return SPHB200_EINVAL;
+  if (!(l->dx > 0.f)) return SPHB200_EINVAL;
+  int64_t plane = l->n[0];
+  if (l->dim == 3) plane *= l->n[1];
+  const int64_t full = plane * l->n[l->dim - 1];
+  if (full > INT32_MAX) return SPHB200_EINVAL;  // ids are int32, like the reference's indices
+  return plane * (l->k_hi - l->k_lo);
+}
+
+int sphb200_init_lattice(const sphb200_lattice* l, sphb200_state* out, int32_t* ids, void* stream) {
+  const int64_t rows = sphb200_lattice_rows(l);
+  if (rows < 0) return (int)rows;
+  if (!out) return SPHB200_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SPHB200_ENODEV;
+  if (rows == 0) return SPHB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t vb = (size_t)rows * l->dim * sizeof(float), sb = (size_t)rows * sizeof(float);
+  float* zv[] = {out->dudt, out->dvdt, out->nw};
+  for (float* p : zv)
+    if (p) CK(cudaMemsetAsync(p, 0, vb, st));
+  float* zs[] = {out->drhodt, out->dTdt};
+  for (float* p : zs)
+    if (p) CK(cudaMemsetAsync(p, 0, sb, st));
+  LatticeArgs a;
+  a.l = *l;
+  a.out = *out;
+  a.ids = ids;
+  a.rows = rows;
+  int sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess)
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (rows + 255) / 256;
+  const int nb = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+  if (l->dim == 2) k_init_lattice<2><<<nb, 256, 0, st>>>(a);
+  else k_init_lattice<3><<<nb, 256, 0, st>>>(a);
+  CK(cudaGetLastError());
   return SPHB200_OK;
 }
 

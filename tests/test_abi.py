@@ -49,14 +49,16 @@ def test_struct_layout_matches_header(lib):
     cfg = lib.default_config()  # asserts sizeof(Config) == struct_size written by the C side
     assert cfg.dim == 3 and cfg.gamma == 1.0 and cfg.p_ref == 100.0
     # compile a one-liner against the header to cross-check the sizes with a C compiler
-    code = ('#include <stdio.h>\n#include "sphb200.h"\nint main(){printf("%zu %zu %zu",'
-            "sizeof(sphb200_config),sizeof(sphb200_state),sizeof(sphb200_bc_rule));return 0;}")
+    code = ('#include <stdio.h>\n#include "sphb200.h"\nint main(){printf("%zu %zu %zu %zu",'
+            "sizeof(sphb200_config),sizeof(sphb200_state),sizeof(sphb200_bc_rule),"
+            "sizeof(sphb200_lattice));return 0;}")
     exe = os.path.join(ROOT, "build", "abi_sizes")
     os.makedirs(os.path.dirname(exe), exist_ok=True)
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe],
                    input=code, text=True, check=True)
     sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True).stdout.split()]
-    assert sizes == [C.sizeof(lib.Config), C.sizeof(lib.State), C.sizeof(lib.BcRule)]
+    assert sizes == [C.sizeof(lib.Config), C.sizeof(lib.State), C.sizeof(lib.BcRule),
+                     C.sizeof(lib.Lattice)]
 
 
 def test_argument_validation_is_host_side(lib):
