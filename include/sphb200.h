@@ -217,6 +217,16 @@ int sphb200_engine_set_wall_layer(sphb200_engine *e, const float *layer, int n_l
                                   const float *offset, double cutoff);
 /* sync: kinetic energy 0.5*sum(m u.u) (utils.py:128-133) and max |u| (utils.py:136-166). */
 int sphb200_engine_stats(sphb200_engine *e, double *ekin, double *u_max, void *stream);
+/* sync: get_stats (jax_sph/utils.py:156-166, what Logger.print_stats prints, :288-296) on the
+ * resident state, one pass:
+ *   out[0]         Ekin = 0.5 * dx^dim * sum over FLUID particles of |v|^2 (get_ekin, :128-133:
+ *                  the TRANSPORT velocity, fluid only -- unlike sphb200_engine_stats)
+ *   out[1 + 3k..]  min, max, SUM of get_array_stats (:136-153; Euclidean norm for vectors) for
+ *                  k = 0..4: u, v, rho, p, T, over all particles (mean = sum / out[16])
+ *   out[16]        particles counted (a slab engine counts its own particles: the caller
+ *                  reduces min / max / sum / count over the ranks) */
+#define SPHB200_NSTATS 20
+int sphb200_engine_get_stats(sphb200_engine *e, double out[SPHB200_NSTATS], void *stream);
 /* Kernel launches issued by this engine so far (bench.py's gpu_launches). */
 int64_t sphb200_engine_launches(const sphb200_engine *e);
 /* Sweep timing: CUDA-event ms of the last step's passes: [0] integrate+hash, [1] sort/reorder,

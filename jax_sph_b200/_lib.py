@@ -88,6 +88,7 @@ SYMBOLS = {
     "sphb200_engine_error": (C.c_int, [_P, C.POINTER(C.c_uint32), _P]),
     "sphb200_engine_neighbor_list": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P]),
     "sphb200_engine_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), _P]),
+    "sphb200_engine_get_stats": (C.c_int, [_P, C.POINTER(C.c_double * 20), _P]),
     "sphb200_engine_set_wall_layer": (C.c_int, [_P, _P, C.c_int, _P, C.c_double]),
     "sphb200_engine_launches": (C.c_int64, [_P]),
     "sphb200_engine_profile": (C.c_int, [_P, C.c_int]),

@@ -62,7 +62,7 @@ struct sphb200_engine {
   unsigned char* pl_ok;
   int pl_lmax;
   unsigned* err;
-  double* stats;  // [ekin, umax]
+  double* stats;  // [ekin, umax] of sphb200_engine_stats / the SPHB200_NSTATS words of _get_stats
   int nscan_blocks;
   int tpb, lcap;
   SweepPlan planA, planR, planW, planC, planN;
@@ -361,7 +361,7 @@ void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, Layout& L) {
   L.maxocc = take(4);
   L.wallcount = take(4);
   L.err = take(4);
-  L.stats = take(16);
+  L.stats = take(SPHB200_NSTATS * 8);
   L.dn = take(DN_WORDS * 4);
   L.pl_lmax = plan_lmax(c);
   if (L.pl_lmax > 0) {
@@ -833,6 +833,87 @@ __global__ void __launch_bounds__(256) k_stats(int n, Slab sl, Frame f, double* 
     atomicAdd(&out[0], ek);
     atomicMax(reinterpret_cast<unsigned long long*>(&out[1]),
               (unsigned long long)__double_as_longlong((double)um));
+  }
+}
+
+// get_stats (jax_sph/utils.py:128-166) on the resident frame, any particle order:
+//   out[0]            sum over FLUID particles of |v|^2           (get_ekin, utils.py:128-133)
+//   out[1 + 3k + 0/1] min / max as order-preserving uint keys, out[1 + 3k + 2] sum, for
+//                     k = |u|, |v|, rho, p, T                      (get_array_stats, :136-153)
+//   out[16]           particles counted
+__device__ __forceinline__ unsigned f2key(float x) {
+  const unsigned b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_get_stats(int n, Slab sl, Frame f, double* out) {
+  const int bound = sl.dn ? sl.dn[DN_OWN] : n;
+  double sum[6] = {0, 0, 0, 0, 0, 0};  // ekin, u, v, rho, p, T
+  float mn[5], mx[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    mn[k] = INFINITY;
+    mx[k] = -INFINITY;
+  }
+  int cnt = 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < bound; t += gridDim.x * blockDim.x) {
+    const int p = sl.base + t;
+    const float4 pt = f.pt[p], u = f.um[p], v = f.vv[p], st = f.st[p];
+    const float uu = u.x * u.x + u.y * u.y + (DIM == 3 ? u.z * u.z : 0.f);
+    const float vv = v.x * v.x + v.y * v.y + (DIM == 3 ? v.z * v.z : 0.f);
+    const float val[5] = {sqrtf(uu), sqrtf(vv), st.x, st.y, st.z};
+    if (__float_as_int(pt.w) == SPHB200_TAG_FLUID) sum[0] += (double)vv;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      sum[k + 1] += (double)val[k];
+      mn[k] = fminf(mn[k], val[k]);
+      mx[k] = fmaxf(mx[k], val[k]);
+    }
+    ++cnt;
+  }
+  __shared__ double s_sum[8][6];
+  __shared__ float s_mn[8][5], s_mx[8][5];
+  __shared__ int s_cnt[8];
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sum[k] += __shfl_xor_sync(FULL_MASK, sum[k], o);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      mn[k] = fminf(mn[k], __shfl_xor_sync(FULL_MASK, mn[k], o));
+      mx[k] = fmaxf(mx[k], __shfl_xor_sync(FULL_MASK, mx[k], o));
+    }
+    cnt += __shfl_xor_sync(FULL_MASK, cnt, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    for (int k = 0; k < 6; ++k) s_sum[warp][k] = sum[k];
+    for (int k = 0; k < 5; ++k) {
+      s_mn[warp][k] = mn[k];
+      s_mx[warp][k] = mx[k];
+    }
+    s_cnt[warp] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      for (int k = 0; k < 6; ++k) s_sum[0][k] += s_sum[w][k];
+      for (int k = 0; k < 5; ++k) {
+        s_mn[0][k] = fminf(s_mn[0][k], s_mn[w][k]);
+        s_mx[0][k] = fmaxf(s_mx[0][k], s_mx[w][k]);
+      }
+      s_cnt[0] += s_cnt[w];
+    }
+    if (s_cnt[0] > 0) {
+      atomicAdd(&out[0], s_sum[0][0]);
+      unsigned long long* key = reinterpret_cast<unsigned long long*>(out);
+      for (int k = 0; k < 5; ++k) {
+        atomicMin(&key[1 + 3 * k], (unsigned long long)f2key(s_mn[0][k]));
+        atomicMax(&key[2 + 3 * k], (unsigned long long)f2key(s_mx[0][k]));
+        atomicAdd(&out[3 + 3 * k], s_sum[0][k + 1]);
+      }
+      atomicAdd(&out[16], (double)s_cnt[0]);
+    }
   }
 }
 
@@ -1362,6 +1443,45 @@ int sphb200_init_lattice(const sphb200_lattice* l, sphb200_state* out, int32_t* 
   if (l->dim == 2) k_init_lattice<2><<<nb, 256, 0, st>>>(a);
   else k_init_lattice<3><<<nb, 256, 0, st>>>(a);
   CK(cudaGetLastError());
+  return SPHB200_OK;
+}
+
+int sphb200_engine_get_stats(sphb200_engine* e, double out[SPHB200_NSTATS], void* stream) {
+  if (!e || !out) return SPHB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  // min slots start at the largest key, everything else at zero
+  unsigned long long init[SPHB200_NSTATS];
+  memset(init, 0, sizeof(init));
+  for (int k = 0; k < 5; ++k) init[1 + 3 * k] = ~0ull;
+  CK(cudaMemcpyAsync(e->stats, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  const int bound = e->slab_on ? e->sgeom.own_cap : e->n;
+  int nb = (bound + 255) / 256;
+  if (nb > 148 * 8) nb = 148 * 8;
+  if (e->dim == 2) k_get_stats<2><<<nb, 256, 0, st>>>(bound, e->slab, e->fr[e->cur], e->stats);
+  else k_get_stats<3><<<nb, 256, 0, st>>>(bound, e->slab, e->fr[e->cur], e->stats);
+  CK(cudaGetLastError());
+  e->launches++;
+  unsigned long long h[SPHB200_NSTATS];
+  CK(cudaMemcpyAsync(h, e->stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memset(out, 0, SPHB200_NSTATS * sizeof(double));
+  double d[SPHB200_NSTATS];
+  memcpy(d, h, sizeof(h));
+  const double count = d[16];
+  out[16] = count;
+  double vol = 1.0;
+  for (int a = 0; a < e->dim; ++a) vol *= e->cfg.dx;
+  out[0] = 0.5 * d[0] * vol;  // utils.py:133
+  for (int k = 0; k < 5; ++k) {
+    for (int m = 0; m < 2; ++m) {
+      unsigned key = (unsigned)h[1 + 3 * k + m];
+      unsigned bits = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+      float v;
+      memcpy(&v, &bits, 4);
+      out[1 + 3 * k + m] = count > 0 ? (double)v : 0.0;
+    }
+    out[3 + 3 * k] = d[3 + 3 * k];
+  }
   return SPHB200_OK;
 }
 

@@ -116,6 +116,27 @@ def make_config(
     return cfg
 
 
+STAT_VARS = ("u", "v", "rho", "p", "T")
+
+
+def stats_from_words(words, props):
+    """Pick `props` out of the SPHB200_NSTATS words of sphb200_engine_get_stats (summed /
+    min-max-reduced over the ranks first on a slab engine)."""
+    res = {}
+    for prop in props:
+        if prop == "Ekin":
+            res[prop] = words[0]
+            continue
+        var, operation = prop.split("_")  # e.g. "u_max", utils.py:164
+        if var not in STAT_VARS or operation not in ("min", "max", "mean"):
+            raise _lib.Sphb200Error(f"get_stats: {prop!r} is not offered on the device "
+                                    f"(Ekin, <{'|'.join(STAT_VARS)}>_<min|max|mean>)")
+        k = 1 + 3 * STAT_VARS.index(var)
+        res[prop] = {"min": words[k], "max": words[k + 1],
+                     "mean": words[k + 2] / max(words[16], 1.0)}[operation]
+    return res
+
+
 def config_from_setup(setup, **tuning):
     """`setup` is anything exposing the fields of the reference's
     SimulationSetup / WCSPH call (jax_sph/simulate.py:49-69): used by tests and
@@ -328,6 +349,14 @@ class Engine:
         ek, um = C.c_double(), C.c_double()
         _lib.check(self.lib.sphb200_engine_stats(self._h, C.byref(ek), C.byref(um), _stream_ptr()))
         return ek.value, um.value
+
+    def get_stats(self, props=("Ekin", "u_max")):
+        """`get_stats(state, props, dx)` of jax_sph/utils.py:156-166 on the resident state:
+        "Ekin" (get_ekin: transport velocity, fluid particles, times dx**dim) or
+        "<var>_<min|max|mean>" for var in u, v, rho, p, T (Euclidean norm for vectors)."""
+        out = (C.c_double * 20)()
+        _lib.check(self.lib.sphb200_engine_get_stats(self._h, C.byref(out), _stream_ptr()))
+        return stats_from_words(list(out), props)
 
     def launches(self) -> int:
         return int(self.lib.sphb200_engine_launches(self._h))

@@ -56,6 +56,19 @@ def _host(v):
     return np.asarray(v)
 
 
+def _plain(x):
+    """NumPy scalars / arrays -> Python numbers / lists (YAML dump of a config dict)."""
+    if isinstance(x, dict):
+        return {str(k): _plain(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_plain(v) for v in x]
+    if isinstance(x, np.ndarray):
+        return x.tolist()
+    if isinstance(x, np.generic):
+        return x.item()
+    return x
+
+
 def io_setup(cfg, stamp: Optional[str] = None) -> str:
     """io_state.py:14-27: `<data_path>/<dim>D_<CASE>_<solver>_<seed>_<time>` for simulation runs
     that write, else `<data_path>/`; the directory is created.  (The reference also dumps
@@ -72,7 +85,7 @@ def io_setup(cfg, stamp: Optional[str] = None) -> str:
         import yaml
 
         with open(os.path.join(d, "config.yaml"), "w") as f:
-            yaml.safe_dump(cfg, f)
+            yaml.safe_dump(_plain(cfg), f)
     return d
 
 

@@ -1,0 +1,198 @@
+"""The driver loop around the hot path: a mirror of ``simulate(cfg)`` (jax_sph/simulate.py:19-136)
+with the state resident in a B200 engine.
+
+    from jax_sph_b200.simulate import defaults, simulate
+    cfg = defaults(case=dict(name="tgv", dim=3, dx=6.2832 / 64, viscosity=0.02),
+                   solver=dict(tvf=1.0, t_end=1.0), io=dict(write_type=["h5"], write_every=100))
+    engine = simulate(cfg)
+
+What is kept: the config keys (jax_sph/defaults.py), the time-step rule (case_setup.py:94-112),
+the order of the loop -- ``write_state(step - 1)``, ``advance(dt)``, overflow check, progress
+line every ``write_every`` steps (simulate.py:113-134, utils.py:278-296) -- the file names and
+the printed line format.  What differs, by construction: there is no edge list to re-allocate
+(the per-step ``did_buffer_overflow`` test becomes the engine's device error word, read at
+the logging cadence instead of every step, so the loop has no per-step host sync), and the
+reference's untimed ``advance(0.0, ...)`` compile call (simulate.py:108-109, result discarded)
+has nothing to compile.
+
+Cases.  ``cfg.case.name == "tgv"`` with a Cartesian start and no position noise is built on the
+device (case_setup.lattice_spec / init_lattice).  Every other case is passed in prepared:
+``simulate(cfg, setup=obj)`` where ``obj`` carries the reference's ``initialize()`` results as
+plain attributes (``state``, ``box_size``, ``dt``, ... -- exactly what ``config_from_setup``
+reads); the case classes themselves (cases/*.py) are outside the hot-path scope.
+"""
+
+import copy
+import time
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib, case_setup, io_state
+from .engine import Engine, config_from_setup, make_config
+
+EPS = float(np.finfo(np.float32).eps)  # jnp.finfo(float).eps with x64 off (case_setup.py:26)
+
+
+def defaults(**overrides) -> Dict:
+    """The entries of jax_sph/defaults.py:11-148 the path reads, as a plain nested dict;
+    ``overrides`` are merged per section (``defaults(case=dict(dx=0.02))``)."""
+    cfg = {
+        "seed": 123, "dtype": "float32",
+        "case": dict(name="tgv", mode="sim", dim=3, dx=0.05, r0_type="cartesian",
+                     r0_noise_factor=0.0, g_ext_magnitude=0.0, viscosity=0.01, u_ref=1.0,
+                     c_ref_factor=10.0, rho_ref=1.0, T_ref=1.0, kappa_ref=0.0, Cp_ref=0.0),
+        "solver": dict(name="SPH", tvf=0.0, cfl=0.25, density_evolution=False,
+                       density_renormalize=False, dt=None, t_end=0.2, artificial_alpha=0.0,
+                       free_slip=False, eta_limiter=3, n_walls=3, heat_conduction=False,
+                       is_bc_trick=False, diff_delta=0.1, diff_alpha=0.01),
+        "kernel": dict(name="QSK", h_factor=1.0),
+        "eos": dict(name="Tait", gamma=1.0, p_bg_factor=0.0),
+        "io": dict(write_type=[], write_every=1, data_path="./", print_props=["Ekin", "u_max"]),
+    }
+    for section, vals in overrides.items():
+        if isinstance(vals, dict):
+            unknown = set(vals) - set(cfg.get(section, vals))
+            if section in cfg and unknown:
+                raise _lib.Sphb200Error(f"unknown config keys in {section}: {sorted(unknown)}")
+            cfg.setdefault(section, {}).update(vals)
+        else:
+            cfg[section] = vals
+    return cfg
+
+
+def time_step(cfg) -> float:
+    """case_setup.py:94-112: CFL minimum of the convective, viscous and body-force limits,
+    overridden by an explicit ``solver.dt``."""
+    g = io_state._get
+    h = g(cfg, "case.dx")
+    u_ref, rho_ref = g(cfg, "case.u_ref"), g(cfg, "case.rho_ref")
+    c_ref = g(cfg, "case.c_ref_factor") * u_ref
+    cfl = g(cfg, "solver.cfl")
+    dt_convective = cfl * h / (c_ref + u_ref)
+    dt_viscous = cfl * h**2 * rho_ref / (g(cfg, "case.viscosity") + EPS)
+    dt_body_force = cfl * (h / (g(cfg, "case.g_ext_magnitude") + EPS)) ** 0.5
+    dt = float(np.amin([dt_convective, dt_viscous, dt_body_force]))
+    explicit = g(cfg, "solver.dt")
+    return float(explicit) if explicit is not None else dt
+
+
+class _Prepared:
+    """What the loop needs of a case: engine config, state, dt, sequence length."""
+
+    def __init__(self, engine_cfg, state, dt, sequence_length, dx, n):
+        self.engine_cfg, self.state, self.dt = engine_cfg, state, dt
+        self.sequence_length, self.dx, self.n = sequence_length, dx, n
+
+
+def _prepare_tgv(cfg) -> _Prepared:
+    g = io_state._get
+    if g(cfg, "case.r0_type") != "cartesian" or g(cfg, "case.r0_noise_factor") != 0.0:
+        raise _lib.Sphb200Error(
+            "the on-device start is the Cartesian lattice without noise; pass relaxed / noisy "
+            "starts as a prepared setup (simulate(cfg, setup=...))")
+    if str(g(cfg, "dtype")) != "float32":
+        raise _lib.Sphb200Error("the engine is float32 only (cfg.dtype)")
+    dim, dx = g(cfg, "case.dim"), g(cfg, "case.dx")
+    box = [1.0, 1.0] if dim == 2 else [2 * np.pi] * 3  # cases/tgv.py:25-29
+    rho_ref, u_ref = g(cfg, "case.rho_ref"), g(cfg, "case.u_ref")
+    c_ref = g(cfg, "case.c_ref_factor") * u_ref
+    gamma = g(cfg, "eos.gamma")
+    p_ref = rho_ref * c_ref**2 / gamma       # case_setup.py:82
+    p_bg = g(cfg, "eos.p_bg_factor") * p_ref  # :84
+    dt = time_step(cfg)
+    seq = 5000 if g(cfg, "case.mode") == "rlx" else int(g(cfg, "solver.t_end") / dt)  # :106-112
+    name = g(cfg, "solver.name")
+    lat = case_setup.lattice_spec(
+        box, dx, velocity="tgv2d" if dim == 2 else "tgv3d", rho=rho_ref, p=p_bg,
+        eta=g(cfg, "case.viscosity"), T=g(cfg, "case.T_ref"), kappa=g(cfg, "case.kappa_ref"),
+        Cp=g(cfg, "case.Cp_ref"))
+    ecfg = make_config(
+        dim, box, dx, dt, solver=name, kernel=g(cfg, "kernel.name"),
+        h_fac=g(cfg, "kernel.h_factor"), tvf=g(cfg, "solver.tvf"), p_ref=p_ref, rho_ref=rho_ref,
+        p_bg=p_bg, gamma=gamma, u_ref=u_ref, c_ref=c_ref, eta_limiter=g(cfg, "solver.eta_limiter"),
+        is_bc_trick=g(cfg, "solver.is_bc_trick"), is_rho_evol=g(cfg, "solver.density_evolution"),
+        is_rho_renorm=g(cfg, "solver.density_renormalize"), is_free_slip=g(cfg, "solver.free_slip"),
+        is_heat_conduction=g(cfg, "solver.heat_conduction"),
+        artificial_alpha=g(cfg, "solver.artificial_alpha"),
+        diff_delta=g(cfg, "solver.diff_delta"), diff_alpha=g(cfg, "solver.diff_alpha"))
+    state = case_setup.init_lattice(lat)
+    return _Prepared(ecfg, state, dt, seq, dx, case_setup.lattice_rows(lat))
+
+
+def _prepare_setup(cfg, setup, tuning) -> _Prepared:
+    dt = float(setup.dt)
+    seq = getattr(setup, "sequence_length", None)
+    if seq is None:
+        seq = int(io_state._get(cfg, "solver.t_end") / dt)
+    return _Prepared(config_from_setup(setup, **tuning), setup.state, dt, int(seq), setup.dx,
+                     len(setup.state["r"]))
+
+
+def log_line(step: int, sequence_length: int, dt: float, stats: Dict) -> str:
+    """Logger.print_stats (utils.py:288-296)."""
+    digits = len(str(sequence_length))
+    stats_str = ", ".join(f"{k}={v:.5f}" for k, v in stats.items())
+    return f"{str(step).zfill(digits)}/{sequence_length}, t={(step + 1) * dt:.4f}, {stats_str}"
+
+
+def simulate(cfg, setup=None, out_dir: Optional[str] = None, log=print, **tuning):
+    """Run the loop of jax_sph/simulate.py:95-136 on a resident engine and return it (state in
+    HBM, ``engine.download()`` for the final fields).  ``cfg``: a nested dict / namespace with
+    the reference's keys (see ``defaults``); it is not modified -- the derived entries the
+    reference writes back (solver.dt, solver.sequence_length, case.c_ref ..., case_setup.py:
+    196-199) are on the returned engine as ``engine.run_cfg``."""
+    if isinstance(cfg, dict):
+        cfg = copy.deepcopy(cfg)
+    g = io_state._get
+    if setup is not None:
+        prep = _prepare_setup(cfg, setup, tuning)
+    elif str(g(cfg, "case.name")).lower() == "tgv":
+        prep = _prepare_tgv(cfg)
+    else:
+        raise _lib.Sphb200Error(
+            f"case {g(cfg, 'case.name')!r} is not built on the device: pass its initialize() "
+            "results as a prepared setup")
+    if isinstance(cfg, dict):
+        cfg["solver"]["dt"], cfg["solver"]["sequence_length"] = prep.dt, prep.sequence_length
+        cfg["case"]["num_particles_max"] = prep.n
+    write_cfg = cfg if isinstance(cfg, dict) else {
+        "case": dict(mode=g(cfg, "case.mode"), name=g(cfg, "case.name"), dim=g(cfg, "case.dim"),
+                     dx=g(cfg, "case.dx")),
+        "seed": g(cfg, "seed"), "solver": dict(name=g(cfg, "solver.name"),
+                                               sequence_length=prep.sequence_length),
+        "io": dict(write_every=g(cfg, "io.write_every"), write_type=list(g(cfg, "io.write_type")),
+                   data_path=g(cfg, "io.data_path"))}
+    write_every = g(cfg, "io.write_every")
+    props = list(g(cfg, "io.print_props"))
+    directory = out_dir if out_dir is not None else io_state.io_setup(write_cfg)
+
+    engine = Engine(prep.engine_cfg, prep.n)
+    engine.upload(prep.state)
+    engine.run_cfg = write_cfg
+    writer = io_state.TrajectoryWriter(engine, directory, write_cfg) if g(cfg, "io.write_type") else None
+
+    start = time.time()
+    for step in range(prep.sequence_length + 2):  # simulate.py:113
+        if writer is not None:
+            writer.write(step - 1)
+        engine.step(prep.dt, 1)
+        if step % write_every == 0:
+            # simulate.py:120-131: the overflow check (no list to re-allocate: any device error
+            # is fatal), then the progress line (:133-134)
+            err = engine.error()
+            if err:
+                if writer is not None:
+                    writer.close()
+                raise _lib.Sphb200Error(f"device error word {err:#x} at step {step}")
+            if log is not None:
+                log(log_line(step, prep.sequence_length, prep.dt, engine.get_stats(props)))
+    if writer is not None:
+        writer.close()
+    err = engine.error()
+    if err:
+        raise _lib.Sphb200Error(f"device error word {err:#x} at the end of the run")
+    if log is not None:
+        log(f"time: {time.time() - start:.2f} s")
+    engine.out_dir = directory
+    return engine
