@@ -194,6 +194,16 @@ int sphb200_engine_destroy(sphb200_engine *e);
 int sphb200_engine_upload(sphb200_engine *e, const sphb200_state *s, int on_host, void *stream);
 /* nsteps x advance(dt) (integrator.py:22-56) or forward only, per `flags`. */
 int sphb200_engine_step(sphb200_engine *e, double dt, int nsteps, uint32_t flags, void *stream);
+/* One advance(dt, state, neighbors) (integrator.py:22-56) on HOST buffers, the call a reference
+ * user makes with a host-resident state: copies the non-NULL members of *in host -> device,
+ * runs one step (`flags` as in sphb200_engine_step) and copies the non-NULL members of *out
+ * device -> host in the original particle order.  The entries that are final after the
+ * integrate / reorder pass (r; u and v too unless a wall sweep or the bc table rewrites them)
+ * travel back on an internal high-priority stream WHILE the interaction sweeps run; `stream`
+ * waits for that copy before the call's work on it ends, so synchronising `stream` is enough.
+ * Pinned host memory is needed for the copies to overlap. */
+int sphb200_engine_advance_host(sphb200_engine *e, double dt, const sphb200_state *in,
+                                sphb200_state *out, uint32_t flags, void *stream);
 /* Write the state back in the ORIGINAL particle order (index-stable API). NULL members are skipped. */
 int sphb200_engine_download(sphb200_engine *e, sphb200_state *out, int on_host, void *stream);
 /* sync: read and clear the device error word. */

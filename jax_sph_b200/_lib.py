@@ -84,6 +84,8 @@ SYMBOLS = {
     "sphb200_engine_destroy": (C.c_int, [_P]),
     "sphb200_engine_upload": (C.c_int, [_P, C.POINTER(State), C.c_int, _P]),
     "sphb200_engine_step": (C.c_int, [_P, C.c_double, C.c_int, C.c_uint32, _P]),
+    "sphb200_engine_advance_host": (C.c_int, [_P, C.c_double, C.POINTER(State), C.POINTER(State),
+                                             C.c_uint32, _P]),
     "sphb200_engine_download": (C.c_int, [_P, C.POINTER(State), C.c_int, _P]),
     "sphb200_engine_error": (C.c_int, [_P, C.POINTER(C.c_uint32), _P]),
     "sphb200_engine_neighbor_list": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P]),

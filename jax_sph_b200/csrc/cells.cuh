@@ -335,7 +335,12 @@ __global__ void __launch_bounds__(256) k_unpack(int n, Slab sl, Frame f, StateOu
     o.ids[t] = p;
     p = t;
   }
-  float4 pt = f.pt[s], um = f.um[s], vv = f.vv[s], st = f.st[s], du = f.du[s], dv = f.dv[s];
+  // a split download (advance_host) asks for a few entries only: load just their quads
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 pt = (o.r || o.tag) ? f.pt[s] : z4, um = (o.u || o.mass) ? f.um[s] : z4;
+  const float4 vv = (o.v || o.eta) ? f.vv[s] : z4;
+  const float4 st = (o.rho || o.p || o.T || o.dTdt) ? f.st[s] : z4;
+  const float4 du = (o.dudt || o.drhodt) ? f.du[s] : z4, dv = o.dvdt ? f.dv[s] : z4;
   store_vec<DIM>(o.r, p, pt);
   store_vec<DIM>(o.u, p, um);
   store_vec<DIM>(o.v, p, vv);

@@ -95,6 +95,12 @@ struct sphb200_engine {
   cudaStream_t side;
   cudaEvent_t ev_main, ev_side;
   bool overlap;       // side stream and events exist (slab engines)
+  // advance_host: the entries that are final after the integrate / reorder pass (r, and u, v
+  // when no wall sweep or bc table rewrites them) go back to the host on this stream WHILE the
+  // sweeps run
+  cudaStream_t io_side;
+  cudaEvent_t ev_io_fork, ev_io_join;
+  bool io_on;
   int pre_stage;      // stage whose interior tiles are already running on the side stream, -1
   int delta_sub;      // slab engine, Delta-SPH density diffusion: next of its three sweeps
   bool stage_more;    // forward_stage ran only part of the stage (another halo refresh first)
@@ -939,6 +945,7 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->part = 0;
   e->pre_stage = -1;
   e->overlap = false;
+  e->io_on = false;
   e->delta_sub = 0;
   e->stage_more = false;
   int dev = 0;
@@ -1141,6 +1148,11 @@ int sphb200_engine_destroy(sphb200_engine* e) {
     cudaEventDestroy(e->ev_main);
     cudaEventDestroy(e->ev_side);
   }
+  if (e->io_on) {
+    cudaStreamDestroy(e->io_side);
+    cudaEventDestroy(e->ev_io_fork);
+    cudaEventDestroy(e->ev_io_join);
+  }
   if (e->own_arena) cudaFree(e->arena);
   delete e;
   return SPHB200_OK;
@@ -1250,8 +1262,11 @@ int sphb200_engine_upload(sphb200_engine* e, const sphb200_state* s, int on_host
 }
 
 // rows: capacity of the arrays in *out; ids != NULL (slab mode): local order + global indices
+// `part` (host downloads only): 0 = every entry of *out; 1 = only the entries in `early`
+// (r [, u, v]); 2 = all the others.  The staging offsets are those of the full *out either way,
+// so the two halves of a split download never share staging memory.
 static int download_impl(sphb200_engine* e, sphb200_state* out, int rows, int32_t* ids,
-                         int on_host, void* stream) {
+                         int on_host, void* stream, int part = 0, bool early_uv = false) {
   if (!e || !out) return SPHB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const int n = rows, d = e->dim;
@@ -1284,6 +1299,30 @@ static int download_impl(sphb200_engine* e, sphb200_state* out, int rows, int32_
     dv.tag = (int32_t*)stage(out->tag, ns);
     if (ids) dids = (int32_t*)stage(ids, ns);
   }
+  if (part != 0) {
+    if (!on_host || ids) return SPHB200_EINVAL;
+    const void* keep[3] = {dv.r, early_uv ? dv.u : nullptr, early_uv ? dv.v : nullptr};
+    int m = 0;
+    for (int i = 0; i < nback; ++i) {
+      const bool is_early = back[i].dptr && (back[i].dptr == keep[0] || back[i].dptr == keep[1] ||
+                                             back[i].dptr == keep[2]);
+      if (is_early == (part == 1)) back[m++] = back[i];
+    }
+    nback = m;
+    if (part == 1) {
+      sphb200_state only{};
+      only.r = dv.r;
+      if (early_uv) {
+        only.u = dv.u;
+        only.v = dv.v;
+      }
+      dv = only;
+    } else {
+      dv.r = nullptr;
+      if (early_uv) dv.u = dv.v = nullptr;
+    }
+    if (nback == 0) return SPHB200_OK;
+  }
   StateOut so{dv.r, dv.u, dv.v, dv.dudt, dv.dvdt, dv.nw, dv.rho, dv.p, dv.drhodt, dv.mass,
               dv.eta, dv.T, dv.dTdt, dv.kappa, dv.Cp, dv.tag, dids};
   const int nb = (n + 255) / 256;
@@ -1299,6 +1338,51 @@ static int download_impl(sphb200_engine* e, sphb200_state* out, int rows, int32_
 int sphb200_engine_download(sphb200_engine* e, sphb200_state* out, int on_host, void* stream) {
   if (!e || e->slab_on) return SPHB200_EINVAL;
   return download_impl(e, out, e->n, nullptr, on_host, stream);
+}
+
+int sphb200_engine_advance_host(sphb200_engine* e, double dt, const sphb200_state* in,
+                                sphb200_state* out, uint32_t flags, void* stream) {
+  if (!e || !in || !out || e->slab_on) return SPHB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!e->io_on) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = greatest priority
+    if (cudaStreamCreateWithPriority(&e->io_side, cudaStreamNonBlocking, hi) != cudaSuccess)
+      return SPHB200_ECUDA;
+    if (cudaEventCreateWithFlags(&e->ev_io_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_io_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaStreamDestroy(e->io_side);
+      return SPHB200_ECUDA;
+    }
+    e->io_on = true;
+  }
+  int rc = upload_impl(e, in, e->n, nullptr, 1, stream);
+  if (rc) return rc;
+  Kick k;
+  k.dt = (float)dt;
+  k.c2 = (float)(e->cfg.tvf * 0.5) * (float)dt;
+  k.on = (flags & SPHB200_STEP_INTEGRATE) ? 1 : 0;
+  const bool v_is_u = k.on && e->cfg.tvf == 0.0;
+  if (e->profile) cudaEventRecord(e->ev[0], st);
+  rc = build_cells(e, k, st);
+  if (rc) return rc;
+  if (e->profile) cudaEventRecord(e->ev[2], st);
+  // r is final once the particles are integrated and reordered; u and v too unless the wall
+  // sweep (generalized wall BC) or the case's bc table rewrites them after forward().  With
+  // v == u (no transport velocity) the frame's v is written by the force sweep: not early.
+  const bool early_uv = !(e->cfg.flags & SPHB200_F_BC_TRICK) && !bc_table_on(e->cfg) && !v_is_u;
+  CK(cudaEventRecord(e->ev_io_fork, st));
+  CK(cudaStreamWaitEvent(e->io_side, e->ev_io_fork, 0));
+  rc = download_impl(e, out, e->n, nullptr, 1, (void*)e->io_side, 1, early_uv);
+  if (rc) return rc;
+  CK(cudaEventRecord(e->ev_io_join, e->io_side));
+  rc = run_forward(e, flags, v_is_u, st);
+  if (rc) return rc;
+  if (e->profile) cudaEventRecord(e->ev[5], st);
+  rc = download_impl(e, out, e->n, nullptr, 1, stream, 2, early_uv);
+  if (rc) return rc;
+  CK(cudaStreamWaitEvent(st, e->ev_io_join, 0));  // the caller's stream sees the whole result
+  return SPHB200_OK;
 }
 
 int sphb200_engine_step(sphb200_engine* e, double dt, int nsteps, uint32_t flags, void* stream) {

@@ -316,10 +316,21 @@ class Engine:
         `state`'s own arrays) and returns the full state dict -- the untouched entries are the
         caller's arrays, exactly what the reference's advance() returns for them."""
         read, written = self.live_fields()
-        self.upload({k: state[k] for k in read})
-        self.step(dt, 1)
         dst = out if out is not None else state
-        self.download(out={k: dst[k] for k in written})
+        st_in, host_in, keep_in = self._state_struct({k: state[k] for k in read}, writable=False)
+        st_out, host_out, keep_out = self._state_struct({k: dst[k] for k in written}, writable=True)
+        if host_in and host_out:
+            # one fused call: r (and u, v when nothing rewrites them after the reorder pass) go
+            # back to the host while the sweeps run (sphb200_engine_advance_host)
+            self._keep = (keep_in, keep_out)
+            _lib.check(self.lib.sphb200_engine_advance_host(
+                self._h, float(dt), C.byref(st_in), C.byref(st_out),
+                _lib.STEP_INTEGRATE | _lib.STEP_BC, _stream_ptr()))
+            _torch().cuda.current_stream().synchronize()
+        else:
+            self.upload({k: state[k] for k in read})
+            self.step(dt, 1)
+            self.download(out={k: dst[k] for k in written})
         res = dict(state)
         res.update({k: dst[k] for k in written})
         return res
