@@ -1262,11 +1262,15 @@ int sphb200_engine_upload(sphb200_engine* e, const sphb200_state* s, int on_host
 }
 
 // rows: capacity of the arrays in *out; ids != NULL (slab mode): local order + global indices
-// `part` (host downloads only): 0 = every entry of *out; 1 = only the entries in `early`
-// (r [, u, v]); 2 = all the others.  The staging offsets are those of the full *out either way,
-// so the two halves of a split download never share staging memory.
+// `mask` (host downloads only): which entries of *out this call moves (DL_ALL: every one).  The
+// staging offsets are those of the full *out for any mask, so the parts of a split download
+// (advance_host) never share staging memory.
+enum : unsigned {
+  DL_R = 1u, DL_U = 2u, DL_V = 4u, DL_RHO = 8u, DL_P = 16u, DL_DUDT = 32u, DL_DVDT = 64u,
+  DL_REST = 128u, DL_ALL = 255u
+};
 static int download_impl(sphb200_engine* e, sphb200_state* out, int rows, int32_t* ids,
-                         int on_host, void* stream, int part = 0, bool early_uv = false) {
+                         int on_host, void* stream, unsigned mask = DL_ALL) {
   if (!e || !out) return SPHB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const int n = rows, d = e->dim;
@@ -1299,27 +1303,27 @@ static int download_impl(sphb200_engine* e, sphb200_state* out, int rows, int32_
     dv.tag = (int32_t*)stage(out->tag, ns);
     if (ids) dids = (int32_t*)stage(ids, ns);
   }
-  if (part != 0) {
+  if (mask != DL_ALL) {
     if (!on_host || ids) return SPHB200_EINVAL;
-    const void* keep[3] = {dv.r, early_uv ? dv.u : nullptr, early_uv ? dv.v : nullptr};
-    int m = 0;
-    for (int i = 0; i < nback; ++i) {
-      const bool is_early = back[i].dptr && (back[i].dptr == keep[0] || back[i].dptr == keep[1] ||
-                                             back[i].dptr == keep[2]);
-      if (is_early == (part == 1)) back[m++] = back[i];
-    }
-    nback = m;
-    if (part == 1) {
-      sphb200_state only{};
-      only.r = dv.r;
-      if (early_uv) {
-        only.u = dv.u;
-        only.v = dv.v;
+    auto drop = [&](void* dptr) {
+      int m = 0;
+      for (int i = 0; i < nback; ++i)
+        if (back[i].dptr != dptr) back[m++] = back[i];
+      nback = m;
+    };
+    struct Sel { float** f; unsigned bit; } sel[] = {
+        {&dv.r, DL_R}, {&dv.u, DL_U}, {&dv.v, DL_V}, {&dv.rho, DL_RHO}, {&dv.p, DL_P},
+        {&dv.dudt, DL_DUDT}, {&dv.dvdt, DL_DVDT}, {&dv.nw, DL_REST}, {&dv.drhodt, DL_REST},
+        {&dv.mass, DL_REST}, {&dv.eta, DL_REST}, {&dv.T, DL_REST}, {&dv.dTdt, DL_REST},
+        {&dv.kappa, DL_REST}, {&dv.Cp, DL_REST}};
+    for (const Sel& q : sel)
+      if (!(mask & q.bit) && *q.f) {
+        drop(*q.f);
+        *q.f = nullptr;
       }
-      dv = only;
-    } else {
-      dv.r = nullptr;
-      if (early_uv) dv.u = dv.v = nullptr;
+    if (!(mask & DL_REST) && dv.tag) {
+      drop(dv.tag);
+      dv.tag = nullptr;
     }
     if (nback == 0) return SPHB200_OK;
   }
@@ -1370,16 +1374,30 @@ int sphb200_engine_advance_host(sphb200_engine* e, double dt, const sphb200_stat
   // r is final once the particles are integrated and reordered; u and v too unless the wall
   // sweep (generalized wall BC) or the case's bc table rewrites them after forward().  With
   // v == u (no transport velocity) the frame's v is written by the force sweep: not early.
-  const bool early_uv = !(e->cfg.flags & SPHB200_F_BC_TRICK) && !bc_table_on(e->cfg) && !v_is_u;
+  // rho and p are final after the density / renormalisation / wall stages (the force sweep
+  // reads them only) unless the bc table sets p afterwards.
+  const bool bc_on = bc_table_on(e->cfg);
+  const bool early_uv = !(e->cfg.flags & SPHB200_F_BC_TRICK) && !bc_on && !v_is_u;
+  const unsigned m_early = DL_R | (early_uv ? (DL_U | DL_V) : 0u);
+  const unsigned m_mid = bc_on ? 0u : (DL_RHO | DL_P);
   CK(cudaEventRecord(e->ev_io_fork, st));
   CK(cudaStreamWaitEvent(e->io_side, e->ev_io_fork, 0));
-  rc = download_impl(e, out, e->n, nullptr, 1, (void*)e->io_side, 1, early_uv);
+  rc = download_impl(e, out, e->n, nullptr, 1, (void*)e->io_side, m_early);
   if (rc) return rc;
+  for (int stage = 0; stage < 4; ++stage) {  // run_forward, with the rho / p copy before the force stage
+    if (stage == 3 && m_mid) {
+      CK(cudaEventRecord(e->ev_io_fork, st));
+      CK(cudaStreamWaitEvent(e->io_side, e->ev_io_fork, 0));
+      rc = download_impl(e, out, e->n, nullptr, 1, (void*)e->io_side, m_mid);
+      if (rc) return rc;
+    }
+    int wrote;
+    rc = forward_stage(e, stage, flags, v_is_u, st, &wrote);
+    if (rc) return rc;
+  }
   CK(cudaEventRecord(e->ev_io_join, e->io_side));
-  rc = run_forward(e, flags, v_is_u, st);
-  if (rc) return rc;
   if (e->profile) cudaEventRecord(e->ev[5], st);
-  rc = download_impl(e, out, e->n, nullptr, 1, stream, 2, early_uv);
+  rc = download_impl(e, out, e->n, nullptr, 1, stream, DL_ALL & ~(m_early | m_mid));
   if (rc) return rc;
   CK(cudaStreamWaitEvent(st, e->ev_io_join, 0));  // the caller's stream sees the whole result
   return SPHB200_OK;

@@ -221,10 +221,14 @@ def test_advance_host_moves_only_live_fields(kw):
     dict(case="tgv", dim=2, dx=0.04),                                    # v == u: r leaves early
     dict(case="db", dim=2, dx=0.05),                                     # wall sweep + bc table: r only
     dict(case="ht", dim=3, dx=0.05),
+    dict(case="tgv", dim=2, dx=0.04, solver="RIE", density_evolution=True),   # rho, p before the force stage
+    dict(case="tgv", dim=3, dx=2 * np.pi / 12, solver="DELTA", density_evolution=True),
+    dict(case="db", dim=2, dx=0.05, density_evolution=True, density_renormalize=True),
 ])
 def test_advance_host_overlapped_download_is_bit_exact(kw):
     """sphb200_engine_advance_host sends r (and u, v where nothing rewrites them after the
-    reorder pass) back to the host while the sweeps run: the result must equal, bit for bit,
+    reorder pass) back to the host while the sweeps run, and rho, p while the force sweep runs
+    (unless a bc table sets p afterwards): the result must equal, bit for bit,
     upload + step + download of the same entries on a second engine (same upload order, so the
     sums run in the same order), over several steps and with pinned host buffers."""
     import torch
