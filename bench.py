@@ -550,63 +550,78 @@ def run_slab(args, world, rank, local, saved_stdout):
     print(json.dumps(line))
 
 
+def cpu_workers():
+    """How many single-core oracle workers the host takes: one per core, bounded by memory
+    (a worker of the default sample peaks near 0.9 GB) and by 32."""
+    cores = os.cpu_count() or 1
+    try:
+        with open("/proc/meminfo") as f:
+            avail_kb = next(int(l.split()[1]) for l in f if l.startswith("MemAvailable"))
+        cores = min(cores, max(1, int(avail_kb / 1024 / 1024 * 0.5 / 1.5)))
+    except Exception:
+        pass
+    return max(1, min(cores, 32))
+
+
+def run_cpu_arm(args, steps, warmup=1):
+    """The CPU implementation of the path on ALL host cores: one oracle worker per core
+    (oracle/cpu_arm.py: the NumPy restatement of the reference's edge-list algorithm on an
+    independent periodic box each), aggregate particle-updates/s over the common window
+    [first worker's start, last worker's end]."""
+    workers = cpu_workers()
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1",
+               CUDA_VISIBLE_DEVICES="")
+    cmd = [sys.executable, "-m", "oracle.cpu_arm", "--workload", args.workload, "--nx",
+           str(args.cpu_nx), "--warmup", str(warmup), "--steps", str(steps)]
+    procs = [subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, text=True)
+             for _ in range(workers)]
+    res = []
+    for p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("oracle.cpu_arm worker failed")
+        res.append(json.loads(out.strip().splitlines()[-1]))
+    n = res[0]["n"]
+    window = max(r["t1"] for r in res) - min(r["t0"] for r in res)
+    value = workers * n * steps / window
+    per_core = float(np.mean([r["n"] * r["steps"] / (r["t1"] - r["t0"]) for r in res]))
+    return dict(value=value, workers=workers, n=n, window_s=window, per_core=per_core)
+
+
 def cpu_baseline(args, bounded=True):
     """The NumPy oracle (port of the reference algorithm) on the host cores, on a
     bounded sample of the same workload."""
-    from oracle import cases, integrator
-
-    nx = args.cpu_nx
-    if args.workload == "tgv3d":
-        setup = cases.make_case("tgv", dim=3, dx=2 * np.pi / nx, dtype=np.float32, tvf=1.0,
-                                viscosity=0.02)
-    elif args.workload == "ht3d":
-        setup = cases.make_case("ht", dim=3, dx=1.0 / nx, dtype=np.float32)
-    else:
-        setup = cases.make_case("tgv", dim=2, dx=1.0 / nx, dtype=np.float32, tvf=1.0)
-    n = len(setup.state["r"])
-    steps = args.cpu_steps
-    integrator.simulate(setup, 1, fast_segment_sum=True)
-    t0 = time.perf_counter()
-    integrator.simulate(setup, steps, fast_segment_sum=True)
-    dt = time.perf_counter() - t0
-    return {"value": n * steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{args.workload} nx={nx} N={n}, {steps} steps, NumPy restatement of the "
-                      "reference edge-list algorithm (jax is not installable here), "
-                      f"{dt:.1f} s wall, host has {os.cpu_count()} cores"}
+    r = run_cpu_arm(args, args.cpu_steps)
+    return {"value": r["value"], "unit": UNIT, "cores": r["workers"], "kind": "port",
+            "sample": f"{args.workload} nx={args.cpu_nx} N={r['n']} per worker, {args.cpu_steps} "
+                      f"steps, {r['workers']} single-core workers (one periodic box each) of the "
+                      "NumPy restatement of the reference edge-list algorithm (jax is not "
+                      f"installable here), {r['window_s']:.1f} s wall, "
+                      f"{r['per_core']:.0f} particle-updates/s per worker, host has "
+                      f"{os.cpu_count()} cores"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import cases, integrator
-
-    nx = args.cpu_nx
-    if args.workload == "tgv3d":
-        setup = cases.make_case("tgv", dim=3, dx=2 * np.pi / nx, dtype=np.float32, tvf=1.0,
-                                viscosity=0.02)
-    elif args.workload == "ht3d":
-        setup = cases.make_case("ht", dim=3, dx=1.0 / nx, dtype=np.float32)
-    else:
-        setup = cases.make_case("tgv", dim=2, dx=1.0 / nx, dtype=np.float32, tvf=1.0)
-    n = len(setup.state["r"])
     sub = max(1, args.cpu_steps // 4)
-    for _ in range(min(args.warmup, 1)):
-        integrator.simulate(setup, 1, fast_segment_sum=True)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        integrator.simulate(setup, sub, fast_segment_sum=True)
-    dt = time.perf_counter() - t0
-    value = n * sub * args.steps / dt
-    sample = (f"{args.workload} nx={nx} N={n}: each bench step = {sub} advance() calls of the NumPy "
-              "port of the reference algorithm (jax/jaxlib absent, reference not runnable)")
+    r = run_cpu_arm(args, sub * args.steps, warmup=min(args.warmup, 1))
+    value = r["value"]
+    sample = (f"{args.workload} nx={args.cpu_nx} N={r['n']} per worker: each bench step = {sub} "
+              f"advance() calls on each of {r['workers']} single-core workers (one periodic box "
+              "each) of the NumPy port of the reference algorithm (jax/jaxlib absent, reference "
+              f"not runnable); {r['per_core']:.0f} particle-updates/s per worker")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": r["window_s"] / args.steps * 1e3,
+        "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload} (bounded sample nx={nx} N={n})"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "config": {"workload": f"{args.workload} (bounded sample nx={args.cpu_nx} N={r['n']} x "
+                               f"{r['workers']} workers)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["workers"], "kind": "port",
+                         "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
