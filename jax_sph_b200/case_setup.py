@@ -131,3 +131,31 @@ def _bare_spec(box_size, dx):
     lat.wall_axis = -1
     lat.dx = dx
     return lat
+
+
+def slab_planes(engine, n_last: int, dx: float) -> Tuple[int, int]:
+    """Lattice planes [k_lo, k_hi) of the last axis whose particles a SlabEngine rank owns at
+    the start: plane k sits at (k + 0.5) dx (float32, as the kernel writes it) and belongs to
+    the rank whose cell layers [z0, z1) contain it (slab.layer_of, the rule select_own applies
+    to a global state).  Layers grow with k, so the planes of a rank are one range."""
+    from .slab import layer_of
+
+    ax = ((np.arange(n_last, dtype=np.float32) + np.float32(0.5)) * np.float32(dx)).astype(np.float32)
+    lay = layer_of(ax, engine.inv_cell, engine.layers)
+    mine = np.nonzero((lay >= engine.z0) & (lay < engine.z1))[0]
+    if len(mine) == 0:
+        return 0, 0
+    return int(mine[0]), int(mine[-1]) + 1
+
+
+def init_slab(engine, box_size, dx, **spec):
+    """Device-made start of ONE rank of a slab-decomposed run: the rank's lattice planes are
+    generated where they will live (no global state on the host, no host-to-device copy) and
+    uploaded with their full-lattice ids.  Returns the number of particles the rank holds."""
+    n = lattice_shape(box_size, dx)
+    lat = lattice_spec(box_size, dx, planes=slab_planes(engine, n[-1], dx), **spec)
+    state = init_lattice(lat, with_ids=True)
+    ids = state.pop("ids")
+    engine.upload(state, ids)
+    return int(ids.numel())
+

@@ -171,3 +171,55 @@ def test_engine_steps_from_the_device_made_state():
     for k in ("r", "u", "rho"):
         scale = float(np.abs(res[0][k]).max())
         assert np.abs(res[1][k] - res[0][k]).max() <= 1e-5 * scale, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("workload,nx,nranks", [("tgv3d", 24, 3), ("ht3d", 40, 2), ("tgv2d", 60, 4)])
+def test_slab_ranks_start_from_device_made_planes(workload, nx, nranks):
+    """case_setup.init_slab: every rank of a slab ring generates its own planes on the device;
+    the ring then holds exactly the particles select_own() cuts out of the host-made global
+    state, and steps to the same fields (one device, local ring: tests/test_gpu_slab.py)."""
+    import bench
+    from jax_sph_b200 import SlabEngine, make_config
+    from jax_sph_b200.slab import assemble, step_local_ring
+
+    host, meta = bench.lattice_state(workload, nx)
+    n = len(host["r"])
+    kw = dict(meta.get("cfg_kwargs", {}))
+
+    def cfg():
+        return make_config(meta["dim"], meta["box"], meta["dx"], meta["dt"], tvf=meta["tvf"],
+                           c_ref=meta["c_ref"], p_ref=meta["p_ref"], **kw)
+
+    if workload == "ht3d":
+        spec = dict(wall_axis=1, n_walls=meta["n_walls"], hot=(0.25, 0.75), T_hot=1.23,
+                    p=meta["p_bg"], eta=meta["viscosity"], kappa=meta["kappa"], Cp=meta["Cp"])
+    else:
+        spec = dict(velocity=workload, eta=meta["viscosity"])
+    dev_ring = [SlabEngine(cfg(), r, nranks) for r in range(nranks)]
+    host_ring = [SlabEngine(cfg(), r, nranks) for r in range(nranks)]
+    total = 0
+    for e, h in zip(dev_ring, host_ring):
+        rows = case_setup.init_slab(e, meta["box"], meta["dx"], **spec)
+        local, ids = h.select_own(host)
+        h.upload(local, ids)
+        assert rows == len(ids)
+        got_local, got_ids = e.download()
+        assert np.array_equal(np.sort(got_ids.numpy()), np.sort(ids))
+        total += rows
+    assert total == n
+    for ring in (dev_ring, host_ring):
+        step_local_ring(ring, meta["dt"], 6)
+    res = []
+    for ring in (dev_ring, host_ring):
+        parts = []
+        for e in ring:
+            assert e.error(reduce=False) == 0
+            local, ids = e.download()
+            parts.append(({k: v.numpy() for k, v in local.items()}, ids.numpy()))
+        res.append(assemble(parts, n))
+    for k in ("r", "u", "rho", "T"):
+        scale = float(np.abs(res[1][k]).max())
+        assert np.abs(res[0][k] - res[1][k]).max() <= 1e-5 * scale, k
+    assert np.array_equal(res[0]["tag"], res[1]["tag"])
+
