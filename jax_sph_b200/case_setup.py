@@ -159,3 +159,27 @@ def init_slab(engine, box_size, dx, **spec):
     engine.upload(state, ids)
     return int(ids.numel())
 
+
+def apply_state0(state: Dict, state0: Dict, keys: Sequence[str] = ("r",)) -> Dict:
+    """The restart / relaxed-start rule of SimulationSetup.initialize() (jax_sph/case_setup.py:
+    184-194): for every key in `keys`, the FLUID entries of `state` are overwritten by the
+    fluid entries of `state0` (a snapshot read with io_state.read_h5), walls keep the freshly
+    generated values.  Works on NumPy arrays and on torch tensors (host or CUDA); `state` is
+    modified in place and returned."""
+    FLUID = 0
+    mask, mask0 = state["tag"] == FLUID, state0["tag"] == FLUID
+    for k in state:
+        if k not in keys:
+            continue
+        if k not in state0:
+            raise ValueError(f"Key {k} not found in state0 file.")
+        src = state0[k][mask0]
+        if tuple(state[k][mask].shape) != tuple(src.shape):
+            raise ValueError(f"Shape mismatch for key {k} in state0 file.")
+        if hasattr(state[k], "is_cuda") and not hasattr(src, "is_cuda"):
+            import torch
+
+            src = torch.as_tensor(np.ascontiguousarray(src), device=state[k].device)
+        state[k][mask] = src
+    return state
+

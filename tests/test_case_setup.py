@@ -68,6 +68,28 @@ def test_no_cpu_fallback():
         case_setup.init_lattice(case_setup.lattice_spec([1.0, 1.0], 0.1))
 
 
+def test_apply_state0_overwrites_fluid_entries_only():
+    """case_setup.py:184-194: restart keys come from the snapshot for FLUID particles only."""
+    rng = np.random.default_rng(1)
+    tag = np.array([0, 1, 0, 0, 3, 1], dtype=np.int32)
+    state = {"r": rng.random((6, 2), dtype=np.float32), "u": rng.random((6, 2), dtype=np.float32),
+             "rho": np.ones(6, dtype=np.float32), "tag": tag}
+    # the snapshot holds the same fluid particles, walls in another place of the arrays
+    tag0 = np.array([1, 0, 0, 1, 0, 3], dtype=np.int32)
+    snap = {"r": rng.random((6, 2), dtype=np.float32), "u": rng.random((6, 2), dtype=np.float32),
+            "rho": np.full(6, 2.0, dtype=np.float32), "tag": tag0}
+    before = {k: v.copy() for k, v in state.items()}
+    case_setup.apply_state0(state, snap, keys=("r", "rho"))
+    assert np.array_equal(state["r"][tag == 0], snap["r"][tag0 == 0])
+    assert np.array_equal(state["r"][tag != 0], before["r"][tag != 0])
+    assert np.array_equal(state["rho"], np.where(tag == 0, 2.0, 1.0).astype(np.float32))
+    assert np.array_equal(state["u"], before["u"])  # not in keys
+    with pytest.raises(ValueError, match="not found"):
+        case_setup.apply_state0(state, {"tag": tag0}, keys=("r",))
+    with pytest.raises(ValueError, match="Shape mismatch"):
+        case_setup.apply_state0(state, {"r": snap["r"][:4], "tag": tag0[:4]}, keys=("r",))
+
+
 # ---------------------------------------------------------------- device (B200)
 def _np(state):
     return {k: v.cpu().numpy() for k, v in state.items()}

@@ -108,3 +108,32 @@ def test_simulate_tgv_equals_the_oracle_loop(tmp_path):
     assert re.fullmatch(rf"0+/{seq}, t=\d\.\d{{4}}, Ekin=\d\.\d{{5}}, u_max=\d\.\d{{5}}", stat_lines[0])
     ek = [float(re.search(r"Ekin=([\d.]+)", l).group(1)) for l in stat_lines]
     assert 0.2 < ek[0] < 0.26 and ek[-1] <= ek[0]  # 2D TGV: E_kin(0) = 1/4 per unit area
+
+
+@pytest.mark.gpu
+def test_simulate_with_a_prepared_setup(tmp_path):
+    """Cases that are not built on the device go in prepared (the reference's initialize()
+    results as plain attributes): dam break with walls, bc table and gravity, vtk output."""
+    from _util import assert_close
+    from jax_sph_b200 import io_state
+    from oracle import cases, integrator
+
+    setup = cases.make_case("db", dim=2, dx=0.05, dtype=np.float32)
+    setup.sequence_length = 6
+    cfg = sim.defaults(case=dict(name="db", dim=2, dx=0.05), solver=dict(name="SPH"),
+                       io=dict(write_type=["vtk"], write_every=4, data_path=str(tmp_path),
+                               print_props=["Ekin", "u_max", "rho_min", "p_max"]))
+    lines = []
+    eng = sim.simulate(cfg, setup=setup, log=lines.append)
+    ref = integrator.simulate(setup, setup.sequence_length + 2, fast_segment_sum=True)
+    got = {k: v.numpy() for k, v in eng.download(host=True).items()}
+    for k in ("r", "u", "rho", "p"):
+        assert_close(k, got[k], ref[k], setup, factor=3.0, what="simulate(db) final state")
+    assert "rho_min=" in lines[0] and "p_max=" in lines[0]
+    files = sorted(f for f in os.listdir(eng.out_dir) if f.endswith(".vtk"))
+    assert files == ["traj_0.vtk", "traj_4.vtk"]
+    snap = io_state.read_vtk(os.path.join(eng.out_dir, "traj_4.vtk"))
+    ref5 = integrator.simulate(setup, 5, fast_segment_sum=True)
+    assert_close("r", snap["r"][:, :2], ref5["r"], setup, factor=3.0, what="vtk snapshot")
+    assert np.array_equal(snap["tag"], setup.state["tag"])
+
