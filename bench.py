@@ -424,6 +424,7 @@ def run_slab(args, world, rank, local, saved_stdout):
     import torch.distributed as dist
 
     from jax_sph_b200 import SlabEngine, make_config
+    from jax_sph_b200.engine import STATE_KEYS
     from jax_sph_b200.slab import layer_of
 
     meta = lattice_meta(args.workload, args.nx)
@@ -490,17 +491,17 @@ def run_slab(args, world, rank, local, saved_stdout):
 
     # end to end: this rank's slab host -> device, one advance (with its exchanges), device -> host
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    host_in, ids_h = eng.download()
-    bytes_in = sum(v.numel() * v.element_size() for v in host_in.values()) + ids_h.numel() * 4
+    read, written = eng.live_fields()
+    host_in, ids_h = eng.download([k for k in STATE_KEYS if k in read or k in written])
+    bytes_in = sum(host_in[k].numel() * host_in[k].element_size() for k in read) + ids_h.numel() * 4
+    bytes_out = sum(v.numel() * v.element_size() for v in host_in.values()) + ids_h.numel() * 4
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        eng.upload(host_in, ids_h)
-        eng.step(meta["dt"], 1)
-        host_in, ids_h = eng.download()
+        host_in, ids_h = eng.advance_host(meta["dt"], host_in, ids_h)
     barrier()
     e2e_s = reduce_max(time.perf_counter() - t0)
-    bytes_all = torch.tensor([bytes_in], device="cuda", dtype=torch.int64)
+    bytes_all = torch.tensor([bytes_in, bytes_out], device="cuda", dtype=torch.int64)
     dist.all_reduce(bytes_all)
     barrier()
     dist.destroy_process_group()
@@ -540,9 +541,12 @@ def run_slab(args, world, rank, local, saved_stdout):
                                 "per-rank state fits L2 (strong scaling of the named size)"},
         "clocks": clocks, "gpu_launches": int(launches), "device_error_word": err,
         "e2e": {"value": n_total * e2e_steps / e2e_s, "unit": UNIT,
-                "h2d_bytes_per_step": int(bytes_all.item()), "d2h_bytes_per_step": int(bytes_all.item()),
+                "h2d_bytes_per_step": int(bytes_all[0].item()), "d2h_bytes_per_step": int(bytes_all[1].item()),
                 "steps": e2e_steps,
-                "what": "per rank: SlabEngine.upload(own slab, host) + step (with exchanges) + download(host), every step"},
+                "what": "per rank, every step: SlabEngine.advance_host(dt, pinned host slab) = H2D of the "
+                        f"entries advance() reads ({','.join(read)}) + ids, one step with its ring "
+                        "exchanges, D2H of the entries it reads or writes (the particle set changes "
+                        "by migration) + ids"},
         "roofline": roof,
         "cpu_baseline": {"value": None, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": "reported at N=1 only"},

@@ -137,6 +137,29 @@ def stats_from_words(words, props):
     return res
 
 
+def live_fields(cfg):
+    """(read, written): the state entries one `advance(dt, state, neighbors)`
+    (jax_sph/integrator.py:22-56 + jax_sph/solver.py:705-949) of THIS solver variant reads
+    and the ones it changes.  Everything else passes through the reference's advance()
+    untouched (`v` is overwritten before it is read, integrator.py:27; `p` is recomputed
+    from rho, solver.py:801, and only the Riemann continuity equation reads the incoming
+    one, :773-791; `drhodt` is an output of the evolution variants only; T / dTdt / kappa /
+    Cp matter with heat conduction only, :832-849; `nw` with free-slip or Riemann walls)."""
+    f = cfg.flags
+    rie = cfg.solver == _lib.SOLVER["RIE"]
+    evol, heat = bool(f & _lib.F_RHO_EVOL), bool(f & _lib.F_HEAT)
+    has_nw = rie or bool(f & _lib.F_FREE_SLIP)
+    read = ["r", "u", "dudt", "dvdt", "tag", "mass", "eta", "rho"]
+    read += ["p"] if (rie and evol) else []
+    read += ["T", "dTdt", "kappa", "Cp"] if heat else []
+    read += ["nw"] if has_nw else []
+    written = ["r", "u", "v", "dudt", "dvdt", "rho", "p"]
+    written += ["drhodt"] if evol else []
+    written += ["T", "dTdt"] if heat else []
+    written += ["nw"] if (has_nw and getattr(cfg, "wall_layer", None)) else []
+    return tuple(read), tuple(written)
+
+
 def config_from_setup(setup, **tuning):
     """`setup` is anything exposing the fields of the reference's
     SimulationSetup / WCSPH call (jax_sph/simulate.py:49-69): used by tests and
@@ -288,26 +311,9 @@ class Engine:
         return out
 
     def live_fields(self):
-        """(read, written): the state entries one `advance(dt, state, neighbors)`
-        (jax_sph/integrator.py:22-56 + jax_sph/solver.py:705-949) of THIS solver variant reads
-        and the ones it changes.  Everything else passes through the reference's advance()
-        untouched (`v` is overwritten before it is read, integrator.py:27; `p` is recomputed
-        from rho, solver.py:801, and only the Riemann continuity equation reads the incoming
-        one, :773-791; `drhodt` is an output of the evolution variants only; T / dTdt / kappa /
-        Cp matter with heat conduction only, :832-849; `nw` with free-slip or Riemann walls)."""
-        f = self.cfg.flags
-        rie = self.cfg.solver == _lib.SOLVER["RIE"]
-        evol, heat = bool(f & _lib.F_RHO_EVOL), bool(f & _lib.F_HEAT)
-        has_nw = rie or bool(f & _lib.F_FREE_SLIP)
-        read = ["r", "u", "dudt", "dvdt", "tag", "mass", "eta", "rho"]
-        read += ["p"] if (rie and evol) else []
-        read += ["T", "dTdt", "kappa", "Cp"] if heat else []
-        read += ["nw"] if has_nw else []
-        written = ["r", "u", "v", "dudt", "dvdt", "rho", "p"]
-        written += ["drhodt"] if evol else []
-        written += ["T", "dTdt"] if heat else []
-        written += ["nw"] if (has_nw and getattr(self.cfg, "wall_layer", None)) else []
-        return tuple(read), tuple(written)
+        """(read, written) state entries of one advance() of this solver variant: see
+        `live_fields` (module level)."""
+        return live_fields(self.cfg)
 
     def advance_host(self, dt: float, state: Dict, out: Optional[Dict] = None):
         """`advance(dt, state, neighbors)` on HOST buffers, the call a reference user makes with

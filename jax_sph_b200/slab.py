@@ -228,6 +228,25 @@ class SlabEngine:
                 self._exchange(nb, phase)
                 phase += 1
 
+    def live_fields(self):
+        """(read, written) of one advance() of this solver variant (engine.live_fields)."""
+        from .engine import live_fields
+
+        return live_fields(self.cfg)
+
+    def advance_host(self, dt: float, local: Dict, ids):
+        """One `advance(dt, state, neighbors)` on this rank's HOST-resident particles: copies
+        host -> device only the entries advance() reads, steps (with the ring exchanges), and
+        copies device -> host the entries it writes PLUS the ones it reads -- particles migrate
+        between ranks during the step, so the constant entries (tag, mass, eta, ...) of the new
+        particle set have to come back with it.  Returns (local state, ids) of the rank's
+        particles after the step; entries advance() neither reads nor writes are dropped."""
+        read, written = self.live_fields()
+        self.upload({k: local[k] for k in read}, ids)
+        self.step(dt, 1)
+        keys = [k for k in STATE_KEYS if k in read or k in written]
+        return self.download(keys)
+
     def counts(self) -> Dict[str, int]:
         out = (C.c_int32 * 8)()
         _lib.check(self.lib.sphb200_slab_counts(self._h, C.byref(out), _stream_ptr()))
