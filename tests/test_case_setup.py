@@ -90,6 +90,32 @@ def test_apply_state0_overwrites_fluid_entries_only():
         case_setup.apply_state0(state, {"r": snap["r"][:4], "tag": tag0[:4]}, keys=("r",))
 
 
+@pytest.mark.parametrize("n_last,dx,layers,nranks", [(256, 2 * np.pi / 256, 170, 8), (427, 1 / 854, 142, 8),
+                                                     (30, 1 / 30, 6, 4), (50, 0.02, 16, 3), (7, 0.1, 4, 4)])
+def test_slab_planes_partition_the_lattice(n_last, dx, layers, nranks):
+    """The plane ranges of the ranks of a ring are disjoint, ordered and cover the lattice, and
+    agree with the rule select_own applies to a global state (slab.own_rows)."""
+    from types import SimpleNamespace
+
+    from jax_sph_b200.slab import own_rows, slab_range
+
+    inv_cell = layers / (n_last * dx)
+    ax = ((np.arange(n_last, dtype=np.float32) + np.float32(0.5)) * np.float32(dx)).astype(np.float32)
+    nxt = 0
+    for rank in range(nranks):
+        z0, z1 = slab_range(layers, rank, nranks)
+        eng = SimpleNamespace(inv_cell=inv_cell, layers=layers, z0=z0, z1=z1)
+        k_lo, k_hi = case_setup.slab_planes(eng, n_last, dx)
+        mine = own_rows(ax, inv_cell, layers, rank, nranks)
+        if len(mine) == 0:
+            assert k_lo == k_hi
+            continue
+        assert (k_lo, k_hi) == (int(mine[0]), int(mine[-1]) + 1) and k_hi - k_lo == len(mine)
+        assert k_lo == nxt
+        nxt = k_hi
+    assert nxt == n_last
+
+
 # ---------------------------------------------------------------- device (B200)
 def _np(state):
     return {k: v.cpu().numpy() for k, v in state.items()}
