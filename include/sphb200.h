@@ -321,6 +321,19 @@ int64_t sphb200_lattice_rows(const sphb200_lattice *l);
 /* Fill a state in the reference layout, DEVICE pointers; NULL members are skipped; dudt, dvdt,
  * drhodt, dTdt, nw are zeroed.  `ids` (int32, device) may be NULL. */
 int sphb200_init_lattice(const sphb200_lattice *l, sphb200_state *out, int32_t *ids, void *stream);
+/* u (and v, either may be NULL) = the case's velocity field at the given positions (device
+ * pointers, (n, dim) float32): vmap(self._init_velocity2D / 3D)(r), case_setup.py:146-150, for
+ * starts whose positions do not come from the lattice kernel (noise, relaxed states). */
+int sphb200_eval_velocity(int32_t dim, int64_t n, int32_t velocity, const float *r, float *u,
+                          float *v, void *stream);
+/* Position noise of SimulationSetup.initialize() (case_setup.py:138-144, utils.py:120-125):
+ * r += std * N(0, 1) on the FLUID particles (tag NULL: all), wrapped into the periodic box as
+ * shift_fn does (jnp.mod(r + dr, side), space.py:207-209).  The deviates come from a
+ * counter-based Philox-4x32-10 generator keyed by `seed` and the particle's row (`ids`, or the
+ * array index when NULL), Box-Muller: the same start for any slab decomposition.  NOT
+ * jax.random's threefry stream -- same distribution, other numbers. */
+int sphb200_add_noise(int32_t dim, int64_t n, float *r, const int32_t *tag, const int32_t *ids,
+                      double std, uint64_t seed, const double box[3], void *stream);
 
 /* ---- stateless entry points (device pointers, caller-owned workspace) ----- */
 int sphb200_workspace_bytes(const sphb200_config *cfg, int64_t n, size_t *bytes);

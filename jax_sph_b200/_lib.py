@@ -106,6 +106,9 @@ SYMBOLS = {
                                    C.POINTER(C.c_int64)]),
     "sphb200_lattice_rows": (C.c_int64, [C.POINTER(Lattice)]),
     "sphb200_init_lattice": (C.c_int, [C.POINTER(Lattice), C.POINTER(State), _P, _P]),
+    "sphb200_eval_velocity": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P]),
+    "sphb200_add_noise": (C.c_int, [C.c_int32, C.c_int64, _P, _P, _P, C.c_double, C.c_uint64,
+                                    C.POINTER(C.c_double * 3), _P]),
     "sphb200_workspace_bytes": (C.c_int, [C.POINTER(Config), C.c_int64, C.POINTER(C.c_size_t)]),
     "sphb200_neighbor_list": (C.c_int, [C.POINTER(Config), C.c_int64, _P, _P, C.c_int64, C.c_int,
                                         _P, _P, _P, C.c_size_t, _P]),

@@ -11,9 +11,13 @@ Mirrors, with the output resident in HBM (torch CUDA tensors in the reference's 
 The reference builds these with NumPy ``meshgrid`` + ``vstack`` on the host and ships the
 whole state to the device; here one write-only kernel (csrc/init.cuh) fills the arrays, also
 per slab (``planes``) for the multi-GPU engine, so that a 64 M-particle start costs
-milliseconds.  Position noise (``case.r0_noise_factor``, jax.random) and relaxed starts
-(``case.r0_type == "relaxed"``, read from a state file) stay on the host side: out of scope.
-All compute goes through ``sphb200_init_lattice`` (include/sphb200.h); no CPU fallback.
+milliseconds.  Position noise (``case.r0_noise_factor``) is added on the device as well
+(``add_noise``: counter-based Philox deviates keyed by seed and lattice row -- the same
+distribution as the reference's jax.random stream, not the same numbers), and the case's
+velocity field can be evaluated at any positions (``eval_velocity``: noisy and relaxed starts,
+``case.r0_type == "relaxed"`` with the positions read from a state file).
+All compute goes through ``sphb200_init_lattice`` / ``sphb200_add_noise`` /
+``sphb200_eval_velocity`` (include/sphb200.h); no CPU fallback.
 """
 
 import ctypes as C
@@ -182,4 +186,54 @@ def apply_state0(state: Dict, state0: Dict, keys: Sequence[str] = ("r",)) -> Dic
             src = torch.as_tensor(np.ascontiguousarray(src), device=state[k].device)
         state[k][mask] = src
     return state
+
+
+def add_noise(state: Dict, std: float, seed: int, box_size, ids=None) -> Dict:
+    """`r = shift_fn(r, get_noise_masked(r.shape, tag == FLUID, key, std))` of
+    SimulationSetup.initialize() (jax_sph/case_setup.py:138-144) on CUDA tensors, in place.
+    `ids` (or state["ids"]): full-lattice rows of a slab's particles, so that every
+    decomposition draws the same deviates."""
+    from .engine import _stream_ptr
+
+    r = state["r"]
+    if not r.is_cuda:
+        raise _lib.Sphb200Error("add_noise works on CUDA tensors (there is no CPU fallback)")
+    n, dim = r.shape
+    box = (C.c_double * 3)(*([float(b) for b in np.asarray(box_size, dtype=np.float64).reshape(-1)]
+                             + [1.0])[:3])
+    tag = state.get("tag")
+    ids = ids if ids is not None else state.get("ids")
+    _lib.check(_lib.load().sphb200_add_noise(
+        dim, n, C.c_void_p(r.data_ptr()), C.c_void_p(tag.data_ptr() if tag is not None else None),
+        C.c_void_p(ids.data_ptr() if ids is not None else None), float(std),
+        int(seed) & 0xFFFFFFFFFFFFFFFF, C.byref(box), _stream_ptr()))
+    return state
+
+
+def eval_velocity(state: Dict, velocity: str) -> Dict:
+    """`u = v = vmap(self._init_velocity{2,3}D)(r)` (case_setup.py:146-150) at the CURRENT
+    positions of `state` (CUDA tensors), in place."""
+    import torch
+
+    from .engine import _stream_ptr
+
+    if velocity not in _VEL:
+        raise _lib.Sphb200Error(f"velocity {velocity!r} is not one of {tuple(_VEL)}")
+    r = state["r"]
+    if not r.is_cuda:
+        raise _lib.Sphb200Error("eval_velocity works on CUDA tensors (there is no CPU fallback)")
+    n, dim = r.shape
+    for k in ("u", "v"):
+        if k not in state:
+            state[k] = torch.empty_like(r)
+    _lib.check(_lib.load().sphb200_eval_velocity(
+        dim, n, _VEL[velocity], C.c_void_p(r.data_ptr()), C.c_void_p(state["u"].data_ptr()),
+        C.c_void_p(state["v"].data_ptr()), _stream_ptr()))
+    return state
+
+
+def relaxed_state_name(case_name: str, dim: int, dx: float, seed: int) -> str:
+    """File stem of a relaxed start, `_get_relaxed_r0` (case_setup.py:277-280) and the name
+    write_state gives the last state of a relaxation run (io_state.py:57-59): tgv_3_0.02_42."""
+    return "_".join([str(case_name), str(dim), str(dx), str(seed)])
 

@@ -1587,6 +1587,43 @@ int sphb200_engine_get_stats(sphb200_engine* e, double out[SPHB200_NSTATS], void
   return SPHB200_OK;
 }
 
+int sphb200_eval_velocity(int32_t dim, int64_t n, int32_t velocity, const float* r, float* u,
+                          float* v, void* stream) {
+  if ((dim != 2 && dim != 3) || n < 0 || !r) return SPHB200_EINVAL;
+  if (velocity < SPHB200_VEL_REST || velocity > SPHB200_VEL_TGV3D) return SPHB200_EINVAL;
+  if (velocity == SPHB200_VEL_TGV3D && dim != 3) return SPHB200_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SPHB200_ENODEV;
+  if (n == 0) return SPHB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t want = (n + 255) / 256;
+  const int nb = (int)(want < 148 * 8 ? want : 148 * 8);
+  if (dim == 2) k_eval_velocity<2><<<nb, 256, 0, st>>>(n, velocity, r, u, v);
+  else k_eval_velocity<3><<<nb, 256, 0, st>>>(n, velocity, r, u, v);
+  CK(cudaGetLastError());
+  return SPHB200_OK;
+}
+
+int sphb200_add_noise(int32_t dim, int64_t n, float* r, const int32_t* tag, const int32_t* ids,
+                      double std, uint64_t seed, const double box[3], void* stream) {
+  if ((dim != 2 && dim != 3) || n < 0 || !r || !box || !(std >= 0.0)) return SPHB200_EINVAL;
+  for (int d = 0; d < dim; ++d)
+    if (!(box[d] > 0.0)) return SPHB200_EINVAL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SPHB200_ENODEV;
+  if (n == 0 || std == 0.0) return SPHB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t want = (n + 255) / 256;
+  const int nb = (int)(want < 148 * 8 ? want : 148 * 8);
+  const float b2 = dim == 3 ? (float)box[2] : 1.0f;
+  if (dim == 2)
+    k_add_noise<2><<<nb, 256, 0, st>>>(n, r, tag, ids, (float)std, seed, (float)box[0], (float)box[1], b2);
+  else
+    k_add_noise<3><<<nb, 256, 0, st>>>(n, r, tag, ids, (float)std, seed, (float)box[0], (float)box[1], b2);
+  CK(cudaGetLastError());
+  return SPHB200_OK;
+}
+
 int64_t sphb200_engine_launches(const sphb200_engine* e) { return e ? e->launches : -1; }
 
 int sphb200_engine_profile(sphb200_engine* e, int enable) {

@@ -11,8 +11,29 @@
 #include <stdint.h>
 
 #include "../../include/sphb200.h"
+#include "common.cuh"
 
 namespace sphb200 {
+
+// ---- velocity field of a case at given positions (cases/tgv.py:37-51) ----------------------
+template <int DIM>
+__device__ __forceinline__ void case_velocity(int kind, const float (&x)[3], float (&u)[3]) {
+  u[0] = u[1] = u[2] = 0.f;
+  if (kind == SPHB200_VEL_TGV2D) {
+    float sx, cx, sy, cy;
+    sincosf(6.2831853071795864769f * x[0], &sx, &cx);
+    sincosf(6.2831853071795864769f * x[1], &sy, &cy);
+    u[0] = -1.0f * cx * sy;
+    u[1] = sx * cy;
+  } else if (kind == SPHB200_VEL_TGV3D) {
+    float sx, cx, sy, cy;
+    sincosf(x[0], &sx, &cx);
+    sincosf(x[1], &sy, &cy);
+    const float cz = cosf(x[2]);
+    u[0] = sx * cy * cz;
+    u[1] = -cx * sy * cz;
+  }
+}
 
 struct LatticeArgs {
   sphb200_lattice l;
@@ -58,21 +79,8 @@ __global__ void __launch_bounds__(256) k_init_lattice(const LatticeArgs a) {
       }
     }
 
-    float u[3] = {0.f, 0.f, 0.f};
-    if (l.velocity == SPHB200_VEL_TGV2D) {  // cases/tgv.py:37-43
-      float sx, cx, sy, cy;
-      sincosf(6.2831853071795864769f * x[0], &sx, &cx);
-      sincosf(6.2831853071795864769f * x[1], &sy, &cy);
-      u[0] = -1.0f * cx * sy;
-      u[1] = sx * cy;
-    } else if (l.velocity == SPHB200_VEL_TGV3D) {  // cases/tgv.py:45-51
-      float sx, cx, sy, cy;
-      sincosf(x[0], &sx, &cx);
-      sincosf(x[1], &sy, &cy);
-      const float cz = cosf(x[2]);
-      u[0] = sx * cy * cz;
-      u[1] = -cx * sy * cz;
-    }
+    float u[3];
+    case_velocity<DIM>(l.velocity, x, u);
 
     const sphb200_state& o = a.out;
 #pragma unroll
@@ -90,6 +98,71 @@ __global__ void __launch_bounds__(256) k_init_lattice(const LatticeArgs a) {
     if (o.Cp) o.Cp[row] = l.Cp;
     if (o.tag) o.tag[row] = tag;
     if (a.ids) a.ids[row] = (int32_t)id;
+  }
+}
+
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_eval_velocity(long long n, int kind,
+                                                       const float* __restrict__ r,
+                                                       float* __restrict__ u, float* __restrict__ v) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    float x[3] = {0.f, 0.f, 0.f}, w[3];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) x[d] = r[p * DIM + d];
+    case_velocity<DIM>(kind, x, w);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      if (u) u[p * DIM + d] = w[d];
+      if (v) v[p * DIM + d] = w[d];
+    }
+  }
+}
+
+// ---- position noise (case_setup.py:138-144, utils.py:120-125) --------------------------------
+// Philox-4x32-10 (Salmon et al. 2011): counter = (row, 0, 0, 0), key = seed.  Counter-based, so
+// a particle's deviates depend on its ROW in the full lattice only -- the same start for any
+// slab decomposition.  Not jax.random's threefry stream: same distribution, other numbers.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_add_noise(long long n, float* __restrict__ r,
+                                                   const int32_t* __restrict__ tag,
+                                                   const int32_t* __restrict__ ids, float std,
+                                                   unsigned long long seed, float bx, float by,
+                                                   float bz) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float box[3] = {bx, by, bz};
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    if (tag && tag[p] != SPHB200_TAG_FLUID) continue;  // get_noise_masked: fluid only
+    const unsigned long long row = ids ? (unsigned long long)(unsigned)ids[p] : (unsigned long long)p;
+    const uint4 x = philox4x32_10(make_uint4((unsigned)row, (unsigned)(row >> 32), 0u, 0u),
+                                  make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    // Box-Muller on two pairs: u1 in (0, 1], u2 in [0, 1)
+    const float a0 = ((float)(x.x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    const float a1 = (float)(x.y >> 8) * (1.0f / 16777216.0f);
+    const float b0 = ((float)(x.z >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    const float b1 = (float)(x.w >> 8) * (1.0f / 16777216.0f);
+    float s0, c0, s1, c1;
+    sincosf(6.2831853071795864769f * a1, &s0, &c0);
+    sincosf(6.2831853071795864769f * b1, &s1, &c1);
+    const float m0 = sqrtf(-2.0f * logf(a0)), m1 = sqrtf(-2.0f * logf(b0));
+    const float z[3] = {m0 * c0, m0 * s0, m1 * c1};
+    (void)s1;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)  // shift_fn: jnp.mod(r + dr, side), space.py:207-209
+      r[p * DIM + d] = mod_side(__fadd_rn(r[p * DIM + d], __fmul_rn(std, z[d])), box[d]);
   }
 }
 

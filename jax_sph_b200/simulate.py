@@ -15,8 +15,11 @@ the logging cadence instead of every step, so the loop has no per-step host sync
 reference's untimed ``advance(0.0, ...)`` compile call (simulate.py:108-109, result discarded)
 has nothing to compile.
 
-Cases.  ``cfg.case.name == "tgv"`` with a Cartesian start and no position noise is built on the
-device (case_setup.lattice_spec / init_lattice).  Every other case is passed in prepared:
+Cases.  ``cfg.case.name == "tgv"`` is built on the device (case_setup.lattice_spec /
+init_lattice / add_noise / eval_velocity): Cartesian starts with or without position noise, the
+relaxation run of the reference's validation scripts (``case.mode="rlx"``: noisy lattice at
+rest, 5000 steps, last state written as ``tgv_<dim>_<dx>_<seed>.h5``, validation/tgv3d.sh:19)
+and the relaxed start that reads it back (``case.r0_type="relaxed"``).  Every other case is passed in prepared:
 ``simulate(cfg, setup=obj)`` where ``obj`` carries the reference's ``initialize()`` results as
 plain attributes (``state``, ``box_size``, ``dt``, ... -- exactly what ``config_from_setup``
 reads); the case classes themselves (cases/*.py) are outside the hot-path scope.
@@ -39,7 +42,7 @@ def defaults(**overrides) -> Dict:
     ``overrides`` are merged per section (``defaults(case=dict(dx=0.02))``)."""
     cfg = {
         "seed": 123, "dtype": "float32",
-        "case": dict(name="tgv", mode="sim", dim=3, dx=0.05, r0_type="cartesian",
+        "case": dict(name="tgv", mode="sim", dim=3, dx=0.05, r0_type="cartesian", state0_path=None,
                      r0_noise_factor=0.0, g_ext_magnitude=0.0, viscosity=0.01, u_ref=1.0,
                      c_ref_factor=10.0, rho_ref=1.0, T_ref=1.0, kappa_ref=0.0, Cp_ref=0.0),
         "solver": dict(name="SPH", tvf=0.0, cfl=0.25, density_evolution=False,
@@ -87,10 +90,9 @@ class _Prepared:
 
 def _prepare_tgv(cfg) -> _Prepared:
     g = io_state._get
-    if g(cfg, "case.r0_type") != "cartesian" or g(cfg, "case.r0_noise_factor") != 0.0:
-        raise _lib.Sphb200Error(
-            "the on-device start is the Cartesian lattice without noise; pass relaxed / noisy "
-            "starts as a prepared setup (simulate(cfg, setup=...))")
+    r0_type, mode = g(cfg, "case.r0_type"), g(cfg, "case.mode")
+    if r0_type not in ("cartesian", "relaxed") or mode not in ("sim", "rlx"):
+        raise _lib.Sphb200Error(f"case.r0_type {r0_type!r} / case.mode {mode!r} not supported")
     if str(g(cfg, "dtype")) != "float32":
         raise _lib.Sphb200Error("the engine is float32 only (cfg.dtype)")
     dim, dx = g(cfg, "case.dim"), g(cfg, "case.dx")
@@ -103,8 +105,11 @@ def _prepare_tgv(cfg) -> _Prepared:
     dt = time_step(cfg)
     seq = 5000 if g(cfg, "case.mode") == "rlx" else int(g(cfg, "solver.t_end") / dt)  # :106-112
     name = g(cfg, "solver.name")
+    field = "tgv2d" if dim == 2 else "tgv3d"
+    if mode == "rlx":
+        field = "rest"  # set_relaxation: zero velocity, no external force (case_setup.py:371-389)
     lat = case_setup.lattice_spec(
-        box, dx, velocity="tgv2d" if dim == 2 else "tgv3d", rho=rho_ref, p=p_bg,
+        box, dx, velocity=field, rho=rho_ref, p=p_bg,
         eta=g(cfg, "case.viscosity"), T=g(cfg, "case.T_ref"), kappa=g(cfg, "case.kappa_ref"),
         Cp=g(cfg, "case.Cp_ref"))
     ecfg = make_config(
@@ -117,7 +122,37 @@ def _prepare_tgv(cfg) -> _Prepared:
         artificial_alpha=g(cfg, "solver.artificial_alpha"),
         diff_delta=g(cfg, "solver.diff_delta"), diff_alpha=g(cfg, "solver.diff_alpha"))
     state = case_setup.init_lattice(lat)
+    if r0_type == "relaxed" and mode == "sim":
+        # TGV.__init__ (cases/tgv.py:20-23) + _get_relaxed_r0 (case_setup.py:274-294): positions
+        # of the relaxed state, velocities evaluated there
+        import os
+
+        path = g(cfg, "case.state0_path") if _has(cfg, "case.state0_path") else None
+        if path is None:
+            stem = case_setup.relaxed_state_name(g(cfg, "case.name"), dim, dx, g(cfg, "seed"))
+            path = os.path.join("data_relaxed", stem + ".h5")
+        if not os.path.isfile(path):
+            raise FileNotFoundError(
+                f"{path}: first run the relaxation (case.mode='rlx', solver.tvf=1, "
+                "case.r0_noise_factor=0.25, io.write_type=['h5'], io.data_path='data_relaxed/')")
+        snap = io_state.read_h5(path, array_type="torch")
+        if tuple(snap["r"].shape) != tuple(state["r"].shape):
+            raise _lib.Sphb200Error(f"{path}: {tuple(snap['r'].shape)} positions, the case has "
+                                    f"{tuple(state['r'].shape)}")
+        state["r"] = snap["r"].contiguous()
+        case_setup.eval_velocity(state, field)
+    elif g(cfg, "case.r0_noise_factor") != 0.0:
+        # case_setup.py:138-150: noise on the fluid particles, wrapped, THEN the velocity field
+        case_setup.add_noise(state, g(cfg, "case.r0_noise_factor") * dx, g(cfg, "seed"), box)
+        case_setup.eval_velocity(state, field)
     return _Prepared(ecfg, state, dt, seq, dx, case_setup.lattice_rows(lat))
+
+
+def _has(cfg, path) -> bool:
+    try:
+        return io_state._get(cfg, path) is not None
+    except (KeyError, AttributeError):
+        return False
 
 
 def _prepare_setup(cfg, setup, tuning) -> _Prepared:

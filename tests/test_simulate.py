@@ -45,8 +45,15 @@ def test_log_line_format_and_stat_selection():
 def test_cases_not_built_on_the_device_are_refused():
     with pytest.raises(_lib.Sphb200Error, match="prepared setup"):
         sim.simulate(sim.defaults(case=dict(name="db", dim=2)))
-    with pytest.raises(_lib.Sphb200Error, match="without noise"):
-        sim.simulate(sim.defaults(case=dict(r0_noise_factor=0.25)))
+    with pytest.raises(_lib.Sphb200Error, match="not supported"):
+        sim.simulate(sim.defaults(case=dict(r0_type="poisson")))
+    with pytest.raises(FileNotFoundError, match="first run the relaxation"):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise FileNotFoundError("first run the relaxation (no device: lattice not built)")
+        sim.simulate(sim.defaults(case=dict(dim=2, dx=0.1, r0_type="relaxed",
+                                            state0_path="/nonexistent/tgv.h5")))
 
 
 @pytest.mark.gpu
@@ -136,4 +143,85 @@ def test_simulate_with_a_prepared_setup(tmp_path):
     ref5 = integrator.simulate(setup, 5, fast_segment_sum=True)
     assert_close("r", snap["r"][:, :2], ref5["r"], setup, factor=3.0, what="vtk snapshot")
     assert np.array_equal(snap["tag"], setup.state["tag"])
+
+
+@pytest.mark.gpu
+def test_relaxation_run_and_relaxed_start(tmp_path):
+    """validation/tgv2d.sh:13 + :17 on the engine: (1) relaxation -- noisy lattice at rest,
+    tvf = 1, background pressure, 5000 steps, last state written as tgv_2_<dx>_<seed>.h5;
+    (2) the simulation that starts from it (case.r0_type = "relaxed"): same particle count,
+    positions of the relaxed state, TGV velocities evaluated there."""
+    from jax_sph_b200 import case_setup, io_state
+
+    dx = 0.05
+    rlx = sim.defaults(seed=7, case=dict(name="tgv", dim=2, dx=dx, mode="rlx", r0_noise_factor=0.25),
+                       solver=dict(tvf=1.0), eos=dict(p_bg_factor=0.02),
+                       io=dict(write_type=["h5"], write_every=1000, data_path=str(tmp_path)))
+    lines = []
+    eng = sim.simulate(rlx, log=lines.append)
+    stem = case_setup.relaxed_state_name("tgv", 2, dx, 7)
+    path = tmp_path / (stem + ".h5")
+    assert eng.run_cfg["solver"]["sequence_length"] == 5000 and path.exists()
+    assert sorted(f for f in os.listdir(tmp_path) if f.endswith(".h5")) == [stem + ".h5"]
+    relaxed = io_state.read_h5(str(path))
+    n = int(round(1 / dx)) ** 2
+    assert relaxed["r"].shape == (n, 2)
+    assert (relaxed["r"] >= 0).all() and (relaxed["r"] <= 1).all()
+    # the relaxation spreads the noisy particles: density close to uniform, almost at rest
+    assert abs(float(relaxed["rho"].mean()) - 1.0) < 0.05 and float(relaxed["rho"].std()) < 0.05
+    assert float(np.abs(relaxed["u"]).max()) < 0.5
+    lattice = (np.arange(int(round(1 / dx))) + 0.5) * dx
+    off_lattice = np.abs(relaxed["r"][:, 0, None] - lattice[None]).min(axis=1)
+    assert off_lattice.max() > 0.1 * dx  # not the Cartesian start any more
+
+    run = sim.defaults(seed=7, case=dict(name="tgv", dim=2, dx=dx, r0_type="relaxed",
+                                         state0_path=str(path)),
+                       solver=dict(tvf=1.0, t_end=0.01), io=dict(data_path=str(tmp_path)))
+    lines = []
+    eng = sim.simulate(run, log=lines.append)
+    ek0 = float(re.search(r"Ekin=([\d.]+)", lines[0]).group(1))
+    assert 0.2 < ek0 < 0.27  # TGV field on the relaxed positions
+    got = eng.download(host=True)
+    assert got["r"].shape == (n, 2) and bool(np.isfinite(got["u"].numpy()).all())
+
+
+@pytest.mark.gpu
+def test_noise_and_velocity_kernels():
+    """sphb200_add_noise / sphb200_eval_velocity: Gaussian noise of the requested width on the
+    fluid particles only, wrapped into the box, reproducible per (seed, lattice row) for any
+    slab; the velocity field at arbitrary positions equals the lattice kernel's."""
+    import torch
+
+    from jax_sph_b200 import case_setup
+
+    box, dx = [1.0, 0.26, 0.5], 0.02
+    kw = dict(wall_axis=1, n_walls=3)
+    clean = case_setup.init_lattice(case_setup.lattice_spec(box, dx, **kw))
+    a = case_setup.init_lattice(case_setup.lattice_spec(box, dx, **kw))
+    b = case_setup.init_lattice(case_setup.lattice_spec(box, dx, **kw))
+    case_setup.add_noise(a, 0.25 * dx, 42, box)
+    case_setup.add_noise(b, 0.25 * dx, 42, box)
+    assert torch.equal(a["r"], b["r"])
+    fluid = (clean["tag"] == 0)
+    assert torch.equal(a["r"][~fluid], clean["r"][~fluid])  # get_noise_masked: walls stay
+    d = (a["r"] - clean["r"])[fluid]
+    boxt = torch.tensor(box, device="cuda")
+    d = d - boxt * torch.round(d / boxt)  # undo the periodic wrap
+    assert abs(float(d.mean())) < 2e-4 and abs(float(d.std()) / (0.25 * dx) - 1.0) < 0.02
+    assert (a["r"] >= 0).all() and (a["r"] <= boxt).all()
+    c = case_setup.init_lattice(case_setup.lattice_spec(box, dx, **kw))
+    case_setup.add_noise(c, 0.25 * dx, 43, box)
+    assert not torch.equal(a["r"], c["r"])
+    # a slab draws the deviates of its full-lattice rows
+    slab = case_setup.init_lattice(case_setup.lattice_spec(box, dx, planes=(5, 9), **kw), with_ids=True)
+    case_setup.add_noise(slab, 0.25 * dx, 42, box)
+    assert torch.equal(slab["r"], a["r"][slab["ids"].long()])
+    # velocity field at given positions
+    lat = case_setup.lattice_spec([2 * np.pi] * 3, 2 * np.pi / 16, velocity="tgv3d")
+    st = case_setup.init_lattice(lat)
+    want = st["u"].clone()
+    st["u"].zero_()
+    st["v"].zero_()
+    case_setup.eval_velocity(st, "tgv3d")
+    assert torch.equal(st["u"], want) and torch.equal(st["v"], want)
 
