@@ -11,10 +11,14 @@ oracle) and therefore complement the per-step parity tests:
   plots its runs against (validation/ref/tgv3d_ref_50.txt, sub-sampled in
   tests/golden/validation_tgv3d_re50.csv), and convergence towards it with resolution.
 
-The runs start from the Cartesian lattice; the reference starts from a relaxed
-particle distribution (case.mode=rlx), which is not reproduced here, so the bounds
-are those of the lattice start (measured on B200, scripts/validate_curves.py:
-u_max(2)/theory = 0.963; max |E - E_ref|/E_0 = 0.175 at nx = 64, 0.246 at nx = 32).
+The first runs start from the Cartesian lattice, so their bounds are those of the lattice
+start (measured on B200, scripts/validate_curves.py: u_max(2)/theory = 0.963;
+max |E - E_ref|/E_0 = 0.175 at nx = 64, 0.246 at nx = 32).  The reference starts from a
+relaxed particle distribution (case.mode=rlx, validation/tgv3d.sh:19); the last test runs
+that whole workflow through jax_sph_b200.simulate -- relaxation, relaxed start, E_kin as
+validate.py:116-117 computes it -- and the curve then follows the JAX-Fluids reference to
+0.035 E_0 at nx = 32 (0.022 at nx = 64, scripts/validate_relaxed.py,
+profiles/r01_validation_relaxed_tgv3d.txt).
 That the engine integrates the same equations as the reference is what the parity
 tests establish; these curves guard the long-time behaviour (no energy growth, no
 drift, right decay rate) at sizes the oracle cannot reach.
@@ -134,3 +138,37 @@ def test_channel_flow_matches_analytical_solution(case, tvf, solver):
         got = interp_vel(state, setup.box_size, dx, 2, rs)
         assert np.allclose(got, series(y_axis, tp), atol=1e-2), (case, solver, tvf, tp)
     assert eng.error() == 0
+
+
+def test_tgv3d_relaxed_start_follows_the_reference_curve(tmp_path):
+    """validation/tgv3d.sh:19-20 end to end on the engine at nx = 32: relaxation run, then the
+    Re = 50 simulation from the relaxed positions; E_kin(t) per unit volume (get_ekin / volume,
+    validate.py:116-117) within 0.06 E_0 of the JAX-Fluids curve over t in [0, 10] (measured
+    0.035; the lattice start of the same resolution is 0.25 off)."""
+    import re
+
+    from jax_sph_b200 import case_setup
+    from jax_sph_b200.simulate import defaults, simulate
+
+    nx = 32
+    dx = 2 * np.pi / nx
+    simulate(defaults(seed=123, case=dict(name="tgv", dim=3, dx=dx, mode="rlx", r0_noise_factor=0.25,
+                                          viscosity=0.02),
+                      solver=dict(tvf=1.0), eos=dict(p_bg_factor=0.02),
+                      io=dict(write_type=["h5"], write_every=2500, data_path=str(tmp_path))), log=None)
+    path = os.path.join(str(tmp_path), case_setup.relaxed_state_name("tgv", 3, dx, 123) + ".h5")
+    lines = []
+    eng = simulate(defaults(seed=123, case=dict(name="tgv", dim=3, dx=dx, viscosity=0.02,
+                                                r0_type="relaxed", state0_path=path),
+                            solver=dict(tvf=1.0, t_end=10.0),
+                            io=dict(write_every=50, data_path=str(tmp_path))), log=lines.append)
+    assert eng.error() == 0
+    pts = [re.search(r"t=([\d.]+), Ekin=([\d.]+)", l) for l in lines]
+    t = np.array([float(m.group(1)) for m in pts if m])
+    ek = np.array([float(m.group(2)) for m in pts if m]) / (2 * np.pi) ** 3
+    ref = np.loadtxt(os.path.join(GOLDEN, "validation_tgv3d_re50.csv"), delimiter=",")
+    e_ref = np.interp(t, ref[:, 0], ref[:, 2])
+    assert len(t) > 40 and t[-1] > 9.5
+    assert np.abs(ek - e_ref).max() <= 0.06 * ref[0, 2]
+    assert (np.diff(ek) <= 1e-5).all()  # monotone decay, no energy growth
+
