@@ -141,17 +141,6 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def make_setup(workload, nx):
-    from oracle import cases
-
-    if workload == "tgv3d":
-        return cases.make_case("tgv", dim=3, dx=2 * np.pi / nx, dtype=np.float32, tvf=1.0,
-                               viscosity=0.02)
-    if workload == "tgv2d":
-        return cases.make_case("tgv", dim=2, dx=1.0 / nx, dtype=np.float32, tvf=1.0)
-    raise ValueError(workload)
-
-
 def ht3d_meta(nx):
     """BASELINE configs[4]: cases/ht.yaml with case.dim=3 (3D channel with a hot patch in the
     bottom wall, cases/ht.py:29-187): box L x (H + 6 dx) x W = 1.0 x (0.2 + 6 dx) x 0.5,
