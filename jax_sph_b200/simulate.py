@@ -19,7 +19,9 @@ Cases.  ``cfg.case.name == "tgv"`` is built on the device (case_setup.lattice_sp
 init_lattice / add_noise / eval_velocity): Cartesian starts with or without position noise, the
 relaxation run of the reference's validation scripts (``case.mode="rlx"``: noisy lattice at
 rest, 5000 steps, last state written as ``tgv_<dim>_<dx>_<seed>.h5``, validation/tgv3d.sh:19)
-and the relaxed start that reads it back (``case.r0_type="relaxed"``).  Every other case is passed in prepared:
+and the relaxed start that reads it back (``case.r0_type="relaxed"``); so is the heated
+channel ``cfg.case.name == "ht"`` (cases/ht.py, 2D and 3D: BASELINE configs[4]) on one regular
+lattice of walls and fluid.  Every other case is passed in prepared:
 ``simulate(cfg, setup=obj)`` where ``obj`` carries the reference's ``initialize()`` results as
 plain attributes (``state``, ``box_size``, ``dt``, ... -- exactly what ``config_from_setup``
 reads); the case classes themselves (cases/*.py) are outside the hot-path scope.
@@ -52,6 +54,8 @@ def defaults(**overrides) -> Dict:
         "kernel": dict(name="QSK", h_factor=1.0),
         "eos": dict(name="Tait", gamma=1.0, p_bg_factor=0.0),
         "io": dict(write_type=[], write_every=1, data_path="./", print_props=["Ekin", "u_max"]),
+        # cases/ht.yaml `case.special` (read by the heated channel only)
+        "special": dict(hot_wall_temperature=1.23, hot_wall_half_width=0.25, L=1.0, H=0.2),
     }
     for section, vals in overrides.items():
         if isinstance(vals, dict):
@@ -148,6 +152,71 @@ def _prepare_tgv(cfg) -> _Prepared:
     return _Prepared(ecfg, state, dt, seq, dx, case_setup.lattice_rows(lat))
 
 
+def ht_case(cfg) -> Dict:
+    """Heated channel (cases/ht.py:29-187, cases/ht.yaml) in table form: box, lattice counts,
+    the band force `_external_acceleration_fn` (:139-149) and `_boundary_conditions_fn`
+    (:151-187).  Walls and fluid sit on ONE regular lattice (i + 0.5) dx: where H / dx is not an
+    integer the reference leaves a sub-dx gap under the top wall, and it enumerates walls before
+    fluid -- the particles are the same, their order in the arrays is the lattice's."""
+    g = io_state._get
+    dim, dx, n_walls = g(cfg, "case.dim"), g(cfg, "case.dx"), g(cfg, "solver.n_walls")
+    sp = {k: (g(cfg, "special." + k) if _has(cfg, "special." + k) else v) for k, v in
+          dict(hot_wall_temperature=1.23, hot_wall_half_width=0.25, L=1.0, H=0.2).items()}
+    box = [sp["L"], sp["H"] + 2 * n_walls * dx] + ([0.5] if dim == 3 else [])  # ht.py:29-37
+    nxyz = [int(round(sp["L"] / dx)), int(round(sp["H"] / dx)) + 2 * n_walls] + (
+        [int(round(0.5 / dx))] if dim == 3 else [])
+    zero = [0.0, 0.0, 0.0]
+    T_ref = g(cfg, "case.T_ref")
+    st = dict(u=zero, v=zero, zero_dudt=True, zero_dvdt=True, zero_dTdt=True)
+    bc_table = {"tags": {1: dict(st, T=T_ref), 3: dict(st, T=sp["hot_wall_temperature"])},
+                "inflow_x": dict(x=float(n_walls * dx), T=T_ref),
+                "outflow_x": dict(x=float(box[0]) - n_walls * dx)}
+    g_ext_spec = {"mode": "band", "g": [g(cfg, "case.g_ext_magnitude"), 0.0, 0.0], "axis": 1,
+                  "lo": float(n_walls * dx), "hi": float(box[1] - n_walls * dx)}
+    hot = (box[0] / 2 - sp["hot_wall_half_width"], box[0] / 2 + sp["hot_wall_half_width"])
+    return dict(box=box, nxyz=nxyz, bc_table=bc_table, g_ext_spec=g_ext_spec, hot=hot,
+                T_hot=sp["hot_wall_temperature"], n_walls=n_walls)
+
+
+def _prepare_ht(cfg) -> _Prepared:
+    g = io_state._get
+    if g(cfg, "case.r0_type") != "cartesian" or g(cfg, "case.mode") != "sim":
+        raise _lib.Sphb200Error("the heated channel is built from the Cartesian lattice in "
+                                "simulation mode; pass other starts as a prepared setup")
+    if str(g(cfg, "dtype")) != "float32":
+        raise _lib.Sphb200Error("the engine is float32 only (cfg.dtype)")
+    dim, dx = g(cfg, "case.dim"), g(cfg, "case.dx")
+    ht = ht_case(cfg)
+    rho_ref, u_ref = g(cfg, "case.rho_ref"), g(cfg, "case.u_ref")
+    c_ref = g(cfg, "case.c_ref_factor") * u_ref
+    gamma = g(cfg, "eos.gamma")
+    p_ref = rho_ref * c_ref**2 / gamma
+    p_bg = g(cfg, "eos.p_bg_factor") * p_ref
+    dt = time_step(cfg)
+    seq = int(g(cfg, "solver.t_end") / dt)
+    lat = case_setup.lattice_spec(
+        ht["box"], dx, wall_axis=1, n_walls=ht["n_walls"], hot=ht["hot"], T_hot=ht["T_hot"],
+        rho=rho_ref, p=p_bg, eta=g(cfg, "case.viscosity"), T=g(cfg, "case.T_ref"),
+        kappa=g(cfg, "case.kappa_ref"), Cp=g(cfg, "case.Cp_ref"))
+    if [lat.n[a] for a in range(dim)] != ht["nxyz"]:
+        raise _lib.Sphb200Error(f"lattice {list(lat.n)[:dim]} != walls + fluid {ht['nxyz']}: pick dx "
+                                "with H / dx, L / dx (and 0.5 / dx) away from half-integers")
+    ecfg = make_config(
+        dim, ht["box"], dx, dt, solver=g(cfg, "solver.name"), kernel=g(cfg, "kernel.name"),
+        h_fac=g(cfg, "kernel.h_factor"), tvf=g(cfg, "solver.tvf"), p_ref=p_ref, rho_ref=rho_ref,
+        p_bg=p_bg, gamma=gamma, u_ref=u_ref, c_ref=c_ref, eta_limiter=g(cfg, "solver.eta_limiter"),
+        is_bc_trick=g(cfg, "solver.is_bc_trick"), is_rho_evol=g(cfg, "solver.density_evolution"),
+        is_rho_renorm=g(cfg, "solver.density_renormalize"), is_free_slip=g(cfg, "solver.free_slip"),
+        is_heat_conduction=g(cfg, "solver.heat_conduction"),
+        artificial_alpha=g(cfg, "solver.artificial_alpha"),
+        diff_delta=g(cfg, "solver.diff_delta"), diff_alpha=g(cfg, "solver.diff_alpha"),
+        g_ext_spec=ht["g_ext_spec"], bc_table=ht["bc_table"])
+    state = case_setup.init_lattice(lat)
+    if g(cfg, "case.r0_noise_factor") != 0.0:  # case_setup.py:138-144 (velocities stay zero)
+        case_setup.add_noise(state, g(cfg, "case.r0_noise_factor") * dx, g(cfg, "seed"), ht["box"])
+    return _Prepared(ecfg, state, dt, seq, dx, case_setup.lattice_rows(lat))
+
+
 def _has(cfg, path) -> bool:
     try:
         return io_state._get(cfg, path) is not None
@@ -184,6 +253,8 @@ def simulate(cfg, setup=None, out_dir: Optional[str] = None, log=print, **tuning
         prep = _prepare_setup(cfg, setup, tuning)
     elif str(g(cfg, "case.name")).lower() == "tgv":
         prep = _prepare_tgv(cfg)
+    elif str(g(cfg, "case.name")).lower() == "ht":
+        prep = _prepare_ht(cfg)
     else:
         raise _lib.Sphb200Error(
             f"case {g(cfg, 'case.name')!r} is not built on the device: pass its initialize() "

@@ -42,6 +42,51 @@ def test_log_line_format_and_stat_selection():
         stats_from_words(words, ["nw_max"])
 
 
+@pytest.mark.parametrize("dim,dx", [(2, 0.02), (3, 0.04), (2, 0.05)])
+def test_heated_channel_tables_equal_the_oracle_case(dim, dx):
+    """simulate.ht_case / time_step against the oracle's case object (pinned to the
+    reference's cases/ht.py by tests/test_reference_pins.py): box, particle count, dt, the bc
+    table, the band force and the engine config built from them."""
+    from jax_sph_b200 import config_from_setup, make_config
+    from oracle import cases
+
+    setup = cases.make_case("ht", dim=dim, dx=dx, dtype=np.float32, r0_noise_factor=0.0)
+    cfg = sim.defaults(case=dict(name="ht", dim=dim, dx=dx, g_ext_magnitude=2.3, kappa_ref=7.313,
+                                 Cp_ref=305.27),
+                       solver=dict(heat_conduction=True, is_bc_trick=True, t_end=1.5),
+                       eos=dict(p_bg_factor=0.05))
+    ht = sim.ht_case(cfg)
+    assert np.allclose(ht["box"], setup.box_size, rtol=1e-12)
+    assert int(np.prod(ht["nxyz"])) == len(setup.state["r"])
+    assert abs(sim.time_step(cfg) - setup.dt) <= 1e-12 * setup.dt
+    assert ht["bc_table"] == setup.bc_table
+    g1, g2 = ht["g_ext_spec"], setup.g_ext_spec
+    assert g1["mode"] == g2["mode"] and g1["axis"] == g2["axis"] and np.allclose(g1["g"], g2["g"])
+    assert abs(g1["lo"] - g2["lo"]) < 1e-12 and abs(g1["hi"] - g2["hi"]) < 1e-12
+    # tags of the lattice rule (init.cuh) == tags of the case, particle by particle
+    n = ht["nxyz"]
+    grids = np.meshgrid(*[np.arange(k) for k in n], indexing="xy")
+    idx = np.stack([g.ravel() for g in grids], axis=1)
+    x = ((idx[:, 0] + np.float32(0.5)) * np.float32(dx)).astype(np.float32)
+    wall = (idx[:, 1] < 3) | (idx[:, 1] >= n[1] - 3)
+    hot = (idx[:, 1] < 3) & (x < np.float32(ht["hot"][1])) & (x > np.float32(ht["hot"][0]))
+    tag = np.where(hot, 3, np.where(wall, 1, 0))
+    q = np.rint(setup.state["r"] / dx - 0.5).astype(np.int64)
+    key_ref = np.lexsort(tuple(q[:, a] for a in range(dim)))
+    key_lat = np.lexsort(tuple(idx[:, a] for a in range(dim)))
+    assert np.array_equal(tag[key_lat], setup.state["tag"][key_ref])
+    # the engine config the driver builds == the one built from the oracle's case object
+    a = make_config(dim, ht["box"], dx, sim.time_step(cfg), p_ref=100.0, p_bg=5.0, c_ref=10.0,
+                    is_bc_trick=True, is_heat_conduction=True, g_ext_spec=ht["g_ext_spec"],
+                    bc_table=ht["bc_table"])
+    b = config_from_setup(setup)
+    import ctypes as C
+
+    raw = lambda c: bytes((C.c_char * C.sizeof(type(c))).from_buffer_copy(c))  # noqa: E731
+    a.dt = b.dt  # equal to 1e-12 relative (asserted above), not necessarily to the last bit
+    assert raw(a) == raw(b)
+
+
 def test_cases_not_built_on_the_device_are_refused():
     with pytest.raises(_lib.Sphb200Error, match="prepared setup"):
         sim.simulate(sim.defaults(case=dict(name="db", dim=2)))
@@ -224,4 +269,39 @@ def test_noise_and_velocity_kernels():
     st["v"].zero_()
     case_setup.eval_velocity(st, "tgv3d")
     assert torch.equal(st["u"], want) and torch.equal(st["v"], want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,dx", [(2, 0.02), (3, 0.05)])
+def test_simulate_heated_channel_equals_the_oracle_loop(dim, dx, tmp_path):
+    """cases/ht.yaml through the driver (device-made walls + fluid, band force, bc table, heat
+    conduction) against the oracle's loop on its own case object; the two enumerate the same
+    lattice in different orders, so particles are matched by their start positions."""
+    from _util import assert_close
+    from oracle import cases, integrator
+
+    setup = cases.make_case("ht", dim=dim, dx=dx, dtype=np.float32, r0_noise_factor=0.0)
+    nsteps = 6
+    cfg = sim.defaults(case=dict(name="ht", dim=dim, dx=dx, g_ext_magnitude=2.3, kappa_ref=7.313,
+                                 Cp_ref=305.27),
+                       solver=dict(heat_conduction=True, is_bc_trick=True,
+                                   t_end=(nsteps - 2 + 0.5) * setup.dt),
+                       eos=dict(p_bg_factor=0.05),
+                       io=dict(write_every=3, data_path=str(tmp_path), print_props=["Ekin", "u_max", "T_max"]))
+    lines = []
+    eng = sim.simulate(cfg, log=lines.append)
+    assert eng.run_cfg["solver"]["sequence_length"] == nsteps - 2
+    got = {k: v.numpy() for k, v in eng.download(host=True).items()}
+    ref = integrator.simulate(setup, nsteps, fast_segment_sum=True)
+    # match by the start lattice: the driver's rows are meshgrid("xy") order
+    n = sim.ht_case(cfg)["nxyz"]
+    grids = np.meshgrid(*[np.arange(k) for k in n], indexing="xy")
+    idx = np.stack([g.ravel() for g in grids], axis=1)
+    q = np.rint(setup.state["r"] / dx - 0.5).astype(np.int64)
+    perm_ref = np.lexsort(tuple(q[:, a] for a in range(dim)))
+    perm_lat = np.lexsort(tuple(idx[:, a] for a in range(dim)))
+    assert np.array_equal(got["tag"][perm_lat], ref["tag"][perm_ref])
+    for k in ("r", "u", "rho", "p", "T"):
+        assert_close(k, got[k][perm_lat], ref[k][perm_ref], setup, factor=3.0, what=f"simulate(ht {dim}D)")
+    assert "T_max=1.23000" in lines[0]
 
