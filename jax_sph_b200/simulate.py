@@ -20,8 +20,8 @@ init_lattice / add_noise / eval_velocity): Cartesian starts with or without posi
 relaxation run of the reference's validation scripts (``case.mode="rlx"``: noisy lattice at
 rest, 5000 steps, last state written as ``tgv_<dim>_<dx>_<seed>.h5``, validation/tgv3d.sh:19)
 and the relaxed start that reads it back (``case.r0_type="relaxed"``); so is the heated
-channel ``cfg.case.name == "ht"`` (cases/ht.py, 2D and 3D: BASELINE configs[4]) on one regular
-lattice of walls and fluid.  Every other case is passed in prepared:
+channel ``cfg.case.name == "ht"`` (cases/ht.py, 2D and 3D: BASELINE configs[4]) and the
+Poiseuille flow ``"pf"`` (cases/pf.py) on one regular lattice of walls and fluid.  Every other case is passed in prepared:
 ``simulate(cfg, setup=obj)`` where ``obj`` carries the reference's ``initialize()`` results as
 plain attributes (``state``, ``box_size``, ``dt``, ... -- exactly what ``config_from_setup``
 reads); the case classes themselves (cases/*.py) are outside the hot-path scope.
@@ -54,13 +54,13 @@ def defaults(**overrides) -> Dict:
         "kernel": dict(name="QSK", h_factor=1.0),
         "eos": dict(name="Tait", gamma=1.0, p_bg_factor=0.0),
         "io": dict(write_type=[], write_every=1, data_path="./", print_props=["Ekin", "u_max"]),
-        # cases/ht.yaml `case.special` (read by the heated channel only)
-        "special": dict(hot_wall_temperature=1.23, hot_wall_half_width=0.25, L=1.0, H=0.2),
+        # `case.special` of cases/ht.yaml / pf.yaml: per-case defaults apply where a key is absent
+        "special": dict(),
     }
     for section, vals in overrides.items():
         if isinstance(vals, dict):
             unknown = set(vals) - set(cfg.get(section, vals))
-            if section in cfg and unknown:
+            if section in cfg and unknown and section != "special":
                 raise _lib.Sphb200Error(f"unknown config keys in {section}: {sorted(unknown)}")
             cfg.setdefault(section, {}).update(vals)
         else:
@@ -152,41 +152,59 @@ def _prepare_tgv(cfg) -> _Prepared:
     return _Prepared(ecfg, state, dt, seq, dx, case_setup.lattice_rows(lat))
 
 
-def ht_case(cfg) -> Dict:
-    """Heated channel (cases/ht.py:29-187, cases/ht.yaml) in table form: box, lattice counts,
-    the band force `_external_acceleration_fn` (:139-149) and `_boundary_conditions_fn`
-    (:151-187).  Walls and fluid sit on ONE regular lattice (i + 0.5) dx: where H / dx is not an
-    integer the reference leaves a sub-dx gap under the top wall, and it enumerates walls before
-    fluid -- the particles are the same, their order in the arrays is the lattice's."""
+_CHANNEL_SPECIAL = {
+    # cases/ht.yaml / cases/pf.yaml `case.special`, and the depth of the 3D box (ht.py:37, pf.py)
+    "ht": (dict(hot_wall_temperature=1.23, hot_wall_half_width=0.25, L=1.0, H=0.2), 0.5),
+    "pf": (dict(L=0.4, H=1.0), 0.4),
+}
+
+
+def channel_case(cfg) -> Dict:
+    """The two channel cases with walls below and above and a periodic stream-wise axis --
+    heated channel (cases/ht.py:29-187, ht.yaml) and Poiseuille flow (cases/pf.py, pf.yaml) --
+    in table form: box, lattice counts, the band force `_external_acceleration_fn`
+    (ht.py:139-149) and `_boundary_conditions_fn` (ht.py:151-187; pf: walls at rest).  Walls
+    and fluid sit on ONE regular lattice (i + 0.5) dx: where H / dx is not an integer the
+    reference leaves a sub-dx gap under the top wall, and it enumerates walls before fluid --
+    the particles are the same, their order in the arrays is the lattice's."""
     g = io_state._get
+    name = str(g(cfg, "case.name")).lower()
+    special, depth = _CHANNEL_SPECIAL[name]
     dim, dx, n_walls = g(cfg, "case.dim"), g(cfg, "case.dx"), g(cfg, "solver.n_walls")
-    sp = {k: (g(cfg, "special." + k) if _has(cfg, "special." + k) else v) for k, v in
-          dict(hot_wall_temperature=1.23, hot_wall_half_width=0.25, L=1.0, H=0.2).items()}
-    box = [sp["L"], sp["H"] + 2 * n_walls * dx] + ([0.5] if dim == 3 else [])  # ht.py:29-37
+    sp = {k: (g(cfg, "special." + k) if _has(cfg, "special." + k) else v) for k, v in special.items()}
+    box = [sp["L"], sp["H"] + 2 * n_walls * dx] + ([depth] if dim == 3 else [])
     nxyz = [int(round(sp["L"] / dx)), int(round(sp["H"] / dx)) + 2 * n_walls] + (
-        [int(round(0.5 / dx))] if dim == 3 else [])
+        [int(round(depth / dx))] if dim == 3 else [])
     zero = [0.0, 0.0, 0.0]
+    g_ext_spec = {"mode": "band", "g": [g(cfg, "case.g_ext_magnitude"), 0.0, 0.0], "axis": 1,
+                  "lo": float(n_walls * dx), "hi": float(box[1] - n_walls * dx)}
+    if name == "pf":
+        bc_table = {"tags": {1: dict(u=zero, v=zero, zero_dudt=True, zero_dvdt=True)},
+                    "inflow_x": None, "outflow_x": None}
+        return dict(box=box, nxyz=nxyz, bc_table=bc_table, g_ext_spec=g_ext_spec, hot=None,
+                    T_hot=g(cfg, "case.T_ref"), n_walls=n_walls)
     T_ref = g(cfg, "case.T_ref")
     st = dict(u=zero, v=zero, zero_dudt=True, zero_dvdt=True, zero_dTdt=True)
     bc_table = {"tags": {1: dict(st, T=T_ref), 3: dict(st, T=sp["hot_wall_temperature"])},
                 "inflow_x": dict(x=float(n_walls * dx), T=T_ref),
                 "outflow_x": dict(x=float(box[0]) - n_walls * dx)}
-    g_ext_spec = {"mode": "band", "g": [g(cfg, "case.g_ext_magnitude"), 0.0, 0.0], "axis": 1,
-                  "lo": float(n_walls * dx), "hi": float(box[1] - n_walls * dx)}
     hot = (box[0] / 2 - sp["hot_wall_half_width"], box[0] / 2 + sp["hot_wall_half_width"])
     return dict(box=box, nxyz=nxyz, bc_table=bc_table, g_ext_spec=g_ext_spec, hot=hot,
                 T_hot=sp["hot_wall_temperature"], n_walls=n_walls)
 
 
-def _prepare_ht(cfg) -> _Prepared:
+ht_case = channel_case  # the heated channel was the first of the two
+
+
+def _prepare_channel(cfg) -> _Prepared:
     g = io_state._get
     if g(cfg, "case.r0_type") != "cartesian" or g(cfg, "case.mode") != "sim":
-        raise _lib.Sphb200Error("the heated channel is built from the Cartesian lattice in "
+        raise _lib.Sphb200Error("the channel cases are built from the Cartesian lattice in "
                                 "simulation mode; pass other starts as a prepared setup")
     if str(g(cfg, "dtype")) != "float32":
         raise _lib.Sphb200Error("the engine is float32 only (cfg.dtype)")
     dim, dx = g(cfg, "case.dim"), g(cfg, "case.dx")
-    ht = ht_case(cfg)
+    ht = channel_case(cfg)
     rho_ref, u_ref = g(cfg, "case.rho_ref"), g(cfg, "case.u_ref")
     c_ref = g(cfg, "case.c_ref_factor") * u_ref
     gamma = g(cfg, "eos.gamma")
@@ -253,8 +271,8 @@ def simulate(cfg, setup=None, out_dir: Optional[str] = None, log=print, **tuning
         prep = _prepare_setup(cfg, setup, tuning)
     elif str(g(cfg, "case.name")).lower() == "tgv":
         prep = _prepare_tgv(cfg)
-    elif str(g(cfg, "case.name")).lower() == "ht":
-        prep = _prepare_ht(cfg)
+    elif str(g(cfg, "case.name")).lower() in _CHANNEL_SPECIAL:
+        prep = _prepare_channel(cfg)
     else:
         raise _lib.Sphb200Error(
             f"case {g(cfg, 'case.name')!r} is not built on the device: pass its initialize() "

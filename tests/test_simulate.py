@@ -272,36 +272,79 @@ def test_noise_and_velocity_kernels():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dim,dx", [(2, 0.02), (3, 0.05)])
-def test_simulate_heated_channel_equals_the_oracle_loop(dim, dx, tmp_path):
-    """cases/ht.yaml through the driver (device-made walls + fluid, band force, bc table, heat
-    conduction) against the oracle's loop on its own case object; the two enumerate the same
-    lattice in different orders, so particles are matched by their start positions."""
+@pytest.mark.parametrize("case,dim,dx", [("ht", 2, 0.02), ("ht", 3, 0.05), ("pf", 2, 0.05)])
+def test_simulate_channel_cases_equal_the_oracle_loop(case, dim, dx, tmp_path):
+    """cases/ht.yaml and cases/pf.yaml through the driver (device-made walls + fluid, band force,
+    bc table, heat conduction for ht) against the oracle's loop on its own case object; the two
+    enumerate the same lattice in different orders, so particles are matched by their start
+    positions."""
     from _util import assert_close
     from oracle import cases, integrator
 
-    setup = cases.make_case("ht", dim=dim, dx=dx, dtype=np.float32, r0_noise_factor=0.0)
+    setup = cases.make_case(case, dim=dim, dx=dx, dtype=np.float32, r0_noise_factor=0.0)
     nsteps = 6
-    cfg = sim.defaults(case=dict(name="ht", dim=dim, dx=dx, g_ext_magnitude=2.3, kappa_ref=7.313,
-                                 Cp_ref=305.27),
-                       solver=dict(heat_conduction=True, is_bc_trick=True,
-                                   t_end=(nsteps - 2 + 0.5) * setup.dt),
-                       eos=dict(p_bg_factor=0.05),
-                       io=dict(write_every=3, data_path=str(tmp_path), print_props=["Ekin", "u_max", "T_max"]))
+    if case == "ht":
+        over = dict(case=dict(name="ht", dim=dim, dx=dx, g_ext_magnitude=2.3, kappa_ref=7.313,
+                              Cp_ref=305.27),
+                    solver=dict(heat_conduction=True, is_bc_trick=True), eos=dict(p_bg_factor=0.05))
+        props, keys = ["Ekin", "u_max", "T_max"], ("r", "u", "rho", "p", "T")
+    else:
+        over = dict(case=dict(name="pf", dim=dim, dx=dx, viscosity=100.0, u_ref=1.25,
+                              g_ext_magnitude=1000.0),
+                    solver=dict(is_bc_trick=True))
+        props, keys = ["Ekin", "u_max"], ("r", "u", "rho", "p")
+    over["solver"]["t_end"] = (nsteps - 2 + 0.5) * setup.dt
+    over["io"] = dict(write_every=3, data_path=str(tmp_path), print_props=props)
+    cfg = sim.defaults(**over)
     lines = []
     eng = sim.simulate(cfg, log=lines.append)
     assert eng.run_cfg["solver"]["sequence_length"] == nsteps - 2
     got = {k: v.numpy() for k, v in eng.download(host=True).items()}
     ref = integrator.simulate(setup, nsteps, fast_segment_sum=True)
     # match by the start lattice: the driver's rows are meshgrid("xy") order
-    n = sim.ht_case(cfg)["nxyz"]
+    n = sim.channel_case(cfg)["nxyz"]
     grids = np.meshgrid(*[np.arange(k) for k in n], indexing="xy")
     idx = np.stack([g.ravel() for g in grids], axis=1)
     q = np.rint(setup.state["r"] / dx - 0.5).astype(np.int64)
     perm_ref = np.lexsort(tuple(q[:, a] for a in range(dim)))
     perm_lat = np.lexsort(tuple(idx[:, a] for a in range(dim)))
     assert np.array_equal(got["tag"][perm_lat], ref["tag"][perm_ref])
-    for k in ("r", "u", "rho", "p", "T"):
-        assert_close(k, got[k][perm_lat], ref[k][perm_ref], setup, factor=3.0, what=f"simulate(ht {dim}D)")
-    assert "T_max=1.23000" in lines[0]
+    for k in keys:
+        assert_close(k, got[k][perm_lat], ref[k][perm_ref], setup, factor=3.0, what=f"simulate({case} {dim}D)")
+    if case == "ht":
+        assert "T_max=1.23000" in lines[0]
+
+
+@pytest.mark.parametrize("dim,dx", [(2, 0.0166666), (2, 0.05), (3, 0.05)])
+def test_poiseuille_tables_equal_the_oracle_case(dim, dx):
+    """simulate.channel_case for cases/pf.yaml (the case the reference's tests/test_pf2d.py
+    integrates) against the oracle's case object: box, count, dt, tables, engine config."""
+    import ctypes as C
+
+    from jax_sph_b200 import config_from_setup, make_config
+    from oracle import cases
+
+    setup = cases.make_case("pf", dim=dim, dx=dx, dtype=np.float32)
+    cfg = sim.defaults(case=dict(name="pf", dim=dim, dx=dx, viscosity=100.0, u_ref=1.25,
+                                 g_ext_magnitude=1000.0),
+                       solver=dict(is_bc_trick=True))
+    ch = sim.channel_case(cfg)
+    assert np.allclose(ch["box"], setup.box_size, rtol=1e-12) and ch["hot"] is None
+    assert int(np.prod(ch["nxyz"])) == len(setup.state["r"])
+    assert abs(sim.time_step(cfg) - setup.dt) <= 1e-12 * setup.dt
+    assert ch["bc_table"] == setup.bc_table
+    g1, g2 = ch["g_ext_spec"], setup.g_ext_spec
+    assert g1["mode"] == g2["mode"] and g1["axis"] == g2["axis"] and np.allclose(g1["g"], g2["g"])
+    assert abs(g1["lo"] - g2["lo"]) < 1e-12 and abs(g1["hi"] - g2["hi"]) < 1e-12
+    a = make_config(dim, ch["box"], dx, setup.dt, p_ref=setup.p_ref, p_bg=setup.p_bg,
+                    c_ref=setup.c_ref, u_ref=1.25, is_bc_trick=True, g_ext_spec=ch["g_ext_spec"],
+                    bc_table=ch["bc_table"])
+    b = config_from_setup(setup)
+    raw = lambda c: bytes((C.c_char * C.sizeof(type(c))).from_buffer_copy(c))  # noqa: E731
+    assert raw(a) == raw(b)
+    # tags: walls below and above, no hot patch
+    n = ch["nxyz"]
+    q = np.rint(setup.state["r"] / dx - 0.5).astype(np.int64)
+    wall_ref = setup.state["tag"] == 1
+    assert np.array_equal(wall_ref, (q[:, 1] < 3) | (q[:, 1] >= n[1] - 3))
 
