@@ -144,3 +144,25 @@ def test_bench_ht3d_lattice_is_the_reference_case():
     # a slab's planes carry the ids of the full enumeration
     sub, _ = bench.ht3d_state(nx, planes=np.arange(meta["nxyz"][2]) % 3 == 1)
     assert len(np.unique(sub["ids"])) == len(sub["ids"]) < len(state["r"])
+
+
+def test_eos_records_keep_the_reference_forms_and_feed_the_engine_config():
+    """jax_sph_b200.eos: closed forms of jax_sph/eos.py:20-57 (value-identical to the oracle's
+    restatement in float64), reference attribute names, and the make_config keywords."""
+    from jax_sph_b200 import eos, make_config
+    from oracle import eos as oeos
+
+    rho = np.linspace(0.9, 1.1, 21)
+    t, r = eos.TaitEoS(100.0, 1.0, 5.0, 7.0), eos.RIEMANNEoS(1.0, 0.5, 1.25)
+    ot, orr = oeos.TaitEoS(100.0, 1.0, 5.0, 7.0), oeos.RIEMANNEoS(1.0, 0.5, 1.25)
+    assert np.array_equal(t.p_fn(rho), ot.p_fn(rho)) and np.array_equal(r.p_fn(rho), orr.p_fn(rho))
+    assert np.allclose(t.rho_fn(t.p_fn(rho)), rho, rtol=1e-13)
+    assert np.allclose(r.rho_fn(r.p_fn(rho)), rho, rtol=1e-13)
+    assert (t.p_ref, t.rho_ref, t.p_bg, t.gamma) == (100.0, 1.0, 5.0, 7.0) and not hasattr(t, "u_ref")
+    assert (r.rho_ref, r.p_bg, r.u_ref) == (1.0, 0.5, 1.25)
+    cfg = make_config(2, [1.0, 1.0], 0.02, 1e-4, **t.engine_fields())
+    assert cfg.eos == 0 and cfg.p_ref == 100.0 and cfg.gamma == 7.0 and cfg.p_bg == 5.0
+    cfg = make_config(2, [1.0, 1.0], 0.02, 1e-4, solver="RIE", **r.engine_fields())
+    assert cfg.eos == 1 and cfg.u_ref == 1.25 and cfg.p_bg == 0.5
+    with pytest.raises(ValueError):
+        eos.TaitEoS(100.0, 0.0, 0.0, 1.0)
