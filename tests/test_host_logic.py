@@ -166,3 +166,28 @@ def test_eos_records_keep_the_reference_forms_and_feed_the_engine_config():
     assert cfg.eos == 1 and cfg.u_ref == 1.25 and cfg.p_bg == 0.5
     with pytest.raises(ValueError):
         eos.TaitEoS(100.0, 0.0, 0.0, 1.0)
+
+
+def test_cpu_arm_worker_and_aggregation(monkeypatch):
+    """bench.py's CPU arm: one oracle worker per core (oracle/cpu_arm.py), aggregate over the
+    common window.  Tiny sample, two workers."""
+    import argparse
+    import json
+    import subprocess
+    import sys
+
+    import bench
+
+    out = subprocess.run([sys.executable, "-m", "oracle.cpu_arm", "--workload", "tgv2d", "--nx", "12",
+                          "--warmup", "0", "--steps", "1"], cwd=bench.ROOT, capture_output=True,
+                         text=True, check=True).stdout
+    rec = json.loads(out.strip().splitlines()[-1])
+    assert rec["n"] == 144 and rec["steps"] == 1 and rec["t1"] > rec["t0"]
+    monkeypatch.setattr(bench, "cpu_workers", lambda: 2)
+    args = argparse.Namespace(workload="tgv2d", cpu_nx=12, cpu_steps=2)
+    r = bench.run_cpu_arm(args, 2, warmup=0)
+    assert r["workers"] == 2 and r["n"] == 144 and r["window_s"] > 0
+    # the aggregate cannot exceed the sum of the workers' own rates
+    assert 0 < r["value"] <= 2 * r["per_core"] * 1.0001
+    base = bench.cpu_baseline(args)
+    assert base["cores"] == 2 and base["kind"] == "port" and "2 single-core workers" in base["sample"]
