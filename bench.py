@@ -276,7 +276,7 @@ def config_of(args, meta):
                        c_ref=meta["c_ref"], p_ref=meta["p_ref"],
                        cell_sub=[args.sub] * dim if args.sub else None,
                        threads=args.threads, list_cap=args.list_cap,
-                       tile=[args.tile_x, 0, 0] if args.tile_x else None,
+                       tile=[args.tile_x, 0, 0] if args.tile_x else None, skin=args.skin,
                        **meta.get("cfg_kwargs", {}))
 
 
@@ -348,6 +348,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     err = eng.error()
+    counters = eng.counters()
 
     # per-pass CUDA-event times (same stream, separate loop of the same steps)
     eng.profile(True)
@@ -393,7 +394,11 @@ def run_ours(args):
         "config": {"workload": workload_name(args, n),
                    "particles_per_gpu": n, "parallelism": "1 engine per GPU" if world == 1 else
                    f"{world} independent periodic boxes (replicas, no halo exchange yet)",
-                   "l2_policy": "state (>1.8 GB) larger than L2", "plan": eng.plan()},
+                   "l2_policy": "state (>1.8 GB) larger than L2", "plan": eng.plan(),
+                   "neighbour_search": dict(counters, timed_steps=args.steps, note=(
+                       "steps / searches since engine creation (warm-up included): the cell sort "
+                       "and candidate walk run when a particle has moved half the list skin; the "
+                       "exact d^2 < cutoff^2 membership test runs for every pair on every step"))},
         "clocks": clocks, "gpu_launches": int(launches), "device_error_word": err,
         "e2e": {"value": world * n * e2e_steps / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": int(bytes_in), "d2h_bytes_per_step": int(bytes_out),
@@ -636,6 +641,8 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--list-cap", type=int, default=0)
     ap.add_argument("--tile-x", type=int, default=0)
+    ap.add_argument("--skin", type=float, default=0.0,
+                    help="neighbour-list skin / cutoff (0 = engine default, < 0 = search every step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SPHB200_ABI_VERSION 2
+#define SPHB200_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------- */
 #define SPHB200_OK 0
@@ -158,7 +158,12 @@ typedef struct sphb200_config {
                         * forward(): 0 = auto (1.3 x the uniform-fluid neighbour count), -1 = off */
   float diff_delta;    /* DELTA: solver.py:623, defaults.py:97 */
   float diff_alpha;    /* DELTA: solver.py:624, defaults.py:99 */
-  int32_t reserved[5];
+  float skin;          /* neighbour-list skin as a fraction of the cutoff: the search (cell sort +
+                        * candidate walk) runs only when a particle has travelled more than half the
+                        * skin since the last one; the exact d^2 < cutoff^2 membership test of
+                        * jax_md/partition.py:897 still runs for every pair on every step, so the
+                        * neighbour sets are the reference's.  0 = automatic, < 0 = search every step */
+  int32_t reserved[4];
 } sphb200_config;
 
 /* State dict of the reference (solver.py:930-947), device or host pointers.
@@ -247,6 +252,14 @@ int sphb200_engine_profile(sphb200_engine *e, int enable);
 int sphb200_engine_last_times(sphb200_engine *e, float ms[8]);
 /* cell-grid facts for reports: ncells[3], sub[3], tile[3], threads, list_cap, stage_cap(A,B,C). */
 int sphb200_engine_plan(const sphb200_engine *e, int32_t out[16]);
+/* sync: [0] steps run since creation, [1] searches (cell sort + candidate walk) among them,
+ * [2] row length of the neighbour lists, [3] skin in 1e-6 of the cutoff, [4] tiles,
+ * [5] tiles whose lists do not exist (swept by their own search), [6..7] reserved. */
+int sphb200_engine_counters(sphb200_engine *e, int64_t out[8], void *stream);
+/* sync: measured FP32 throughput of this device in TFLOP/s (2 flop per lane-FMA): a grid of
+ * independent FMA chains, `packed` = 0: FFMA, 1: FFMA2 (fma.rn.f32x2).  The roofline denominator
+ * of the interaction sweeps (bench.py); ms = kernel time of the measurement. */
+int sphb200_fp32_peak(int packed, double *tflops, double *ms, void *stream);
 
 /* ---- slab decomposition: one engine per GPU, the caller moves the messages ----------------
  * The reference drives ONE device (jax_sph/simulate.py:110-134); north_star asks for the

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsphb200.so")
 
 # ---- constants mirrored from include/sphb200.h ------------------------------
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, EINVAL, ENOMEM, ECUDA, EDTYPE, EUNSUP, ENODEV = 0, -1, -2, -3, -4, -5, -6
 ERR_NEIGHBOR_OVERFLOW, ERR_CELL_OVERFLOW, ERR_STAGE_OVERFLOW, ERR_NONFINITE = 1, 2, 4, 8
 ERR_OUTSIDE_BOX = 16
@@ -51,7 +51,8 @@ class Config(C.Structure):
         ("bc_outflow_on", C.c_int32), ("bc_outflow_x", C.c_float),
         ("cell_sub", C.c_int32 * 3), ("tile", C.c_int32 * 3), ("threads", C.c_int32),
         ("list_cap", C.c_int32), ("stage_cap", C.c_int32), ("nl_cap", C.c_int32),
-        ("diff_delta", C.c_float), ("diff_alpha", C.c_float), ("reserved", C.c_int32 * 5),
+        ("diff_delta", C.c_float), ("diff_alpha", C.c_float), ("skin", C.c_float),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -96,6 +97,8 @@ SYMBOLS = {
     "sphb200_engine_profile": (C.c_int, [_P, C.c_int]),
     "sphb200_engine_last_times": (C.c_int, [_P, C.POINTER(C.c_float * 8)]),
     "sphb200_engine_plan": (C.c_int, [_P, C.POINTER(C.c_int32 * 16)]),
+    "sphb200_engine_counters": (C.c_int, [_P, C.POINTER(C.c_int64 * 8), _P]),
+    "sphb200_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _P]),
     "sphb200_slab_create": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.c_int64, C.c_int64,
                                       C.c_int64, C.POINTER(_P)]),
     "sphb200_slab_info": (C.c_int, [_P, C.POINTER(C.c_int64 * 16), C.POINTER(C.c_double * 4)]),

@@ -56,14 +56,18 @@ __host__ __device__ inline MigView mig_view(char* b, int cap) {
 // writes key + arrival rank (8 B); cell counters live in L2.  Slab mode: a particle
 // whose new cell lies outside the rank's own layers is an emigrant: its integrated
 // record goes to the send buffer of that direction and its key becomes -1.
+// `gate` (all kernels of the re-sort): a device word; the launch does nothing unless it is set
+// (nullptr: always runs).  The kernels are grid-stride loops so that a gated-off launch costs a
+// few hundred block exits, not one per 256 particles.
 template <int DIM>
 __global__ void __launch_bounds__(256) k_hash(int n, Grid g, Kick k, Slab sl, Frame f,
                                               int* __restrict__ key, int* __restrict__ rnk,
-                                              int* __restrict__ count, unsigned* __restrict__ err) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+                                              int* __restrict__ count, unsigned* __restrict__ err,
+                                              const int* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
   const int n_int = sl.dn ? sl.dn[DN_OWN] : n;           // integrated sources (own)
   const int n_src = sl.dn ? n_int + sl.dn[DN_IN] : n;    // + immigrants (already integrated)
-  if (t >= n_src) return;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_src; t += gridDim.x * blockDim.x) {
   const int p = sl.base + t;
   float4 a = f.pt[p];
   float r[3] = {a.x, a.y, a.z};
@@ -94,12 +98,12 @@ __global__ void __launch_bounds__(256) k_hash(int n, Grid g, Kick k, Slab sl, Fr
       key[p] = -1;
       if (!(down || up) || t >= n_int) {
         atomicOr(err, SPHB200_ERR_SLAB_MIGRATION);
-        return;
+        continue;
       }
       const int slot = atomicAdd(&sl.dn[down ? DN_EMIG_LO : DN_EMIG_HI], 1);
       if (slot >= sl.mig_cap) {
         atomicOr(err, SPHB200_ERR_SLAB_OVERFLOW);
-        return;
+        continue;
       }
       MigView m = mig_view(down ? sl.mig_lo : sl.mig_hi, sl.mig_cap);
       const float4 um = f.um[p], vv = f.vv[p];
@@ -112,11 +116,12 @@ __global__ void __launch_bounds__(256) k_hash(int n, Grid g, Kick k, Slab sl, Fr
       if (f.kc) m.kc[slot] = f.kc[p];
       if (f.nw) m.nw[slot] = f.nw[p];
       if (f.ge) m.ge[slot] = f.ge[p];
-      return;
+      continue;
     }
   }
   key[p] = cell;
   rnk[p] = atomicAdd(&count[cell], 1);
+  }
 }
 
 // K2: exclusive scan of the cell histogram -> cell_start[0..C].  Three small
@@ -153,7 +158,9 @@ __device__ __forceinline__ int block_incl_scan(int v, int* sh /* >= 32 ints */, 
 }
 
 __global__ void __launch_bounds__(SCAN_TPB) k_scan_partial(int c, const int* __restrict__ count,
-                                                           int* __restrict__ bsum) {
+                                                           int* __restrict__ bsum,
+                                                           const int* __restrict__ gate = nullptr) {
+  if (gate != nullptr && *gate == 0) return;
   __shared__ int sh[32];
   int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int s = 0;
@@ -165,7 +172,9 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_partial(int c, const int* __r
 }
 
 // single block: exclusive scan of bsum[0..nb) in place (nb arbitrary)
-__global__ void __launch_bounds__(1024) k_scan_bsum(int nb, int* __restrict__ bsum) {
+__global__ void __launch_bounds__(1024) k_scan_bsum(int nb, int* __restrict__ bsum,
+                                                    const int* __restrict__ gate = nullptr) {
+  if (gate != nullptr && *gate == 0) return;
   __shared__ int sh[32];
   __shared__ int carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -187,7 +196,9 @@ __global__ void __launch_bounds__(1024) k_scan_bsum(int nb, int* __restrict__ bs
 __global__ void __launch_bounds__(SCAN_TPB) k_scan_final(int c, int off, int* __restrict__ count,
                                                          const int* __restrict__ bsum,
                                                          int* __restrict__ start,
-                                                         int* __restrict__ maxocc) {
+                                                         int* __restrict__ maxocc,
+                                                         const int* __restrict__ gate = nullptr) {
+  if (gate != nullptr && *gate == 0) return;
   __shared__ int sh[32];
   int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
@@ -219,12 +230,15 @@ __global__ void __launch_bounds__(SCAN_TPB) k_scan_final(int c, int off, int* __
 __global__ void __launch_bounds__(256) k_scatter_src(int n, Slab sl, const int* __restrict__ key,
                                                      const int* __restrict__ rnk,
                                                      const int* __restrict__ start,
-                                                     int* __restrict__ src) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (sl.dn ? sl.dn[DN_OWN] + sl.dn[DN_IN] : n)) return;
-  const int p = sl.base + t;
-  const int k = key[p];
-  if (k >= 0) src[start[k] + rnk[p]] = p;  // emigrants (key -1) drop out here
+                                                     int* __restrict__ src,
+                                                     const int* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
+  const int bound = sl.dn ? sl.dn[DN_OWN] + sl.dn[DN_IN] : n;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < bound; t += gridDim.x * blockDim.x) {
+    const int p = sl.base + t;
+    const int k = key[p];
+    if (k >= 0) src[start[k] + rnk[p]] = p;  // emigrants (key -1) drop out here
+  }
 }
 
 // K4: stable in-cell rank + integrate + gather the whole frame into the new
@@ -237,17 +251,21 @@ template <int DIM>
 __global__ void __launch_bounds__(256) k_reorder(int n, Grid g, Kick k, Slab sl, ReorderOpt o,
                                                  Frame a, Frame b, const int* __restrict__ key,
                                                  const int* __restrict__ start,
-                                                 const int* __restrict__ src) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+                                                 const int* __restrict__ src,
+                                                 const int* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
   // slab mode: the own count after migration is the scan total (halo cells are still empty)
-  if (t >= (sl.dn ? start[g.ncells] - sl.base : n)) return;
+  const int bound = sl.dn ? start[g.ncells] - sl.base : n;
+  const int kick_on = k.on;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < bound; t += gridDim.x * blockDim.x) {
   const int s = sl.base + t;
   int p = src[s];
+  k.on = kick_on;
   if (sl.dn && p - sl.base >= sl.dn[DN_OWN]) k.on = 0;  // immigrants arrive integrated
   int cell = key[p];
   int lo = start[cell], hi = start[cell + 1];
   int rank = 0;
-  for (int t = lo; t < hi; ++t) rank += (__ldg(&src[t]) < p);
+  for (int q = lo; q < hi; ++q) rank += (__ldg(&src[q]) < p);
   int f = lo + rank;
 
   float4 pt = a.pt[p], um = a.um[p], vv = a.vv[p], du = a.du[p];
@@ -262,6 +280,77 @@ __global__ void __launch_bounds__(256) k_reorder(int n, Grid g, Kick k, Slab sl,
   if (o.heat) b.kc[f] = a.kc[p];
   if (o.has_nw) b.nw[f] = a.nw[p];
   if (o.has_ge) b.ge[f] = a.ge[p];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Resident single-GPU engines keep the particles in place between two searches (sweep.cuh):
+//
+// k_drift: kick + drift + wrap of integrator.py:26-30 / space.py:207-209 IN PLACE, the path each
+// particle has travelled since the last sort, and the decision whether THIS step re-sorts and
+// searches: a path longer than `limit` (half the skin of the neighbour lists) raises *flag_cur.
+// Sweeps only ever see positions whose paths are within the limit, so a pair that is inside the
+// cutoff now was inside cutoff + skin at the last search and is in the skin list.
+// The flag words alternate between steps: this launch also clears the next step's word.
+template <int DIM>
+__global__ void __launch_bounds__(256) k_drift(int n, Grid g, Kick k, Frame f,
+                                               float* __restrict__ path, int* flag_cur,
+                                               int* flag_next, int force, float limit,
+                                               unsigned* __restrict__ err) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *flag_next = 0;
+    if (force) atomicOr(flag_cur, 1);
+  }
+  bool over = false;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const float4 a = f.pt[p], b = f.um[p], w = f.vv[p];
+    float r[3] = {a.x, a.y, a.z}, u[3] = {b.x, b.y, b.z}, v[3] = {w.x, w.y, w.z};
+    integrate_one<DIM>(k, g, r, u, v, f.du[p], f.dv[p]);
+    float s2 = 0.f;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      const float s = k.dt * v[d];
+      s2 += s * s;
+    }
+    const float pl = path[p] + sqrtf(s2);
+    path[p] = pl;
+    over = over || !(pl <= limit);
+    const bool finite = isfinite(r[0]) && isfinite(r[1]) && (DIM == 2 || isfinite(r[2]));
+    if (!finite) atomicOr(err, SPHB200_ERR_NONFINITE);
+    const bool inside = r[0] >= 0.f && r[0] <= g.box[0] && r[1] >= 0.f && r[1] <= g.box[1] &&
+                        (DIM == 2 || (r[2] >= 0.f && r[2] <= g.box[2]));
+    if (finite && !inside) atomicOr(err, SPHB200_ERR_OUTSIDE_BOX);
+    f.pt[p] = make_float4(r[0], r[1], r[2], a.w);
+    f.um[p] = make_float4(u[0], u[1], u[2], b.w);
+    f.vv[p] = make_float4(v[0], v[1], v[2], w.w);
+  }
+  if (__syncthreads_or(over) && threadIdx.x == 0) atomicOr(flag_cur, 1);
+}
+
+// forward-only steps (no integration): just the flag protocol of k_drift
+__global__ void k_gate(int* flag_cur, int* flag_next, int force) {
+  *flag_next = 0;
+  if (force) *flag_cur = 1;
+}
+
+// After a re-sort (k_reorder: frame a -> frame b) the sorted particles go back to frame a, so
+// that the host always launches on the same frame whether or not the device decided to re-sort.
+__global__ void __launch_bounds__(256) k_copyback(int n, ReorderOpt o, Frame a, Frame b,
+                                                  float* __restrict__ path,
+                                                  const int* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    a.pt[p] = b.pt[p];
+    a.um[p] = b.um[p];
+    a.vv[p] = b.vv[p];
+    a.st[p] = b.st[p];
+    a.du[p] = b.du[p];
+    a.id[p] = b.id[p];
+    if (o.heat) a.kc[p] = b.kc[p];
+    if (o.has_nw) a.nw[p] = b.nw[p];
+    if (o.has_ge) a.ge[p] = b.ge[p];
+    path[p] = 0.f;
+  }
 }
 
 // ---------------------------------------------------------------------------

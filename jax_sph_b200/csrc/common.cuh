@@ -42,8 +42,11 @@ struct Grid {
   float inv_cell[3];
   float box[3], half[3];
   float c2;      // f32(cutoff)^2 rounded to f32  (jax_md/partition.py:820-822)
-  float c2_hi;   // fast-reject threshold  (> c2, covers rounding of the fast path)
+  float c2_hi;   // threshold of the search: (cutoff + skin)^2 plus the rounding of its cheap test
   float c2_lo;   // below this the pair is inside for every rounding
+  float c2_fb;   // cheap-reject threshold of the fall-back search inside list consumers: c2_hi,
+                 // or +inf when the cell table may be frozen (a particle that drifted across the
+                 // periodic seam since the last sort is not where the image shift expects it)
   // Slab decomposition (one rank's view; single GPU: goff = 0, ng = n, own = [0, n)).
   // n[] are the LOCAL cells this rank indexes (own layers + S halo layers each side along the
   // slab axis), positions stay global, so the periodic image of a staged cell is decided by
@@ -52,6 +55,7 @@ struct Grid {
   int ng[3];     // global cells per axis
   int own_lo[3], own_hi[3];  // local cell range this rank owns (sweeps tile exactly this range)
   int block0;    // first tile of this launch (a sweep may be launched over a sub-range of tiles)
+  int ntl;       // tiles of this launch: [block0, block0 + ntl)
 };
 
 // Derived float32 constants, rounded where the reference rounds them.

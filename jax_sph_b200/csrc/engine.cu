@@ -1,11 +1,15 @@
 // engine.cu -- host side of libsphb200.so: planning, arena, launches, C ABI.
 //
-// The per-step pipeline (one call of si_euler.advance, integrator.py:22-56):
-//   k_hash        kick + drift + wrap (recomputed, not stored) -> cell key, arrival rank, histogram
-//   k_scan_*      cell histogram -> cell_start table
-//   k_scatter_src arrival slot -> source index
-//   k_reorder     stable in-cell rank, kick + drift + wrap, gather into the new cell-sorted frame
-//   k_sweep<PhysDensity>  [k_sweep<PhysRenorm>]  [k_sweep<PhysWall>]  k_sweep<PhysForce>  [k_bc]
+// The per-step pipeline (one call of si_euler.advance, integrator.py:22-56) of a resident engine:
+//   k_drift       kick + drift + wrap in place; path travelled since the last sort; raises the
+//                 step's re-sort flag when a path exceeds half the skin of the neighbour lists
+//   [flag set]    k_hash -> k_scan_* -> k_scatter_src -> k_reorder -> k_copyback   (cell sort)
+//                 k_sweep<PhysNone, LIST_BUILD>                                     (the search)
+//   k_sweep<PhysDensity, LIST_FILTER>  exact membership test + density + exact list of the step
+//   [k_sweep<PhysRenorm>]  [k_sweep<PhysWall>]  k_sweep<PhysForce>  (LIST_CONSUME)  [k_bc]
+// The flag lives on the device: every kernel of the bracketed group is launched every step and
+// returns at once unless it is set, so a step never synchronises with the host.  Slab engines
+// (one per GPU) sort and search every step: particles migrate between ranks (slab.cuh).
 // The state never leaves HBM between steps; the original particle order is
 // restored only by k_unpack (download).
 #include <cuda_runtime.h>
@@ -56,16 +60,30 @@ struct sphb200_engine {
   int cur;
   bool cells_valid;
   int *key, *rnk, *src, *count, *start, *bsum, *maxocc, *wallcount, *nl_counts;
-  // per-step neighbour lists shared by the sweeps of one forward() (sweep.cuh, NList)
+  // neighbour lists (sweep.cuh, NList): pl_* the exact list of the step, sl_* the skin list
   unsigned short* pl_list;
   int* pl_cnt;
   unsigned char* pl_ok;
   int pl_lmax;
+  unsigned short* sl_list;
+  int* sl_cnt;
+  // frozen sort (resident single-GPU engines): the particles keep their slots and the cell table
+  // stays as it is until a particle has travelled more than path_limit since the last sort
+  bool inplace;
+  double skin_frac;         // skin / cutoff
+  float path_limit;         // < 0: sort + search every step
+  float* path;              // [n] path length since the last sort
+  int* ctl;                 // [0], [1] re-sort flag of even / odd steps, [2] searches so far
+  unsigned long long step_no;
+  const int* gate_cur;      // flag word of the step being enqueued (nullptr: ungated)
+  bool force_rebuild;       // the next step must sort + search (new state, lists stale)
+  bool maybe_drifted;       // particles may have left the cells of the frozen table
+  int num_sms;
   unsigned* err;
   double* stats;  // [ekin, umax] of sphb200_engine_stats / the SPHB200_NSTATS words of _get_stats
   int nscan_blocks;
   int tpb, lcap;
-  SweepPlan planA, planR, planW, planC, planN;
+  SweepPlan planA, planR, planW, planC, planN, planB;
   bool has_kc, has_nw, has_ut, has_ge;
   int64_t launches;
   bool profile;
@@ -166,8 +184,16 @@ int max_stage_bytes(const sphb200_config& c) {
 }
 
 // Cell grid, stencil and tiling (host).  nranks > 1: the local view of rank `rank`.
-void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nranks = 1) {
-  const double cutoff = kernel_cutoff(c);
+// skin / cutoff of an engine for this config (slab engines: 0, they search every step)
+double plan_skin(const sphb200_config& c, bool slab) {
+  if (slab || c.nl_cap < 0 || c.skin < 0.f) return 0.0;
+  if (c.skin > 0.f) return c.skin > 1.f ? 1.0 : (double)c.skin;
+  return 0.10;  // tuned on B200 (profiles/r02_skin_*.txt)
+}
+
+void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nranks = 1,
+               double skin_frac = 0.0) {
+  const double cutoff = kernel_cutoff(c) * (1.0 + skin_frac);  // what the cells and the search cover
   double pop = 1.0;
   g.exact_all = 0;
   g.ncells = 1;
@@ -240,11 +266,14 @@ void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nran
   }
   for (int a = 0; a < 3; ++a) g.nt[a] = (g.own_hi[a] - g.own_lo[a] + g.T[a] - 1) / g.T[a];
 
-  const float cf = (float)cutoff;
+  const float cf = (float)kernel_cutoff(c);
   g.c2 = cf * cf;  // float32 product, jax_md/partition.py:820-822
+  g.block0 = 0;
+  g.ntl = g.nt[0] * g.nt[1] * g.nt[2];
   if (g.exact_all) {
     g.c2_hi = INFINITY;
     g.c2_lo = -1.0f;
+    g.c2_fb = INFINITY;
   } else {
     double side = 0;
     for (int a = 0; a < c.dim; ++a) side = fmax(side, c.box[a]);
@@ -252,6 +281,7 @@ void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nran
     const double chi = cutoff + errd, clo = fmax(0.0, cutoff - errd);
     g.c2_hi = (float)(chi * chi * (1.0 + 1e-6));
     g.c2_lo = (float)(clo * clo * (1.0 - 1e-6));
+    g.c2_fb = skin_frac > 0.0 ? INFINITY : g.c2_hi;
   }
 }
 
@@ -309,7 +339,7 @@ bool bc_table_on(const sphb200_config& c) {
 struct Layout {
   size_t frame[2][12];
   size_t key, rnk, src, count, start, bsum, maxocc, wallcount, err, stats, nl_counts, ut;
-  size_t pl_list, pl_cnt, pl_ok;
+  size_t pl_list, pl_cnt, pl_ok, sl_list, sl_cnt, path, ctl;
   size_t dl, dg;  // Delta-SPH density diffusion (PhysDelta)
   int pl_lmax;
   size_t dn;
@@ -326,17 +356,17 @@ void feature_flags(const sphb200_config& c, bool& kc, bool& nw, bool& ut, bool& 
 
 // Row length of the per-step neighbour lists: 1.3 x the expected number of
 // neighbours of a particle in a uniform fluid (+8), a multiple of 8; 0 = lists off.
-int plan_lmax(const sphb200_config& c) {
+int plan_lmax(const sphb200_config& c, double skin_frac) {
   if (c.nl_cap < 0) return 0;
   if (c.nl_cap > 0) return (c.nl_cap + 7) / 8 * 8;
-  const double q = kernel_cutoff(c) / c.dx;
+  const double q = kernel_cutoff(c) * (1.0 + skin_frac) / c.dx;
   const double expect = c.dim == 2 ? M_PI * q * q : 4.0 / 3.0 * M_PI * q * q * q;
   int lmax = ((int)(1.3 * expect) + 8 + 7) / 8 * 8;
   if (lmax > 1024) lmax = 0;  // very wide kernels: not worth the memory
   return lmax;
 }
 
-void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, Layout& L) {
+void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, double skin_frac, Layout& L) {
   bool kc, nw, ut, ge;
   feature_flags(c, kc, nw, ut, ge);
   size_t off = 0;
@@ -369,13 +399,17 @@ void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, Layout& L) {
   L.err = take(4);
   L.stats = take(SPHB200_NSTATS * 8);
   L.dn = take(DN_WORDS * 4);
-  L.pl_lmax = plan_lmax(c);
+  L.path = take((size_t)n * 4);
+  L.ctl = take(8 * 4);
+  L.pl_lmax = plan_lmax(c, skin_frac);
   if (L.pl_lmax > 0) {
     L.pl_list = take((size_t)n * L.pl_lmax * 2);
     L.pl_cnt = take((size_t)n * 4);
+    L.sl_list = take((size_t)n * L.pl_lmax * 2);
+    L.sl_cnt = take((size_t)n * 4);
     L.pl_ok = take((size_t)g.nt[0] * g.nt[1] * g.nt[2]);
   } else {
-    L.pl_list = L.pl_cnt = L.pl_ok = (size_t)-1;
+    L.pl_list = L.pl_cnt = L.pl_ok = L.sl_list = L.sl_cnt = (size_t)-1;
   }
   L.total = off;
 }
@@ -417,16 +451,29 @@ SweepPlan plan_sweep_bytes(const sphb200_engine* e, int sb, int lcap) {
   return p;
 }
 
+// gate: device flag word the launch is conditional on (the search of a resident engine: a small
+// persistent grid, so that a gated-off launch costs one block exit per SM); fresh: the cell table
+// was rebuilt from the current positions just before (the fall-back search may use its cheap
+// reject although the engine's lists carry a skin).
 template <class K>
 int launch_sweep(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f, const Extra& ex,
-                 cudaStream_t st, const NList& nl = NList{nullptr, nullptr, nullptr, 0, 0}) {
+                 cudaStream_t st,
+                 const NList& nl = NList{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr},
+                 const int* gate = nullptr, bool persistent = false, bool fresh = false) {
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
   // a sweep may stage fewer bytes than its plan was sized for, never more
   const int sb = ex.sb > 0 ? ex.sb : 16 * ex.nq;
   if (sb > sp.sb) return SPHB200_EINVAL;
-  SweepDims sd{sp.cap, sp.lcap, sb};
+  SweepDims sd{sp.cap, sp.lcap, sb, gate, 1};
   const int all = e->grid.nt[0] * e->grid.nt[1] * e->grid.nt[2];
   Grid g = e->grid;
+  if (fresh) g.c2_fb = g.c2_hi;
+  int resident = 0;
+  if (persistent) {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, e->tpb, sp.smem));
+    resident = (per_sm > 0 ? per_sm : 1) * e->num_sms;
+  }
   // tile layers along the slab axis (the slowest tile index) covered by this launch
   const int ax = e->dim - 1, nl_ax = g.nt[ax], per_layer = all / nl_ax;
   int ranges[2][2] = {{0, nl_ax}, {0, 0}};
@@ -440,7 +487,9 @@ int launch_sweep(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f,
     const int blocks = (ranges[r][1] - ranges[r][0]) * per_layer;
     if (blocks <= 0) continue;
     g.block0 = ranges[r][0] * per_layer;
-    kern<<<blocks, e->tpb, sp.smem, st>>>(g, e->consts, f, e->start, sd, ex, e->err, nl);
+    g.ntl = blocks;
+    const int grid = (persistent && blocks > resident) ? resident : blocks;
+    kern<<<grid, e->tpb, sp.smem, st>>>(g, e->consts, f, e->start, sd, ex, e->err, nl);
     e->launches++;
   }
   CK(cudaGetLastError());
@@ -518,42 +567,63 @@ __global__ void __launch_bounds__(256)
 
 // first half of the cell pipeline: kick + drift + wrap (recomputed later, not stored), cell
 // key, arrival rank, histogram; slab mode: emigrants leave through e->slab.mig_*
-int hash_cells(sphb200_engine* e, const Kick& k, cudaStream_t st) {
+// blocks of a grid-stride streaming kernel over `bound` particles
+int stream_blocks(const sphb200_engine* e, int bound) {
+  const int nb = (bound + 255) / 256, cap = e->num_sms * 16;
+  return nb < cap ? (nb > 0 ? nb : 1) : cap;
+}
+
+int hash_cells(sphb200_engine* e, const Kick& k, cudaStream_t st, const int* gate = nullptr) {
   const int bound = e->slab_on ? e->sgeom.own_cap : e->n;
-  const int nb = (bound + 255) / 256;
+  const int nb = stream_blocks(e, bound);
   Frame& A = e->fr[e->cur];
   if (e->dim == 2)
-    k_hash<2><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, A, e->key, e->rnk, e->count, e->err);
+    k_hash<2><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, A, e->key, e->rnk, e->count, e->err, gate);
   else
-    k_hash<3><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, A, e->key, e->rnk, e->count, e->err);
+    k_hash<3><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, A, e->key, e->rnk, e->count, e->err, gate);
   e->launches += 1;
   CK(cudaGetLastError());
   return SPHB200_OK;
 }
 
 // second half: cell table, slot -> source, stable reorder into the other frame
-int sort_cells(sphb200_engine* e, const Kick& k, cudaStream_t st) {
+// nw_fn of the integrator on the current frame (integrator.py:33-34: after the drift)
+int wall_normals(sphb200_engine* e, cudaStream_t st);
+
+int sort_cells(sphb200_engine* e, const Kick& k, cudaStream_t st, const int* gate = nullptr) {
   // slab mode: sources are own + immigrants; the new own count is only known on the device
   const int bound = e->slab_on ? e->sgeom.own_cap + 2 * e->slab.mig_cap : e->n;
-  const int nb = (bound + 255) / 256;
+  const int nb = stream_blocks(e, bound);
   Frame& A = e->fr[e->cur];
   Frame& B = e->fr[1 - e->cur];
   const int c = e->grid.ncells;
   const int sb = (c + SCAN_TILE) / SCAN_TILE;  // covers index c itself (start[c] = total)
-  k_scan_partial<<<sb, SCAN_TPB, 0, st>>>(c, e->count, e->bsum);
-  k_scan_bsum<<<1, 1024, 0, st>>>(sb, e->bsum);
-  k_scan_final<<<sb, SCAN_TPB, 0, st>>>(c, e->slab.base, e->count, e->bsum, e->start, e->maxocc);
-  k_scatter_src<<<nb, 256, 0, st>>>(bound, e->slab, e->key, e->rnk, e->start, e->src);
+  k_scan_partial<<<sb, SCAN_TPB, 0, st>>>(c, e->count, e->bsum, gate);
+  k_scan_bsum<<<1, 1024, 0, st>>>(sb, e->bsum, gate);
+  k_scan_final<<<sb, SCAN_TPB, 0, st>>>(c, e->slab.base, e->count, e->bsum, e->start, e->maxocc, gate);
+  k_scatter_src<<<nb, 256, 0, st>>>(bound, e->slab, e->key, e->rnk, e->start, e->src, gate);
   ReorderOpt o{e->has_kc ? 1 : 0, e->has_nw ? 1 : 0, e->has_ge ? 1 : 0};
   if (e->dim == 2)
-    k_reorder<2><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, o, A, B, e->key, e->start, e->src);
+    k_reorder<2><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, o, A, B, e->key, e->start, e->src, gate);
   else
-    k_reorder<3><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, o, A, B, e->key, e->start, e->src);
+    k_reorder<3><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, o, A, B, e->key, e->start, e->src, gate);
   e->launches += 5;
   CK(cudaGetLastError());
-  e->cur ^= 1;
+  if (e->inplace) {  // the sorted particles go back to the frame the host keeps launching on
+    k_copyback<<<nb, 256, 0, st>>>(e->n, o, A, B, e->path, gate);
+    e->launches++;
+    CK(cudaGetLastError());
+  } else {
+    e->cur ^= 1;
+  }
   e->cells_valid = true;
-  if (e->wl_n > 0 && e->has_nw && k.on) {  // integrator.py:33-34: nw = nw_fn(r) after the drift
+  if (e->inplace) return SPHB200_OK;  // begin_step runs nw_fn itself, on every integrating step
+  if (k.on) return wall_normals(e, st);
+  return SPHB200_OK;
+}
+
+int wall_normals(sphb200_engine* e, cudaStream_t st) {
+  if (e->wl_n > 0 && e->has_nw) {
     const int wb = e->slab_on ? e->sgeom.own_cap : e->n;
     Frame& F = e->fr[e->cur];
     if (e->dim == 2)
@@ -570,10 +640,47 @@ int sort_cells(sphb200_engine* e, const Kick& k, cudaStream_t st) {
   return SPHB200_OK;
 }
 
-int build_cells(sphb200_engine* e, const Kick& k, cudaStream_t st) {
-  int rc = hash_cells(e, k, st);
+// First half of one step of a resident engine: kick + drift + wrap in place and, when the
+// device decides so (k_drift) or the host knows the lists are stale, the cell sort.  The
+// search itself is the first launch of forward_stage(0), gated on the same flag word.
+int begin_step(sphb200_engine* e, const Kick& k, cudaStream_t st) {
+  int* fc = e->ctl + (e->step_no & 1ull);
+  int* fn = e->ctl + ((e->step_no + 1ull) & 1ull);
+  const int force = (e->force_rebuild || !e->cells_valid) ? 1 : 0;
+  Frame& F = e->fr[e->cur];
+  if (k.on) {
+    const int nb = stream_blocks(e, e->n);
+    if (e->dim == 2)
+      k_drift<2><<<nb, 256, 0, st>>>(e->n, e->grid, k, F, e->path, fc, fn, force, e->path_limit, e->err);
+    else
+      k_drift<3><<<nb, 256, 0, st>>>(e->n, e->grid, k, F, e->path, fc, fn, force, e->path_limit, e->err);
+    e->maybe_drifted = true;
+  } else {
+    k_gate<<<1, 1, 0, st>>>(fc, fn, force);
+  }
+  e->launches++;
+  CK(cudaGetLastError());
+  const Kick off{0.f, 0.f, 0};
+  int rc = hash_cells(e, off, st, fc);
+  if (!rc) rc = sort_cells(e, off, st, fc);
   if (rc) return rc;
-  return sort_cells(e, k, st);
+  if (k.on) rc = wall_normals(e, st);
+  e->gate_cur = fc;
+  e->force_rebuild = false;
+  e->step_no++;
+  return rc;
+}
+
+// Sort the current positions now (ungated) -- for callers that search on their own right
+// after (the neighbour-list materialiser).  The engine's lists no longer describe the new
+// order: the next step searches again.
+int sort_now(sphb200_engine* e, cudaStream_t st) {
+  const Kick off{0.f, 0.f, 0};
+  int rc = hash_cells(e, off, st);
+  if (!rc) rc = sort_cells(e, off, st);
+  e->force_rebuild = true;
+  e->maybe_drifted = false;
+  return rc;
 }
 
 // One stage of WCSPH.forward (solver.py:705-949): 0 density + EoS, 1 Shepard renormalisation,
@@ -614,8 +721,9 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
       plan_sweep_bytes(e, force_sb, e->pl_lmax > 0 ? (e->lcap < 24 ? e->lcap : 24) : e->lcap);
   const bool dens_extras = e->has_ut || (rie && bc_trick && heat);
   const SweepPlan planD = !evol ? (dens_extras ? e->planW : e->planA) : (!rie ? e->planR : e->planW);
-  // neighbour lists: built by the density sweep, consumed by every later sweep of this step
-  NList nl{e->pl_list, e->pl_cnt, e->pl_ok, e->pl_lmax, 0};
+  // neighbour lists (sweep.cuh): skin list from the last search, exact list written by the
+  // density sweep of this step and consumed by every later sweep
+  NList nl{e->pl_list, e->pl_cnt, e->sl_list, e->sl_cnt, e->pl_ok, e->pl_lmax, 0, e->ctl + 2};
   const SweepPlan planG = plan_sweep(e, e->dim == 3 ? 4 : 2, 24);  // PhysDelta<1>
   {
     int mc = planD.cap < planF.cap ? planD.cap : planF.cap;
@@ -627,8 +735,20 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
     if (wall_sweep && e->planC.cap < mc) mc = e->planC.cap;
     nl.min_cap = mc;
   }
-  // ---- density -------------------------------------------------------------
+  // ---- the search (on the steps that re-sorted), then density ---------------
   if (stage == 0) {
+    const bool first_sub = !(e->slab_on && delta_on && evol && e->delta_sub > 0);
+    if (e->pl_lmax > 0 && first_sub) {
+      Extra exb = make_extra();
+      exb.nq = 1;
+      Frame& FB = e->fr[e->cur];
+      const int* gate = e->inplace ? e->gate_cur : nullptr;
+      if (e->dim == 2)
+        rc = launch_sweep(e, k_sweep<2, PhysNone, LIST_BUILD>, e->planB, FB, exb, st, nl, gate, gate != nullptr);
+      else
+        rc = launch_sweep(e, k_sweep<3, PhysNone, LIST_BUILD>, e->planB, FB, exb, st, nl, gate, gate != nullptr);
+      if (rc) return rc;
+    }
     Extra ex = make_extra();
     ex.utilde = e->has_ut;
     ex.wallT = rie && bc_trick && heat;
@@ -639,12 +759,12 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
     if (!evol) {
       if (dens_extras) {
         ex.nq = 3;  // 3 quads fit in the 4-quad plan
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_SUM_X>, LIST_BUILD>, planD, F, ex, st, nl)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_SUM_X>, LIST_FILTER>, planD, F, ex, st, nl)
         DISPATCH_DK(e, CALL);
 #undef CALL
       } else {
         ex.nq = 1;
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_SUM>, LIST_BUILD>, planD, F, ex, st, nl)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_SUM>, LIST_FILTER>, planD, F, ex, st, nl)
         DISPATCH_DK(e, CALL);
 #undef CALL
       }
@@ -656,7 +776,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
       for (int sub = sub0; sub < sub1 && !rc; ++sub) {
         if (sub == 0) {
           ex.nq = 1;
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDelta<D, K, 0>, LIST_BUILD>, e->planA, F, ex, st, nl)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDelta<D, K, 0>, LIST_FILTER>, e->planA, F, ex, st, nl)
           DISPATCH_DK(e, CALL);
 #undef CALL
         } else if (sub == 1) {
@@ -683,12 +803,12 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
       }
     } else if (!rie) {
       ex.nq = 2;
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_EVOL_SPH>, LIST_BUILD>, planD, F, ex, st, nl)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_EVOL_SPH>, LIST_FILTER>, planD, F, ex, st, nl)
       DISPATCH_DK(e, CALL);
 #undef CALL
     } else {
       ex.nq = 4;
-#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_EVOL_RIE>, LIST_BUILD>, planD, F, ex, st, nl)
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_EVOL_RIE>, LIST_FILTER>, planD, F, ex, st, nl)
       DISPATCH_DK(e, CALL);
 #undef CALL
     }
@@ -957,11 +1077,20 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   if (e->tpb > 512) e->tpb = 512;
   e->lcap = cfg->list_cap > 0 ? cfg->list_cap : 48;  // tuned on B200 (profiles/, tune logs)
   if (e->lcap < SWEEP_CHUNK) e->lcap = SWEEP_CHUNK;
-  plan_grid(*cfg, e->grid, e->tpb, e->slab_rank, e->slab_nranks);
+  e->inplace = !e->slab_on;
+  e->skin_frac = plan_skin(*cfg, e->slab_on);
+  plan_grid(*cfg, e->grid, e->tpb, e->slab_rank, e->slab_nranks, e->skin_frac);
+  // half the skin, minus a margin for the rounding of positions and of the accumulated path
+  e->path_limit = e->skin_frac > 0.0 ? (float)(0.5 * e->skin_frac * kernel_cutoff(*cfg) * (1.0 - 1e-3)) : -1.0f;
+  e->step_no = 0;
+  e->gate_cur = nullptr;
+  e->force_rebuild = true;
+  e->maybe_drifted = false;
+  CK(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev));
   plan_consts(*cfg, e->consts);
   feature_flags(*cfg, e->has_kc, e->has_nw, e->has_ut, e->has_ge);
   Layout L;
-  plan_layout(*cfg, n, e->grid, L);
+  plan_layout(*cfg, n, e->grid, e->skin_frac, L);
   if (ws_bytes < L.total) return SPHB200_ENOMEM;
   e->arena = (char*)ws;
   e->arena_bytes = L.total;
@@ -1004,6 +1133,10 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->pl_list = L.pl_lmax ? (unsigned short*)(e->arena + L.pl_list) : nullptr;
   e->pl_cnt = L.pl_lmax ? (int*)(e->arena + L.pl_cnt) : nullptr;
   e->pl_ok = L.pl_lmax ? (unsigned char*)(e->arena + L.pl_ok) : nullptr;
+  e->sl_list = L.pl_lmax ? (unsigned short*)(e->arena + L.sl_list) : nullptr;
+  e->sl_cnt = L.pl_lmax ? (int*)(e->arena + L.sl_cnt) : nullptr;
+  e->path = (float*)(e->arena + L.path);
+  e->ctl = (int*)(e->arena + L.ctl);
   e->dn = (int*)(e->arena + L.dn);
   memset(&e->slab, 0, sizeof(e->slab));
   memset(&e->sgeom, 0, sizeof(e->sgeom));
@@ -1030,11 +1163,15 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->hstage = nullptr;
   e->hstage_bytes = 0;
   memset(e->times, 0, sizeof(e->times));
-  e->planA = plan_sweep(e, 1, e->lcap);
-  e->planR = plan_sweep(e, 2, e->lcap);
-  e->planW = plan_sweep(e, 4, e->lcap);
-  e->planC = plan_sweep(e, 4, 24);  // wall sweep: a list consumer
+  // sweeps that search (the list builder, the materialiser; every sweep when the lists are
+  // off) want long per-thread columns, list consumers the minimum (their fall-back path only)
+  const int lc = e->pl_lmax > 0 ? (e->lcap < 24 ? e->lcap : 24) : e->lcap;
+  e->planA = plan_sweep(e, 1, lc);
+  e->planR = plan_sweep(e, 2, lc);
+  e->planW = plan_sweep(e, 4, lc);
+  e->planC = plan_sweep(e, 4, lc);
   e->planN = plan_sweep(e, 2, e->lcap);
+  e->planB = plan_sweep(e, 1, e->lcap);
   e->needs_zero = true;  // control words are zeroed on the first upload's stream
   return SPHB200_OK;
 }
@@ -1045,6 +1182,49 @@ struct HostStage {
 };
 
 size_t state_floats(int dim) { return (size_t)(7 * dim + 10); }
+
+__global__ void k_count_bad(int tiles, const unsigned char* __restrict__ ok, int* out) {
+  int bad = 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < tiles; t += gridDim.x * blockDim.x)
+    bad += ok[t] == 0;
+  for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(FULL_MASK, bad, o);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, bad);
+}
+
+// Independent FMA chains: 16 per thread (8 packed pairs), no memory traffic.
+template <bool PACKED>
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a, float b) {
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = (float)(threadIdx.x + i) * 1e-3f;
+  if (PACKED) {
+    unsigned long long v[8], pa, pb;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(pa) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(pb) : "f"(b));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm("mov.b64 %0, {%1, %2};" : "=l"(v[i]) : "f"(x[2 * i]), "f"(x[2 * i + 1]));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v[i]) : "l"(pa), "l"(pb));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm("mov.b64 {%0, %1}, %2;" : "=f"(x[2 * i]), "=f"(x[2 * i + 1]) : "l"(v[i]));
+  } else {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = __fmaf_rn(x[i], a, b);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 
 }  // namespace
 
@@ -1084,9 +1264,10 @@ int sphb200_engine_bytes(const sphb200_config* cfg, int64_t n, size_t* bytes) {
   if (rc) return rc;
   if (!bytes) return SPHB200_EINVAL;
   Grid g;
-  plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : DEFAULT_TPB);
+  const double skin = plan_skin(*cfg, false);
+  plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : DEFAULT_TPB, 0, 1, skin);
   Layout L;
-  plan_layout(*cfg, n, g, L);
+  plan_layout(*cfg, n, g, skin, L);
   *bytes = L.total;
   return SPHB200_OK;
 }
@@ -1234,12 +1415,16 @@ static int upload_impl(sphb200_engine* e, const sphb200_state* s, int rows, cons
   if (e->has_ge && !dv.g_ext) return SPHB200_EINVAL;
   e->cur = 0;
   e->cells_valid = false;
+  e->force_rebuild = true;
+  e->maybe_drifted = false;
   if (e->needs_zero) {
     CK(cudaMemsetAsync(e->count, 0, (size_t)e->grid.ncells * 4, st));
     CK(cudaMemsetAsync(e->maxocc, 0, 4, st));
     CK(cudaMemsetAsync(e->err, 0, 4, st));
+    CK(cudaMemsetAsync(e->ctl, 0, 8 * 4, st));
     e->needs_zero = false;
   }
+  if (e->inplace) CK(cudaMemsetAsync(e->path, 0, (size_t)e->n * 4, st));
   CK(cudaMemsetAsync(e->wallcount, 0, 4, st));
   if (e->slab_on) {
     int h[DN_WORDS] = {0};
@@ -1368,7 +1553,7 @@ int sphb200_engine_advance_host(sphb200_engine* e, double dt, const sphb200_stat
   k.on = (flags & SPHB200_STEP_INTEGRATE) ? 1 : 0;
   const bool v_is_u = k.on && e->cfg.tvf == 0.0;
   if (e->profile) cudaEventRecord(e->ev[0], st);
-  rc = build_cells(e, k, st);
+  rc = begin_step(e, k, st);
   if (rc) return rc;
   if (e->profile) cudaEventRecord(e->ev[2], st);
   // r is final once the particles are integrated and reordered; u and v too unless the wall
@@ -1413,7 +1598,7 @@ int sphb200_engine_step(sphb200_engine* e, double dt, int nsteps, uint32_t flags
   const bool v_is_u = k.on && e->cfg.tvf == 0.0;
   for (int s = 0; s < nsteps; ++s) {
     if (e->profile) cudaEventRecord(e->ev[0], st);
-    int rc = build_cells(e, k, st);
+    int rc = begin_step(e, k, st);
     if (rc) return rc;
     if (e->profile) cudaEventRecord(e->ev[2], st);
     rc = run_forward(e, flags, v_is_u, st);
@@ -1439,9 +1624,8 @@ int sphb200_engine_neighbor_list(sphb200_engine* e, int32_t* idx, int64_t capaci
   if (!e || e->slab_on || capacity < 0 || capacity >= 2147483647LL) return SPHB200_EINVAL;
   if (!idx && capacity != 0) return SPHB200_EINVAL;  // idx == NULL: count only
   cudaStream_t st = (cudaStream_t)stream;
-  if (!e->cells_valid) {
-    Kick k{0.f, 0.f, 0};
-    int rc = build_cells(e, k, st);
+  if (!e->cells_valid || e->maybe_drifted) {  // the materialiser searches fresh cells
+    int rc = sort_now(e, st);
     if (rc) return rc;
   }
   const int n = e->n;
@@ -1455,8 +1639,9 @@ int sphb200_engine_neighbor_list(sphb200_engine* e, int32_t* idx, int64_t capaci
   ex.nl_idx = idx;
   ex.nl_capacity = capacity;
   ex.nl_fill = 0;
-  if (e->dim == 2) rc = launch_sweep(e, k_sweep<2, PhysNeighbors<2>>, e->planN, F, ex, st);
-  else rc = launch_sweep(e, k_sweep<3, PhysNeighbors<3>>, e->planN, F, ex, st);
+  const NList none{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr};
+  if (e->dim == 2) rc = launch_sweep(e, k_sweep<2, PhysNeighbors<2>>, e->planN, F, ex, st, none, nullptr, false, true);
+  else rc = launch_sweep(e, k_sweep<3, PhysNeighbors<3>>, e->planN, F, ex, st, none, nullptr, false, true);
   if (rc) return rc;
   // exclusive scan of the per-sender counts (original order) -> offsets (reuse rnk as scratch)
   const int sb = (n + SCAN_TILE - 1) / SCAN_TILE;
@@ -1475,8 +1660,8 @@ int sphb200_engine_neighbor_list(sphb200_engine* e, int32_t* idx, int64_t capaci
   e->launches += 1;
   ex.nl_fill = 1;
   ex.nl_offsets = e->rnk;
-  if (e->dim == 2) rc = launch_sweep(e, k_sweep<2, PhysNeighbors<2>>, e->planN, F, ex, st);
-  else rc = launch_sweep(e, k_sweep<3, PhysNeighbors<3>>, e->planN, F, ex, st);
+  if (e->dim == 2) rc = launch_sweep(e, k_sweep<2, PhysNeighbors<2>>, e->planN, F, ex, st, none, nullptr, false, true);
+  else rc = launch_sweep(e, k_sweep<3, PhysNeighbors<3>>, e->planN, F, ex, st, none, nullptr, false, true);
   CK(cudaGetLastError());
   return rc;
 }
@@ -1668,6 +1853,61 @@ int sphb200_engine_plan(const sphb200_engine* e, int32_t out[16]) {
   return SPHB200_OK;
 }
 
+int sphb200_engine_counters(sphb200_engine* e, int64_t out[8], void* stream) {
+  if (!e || !out) return SPHB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles = e->grid.nt[0] * e->grid.nt[1] * e->grid.nt[2];
+  int h[4] = {0, 0, 0, 0};
+  CK(cudaMemsetAsync(e->ctl + 3, 0, 4, st));
+  if (e->pl_ok && e->cells_valid) {
+    k_count_bad<<<64, 256, 0, st>>>(tiles, e->pl_ok, e->ctl + 3);
+    e->launches++;
+  }
+  CK(cudaMemcpyAsync(h, e->ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int i = 0; i < 8; ++i) out[i] = 0;
+  out[0] = (int64_t)e->step_no;
+  out[1] = h[2];
+  out[2] = e->pl_lmax;
+  out[3] = (int64_t)(e->skin_frac * 1e6 + 0.5);
+  out[4] = tiles;
+  out[5] = e->pl_ok ? h[3] : tiles;
+  return SPHB200_OK;
+}
+
+int sphb200_fp32_peak(int packed, double* tflops, double* ms, void* stream) {
+  if (!tflops) return SPHB200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int blocks = sms * 8, threads = 256, iters = 1 << 14;
+  float* out = nullptr;
+  if (cudaMalloc((void**)&out, (size_t)blocks * threads * 4) != cudaSuccess) return SPHB200_ENOMEM;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {  // first round warms up
+    cudaEventRecord(e0, st);
+    if (packed) k_fma_peak<true><<<blocks, threads, 0, st>>>(out, iters, 0.999f, 1e-3f);
+    else k_fma_peak<false><<<blocks, threads, 0, st>>>(out, iters, 0.999f, 1e-3f);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e0, e1);
+    if (rep > 0 && t < best) best = t;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (cudaGetLastError() != cudaSuccess) return SPHB200_ECUDA;
+  const double flop = 2.0 * 64.0 * iters * (double)blocks * threads;  // 64 lane-FMAs per iteration
+  *tflops = flop / (best * 1e-3) * 1e-12;
+  if (ms) *ms = best;
+  return SPHB200_OK;
+}
+
 // ---- slab decomposition (one engine per rank; the caller moves the messages) ----------------
 static int slab_spec(const sphb200_config* cfg, int rank, int nranks, int64_t own_cap,
                      int64_t halo_cap, int64_t mig_cap, SlabSpec* sp) {
@@ -1709,7 +1949,7 @@ int sphb200_slab_create(const sphb200_config* cfg, int rank, int nranks, int64_t
   Grid g;
   plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : DEFAULT_TPB, rank, nranks);
   Layout L;
-  plan_layout(*cfg, slab_slots(sp), g, L);
+  plan_layout(*cfg, slab_slots(sp), g, 0.0, L);
   void* ws = nullptr;
   if (cudaMalloc(&ws, L.total) != cudaSuccess) return SPHB200_ENOMEM;
   sphb200_engine* e = new (std::nothrow) sphb200_engine();
@@ -1930,9 +2170,11 @@ static int with_engine(const sphb200_config* cfg, int64_t n, void* ws, size_t ws
 int sphb200_neighbor_list(const sphb200_config* cfg, int64_t n, const float* r, int32_t* idx,
                           int64_t capacity, int mask_self, int64_t* count, uint32_t* err,
                           void* ws, size_t ws_bytes, void* stream) {
-  if (!r) return SPHB200_EINVAL;
+  if (!r || !cfg) return SPHB200_EINVAL;
   sphb200_engine* e = nullptr;
-  int rc = with_engine(cfg, n, ws, ws_bytes, &e);
+  sphb200_config one = *cfg;  // a one-shot search: cells of half a cutoff, no skin
+  one.skin = -1.f;
+  int rc = with_engine(&one, n, ws, ws_bytes, &e);
   if (rc) return rc;
   sphb200_state s;
   memset(&s, 0, sizeof(s));

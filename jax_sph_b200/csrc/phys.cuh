@@ -29,14 +29,36 @@ __device__ __forceinline__ float dot3(const float (&a)[3], const float (&b)[3], 
 }
 
 // ---------------------------------------------------------------------------
+// The search (LIST_BUILD) carries no physics: it stages positions only.
+struct PhysNone {
+  static constexpr int MINB = 2;
+  static constexpr bool SENDER_VIEW = false;
+  static constexpr bool SPARSE = false;
+  struct Own {};
+  struct Acc {};
+  __device__ static void stage(const Consts&, const Frame& f, const Extra&, int gp, float4* sq,
+                               int, int d) {
+    sq[d] = f.pt[gp];
+  }
+  __device__ static void load_own(const Consts&, const Frame&, const Extra&, int, float4, Own&) {}
+  __device__ static bool active(const Consts&, const Own&) { return true; }
+  __device__ static void init(Acc&) {}
+  __device__ static void pair(const Consts&, const Extra&, const Own&, Acc&, const float4*, int,
+                              int, float4, const float (&)[3], float) {}
+  __device__ static void finish(const Consts&, const Frame&, const Extra&, int, const Own&,
+                                const Acc&) {}
+};
+
+// ---------------------------------------------------------------------------
 // DENS_SUM_X: summation plus the RIE wall helpers (u_tilde, wall temperature); the helpers
 // are compiled out of DENS_SUM / DENS_EVOL_SPH, which never need them.
 enum { DENS_SUM = 0, DENS_EVOL_SPH = 1, DENS_EVOL_RIE = 2, DENS_SUM_X = 3 };
 
 template <int DIM, int KERN, int MODE>
 struct PhysDensity {
-  static constexpr int MINB = (MODE == DENS_EVOL_RIE) ? 1 : 2;
+  static constexpr int MINB = (MODE == DENS_EVOL_RIE || MODE == DENS_SUM_X) ? 1 : 2;  // the heavy modes stage 48-64 B: one block per SM anyway
   static constexpr bool SENDER_VIEW = false;
+  static constexpr bool SPARSE = false;  // true: most particles are inactive (tile skip, sweep.cuh)
   // builder phase 2 takes two survivors per trip (sweep.cuh); heavy pair() bodies opt out
   static constexpr bool PAIR2 = MODE != DENS_EVOL_RIE;
   static constexpr bool SUM = MODE == DENS_SUM || MODE == DENS_SUM_X;
@@ -184,6 +206,7 @@ template <int DIM, int KERN, int STEP>
 struct PhysDelta {
   static constexpr int MINB = STEP == 0 ? 2 : 1;
   static constexpr bool SENDER_VIEW = false;
+  static constexpr bool SPARSE = false;  // true: most particles are inactive (tile skip, sweep.cuh)
   // builder phase 2 takes two survivors per trip (sweep.cuh); heavy pair() bodies opt out
   static constexpr bool PAIR2 = true;
   // Staged records, packed so that the stencil of a tile fits ONE staging group (a tile whose
@@ -364,6 +387,7 @@ template <int DIM, int KERN>
 struct PhysRenorm {
   static constexpr int MINB = 2;
   static constexpr bool SENDER_VIEW = false;
+  static constexpr bool SPARSE = false;  // true: most particles are inactive (tile skip, sweep.cuh)
   // builder phase 2 takes two survivors per trip (sweep.cuh); heavy pair() bodies opt out
   static constexpr bool PAIR2 = true;
   struct Own {};
@@ -400,6 +424,7 @@ template <int DIM, int KERN>
 struct PhysWall {
   static constexpr int MINB = 1;
   static constexpr bool SENDER_VIEW = false;
+  static constexpr bool SPARSE = true;   // true: most particles are inactive (tile skip, sweep.cuh)
   // builder phase 2 takes two survivors per trip (sweep.cuh); heavy pair() bodies opt out
   static constexpr bool PAIR2 = true;
   struct Own {
@@ -505,6 +530,7 @@ template <int DIM, int KERN, int SOLVER, int FEAT>
 struct PhysForce {
   static constexpr int MINB = 1;
   static constexpr bool SENDER_VIEW = false;
+  static constexpr bool SPARSE = false;  // true: most particles are inactive (tile skip, sweep.cuh)
   // builder phase 2 takes two survivors per trip (sweep.cuh); heavy pair() bodies opt out
   static constexpr bool PAIR2 = true;
   struct Own {
@@ -780,6 +806,7 @@ template <int DIM>
 struct PhysNeighbors {
   static constexpr int MINB = 2;
   static constexpr bool SENDER_VIEW = true;
+  static constexpr bool SPARSE = false;
   // builder phase 2 takes two survivors per trip (sweep.cuh); heavy pair() bodies opt out
   static constexpr bool PAIR2 = true;
   struct Own {

@@ -1,24 +1,31 @@
-// sweep.cuh -- the list-free pairwise sweep over cell-sorted particles.
+// sweep.cuh -- the pairwise sweeps over cell-sorted particles.
 //
 // Replaces the reference's candidate gather + prune + E-sized gathers +
 // segment_sum chains (jax_md/partition.py:832-909, solver.py:722-731 and every
-// ops.segment_sum in solver.py:750-928) by one kernel template.
+// ops.segment_sum in solver.py:750-928) by one kernel template in four roles.
 //
-// One thread block owns a tile of T[0] x T[1] x T[2] cells.  It
-//   1. stages the particles of the tile's stencil (tile + S cells each side)
-//      into shared memory with coalesced float4 loads, nq quads per particle;
-//   2. phase 1: every thread walks ITS OWN (2S+1)^d window of the staged cells
-//      with a cheap squared-distance test (no periodic fold: the image shift is
-//      applied once per row/segment to the thread's own coordinates) and appends
-//      the survivors' staged indices to a per-thread uint16 list in shared memory;
-//   3. phase 2: every thread consumes its list -- all lanes busy with real
-//      neighbours -- re-deriving the displacement with the reference's exact
-//      float32 arithmetic (space.py:170-181) and, inside the rounding band
-//      around the cutoff, the reference's membership metric d(r_j, r_i) < cutoff^2
-//      (jax_md/partition.py:897), so the neighbour SET is the reference's, bit for bit.
-// Phase 1 and phase 2 each exist at exactly one code site (the hot loops must
-// stay inside the instruction cache).  The physics (what is accumulated per
-// pair, what is written per particle) is a policy class P, see phys.cuh.
+// One thread block owns a tile of T[0] x T[1] x T[2] cells and stages the particles of the
+// tile's stencil (tile + S cells each side) into shared memory with coalesced float4 loads.
+//
+//   LIST_BUILD    (PhysNone, on the steps that re-sort the particles) the SEARCH: every thread
+//                 walks its own (2S+1)^d window of the staged cells with a cheap squared-distance
+//                 test against (cutoff + skin)^2 and writes the survivors' staged indices to its
+//                 row of the SKIN LIST in HBM.  No physics.
+//   LIST_FILTER   (the first sweep of forward(): density) every thread steps through its
+//                 skin-list row, re-derives the displacement with the reference's exact float32
+//                 arithmetic (space.py:170-181), keeps the pairs with d^2 < cutoff^2
+//                 (jax_md/partition.py:897 -- membership is decided every step, so the neighbour
+//                 set is the reference's although the search is amortised over several steps),
+//                 accumulates the physics and writes the survivors to the EXACT LIST of the step.
+//   LIST_CONSUME  (renormalisation, wall, force) steps through the exact list: every lane on a
+//                 real pair, no test.
+//   LIST_NONE     search + exact test + physics in one kernel (the neighbour-list materialiser;
+//                 also the fall-back path inside FILTER / CONSUME kernels for a tile whose lists
+//                 do not exist: stencil larger than one staging group, or a row overflow).
+// Between two searches the particles keep their slots and the cell table is frozen: a staged
+// index means the same particle in every sweep of every step until the next search (engine.cu).
+// The physics (what is accumulated per pair, what is written per particle) is a policy class P,
+// see phys.cuh.
 #pragma once
 #include "common.cuh"
 
@@ -35,26 +42,32 @@ struct SweepDims {
   int cap;   // staged particles per block
   int lcap;  // list entries per thread (>= SWEEP_CHUNK)
   int sb;    // bytes staged per particle (16 per quad + scalar columns, see phys.cuh)
+  const int* gate;  // device word; the launch does nothing unless *gate == gate_want (nullptr: always runs)
+  int gate_want;
 };
 
-// Per-step neighbour lists in HBM, shared by all sweeps of one forward():
-// the first sweep (density) BUILDS them from its phase-2 survivors, the later
-// sweeps (renorm / wall / force) CONSUME them and skip the search altogether.
-// Entries are STAGED indices (uint16): every sweep of a step stages a tile's
-// stencil in the same order, so the index means the same particle everywhere.
-// A particle's row is lmax entries, written in 16-byte chunks of 8.  A tile
-// whose stencil does not fit one staging group, or that holds a particle with
-// more than lmax neighbours, is marked not-ok and its consumers search on
-// their own (the list is an accelerator, never a correctness dependency).
+// Neighbour lists in HBM.  Entries are STAGED indices (uint16): every sweep stages a tile's
+// stencil in the same order, so the index means the same particle everywhere.  A particle's row
+// is lmax entries, read and written in 16-byte chunks of 8.
+//   sl / scnt  skin list: pairs within cutoff + skin when the particles were last sorted
+//              (LIST_BUILD writes, LIST_FILTER reads)
+//   xl / xcnt  exact list of the current step: the subset with d^2 < cutoff^2 now
+//              (LIST_FILTER writes, LIST_CONSUME reads)
+// A tile whose stencil does not fit one staging group of every sweep, or that holds a particle
+// with more than lmax skin neighbours, is marked not-ok and every sweep searches it on its own
+// (the lists are an accelerator, never a correctness dependency).
 struct NList {
-  unsigned short* list;  // [n][lmax], nullptr = lists off
-  int* cnt;              // [n] neighbours stored for the particle
+  unsigned short* xl;    // [n][lmax], nullptr = lists off
+  int* xcnt;             // [n]
+  unsigned short* sl;    // [n][lmax]
+  int* scnt;             // [n]
   unsigned char* ok;     // [tiles]
   int lmax;              // multiple of 8
   int min_cap;           // smallest staging capacity among the step's sweeps
+  int* nbuilds;          // device counter: searches run so far (LIST_BUILD adds one per launch)
 };
 
-enum { LIST_NONE = 0, LIST_BUILD = 1, LIST_CONSUME = 2 };
+enum { LIST_NONE = 0, LIST_BUILD = 1, LIST_CONSUME = 2, LIST_FILTER = 3 };
 
 __host__ __device__ inline size_t sweep_smem_bytes(int sb, int cap, int lcap, int tpb) {
   (void)tpb;
@@ -66,7 +79,9 @@ __device__ __forceinline__ int wrap_count(int u, int n) { return u < 0 ? -1 : (u
 __device__ __forceinline__ int wrap_cell(int u, int n) { return u < 0 ? u + n : (u >= n ? u - n : u); }
 
 // Reference displacement r_i - r_j (space.py:170-181) of one staged neighbour; INTERIOR: no
-// periodic image inside the tile's stencil, the fold is two adds.
+// periodic image inside the tile's stencil, the fold is two adds.  (A particle that drifted
+// across the periodic seam since the last sort is more than a cutoff away from every own
+// particle of an interior tile: the unfolded distance rejects it, as it must.)
 template <int DIM, bool INTERIOR>
 __device__ __forceinline__ void pair_disp(const Grid& g, const float (&ri)[3], const float4 pj,
                                           float (&dr)[3]) {
@@ -81,17 +96,21 @@ __device__ __forceinline__ void pair_disp(const Grid& g, const float (&ri)[3], c
   }
 }
 
-// List consumer: the neighbours of particle p were found by this step's density sweep.  All
-// lanes step through their rows together, every lane on a real pair, two pairs per iteration
-// so that two independent dependency chains (LDS -> displacement -> rsqrt -> kernel -> pair
-// terms) are in flight per warp: with one 512-thread block per SM there are only four warps
-// per scheduler to hide those latencies otherwise.
-template <int DIM, class P, bool INTERIOR>
+// List consumer.  All lanes step through their rows together, two pairs per iteration so that
+// two independent dependency chains (LDS -> displacement -> rsqrt -> kernel -> pair terms) are
+// in flight per warp.  FILTER: the row is the skin list; the exact membership test of the
+// reference runs on every entry and the survivors are appended to the exact list of the step
+// (four entries per 64-bit shift register, one STG.64 per four survivors).
+template <int DIM, class P, bool INTERIOR, bool FILTER>
 __device__ __forceinline__ void consume_list(const Grid& g, const Consts& c, const Extra& ex,
                                              const NList& nl, const float4* sq, int cap, int p,
-                                             int nn, const float (&ri)[3],
+                                             int nn, bool have, const float (&ri)[3],
                                              const typename P::Own& own, typename P::Acc& acc) {
-  const uint4* lrow = reinterpret_cast<const uint4*>(nl.list + (size_t)p * nl.lmax);
+  const size_t roff = (size_t)p * nl.lmax;
+  const uint4* lrow = reinterpret_cast<const uint4*>((FILTER ? nl.sl : nl.xl) + roff);
+  unsigned long long* xrow = reinterpret_cast<unsigned long long*>(nl.xl + roff);
+  unsigned long long xw = 0ull;
+  int m = 0;
   uint4 cur = make_uint4(0u, 0u, 0u, 0u), nxt = cur;
   if (nn > 0) nxt = __ldg(lrow);
   int k = 0;
@@ -108,8 +127,21 @@ __device__ __forceinline__ void consume_list(const Grid& g, const Consts& c, con
     pair_disp<DIM, INTERIOR>(g, ri, p0, d0);
     pair_disp<DIM, INTERIOR>(g, ri, p1, d1);
     const float s0 = sumsq<DIM>(d0), s1 = sumsq<DIM>(d1);
-    P::pair(c, ex, own, acc, sq, cap, j0, p0, d0, s0);
-    P::pair(c, ex, own, acc, sq, cap, j1, p1, d1, s1);
+    if (FILTER) {
+      if (s0 < g.c2) {
+        xw = (xw >> 16) | ((unsigned long long)j0 << 48);
+        if ((++m & 3) == 0) xrow[(m >> 2) - 1] = xw;
+        P::pair(c, ex, own, acc, sq, cap, j0, p0, d0, s0);
+      }
+      if (s1 < g.c2) {
+        xw = (xw >> 16) | ((unsigned long long)j1 << 48);
+        if ((++m & 3) == 0) xrow[(m >> 2) - 1] = xw;
+        P::pair(c, ex, own, acc, sq, cap, j1, p1, d1, s1);
+      }
+    } else {
+      P::pair(c, ex, own, acc, sq, cap, j0, p0, d0, s0);
+      P::pair(c, ex, own, acc, sq, cap, j1, p1, d1, s1);
+    }
   }
   if (k < nn) {
     if ((k & 7) == 0) cur = nxt;
@@ -117,14 +149,136 @@ __device__ __forceinline__ void consume_list(const Grid& g, const Consts& c, con
     const float4 p0 = sq[j0];
     float d0[3];
     pair_disp<DIM, INTERIOR>(g, ri, p0, d0);
-    P::pair(c, ex, own, acc, sq, cap, j0, p0, d0, sumsq<DIM>(d0));
+    const float s0 = sumsq<DIM>(d0);
+    if (!FILTER || s0 < g.c2) {
+      if (FILTER) {
+        xw = (xw >> 16) | ((unsigned long long)j0 << 48);
+        if ((++m & 3) == 0) xrow[(m >> 2) - 1] = xw;
+      }
+      P::pair(c, ex, own, acc, sq, cap, j0, p0, d0, s0);
+    }
+  }
+  if (FILTER && have) {
+    if (m & 3) xrow[m >> 2] = xw >> (16 * (4 - (m & 3)));  // the last, partial group of four
+    nl.xcnt[p] = m;
   }
 }
+
+// The search: one thread's walk through its (2S+1)^d window of the staged cells, as
+// 2 * W1 * W2 (row, x-segment) pieces (the x range of a row is split where the periodic image
+// changes).  All lanes of a warp advance through the pieces together.
+template <int DIM>
+struct Walk {
+  int w0[3], ka, kb, ks, it_step, nit;
+  float xs0, xs1;
+  int it, wy, wz, j, jb, row;
+  bool inwin;
+  float xs, ys, zs;
+
+  // ci: the particle's cell at the time of the last sort, relative to the local grid
+  __device__ __forceinline__ void init(const Grid& g, const int (&sa0)[3], const int (&ci)[3],
+                                       const float (&ri)[3], bool have) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) w0[a] = (g.n[a] >= 2 * g.S[a] + 1) ? (ci[a] - g.S[a] - sa0[a]) : 0;
+    const int kz = -sa0[0], kn = g.n[0] - sa0[0];  // staged x index of unwrapped cells 0 and n
+    ka = w0[0];
+    kb = w0[0] + g.W[0];
+    ks = kb;
+    if (ka < kz && kz < kb) ks = kz;
+    else if (ka < kn && kn < kb) ks = kn;
+    xs0 = ri[0] - (float)wrap_count(sa0[0] + ka, g.n[0]) * g.box[0];  // x is never the slab axis
+    xs1 = ri[0] - (float)wrap_count(sa0[0] + ks, g.n[0]) * g.box[0];
+    // the second x segment exists only where the window crosses the periodic seam: elsewhere
+    // (all lanes of the warp agree) the row loop visits first segments only
+    it_step = __any_sync(FULL_MASK, have && ks < kb) ? 1 : 2;
+    nit = 2 * g.W[1] * g.W[2];
+    it = -1; wy = -1; wz = 0; j = 0; jb = 0; row = 0;
+    inwin = false;
+    xs = ys = zs = 0.f;
+  }
+
+  // Phase 1: cheap reject against `thr`, survivors appended to the thread's shared-memory column
+  // (cnt entries so far, lcap at most).  Returns true when the window is exhausted, false when
+  // some lane's column cannot take the next chunk (the caller drains the columns and calls again).
+  __device__ __forceinline__ bool run(const Grid& g, const float4* sq, unsigned short* list, int tid,
+                                      int lcap, int& cnt, const int* soff, int base, int e_a,
+                                      int e_b, int nxs, int slen1, const int (&sa0)[3],
+                                      const float (&ri)[3], bool act, float thr) {
+    for (;;) {
+      const int rem = jb - j;
+      if (!__any_sync(FULL_MASK, rem > 0)) {
+        it = it < 0 ? 0 : it + it_step;
+        if (it >= nit) return true;
+        const int sgm = it & 1;
+        if (sgm == 0) {
+          if (++wy == g.W[1]) {
+            wy = 0;
+            ++wz;
+          }
+          const int ry = w0[1] + wy, rz = w0[2] + wz;
+          row = rz * slen1 + ry;
+          inwin = act;
+          ys = ri[1] - (float)wrap_count(sa0[1] + ry + g.goff[1], g.ng[1]) * g.box[1];
+          zs = ri[2] - (float)wrap_count(sa0[2] + rz + g.goff[2], g.ng[2]) * g.box[2];
+        }
+        const int kk0 = sgm == 0 ? ka : ks, kk1 = sgm == 0 ? ks : kb;
+        j = jb = 0;
+        if (inwin && kk0 < kk1) {
+          const int ea = max(row * nxs + kk0, e_a), eb = min(row * nxs + kk1, e_b);
+          if (ea < eb) {
+            j = soff[ea] - base;
+            jb = soff[eb] - base;
+          }
+        }
+        xs = sgm == 0 ? xs0 : xs1;
+        continue;
+      }
+      const int want = rem > 0 ? min(rem, SWEEP_CHUNK) : 0;
+      if (__any_sync(FULL_MASK, want > lcap - cnt)) return false;  // drain first
+      const int e = j + want;
+      int lo = cnt * LS + tid;  // tid < LS: lo / LS is the entry count at any time
+      // four candidates per trip, loaded before the first append: the appends go to the
+      // same shared-memory window the candidates come from, so the compiler would
+      // otherwise keep every load behind the previous store (one LDS latency per candidate)
+      for (; j + 4 <= e; j += 4) {
+        const float4 p0 = sq[j], p1 = sq[j + 1], p2 = sq[j + 2], p3 = sq[j + 3];
+        float t0 = xs - p0.x, t1 = xs - p1.x, t2 = xs - p2.x, t3 = xs - p3.x;
+        float d0 = t0 * t0, d1 = t1 * t1, d2 = t2 * t2, d3 = t3 * t3;
+        t0 = ys - p0.y; t1 = ys - p1.y; t2 = ys - p2.y; t3 = ys - p3.y;
+        d0 += t0 * t0; d1 += t1 * t1; d2 += t2 * t2; d3 += t3 * t3;
+        if (DIM == 3) {
+          t0 = zs - p0.z; t1 = zs - p1.z; t2 = zs - p2.z; t3 = zs - p3.z;
+          d0 += t0 * t0; d1 += t1 * t1; d2 += t2 * t2; d3 += t3 * t3;
+        }
+        if (d0 < thr) { list[lo] = (unsigned short)j; lo += LS; }
+        if (d1 < thr) { list[lo] = (unsigned short)(j + 1); lo += LS; }
+        if (d2 < thr) { list[lo] = (unsigned short)(j + 2); lo += LS; }
+        if (d3 < thr) { list[lo] = (unsigned short)(j + 3); lo += LS; }
+      }
+#pragma unroll 1
+      for (; j < e; ++j) {
+        const float4 pj = sq[j];
+        const float dx = xs - pj.x, dy = ys - pj.y;
+        float d2 = dx * dx + dy * dy;
+        if (DIM == 3) {
+          const float dz = zs - pj.z;
+          d2 += dz * dz;
+        }
+        if (d2 < thr) {
+          list[lo] = (unsigned short)j;
+          lo += LS;
+        }
+      }
+      cnt = lo / LS;
+    }
+  }
+};
 
 template <int DIM, class P, int LM = LIST_NONE>
 __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
     k_sweep(const Grid g, const Consts c, const Frame f, const int* __restrict__ cs,
             const SweepDims sd, const Extra ex, unsigned* __restrict__ err, const NList nl) {
+  if (sd.gate != nullptr && *sd.gate != sd.gate_want) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int TPB = blockDim.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = TPB >> 5;
@@ -133,371 +287,297 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
   int* soff = reinterpret_cast<int*>(list + (size_t)sd.lcap * LS);
   int* own_off = soff + (MAX_SOFF + 1);
   int* own_start = own_off + (MAX_RUNS + 1);
-
-  // ---- tile geometry (uniform) -------------------------------------------
-  int b = blockIdx.x + g.block0;
-  const int tile_id = b;
-  const int tx = b % g.nt[0];
-  b /= g.nt[0];
-  const int ty = b % g.nt[1];
-  const int tz = b / g.nt[1];
-  int c0[3] = {g.own_lo[0] + tx * g.T[0], g.own_lo[1] + ty * g.T[1], g.own_lo[2] + tz * g.T[2]};
-  int no[3], sa0[3], slen[3];
-  bool interior = true;  // no periodic image inside this tile's stencil
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    no[a] = min(g.T[a], g.own_hi[a] - c0[a]);
-    if (g.n[a] >= 2 * g.S[a] + 1) {
-      sa0[a] = c0[a] - g.S[a];
-      slen[a] = no[a] + 2 * g.S[a];
-    } else {
-      sa0[a] = 0;
-      slen[a] = g.n[a];
-    }
-    interior = interior && (a >= DIM || (sa0[a] + g.goff[a] >= 0 &&
-                                         sa0[a] + g.goff[a] + slen[a] <= g.ng[a] &&
-                                         g.n[a] >= 2 * g.S[a] + 2));
-  }
-  if (g.exact_all) interior = false;
-  const int nxs = slen[0];
-  const int nrows = slen[1] * slen[2];
-  const int E = nrows * nxs;
-  const int nruns = no[1] * no[2];
-
-  if (tid < nruns) {
-    int ry = tid % no[1], rz = tid / no[1];
-    int cell = ((c0[2] + rz) * g.n[1] + (c0[1] + ry)) * g.n[0] + c0[0];
-    int s = cs[cell];
-    own_start[tid] = s;
-    own_off[tid + 1] = cs[cell + no[0]] - s;
-  }
-  for (int e = tid; e < E; e += TPB) {
-    int k = e % nxs, row = e / nxs;
-    int ry = row % slen[1], rz = row / slen[1];
-    int cell = (wrap_cell(sa0[2] + rz, g.n[2]) * g.n[1] + wrap_cell(sa0[1] + ry, g.n[1])) * g.n[0] +
-               wrap_cell(sa0[0] + k, g.n[0]);
-    soff[e] = cs[cell + 1] - cs[cell];
-  }
-  __syncthreads();
-  if (warp == 0) {
-    // exclusive scan of soff[0..E) in place, soff[E] = total
-    int carry = 0;
-    for (int base = 0; base < E; base += 32) {
-      int i = base + lane;
-      int v = i < E ? soff[i] : 0;
-      int inc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(FULL_MASK, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (i < E) soff[i] = carry + inc - v;
-      carry += __shfl_sync(FULL_MASK, inc, 31);
-    }
-    if (lane == 0) {
-      soff[E] = carry;
-      int acc = 0;
-      own_off[0] = 0;
-      for (int r = 0; r < nruns; ++r) {
-        acc += own_off[r + 1];
-        own_off[r + 1] = acc;
-      }
-    }
-  }
-  __syncthreads();
-  const int tile_n = own_off[nruns];
-  if (tile_n == 0) return;
-  const int total_staged = soff[E];
-  const bool single_group = total_staged <= sd.cap;
-  const int kz = -sa0[0], kn = g.n[0] - sa0[0];  // staged x index of unwrapped cells 0 and n
-  const int nit = 2 * g.W[1] * g.W[2];
-
-  // neighbour-list mode of this block (uniform over the block, see NList)
   __shared__ int s_bad;
-  bool nl_build = false, nl_use = false;
-  if (LM == LIST_BUILD) {
-    nl_build = nl.list != nullptr && total_staged <= nl.min_cap;
-    if (tid == 0) s_bad = nl_build ? 0 : 1;  // ordered before any other write by the staging barrier
-  }
-  if (LM == LIST_CONSUME) nl_use = nl.list != nullptr && nl.ok[tile_id] != 0;
+  if (LM == LIST_BUILD && blockIdx.x == 0 && tid == 0 && nl.nbuilds) atomicAdd(nl.nbuilds, 1);
 
-  for (int ib = 0; ib < tile_n; ib += TPB) {
-    // ---- own particle ------------------------------------------------------
-    const int t = ib + tid;
-    const bool have = t < tile_n;
-    int p = 0;
-    if (have) {
-      int r = 0;
-      while (t >= own_off[r + 1]) ++r;
-      p = own_start[r] + (t - own_off[r]);
-    }
-    typename P::Own own;
-    typename P::Acc acc;
-    float ri[3] = {0.f, 0.f, 0.f};
-    int ci[3] = {0, 0, 0};
-    bool act = false;
-    if (have) {
-      float4 q = f.pt[p];
-      ri[0] = q.x; ri[1] = q.y; ri[2] = q.z;
-      cell_of<DIM>(g, ri, ci);
-      P::load_own(c, f, ex, p, q, own);
-      act = P::active(c, own);
-    }
-    P::init(acc);
-    int gk = 0, carry = 0;  // LIST_BUILD: entries already in HBM / survivors waiting in the column
-    // window origin in staged coordinates
-    int w0[3];
+  // a launch covers tiles [block0, block0 + ntl); gated launches use a small persistent grid
+  for (int tq = blockIdx.x; tq < g.ntl; tq += gridDim.x) {
+    if (tq != (int)blockIdx.x) __syncthreads();  // readers of the previous tile's tables are done
+
+    // ---- tile geometry (uniform) -------------------------------------------
+    int b = tq + g.block0;
+    const int tile_id = b;
+    const int tx = b % g.nt[0];
+    b /= g.nt[0];
+    const int ty = b % g.nt[1];
+    const int tz = b / g.nt[1];
+    int c0[3] = {g.own_lo[0] + tx * g.T[0], g.own_lo[1] + ty * g.T[1], g.own_lo[2] + tz * g.T[2]};
+    int no[3], sa0[3], slen[3];
+    bool interior = true;  // no periodic image inside this tile's stencil
 #pragma unroll
-    for (int a = 0; a < 3; ++a) w0[a] = (g.n[a] >= 2 * g.S[a] + 1) ? (ci[a] - g.S[a] - sa0[a]) : 0;
-    // x window, split where the periodic image changes
-    const int ka = w0[0], kb = w0[0] + g.W[0];
-    int ks = kb;
-    if (ka < kz && kz < kb) ks = kz;
-    else if (ka < kn && kn < kb) ks = kn;
-    const float xs0 = ri[0] - (float)wrap_count(sa0[0] + ka, g.n[0]) * g.box[0];  // x is never the slab axis
-    const float xs1 = ri[0] - (float)wrap_count(sa0[0] + ks, g.n[0]) * g.box[0];
-    // the second x segment exists only where the window crosses the periodic seam: elsewhere
-    // (all lanes of the warp agree) the row loop visits first segments only
-    const int it_step = __any_sync(FULL_MASK, have && ks < kb) ? 1 : 2;
+    for (int a = 0; a < 3; ++a) {
+      no[a] = min(g.T[a], g.own_hi[a] - c0[a]);
+      if (g.n[a] >= 2 * g.S[a] + 1) {
+        sa0[a] = c0[a] - g.S[a];
+        slen[a] = no[a] + 2 * g.S[a];
+      } else {
+        sa0[a] = 0;
+        slen[a] = g.n[a];
+      }
+      interior = interior && (a >= DIM || (sa0[a] + g.goff[a] >= 0 &&
+                                           sa0[a] + g.goff[a] + slen[a] <= g.ng[a] &&
+                                           g.n[a] >= 2 * g.S[a] + 2));
+    }
+    if (g.exact_all) interior = false;
+    const int nxs = slen[0];
+    const int nrows = slen[1] * slen[2];
+    const int E = nrows * nxs;
+    const int nruns = no[1] * no[2];
 
-    // ---- staging groups: maximal runs [e_a, e_b) of consecutive (row, cell) entries that
-    //      fit the staging buffer (one group unless the stencil is unusually crowded) ----
-    int e_a = 0;
-    while (e_a < E) {
-      const int base = soff[e_a];
-      int e_b = E;
-      if (!single_group) {
-        int lo = e_a, hi = E;  // largest e_b with soff[e_b] - base <= cap (soff is monotone)
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (soff[mid] - base <= sd.cap) lo = mid;
-          else hi = mid - 1;
+    if (tid < nruns) {
+      int ry = tid % no[1], rz = tid / no[1];
+      int cell = ((c0[2] + rz) * g.n[1] + (c0[1] + ry)) * g.n[0] + c0[0];
+      int s = cs[cell];
+      own_start[tid] = s;
+      own_off[tid + 1] = cs[cell + no[0]] - s;
+    }
+    for (int e = tid; e < E; e += TPB) {
+      int k = e % nxs, row = e / nxs;
+      int ry = row % slen[1], rz = row / slen[1];
+      int cell = (wrap_cell(sa0[2] + rz, g.n[2]) * g.n[1] + wrap_cell(sa0[1] + ry, g.n[1])) * g.n[0] +
+                 wrap_cell(sa0[0] + k, g.n[0]);
+      soff[e] = cs[cell + 1] - cs[cell];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // exclusive scan of soff[0..E) in place, soff[E] = total
+      int carry = 0;
+      for (int base = 0; base < E; base += 32) {
+        int i = base + lane;
+        int v = i < E ? soff[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int t = __shfl_up_sync(FULL_MASK, inc, o);
+          if (lane >= o) inc += t;
         }
-        e_b = lo;
+        if (i < E) soff[i] = carry + inc - v;
+        carry += __shfl_sync(FULL_MASK, inc, 31);
       }
-      bool skip = false;
-      if (e_b == e_a) {  // one cell alone exceeds the staging buffer
-        if (tid == 0) atomicOr(err, SPHB200_ERR_STAGE_OVERFLOW);
-        e_b = e_a + 1;
-        skip = true;
-      }
-      if (!skip && !(single_group && ib > 0)) {
-        if (ib > 0 || e_a > 0) __syncthreads();  // previous readers done
-        const int r_first = e_a / nxs, r_last = (e_b - 1) / nxs;
-        const int njobs = (r_last - r_first + 1) * 3;
-        for (int job = warp; job < njobs; job += nwarps) {
-          const int row = r_first + job / 3;
-          const int seg = job % 3 - 1;
-          const int klo = row == r_first ? e_a - row * nxs : 0;
-          const int khi = row == r_last ? e_b - row * nxs : nxs;
-          int k0 = max(klo, seg * g.n[0] - sa0[0]);
-          int k1 = min(khi, (seg + 1) * g.n[0] - sa0[0]);
-          if (k0 >= k1) continue;
-          const int ry = row % slen[1], rz = row / slen[1];
-          const int rowcell =
-              (wrap_cell(sa0[2] + rz, g.n[2]) * g.n[1] + wrap_cell(sa0[1] + ry, g.n[1])) * g.n[0];
-          const int gstart = cs[rowcell + (sa0[0] + k0 - seg * g.n[0])];
-          const int dst = soff[row * nxs + k0] - base;
-          const int len = soff[row * nxs + k1] - soff[row * nxs + k0];
-          for (int m = lane; m < len; m += 32) P::stage(c, f, ex, gstart + m, sq, sd.cap, dst + m);
+      if (lane == 0) {
+        soff[E] = carry;
+        int acc = 0;
+        own_off[0] = 0;
+        for (int r = 0; r < nruns; ++r) {
+          acc += own_off[r + 1];
+          own_off[r + 1] = acc;
         }
-        __syncthreads();
       }
-      if (!skip && LM == LIST_CONSUME && nl_use) {
-        const int nn = (have && act) ? nl.cnt[p] : 0;
-        if (interior)
-          consume_list<DIM, P, true>(g, c, ex, nl, sq, sd.cap, p, nn, ri, own, acc);
-        else
-          consume_list<DIM, P, false>(g, c, ex, nl, sq, sd.cap, p, nn, ri, own, acc);
-      } else if (!skip) {
-        // Walk the thread's window as 2 * W1 * W2 (row, x-segment) pieces.  All lanes
-        // advance through the pieces together; a warp-wide vote switches to phase 2
-        // whenever some lane's list cannot take the next chunk.
-        int it = -1, wy = -1, wz = 0, cnt = 0;
-        int j = 0, jb = 0, row = 0;
-        bool inwin = false;
-        float xs = 0.f, ys = 0.f, zs = 0.f;
+    }
+    __syncthreads();
+    const int tile_n = own_off[nruns];
+    if (tile_n == 0) continue;
+    const int total_staged = soff[E];
+    const bool single_group = total_staged <= sd.cap;
+
+    // list mode of this tile (uniform over the block, see NList)
+    bool nl_use = false;
+    if (LM == LIST_BUILD) {
+      if (nl.sl == nullptr || total_staged > nl.min_cap) {  // no lists for this tile
+        if (tid == 0 && nl.ok) nl.ok[tile_id] = 0;
+        continue;
+      }
+      if (tid == 0) s_bad = 0;  // ordered before any other write by the staging barrier
+    }
+    if (LM == LIST_CONSUME || LM == LIST_FILTER) nl_use = nl.xl != nullptr && nl.ok[tile_id] != 0;
+
+    // stage the (row, cell) entries [e_a, e_b) of the stencil; `base` = staged index of e_a
+    auto stage_group = [&](int e_a, int e_b, int base) {
+      const int r_first = e_a / nxs, r_last = (e_b - 1) / nxs;
+      const int njobs = (r_last - r_first + 1) * 3;
+      for (int job = warp; job < njobs; job += nwarps) {
+        const int row = r_first + job / 3;
+        const int seg = job % 3 - 1;
+        const int klo = row == r_first ? e_a - row * nxs : 0;
+        const int khi = row == r_last ? e_b - row * nxs : nxs;
+        int k0 = max(klo, seg * g.n[0] - sa0[0]);
+        int k1 = min(khi, (seg + 1) * g.n[0] - sa0[0]);
+        if (k0 >= k1) continue;
+        const int ry = row % slen[1], rz = row / slen[1];
+        const int rowcell =
+            (wrap_cell(sa0[2] + rz, g.n[2]) * g.n[1] + wrap_cell(sa0[1] + ry, g.n[1])) * g.n[0];
+        const int gstart = cs[rowcell + (sa0[0] + k0 - seg * g.n[0])];
+        const int dst = soff[row * nxs + k0] - base;
+        const int len = soff[row * nxs + k1] - soff[row * nxs + k0];
+        for (int m = lane; m < len; m += 32) P::stage(c, f, ex, gstart + m, sq, sd.cap, dst + m);
+      }
+    };
+
+    bool staged = false;  // single-group tiles stage once for all rounds of own particles
+    for (int ib = 0; ib < tile_n; ib += TPB) {
+      // ---- own particle ------------------------------------------------------
+      const int t = ib + tid;
+      const bool have = t < tile_n;
+      int p = 0, run = 0;
+      if (have) {
+        while (t >= own_off[run + 1]) ++run;
+        p = own_start[run] + (t - own_off[run]);
+      }
+      typename P::Own own;
+      typename P::Acc acc;
+      float ri[3] = {0.f, 0.f, 0.f};
+      bool act = false;
+      if (have) {
+        float4 q = f.pt[p];
+        ri[0] = q.x; ri[1] = q.y; ri[2] = q.z;
+        P::load_own(c, f, ex, p, q, own);
+        act = P::active(c, own);
+      }
+      P::init(acc);
+      // sparse policies (the wall sweep: wall particles only) skip tiles without work
+      const bool any_act = P::SPARSE ? (__syncthreads_or(have && act) != 0) : true;
+
+      // The particle's cell at the time of the last sort (the window of the search is laid
+      // around it): its run gives (y, z), the row's cell table the x cell.  Only search paths
+      // need it.
+      int ci[3] = {0, 0, 0};
+      if ((LM == LIST_BUILD || !nl_use) && have) {
+        const int ry = run % no[1], rz = run / no[1];
+        const int rowcell0 = ((c0[2] + rz) * g.n[1] + (c0[1] + ry)) * g.n[0] + c0[0];
+        int kx = 0;
+        while (kx + 1 < no[0] && __ldg(cs + rowcell0 + kx + 1) <= p) ++kx;
+        ci[0] = c0[0] + kx; ci[1] = c0[1] + ry; ci[2] = c0[2] + rz;
+      }
+
+      if (LM == LIST_BUILD) {
+        // ---------------- the search: skin list of every own particle -> HBM ----------------
+        if (!staged) {
+          stage_group(0, E, 0);
+          __syncthreads();
+          staged = true;
+        }
+        Walk<DIM> wk;
+        wk.init(g, sa0, ci, ri, have);
+        int cnt = 0, gk = 0;  // entries waiting in the column / already in HBM
+        unsigned short* col = list + tid;
+        unsigned short* grow = nl.sl + (size_t)p * nl.lmax;
         for (;;) {
-          bool fin = false;
-          // ---------------- phase 1: cheap reject, append survivors ----------------
-          for (;;) {
-            const int rem = jb - j;
-            if (!__any_sync(FULL_MASK, rem > 0)) {
-              it = it < 0 ? 0 : it + it_step;
-              if (it >= nit) {
-                fin = true;
-                break;
-              }
-              const int sgm = it & 1;
-              if (sgm == 0) {
-                if (++wy == g.W[1]) {
-                  wy = 0;
-                  ++wz;
-                }
-                const int ry = w0[1] + wy, rz = w0[2] + wz;
-                row = rz * slen[1] + ry;
-                inwin = act;
-                ys = ri[1] - (float)wrap_count(sa0[1] + ry + g.goff[1], g.ng[1]) * g.box[1];
-                zs = ri[2] - (float)wrap_count(sa0[2] + rz + g.goff[2], g.ng[2]) * g.box[2];
-              }
-              const int kk0 = sgm == 0 ? ka : ks, kk1 = sgm == 0 ? ks : kb;
-              j = jb = 0;
-              if (inwin && kk0 < kk1) {
-                const int ea = max(row * nxs + kk0, e_a), eb = min(row * nxs + kk1, e_b);
-                if (ea < eb) {
-                  j = soff[ea] - base;
-                  jb = soff[eb] - base;
-                }
-              }
-              xs = sgm == 0 ? xs0 : xs1;
-              continue;
-            }
-            const int want = rem > 0 ? min(rem, SWEEP_CHUNK) : 0;
-            if (__any_sync(FULL_MASK, want > sd.lcap - cnt)) break;  // flush first
-            const int e = j + want;
-            int lo = cnt * LS + tid;  // tid < LS: lo / LS is the entry count at any time
-            // four candidates per trip, loaded before the first append: the appends go to the
-            // same shared-memory window the candidates come from, so the compiler would
-            // otherwise keep every load behind the previous store (one LDS latency per candidate)
-            for (; j + 4 <= e; j += 4) {
-              const float4 p0 = sq[j], p1 = sq[j + 1], p2 = sq[j + 2], p3 = sq[j + 3];
-              float t0 = xs - p0.x, t1 = xs - p1.x, t2 = xs - p2.x, t3 = xs - p3.x;
-              float d0 = t0 * t0, d1 = t1 * t1, d2 = t2 * t2, d3 = t3 * t3;
-              t0 = ys - p0.y; t1 = ys - p1.y; t2 = ys - p2.y; t3 = ys - p3.y;
-              d0 += t0 * t0; d1 += t1 * t1; d2 += t2 * t2; d3 += t3 * t3;
-              if (DIM == 3) {
-                t0 = zs - p0.z; t1 = zs - p1.z; t2 = zs - p2.z; t3 = zs - p3.z;
-                d0 += t0 * t0; d1 += t1 * t1; d2 += t2 * t2; d3 += t3 * t3;
-              }
-              if (d0 < g.c2_hi) { list[lo] = (unsigned short)j; lo += LS; }
-              if (d1 < g.c2_hi) { list[lo] = (unsigned short)(j + 1); lo += LS; }
-              if (d2 < g.c2_hi) { list[lo] = (unsigned short)(j + 2); lo += LS; }
-              if (d3 < g.c2_hi) { list[lo] = (unsigned short)(j + 3); lo += LS; }
-            }
-#pragma unroll 1
-            for (; j < e; ++j) {
-              const float4 pj = sq[j];
-              const float dx = xs - pj.x, dy = ys - pj.y;
-              float d2 = dx * dx + dy * dy;
-              if (DIM == 3) {
-                const float dz = zs - pj.z;
-                d2 += dz * dz;
-              }
-              if (d2 < g.c2_hi) {
-                list[lo] = (unsigned short)j;
-                lo += LS;
-              }
-            }
-            cnt = lo / LS;
+          const bool fin = wk.run(g, sq, list, tid, sd.lcap, cnt, soff, 0, 0, E, nxs, slen[1], sa0,
+                                  ri, have, g.c2_hi);
+          // full chunks of 8 -> one STG.128 each; the remainder waits at the head of the column
+          int w = 0;
+          for (; cnt - w >= 8; w += 8) {
+            uint4 v;
+            v.x = (unsigned)col[(w + 0) * LS] | ((unsigned)col[(w + 1) * LS] << 16);
+            v.y = (unsigned)col[(w + 2) * LS] | ((unsigned)col[(w + 3) * LS] << 16);
+            v.z = (unsigned)col[(w + 4) * LS] | ((unsigned)col[(w + 5) * LS] << 16);
+            v.w = (unsigned)col[(w + 6) * LS] | ((unsigned)col[(w + 7) * LS] << 16);
+            if (gk + 8 <= nl.lmax) *reinterpret_cast<uint4*>(grow + gk) = v;
+            else s_bad = 1;
+            gk += 8;
           }
-          // ---------------- phase 2: real neighbours, exact arithmetic ----------------
-          int m = carry;
-          int k = carry;
-          if (LM == LIST_BUILD && P::PAIR2) {
-            // the list builder takes two survivors per trip (both loaded before the first
-            // in-place compaction store, which the compiler must otherwise order against
-            // every later load): two independent LDS -> displacement -> kernel chains
-#pragma unroll 1
-            for (; k + 1 < cnt; k += 2) {
-              const int j0 = list[k * LS + tid], j1 = list[(k + 1) * LS + tid];
-              const float4 p0 = sq[j0], p1 = sq[j1];
-              float r0[3], r1[3];
-              if (interior) {
-                pair_disp<DIM, true>(g, ri, p0, r0);
-                pair_disp<DIM, true>(g, ri, p1, r1);
-              } else {
-                pair_disp<DIM, false>(g, ri, p0, r0);
-                pair_disp<DIM, false>(g, ri, p1, r1);
-              }
-              const float s0 = sumsq<DIM>(r0), s1 = sumsq<DIM>(r1);
-              if (s0 < g.c2) {  // membership: see the note in the loop below
-                if (nl_build) {
-                  list[m * LS + tid] = (unsigned short)j0;  // m <= k: never an unread entry
-                  ++m;
-                }
-                P::pair(c, ex, own, acc, sq, sd.cap, j0, p0, r0, s0);
-              }
-              if (s1 < g.c2) {
-                if (nl_build) {
-                  list[m * LS + tid] = (unsigned short)j1;
-                  ++m;
-                }
-                P::pair(c, ex, own, acc, sq, sd.cap, j1, p1, r1, s1);
-              }
-            }
-          }
-#pragma unroll 1
-          for (; k < cnt; ++k) {
-            const int jn = list[k * LS + tid];
-            const float4 pj = sq[jn];
-            float dr[3];
-            if (interior) pair_disp<DIM, true>(g, ri, pj, dr);
-            else pair_disp<DIM, false>(g, ri, pj, dr);
-            const float d2 = sumsq<DIM>(dr);
-            // Membership.  The reference decides it on d(r_sender, r_receiver)^2 < cutoff^2
-            // (jax_md/partition.py:897).  For the materialiser (SENDER_VIEW) the thread's
-            // particle IS the sender, so d2 is that very number and the list is the
-            // reference's bit for bit.  In the physics sweeps d2 is the receiver view, which
-            // can differ in the last bit for a pair on the rounding edge of the cutoff -- where
-            // every kernel is max(0, .)-clamped to exactly zero (and ~(1e-7)^4 of its peak one
-            // ulp inside), so such a pair contributes nothing either way.
-            if (!(d2 < g.c2)) continue;
-            if (LM == LIST_BUILD && nl_build) {  // keep the survivor, compacted in place (m <= k)
-              list[m * LS + tid] = (unsigned short)jn;
-              ++m;
-            }
-            P::pair(c, ex, own, acc, sq, sd.cap, jn, pj, dr, d2);
-          }
-          if (LM == LIST_BUILD && nl_build) {
-            // survivors [0, m) of the column -> HBM in chunks of 8; the remainder waits
-            unsigned short* col = list + tid;
-            int w = 0;
-            for (; m - w >= 8; w += 8) {
-              uint4 v;
-              v.x = (unsigned)col[(w + 0) * LS] | ((unsigned)col[(w + 1) * LS] << 16);
-              v.y = (unsigned)col[(w + 2) * LS] | ((unsigned)col[(w + 3) * LS] << 16);
-              v.z = (unsigned)col[(w + 4) * LS] | ((unsigned)col[(w + 5) * LS] << 16);
-              v.w = (unsigned)col[(w + 6) * LS] | ((unsigned)col[(w + 7) * LS] << 16);
-              if (gk + 8 <= nl.lmax)
-                *reinterpret_cast<uint4*>(nl.list + (size_t)p * nl.lmax + gk) = v;
-              else
-                s_bad = 1;
-              gk += 8;
-            }
-            const int r = m - w;
-            if (w > 0)
-              for (int i = 0; i < r; ++i) col[i * LS] = col[(w + i) * LS];
-            carry = r;
-            cnt = r;
-          } else {
-            cnt = 0;
-          }
+          const int r = cnt - w;
+          if (w > 0)
+            for (int i = 0; i < r; ++i) col[i * LS] = col[(w + i) * LS];
+          cnt = r;
           if (fin) break;
         }
-        if (LM == LIST_BUILD && nl_build && have) {
-          // tail chunk (its unused slots are never read: cnt says how many are real)
-          if (carry > 0) {
-            const unsigned short* col = list + tid;
+        if (have) {
+          if (cnt > 0) {  // tail chunk (its unused slots are never read: scnt says how many are real)
             unsigned e8[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) e8[i] = i < carry ? (unsigned)col[i * LS] : 0u;
+            for (int i = 0; i < 8; ++i) e8[i] = i < cnt ? (unsigned)col[i * LS] : 0u;
             if (gk + 8 <= nl.lmax)
-              *reinterpret_cast<uint4*>(nl.list + (size_t)p * nl.lmax + gk) =
+              *reinterpret_cast<uint4*>(grow + gk) =
                   make_uint4(e8[0] | (e8[1] << 16), e8[2] | (e8[3] << 16), e8[4] | (e8[5] << 16),
                              e8[6] | (e8[7] << 16));
             else
               s_bad = 1;
           }
-          nl.cnt[p] = gk + carry;
+          nl.scnt[p] = gk + cnt;
         }
+        continue;
       }
-      e_a = e_b;
+
+      if (nl_use) {
+        // ---------------- list consumer (FILTER: exact test + exact list of the step) --------
+        if (any_act) {
+          if (!staged) {
+            if (ib > 0) __syncthreads();
+            stage_group(0, E, 0);
+            __syncthreads();
+            staged = true;
+          }
+          const int nn = (have && act) ? (LM == LIST_FILTER ? nl.scnt[p] : nl.xcnt[p]) : 0;
+          if (interior)
+            consume_list<DIM, P, true, LM == LIST_FILTER>(g, c, ex, nl, sq, sd.cap, p, nn, have && act,
+                                                          ri, own, acc);
+          else
+            consume_list<DIM, P, false, LM == LIST_FILTER>(g, c, ex, nl, sq, sd.cap, p, nn,
+                                                           have && act, ri, own, acc);
+        }
+        if (have) P::finish(c, f, ex, p, own, acc);
+        continue;
+      }
+
+      // ---------------- search + exact test + physics (no lists for this tile) ----------------
+      // Staging groups: maximal runs [e_a, e_b) of consecutive (row, cell) entries that fit the
+      // staging buffer (one group unless the stencil is unusually crowded).
+      Walk<DIM> wk;
+      int e_a = 0;
+      while (any_act && e_a < E) {
+        const int base = soff[e_a];
+        int e_b = E;
+        if (!single_group) {
+          int lo = e_a, hi = E;  // largest e_b with soff[e_b] - base <= cap (soff is monotone)
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (soff[mid] - base <= sd.cap) lo = mid;
+            else hi = mid - 1;
+          }
+          e_b = lo;
+        }
+        bool skip = false;
+        if (e_b == e_a) {  // one cell alone exceeds the staging buffer
+          if (tid == 0) atomicOr(err, SPHB200_ERR_STAGE_OVERFLOW);
+          e_b = e_a + 1;
+          skip = true;
+        }
+        if (!skip && !(single_group && staged)) {
+          if (ib > 0 || e_a > 0) __syncthreads();  // previous readers done
+          stage_group(e_a, e_b, base);
+          __syncthreads();
+          staged = single_group;
+        }
+        if (!skip) {
+          wk.init(g, sa0, ci, ri, have);
+          int cnt = 0;
+          for (;;) {
+            // phase 1: cheap reject; c2_fb is +inf while the cell table may be frozen (a particle
+            // that drifted across the periodic seam is not where the image shift expects it)
+            const bool fin = wk.run(g, sq, list, tid, sd.lcap, cnt, soff, base, e_a, e_b, nxs, slen[1],
+                                    sa0, ri, act, g.c2_fb);
+            // phase 2: real neighbours, exact arithmetic
+#pragma unroll 1
+            for (int k = 0; k < cnt; ++k) {
+              const int jn = list[k * LS + tid];
+              const float4 pj = sq[jn];
+              float dr[3];
+              if (interior) pair_disp<DIM, true>(g, ri, pj, dr);
+              else pair_disp<DIM, false>(g, ri, pj, dr);
+              const float d2 = sumsq<DIM>(dr);
+              // Membership.  The reference decides it on d(r_sender, r_receiver)^2 < cutoff^2
+              // (jax_md/partition.py:897).  For the materialiser the thread's particle IS the
+              // sender, so d2 is that very number and the list is the reference's bit for bit.
+              // In the physics sweeps d2 is the receiver view, which can differ in the last bit
+              // for a pair on the rounding edge of the cutoff -- where every kernel is
+              // max(0, .)-clamped to exactly zero (and ~(1e-7)^4 of its peak one ulp inside), so
+              // such a pair contributes nothing either way.
+              if (!(d2 < g.c2)) continue;
+              P::pair(c, ex, own, acc, sq, sd.cap, jn, pj, dr, d2);
+            }
+            cnt = 0;
+            if (fin) break;
+          }
+        }
+        e_a = e_b;
+      }
+      if (have) P::finish(c, f, ex, p, own, acc);
     }
-    if (have) P::finish(c, f, ex, p, own, acc);
-  }
-  if (LM == LIST_BUILD && nl.list != nullptr) {
-    __syncthreads();
-    if (tid == 0) nl.ok[tile_id] = s_bad ? 0 : 1;
+    if (LM == LIST_BUILD) {
+      __syncthreads();
+      if (tid == 0) nl.ok[tile_id] = s_bad ? 0 : 1;
+    }
   }
 }
 

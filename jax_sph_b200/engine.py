@@ -22,7 +22,7 @@ def make_config(
     is_bc_trick=False, is_rho_evol=False, is_rho_renorm=False, is_free_slip=False,
     is_heat_conduction=False, artificial_alpha=0.0, g_ext_spec=None, bc_table=None,
     cell_sub=None, tile=None, threads=0, list_cap=0, stage_cap=0, nl_cap=0, g_ext_array=False,
-    r_cutoff=0.0, wall_layer=None, diff_delta=0.1, diff_alpha=0.01,
+    r_cutoff=0.0, wall_layer=None, diff_delta=0.1, diff_alpha=0.01, skin=0.0,
 ):
     """Build a `sphb200_config` from the WCSPH constructor arguments
     (jax_sph/solver.py:616-637) plus the table forms of the case callables."""
@@ -111,6 +111,8 @@ def make_config(
     cfg.nl_cap = nl_cap
     cfg.r_cutoff = float(r_cutoff)
     cfg.diff_delta, cfg.diff_alpha = float(diff_delta), float(diff_alpha)
+    # neighbour-list skin / cutoff: 0 = automatic, < 0 = sort and search every step
+    cfg.skin = float(skin)
     # not part of the C struct: Engine / SlabEngine hand it to sphb200_engine_set_wall_layer
     cfg.wall_layer = wall_layer
     return cfg
@@ -385,6 +387,15 @@ class Engine:
         ms = (C.c_float * 8)()
         _lib.check(self.lib.sphb200_engine_last_times(self._h, C.byref(ms)))
         return dict(cells=ms[1], density=ms[2], wall=ms[3], force=ms[4], total=ms[5])
+
+    def counters(self):
+        """steps run, searches (cell sort + candidate walk) among them, list row length, skin /
+        cutoff, tiles, tiles swept without lists (sphb200_engine_counters)."""
+        out = (C.c_int64 * 8)()
+        _lib.check(self.lib.sphb200_engine_counters(self._h, C.byref(out), _stream_ptr()))
+        v = list(out)
+        return dict(steps=v[0], searches=v[1], list_rows=v[2], skin=v[3] * 1e-6, tiles=v[4],
+                    tiles_without_lists=v[5])
 
     def plan(self):
         out = (C.c_int32 * 16)()

@@ -142,6 +142,12 @@ LONG_CASES = {
     "ht2d": (["config=cases/ht.yaml", "case.dx=0.04"], dict(case="ht", dim=2, dx=0.04)),
     "cf2d": (["config=cases/cf.yaml", "case.dx=0.05", "solver.dt=null"],
              dict(case="cf", dim=2, dx=0.05)),
+    # 3D at sizes where the engine's interior tiles exist (24 cells per axis in the periodic box)
+    "tgv3d_tvf24": (["config=cases/tgv.yaml", "case.dim=3", "case.dx=0.2617993877991494",
+                     "case.viscosity=0.02", "solver.tvf=1.0", "case.r0_noise_factor=0.25"],
+                    dict(case="tgv", dim=3, dx=0.2617993877991494, tvf=1.0, viscosity=0.02)),
+    "ht3d": (["config=cases/ht.yaml", "case.dim=3", "case.dx=0.04"],
+             dict(case="ht", dim=3, dx=0.04)),
 }
 
 
