@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(256) k_scatter_src(int n, Slab sl, const int* 
 // (cell-sorted) frame.  One thread per arrival slot.
 struct ReorderOpt {
   int heat, has_nw, has_ge;
+  int keep_acc;  // carry dudt / dvdt along (a sort BETWEEN two steps: the next kick needs them)
 };
 
 template <int DIM>
@@ -275,7 +276,8 @@ __global__ void __launch_bounds__(256) k_reorder(int n, Grid g, Kick k, Slab sl,
   b.um[f] = make_float4(u[0], u[1], u[2], um.w);
   b.vv[f] = make_float4(v[0], v[1], v[2], vv.w);
   b.st[f] = a.st[p];
-  b.du[f] = make_float4(0.f, 0.f, 0.f, du.w);  // drhodt passes through when not evolved
+  b.du[f] = o.keep_acc ? du : make_float4(0.f, 0.f, 0.f, du.w);  // drhodt passes through when not evolved
+  if (o.keep_acc) b.dv[f] = a.dv[p];
   b.id[f] = a.id[p];
   if (o.heat) b.kc[f] = a.kc[p];
   if (o.has_nw) b.nw[f] = a.nw[p];
@@ -345,6 +347,7 @@ __global__ void __launch_bounds__(256) k_copyback(int n, ReorderOpt o, Frame a, 
     a.vv[p] = b.vv[p];
     a.st[p] = b.st[p];
     a.du[p] = b.du[p];
+    if (o.keep_acc) a.dv[p] = b.dv[p];
     a.id[p] = b.id[p];
     if (o.heat) a.kc[p] = b.kc[p];
     if (o.has_nw) a.nw[p] = b.nw[p];

@@ -307,6 +307,142 @@ __device__ __forceinline__ float fsqrt(float a) {
 }
 #endif
 
+// ---------------------------------------------------------------------------
+// Packed float32 pairs: sm_100 executes add / mul / fma on two float32 lanes of a 64-bit register
+// pair in one instruction (PTX add.rn.f32x2 ..., SASS FADD2 / FMUL2 / FFMA2), each lane rounded
+// exactly like the scalar operation.  The list consumers keep two pairs in flight per thread
+// (sweep.cuh) and evaluate them in the two halves: half the issue slots of the FP32 work.
+// Packing and unpacking are register-pair moves (free).  ptxas contracts mul.f32x2 + add.f32x2
+// into FFMA2 even with .rn: where the reference's value needs the unfused product (sumsq2) the
+// adds are scalar __fadd_rn.
+struct F2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ F2 f2(float a, float b) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ F2 f2(float a) { return f2(a, a); }
+__device__ __forceinline__ float lo(F2 a) {
+  float x, y;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+  (void)y;
+  return x;
+}
+__device__ __forceinline__ float hi(F2 a) {
+  float x, y;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v));
+  (void)x;
+  return y;
+}
+__device__ __forceinline__ F2 add2(F2 a, F2 b) {
+  F2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 sub2(F2 a, F2 b) {
+  F2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) {
+  F2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+  F2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+// acc += a * b / acc += a with the accumulator tied to the output register pair (a loop-carried
+// accumulator written by a fresh asm output costs two moves per trip otherwise)
+__device__ __forceinline__ void fma2_into(F2& acc, F2 a, F2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc.v) : "l"(a.v), "l"(b.v));
+}
+__device__ __forceinline__ void add2_into(F2& acc, F2 a) {
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc.v) : "l"(a.v));
+}
+__device__ __forceinline__ F2 neg2(F2 a) { return f2(-lo(a), -hi(a)); }
+__device__ __forceinline__ F2 max2(F2 a, float b) { return f2(fmaxf(lo(a), b), fmaxf(hi(a), b)); }
+__device__ __forceinline__ F2 sel2(bool v0, bool v1, F2 a) { return f2(v0 ? lo(a) : 0.0f, v1 ? hi(a) : 0.0f); }
+
+// disp1_nowrap of two neighbours at once (same value per half as the scalar form)
+__device__ __forceinline__ F2 disp2_nowrap(float a, F2 b, float half) {
+  return sub2(add2(sub2(f2(a), b), f2(half)), f2(half));
+}
+// sumsq of two displacements: products packed, the two adds scalar and unfused (space.py:184-192)
+template <int DIM>
+__device__ __forceinline__ F2 sumsq2(const F2 (&d)[3]) {
+  const F2 x = mul2(d[0], d[0]), y = mul2(d[1], d[1]);
+  float s0 = __fadd_rn(lo(x), lo(y)), s1 = __fadd_rn(hi(x), hi(y));
+  if (DIM == 3) {
+    const F2 z = mul2(d[2], d[2]);
+    s0 = __fadd_rn(s0, lo(z));
+    s1 = __fadd_rn(s1, hi(z));
+  }
+  return f2(s0, s1);
+}
+
+#ifdef SPHB200_PRECISE
+__device__ __forceinline__ F2 frcp2(F2 a) { return f2(1.0f / lo(a), 1.0f / hi(a)); }
+__device__ __forceinline__ F2 fsqrt2(F2 a) { return f2(__fsqrt_rn(lo(a)), __fsqrt_rn(hi(a))); }
+#else
+__device__ __forceinline__ F2 frcp2(F2 a) { return f2(frcp(lo(a)), frcp(hi(a))); }
+// fsqrt of both halves: the rsqrt seeds are scalar MUFU ops, the Newton step is packed
+__device__ __forceinline__ F2 fsqrt2(F2 a) {
+  a = max2(a, 1e-30f);
+  float r0, r1;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(lo(a)));
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(hi(a)));
+  const F2 r = f2(r0, r1);
+  const F2 s = mul2(a, r);
+  const F2 e = fma2(mul2(s, f2(-1.0f)), s, a);
+  return fma2(e, mul2(r, f2(0.5f)), s);
+}
+#endif
+
+// kernel_w / kernel_gw of two distances (same arithmetic per half as the scalar forms)
+template <int KERN>
+__device__ __forceinline__ F2 kernel_w2(const Consts& c, F2 r) {
+  if (KERN == SPHB200_KERNEL_QSK) {
+    // k - r / h with one rounding, as the compiler contracts the scalar form
+    const F2 no = f2(-c.ooh);
+    const F2 q1 = max2(fma2(r, no, f2(1.0f)), 0.0f), q2 = max2(fma2(r, no, f2(2.0f)), 0.0f),
+             q3 = max2(fma2(r, no, f2(3.0f)), 0.0f);
+    const F2 a1 = mul2(q1, q1), a2 = mul2(q2, q2), a3 = mul2(q3, q3);
+    const F2 p1 = mul2(mul2(a1, a1), q1), p2 = mul2(mul2(a2, a2), q2), p3 = mul2(mul2(a3, a3), q3);
+    return mul2(f2(c.sigma), fma2(f2(15.0f), p1, fma2(f2(-6.0f), p2, p3)));
+  } else if (KERN == SPHB200_KERNEL_WC2K) {
+    const F2 q = mul2(r, f2(c.ooh));
+    const F2 q1 = max2(fma2(q, f2(-0.5f), f2(1.0f)), 0.0f);
+    const F2 a = mul2(q1, q1);
+    return mul2(f2(c.sigma), mul2(mul2(a, a), fma2(q, f2(2.0f), f2(1.0f))));
+  } else {
+    return f2(kernel_w<KERN>(c, lo(r)), kernel_w<KERN>(c, hi(r)));
+  }
+}
+
+template <int KERN>
+__device__ __forceinline__ F2 kernel_gw2(const Consts& c, F2 r) {
+  if (KERN == SPHB200_KERNEL_QSK) {
+    // k - r / h with one rounding, as the compiler contracts the scalar form
+    const F2 no = f2(-c.ooh);
+    const F2 q1 = max2(fma2(r, no, f2(1.0f)), 0.0f), q2 = max2(fma2(r, no, f2(2.0f)), 0.0f),
+             q3 = max2(fma2(r, no, f2(3.0f)), 0.0f);
+    const F2 a1 = mul2(q1, q1), a2 = mul2(q2, q2), a3 = mul2(q3, q3);
+    const F2 poly = fma2(f2(-75.0f), mul2(a1, a1), fma2(f2(30.0f), mul2(a2, a2), mul2(f2(-5.0f), mul2(a3, a3))));
+    return mul2(f2(c.sigma_ooh), poly);
+  } else if (KERN == SPHB200_KERNEL_WC2K) {
+    const F2 q = mul2(r, f2(c.ooh));
+    const F2 q1 = max2(fma2(q, f2(-0.5f), f2(1.0f)), 0.0f);
+    return mul2(f2(c.sigma_ooh), mul2(mul2(q, f2(-5.0f)), mul2(mul2(q1, q1), q1)));
+  } else {
+    return f2(kernel_gw<KERN>(c, lo(r)), kernel_gw<KERN>(c, hi(r)));
+  }
+}
+
 // eos.py:33-38 / :53-57
 __device__ __forceinline__ float eos_p(const Consts& c, float rho) {
   if (c.eos == SPHB200_EOS_TAIT) {

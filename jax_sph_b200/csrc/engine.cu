@@ -358,10 +358,10 @@ void feature_flags(const sphb200_config& c, bool& kc, bool& nw, bool& ut, bool& 
 // neighbours of a particle in a uniform fluid (+8), a multiple of 8; 0 = lists off.
 int plan_lmax(const sphb200_config& c, double skin_frac) {
   if (c.nl_cap < 0) return 0;
-  if (c.nl_cap > 0) return (c.nl_cap + 7) / 8 * 8;
+  if (c.nl_cap > 0) return (c.nl_cap + 15) / 16 * 16;
   const double q = kernel_cutoff(c) * (1.0 + skin_frac) / c.dx;
   const double expect = c.dim == 2 ? M_PI * q * q : 4.0 / 3.0 * M_PI * q * q * q;
-  int lmax = ((int)(1.3 * expect) + 8 + 7) / 8 * 8;
+  int lmax = ((int)(1.3 * expect) + 8 + 15) / 16 * 16;  // rows are blocks of 16 entries
   if (lmax > 1024) lmax = 0;  // very wide kernels: not worth the memory
   return lmax;
 }
@@ -590,7 +590,8 @@ int hash_cells(sphb200_engine* e, const Kick& k, cudaStream_t st, const int* gat
 // nw_fn of the integrator on the current frame (integrator.py:33-34: after the drift)
 int wall_normals(sphb200_engine* e, cudaStream_t st);
 
-int sort_cells(sphb200_engine* e, const Kick& k, cudaStream_t st, const int* gate = nullptr) {
+int sort_cells(sphb200_engine* e, const Kick& k, cudaStream_t st, const int* gate = nullptr,
+               bool keep_acc = false) {
   // slab mode: sources are own + immigrants; the new own count is only known on the device
   const int bound = e->slab_on ? e->sgeom.own_cap + 2 * e->slab.mig_cap : e->n;
   const int nb = stream_blocks(e, bound);
@@ -602,7 +603,7 @@ int sort_cells(sphb200_engine* e, const Kick& k, cudaStream_t st, const int* gat
   k_scan_bsum<<<1, 1024, 0, st>>>(sb, e->bsum, gate);
   k_scan_final<<<sb, SCAN_TPB, 0, st>>>(c, e->slab.base, e->count, e->bsum, e->start, e->maxocc, gate);
   k_scatter_src<<<nb, 256, 0, st>>>(bound, e->slab, e->key, e->rnk, e->start, e->src, gate);
-  ReorderOpt o{e->has_kc ? 1 : 0, e->has_nw ? 1 : 0, e->has_ge ? 1 : 0};
+  ReorderOpt o{e->has_kc ? 1 : 0, e->has_nw ? 1 : 0, e->has_ge ? 1 : 0, keep_acc ? 1 : 0};
   if (e->dim == 2)
     k_reorder<2><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, o, A, B, e->key, e->start, e->src, gate);
   else
@@ -677,7 +678,7 @@ int begin_step(sphb200_engine* e, const Kick& k, cudaStream_t st) {
 int sort_now(sphb200_engine* e, cudaStream_t st) {
   const Kick off{0.f, 0.f, 0};
   int rc = hash_cells(e, off, st);
-  if (!rc) rc = sort_cells(e, off, st);
+  if (!rc) rc = sort_cells(e, off, st, nullptr, true);  // the next kick needs dudt / dvdt
   e->force_rebuild = true;
   e->maybe_drifted = false;
   return rc;
@@ -1171,7 +1172,7 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->planW = plan_sweep(e, 4, lc);
   e->planC = plan_sweep(e, 4, lc);
   e->planN = plan_sweep(e, 2, e->lcap);
-  e->planB = plan_sweep(e, 1, e->lcap);
+  e->planB = plan_sweep(e, 1, e->lcap < 32 ? 32 : e->lcap);  // the search flushes blocks of 16
   e->needs_zero = true;  // control words are zeroed on the first upload's stream
   return SPHB200_OK;
 }

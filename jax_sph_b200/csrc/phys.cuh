@@ -34,8 +34,11 @@ struct PhysNone {
   static constexpr int MINB = 2;
   static constexpr bool SENDER_VIEW = false;
   static constexpr bool SPARSE = false;
+  static constexpr bool HAS_PAIR2 = false;
   struct Own {};
   struct Acc {};
+  template <class F>
+  __device__ static void each_acc(Acc&, F) {}
   __device__ static void stage(const Consts&, const Frame& f, const Extra&, int gp, float4* sq,
                                int, int d) {
     sq[d] = f.pt[gp];
@@ -72,6 +75,28 @@ struct PhysDensity {
     float swf, sT;  // RIE wall helpers
     float su[3];
   };
+  template <class F>
+  __device__ static void each_acc(Acc& a, F f) {
+    f(a.s);
+    if (XTRA) {
+      f(a.swf); f(a.sT); f(a.su[0]); f(a.su[1]); f(a.su[2]);
+    }
+  }
+  // plain summation: the packed pair body of the list consumers (sweep.cuh, Pair2)
+  static constexpr bool HAS_PAIR2 = MODE == DENS_SUM;
+  struct Acc2 {
+    F2 s;
+  };
+  __device__ static void init2(Acc2& a) { a.s = f2(0.0f); }
+  __device__ static void pair2(const Consts& c, const Extra&, const Own&, Acc2& a, const float4*,
+                               int, int, int, float4, float4, const F2 (&)[3], F2 d2, bool v0,
+                               bool v1) {
+    add2_into(a.s, sel2(v0, v1, kernel_w2<KERN>(c, fsqrt2(d2))));
+  }
+  __device__ static void fold(const Acc2& a2, Acc& a) {
+    init(a);
+    a.s = lo(a2.s) + hi(a2.s);
+  }
   __device__ static void stage(const Consts& c, const Frame& f, const Extra& ex, int gp,
                                float4* sq, int cap, int d) {
     sq[d] = f.pt[gp];
@@ -223,6 +248,12 @@ struct PhysDelta {
   struct Acc {
     float m[9];  // STEP 0: M;  STEP 1: G (0..2), H (3..5);  STEP 2: diff (0), cont (1)
   };
+  static constexpr bool HAS_PAIR2 = false;
+  template <class F>
+  __device__ static void each_acc(Acc& a, F f) {
+#pragma unroll
+    for (int k = 0; k < (STEP == 0 ? 9 : (STEP == 1 ? 6 : 2)); ++k) f(a.m[k]);
+  }
   __host__ __device__ static int nq() { return STEP == 0 ? 1 : (STEP == 1 ? (DIM == 3 ? 4 : 2) : 3); }
   __device__ static void stage(const Consts&, const Frame& f, const Extra&, int gp, float4* sq,
                                int cap, int d) {
@@ -394,6 +425,11 @@ struct PhysRenorm {
   struct Acc {
     float num, den;
   };
+  static constexpr bool HAS_PAIR2 = false;
+  template <class F>
+  __device__ static void each_acc(Acc& a, F f) {
+    f(a.num); f(a.den);
+  }
   __device__ static void stage(const Consts&, const Frame& f, const Extra&, int gp, float4* sq,
                                int cap, int d) {
     sq[d] = f.pt[gp];
@@ -434,6 +470,15 @@ struct PhysWall {
     float sw, sp, sT;
     float su[3], sv[3], srr[3];
   };
+  static constexpr bool HAS_PAIR2 = false;
+  template <class F>
+  __device__ static void each_acc(Acc& a, F f) {
+    f(a.sw); f(a.sp); f(a.sT);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      f(a.su[k]); f(a.sv[k]); f(a.srr[k]);
+    }
+  }
   __device__ static void stage(const Consts&, const Frame& f, const Extra&, int gp, float4* sq,
                                int cap, int d) {
     sq[d] = f.pt[gp];
@@ -543,6 +588,78 @@ struct PhysForce {
     float dT;
   };
   static constexpr bool COMPACT = SOLVER == SPHB200_SOLVER_SPH && FEAT != FORCE_GENERIC;
+  template <class F>
+  __device__ static void each_acc(Acc& a, F f) {
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+      f(a.a[k]); f(a.tv[k]);
+      if (FEAT == FORCE_GENERIC) f(a.av[k]);
+    }
+    if (FEAT == FORCE_GENERIC) f(a.dT);
+  }
+  // The two headline variants: packed pair body of the list consumers (sweep.cuh, Pair2) -- the
+  // arithmetic of pair() below for two neighbours in the two halves of packed registers.  A lane
+  // without a pair (v false) computes on staged slot 0 with its coefficient c forced to zero.
+  static constexpr bool HAS_PAIR2 = COMPACT;
+  struct Acc2 {
+    F2 a[3], tv[3];
+  };
+  __device__ static void init2(Acc2& a) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a.a[k] = a.tv[k] = f2(0.0f);
+  }
+  __device__ static void pair2(const Consts& c, const Extra&, const Own& o, Acc2& a,
+                               const float4* sq, int cap, int j0, int j1, float4 p0, float4 p1,
+                               const F2 (&dr)[3], F2 d2, bool v0, bool v1) {
+    const float4 qa = sq[cap + j0], qb = sq[cap + j1];
+    const F2 uj[3] = {f2(qa.x, qb.x), f2(qa.y, qb.y), f2(qa.z, qb.z)};
+    const F2 rho_j = f2(p0.w, p1.w), p_j = f2(qa.w, qb.w);
+    F2 eta_j, V2_j, hdv[3];
+    if (FEAT == FORCE_TVF) {
+      const float4 ra = sq[2 * cap + j0], rb = sq[2 * cap + j1];
+      hdv[0] = f2(ra.x, rb.x); hdv[1] = f2(ra.y, rb.y); hdv[2] = f2(ra.z, rb.z);
+      V2_j = f2(ra.w, rb.w);
+      const float* ec = reinterpret_cast<const float*>(sq + 3 * cap);
+      eta_j = f2(ec[j0], ec[j1]);
+    } else {
+      const float2* ev = reinterpret_cast<const float2*>(sq + 2 * cap);
+      const float2 ea = ev[j0], eb = ev[j1];
+      eta_j = f2(ea.x, eb.x);
+      V2_j = f2(ea.y, eb.y);
+    }
+    const F2 dist = fsqrt2(d2);
+    const F2 gw = kernel_gw2<KERN>(c, dist);
+    const F2 id = frcp2(add2(dist, f2(c.eps)));
+    const F2 wv = mul2(add2(f2(o.V2), V2_j), f2(o.inv_m));                  // :205 / :247
+    const F2 cc = sel2(v0, v1, mul2(mul2(wv, gw), id));                     // :206 / :248
+    const F2 eta_ij = mul2(mul2(f2(o.eta2), eta_j),
+                           frcp2(add2(add2(f2(o.eta), eta_j), f2(c.eps))));  // :243
+    const F2 p_ij = mul2(fma2(rho_j, f2(o.p), mul2(f2(o.rho), p_j)),
+                         frcp2(add2(f2(o.rho), rho_j)));                     // :244
+    const F2 ncp = mul2(cc, neg2(p_ij)), ce = mul2(cc, eta_ij);
+    F2 cj = f2(0.0f);
+    if (FEAT == FORCE_TVF) {  // c (A_j r)_k = cj u_j[k]   (:250-251)
+      F2 d = mul2(hdv[0], dr[0]);
+      d = fma2(hdv[1], dr[1], d);
+      if (DIM == 3) d = fma2(hdv[2], dr[2], d);
+      cj = mul2(cc, d);
+    }
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+      fma2_into(a.tv[k], cc, dr[k]);                      // sum_j c r  (:199-213, :912-921)
+      fma2_into(a.a[k], ncp, dr[k]);                      // -c p_ij r
+      fma2_into(a.a[k], ce, sub2(f2(o.u[k]), uj[k]));     // c eta_ij u_ij
+      if (FEAT == FORCE_TVF) fma2_into(a.a[k], cj, uj[k]);
+    }
+  }
+  __device__ static void fold(const Acc2& a2, Acc& a) {
+    init(a);
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+      a.a[k] = lo(a2.a[k]) + hi(a2.a[k]);
+      a.tv[k] = lo(a2.tv[k]) + hi(a2.tv[k]);
+    }
+  }
   static constexpr int CQ = FEAT == FORCE_TVF ? 3 : 2;  // quads of the compact record
   // bytes staged per particle (engine.cu sizes the staging buffer with it)
   __host__ __device__ static int stage_bytes(int nq_generic) {
@@ -816,6 +933,9 @@ struct PhysNeighbors {
   struct Acc {
     int n;
   };
+  static constexpr bool HAS_PAIR2 = false;
+  template <class F>
+  __device__ static void each_acc(Acc&, F) {}
   __device__ static void stage(const Consts&, const Frame& f, const Extra&, int gp, float4* sq,
                                int cap, int d) {
     sq[d] = f.pt[gp];

@@ -61,9 +61,35 @@ def max_err(a, b):
     return float(np.abs(a - b).max()) if a.size else 0.0
 
 
-def assert_close(key, got, ref, setup, factor=1.0, what=""):
+def periodic_err(a, b, box):
+    """max |a - b| of positions up to periodic images: a particle a rounding error away from the
+    seam is wrapped to the other side of the box by one implementation and not by the other."""
+    d = np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)
+    box = np.asarray(box, dtype=np.float64).reshape(-1)[: d.shape[-1]]
+    d -= box * np.round(d / box)
+    return float(np.abs(d).max()) if d.size else 0.0
+
+
+AMPLIFIED = 1e-3
+
+
+def assert_close(key, got, ref, setup, factor=1.0, what="", ref64=None):
+    """`ref64` (the float64 oracle, optional): particles on which the reference's OWN float32 and
+    float64 results disagree are ill-conditioned -- e.g. the Shepard averages sum(w f) / (sum(w)
+    + EPS) of the outermost wall layer, whose only fluid neighbours sit ON the cutoff (sum(w) ~
+    EPS): a last-bit change of sum(w) moves the quotient by O(1) between the reference's two
+    precisions.  There, and only there, the bound is widened by AMPLIFIED x |ref32 - ref64| of
+    that very particle (a summation-order change is a ~1e-7 relative perturbation of the sums,
+    the precision change an O(1) one)."""
     tol = factor * tolerance(key, ref, setup)
-    err = max_err(got, ref)
+    if ref64 is not None and key != "r":
+        a, b = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+        allow = tol + AMPLIFIED * np.abs(b - np.asarray(ref64, dtype=np.float64))
+        bad = np.abs(a - b) > allow
+        assert not bad.any(), (f"{what} {key}: {int(bad.sum())} entries off, worst abs err "
+                               f"{np.abs(a - b)[bad].max():.3e} > tol {tol:.3e}")
+        return float(np.abs(a - b).max()), tol
+    err = periodic_err(got, ref, setup.box_size) if key == "r" else max_err(got, ref)
     assert err <= tol, f"{what} {key}: max abs err {err:.3e} > tol {tol:.3e} (max|ref| {np.abs(ref).max():.3e})"
     return err, tol
 

@@ -39,7 +39,10 @@ def _run_pair(kw, nranks, nsteps, **tuning):
 
     setup = cases.make_case(dtype=np.float32, **kw)
     n = len(setup.state["r"])
-    cfg = config_from_setup(setup, **tuning)
+    # skin off: the single engine sorts every step like the slab engines do, so that the two runs
+    # differ by the decomposition only (the frozen-sort path is compared with the oracle in
+    # test_gpu_parity3d.py / test_gpu_reference.py)
+    cfg = config_from_setup(setup, skin=-1.0, **tuning)
     single = Engine(cfg, n)
     single.upload(setup.state)
     single.step(setup.dt, nsteps)
@@ -105,7 +108,7 @@ def test_slab_forward_only_is_bitwise_single_engine():
     setup.state["r"] = np.mod(setup.state["r"] + rng.uniform(-0.2, 0.2, setup.state["r"].shape)
                               * setup.dx, setup.box_size).astype(np.float32)
     n = len(setup.state["r"])
-    single = Engine(config_from_setup(setup), n)
+    single = Engine(config_from_setup(setup, skin=-1.0), n)  # the cell grid of the slab engines
     single.upload(setup.state)
     single.step(0.0, 1, integrate=False, bc=False)
     ref = single.download(host=True)
