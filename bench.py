@@ -276,7 +276,8 @@ def config_of(args, meta):
                        c_ref=meta["c_ref"], p_ref=meta["p_ref"],
                        cell_sub=[args.sub] * dim if args.sub else None,
                        threads=args.threads, list_cap=args.list_cap,
-                       tile=[args.tile_x, 0, 0] if args.tile_x else None, skin=args.skin,
+                       tile=[args.tile_x, args.tile_y, args.tile_z] if args.tile_x else None,
+                       skin=args.skin,
                        **meta.get("cfg_kwargs", {}))
 
 
@@ -641,6 +642,8 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--list-cap", type=int, default=0)
     ap.add_argument("--tile-x", type=int, default=0)
+    ap.add_argument("--tile-y", type=int, default=0)
+    ap.add_argument("--tile-z", type=int, default=0)
     ap.add_argument("--skin", type=float, default=0.0,
                     help="neighbour-list skin / cutoff (0 = engine default, < 0 = search every step)")
     args = ap.parse_args()

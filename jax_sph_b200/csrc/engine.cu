@@ -358,10 +358,10 @@ void feature_flags(const sphb200_config& c, bool& kc, bool& nw, bool& ut, bool& 
 // neighbours of a particle in a uniform fluid (+8), a multiple of 8; 0 = lists off.
 int plan_lmax(const sphb200_config& c, double skin_frac) {
   if (c.nl_cap < 0) return 0;
-  if (c.nl_cap > 0) return (c.nl_cap + 15) / 16 * 16;
+  if (c.nl_cap > 0) return (c.nl_cap + 7) / 8 * 8;
   const double q = kernel_cutoff(c) * (1.0 + skin_frac) / c.dx;
   const double expect = c.dim == 2 ? M_PI * q * q : 4.0 / 3.0 * M_PI * q * q * q;
-  int lmax = ((int)(1.3 * expect) + 8 + 15) / 16 * 16;  // rows are blocks of 16 entries
+  int lmax = ((int)(1.3 * expect) + 8 + 7) / 8 * 8;
   if (lmax > 1024) lmax = 0;  // very wide kernels: not worth the memory
   return lmax;
 }
@@ -1172,7 +1172,7 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->planW = plan_sweep(e, 4, lc);
   e->planC = plan_sweep(e, 4, lc);
   e->planN = plan_sweep(e, 2, e->lcap);
-  e->planB = plan_sweep(e, 1, e->lcap < 32 ? 32 : e->lcap);  // the search flushes blocks of 16
+  e->planB = plan_sweep(e, 1, e->lcap);
   e->needs_zero = true;  // control words are zeroed on the first upload's stream
   return SPHB200_OK;
 }

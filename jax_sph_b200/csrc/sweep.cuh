@@ -62,7 +62,7 @@ struct NList {
   unsigned short* sl;    // [n][lmax]
   int* scnt;             // [n]
   unsigned char* ok;     // [tiles]
-  int lmax;              // multiple of 16
+  int lmax;              // multiple of 8
   int min_cap;           // smallest staging capacity among the step's sweeps
   int* nbuilds;          // device counter: searches run so far (LIST_BUILD adds one per launch)
 };
@@ -97,28 +97,9 @@ __device__ __forceinline__ void pair_disp(const Grid& g, const float (&ri)[3], c
 }
 
 // ---------------------------------------------------------------------------
-// List consumers work with LPP lanes per particle ("quarter warp per particle"): the lanes of a
-// group take consecutive entries of the particle's row, so that
-//   * the 16-byte gathers of one LDS.128 phase (a quarter warp) go to consecutive -- mostly
-//     conflict-free -- staged slots instead of eight random ones (the sweeps were bound by
-//     shared-memory wavefronts, 58 % of them bank conflicts, when every lane walked its own row),
-//   * the row is read with one coalesced 16-byte segment per group and trip,
-//   * FILTER compacts the survivors of a trip with a ballot: no per-lane shift registers.
-// Each lane keeps TWO pairs in flight (entries k and k + LPP) and evaluates them in the two
-// halves of packed float32 registers (FADD2 / FMUL2 / FFMA2, common.cuh).  The partial sums of a
-// group are combined with shuffles; lane 0 of the group runs the per-particle epilogue.
-constexpr int LPP = 8;
-
-// Physical position of logical entry e of a row: blocks of 2 * LPP entries, entry q of a block
-// at 2 * (q mod LPP) + q / LPP (the two entries of a lane share a 32-bit word).
-__host__ __device__ __forceinline__ int list_slot(int e) {
-  const int q = e & (2 * LPP - 1);
-  return (e - q) + 2 * (q & (LPP - 1)) + (q >> 3);
-}
-static_assert(LPP == 8, "list_slot and the builder's flush assume blocks of 16 entries");
-
-// Physics policies that provide a packed pair body (pair2 on Acc2) opt in with HAS_PAIR2; the
-// others get two predicated scalar pair() calls.
+// Physics policies that provide a packed pair body (pair2 on Acc2: two neighbours in the two
+// halves of packed float32 registers, common.cuh) opt in with HAS_PAIR2; the others get two
+// predicated scalar pair() calls.
 template <class P, bool = P::HAS_PAIR2>
 struct Pair2 {
   using Acc2 = typename P::Acc;
@@ -151,101 +132,76 @@ struct Pair2<P, true> {
   __device__ static __forceinline__ void fold(const Acc2& a2, typename P::Acc& a) { P::fold(a2, a); }
 };
 
-// One tile whose lists exist: every own particle of the tile, LPP lanes each.  FILTER: the row is
-// the skin list; the exact membership test of the reference (d^2 < cutoff^2 on the float32
-// displacement of space.py:170-181) runs on every entry and the survivors become the exact list
-// of the step.
+// List consumer: every thread steps through the row of its own particle, one 32-bit word = two
+// entries per trip, evaluated in the two halves of packed float32 registers (FADD2 / FMUL2 /
+// FFMA2): half the issue slots of the displacement, distance and kernel arithmetic, and two
+// independent LDS -> displacement -> rsqrt -> kernel -> pair-term chains in flight per thread.
+// FILTER: the row is the skin list; the exact membership test of the reference (d^2 < cutoff^2
+// on the float32 displacement of space.py:170-181) runs on every entry and the survivors are
+// appended to the exact list of the step through a 64-bit shift register (one STG.64 per four
+// survivors, branch-free).
+// (Eight lanes per particle with ballot compaction were tried instead: 38 % fewer bank
+// conflicts, but the per-particle prologue / reduction / epilogue and the exposed latency of the
+// short rows cost more than they save: profiles/r02_sweeps_qw_tgv3d_128_raw.txt.)
 template <int DIM, class P, bool INTERIOR, bool FILTER>
-__device__ __forceinline__ void consume_tile(const Grid& g, const Consts& c, const Frame& f,
-                                             const Extra& ex, const NList& nl, const float4* sq,
-                                             int cap, int tile_n, int nruns, const int* own_off,
-                                             const int* own_start, bool any_act) {
+__device__ __forceinline__ void consume_list(const Grid& g, const Consts& c, const Extra& ex,
+                                             const NList& nl, const float4* sq, int cap, int p,
+                                             int nn, bool have, const float (&ri)[3],
+                                             const typename P::Own& own, typename P::Acc& acc) {
   using P2 = Pair2<P>;
-  constexpr int PPW = 32 / LPP;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int sub = lane & (LPP - 1), grp = lane / LPP, gshift = lane & ~(LPP - 1);
-  const unsigned lt = (1u << sub) - 1u, gm = (1u << LPP) - 1u;
-  (void)nruns;
-  for (int t0 = warp * PPW; t0 < tile_n; t0 += nwarps * PPW) {
-    const int t = t0 + grp;
-    const bool have = t < tile_n;
-    int p = 0;
-    if (have) {
-      int run = 0;
-      while (t >= own_off[run + 1]) ++run;
-      p = own_start[run] + (t - own_off[run]);
-    }
-    typename P::Own own;
-    typename P::Acc acc;
-    float ri[3] = {0.f, 0.f, 0.f};
-    bool act = false;
-    if (have) {
-      const float4 q = f.pt[p];
-      ri[0] = q.x; ri[1] = q.y; ri[2] = q.z;
-      P::load_own(c, f, ex, p, q, own);
-      act = P::active(c, own);
-    }
-    // The row is stored in blocks of 16 entries, interleaved so that lane `sub` of the group
-    // finds its two entries of a block (logical positions sub and sub + LPP) in ONE 32-bit word
-    // at word `sub` of the block: one coalesced 32-byte segment per group and trip.
-    const size_t roff = (size_t)p * nl.lmax;
-    const unsigned* rp = reinterpret_cast<const unsigned*>((FILTER ? nl.sl : nl.xl) + roff) + sub;
-    unsigned short* xrow = nl.xl + roff;
-    const int nn = (have && act && any_act) ? (FILTER ? nl.scnt[p] : nl.xcnt[p]) : 0;
-    const int ntrip = (__reduce_max_sync(FULL_MASK, nn) + 2 * LPP - 1) / (2 * LPP);
-    const int mytrips = (nn + 2 * LPP - 1) / (2 * LPP);
-    typename P2::Acc2 acc2;
-    P2::init(acc2);
-    int m = 0;  // FILTER: survivors written so far (the same in all lanes of the group)
-    // the words of the next two trips are in flight while this trip's pairs are evaluated
-    unsigned wa = mytrips > 0 ? __ldg(rp) : 0u, wb = mytrips > 1 ? __ldg(rp + LPP) : 0u;
-    int k = sub;  // logical position of this lane's first entry in the current block
+  const size_t roff = (size_t)p * nl.lmax;
+  const uint4* lrow = reinterpret_cast<const uint4*>((FILTER ? nl.sl : nl.xl) + roff);
+  unsigned long long* xp = reinterpret_cast<unsigned long long*>(nl.xl + roff);
+  unsigned long long xw = 0ull;
+  int m = 0;
+  typename P2::Acc2 acc2;
+  P2::init(acc2);
+  uint4 cur = make_uint4(0u, 0u, 0u, 0u), nxt = cur;
+  if (nn > 0) nxt = __ldg(lrow);
 #pragma unroll 1
-    for (int tr = 0; tr < ntrip; ++tr) {
-      const unsigned w = wa;
-      wa = wb;
-      wb = tr + 2 < mytrips ? __ldg(rp + 2 * LPP) : 0u;
-      rp += LPP;
-      bool v0 = k < nn, v1 = k + LPP < nn;
-      k += 2 * LPP;
-      const int j0 = v0 ? (int)(w & 0xffffu) : 0, j1 = v1 ? (int)(w >> 16) : 0;
-      const float4 p0 = sq[j0], p1 = sq[j1];
-      F2 dr[3];
-      if (INTERIOR) {
-        dr[0] = disp2_nowrap(ri[0], f2(p0.x, p1.x), g.half[0]);
-        dr[1] = disp2_nowrap(ri[1], f2(p0.y, p1.y), g.half[1]);
-        dr[2] = (DIM == 3) ? disp2_nowrap(ri[2], f2(p0.z, p1.z), g.half[2]) : f2(0.0f);
-      } else {
-        dr[0] = f2(disp1(ri[0], p0.x, g.half[0], g.box[0]), disp1(ri[0], p1.x, g.half[0], g.box[0]));
-        dr[1] = f2(disp1(ri[1], p0.y, g.half[1], g.box[1]), disp1(ri[1], p1.y, g.half[1], g.box[1]));
-        dr[2] = (DIM == 3) ? f2(disp1(ri[2], p0.z, g.half[2], g.box[2]),
-                                disp1(ri[2], p1.z, g.half[2], g.box[2]))
-                           : f2(0.0f);
-      }
-      const F2 d2 = sumsq2<DIM>(dr);
-      if (FILTER) {
-        v0 = v0 && lo(d2) < g.c2;
-        v1 = v1 && hi(d2) < g.c2;
-        const unsigned b0 = (__ballot_sync(FULL_MASK, v0) >> gshift) & gm;
-        const unsigned b1 = (__ballot_sync(FULL_MASK, v1) >> gshift) & gm;
-        const int e0 = m + __popc(b0 & lt);
-        m += __popc(b0);
-        const int e1 = m + __popc(b1 & lt);
-        m += __popc(b1);
-        if (v0) xrow[list_slot(e0)] = (unsigned short)j0;
-        if (v1) xrow[list_slot(e1)] = (unsigned short)j1;
-      }
-      P2::pair2(c, ex, own, acc2, sq, cap, j0, j1, p0, p1, dr, d2, v0, v1);
+  for (int k = 0; k < nn; k += 2) {
+    if ((k & 7) == 0) {
+      cur = nxt;
+      ++lrow;
+      if (k + 8 < nn) nxt = __ldg(lrow);
     }
-    P2::fold(acc2, acc);
-    P::each_acc(acc, [](float& x) {
-#pragma unroll
-      for (int o = 1; o < LPP; o <<= 1) x += __shfl_xor_sync(FULL_MASK, x, o);
-    });
-    if (have && sub == 0) {
-      if (FILTER && act) nl.xcnt[p] = m;
-      P::finish(c, f, ex, p, own, acc);
+    const unsigned w = cur.x;
+    cur.x = cur.y; cur.y = cur.z; cur.z = cur.w;
+    bool v0 = true, v1 = k + 1 < nn;
+    const int j0 = (int)(w & 0xffffu), j1 = v1 ? (int)(w >> 16) : 0;
+    const float4 p0 = sq[j0], p1 = sq[j1];
+    F2 dr[3];
+    if (INTERIOR) {
+      dr[0] = disp2_nowrap(ri[0], f2(p0.x, p1.x), g.half[0]);
+      dr[1] = disp2_nowrap(ri[1], f2(p0.y, p1.y), g.half[1]);
+      dr[2] = (DIM == 3) ? disp2_nowrap(ri[2], f2(p0.z, p1.z), g.half[2]) : f2(0.0f);
+    } else {
+      dr[0] = f2(disp1(ri[0], p0.x, g.half[0], g.box[0]), disp1(ri[0], p1.x, g.half[0], g.box[0]));
+      dr[1] = f2(disp1(ri[1], p0.y, g.half[1], g.box[1]), disp1(ri[1], p1.y, g.half[1], g.box[1]));
+      dr[2] = (DIM == 3) ? f2(disp1(ri[2], p0.z, g.half[2], g.box[2]),
+                              disp1(ri[2], p1.z, g.half[2], g.box[2]))
+                         : f2(0.0f);
     }
+    const F2 d2 = sumsq2<DIM>(dr);
+    if (FILTER) {
+      v0 = lo(d2) < g.c2;
+      v1 = v1 && hi(d2) < g.c2;
+      // survivors -> the exact list: shift in, count, store every fourth (no divergent blocks)
+      const unsigned long long x0 = (xw >> 16) | ((unsigned long long)j0 << 48);
+      xw = v0 ? x0 : xw;
+      m += v0 ? 1 : 0;
+      if (v0 && (m & 3) == 0) *xp++ = xw;
+      const unsigned long long x1 = (xw >> 16) | ((unsigned long long)j1 << 48);
+      xw = v1 ? x1 : xw;
+      m += v1 ? 1 : 0;
+      if (v1 && (m & 3) == 0) *xp++ = xw;
+    }
+    P2::pair2(c, ex, own, acc2, sq, cap, j0, j1, p0, p1, dr, d2, v0, v1);
+  }
+  P2::fold(acc2, acc);
+  if (FILTER && have) {
+    if (m & 3) *xp = xw >> (16 * (4 - (m & 3)));  // the last, partial group of four
+    nl.xcnt[p] = m;
   }
 }
 
@@ -488,36 +444,6 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
       }
     };
 
-    if constexpr (LM == LIST_CONSUME || LM == LIST_FILTER) {
-      if (nl_use) {
-        // ---------------- list consumer (FILTER: exact test + exact list of the step) --------
-        bool any_act = true;
-        if (P::SPARSE) {  // most particles inactive (the wall sweep): skip tiles without work
-          bool mine = false;
-          for (int t = tid; t < tile_n; t += TPB) {
-            int run = 0;
-            while (t >= own_off[run + 1]) ++run;
-            const int p = own_start[run] + (t - own_off[run]);
-            typename P::Own o;
-            P::load_own(c, f, ex, p, f.pt[p], o);
-            mine = mine || P::active(c, o);
-          }
-          any_act = __syncthreads_or(mine) != 0;
-        }
-        if (any_act) {
-          stage_group(0, E, 0);
-          __syncthreads();
-        }
-        if (interior)
-          consume_tile<DIM, P, true, LM == LIST_FILTER>(g, c, f, ex, nl, sq, sd.cap, tile_n, nruns,
-                                                        own_off, own_start, any_act);
-        else
-          consume_tile<DIM, P, false, LM == LIST_FILTER>(g, c, f, ex, nl, sq, sd.cap, tile_n, nruns,
-                                                         own_off, own_start, any_act);
-        continue;
-      }
-    }
-
     bool staged = false;  // single-group tiles stage once for all rounds of own particles
     for (int ib = 0; ib < tile_n; ib += TPB) {
       // ---- own particle ------------------------------------------------------
@@ -546,12 +472,35 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
       // around it): its run gives (y, z), the row's cell table the x cell.  Only search paths
       // need it.
       int ci[3] = {0, 0, 0};
-      if (have) {
+      if ((LM == LIST_BUILD || !nl_use) && have) {
         const int ry = run % no[1], rz = run / no[1];
         const int rowcell0 = ((c0[2] + rz) * g.n[1] + (c0[1] + ry)) * g.n[0] + c0[0];
         int kx = 0;
         while (kx + 1 < no[0] && __ldg(cs + rowcell0 + kx + 1) <= p) ++kx;
         ci[0] = c0[0] + kx; ci[1] = c0[1] + ry; ci[2] = c0[2] + rz;
+      }
+
+      if constexpr (LM == LIST_CONSUME || LM == LIST_FILTER) {
+        if (nl_use) {
+          // ---------------- list consumer (FILTER: exact test + exact list of the step) ------
+          if (any_act) {
+            if (!staged) {
+              if (ib > 0) __syncthreads();
+              stage_group(0, E, 0);
+              __syncthreads();
+              staged = true;
+            }
+            const int nn = (have && act) ? (LM == LIST_FILTER ? nl.scnt[p] : nl.xcnt[p]) : 0;
+            if (interior)
+              consume_list<DIM, P, true, LM == LIST_FILTER>(g, c, ex, nl, sq, sd.cap, p, nn,
+                                                            have && act, ri, own, acc);
+            else
+              consume_list<DIM, P, false, LM == LIST_FILTER>(g, c, ex, nl, sq, sd.cap, p, nn,
+                                                             have && act, ri, own, acc);
+          }
+          if (have) P::finish(c, f, ex, p, own, acc);
+          continue;
+        }
       }
 
       if (LM == LIST_BUILD) {
@@ -569,26 +518,17 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
         for (;;) {
           const bool fin = wk.run(g, sq, list, tid, sd.lcap, cnt, soff, 0, 0, E, nxs, slen[1], sa0,
                                   ri, have, g.c2_hi);
-          // full blocks of 16 -> two STG.128 each, in the interleaved order the consumers read
-          // (list_slot); the remainder waits at the head of the column
+          // full chunks of 8 -> one STG.128 each; the remainder waits at the head of the column
           int w = 0;
-          for (; cnt - w >= 16; w += 16) {
-            uint4 v0, v1;
-            v0.x = (unsigned)col[(w + 0) * LS] | ((unsigned)col[(w + 8) * LS] << 16);
-            v0.y = (unsigned)col[(w + 1) * LS] | ((unsigned)col[(w + 9) * LS] << 16);
-            v0.z = (unsigned)col[(w + 2) * LS] | ((unsigned)col[(w + 10) * LS] << 16);
-            v0.w = (unsigned)col[(w + 3) * LS] | ((unsigned)col[(w + 11) * LS] << 16);
-            v1.x = (unsigned)col[(w + 4) * LS] | ((unsigned)col[(w + 12) * LS] << 16);
-            v1.y = (unsigned)col[(w + 5) * LS] | ((unsigned)col[(w + 13) * LS] << 16);
-            v1.z = (unsigned)col[(w + 6) * LS] | ((unsigned)col[(w + 14) * LS] << 16);
-            v1.w = (unsigned)col[(w + 7) * LS] | ((unsigned)col[(w + 15) * LS] << 16);
-            if (gk + 16 <= nl.lmax) {
-              *reinterpret_cast<uint4*>(grow + gk) = v0;
-              *reinterpret_cast<uint4*>(grow + gk + 8) = v1;
-            } else {
-              s_bad = 1;
-            }
-            gk += 16;
+          for (; cnt - w >= 8; w += 8) {
+            uint4 v;
+            v.x = (unsigned)col[(w + 0) * LS] | ((unsigned)col[(w + 1) * LS] << 16);
+            v.y = (unsigned)col[(w + 2) * LS] | ((unsigned)col[(w + 3) * LS] << 16);
+            v.z = (unsigned)col[(w + 4) * LS] | ((unsigned)col[(w + 5) * LS] << 16);
+            v.w = (unsigned)col[(w + 6) * LS] | ((unsigned)col[(w + 7) * LS] << 16);
+            if (gk + 8 <= nl.lmax) *reinterpret_cast<uint4*>(grow + gk) = v;
+            else s_bad = 1;
+            gk += 8;
           }
           const int r = cnt - w;
           if (w > 0)
@@ -597,20 +537,16 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
           if (fin) break;
         }
         if (have) {
-          if (cnt > 0) {  // tail block (its unused slots are never used: scnt says how many are real)
-            unsigned e16[16];
+          if (cnt > 0) {  // tail chunk (its unused slots are never read: scnt says how many are real)
+            unsigned e8[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) e16[i] = i < cnt ? (unsigned)col[i * LS] : 0u;
-            if (gk + 16 <= nl.lmax) {
+            for (int i = 0; i < 8; ++i) e8[i] = i < cnt ? (unsigned)col[i * LS] : 0u;
+            if (gk + 8 <= nl.lmax)
               *reinterpret_cast<uint4*>(grow + gk) =
-                  make_uint4(e16[0] | (e16[8] << 16), e16[1] | (e16[9] << 16),
-                             e16[2] | (e16[10] << 16), e16[3] | (e16[11] << 16));
-              *reinterpret_cast<uint4*>(grow + gk + 8) =
-                  make_uint4(e16[4] | (e16[12] << 16), e16[5] | (e16[13] << 16),
-                             e16[6] | (e16[14] << 16), e16[7] | (e16[15] << 16));
-            } else {
+                  make_uint4(e8[0] | (e8[1] << 16), e8[2] | (e8[3] << 16), e8[4] | (e8[5] << 16),
+                             e8[6] | (e8[7] << 16));
+            else
               s_bad = 1;
-            }
           }
           nl.scnt[p] = gk + cnt;
         }
