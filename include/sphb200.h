@@ -271,13 +271,20 @@ int sphb200_fp32_peak(int packed, double *tflops, double *ms, void *stream);
  *     for (phase = 0;; ++phase) {
  *       sphb200_slab_run(e, phase, dt, flags, send_lo, send_hi, recv_lo, recv_hi, stream, &nbytes);
  *       if (nbytes == 0) break;                       // step complete
- *       send send_lo[0:nbytes] to rank-1, send_hi[0:nbytes] to rank+1 (periodic ring),
- *       receive recv_lo[0:nbytes] from rank-1, recv_hi[0:nbytes] from rank+1, stream-ordered
+ *       if (nbytes < 0)                               // -4: agree on the re-sort decision
+ *         max-reduce the int32 at send_lo[0:4] over ALL ranks, in place, stream-ordered
+ *       else
+ *         send send_lo[0:nbytes] to rank-1, send_hi[0:nbytes] to rank+1 (periodic ring),
+ *         receive recv_lo[0:nbytes] from rank-1, recv_hi[0:nbytes] from rank+1, stream-ordered
  *     }
  *
- * phase 0 integrates + hashes and emits the emigrants, phase 1 takes the immigrants, sorts and
- * emits the boundary layers, every later phase takes a halo message and runs the sweeps up to
- * the next one whose results the neighbours need (density -> rho, p; wall BC -> u, v, rho, p).
+ * phase 0 integrates in place and publishes whether a particle of this rank has travelled more
+ * than half the skin of the neighbour lists since the last sort; phase 1 (on the steps where
+ * some rank said so) hashes and emits the emigrants, phase 2 takes the immigrants, sorts, and
+ * emits the boundary layers (every step: positions and state of the halo particles change, the
+ * particle sets only when the ranks sort); every later phase takes a halo message and runs the
+ * sweeps up to the next one whose results the neighbours need (density -> rho, p; wall BC -> u,
+ * v, rho, p).
  * Message sizes depend only on the capacities, counts travel in the message headers and stay
  * on the device: nothing synchronises with the host.  The four buffers are device memory of
  * at least outi[9] bytes each (sphb200_slab_info), owned by the caller (the transport:

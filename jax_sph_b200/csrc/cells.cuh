@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256) k_reorder(int n, Grid g, Kick k, Slab sl,
 // cutoff now was inside cutoff + skin at the last search and is in the skin list.
 // The flag words alternate between steps: this launch also clears the next step's word.
 template <int DIM>
-__global__ void __launch_bounds__(256) k_drift(int n, Grid g, Kick k, Frame f,
+__global__ void __launch_bounds__(256) k_drift(int n, Grid g, Kick k, Slab sl, Frame f,
                                                float* __restrict__ path, int* flag_cur,
                                                int* flag_next, int force, float limit,
                                                unsigned* __restrict__ err) {
@@ -304,7 +304,9 @@ __global__ void __launch_bounds__(256) k_drift(int n, Grid g, Kick k, Frame f,
     if (force) atomicOr(flag_cur, 1);
   }
   bool over = false;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+  const int n_own = sl.dn ? sl.dn[DN_OWN] : n;  // slab engines: own particles only
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_own; t += gridDim.x * blockDim.x) {
+    const int p = sl.base + t;
     const float4 a = f.pt[p], b = f.um[p], w = f.vv[p];
     float r[3] = {a.x, a.y, a.z}, u[3] = {b.x, b.y, b.z}, v[3] = {w.x, w.y, w.z};
     integrate_one<DIM>(k, g, r, u, v, f.du[p], f.dv[p]);
@@ -335,13 +337,22 @@ __global__ void k_gate(int* flag_cur, int* flag_next, int force) {
   if (force) *flag_cur = 1;
 }
 
+// Slab engines agree on the re-sort decision: every rank publishes its flag in a message word,
+// the transport max-reduces the word over the ranks, every rank takes the result.
+__global__ void k_flag_out(const int* flag, int* word) { *word = *flag; }
+__global__ void k_flag_in(const int* word, int* flag) { *flag = *word != 0 ? 1 : 0; }
+
 // After a re-sort (k_reorder: frame a -> frame b) the sorted particles go back to frame a, so
 // that the host always launches on the same frame whether or not the device decided to re-sort.
-__global__ void __launch_bounds__(256) k_copyback(int n, ReorderOpt o, Frame a, Frame b,
-                                                  float* __restrict__ path,
-                                                  const int* __restrict__ gate) {
+__global__ void __launch_bounds__(256) k_copyback(int n, Slab sl, int ncells, ReorderOpt o,
+                                                  Frame a, Frame b, float* __restrict__ path,
+                                                  const int* __restrict__ start,
+                                                  const int* __restrict__ gate, int* nsorts) {
   if (gate != nullptr && *gate == 0) return;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nsorts) atomicAdd(nsorts, 1);
+  const int bound = sl.dn ? start[ncells] - sl.base : n;  // as k_reorder: the new own count
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < bound; t += gridDim.x * blockDim.x) {
+    const int p = sl.base + t;
     a.pt[p] = b.pt[p];
     a.um[p] = b.um[p];
     a.vv[p] = b.vv[p];

@@ -184,9 +184,9 @@ int max_stage_bytes(const sphb200_config& c) {
 }
 
 // Cell grid, stencil and tiling (host).  nranks > 1: the local view of rank `rank`.
-// skin / cutoff of an engine for this config (slab engines: 0, they search every step)
-double plan_skin(const sphb200_config& c, bool slab) {
-  if (slab || c.nl_cap < 0 || c.skin < 0.f) return 0.0;
+// skin / cutoff of an engine for this config
+double plan_skin(const sphb200_config& c) {
+  if (c.nl_cap < 0 || c.skin < 0.f) return 0.0;
   if (c.skin > 0.f) return c.skin > 1.f ? 1.0 : (double)c.skin;
   return 0.10;  // tuned on B200 (profiles/r02_skin_*.txt)
 }
@@ -610,17 +610,15 @@ int sort_cells(sphb200_engine* e, const Kick& k, cudaStream_t st, const int* gat
     k_reorder<3><<<nb, 256, 0, st>>>(bound, e->grid, k, e->slab, o, A, B, e->key, e->start, e->src, gate);
   e->launches += 5;
   CK(cudaGetLastError());
-  if (e->inplace) {  // the sorted particles go back to the frame the host keeps launching on
-    k_copyback<<<nb, 256, 0, st>>>(e->n, o, A, B, e->path, gate);
+  {  // the sorted particles go back to the frame the host keeps launching on
+    k_copyback<<<nb, 256, 0, st>>>(e->n, e->slab, e->grid.ncells, o, A, B, e->path, e->start, gate,
+                                   e->ctl + 2);
     e->launches++;
     CK(cudaGetLastError());
-  } else {
-    e->cur ^= 1;
   }
+  (void)k;
   e->cells_valid = true;
-  if (e->inplace) return SPHB200_OK;  // begin_step runs nw_fn itself, on every integrating step
-  if (k.on) return wall_normals(e, st);
-  return SPHB200_OK;
+  return SPHB200_OK;  // the callers run nw_fn themselves, on every integrating step
 }
 
 int wall_normals(sphb200_engine* e, cudaStream_t st) {
@@ -644,31 +642,38 @@ int wall_normals(sphb200_engine* e, cudaStream_t st) {
 // First half of one step of a resident engine: kick + drift + wrap in place and, when the
 // device decides so (k_drift) or the host knows the lists are stale, the cell sort.  The
 // search itself is the first launch of forward_stage(0), gated on the same flag word.
-int begin_step(sphb200_engine* e, const Kick& k, cudaStream_t st) {
+// kick + drift + wrap in place and this engine's own re-sort decision -> the step's flag word
+int drift_step(sphb200_engine* e, const Kick& k, cudaStream_t st) {
   int* fc = e->ctl + (e->step_no & 1ull);
   int* fn = e->ctl + ((e->step_no + 1ull) & 1ull);
   const int force = (e->force_rebuild || !e->cells_valid) ? 1 : 0;
   Frame& F = e->fr[e->cur];
   if (k.on) {
-    const int nb = stream_blocks(e, e->n);
+    const int nb = stream_blocks(e, e->slab_on ? e->sgeom.own_cap : e->n);
     if (e->dim == 2)
-      k_drift<2><<<nb, 256, 0, st>>>(e->n, e->grid, k, F, e->path, fc, fn, force, e->path_limit, e->err);
+      k_drift<2><<<nb, 256, 0, st>>>(e->n, e->grid, k, e->slab, F, e->path, fc, fn, force, e->path_limit, e->err);
     else
-      k_drift<3><<<nb, 256, 0, st>>>(e->n, e->grid, k, F, e->path, fc, fn, force, e->path_limit, e->err);
+      k_drift<3><<<nb, 256, 0, st>>>(e->n, e->grid, k, e->slab, F, e->path, fc, fn, force, e->path_limit, e->err);
     e->maybe_drifted = true;
   } else {
     k_gate<<<1, 1, 0, st>>>(fc, fn, force);
   }
   e->launches++;
   CK(cudaGetLastError());
-  const Kick off{0.f, 0.f, 0};
-  int rc = hash_cells(e, off, st, fc);
-  if (!rc) rc = sort_cells(e, off, st, fc);
-  if (rc) return rc;
-  if (k.on) rc = wall_normals(e, st);
   e->gate_cur = fc;
   e->force_rebuild = false;
   e->step_no++;
+  return SPHB200_OK;
+}
+
+int begin_step(sphb200_engine* e, const Kick& k, cudaStream_t st) {
+  int rc = drift_step(e, k, st);
+  if (rc) return rc;
+  const Kick off{0.f, 0.f, 0};
+  rc = hash_cells(e, off, st, e->gate_cur);
+  if (!rc) rc = sort_cells(e, off, st, e->gate_cur);
+  if (rc) return rc;
+  if (k.on) rc = wall_normals(e, st);
   return rc;
 }
 
@@ -724,7 +729,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
   const SweepPlan planD = !evol ? (dens_extras ? e->planW : e->planA) : (!rie ? e->planR : e->planW);
   // neighbour lists (sweep.cuh): skin list from the last search, exact list written by the
   // density sweep of this step and consumed by every later sweep
-  NList nl{e->pl_list, e->pl_cnt, e->sl_list, e->sl_cnt, e->pl_ok, e->pl_lmax, 0, e->ctl + 2};
+  NList nl{e->pl_list, e->pl_cnt, e->sl_list, e->sl_cnt, e->pl_ok, e->pl_lmax, 0, nullptr};
   const SweepPlan planG = plan_sweep(e, e->dim == 3 ? 4 : 2, 24);  // PhysDelta<1>
   {
     int mc = planD.cap < planF.cap ? planD.cap : planF.cap;
@@ -1078,8 +1083,8 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   if (e->tpb > 512) e->tpb = 512;
   e->lcap = cfg->list_cap > 0 ? cfg->list_cap : 48;  // tuned on B200 (profiles/, tune logs)
   if (e->lcap < SWEEP_CHUNK) e->lcap = SWEEP_CHUNK;
-  e->inplace = !e->slab_on;
-  e->skin_frac = plan_skin(*cfg, e->slab_on);
+  e->inplace = true;
+  e->skin_frac = plan_skin(*cfg);
   plan_grid(*cfg, e->grid, e->tpb, e->slab_rank, e->slab_nranks, e->skin_frac);
   // half the skin, minus a margin for the rounding of positions and of the accumulated path
   e->path_limit = e->skin_frac > 0.0 ? (float)(0.5 * e->skin_frac * kernel_cutoff(*cfg) * (1.0 - 1e-3)) : -1.0f;
@@ -1265,7 +1270,7 @@ int sphb200_engine_bytes(const sphb200_config* cfg, int64_t n, size_t* bytes) {
   if (rc) return rc;
   if (!bytes) return SPHB200_EINVAL;
   Grid g;
-  const double skin = plan_skin(*cfg, false);
+  const double skin = plan_skin(*cfg);
   plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : DEFAULT_TPB, 0, 1, skin);
   Layout L;
   plan_layout(*cfg, n, g, skin, L);
@@ -1914,7 +1919,7 @@ static int slab_spec(const sphb200_config* cfg, int rank, int nranks, int64_t ow
                      int64_t halo_cap, int64_t mig_cap, SlabSpec* sp) {
   if (nranks < 2 || rank < 0 || rank >= nranks) return SPHB200_EINVAL;
   Grid g;
-  plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : DEFAULT_TPB);
+  plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : DEFAULT_TPB, 0, 1, plan_skin(*cfg));
   const int ax = cfg->dim - 1;
   if (g.exact_all && g.n[ax] < 2 * g.S[ax] + 1) return SPHB200_EINVAL;
   for (int r = 0; r < nranks; ++r) {
@@ -1948,9 +1953,9 @@ int sphb200_slab_create(const sphb200_config* cfg, int rank, int nranks, int64_t
   rc = slab_spec(cfg, rank, nranks, own_cap, halo_cap, mig_cap, &sp);
   if (rc) return rc;
   Grid g;
-  plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : DEFAULT_TPB, rank, nranks);
+  plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : DEFAULT_TPB, rank, nranks, plan_skin(*cfg));
   Layout L;
-  plan_layout(*cfg, slab_slots(sp), g, 0.0, L);
+  plan_layout(*cfg, slab_slots(sp), g, plan_skin(*cfg), L);
   void* ws = nullptr;
   if (cudaMalloc(&ws, L.total) != cudaSuccess) return SPHB200_ENOMEM;
   sphb200_engine* e = new (std::nothrow) sphb200_engine();
@@ -2077,7 +2082,10 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
   const SlabGeom& sg = e->sgeom;
   const int hblocks = 4 * 148;
   *xbytes = 0;
+  const Kick off{0.f, 0.f, 0};
   if (phase == 0) {
+    // kick + drift + wrap in place; this rank's re-sort decision goes into a message word that
+    // the transport max-reduces over the ranks (xbytes = -4): all ranks sort, or none does
     Kick k;
     k.dt = (float)dt;
     k.c2 = (float)(e->cfg.tvf * 0.5) * (float)dt;
@@ -2088,15 +2096,26 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
     sl.mig_lo = (char*)send_lo;
     sl.mig_hi = (char*)send_hi;
     if (e->profile) cudaEventRecord(e->ev[0], st);
-    int rc = hash_cells(e, k, st);
+    int rc = drift_step(e, k, st);
+    if (rc) return rc;
+    k_flag_out<<<1, 1, 0, st>>>(e->gate_cur, (int*)send_lo);
+    e->launches++;
+    CK(cudaGetLastError());
+    *xbytes = -4;
+    return SPHB200_OK;
+  }
+  int* fc = e->ctl + ((e->step_no - 1ull) & 1ull);  // the flag word of this step (drift_step)
+  if (phase == 1) {
+    k_flag_in<<<1, 1, 0, st>>>((const int*)send_lo, fc);
+    int rc = hash_cells(e, off, st, fc);  // emigrants -> send buffers (on the steps that sort)
     if (rc) return rc;
     k_mig_header<<<1, 1, 0, st>>>(sl);
-    e->launches++;
+    e->launches += 2;
     CK(cudaGetLastError());
     *xbytes = (int64_t)mig_bytes(sl.mig_cap);
     return SPHB200_OK;
   }
-  if (phase == 1) {
+  if (phase == 2) {
     const dim3 gi((sl.mig_cap + 255) / 256, 2);
     Frame& A = e->fr[e->cur];
     if (e->dim == 2)
@@ -2105,9 +2124,13 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
     else
       k_immigrate<3><<<gi, 256, 0, st>>>(e->grid, sl, sg, A, (const char*)recv_lo,
                                          (const char*)recv_hi, e->key, e->rnk, e->count, e->err);
-    int rc = sort_cells(e, e->slab_kick, st);
+    int rc = sort_cells(e, off, st, fc);
     if (rc) return rc;
-    k_slab_after_sort<<<1, 1, 0, st>>>(e->grid, sl, sg, e->start, e->err);
+    k_slab_after_sort<<<1, 1, 0, st>>>(e->grid, sl, sg, e->start, e->err, fc);
+    if (e->slab_kick.on) {
+      rc = wall_normals(e, st);
+      if (rc) return rc;
+    }
     const int mask = slab_mask_a(e);
     k_halo_pack<<<dim3(hblocks, 2), 256, 0, st>>>(sl, sg, e->fr[e->cur], mask, e->start,
                                                   (char*)send_lo, (char*)send_hi, e->err);
@@ -2120,7 +2143,7 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
     *xbytes = (int64_t)halo_bytes(mask, sg.halo_cap, sg.ncl);
     return prelaunch_interior(e, next_effective_stage(e, 0), st);
   }
-  // phase >= 2: take in the halo message of the previous phase, then sweep until the next
+  // phase >= 3: take in the halo message of the previous phase, then sweep until the next
   // stage whose results the neighbours need
   if (e->slab_pending_mask) {
     const int mask = e->slab_pending_mask;

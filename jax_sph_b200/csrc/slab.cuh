@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(256) k_immigrate(Grid g, Slab sl, SlabGeom sg,
 
 // after the sort: the scan total is the new own count; reset the per-step counters
 __global__ void k_slab_after_sort(Grid g, Slab sl, SlabGeom sg, const int* __restrict__ start,
-                                  unsigned* __restrict__ err) {
+                                  unsigned* __restrict__ err, const int* __restrict__ gate) {
+  if (gate != nullptr && *gate == 0) return;
   const int n_new = start[g.ncells] - sl.base;
   if (n_new > sg.own_cap) atomicOr(err, SPHB200_ERR_SLAB_OVERFLOW);
   sl.dn[DN_OWN] = n_new;

@@ -64,7 +64,7 @@ struct NList {
   unsigned char* ok;     // [tiles]
   int lmax;              // multiple of 8
   int min_cap;           // smallest staging capacity among the step's sweeps
-  int* nbuilds;          // device counter: searches run so far (LIST_BUILD adds one per launch)
+  int* nbuilds;          // optional device counter, one per LIST_BUILD launch
 };
 
 enum { LIST_NONE = 0, LIST_BUILD = 1, LIST_CONSUME = 2, LIST_FILTER = 3 };

@@ -3,7 +3,10 @@
 The reference drives a single device (jax_sph/simulate.py:110-134); for the large
 3D cases `north_star` asks for the periodic box to be cut into slabs across the
 GPUs of one node, with a halo exchange every step and particle migration at every
-neighbour rebuild (= every step, simulate.py:75-86 passes no dr_threshold).
+neighbour rebuild.  (The reference rebuilds every step, simulate.py:75-86 passes no
+dr_threshold; the engines re-sort and search only when a particle of ANY rank has moved
+half the skin of the neighbour lists -- one 4-byte max-reduction per step decides --
+and test every listed pair against the cutoff on every step, csrc/sweep.cuh.)
 
 Device side: include/sphb200.h `sphb200_slab_*`, csrc/slab.cuh.  This module is
 the transport and the host-side bookkeeping:
@@ -217,6 +220,14 @@ class SlabEngine:
             C.c_void_p(b["recv_hi"].data_ptr()), _stream_ptr(), C.byref(nb)))
         return int(nb.value)
 
+    def _agree(self):
+        """The ranks' re-sort decisions (one int32 word each, written by phase 0 into the head of
+        the send buffer) -> their maximum, in place: all ranks sort and search, or none does."""
+        import torch.distributed as dist
+
+        word = self._buf["send_lo"][:4].view(_torch().int32)
+        dist.all_reduce(word, op=dist.ReduceOp.MAX, group=self.group)
+
     def step(self, dt: float, nsteps: int = 1, integrate: bool = True, bc: bool = True):
         flags = step_flags(integrate, bc)
         for _ in range(nsteps):
@@ -225,7 +236,10 @@ class SlabEngine:
                 nb = self.run_phase(phase, dt, flags)
                 if nb == 0:
                     break
-                self._exchange(nb, phase)
+                if nb < 0:
+                    self._agree()
+                else:
+                    self._exchange(nb, phase)
                 phase += 1
 
     def live_fields(self):
@@ -323,6 +337,14 @@ class SlabEngine:
     def launches(self) -> int:
         return int(self.lib.sphb200_engine_launches(self._h))
 
+    def counters(self):
+        """steps, searches among them, ... of this rank (Engine.counters)."""
+        out = (C.c_int64 * 8)()
+        _lib.check(self.lib.sphb200_engine_counters(self._h, C.byref(out), _stream_ptr()))
+        v = list(out)
+        return dict(steps=v[0], searches=v[1], list_rows=v[2], skin=v[3] * 1e-6, tiles=v[4],
+                    tiles_without_lists=v[5])
+
     def profile(self, on: bool = True):
         _lib.check(self.lib.sphb200_engine_profile(self._h, int(on)))
 
@@ -350,6 +372,14 @@ def step_local_ring(engines, dt: float, nsteps: int = 1, integrate: bool = True,
             nb = nbs[0]
             if nb == 0:
                 break
+            if nb < 0:  # the re-sort decision: maximum over the ranks (SlabEngine._agree)
+                torch = _torch()
+                words = [e._buf["send_lo"][:4].view(torch.int32) for e in engines]
+                top = torch.stack(words).max(dim=0).values
+                for w in words:
+                    w.copy_(top)
+                phase += 1
+                continue
             for r, e in enumerate(engines):
                 lo, hi = ring_neighbours(r, n)
                 e._buf["recv_lo"][:nb].copy_(engines[lo]._buf["send_hi"][:nb])

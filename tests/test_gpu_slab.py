@@ -39,10 +39,9 @@ def _run_pair(kw, nranks, nsteps, **tuning):
 
     setup = cases.make_case(dtype=np.float32, **kw)
     n = len(setup.state["r"])
-    # skin off: the single engine sorts every step like the slab engines do, so that the two runs
-    # differ by the decomposition only (the frozen-sort path is compared with the oracle in
-    # test_gpu_parity3d.py / test_gpu_reference.py)
-    cfg = config_from_setup(setup, skin=-1.0, **tuning)
+    # same plan on both sides: same cells, same skin, and -- the ranks max-reduce their re-sort
+    # decisions -- the same steps sort, so the two runs differ by the decomposition only
+    cfg = config_from_setup(setup, **tuning)
     single = Engine(cfg, n)
     single.upload(setup.state)
     single.step(setup.dt, nsteps)
@@ -83,6 +82,15 @@ def test_slab_ring_matches_single_engine(name, nranks):
         assert ((lay[mine] >= e.z0) & (lay[mine] < e.z1)).all()
 
 
+def test_slab_ring_freezes_and_sorts_together():
+    """The ranks agree on when to sort: after 12 steps every rank has searched the same number of
+    times, fewer than 12, and as often as the single engine."""
+    kw, _ = CASES["tgv3d"]
+    setup, ref, got, owners0, owners1, ring = _run_pair(kw, 2, nsteps=12)
+    searches = [e.counters()["searches"] for e in ring]
+    assert len(set(searches)) == 1 and 1 <= searches[0] < 12, searches
+
+
 def test_slab_migration_happens_and_conserves_particles():
     """2D TGV (velocity along the slab axis) long enough for particles to cross slab faces."""
     kw = dict(case="tgv", dim=2, dx=0.0125, tvf=1.0)
@@ -108,7 +116,7 @@ def test_slab_forward_only_is_bitwise_single_engine():
     setup.state["r"] = np.mod(setup.state["r"] + rng.uniform(-0.2, 0.2, setup.state["r"].shape)
                               * setup.dx, setup.box_size).astype(np.float32)
     n = len(setup.state["r"])
-    single = Engine(config_from_setup(setup, skin=-1.0), n)  # the cell grid of the slab engines
+    single = Engine(config_from_setup(setup), n)
     single.upload(setup.state)
     single.step(0.0, 1, integrate=False, bc=False)
     ref = single.download(host=True)
