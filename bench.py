@@ -6,12 +6,19 @@
 Workload at N=1: BASELINE.json configs[3], the 3D Taylor-Green vortex of
 validation/tgv3d.sh (SPH, tvf=1, viscosity 0.02, Quintic kernel) on a 256^3
 lattice = 16 777 216 particles, float32, synthetic lattice initialisation.
-One "step" = one advance(dt) (integrator.py:22-56): kick + drift + wrap,
-neighbour-structure rebuild, density sweep + EoS, force sweep.
+One "step" = one advance(dt) (integrator.py:22-56): kick + drift + wrap, cell
+sort + neighbour search (on the steps where a particle has moved half the list
+skin since the last one), exact membership test + density sweep + EoS, force
+sweep.
 
 Prints ONE JSON line (rank 0).  `value` times the resident engine (state in
 HBM); `e2e` times the same step through the public host-buffer API with the
-full state copied host->device before and device->host after every step.
+state copied host->device before and device->host after every step;
+`stateless_advance` times the C-ABI call an XLA custom call would make
+(sphb200_advance: device pointers in, device pointers out, caller workspace);
+`configs` holds short runs of the other single-GPU BASELINE configurations
+(C1, C2a, C2b, C3); `roofline` puts the dominant kernel against the FP32 peak
+measured on this device by the library's own FMA kernel.
 """
 
 import argparse
@@ -31,26 +38,63 @@ if ROOT not in sys.path:
 METRIC = "particle-updates/sec"
 UNIT = "particle-updates/s"
 
-# algorithmic HBM bytes per particle-step (float32, 3D / 2D), DESIGN.md section 4
-# (state quads + the particle's neighbour-list row: 93 / 25 entries in chunks of 8 x 2 B + count)
+# Algorithmic HBM bytes per particle-step, float32: what the pass must
+# move if every array crossed HBM once -- integrate 144 (R pt um vv du dv rb, W pt um vv),
+# density 24 (R pt, W rho p), force 76 (R pt um vv st, W dudt dvdt).  `lists` = what the engine
+# adds on top by keeping neighbour lists in HBM: the density pass reads
+# the skin row (147 / 37 entries on the 3D / 2D lattice, 2 B each, in 16-byte chunks) and writes
+# the exact row (123 / 29), the force pass reads the exact row.
 BYTES = {
-    3: dict(cells=276, density=64 + 196, force=112 + 196),
-    2: dict(cells=276, density=64 + 68, force=112 + 68),
+    3: dict(cells=144, density=24, force=76, lists=dict(density=304 + 4 + 246 + 4, force=246 + 4)),
+    2: dict(cells=144, density=24, force=76, lists=dict(density=80 + 4 + 58 + 4, force=58 + 4)),
 }
 # useful flops per directed in-range edge, SURVEY.md section 8d
 FLOPS_EDGE = {3: dict(density=58 + 1, force=58 + 103 + 16), 2: dict(density=50 + 1, force=50 + 63 + 14)}
-FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal non-tensor FP32 FMA peak
+FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal non-tensor FP32 FMA peak
 
 
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep, from the committed
-    ncu capture of this workload (profiles/r01_traffic.json); None when absent."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+def source_sha():
+    """Hash of the CUDA sources: ties a committed ncu capture to the build it describes."""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "jax_sph_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the sweep from the committed
+    ncu capture (profiles/r02_traffic.json: bytes per particle, scaled to this launch).  None
+    unless the capture was taken from THESE sources (source_sha) -- a stale file says nothing."""
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         with open(path) as f:
-            return json.load(f)[kernel]["dram_bytes_per_launch"]
+            t = json.load(f)
+        if t.get("source_sha") != source_sha():
+            return None
+        return t[kernel]["dram_bytes_per_particle"] * n
     except Exception:
         return None
+
+
+def fp32_peak():
+    """Measured FP32 FMA throughput of this device (sphb200_fp32_peak: independent FFMA chains,
+    no memory traffic), TFLOP/s; the denominator of the sweeps' roofline."""
+    import ctypes as C
+
+    from jax_sph_b200 import _lib
+
+    lib = _lib.load()
+    out = {}
+    for name, packed in (("ffma", 0), ("ffma2", 1)):
+        tf, ms = C.c_double(), C.c_double()
+        _lib.check(lib.sphb200_fp32_peak(packed, C.byref(tf), C.byref(ms), None))
+        out[name] = tf.value
+    return out
 
 
 def measured_peaks():
@@ -61,43 +105,60 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def roofline_of(acc, dim, n, edges, peaks, which):
-    """`roofline` object: the DOMINANT kernel of the step (largest CUDA-event time) against
-    the HBM roofline as the contract asks, with its FP32 figure (the sweeps are issue-bound,
-    DESIGN.md section 3) and the same numbers for the other sweep under `kernels`."""
-    names = {"density": "k_sweep<PhysDensity, LIST_BUILD> (density sweep + neighbour-list builder)",
+def roofline_of(acc, dim, n, edges, peaks, which, fp32=None, searches_per_step=None):
+    """`roofline` object: the DOMINANT kernel of the step (largest CUDA-event time) against the
+    roofline that bounds it -- FP32 issue: the sweeps do 20 useful flop per algorithmic byte, the
+    ridge of this device is at 11 -- with the measured FMA peak as the
+    denominator; its HBM figure, the other sweep and the HBM-bound integrate pass beside it."""
+    names = {"density": "k_sweep<PhysDensity, LIST_FILTER> (exact membership test + density sweep"
+                        " + exact list of the step; on sorting steps preceded by the search "
+                        "k_sweep<PhysNone, LIST_BUILD>, included in ms)",
              "force": "k_sweep<PhysForce, LIST_CONSUME> (force sweep)"}
+    peak_tf = fp32["ffma"] if fp32 else FP32_NOMINAL_TFLOPS
+    peak_src = "measured: sphb200_fp32_peak (FFMA chains) on this device" if fp32 else "nominal"
     per = {}
     for k in ("density", "force"):
         ms = acc.get(k, 0.0)
         if not ms:
             continue
         gbs = BYTES[dim][k] * n / (ms * 1e-3) / 1e9
+        gbs_l = (BYTES[dim][k] + BYTES[dim]["lists"][k]) * n / (ms * 1e-3) / 1e9
         tf = FLOPS_EDGE[dim][k] * edges * n / (ms * 1e-3) / 1e12
-        per[k] = {"kernel": names[k], "ms": ms, "achieved": gbs, "frac": gbs / peaks["hbm_gbs"],
-                  "traffic": ncu_traffic(k),
-                  "fp32": {"achieved_tflops": tf, "peak_tflops_nominal": FP32_PEAK_TFLOPS,
-                           "frac": tf / FP32_PEAK_TFLOPS}}
+        per[k] = {"kernel": names[k], "ms": ms, "bound": "fp32", "achieved": tf, "peak": peak_tf,
+                  "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": ncu_traffic(k, n),
+                  "hbm": {"algorithmic_bytes_per_particle": BYTES[dim][k], "achieved_gbs": gbs,
+                          "with_list_rows_gbs": gbs_l, "peak_gbs": peaks["hbm_gbs"],
+                          "frac": gbs / peaks["hbm_gbs"]}}
     if not per:
-        return {"kernel": None, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": None, "traffic": None, "passes_ms": acc}
+        return {"kernel": None, "bound": "fp32", "achieved": None, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": None, "traffic": None, "passes_ms": acc}
     top = max(per, key=lambda k: per[k]["ms"])
     c_ms = acc.get("cells", 0.0)
-    roof = {
-        "kernel": per[top]["kernel"], "bound": "hbm", "achieved": per[top]["achieved"],
-        "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": which, "frac": per[top]["frac"],
-        "traffic": per[top]["traffic"], "ms": per[top]["ms"],
-        "note": "the sweeps are bound by FP32/ALU issue and shared-memory wavefronts, not by HBM "
-                "(20 flop per algorithmic byte, ridge at 11): see fp32 and DESIGN.md section 3; "
-                "the HBM-bound passes are under cells",
-        "fp32": per[top]["fp32"], "kernels": per,
-        "cells": {"kernel": "k_hash + scan + k_scatter_src + k_reorder (integrate, sort, reorder)",
-                  "ms": c_ms,
+    tot_ms = acc.get("total", 0.0)
+    step_tf = sum(FLOPS_EDGE[dim][k] for k in ("density", "force")) * edges * n / (tot_ms * 1e-3) / 1e12 \
+        if tot_ms else None
+    roof = dict(per[top])
+    roof.update({
+        "peak_source": peak_src, "fp32_peaks_tflops": dict(fp32 or {}, nominal=FP32_NOMINAL_TFLOPS),
+        "hbm_peak_source": which,
+        "note": "achieved = useful flops (SURVEY.md 8d: per in-range directed edge, "
+                f"{edges} edges per lattice particle) / CUDA-event time of the pass; the sweeps "
+                "are bound by instruction issue and shared-memory wavefronts (ncu: profiles/), "
+                "not by HBM; `cells` is the HBM-bound integrate pass (plus the cell sort on the "
+                "steps that sort)",
+        "kernels": per,
+        "step": {"ms": tot_ms, "useful_tflops": step_tf,
+                 "frac_of_fp32_peak": step_tf / peak_tf if step_tf else None,
+                 "searches_per_step": searches_per_step},
+        "cells": {"kernel": "k_drift (kick + drift + wrap in place, re-sort decision) [+ k_hash, "
+                            "scan, k_scatter_src, k_reorder, k_copyback on the steps that sort]",
+                  "ms": c_ms, "bound": "hbm",
                   "achieved": BYTES[dim]["cells"] * n / (c_ms * 1e-3) / 1e9 if c_ms else None,
+                  "peak": peaks["hbm_gbs"], "unit": "GB/s",
                   "frac": BYTES[dim]["cells"] * n / (c_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]
                   if c_ms else None},
         "passes_ms": acc,
-    }
+    })
     return roof
 
 
@@ -202,6 +263,58 @@ def ht3d_state(nx, planes=None):
     return state, meta
 
 
+def db2d_meta(dx):
+    """BASELINE configs[2]: cases/db.yaml (2D dam break, cases/db.py:17-142): fluid column
+    L x H = 2 x 1 at rest in a tank L_wall x H_wall = 5.366 x 2 with three wall layers, gravity
+    -e_y, SPH + is_bc_trick + density evolution + artificial viscosity 0.1, u_ref = sqrt(2),
+    viscosity 5e-5; dx = 0.00071 gives 4 028 622 particles."""
+    n_walls, g_mag, viscosity, u_ref = 3, 1.0, 0.00005, 2.0**0.5
+    c_ref = 10.0 * u_ref
+    eps = float(np.finfo(np.float32).eps)
+    dt = float(min(0.25 * dx / (c_ref + u_ref), 0.25 * dx * dx / (viscosity + eps),
+                   0.25 * (dx / (g_mag + eps)) ** 0.5))  # case_setup.py:94-97
+    dxn = n_walls * dx
+    box = [5.366 + 2 * dxn + 0.1, 2.0 + 2 * dxn + 0.1]
+    zero = [0.0, 0.0, 0.0]
+    bc_table = {"tags": {1: dict(u=zero, v=zero, zero_dudt=True, zero_dvdt=True, p=0.0)},
+                "inflow_x": None, "outflow_x": None}
+    return dict(dim=2, box=box, dx=dx, dt=dt, viscosity=viscosity, c_ref=c_ref, p_ref=c_ref**2,
+                tvf=0.0, n_walls=n_walls,
+                cfg_kwargs=dict(is_bc_trick=True, is_rho_evol=True, artificial_alpha=0.1,
+                                g_ext_spec={"mode": "const", "g": [0.0, -g_mag, 0.0]},
+                                bc_table=bc_table))
+
+
+def db2d_state(dx):
+    """Particles of db2d_meta(dx) as cases/db.py:94-127 lays them out: the four wall blocks of
+    pos_box_2d (utils.py:57-78: left, bottom, right, top; lattices (i + 0.5) dx), then the fluid
+    lattice shifted by the wall thickness; float32 arithmetic as upstream."""
+    meta = db2d_meta(dx)
+    t = np.float32
+
+    def init2(bx, by):  # pos_init_cartesian_2d, utils.py:35-46
+        n0, n1 = int(np.round(bx / dx)), int(np.round(by / dx))
+        gx, gy = np.meshgrid(range(n0), range(n1), indexing="xy")
+        return ((np.vstack([gx.ravel(), gy.ravel()]).T.astype(np.float32) + t(0.5)) * t(dx)).astype(np.float32)
+
+    dxn = meta["n_walls"] * dx
+    lw, hw = 5.366, 2.0
+    vertical, horiz = init2(dxn, hw + 2 * dxn), init2(lw, dxn)
+    walls = np.concatenate([vertical, horiz + np.array([dxn, 0.0]),
+                            vertical + np.array([lw + dxn, 0.0]),
+                            horiz + np.array([dxn, hw + dxn])]).astype(np.float32)
+    fluid = (t(dxn) + init2(2.0, 1.0)).astype(np.float32)
+    r = np.concatenate([walls, fluid]).astype(np.float32)
+    tag = np.concatenate([np.full(len(walls), 1), np.full(len(fluid), 0)]).astype(np.int32)
+    n = len(r)
+    ones, zv = np.ones(n, dtype=np.float32), np.zeros((n, 2), dtype=np.float32)
+    state = dict(r=r, u=zv, v=zv.copy(), dudt=zv.copy(), dvdt=zv.copy(), rho=ones.copy(),
+                 p=np.zeros(n, dtype=np.float32), drhodt=np.zeros(n, dtype=np.float32),
+                 mass=ones * t(dx**2), eta=ones * t(meta["viscosity"]), T=ones.copy(),
+                 dTdt=np.zeros(n, dtype=np.float32), tag=tag)
+    return state, meta
+
+
 def lattice_meta(workload, nx):
     if workload == "ht3d":
         return ht3d_meta(nx)
@@ -222,6 +335,8 @@ def lattice_state(workload, nx, planes=None):
     the state then also carries `ids`, the particles' indices in the full lattice."""
     if workload == "ht3d":
         return ht3d_state(nx, planes)
+    if workload == "db2d":
+        return db2d_state(1.0 / nx if nx else 0.00071)  # nx = 0: BASELINE's dx, 4 028 622 particles
     if workload == "tgv3d":
         dim, box = 3, 2 * np.pi
     else:
@@ -263,6 +378,11 @@ def lattice_state(workload, nx, planes=None):
                  tag=np.zeros(n, dtype=np.int32))
     meta = dict(dim=dim, box=[box] * dim, dx=dx, dt=dt, viscosity=viscosity, c_ref=c_ref,
                 p_ref=c_ref**2, tvf=1.0)
+    if workload == "tgv2d_sph":  # BASELINE configs[0]: solver.name=SPH solver.tvf=0.0
+        meta["tvf"] = 0.0
+    if workload == "tgv2d_rie":  # BASELINE configs[1]: solver.name=RIE (+ density evolution)
+        meta["tvf"] = 0.0
+        meta["cfg_kwargs"] = dict(solver="RIE", is_rho_evol=True)
     if planes is not None:
         state["ids"] = ids
     return state, meta
@@ -285,7 +405,116 @@ def workload_name(args, n):
     if args.workload == "ht3d":
         return (f"ht3d nx={args.nx} N={n} SPH bc_trick heat band-g QSK (BASELINE configs[4], "
                 "cases/ht.yaml case.dim=3)")
-    return f"{args.workload} nx={args.nx} N={n} SPH tvf=1 QSK (BASELINE configs[3])"
+    what = {"tgv3d": "SPH tvf=1 QSK (BASELINE configs[3])",
+            "tgv2d": "SPH tvf=1 QSK (BASELINE configs[1], transport-velocity SPH)",
+            "tgv2d_sph": "SPH tvf=0 QSK (BASELINE configs[0], cases/tgv.yaml)",
+            "tgv2d_rie": "RIE + density evolution QSK (BASELINE configs[1], Riemann SPH)",
+            "db2d": "SPH bc_trick density-evolution alpha=0.1 gravity QSK (BASELINE configs[2], "
+                    "cases/db.yaml)"}[args.workload]
+    return f"{args.workload} nx={args.nx} N={n} {what}"
+
+
+# the other single-GPU BASELINE configurations, run for a few steps after the headline
+OTHER_CONFIGS = (("C1", "tgv2d_sph", 50), ("C2a", "tgv2d", 1000), ("C2b", "tgv2d_rie", 1000),
+                 ("C3", "db2d", 0))
+
+
+def run_config(args, workload, nx, steps=20, warmup=3):
+    """particle-updates/s of the resident engine on another BASELINE configuration."""
+    import copy
+
+    import torch
+
+    from jax_sph_b200 import Engine
+
+    a = copy.copy(args)
+    a.workload, a.nx = workload, nx
+    a.sub = a.threads = a.list_cap = a.tile_x = a.tile_y = a.tile_z = 0
+    state, meta = lattice_state(workload, nx)
+    n = len(state["r"])
+    eng = Engine(config_of(a, meta), n)
+    eng.upload({k: torch.from_numpy(v) for k, v in state.items()})
+    eng.step(meta["dt"], warmup)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.step(meta["dt"], steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    err = eng.error()
+    cnt = eng.counters()
+    eng.close()
+    return {"workload": workload_name(a, n), "n": n, "steps": steps, "ms_per_step": ms / steps,
+            "value": n * steps / (ms * 1e-3), "unit": UNIT, "device_error_word": err,
+            "searches": cnt["searches"], "steps_total": cnt["steps"],
+            "tiles_without_lists": cnt["tiles_without_lists"]}
+
+
+def stateless_advance(args, eng_cfg, state, meta, steps):
+    """The drop-in call: sphb200_advance(cfg, n, dt, in, out, err, workspace, stream) on DEVICE
+    pointers with a caller-owned workspace -- what the jax.ffi custom call of INTEGRATION.md
+    executes once per `advance(dt, state, neighbors)` (jax_sph/simulate.py:117).  Outputs of one
+    call are the inputs of the next (two sets of arrays, swapped), the workspace is the same."""
+    import ctypes as C
+
+    import torch
+
+    from jax_sph_b200 import _lib
+    from jax_sph_b200.engine import STATE_KEYS
+
+    lib = _lib.load()
+    n = len(state["r"])
+    nbytes = C.c_size_t()
+    _lib.check(lib.sphb200_workspace_bytes(C.byref(eng_cfg), n, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+    bufs = [{k: torch.from_numpy(np.ascontiguousarray(state[k])).cuda() for k in STATE_KEYS
+             if k in state} for _ in range(2)]
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def struct(d):
+        st = _lib.State()
+        for k, v in d.items():
+            setattr(st, k, v.data_ptr())
+        return st
+
+    sts = [struct(b) for b in bufs]
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def timed(fn, count):
+        i0 = timed.i
+        for i in range(i0, i0 + 3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(i0 + 3, i0 + 3 + count):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        timed.i = i0 + 3 + count
+        return e0.elapsed_time(e1) / count
+
+    timed.i = 0
+
+    def call(fn):
+        return lambda i: _lib.check(fn(C.byref(eng_cfg), n, float(meta["dt"]), C.byref(sts[i % 2]),
+                                       C.byref(sts[(i + 1) % 2]), C.c_void_p(err.data_ptr()),
+                                       C.c_void_p(ws.data_ptr()), nbytes.value, stream))
+
+    ms = timed(call(lib.sphb200_advance_persistent), steps)
+    lib.sphb200_workspace_release(C.c_void_p(ws.data_ptr()))
+    ms_scratch = timed(call(lib.sphb200_advance), min(steps, 3))
+    return {"value": n * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "device_error_word": int(err.item()),
+            "what": "sphb200_advance_persistent on device pointers, the caller's workspace handed "
+                    "in again call after call (the engine in it keeps the particles cell-sorted "
+                    "and the neighbour lists; every call copies the full state in and the full "
+                    "state out in the caller's particle order)",
+            "scratch_workspace": {"value": n / (ms_scratch * 1e-3), "unit": UNIT,
+                                  "ms_per_step": ms_scratch,
+                                  "what": "sphb200_advance: nothing kept between calls (pack, "
+                                          "sort, search, step, unpack every call)"}}
 
 
 def run_ours(args):
@@ -350,6 +579,7 @@ def run_ours(args):
         ms = float(t.item())
     err = eng.error()
     counters = eng.counters()
+    fp32 = fp32_peak()
 
     # per-pass CUDA-event times (same stream, separate loop of the same steps)
     eng.profile(True)
@@ -386,16 +616,31 @@ def run_ours(args):
     per_step_ms = ms / args.steps
     value = world * n * args.steps / (ms * 1e-3)
     edges = 93 if dim == 3 else 25  # directed in-range edges per lattice particle incl. self
-    roof = roofline_of(acc, dim, n, edges, peaks, which)
+    roof = roofline_of(acc, dim, n, edges, peaks, which, fp32,
+                       counters["searches"] / max(counters["steps"], 1))
+    # the C-ABI drop-in call and the other BASELINE configurations (resident engine freed first)
+    cfg_copy = config_of(args, meta)
+    plan = eng.plan()
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    stateless = stateless_advance(args, cfg_copy, state, meta, max(1, min(args.steps, 10)))
+    others = {}
+    if not args.no_configs:
+        for tag, wl, nx_c in OTHER_CONFIGS:
+            try:
+                others[tag] = run_config(args, wl, nx_c)
+            except Exception as ex:  # a failed side run must not hide the headline
+                others[tag] = {"error": repr(ex)}
     cpu = cpu_baseline(args, bounded=True)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args, n),
-                   "particles_per_gpu": n, "parallelism": "1 engine per GPU" if world == 1 else
-                   f"{world} independent periodic boxes (replicas, no halo exchange yet)",
-                   "l2_policy": "state (>1.8 GB) larger than L2", "plan": eng.plan(),
+                   "particles_per_gpu": n, "parallelism": "1 engine on 1 GPU (N > 1: the same box "
+                   "cut into slabs, strong scaling)",
+                   "l2_policy": "state (>1.8 GB) larger than L2", "plan": plan,
                    "neighbour_search": dict(counters, timed_steps=args.steps, note=(
                        "steps / searches since engine creation (warm-up included): the cell sort "
                        "and candidate walk run when a particle has moved half the list skin; the "
@@ -407,6 +652,7 @@ def run_ours(args):
                 "what": "Engine.advance_host(dt, pinned host state) every step: H2D of the "
                         f"entries advance() reads ({','.join(read)}), one step, D2H of the "
                         f"entries it writes ({','.join(written)})"},
+        "stateless_advance": stateless, "configs": others,
         "roofline": roof, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
@@ -514,7 +760,7 @@ def run_slab(args, world, rank, local, saved_stdout):
     peaks, which = measured_peaks()
     edges = 93 if dim == 3 else 25
     n_loc = counts["own"]
-    roof = roofline_of(acc, dim, n_loc, edges, peaks, which)  # rank 0's slab
+    roof = roofline_of(acc, dim, n_loc, edges, peaks, which, fp32_peak())  # rank 0's slab
     roof["kernel"] = str(roof["kernel"]) + ", rank 0's slab"
     roof["traffic"] = None  # the ncu capture is of the single-GPU launch
     line = {
@@ -633,7 +879,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="tgv3d", choices=["tgv3d", "tgv2d", "ht3d"])
+    ap.add_argument("--workload", default="tgv3d",
+                    choices=["tgv3d", "tgv2d", "tgv2d_sph", "tgv2d_rie", "db2d", "ht3d"])
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the short runs of the other BASELINE configurations")
     ap.add_argument("--nx", type=int, default=256)
     ap.add_argument("--cpu-nx", type=int, default=32)
     ap.add_argument("--cpu-steps", type=int, default=3)

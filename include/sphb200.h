@@ -26,7 +26,8 @@
  *     float32, scalar fields (N,) float32, tag (N,) int32.
  *   - float32 only: the reference's float64 mode is not offered (documented drift
  *     bound instead); a float64 request fails with SPHB200_EDTYPE.
- *   - Re-entrant: no global mutable state; one engine per stream/device.
+ *   - Re-entrant: engines share nothing; one engine per stream/device.  The only global state
+ *     is the mutex-protected workspace table of the stateless entry points (see below).
  */
 #ifndef SPHB200_H_
 #define SPHB200_H_
@@ -197,6 +198,12 @@ int sphb200_engine_create_in(const sphb200_config *cfg, int64_t n, void *workspa
 int sphb200_engine_destroy(sphb200_engine *e);
 /* Copy a state in reference layout into the engine (on_host: pointers are host memory). */
 int sphb200_engine_upload(sphb200_engine *e, const sphb200_state *s, int on_host, void *stream);
+/* Copy a state of the SAME particles (row i is still particle i) into the slots they occupy in
+ * the cell-sorted frame.  Unlike sphb200_engine_upload this keeps the cell table and the
+ * neighbour lists: the next step tests every position against the one the particle had when the
+ * cells were made and sorts again only if one moved further than half the list skin -- the
+ * result is the same either way.  Before the first step it is an ordinary upload. */
+int sphb200_engine_refresh(sphb200_engine *e, const sphb200_state *s, int on_host, void *stream);
 /* nsteps x advance(dt) (integrator.py:22-56) or forward only, per `flags`. */
 int sphb200_engine_step(sphb200_engine *e, double dt, int nsteps, uint32_t flags, void *stream);
 /* One advance(dt, state, neighbors) (integrator.py:22-56) on HOST buffers, the call a reference
@@ -355,7 +362,9 @@ int sphb200_eval_velocity(int32_t dim, int64_t n, int32_t velocity, const float 
 int sphb200_add_noise(int32_t dim, int64_t n, float *r, const int32_t *tag, const int32_t *ids,
                       double std, uint64_t seed, const double box[3], void *stream);
 
-/* ---- stateless entry points (device pointers, caller-owned workspace) ----- */
+/* ---- stateless entry points (device pointers, caller-owned workspace) -----
+ * Pure functions of their arguments: out = f(cfg, in); the workspace is scratch (>=
+ * sphb200_workspace_bytes), nothing is kept in it after the call. */
 int sphb200_workspace_bytes(const sphb200_config *cfg, int64_t n, size_t *bytes);
 int sphb200_neighbor_list(const sphb200_config *cfg, int64_t n, const float *r, int32_t *idx,
                           int64_t capacity, int mask_self, int64_t *count, uint32_t *err,
@@ -366,6 +375,21 @@ int sphb200_forward(const sphb200_config *cfg, int64_t n, const sphb200_state *i
 int sphb200_advance(const sphb200_config *cfg, int64_t n, double dt, const sphb200_state *in,
                     sphb200_state *out, uint32_t *err, void *workspace, size_t workspace_bytes,
                     void *stream);
+/* sphb200_advance for a caller that OWNS the workspace from call to call (memory nobody else
+ * writes in between -- NOT an XLA scratch buffer; the jax.ffi shim keeps one allocation per
+ * (cfg, n)).  Still out = f(cfg, in): the result never depends on what the
+ * workspace held.  But when it is handed in again with the same cfg and n, the particles are
+ * found cell-sorted in it with their neighbour lists: the new state goes into the slots its
+ * particles occupy (sphb200_engine_refresh), every position is tested against the sorted one, and
+ * the cell sort + neighbour search run only if a particle moved further than half the list skin
+ * -- a state that has nothing to do with the previous call simply sorts again.  The call then
+ * costs a resident step plus the two state copies.  The library keeps a table workspace pointer
+ * -> engine for this (mutex-protected, at most 8 workspaces); call
+ * sphb200_workspace_release(ws) before the memory is freed or reused (NULL: all). */
+int sphb200_advance_persistent(const sphb200_config *cfg, int64_t n, double dt,
+                               const sphb200_state *in, sphb200_state *out, uint32_t *err,
+                               void *workspace, size_t workspace_bytes, void *stream);
+void sphb200_workspace_release(void *workspace);
 
 #ifdef __cplusplus
 }

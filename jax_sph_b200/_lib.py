@@ -84,6 +84,7 @@ SYMBOLS = {
                                            C.POINTER(_P)]),
     "sphb200_engine_destroy": (C.c_int, [_P]),
     "sphb200_engine_upload": (C.c_int, [_P, C.POINTER(State), C.c_int, _P]),
+    "sphb200_engine_refresh": (C.c_int, [_P, C.POINTER(State), C.c_int, _P]),
     "sphb200_engine_step": (C.c_int, [_P, C.c_double, C.c_int, C.c_uint32, _P]),
     "sphb200_engine_advance_host": (C.c_int, [_P, C.c_double, C.POINTER(State), C.POINTER(State),
                                              C.c_uint32, _P]),
@@ -112,6 +113,7 @@ SYMBOLS = {
     "sphb200_eval_velocity": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "sphb200_add_noise": (C.c_int, [C.c_int32, C.c_int64, _P, _P, _P, C.c_double, C.c_uint64,
                                     C.POINTER(C.c_double * 3), _P]),
+    "sphb200_workspace_release": (None, [_P]),
     "sphb200_workspace_bytes": (C.c_int, [C.POINTER(Config), C.c_int64, C.POINTER(C.c_size_t)]),
     "sphb200_neighbor_list": (C.c_int, [C.POINTER(Config), C.c_int64, _P, _P, C.c_int64, C.c_int,
                                         _P, _P, _P, C.c_size_t, _P]),
@@ -119,6 +121,9 @@ SYMBOLS = {
                                   C.POINTER(State), _P, _P, C.c_size_t, _P]),
     "sphb200_advance": (C.c_int, [C.POINTER(Config), C.c_int64, C.c_double, C.POINTER(State),
                                   C.POINTER(State), _P, _P, C.c_size_t, _P]),
+    "sphb200_advance_persistent": (C.c_int, [C.POINTER(Config), C.c_int64, C.c_double,
+                                             C.POINTER(State), C.POINTER(State), _P, _P,
+                                             C.c_size_t, _P]),
 }
 
 _lib = None

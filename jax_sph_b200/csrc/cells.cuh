@@ -288,16 +288,18 @@ __global__ void __launch_bounds__(256) k_reorder(int n, Grid g, Kick k, Slab sl,
 // ---------------------------------------------------------------------------
 // Resident single-GPU engines keep the particles in place between two searches (sweep.cuh):
 //
-// k_drift: kick + drift + wrap of integrator.py:26-30 / space.py:207-209 IN PLACE, the path each
-// particle has travelled since the last sort, and the decision whether THIS step re-sorts and
-// searches: a path longer than `limit` (half the skin of the neighbour lists) raises *flag_cur.
-// Sweeps only ever see positions whose paths are within the limit, so a pair that is inside the
-// cutoff now was inside cutoff + skin at the last search and is in the skin list.
+// k_drift: kick + drift + wrap of integrator.py:26-30 / space.py:207-209 IN PLACE, and the
+// decision whether THIS step re-sorts and searches: a particle further than `limit` (half the
+// skin of the neighbour lists) from where it was at the last sort (`rb`, minimum image) raises
+// *flag_cur.  Sweeps only ever see positions within the limit, so a pair that is inside the
+// cutoff now was inside cutoff + skin at the last search and is in the skin list.  The criterion
+// is a function of the current positions alone -- a caller may hand in ANY state of the same
+// particles (the stateless entry points do): if it is not close to the sorted one, the step sorts.
 // The flag words alternate between steps: this launch also clears the next step's word.
 template <int DIM>
 __global__ void __launch_bounds__(256) k_drift(int n, Grid g, Kick k, Slab sl, Frame f,
-                                               float* __restrict__ path, int* flag_cur,
-                                               int* flag_next, int force, float limit,
+                                               const float4* __restrict__ rb, int* flag_cur,
+                                               int* flag_next, int force, float limit2,
                                                unsigned* __restrict__ err) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *flag_next = 0;
@@ -307,26 +309,28 @@ __global__ void __launch_bounds__(256) k_drift(int n, Grid g, Kick k, Slab sl, F
   const int n_own = sl.dn ? sl.dn[DN_OWN] : n;  // slab engines: own particles only
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_own; t += gridDim.x * blockDim.x) {
     const int p = sl.base + t;
-    const float4 a = f.pt[p], b = f.um[p], w = f.vv[p];
-    float r[3] = {a.x, a.y, a.z}, u[3] = {b.x, b.y, b.z}, v[3] = {w.x, w.y, w.z};
-    integrate_one<DIM>(k, g, r, u, v, f.du[p], f.dv[p]);
-    float s2 = 0.f;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      const float s = k.dt * v[d];
-      s2 += s * s;
+    const float4 a = f.pt[p];
+    float r[3] = {a.x, a.y, a.z};
+    if (k.on) {
+      const float4 b = f.um[p], w = f.vv[p];
+      float u[3] = {b.x, b.y, b.z}, v[3] = {w.x, w.y, w.z};
+      integrate_one<DIM>(k, g, r, u, v, f.du[p], f.dv[p]);
+      f.pt[p] = make_float4(r[0], r[1], r[2], a.w);
+      f.um[p] = make_float4(u[0], u[1], u[2], b.w);
+      f.vv[p] = make_float4(v[0], v[1], v[2], w.w);
     }
-    const float pl = path[p] + sqrtf(s2);
-    path[p] = pl;
-    over = over || !(pl <= limit);
     const bool finite = isfinite(r[0]) && isfinite(r[1]) && (DIM == 2 || isfinite(r[2]));
     if (!finite) atomicOr(err, SPHB200_ERR_NONFINITE);
     const bool inside = r[0] >= 0.f && r[0] <= g.box[0] && r[1] >= 0.f && r[1] <= g.box[1] &&
                         (DIM == 2 || (r[2] >= 0.f && r[2] <= g.box[2]));
     if (finite && !inside) atomicOr(err, SPHB200_ERR_OUTSIDE_BOX);
-    f.pt[p] = make_float4(r[0], r[1], r[2], a.w);
-    f.um[p] = make_float4(u[0], u[1], u[2], b.w);
-    f.vv[p] = make_float4(v[0], v[1], v[2], w.w);
+    if (!force) {  // (a forced sort needs no test: rb may not exist yet)
+      const float4 q = rb[p];
+      float d[3] = {disp1(r[0], q.x, g.half[0], g.box[0]), disp1(r[1], q.y, g.half[1], g.box[1]),
+                    DIM == 3 ? disp1(r[2], q.z, g.half[2], g.box[2]) : 0.f};
+      const float d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+      over = over || !(d2 <= limit2);
+    }
   }
   if (__syncthreads_or(over) && threadIdx.x == 0) atomicOr(flag_cur, 1);
 }
@@ -345,7 +349,7 @@ __global__ void k_flag_in(const int* word, int* flag) { *flag = *word != 0 ? 1 :
 // After a re-sort (k_reorder: frame a -> frame b) the sorted particles go back to frame a, so
 // that the host always launches on the same frame whether or not the device decided to re-sort.
 __global__ void __launch_bounds__(256) k_copyback(int n, Slab sl, int ncells, ReorderOpt o,
-                                                  Frame a, Frame b, float* __restrict__ path,
+                                                  Frame a, Frame b, float4* __restrict__ rb,
                                                   const int* __restrict__ start,
                                                   const int* __restrict__ gate, int* nsorts) {
   if (gate != nullptr && *gate == 0) return;
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(256) k_copyback(int n, Slab sl, int ncells, Re
     if (o.heat) a.kc[p] = b.kc[p];
     if (o.has_nw) a.nw[p] = b.nw[p];
     if (o.has_ge) a.ge[p] = b.ge[p];
-    path[p] = 0.f;
+    rb[p] = b.pt[p];  // where the particle was when the cells and lists were made
   }
 }
 
@@ -402,10 +406,13 @@ __device__ __forceinline__ void store_vec(float* a, int p, float4 q) {
 }
 
 // `ids` (slab mode): global particle indices of the uploaded rows; frame slots start at `base`.
+// keep_order: the frame already holds THESE particles, cell-sorted (f.id[slot] = row of the
+// particle): slot p takes row f.id[p] of the new state instead of row p -- the cell table and
+// the neighbour lists stay valid as far as the positions allow (k_drift decides).
 template <int DIM>
 __global__ void __launch_bounds__(256) k_pack(int n, StatePtrs s, Frame fin, int base,
                                               const int* __restrict__ ids,
-                                              int* __restrict__ wallcount) {
+                                              int* __restrict__ wallcount, int keep_order) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   Frame f = fin;
@@ -413,18 +420,19 @@ __global__ void __launch_bounds__(256) k_pack(int n, StatePtrs s, Frame fin, int
   if (f.kc) f.kc += base;
   if (f.nw) f.nw += base;
   if (f.ge) f.ge += base;
-  int tag = s.tag ? s.tag[p] : 0;
-  f.pt[p] = load_vec<DIM>(s.r, p, __int_as_float(tag));
-  f.um[p] = load_vec<DIM>(s.u, p, s.mass ? s.mass[p] : 1.0f);
-  f.vv[p] = load_vec<DIM>(s.v, p, s.eta ? s.eta[p] : 0.0f);
-  f.st[p] = make_float4(s.rho ? s.rho[p] : 1.0f, s.p ? s.p[p] : 0.0f, s.T ? s.T[p] : 1.0f,
-                        s.dTdt ? s.dTdt[p] : 0.0f);
-  f.du[p] = load_vec<DIM>(s.dudt, p, s.drhodt ? s.drhodt[p] : 0.0f);
-  f.dv[p] = load_vec<DIM>(s.dvdt, p, 0.0f);
-  if (f.kc) f.kc[p] = make_float2(s.kappa ? s.kappa[p] : 0.0f, s.Cp ? s.Cp[p] : 0.0f);
-  if (f.nw) f.nw[p] = load_vec<DIM>(s.nw, p, 0.0f);
-  if (f.ge) f.ge[p] = load_vec<DIM>(s.g_ext, p, 0.0f);
-  f.id[p] = ids ? ids[p] : p;
+  const int q = keep_order ? f.id[p] : p;  // row of the state this slot takes
+  int tag = s.tag ? s.tag[q] : 0;
+  f.pt[p] = load_vec<DIM>(s.r, q, __int_as_float(tag));
+  f.um[p] = load_vec<DIM>(s.u, q, s.mass ? s.mass[q] : 1.0f);
+  f.vv[p] = load_vec<DIM>(s.v, q, s.eta ? s.eta[q] : 0.0f);
+  f.st[p] = make_float4(s.rho ? s.rho[q] : 1.0f, s.p ? s.p[q] : 0.0f, s.T ? s.T[q] : 1.0f,
+                        s.dTdt ? s.dTdt[q] : 0.0f);
+  f.du[p] = load_vec<DIM>(s.dudt, q, s.drhodt ? s.drhodt[q] : 0.0f);
+  f.dv[p] = load_vec<DIM>(s.dvdt, q, 0.0f);
+  if (f.kc) f.kc[p] = make_float2(s.kappa ? s.kappa[q] : 0.0f, s.Cp ? s.Cp[q] : 0.0f);
+  if (f.nw) f.nw[p] = load_vec<DIM>(s.nw, q, 0.0f);
+  if (f.ge) f.ge[p] = load_vec<DIM>(s.g_ext, q, 0.0f);
+  if (!keep_order) f.id[p] = ids ? ids[p] : p;
   if (is_wall_tag(tag)) atomicAdd(wallcount, 1);
 }
 

@@ -1,8 +1,8 @@
 // engine.cu -- host side of libsphb200.so: planning, arena, launches, C ABI.
 //
 // The per-step pipeline (one call of si_euler.advance, integrator.py:22-56) of a resident engine:
-//   k_drift       kick + drift + wrap in place; path travelled since the last sort; raises the
-//                 step's re-sort flag when a path exceeds half the skin of the neighbour lists
+//   k_drift       kick + drift + wrap in place; raises the step's re-sort flag when a particle is
+//                 further than half the skin of the neighbour lists from where it was sorted
 //   [flag set]    k_hash -> k_scan_* -> k_scatter_src -> k_reorder -> k_copyback   (cell sort)
 //                 k_sweep<PhysNone, LIST_BUILD>                                     (the search)
 //   k_sweep<PhysDensity, LIST_FILTER>  exact membership test + density + exact list of the step
@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
 
 #include "cells.cuh"
@@ -68,16 +69,17 @@ struct sphb200_engine {
   unsigned short* sl_list;
   int* sl_cnt;
   // frozen sort (resident single-GPU engines): the particles keep their slots and the cell table
-  // stays as it is until a particle has travelled more than path_limit since the last sort
+  // stays as it is until a particle is further than path_limit from where it was at the last sort
   bool inplace;
   double skin_frac;         // skin / cutoff
   float path_limit;         // < 0: sort + search every step
-  float* path;              // [n] path length since the last sort
+  float4* rb;               // [n] positions at the last sort
   int* ctl;                 // [0], [1] re-sort flag of even / odd steps, [2] searches so far
   unsigned long long step_no;
   const int* gate_cur;      // flag word of the step being enqueued (nullptr: ungated)
   bool force_rebuild;       // the next step must sort + search (new state, lists stale)
   bool maybe_drifted;       // particles may have left the cells of the frozen table
+  bool positions_replaced;  // a state was uploaded into the sorted slots: test it against rb
   int num_sms;
   unsigned* err;
   double* stats;  // [ekin, umax] of sphb200_engine_stats / the SPHB200_NSTATS words of _get_stats
@@ -399,7 +401,7 @@ void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, double skin_
   L.err = take(4);
   L.stats = take(SPHB200_NSTATS * 8);
   L.dn = take(DN_WORDS * 4);
-  L.path = take((size_t)n * 4);
+  L.path = take((size_t)n * 16);
   L.ctl = take(8 * 4);
   L.pl_lmax = plan_lmax(c, skin_frac);
   if (L.pl_lmax > 0) {
@@ -611,7 +613,7 @@ int sort_cells(sphb200_engine* e, const Kick& k, cudaStream_t st, const int* gat
   e->launches += 5;
   CK(cudaGetLastError());
   {  // the sorted particles go back to the frame the host keeps launching on
-    k_copyback<<<nb, 256, 0, st>>>(e->n, e->slab, e->grid.ncells, o, A, B, e->path, e->start, gate,
+    k_copyback<<<nb, 256, 0, st>>>(e->n, e->slab, e->grid.ncells, o, A, B, e->rb, e->start, gate,
                                    e->ctl + 2);
     e->launches++;
     CK(cudaGetLastError());
@@ -648,13 +650,15 @@ int drift_step(sphb200_engine* e, const Kick& k, cudaStream_t st) {
   int* fn = e->ctl + ((e->step_no + 1ull) & 1ull);
   const int force = (e->force_rebuild || !e->cells_valid) ? 1 : 0;
   Frame& F = e->fr[e->cur];
-  if (k.on) {
+  const float lim2 = e->path_limit < 0.f ? -1.0f : e->path_limit * e->path_limit;
+  if (k.on || e->positions_replaced) {  // (a forward-only call on a re-uploaded state tests it too)
     const int nb = stream_blocks(e, e->slab_on ? e->sgeom.own_cap : e->n);
     if (e->dim == 2)
-      k_drift<2><<<nb, 256, 0, st>>>(e->n, e->grid, k, e->slab, F, e->path, fc, fn, force, e->path_limit, e->err);
+      k_drift<2><<<nb, 256, 0, st>>>(e->n, e->grid, k, e->slab, F, e->rb, fc, fn, force, lim2, e->err);
     else
-      k_drift<3><<<nb, 256, 0, st>>>(e->n, e->grid, k, e->slab, F, e->path, fc, fn, force, e->path_limit, e->err);
+      k_drift<3><<<nb, 256, 0, st>>>(e->n, e->grid, k, e->slab, F, e->rb, fc, fn, force, lim2, e->err);
     e->maybe_drifted = true;
+    e->positions_replaced = false;
   } else {
     k_gate<<<1, 1, 0, st>>>(fc, fn, force);
   }
@@ -1092,6 +1096,7 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->gate_cur = nullptr;
   e->force_rebuild = true;
   e->maybe_drifted = false;
+  e->positions_replaced = false;
   CK(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, dev));
   plan_consts(*cfg, e->consts);
   feature_flags(*cfg, e->has_kc, e->has_nw, e->has_ut, e->has_ge);
@@ -1141,7 +1146,7 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->pl_ok = L.pl_lmax ? (unsigned char*)(e->arena + L.pl_ok) : nullptr;
   e->sl_list = L.pl_lmax ? (unsigned short*)(e->arena + L.sl_list) : nullptr;
   e->sl_cnt = L.pl_lmax ? (int*)(e->arena + L.sl_cnt) : nullptr;
-  e->path = (float*)(e->arena + L.path);
+  e->rb = (float4*)(e->arena + L.path);
   e->ctl = (int*)(e->arena + L.ctl);
   e->dn = (int*)(e->arena + L.dn);
   memset(&e->slab, 0, sizeof(e->slab));
@@ -1383,7 +1388,7 @@ static int ensure_hstage(sphb200_engine* e) {
 
 // rows: particles in *s (slab mode: this rank's own particles, ids = their global indices)
 static int upload_impl(sphb200_engine* e, const sphb200_state* s, int rows, const int32_t* ids,
-                       int on_host, void* stream) {
+                       int on_host, void* stream, bool keep_order = false) {
   if (!e || !s || !s->r) return SPHB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const int n = rows, d = e->dim;
@@ -1419,10 +1424,17 @@ static int upload_impl(sphb200_engine* e, const sphb200_state* s, int rows, cons
   StatePtrs sp{dv.r, dv.u, dv.v, dv.dudt, dv.dvdt, dv.nw, dv.rho, dv.p, dv.drhodt, dv.mass,
                dv.eta, dv.T, dv.dTdt, dv.kappa, dv.Cp, dv.g_ext, dv.tag};
   if (e->has_ge && !dv.g_ext) return SPHB200_EINVAL;
-  e->cur = 0;
-  e->cells_valid = false;
-  e->force_rebuild = true;
-  e->maybe_drifted = false;
+  // keep_order: the same particles as the resident ones go into the slots they occupy; the
+  // cells and lists survive if the new positions are close to the sorted ones (k_drift)
+  keep_order = keep_order && e->cells_valid && !e->slab_on && !ids;
+  if (keep_order) {
+    e->positions_replaced = true;
+  } else {
+    e->cur = 0;
+    e->cells_valid = false;
+    e->force_rebuild = true;
+    e->maybe_drifted = false;
+  }
   if (e->needs_zero) {
     CK(cudaMemsetAsync(e->count, 0, (size_t)e->grid.ncells * 4, st));
     CK(cudaMemsetAsync(e->maxocc, 0, 4, st));
@@ -1430,7 +1442,6 @@ static int upload_impl(sphb200_engine* e, const sphb200_state* s, int rows, cons
     CK(cudaMemsetAsync(e->ctl, 0, 8 * 4, st));
     e->needs_zero = false;
   }
-  if (e->inplace) CK(cudaMemsetAsync(e->path, 0, (size_t)e->n * 4, st));
   CK(cudaMemsetAsync(e->wallcount, 0, 4, st));
   if (e->slab_on) {
     int h[DN_WORDS] = {0};
@@ -1439,8 +1450,8 @@ static int upload_impl(sphb200_engine* e, const sphb200_state* s, int rows, cons
   }
   const int nb = (n + 255) / 256;
   if (n > 0) {
-    if (d == 2) k_pack<2><<<nb, 256, 0, st>>>(n, sp, e->fr[0], e->slab.base, dids, e->wallcount);
-    else k_pack<3><<<nb, 256, 0, st>>>(n, sp, e->fr[0], e->slab.base, dids, e->wallcount);
+    if (d == 2) k_pack<2><<<nb, 256, 0, st>>>(n, sp, e->fr[0], e->slab.base, dids, e->wallcount, keep_order ? 1 : 0);
+    else k_pack<3><<<nb, 256, 0, st>>>(n, sp, e->fr[0], e->slab.base, dids, e->wallcount, keep_order ? 1 : 0);
     e->launches++;
   }
   CK(cudaGetLastError());
@@ -1450,6 +1461,11 @@ static int upload_impl(sphb200_engine* e, const sphb200_state* s, int rows, cons
 int sphb200_engine_upload(sphb200_engine* e, const sphb200_state* s, int on_host, void* stream) {
   if (!e || e->slab_on) return SPHB200_EINVAL;
   return upload_impl(e, s, e->n, nullptr, on_host, stream);
+}
+
+int sphb200_engine_refresh(sphb200_engine* e, const sphb200_state* s, int on_host, void* stream) {
+  if (!e || e->slab_on) return SPHB200_EINVAL;
+  return upload_impl(e, s, e->n, nullptr, on_host, stream, true);
 }
 
 // rows: capacity of the arrays in *out; ids != NULL (slab mode): local order + global indices
@@ -1551,7 +1567,9 @@ int sphb200_engine_advance_host(sphb200_engine* e, double dt, const sphb200_stat
     }
     e->io_on = true;
   }
-  int rc = upload_impl(e, in, e->n, nullptr, 1, stream);
+  // the same particles call after call: the state goes into the slots they occupy, cells and
+  // neighbour lists survive as far as the positions allow (sphb200_engine_refresh)
+  int rc = upload_impl(e, in, e->n, nullptr, 1, stream, true);
   if (rc) return rc;
   Kick k;
   k.dt = (float)dt;
@@ -2212,21 +2230,136 @@ int sphb200_neighbor_list(const sphb200_config* cfg, int64_t n, const float* r, 
   return rc;
 }
 
+// The stateless entry points are pure functions of their arguments.  sphb200_advance_persistent
+// is for a caller that OWNS its workspace between calls (nobody else writes it): handing in the
+// same workspace again gets the engine that lives in it back: the particles are already
+// cell-sorted there and the neighbour lists exist.
+// The new state goes into the slots its particles occupy (k_pack keep_order) and k_drift tests
+// every position against the sorted one, so the result never depends on what the workspace held
+// -- only the cost does.  The cache maps workspace pointers to the host-side engine objects
+// (config + particle count must match, else the workspace is re-initialised).
+namespace {
+struct CachedEngine {
+  void* ws;
+  size_t ws_bytes;
+  int64_t n;
+  sphb200_config cfg;
+  sphb200_engine* e;
+  unsigned long long stamp;
+};
+constexpr int MAX_CACHED = 8;
+CachedEngine g_cache[MAX_CACHED];
+unsigned long long g_stamp = 0;
+std::mutex g_cache_mutex;
+}  // namespace
+
+// DL_* mask of the state entries one step of this solver variant changes (solver.py:930-947:
+// everything else passes through advance() untouched); `nw` only with per-step wall normals.
+static unsigned written_mask(const sphb200_engine* e, bool* rest_some) {
+  const sphb200_config& c = e->cfg;
+  const bool evol = c.flags & SPHB200_F_RHO_EVOL, heat = c.flags & SPHB200_F_HEAT;
+  *rest_some = evol || heat || (e->has_nw && e->wl_n > 0);
+  return DL_R | DL_U | DL_V | DL_RHO | DL_P | DL_DUDT | DL_DVDT;
+}
+
 static int stateless_step(const sphb200_config* cfg, int64_t n, double dt, uint32_t flags,
                           const sphb200_state* in, sphb200_state* out, uint32_t* err, void* ws,
-                          size_t ws_bytes, void* stream) {
-  if (!in || !out) return SPHB200_EINVAL;
-  sphb200_engine* e = nullptr;
-  int rc = with_engine(cfg, n, ws, ws_bytes, &e);
-  if (rc) return rc;
-  rc = sphb200_engine_upload(e, in, 0, stream);
+                          size_t ws_bytes, void* stream, bool persistent = false) {
+  if (!in || !out || !cfg || !ws) return SPHB200_EINVAL;
+  if (!persistent) {  // scratch workspace: nothing survives the call
+    sphb200_engine* e = nullptr;
+    int rc = with_engine(cfg, n, ws, ws_bytes, &e);
+    if (rc) return rc;
+    rc = sphb200_engine_upload(e, in, 0, stream);
+    if (!rc) rc = sphb200_engine_step(e, dt, 1, flags, stream);
+    if (!rc) rc = sphb200_engine_download(e, out, 0, stream);
+    if (!rc && err)
+      rc = cudaMemcpyAsync(err, e->err, 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) == cudaSuccess
+               ? SPHB200_OK : SPHB200_ECUDA;
+    sphb200_engine_destroy(e);
+    return rc;
+  }
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  CachedEngine* slot = nullptr;
+  for (CachedEngine& c : g_cache)
+    if (c.e && c.ws == ws) slot = &c;
+  const bool hit = slot && slot->n == n && slot->ws_bytes == ws_bytes &&
+                   memcmp(&slot->cfg, cfg, sizeof(*cfg)) == 0;
+  int rc = SPHB200_OK;
+  if (!hit) {
+    if (slot) {
+      sphb200_engine_destroy(slot->e);
+      slot->e = nullptr;
+    } else {
+      slot = &g_cache[0];
+      for (CachedEngine& c : g_cache) {  // a free entry, else the least recently used one
+        if (!c.e) { slot = &c; break; }
+        if (c.stamp < slot->stamp) slot = &c;
+      }
+      if (slot->e) {
+        sphb200_engine_destroy(slot->e);
+        slot->e = nullptr;
+      }
+    }
+    sphb200_engine* e = nullptr;
+    rc = with_engine(cfg, n, ws, ws_bytes, &e);
+    if (rc) return rc;
+    slot->ws = ws; slot->ws_bytes = ws_bytes; slot->n = n; slot->cfg = *cfg; slot->e = e;
+  }
+  slot->stamp = ++g_stamp;
+  sphb200_engine* e = slot->e;
+  rc = hit ? sphb200_engine_refresh(e, in, 0, stream) : sphb200_engine_upload(e, in, 0, stream);
   if (!rc) rc = sphb200_engine_step(e, dt, 1, flags, stream);
-  if (!rc) rc = sphb200_engine_download(e, out, 0, stream);
+  if (!rc) {
+    // entries the step changes come back through the permutation (k_unpack scatters by particle
+    // id); the others are the caller's own values: straight copies in -> out
+    bool rest_some = false;
+    written_mask(e, &rest_some);
+    sphb200_state o = *out;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nv = (size_t)n * e->dim * 4, ns = (size_t)n * 4;
+    auto pass = [&](float*& dst, const float* src, size_t bytes) {
+      if (dst && src && dst != src)
+        if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = SPHB200_ECUDA;
+      if (src) dst = nullptr;  // not part of the scatter
+    };
+    const bool evol = cfg->flags & SPHB200_F_RHO_EVOL, heat = cfg->flags & SPHB200_F_HEAT;
+    pass(o.mass, in->mass, ns);
+    pass(o.eta, in->eta, ns);
+    if (!heat) {
+      pass(o.T, in->T, ns);
+      pass(o.dTdt, in->dTdt, ns);
+    }
+    pass(o.kappa, in->kappa, ns);
+    pass(o.Cp, in->Cp, ns);
+    if (!evol) pass(o.drhodt, in->drhodt, ns);
+    if (!(e->has_nw && e->wl_n > 0)) pass(o.nw, in->nw, nv);
+    if (o.tag && in->tag) {
+      if (o.tag != in->tag &&
+          cudaMemcpyAsync(o.tag, in->tag, ns, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        rc = SPHB200_ECUDA;
+      o.tag = nullptr;
+    }
+    if (!rc) rc = sphb200_engine_download(e, &o, 0, stream);
+  }
   if (!rc && err)
     rc = cudaMemcpyAsync(err, e->err, 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) == cudaSuccess
              ? SPHB200_OK : SPHB200_ECUDA;
-  sphb200_engine_destroy(e);
+  if (!rc) rc = cudaMemsetAsync(e->err, 0, 4, (cudaStream_t)stream) == cudaSuccess ? SPHB200_OK : SPHB200_ECUDA;
+  if (rc) {  // never keep an engine in an unknown state
+    sphb200_engine_destroy(e);
+    slot->e = nullptr;
+  }
   return rc;
+}
+
+void sphb200_workspace_release(void* ws) {
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  for (CachedEngine& c : g_cache)
+    if (c.e && (ws == nullptr || c.ws == ws)) {
+      sphb200_engine_destroy(c.e);
+      c.e = nullptr;
+    }
 }
 
 int sphb200_forward(const sphb200_config* cfg, int64_t n, const sphb200_state* in,
@@ -2238,6 +2371,13 @@ int sphb200_advance(const sphb200_config* cfg, int64_t n, double dt, const sphb2
                     sphb200_state* out, uint32_t* err, void* ws, size_t ws_bytes, void* stream) {
   return stateless_step(cfg, n, dt, SPHB200_STEP_INTEGRATE | SPHB200_STEP_BC, in, out, err, ws,
                         ws_bytes, stream);
+}
+
+int sphb200_advance_persistent(const sphb200_config* cfg, int64_t n, double dt,
+                               const sphb200_state* in, sphb200_state* out, uint32_t* err, void* ws,
+                               size_t ws_bytes, void* stream) {
+  return stateless_step(cfg, n, dt, SPHB200_STEP_INTEGRATE | SPHB200_STEP_BC, in, out, err, ws,
+                        ws_bytes, stream, true);
 }
 
 }  // extern "C"

@@ -285,6 +285,14 @@ class Engine:
         self._keep = keep
         _lib.check(self.lib.sphb200_engine_upload(self._h, C.byref(st), int(on_host), _stream_ptr()))
 
+    def refresh(self, state: Dict):
+        """Upload a state of the SAME particles (row i is still particle i) into the slots they
+        occupy: the cell table and the neighbour lists are kept as far as the new positions allow
+        (sphb200_engine_refresh).  Before the first step it is an ordinary upload."""
+        st, on_host, keep = self._state_struct(state, writable=False)
+        self._keep = keep
+        _lib.check(self.lib.sphb200_engine_refresh(self._h, C.byref(st), int(on_host), _stream_ptr()))
+
     def step(self, dt: float, nsteps: int = 1, integrate: bool = True, bc: bool = True):
         flags = (_lib.STEP_INTEGRATE if integrate else 0) | (_lib.STEP_BC if bc else 0)
         _lib.check(self.lib.sphb200_engine_step(self._h, float(dt), int(nsteps), flags, _stream_ptr()))

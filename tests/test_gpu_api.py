@@ -111,6 +111,64 @@ def test_stateless_advance_equals_resident_engine_bitwise():
         assert torch.equal(out[k], ref[k]), k
 
 
+def test_persistent_workspace_advance_is_the_resident_engine():
+    """sphb200_advance_persistent with the same workspace call after call: bitwise the resident
+    engine's trajectory (same slots, same lists, same decisions); and a state that has nothing to
+    do with the previous call (rows permuted) still gives that state's own result."""
+    import torch
+
+    from jax_sph_b200 import Engine, _lib, config_from_setup
+    from oracle import integrator as oint
+
+    setup = _case(case="tgv", dim=3, dx=2 * np.pi / 16, tvf=1.0, viscosity=0.02, r0_noise_factor=0.25)
+    n = len(setup.state["r"])
+    cfg = config_from_setup(setup)
+    nsteps = 12
+    eng = Engine(cfg, n)
+    eng.upload(setup.state)
+    eng.step(setup.dt, nsteps)
+    ref = eng.download()
+    assert 1 <= eng.counters()["searches"] < nsteps
+    lib = _lib.load()
+    nbytes = C.c_size_t()
+    _lib.check(lib.sphb200_workspace_bytes(C.byref(cfg), n, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+    bufs = [_to_cuda(setup.state), {k: torch.empty_like(v) for k, v in _to_cuda(setup.state).items()}]
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def struct(d):
+        st = _lib.State()
+        for k, v in d.items():
+            setattr(st, k, v.data_ptr())
+        return st
+
+    def call(src, dst):
+        _lib.check(lib.sphb200_advance_persistent(
+            C.byref(cfg), n, float(setup.dt), C.byref(struct(src)), C.byref(struct(dst)),
+            C.c_void_p(err.data_ptr()), C.c_void_p(ws.data_ptr()), nbytes.value,
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    for i in range(nsteps):
+        call(bufs[i % 2], bufs[(i + 1) % 2])
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    got = bufs[nsteps % 2]
+    for k in ("r", "u", "v", "rho", "p", "dudt", "dvdt", "tag", "mass"):
+        assert torch.equal(got[k], ref[k]), k
+    # same workspace, unrelated state: the rows of the start state in another order
+    perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    shuffled = {k: v[perm].contiguous() for k, v in _to_cuda(setup.state).items()}
+    out = {k: torch.empty_like(v) for k, v in shuffled.items()}
+    call(shuffled, out)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    lib.sphb200_workspace_release(C.c_void_p(ws.data_ptr()))
+    one = oint.simulate(setup, 1, fast_segment_sum=True)
+    p = perm.cpu().numpy()
+    for k in ("r", "u", "v", "rho", "p", "dudt", "dvdt"):
+        assert_close(k, out[k].cpu().numpy(), one[k][p], setup, what="unrelated state, same workspace")
+
+
 def test_determinism_and_host_pointer_path():
     import torch
 

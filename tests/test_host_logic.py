@@ -195,3 +195,27 @@ def test_cpu_arm_worker_and_aggregation(monkeypatch):
     assert 0 < r["value"] <= 2 * r["per_core"] * 1.0001
     base = bench.cpu_baseline(args)
     assert base["cores"] == 2 and base["kind"] == "port" and "2 single-core workers" in base["sample"]
+
+
+def test_bench_db2d_generator_is_the_reference_case():
+    """bench.py's generator of BASELINE configs[2] (2D dam break) lays out the particles, tags,
+    fields, dt, box and bc / g_ext tables of the case setup (oracle.cases.make_case, itself pinned
+    against SimulationSetup.initialize by tests/test_reference_pins.py), bit for bit."""
+    import bench
+    from oracle import cases
+
+    dx = 0.02
+    state, meta = bench.db2d_state(dx)
+    setup = cases.make_case("db", dim=2, dx=dx, dtype=np.float32)
+    assert len(state["r"]) == len(setup.state["r"])
+    for k, v in state.items():
+        assert np.array_equal(v, setup.state[k]), k
+    assert meta["dt"] == setup.dt and np.allclose(meta["box"], setup.box_size, rtol=0, atol=1e-12)
+    assert meta["cfg_kwargs"]["bc_table"] == setup.bc_table
+    assert meta["cfg_kwargs"]["g_ext_spec"] == setup.g_ext_spec
+    assert setup.is_bc_trick and setup.density_evolution and setup.artificial_alpha == 0.1
+    # BASELINE.md: 4 028 622 particles at dx = 0.00071 (counted, not generated here)
+    n_f = round(2.0 / 0.00071) * round(1.0 / 0.00071)
+    dxn = 3 * 0.00071
+    n_w = 2 * round(dxn / 0.00071) * round((2.0 + 2 * dxn) / 0.00071) + 2 * round(5.366 / 0.00071) * 3
+    assert n_f + n_w == 4028622
