@@ -94,6 +94,9 @@ struct Extra {
   int finalT;      // this sweep integrates T (no wall sweep follows)
   int heat, av, bc_on, free_slip, bc_trick;
   int delta;       // DELTA solver: velocity diffusion term of acceleration_delta_fn
+  // compact force records of every slot (duo force sweep: staged by bulk copies, sweep2.cuh)
+  float4 *rec0, *rec1, *rec2;
+  float* rec_e;
   // neighbour-list materialiser
   int* nl_counts;
   const int* nl_offsets;
@@ -372,6 +375,10 @@ __device__ __forceinline__ F2 sel2(bool v0, bool v1, F2 a) { return f2(v0 ? lo(a
 __device__ __forceinline__ F2 disp2_nowrap(float a, F2 b, float half) {
   return sub2(add2(sub2(f2(a), b), f2(half)), f2(half));
 }
+// ... and of two own particles against one neighbour coordinate
+__device__ __forceinline__ F2 disp2_nowrap2(F2 a, float b, float half) {
+  return sub2(add2(sub2(a, f2(b)), f2(half)), f2(half));
+}
 // sumsq of two displacements: products packed, the two adds scalar and unfused (space.py:184-192)
 template <int DIM>
 __device__ __forceinline__ F2 sumsq2(const F2 (&d)[3]) {
@@ -398,8 +405,10 @@ __device__ __forceinline__ F2 fsqrt2(F2 a) {
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(hi(a)));
   const F2 r = f2(r0, r1);
   const F2 s = mul2(a, r);
-  const F2 e = fma2(mul2(s, f2(-1.0f)), s, a);
-  return fma2(e, mul2(r, f2(0.5f)), s);
+  // s + (a - s s) r / 2 as s - (s s - a)(r / 2): the residual is one FFMA2 (ptxas folds the
+  // subtraction into the product), no separate negation
+  const F2 t = sub2(mul2(s, s), a);
+  return fma2(t, mul2(r, f2(-0.5f)), s);
 }
 #endif
 
@@ -441,6 +450,54 @@ __device__ __forceinline__ F2 kernel_gw2(const Consts& c, F2 r) {
   } else {
     return f2(kernel_gw<KERN>(c, lo(r)), kernel_gw<KERN>(c, hi(r)));
   }
+}
+
+// ---------------------------------------------------------------------------
+// Bulk asynchronous copies global -> shared (the 1-D form of TMA: cp.async.bulk, SASS UBLKCP) that
+// signal an mbarrier in shared memory with the bytes they delivered.  Addresses and sizes are
+// multiples of 16 bytes.
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// orders this thread's earlier generic-proxy accesses of shared memory (and, through a preceding
+// barrier, the block's) before its later asynchronous copies into the same memory
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// one arrival + `bytes` more expected from the copies of the current phase
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                         unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+// asynchronous 4-byte copy global -> shared (LDGSTS) and the wait for all of this thread's
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
 }
 
 // eos.py:33-38 / :53-57

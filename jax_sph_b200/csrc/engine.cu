@@ -27,6 +27,7 @@
 #include "phys.cuh"
 #include "slab.cuh"
 #include "sweep.cuh"
+#include "sweep2.cuh"
 
 using namespace sphb200;
 
@@ -86,6 +87,14 @@ struct sphb200_engine {
   int nscan_blocks;
   int tpb, lcap;
   SweepPlan planA, planR, planW, planC, planN, planB;
+  // duo sweeps (sweep2.cuh): two slot neighbours per thread on one union list; the headline SPH
+  // variants (summation density, compact force record, no wall / renormalisation sweep)
+  bool duo;
+  int duo_tpb, duo_lmax, duo_rows, duo_desc_stride;
+  float4 *rec0, *rec1, *rec2;  // compact force records of every slot
+  float* rec_e;
+  int* duo_desc;               // tile descriptors
+  SweepPlan planDB, planDA;  // search, density filter (the force plan depends on tvf: forward_stage)
   bool has_kc, has_nw, has_ut, has_ge;
   int64_t launches;
   bool profile;
@@ -194,7 +203,7 @@ double plan_skin(const sphb200_config& c) {
 }
 
 void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nranks = 1,
-               double skin_frac = 0.0) {
+               double skin_frac = 0.0, int duo_tpb = 0) {
   const double cutoff = kernel_cutoff(c) * (1.0 + skin_frac);  // what the cells and the search cover
   double pop = 1.0;
   g.exact_all = 0;
@@ -226,7 +235,10 @@ void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nran
     g.T[a] = t;
   }
   while (g.T[1] * g.T[2] > MAX_RUNS) (g.T[2] > 1 ? g.T[2] : g.T[1])--;
-  int t0 = c.tile[0] > 0 ? c.tile[0] : (int)floor(0.93 * tpb / (pop * g.T[1] * g.T[2]) + 0.5);
+  // particles a block wants: one per thread, or two per thread of a duo sweep (with room for the
+  // half-filled duo that ends every odd run)
+  const double want_pop = duo_tpb > 0 ? 0.90 * 2.0 * duo_tpb : 0.93 * tpb;
+  int t0 = c.tile[0] > 0 ? c.tile[0] : (int)floor(want_pop / (pop * g.T[1] * g.T[2]) + 0.5);
   if (t0 < 1) t0 = 1;
   if (t0 > g.n[0]) t0 = g.n[0];
   // MAX_SOFF bound on staged (row, cell) entries
@@ -243,9 +255,22 @@ void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nran
     // sweep with the largest record (sweep.cuh, NList): shorten the tile until the expected
     // stencil population (+8 % for disorder) fits what 227 KB of shared memory hold next to the
     // minimum per-thread lists.
-    const double fit = ((227.0 * 1024 - 1024) - (double)sweep_smem_bytes(0, 0, 24, tpb)) /
+    const double fit = ((227.0 * 1024 - 1024) - (duo_tpb > 0 ? (double)duo_smem_bytes(0, 0, 0)
+                                                             : (double)sweep_smem_bytes(0, 0, 24, tpb))) /
                        max_stage_bytes(c);
-    while (t0 > 2 && entries(t0) * pop * 1.08 > fit) --t0;
+    // (duo sweeps have no second staging group to fall back on inside the kernel: a stencil that
+    // does not fit is swept by the slow per-particle search, so the bound also covers the most
+    // a LATTICE start can put into the stencil, one more plane per axis than the mean)
+    auto lattice_max = [&](int t) {
+      double m = 1.0;
+      for (int a = 0; a < c.dim; ++a) {
+        const int len = a == 0 ? ((g.n[0] >= 2 * g.S[0] + 1) ? t + 2 * g.S[0] : g.n[0])
+                               : ((g.n[a] >= 2 * g.S[a] + 1) ? g.T[a] + 2 * g.S[a] : g.n[a]);
+        m *= floor(len * (c.box[a] / g.n[a]) / c.dx) + 1.0;
+      }
+      return m + 1.0;
+    };
+    while (t0 > 2 && (entries(t0) * pop * 1.08 > fit || (duo_tpb > 0 && lattice_max(t0) > fit))) --t0;
   }
   g.T[0] = t0;
   for (int a = 0; a < 3; ++a) {
@@ -338,11 +363,18 @@ bool bc_table_on(const sphb200_config& c) {
   return c.bc_inflow_on || c.bc_outflow_on;
 }
 
+// duo sweeps (sweep2.cuh): whether this engine uses them and with what
+struct DuoPlan {
+  bool on;
+  int tpb, lmax, rows, desc_stride;
+};
+
 struct Layout {
   size_t frame[2][12];
   size_t key, rnk, src, count, start, bsum, maxocc, wallcount, err, stats, nl_counts, ut;
   size_t pl_list, pl_cnt, pl_ok, sl_list, sl_cnt, path, ctl;
   size_t dl, dg;  // Delta-SPH density diffusion (PhysDelta)
+  size_t rec, desc;  // duo sweeps: compact force records (52 B per slot), tile descriptors
   int pl_lmax;
   size_t dn;
   size_t total;
@@ -368,7 +400,8 @@ int plan_lmax(const sphb200_config& c, double skin_frac) {
   return lmax;
 }
 
-void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, double skin_frac, Layout& L) {
+void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, double skin_frac, Layout& L,
+                 const DuoPlan& dp) {
   bool kc, nw, ut, ge;
   feature_flags(c, kc, nw, ut, ge);
   size_t off = 0;
@@ -409,9 +442,14 @@ void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, double skin_
     L.pl_cnt = take((size_t)n * 4);
     L.sl_list = take((size_t)n * L.pl_lmax * 2);
     L.sl_cnt = take((size_t)n * 4);
-    L.pl_ok = take((size_t)g.nt[0] * g.nt[1] * g.nt[2]);
+    L.pl_ok = take((size_t)g.ncells);  // one flag per tile; sized for any tiling of the cells
   } else {
     L.pl_list = L.pl_cnt = L.pl_ok = L.sl_list = L.sl_cnt = (size_t)-1;
+  }
+  L.rec = L.desc = (size_t)-1;
+  if (dp.on) {
+    L.rec = take((size_t)n * 52);
+    L.desc = take((size_t)g.nt[0] * g.nt[1] * g.nt[2] * dp.desc_stride * 4);
   }
   L.total = off;
 }
@@ -461,12 +499,13 @@ template <class K>
 int launch_sweep(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f, const Extra& ex,
                  cudaStream_t st,
                  const NList& nl = NList{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr},
-                 const int* gate = nullptr, bool persistent = false, bool fresh = false) {
+                 const int* gate = nullptr, bool persistent = false, bool fresh = false,
+                 int gate_want = 1) {
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
   // a sweep may stage fewer bytes than its plan was sized for, never more
   const int sb = ex.sb > 0 ? ex.sb : 16 * ex.nq;
   if (sb > sp.sb) return SPHB200_EINVAL;
-  SweepDims sd{sp.cap, sp.lcap, sb, gate, 1};
+  SweepDims sd{sp.cap, sp.lcap, sb, gate, gate_want};
   const int all = e->grid.nt[0] * e->grid.nt[1] * e->grid.nt[2];
   Grid g = e->grid;
   if (fresh) g.c2_fb = g.c2_hi;
@@ -496,6 +535,81 @@ int launch_sweep(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f,
   }
   CK(cudaGetLastError());
   return SPHB200_OK;
+}
+
+// duo sweeps (sweep2.cuh): same tile ranges and gate protocol as launch_sweep
+template <class K>
+int launch_duo(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f, const Extra& ex,
+               cudaStream_t st, const DuoList& dl, const int* gate = nullptr, bool persistent = false) {
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
+  const int sb = ex.sb > 0 ? ex.sb : 16 * ex.nq;
+  if (sb > sp.sb) return SPHB200_EINVAL;
+  SweepDims sd{sp.cap, sp.lcap, sb, gate, 1};
+  const int all = e->grid.nt[0] * e->grid.nt[1] * e->grid.nt[2];
+  Grid g = e->grid;
+  int resident = 0;
+  if (persistent) {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, e->duo_tpb, sp.smem));
+    resident = (per_sm > 0 ? per_sm : 1) * e->num_sms;
+  }
+  const int ax = e->dim - 1, nl_ax = g.nt[ax], per_layer = all / nl_ax;
+  int ranges[2][2] = {{0, nl_ax}, {0, 0}};
+  if (e->part == 1) {
+    ranges[0][0] = e->int_lo; ranges[0][1] = e->int_hi;
+  } else if (e->part == 2) {
+    ranges[0][0] = 0; ranges[0][1] = e->int_lo;
+    ranges[1][0] = e->int_hi; ranges[1][1] = nl_ax;
+  }
+  for (int r = 0; r < 2; ++r) {
+    const int blocks = (ranges[r][1] - ranges[r][0]) * per_layer;
+    if (blocks <= 0) continue;
+    g.block0 = ranges[r][0] * per_layer;
+    g.ntl = blocks;
+    const int grid = (persistent && blocks > resident) ? resident : blocks;
+    kern<<<grid, e->duo_tpb, sp.smem, st>>>(g, e->consts, f, e->start, sd, ex, e->err, dl);
+    e->launches++;
+  }
+  CK(cudaGetLastError());
+  return SPHB200_OK;
+}
+
+// staging capacity of a duo sweep: what the tile's stencil is expected to hold (+30 %), bounded by
+// shared memory and by the 14 index bits of a list entry
+SweepPlan plan_duo(const sphb200_engine* e, int sb, int lcap) {
+  const Grid& g = e->grid;
+  const sphb200_config& c = e->cfg;
+  double pop = 1.0;
+  for (int a = 0; a < c.dim; ++a) pop *= (c.box[a] / g.ng[a]) / c.dx;
+  int rows = 1;
+  for (int a = 1; a < 3; ++a) rows *= (g.n[a] >= 2 * g.S[a] + 1) ? g.T[a] + 2 * g.S[a] : g.n[a];
+  const int nxs = (g.n[0] >= 2 * g.S[0] + 1) ? g.T[0] + 2 * g.S[0] : g.n[0];
+  long long want = (long long)(rows * (double)nxs * pop * 1.3) + 64;
+  if (c.stage_cap > 0) want = c.stage_cap;
+  if (want > e->n + 32) want = e->n + 32;
+  const long long fit = ((long long)e->max_smem - (long long)duo_smem_bytes(0, 0, lcap)) / sb;
+  if (want > fit) want = fit;
+  if (want > DUO_IDX + 1) want = DUO_IDX + 1;
+  want = want / 32 * 32;
+  if (want < 32) want = 32;
+  SweepPlan p;
+  p.sb = sb;
+  p.cap = (int)want;
+  p.lcap = lcap;
+  p.smem = duo_smem_bytes(sb, p.cap, lcap);
+  return p;
+}
+
+// the solver variants the duo sweeps cover: SPH with summation density and the compact force
+// record (phys.cuh: DENS_SUM, FORCE_PLAIN / FORCE_TVF), nothing between the two sweeps
+bool duo_variant(const sphb200_config& c) {
+  const char* env = getenv("SPHB200_DUO");
+  if (env && env[0] == '0') return false;
+  if (c.solver != SPHB200_SOLVER_SPH || c.nl_cap < 0) return false;
+  if (c.flags & (SPHB200_F_BC_TRICK | SPHB200_F_RHO_EVOL | SPHB200_F_RHO_RENORM | SPHB200_F_HEAT |
+                 SPHB200_F_FREE_SLIP))
+    return false;
+  return c.artificial_alpha == 0.0;
 }
 
 Extra make_extra() {
@@ -745,8 +859,55 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
     if (wall_sweep && e->planC.cap < mc) mc = e->planC.cap;
     nl.min_cap = mc;
   }
+  // duo sweeps (sweep2.cuh) for the tiles whose stencil fits; the others are left to sweep.cuh
+  // kernels that search on their own (nlb: no lists, skip the ok tiles), launched on a small
+  // persistent grid and only when the search counted such tiles (ctl[4])
+  const int ntiles = e->grid.nt[0] * e->grid.nt[1] * e->grid.nt[2];
+  SweepPlan planDF = planF;
+  DuoList dl{e->duo_desc, e->duo_desc_stride, e->sl_list, e->pl_list, e->sl_cnt, e->pl_cnt,
+             e->pl_ok,    e->duo_lmax,        0,          e->duo_rows};
+  NList nlb{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, e->pl_ok};
+  int* const nbad = e->ctl + 4;
+  // bytes of the duo force record in shared memory (phys.cuh, PhysForce: FORCE_PLAIN keeps eta and
+  // (m/rho)^2 in a third quad there)
+  const int duo_force_sb = force_feat == FORCE_TVF ? 52 : 48;
+  if (e->duo) {
+    planDF = plan_duo(e, duo_force_sb, 0);
+    int mc = e->planDB.cap < e->planDA.cap ? e->planDB.cap : e->planDA.cap;
+    if (planDF.cap < mc) mc = planDF.cap;
+    dl.min_cap = mc;
+  }
   // ---- the search (on the steps that re-sorted), then density ---------------
-  if (stage == 0) {
+  if (stage == 0 && e->duo) {
+    Extra exb = make_extra();
+    exb.nq = 1;
+    Frame& F = e->fr[e->cur];
+    const int* gate = e->inplace ? e->gate_cur : nullptr;
+    if (e->dim == 2)
+      rc = launch_duo(e, k_duo<2, PhysNone, DUO_BUILD>, e->planDB, F, exb, st, dl, gate, gate != nullptr);
+    else
+      rc = launch_duo(e, k_duo<3, PhysNone, DUO_BUILD>, e->planDB, F, exb, st, dl, gate, gate != nullptr);
+    if (rc) return rc;
+    k_duo_count_bad<<<1, 1024, 0, st>>>(e->pl_ok, ntiles, nbad, gate);
+    e->launches++;
+    CK(cudaGetLastError());
+    Extra ex = make_extra();
+    ex.finalT = false;
+    ex.st_out = e->fr[1 - e->cur].st;
+    ex.nq = 1;
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysDensity<D, K, DENS_SUM>, DUO_FILTER>, e->planDA, F, ex, st, dl)
+    DISPATCH_DK(e, CALL);
+#undef CALL
+    if (rc) return rc;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysDensity<D, K, DENS_SUM>, LIST_FILTER>, planD, F, ex, st, nlb, nbad, true, false, -1)
+    DISPATCH_DK(e, CALL);
+#undef CALL
+    if (rc) return rc;
+    if (part == 1) return SPHB200_OK;
+    swap_st(e);
+    *wrote = HX_ST;
+    if (e->profile) cudaEventRecord(e->ev[3], st);
+  } else if (stage == 0) {
     const bool first_sub = !(e->slab_on && delta_on && evol && e->delta_sub > 0);
     if (e->pl_lmax > 0 && first_sub) {
       Extra exb = make_extra();
@@ -870,7 +1031,43 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
     ex.bc_trick = bc_trick;
     const SweepPlan& sp = planF;
     Frame& F = e->fr[e->cur];
-    if (!rie) {
+    if (e->duo) {
+      // the compact record of every slot the sweep may stage (own slots; on a slab engine the
+      // halo slots too, once their (rho, p) has arrived: the boundary part of an overlapped step)
+      Extra exd = ex;
+      exd.sb = duo_force_sb;
+      exd.rec0 = e->rec0; exd.rec1 = e->rec1; exd.rec2 = e->rec2; exd.rec_e = e->rec_e;
+      {
+        const int mode = !e->slab_on ? 0 : (part == 1 ? 1 : (part == 2 ? 2 : 0));
+        const int nb = stream_blocks(e, e->n);
+        if (e->dim == 2) {
+          if (force_feat == FORCE_PLAIN) k_force_rec<PhysForce<2, SPHB200_KERNEL_QSK, SPHB200_SOLVER_SPH, FORCE_PLAIN>><<<nb, 256, 0, st>>>(e->n, e->slab, mode, F, exd);
+          else k_force_rec<PhysForce<2, SPHB200_KERNEL_QSK, SPHB200_SOLVER_SPH, FORCE_TVF>><<<nb, 256, 0, st>>>(e->n, e->slab, mode, F, exd);
+        } else {
+          if (force_feat == FORCE_PLAIN) k_force_rec<PhysForce<3, SPHB200_KERNEL_QSK, SPHB200_SOLVER_SPH, FORCE_PLAIN>><<<nb, 256, 0, st>>>(e->n, e->slab, mode, F, exd);
+          else k_force_rec<PhysForce<3, SPHB200_KERNEL_QSK, SPHB200_SOLVER_SPH, FORCE_TVF>><<<nb, 256, 0, st>>>(e->n, e->slab, mode, F, exd);
+        }
+        e->launches++;
+        CK(cudaGetLastError());
+      }
+      if (force_feat == FORCE_PLAIN) {
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>, DUO_CONSUME>, planDF, F, exd, st, dl)
+        DISPATCH_DK(e, CALL);
+#undef CALL
+        if (rc) return rc;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>, LIST_CONSUME>, sp, F, ex, st, nlb, nbad, true, false, -1)
+        DISPATCH_DK(e, CALL);
+#undef CALL
+      } else {
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF>, DUO_CONSUME>, planDF, F, exd, st, dl)
+        DISPATCH_DK(e, CALL);
+#undef CALL
+        if (rc) return rc;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF>, LIST_CONSUME>, sp, F, ex, st, nlb, nbad, true, false, -1)
+        DISPATCH_DK(e, CALL);
+#undef CALL
+      }
+    } else if (!rie) {
       const int feat = force_feat;
       if (feat == FORCE_PLAIN) {
 #define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>, LIST_CONSUME>, sp, F, ex, st, nl)
@@ -1053,6 +1250,54 @@ __global__ void __launch_bounds__(256) k_get_stats(int n, Slab sl, Frame f, doub
   }
 }
 
+bool duo_variant(const sphb200_config& c);
+
+// Grid + duo decision of an engine for n particle slots (every entry point that sizes or creates
+// an engine plans through here, so that they agree on the tiling).
+void plan_all(const sphb200_config& c, int64_t n, int rank, int nranks, Grid& g, DuoPlan& dp) {
+  const int tpb = c.threads > 0 ? (c.threads + 31) / 32 * 32 : DEFAULT_TPB;
+  const double skin = plan_skin(c);
+  dp.on = duo_variant(c);
+  dp.tpb = dp.lmax = dp.rows = dp.desc_stride = 0;
+  if (dp.on) {
+    // tuned on B200 (profiles/r02_duo_*): one block per SM holds the force record of the stencil
+    dp.tpb = c.dim == 3 ? 352 : 256;
+    if (const char* env = getenv("SPHB200_DUO_TPB")) {
+      const int v = atoi(env);
+      if (v >= 32 && v <= DUO_MAXT) dp.tpb = (v + 31) / 32 * 32;
+    }
+  }
+  plan_grid(c, g, tpb > 512 ? 512 : tpb, rank, nranks, skin, dp.tpb);
+  if (!dp.on) return;
+  // the union window of a duo (first particle's window start to the second one's window end)
+  // must not wrap onto itself, and the tile tables must fit
+  bool fits = !g.exact_all && g.n[0] >= g.T[0] + 2 * g.S[0] && g.T[1] * g.T[2] <= DUO_RUNS;
+  for (int a = 1; a < c.dim; ++a) fits = fits && g.n[a] >= 2 * g.S[a] + 1;
+  // Duo list rows live in the buffers of the per-particle lists: about half as many rows (one
+  // per duo; sweep2.cuh numbers them ceil((slot + run ordinal) / 2)), each the union of two
+  // neighbour sets (1.23 x one set for slot neighbours one spacing apart, 1.75 x at worst).
+  const int pl_lmax = plan_lmax(c, skin);
+  const long long runs = (long long)g.n[1] * g.n[2] * g.nt[0];
+  const long long rows = (n + runs) / 2 + 2;
+  const double q = kernel_cutoff(c) * (1.0 + skin) / c.dx;
+  const double expect = c.dim == 2 ? M_PI * q * q : 4.0 / 3.0 * M_PI * q * q * q;
+  long long lmax = ((long long)(1.3 * 1.4 * expect) + 8 + 7) / 8 * 8;
+  const long long room = pl_lmax > 0 ? (long long)n * pl_lmax / rows / 8 * 8 : 0;
+  if (lmax > room) lmax = room;
+  int srows = 1;
+  for (int a = 1; a < 3; ++a) srows *= (g.n[a] >= 2 * g.S[a] + 1) ? g.T[a] + 2 * g.S[a] : g.n[a];
+  const int stride = duo_desc_ints(srows);
+  fits = fits && rows <= n && lmax >= 16 && stride <= DUO_SOFF;
+  dp.rows = (int)rows;
+  dp.lmax = (int)lmax;
+  dp.desc_stride = stride;
+  if (!fits) {
+    dp.on = false;
+    dp.tpb = dp.lmax = dp.rows = dp.desc_stride = 0;
+    plan_grid(c, g, tpb > 512 ? 512 : tpb, rank, nranks, skin, 0);
+  }
+}
+
 struct SlabSpec {
   int rank, nranks;
   int own_cap, halo_cap, mig_cap;
@@ -1089,7 +1334,13 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   if (e->lcap < SWEEP_CHUNK) e->lcap = SWEEP_CHUNK;
   e->inplace = true;
   e->skin_frac = plan_skin(*cfg);
-  plan_grid(*cfg, e->grid, e->tpb, e->slab_rank, e->slab_nranks, e->skin_frac);
+  DuoPlan dp;
+  plan_all(*cfg, n, e->slab_rank, e->slab_nranks, e->grid, dp);
+  e->duo = dp.on;
+  e->duo_tpb = dp.tpb;
+  e->duo_lmax = dp.lmax;
+  e->duo_rows = dp.rows;
+  e->duo_desc_stride = dp.desc_stride;
   // half the skin, minus a margin for the rounding of positions and of the accumulated path
   e->path_limit = e->skin_frac > 0.0 ? (float)(0.5 * e->skin_frac * kernel_cutoff(*cfg) * (1.0 - 1e-3)) : -1.0f;
   e->step_no = 0;
@@ -1101,7 +1352,7 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   plan_consts(*cfg, e->consts);
   feature_flags(*cfg, e->has_kc, e->has_nw, e->has_ut, e->has_ge);
   Layout L;
-  plan_layout(*cfg, n, e->grid, e->skin_frac, L);
+  plan_layout(*cfg, n, e->grid, e->skin_frac, L, dp);
   if (ws_bytes < L.total) return SPHB200_ENOMEM;
   e->arena = (char*)ws;
   e->arena_bytes = L.total;
@@ -1148,6 +1399,16 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->sl_cnt = L.pl_lmax ? (int*)(e->arena + L.sl_cnt) : nullptr;
   e->rb = (float4*)(e->arena + L.path);
   e->ctl = (int*)(e->arena + L.ctl);
+  e->rec0 = e->rec1 = e->rec2 = nullptr;
+  e->rec_e = nullptr;
+  e->duo_desc = nullptr;
+  if (dp.on) {
+    e->rec0 = (float4*)(e->arena + L.rec);
+    e->rec1 = e->rec0 + n;
+    e->rec2 = e->rec1 + n;
+    e->rec_e = (float*)(e->rec2 + n);
+    e->duo_desc = (int*)(e->arena + L.desc);
+  }
   e->dn = (int*)(e->arena + L.dn);
   memset(&e->slab, 0, sizeof(e->slab));
   memset(&e->sgeom, 0, sizeof(e->sgeom));
@@ -1183,6 +1444,10 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->planC = plan_sweep(e, 4, lc);
   e->planN = plan_sweep(e, 2, e->lcap);
   e->planB = plan_sweep(e, 1, e->lcap);
+  if (e->duo) {
+    e->planDB = plan_duo(e, 16, e->lcap);
+    e->planDA = plan_duo(e, 16, 0);
+  }
   e->needs_zero = true;  // control words are zeroed on the first upload's stream
   return SPHB200_OK;
 }
@@ -1276,9 +1541,10 @@ int sphb200_engine_bytes(const sphb200_config* cfg, int64_t n, size_t* bytes) {
   if (!bytes) return SPHB200_EINVAL;
   Grid g;
   const double skin = plan_skin(*cfg);
-  plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : DEFAULT_TPB, 0, 1, skin);
+  DuoPlan dp;
+  plan_all(*cfg, n, 0, 1, g, dp);
   Layout L;
-  plan_layout(*cfg, n, g, skin, L);
+  plan_layout(*cfg, n, g, skin, L, dp);
   *bytes = L.total;
   return SPHB200_OK;
 }
@@ -1867,7 +2133,7 @@ int sphb200_engine_plan(const sphb200_engine* e, int32_t out[16]) {
     out[3 + a] = e->grid.S[a];
     out[6 + a] = e->grid.T[a];
   }
-  out[9] = e->tpb;
+  out[9] = e->duo ? e->duo_tpb : e->tpb;
   out[10] = e->lcap;
   out[11] = e->planA.cap;
   out[12] = e->planW.cap;
@@ -1892,7 +2158,8 @@ int sphb200_engine_counters(sphb200_engine* e, int64_t out[8], void* stream) {
   for (int i = 0; i < 8; ++i) out[i] = 0;
   out[0] = (int64_t)e->step_no;
   out[1] = h[2];
-  out[2] = e->pl_lmax;
+  out[2] = e->duo ? e->duo_lmax : e->pl_lmax;
+  out[6] = e->duo ? 1 : 0;
   out[3] = (int64_t)(e->skin_frac * 1e6 + 0.5);
   out[4] = tiles;
   out[5] = e->pl_ok ? h[3] : tiles;
@@ -1971,9 +2238,10 @@ int sphb200_slab_create(const sphb200_config* cfg, int rank, int nranks, int64_t
   rc = slab_spec(cfg, rank, nranks, own_cap, halo_cap, mig_cap, &sp);
   if (rc) return rc;
   Grid g;
-  plan_grid(*cfg, g, cfg->threads > 0 ? cfg->threads : DEFAULT_TPB, rank, nranks, plan_skin(*cfg));
+  DuoPlan dp;
+  plan_all(*cfg, slab_slots(sp), rank, nranks, g, dp);
   Layout L;
-  plan_layout(*cfg, slab_slots(sp), g, plan_skin(*cfg), L);
+  plan_layout(*cfg, slab_slots(sp), g, plan_skin(*cfg), L, dp);
   void* ws = nullptr;
   if (cudaMalloc(&ws, L.total) != cudaSuccess) return SPHB200_ENOMEM;
   sphb200_engine* e = new (std::nothrow) sphb200_engine();

@@ -35,6 +35,12 @@ struct PhysNone {
   static constexpr bool SENDER_VIEW = false;
   static constexpr bool SPARSE = false;
   static constexpr bool HAS_PAIR2 = false;
+  static constexpr bool HAS_DUO = false;
+  static constexpr int DUO_MINB = 2;
+  static constexpr int DUO_COPIES = 1;  // positions, as they lie in the frame
+  static constexpr bool DUO_REST = false;
+  __device__ static void duo_sources(const Frame& f, const Extra&, const float4* (&a)[1]) { a[0] = f.pt; }
+  __device__ static void stage_rest(const Consts&, const Frame&, const Extra&, int, float4*, int, int) {}
   struct Own {};
   struct Acc {};
   template <class F>
@@ -96,6 +102,31 @@ struct PhysDensity {
   __device__ static void fold(const Acc2& a2, Acc& a) {
     init(a);
     a.s = lo(a2.s) + hi(a2.s);
+  }
+  // plain summation: packed body of the duo sweeps (sweep2.cuh): the two particles of a duo in
+  // the two halves, one neighbour per call
+  static constexpr bool HAS_DUO = MODE == DENS_SUM;
+  static constexpr int DUO_MINB = MODE == DENS_SUM ? 2 : 1;
+  static constexpr int DUO_COPIES = MODE == DENS_SUM ? 1 : 0;  // positions, as they lie in the frame
+  static constexpr bool DUO_REST = false;
+  __device__ static void duo_sources(const Frame& f, const Extra&, const float4* (&a)[1]) { a[0] = f.pt; }
+  __device__ static void stage_rest(const Consts&, const Frame&, const Extra&, int, float4*, int, int) {}
+  struct OwnD {};
+  struct AccD {
+    F2 s;
+  };
+  __device__ static void load_duo(const Own&, const Own&, OwnD&) {}
+  __device__ static void init_duo(AccD& a) { a.s = f2(0.0f); }
+  __device__ static void pair_duo(const Consts& c, const Extra&, const OwnD&, AccD& a,
+                                  const float4*, int, int, float4, const F2 (&)[3], F2 d2, bool v0,
+                                  bool v1) {
+    add2_into(a.s, sel2(v0, v1, kernel_w2<KERN>(c, fsqrt2(d2))));
+  }
+  __device__ static void fold_duo(const AccD& d, Acc& a0, Acc& a1) {
+    init(a0);
+    init(a1);
+    a0.s = lo(d.s);
+    a1.s = hi(d.s);
   }
   __device__ static void stage(const Consts& c, const Frame& f, const Extra& ex, int gp,
                                float4* sq, int cap, int d) {
@@ -249,6 +280,12 @@ struct PhysDelta {
     float m[9];  // STEP 0: M;  STEP 1: G (0..2), H (3..5);  STEP 2: diff (0), cont (1)
   };
   static constexpr bool HAS_PAIR2 = false;
+  static constexpr bool HAS_DUO = false;
+  static constexpr int DUO_MINB = 1;
+  static constexpr int DUO_COPIES = 0;  // arrays the duo sweeps stage by bulk copy (sweep2.cuh)
+  static constexpr bool DUO_REST = false;
+  __device__ static void duo_sources(const Frame&, const Extra&, const float4* (&)[1]) {}
+  __device__ static void stage_rest(const Consts&, const Frame&, const Extra&, int, float4*, int, int) {}
   template <class F>
   __device__ static void each_acc(Acc& a, F f) {
 #pragma unroll
@@ -426,6 +463,12 @@ struct PhysRenorm {
     float num, den;
   };
   static constexpr bool HAS_PAIR2 = false;
+  static constexpr bool HAS_DUO = false;
+  static constexpr int DUO_MINB = 1;
+  static constexpr int DUO_COPIES = 0;  // arrays the duo sweeps stage by bulk copy (sweep2.cuh)
+  static constexpr bool DUO_REST = false;
+  __device__ static void duo_sources(const Frame&, const Extra&, const float4* (&)[1]) {}
+  __device__ static void stage_rest(const Consts&, const Frame&, const Extra&, int, float4*, int, int) {}
   template <class F>
   __device__ static void each_acc(Acc& a, F f) {
     f(a.num); f(a.den);
@@ -471,6 +514,12 @@ struct PhysWall {
     float su[3], sv[3], srr[3];
   };
   static constexpr bool HAS_PAIR2 = false;
+  static constexpr bool HAS_DUO = false;
+  static constexpr int DUO_MINB = 1;
+  static constexpr int DUO_COPIES = 0;  // arrays the duo sweeps stage by bulk copy (sweep2.cuh)
+  static constexpr bool DUO_REST = false;
+  __device__ static void duo_sources(const Frame&, const Extra&, const float4* (&)[1]) {}
+  __device__ static void stage_rest(const Consts&, const Frame&, const Extra&, int, float4*, int, int) {}
   template <class F>
   __device__ static void each_acc(Acc& a, F f) {
     f(a.sw); f(a.sp); f(a.sT);
@@ -658,6 +707,110 @@ struct PhysForce {
     for (int k = 0; k < DIM; ++k) {
       a.a[k] = lo(a2.a[k]) + hi(a2.a[k]);
       a.tv[k] = lo(a2.tv[k]) + hi(a2.tv[k]);
+    }
+  }
+  // The same arithmetic for the two particles of a duo against ONE neighbour (sweep2.cuh): own
+  // values packed once per duo, the neighbour's values broadcast scalars.
+  static constexpr bool HAS_DUO = COMPACT;
+  static constexpr int DUO_MINB = 1;
+  // The duo sweep stages the compact record from per-slot copies of it in HBM (k_force_rec,
+  // Extra::rec*): three quads by bulk copy, and for FORCE_TVF the eta column through registers.
+  //   quad 2 of FORCE_PLAIN there: (eta, (m/rho)^2, 0, 0)
+  static constexpr int DUO_COPIES = COMPACT ? 3 : 0;
+  static constexpr bool DUO_REST = COMPACT && FEAT == FORCE_TVF;
+  __device__ static void duo_sources(const Frame&, const Extra& ex, const float4* (&a)[COMPACT ? 3 : 1]) {
+    if (COMPACT) {
+      a[0] = ex.rec0; a[1] = ex.rec1; a[2] = ex.rec2;
+    }
+  }
+  __device__ static void stage_rest(const Consts&, const Frame&, const Extra& ex, int gp, float4* sq,
+                                    int cap, int d) {
+    cp_async4(reinterpret_cast<float*>(sq + 3 * cap) + d, ex.rec_e + gp);
+  }
+  // the record of one slot, as stage() builds it
+  __device__ static void make_record(const Frame& f, const Extra& ex, int gp) {
+    const float4 pt = f.pt[gp], um = f.um[gp], st = f.st[gp], vv = f.vv[gp];
+    const float vol = um.w / st.x;
+    ex.rec0[gp] = make_float4(pt.x, pt.y, pt.z, st.x);
+    ex.rec1[gp] = make_float4(um.x, um.y, um.z, st.y);
+    if (FEAT == FORCE_TVF) {
+      const float hr = 0.5f * st.x;
+      ex.rec2[gp] = make_float4(hr * (vv.x - um.x), hr * (vv.y - um.y), hr * (vv.z - um.z), vol * vol);
+      ex.rec_e[gp] = vv.w;
+    } else {
+      ex.rec2[gp] = make_float4(vv.w, vol * vol, 0.f, 0.f);
+    }
+  }
+  struct OwnD {
+    F2 u[3];
+    F2 rho, p, eta, eta2, inv_m, V2;
+  };
+  struct AccD {
+    F2 a[3], tv[3];
+  };
+  __device__ static void load_duo(const Own& o0, const Own& o1, OwnD& d) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) d.u[k] = f2(o0.u[k], o1.u[k]);
+    d.rho = f2(o0.rho, o1.rho);
+    d.p = f2(o0.p, o1.p);
+    d.eta = f2(o0.eta, o1.eta);
+    d.eta2 = f2(o0.eta2, o1.eta2);
+    d.inv_m = f2(o0.inv_m, o1.inv_m);
+    d.V2 = f2(o0.V2, o1.V2);
+  }
+  __device__ static void init_duo(AccD& a) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a.a[k] = a.tv[k] = f2(0.0f);
+  }
+  __device__ static void pair_duo(const Consts& c, const Extra&, const OwnD& o, AccD& a,
+                                  const float4* sq, int cap, int j, float4 pj, const F2 (&dr)[3],
+                                  F2 d2, bool v0, bool v1) {
+    const float4 q = sq[cap + j];  // (u_j, p_j)
+    const float rho_j = pj.w, p_j = q.w;
+    float eta_j, V2_j, hx = 0.f, hy = 0.f, hz = 0.f;
+    if (FEAT == FORCE_TVF) {
+      const float4 r = sq[2 * cap + j];
+      hx = r.x; hy = r.y; hz = r.z;
+      V2_j = r.w;
+      eta_j = reinterpret_cast<const float*>(sq + 3 * cap)[j];
+    } else {
+      const float4 ev = sq[2 * cap + j];  // duo layout of FORCE_PLAIN: (eta, (m/rho)^2, -, -)
+      eta_j = ev.x;
+      V2_j = ev.y;
+    }
+    const F2 dist = fsqrt2(d2);
+    const F2 gw = kernel_gw2<KERN>(c, dist);
+    const F2 id = frcp2(add2(dist, f2(c.eps)));
+    const F2 wv = mul2(add2(o.V2, f2(V2_j)), o.inv_m);                      // :205 / :247
+    const F2 cc = sel2(v0, v1, mul2(mul2(wv, gw), id));                     // :206 / :248
+    const F2 eta_ij = mul2(mul2(o.eta2, f2(eta_j)),
+                           frcp2(add2(add2(o.eta, f2(eta_j)), f2(c.eps))));  // :243
+    const F2 p_ij = mul2(fma2(f2(rho_j), o.p, mul2(o.rho, f2(p_j))),
+                         frcp2(add2(o.rho, f2(rho_j))));                     // :244
+    const F2 ncp = mul2(cc, neg2(p_ij)), ce = mul2(cc, eta_ij);
+    F2 cj = f2(0.0f);
+    if (FEAT == FORCE_TVF) {  // c (A_j r)_k = cj u_j[k]   (:250-251)
+      F2 d = mul2(f2(hx), dr[0]);
+      d = fma2(f2(hy), dr[1], d);
+      if (DIM == 3) d = fma2(f2(hz), dr[2], d);
+      cj = mul2(cc, d);
+    }
+    const float uj[3] = {q.x, q.y, q.z};
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+      fma2_into(a.tv[k], cc, dr[k]);                       // sum_j c r  (:199-213, :912-921)
+      fma2_into(a.a[k], ncp, dr[k]);                       // -c p_ij r
+      fma2_into(a.a[k], ce, sub2(o.u[k], f2(uj[k])));      // c eta_ij u_ij
+      if (FEAT == FORCE_TVF) fma2_into(a.a[k], cj, f2(uj[k]));
+    }
+  }
+  __device__ static void fold_duo(const AccD& d, Acc& a0, Acc& a1) {
+    init(a0);
+    init(a1);
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+      a0.a[k] = lo(d.a[k]); a1.a[k] = hi(d.a[k]);
+      a0.tv[k] = lo(d.tv[k]); a1.tv[k] = hi(d.tv[k]);
     }
   }
   static constexpr int CQ = FEAT == FORCE_TVF ? 3 : 2;  // quads of the compact record
@@ -934,6 +1087,12 @@ struct PhysNeighbors {
     int n;
   };
   static constexpr bool HAS_PAIR2 = false;
+  static constexpr bool HAS_DUO = false;
+  static constexpr int DUO_MINB = 1;
+  static constexpr int DUO_COPIES = 0;  // arrays the duo sweeps stage by bulk copy (sweep2.cuh)
+  static constexpr bool DUO_REST = false;
+  __device__ static void duo_sources(const Frame&, const Extra&, const float4* (&)[1]) {}
+  __device__ static void stage_rest(const Consts&, const Frame&, const Extra&, int, float4*, int, int) {}
   template <class F>
   __device__ static void each_acc(Acc&, F) {}
   __device__ static void stage(const Consts&, const Frame& f, const Extra&, int gp, float4* sq,

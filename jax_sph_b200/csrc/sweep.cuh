@@ -42,8 +42,8 @@ struct SweepDims {
   int cap;   // staged particles per block
   int lcap;  // list entries per thread (>= SWEEP_CHUNK)
   int sb;    // bytes staged per particle (16 per quad + scalar columns, see phys.cuh)
-  const int* gate;  // device word; the launch does nothing unless *gate == gate_want (nullptr: always runs)
-  int gate_want;
+  const int* gate;  // device word; the launch does nothing unless *gate == gate_want (nullptr: always
+  int gate_want;    // runs); gate_want < 0: unless *gate != 0
 };
 
 // Neighbour lists in HBM.  Entries are STAGED indices (uint16): every sweep stages a tile's
@@ -65,6 +65,8 @@ struct NList {
   int lmax;              // multiple of 8
   int min_cap;           // smallest staging capacity among the step's sweeps
   int* nbuilds;          // optional device counter, one per LIST_BUILD launch
+  const unsigned char* skip_ok;  // [tiles] or nullptr: tiles marked ok here belong to the duo sweeps
+                                 // (sweep2.cuh); this launch sweeps the others, searching on its own
 };
 
 enum { LIST_NONE = 0, LIST_BUILD = 1, LIST_CONSUME = 2, LIST_FILTER = 3 };
@@ -319,7 +321,7 @@ template <int DIM, class P, int LM = LIST_NONE>
 __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
     k_sweep(const Grid g, const Consts c, const Frame f, const int* __restrict__ cs,
             const SweepDims sd, const Extra ex, unsigned* __restrict__ err, const NList nl) {
-  if (sd.gate != nullptr && *sd.gate != sd.gate_want) return;
+  if (sd.gate != nullptr && (sd.gate_want >= 0 ? *sd.gate != sd.gate_want : *sd.gate == 0)) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int TPB = blockDim.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = TPB >> 5;
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
 
   // a launch covers tiles [block0, block0 + ntl); gated launches use a small persistent grid
   for (int tq = blockIdx.x; tq < g.ntl; tq += gridDim.x) {
+    if (nl.skip_ok != nullptr && nl.skip_ok[tq + g.block0] != 0) continue;
     if (tq != (int)blockIdx.x) __syncthreads();  // readers of the previous tile's tables are done
 
     // ---- tile geometry (uniform) -------------------------------------------
