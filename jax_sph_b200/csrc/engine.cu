@@ -31,10 +31,13 @@
 
 using namespace sphb200;
 
-#define CK(call)                                   \
-  do {                                             \
-    cudaError_t _e = (call);                       \
-    if (_e != cudaSuccess) return SPHB200_ECUDA;   \
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t _e = (call);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      fprintf(stderr, "sphb200: %s at %s:%d\n", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SPHB200_ECUDA;                                                             \
+    }                                                                                   \
   } while (0)
 
 namespace {
@@ -255,7 +258,7 @@ void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nran
     // sweep with the largest record (sweep.cuh, NList): shorten the tile until the expected
     // stencil population (+8 % for disorder) fits what 227 KB of shared memory hold next to the
     // minimum per-thread lists.
-    const double fit = ((227.0 * 1024 - 1024) - (duo_tpb > 0 ? (double)duo_smem_bytes(0, 0, 0)
+    const double fit = ((227.0 * 1024 - 1024) - (duo_tpb > 0 ? (double)duo_smem_bytes(0, 0, 0, 0)
                                                              : (double)sweep_smem_bytes(0, 0, 24, tpb))) /
                        max_stage_bytes(c);
     // (duo sweeps have no second staging group to fall back on inside the kernel: a stencil that
@@ -540,7 +543,9 @@ int launch_sweep(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f,
 // duo sweeps (sweep2.cuh): same tile ranges and gate protocol as launch_sweep
 template <class K>
 int launch_duo(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f, const Extra& ex,
-               cudaStream_t st, const DuoList& dl, const int* gate = nullptr, bool persistent = false) {
+               cudaStream_t st, const DuoList& dl, const int* gate = nullptr, bool persistent = false,
+               int split = 1) {
+  const int threads = e->duo_tpb * split;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.smem));
   const int sb = ex.sb > 0 ? ex.sb : 16 * ex.nq;
   if (sb > sp.sb) return SPHB200_EINVAL;
@@ -550,7 +555,7 @@ int launch_duo(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f, c
   int resident = 0;
   if (persistent) {
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, e->duo_tpb, sp.smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, sp.smem));
     resident = (per_sm > 0 ? per_sm : 1) * e->num_sms;
   }
   const int ax = e->dim - 1, nl_ax = g.nt[ax], per_layer = all / nl_ax;
@@ -567,7 +572,7 @@ int launch_duo(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f, c
     g.block0 = ranges[r][0] * per_layer;
     g.ntl = blocks;
     const int grid = (persistent && blocks > resident) ? resident : blocks;
-    kern<<<grid, e->duo_tpb, sp.smem, st>>>(g, e->consts, f, e->start, sd, ex, e->err, dl);
+    kern<<<grid, threads, sp.smem, st>>>(g, e->consts, f, e->start, sd, ex, e->err, dl);
     e->launches++;
   }
   CK(cudaGetLastError());
@@ -576,7 +581,7 @@ int launch_duo(sphb200_engine* e, K kern, const SweepPlan& sp, const Frame& f, c
 
 // staging capacity of a duo sweep: what the tile's stencil is expected to hold (+30 %), bounded by
 // shared memory and by the 14 index bits of a list entry
-SweepPlan plan_duo(const sphb200_engine* e, int sb, int lcap) {
+SweepPlan plan_duo(const sphb200_engine* e, int sb, int lcap, int blocks_per_sm = 1) {
   const Grid& g = e->grid;
   const sphb200_config& c = e->cfg;
   double pop = 1.0;
@@ -587,7 +592,10 @@ SweepPlan plan_duo(const sphb200_engine* e, int sb, int lcap) {
   long long want = (long long)(rows * (double)nxs * pop * 1.3) + 64;
   if (c.stage_cap > 0) want = c.stage_cap;
   if (want > e->n + 32) want = e->n + 32;
-  const long long fit = ((long long)e->max_smem - (long long)duo_smem_bytes(0, 0, lcap)) / sb;
+  // (a block's share of the SM's shared memory when several are to be resident: 1 KB each is
+  // the system's)
+  const long long room = ((long long)e->max_smem + 1024) / blocks_per_sm - 1024 - 64;
+  const long long fit = (room - (long long)duo_smem_bytes(0, 0, lcap, e->duo_tpb)) / sb;
   if (want > fit) want = fit;
   if (want > DUO_IDX + 1) want = DUO_IDX + 1;
   want = want / 32 * 32;
@@ -596,7 +604,7 @@ SweepPlan plan_duo(const sphb200_engine* e, int sb, int lcap) {
   p.sb = sb;
   p.cap = (int)want;
   p.lcap = lcap;
-  p.smem = duo_smem_bytes(sb, p.cap, lcap);
+  p.smem = duo_smem_bytes(sb, p.cap, lcap, e->duo_tpb);
   return p;
 }
 
@@ -1051,7 +1059,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
         CK(cudaGetLastError());
       }
       if (force_feat == FORCE_PLAIN) {
-#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>, DUO_CONSUME>, planDF, F, exd, st, dl)
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, false, 2)
         DISPATCH_DK(e, CALL);
 #undef CALL
         if (rc) return rc;
@@ -1059,7 +1067,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
         DISPATCH_DK(e, CALL);
 #undef CALL
       } else {
-#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF>, DUO_CONSUME>, planDF, F, exd, st, dl)
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, false, 2)
         DISPATCH_DK(e, CALL);
 #undef CALL
         if (rc) return rc;
@@ -1445,8 +1453,9 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->planN = plan_sweep(e, 2, e->lcap);
   e->planB = plan_sweep(e, 1, e->lcap);
   if (e->duo) {
-    e->planDB = plan_duo(e, 16, e->lcap);
-    e->planDA = plan_duo(e, 16, 0);
+    // the search and the density filter stage positions only: two blocks per SM
+    e->planDB = plan_duo(e, 16, e->lcap < 40 ? e->lcap : 40, 2);
+    e->planDA = plan_duo(e, 16, 0, 2);
   }
   e->needs_zero = true;  // control words are zeroed on the first upload's stream
   return SPHB200_OK;

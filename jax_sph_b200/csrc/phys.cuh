@@ -128,6 +128,8 @@ struct PhysDensity {
     a0.s = lo(d.s);
     a1.s = hi(d.s);
   }
+  template <class F>
+  __device__ static void each_acc_duo(AccD& a, F f) { f(a.s); }
   __device__ static void stage(const Consts& c, const Frame& f, const Extra& ex, int gp,
                                float4* sq, int cap, int d) {
     sq[d] = f.pt[gp];
@@ -811,6 +813,13 @@ struct PhysForce {
     for (int k = 0; k < DIM; ++k) {
       a0.a[k] = lo(d.a[k]); a1.a[k] = hi(d.a[k]);
       a0.tv[k] = lo(d.tv[k]); a1.tv[k] = hi(d.tv[k]);
+    }
+  }
+  template <class F>
+  __device__ static void each_acc_duo(AccD& a, F f) {
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+      f(a.a[k]); f(a.tv[k]);
     }
   }
   static constexpr int CQ = FEAT == FORCE_TVF ? 3 : 2;  // quads of the compact record

@@ -38,7 +38,6 @@ constexpr int DUO_MAXT = 512;    // largest block the kernels are compiled for
 constexpr int DUO_RUNS = 36;     // T[1] * T[2] upper bound
 constexpr int DUO_SOFF = 2047;   // staged (row, cell) entries upper bound
 constexpr int DUO_IDX = 0x3fff;  // staged index bits of a list entry
-constexpr int DUO_LS = DUO_MAXT; // stride of the per-thread columns of DUO_BUILD
 constexpr float DUO_FAR = -1.0e30f;  // coordinate of the far sentinel of the skin rows' padding
 constexpr float DUO_FAR_OWN = 1.0e30f;  // ... and of the missing second particle of a duo (apart from the sentinel too)
 
@@ -57,8 +56,9 @@ struct DuoList {
 
 enum { DUO_BUILD = 1, DUO_CONSUME = 2, DUO_FILTER = 3 };
 
-__host__ __device__ inline size_t duo_smem_bytes(int sb, int cap, int lcap) {
-  return (size_t)sb * cap + (size_t)lcap * DUO_LS * 2 + (DUO_SOFF + 1 + 4 * (DUO_RUNS + 1)) * 4;
+// (the per-thread columns of DUO_BUILD are strided by the block size)
+__host__ __device__ inline size_t duo_smem_bytes(int sb, int cap, int lcap, int tpb) {
+  return (size_t)sb * cap + (size_t)lcap * tpb * 2 + (DUO_SOFF + 1 + 4 * (DUO_RUNS + 1)) * 4;
 }
 
 // ---------------------------------------------------------------------------
@@ -99,6 +99,12 @@ struct Duo {
     a0 = a.a[0];
     a1 = a.a[1];
   }
+  // sum over the two lanes that share a duo (SPLIT == 2)
+  __device__ static __forceinline__ void xsum(AccD& a) {
+    auto f = [](float& v) { v += __shfl_xor_sync(FULL_MASK, v, 1); };
+    P::each_acc(a.a[0], f);
+    P::each_acc(a.a[1], f);
+  }
 };
 template <class P>
 struct Duo<P, true> {
@@ -117,6 +123,13 @@ struct Duo<P, true> {
   __device__ static __forceinline__ void fold(const AccD& a, typename P::Acc& a0,
                                               typename P::Acc& a1) {
     P::fold_duo(a, a0, a1);
+  }
+  __device__ static __forceinline__ void xsum(AccD& a) {
+    P::each_acc_duo(a, [](F2& v) {
+      F2 o;
+      o.v = __shfl_xor_sync(FULL_MASK, v.v, 1);
+      v = add2(v, o);
+    });
   }
 };
 
@@ -144,10 +157,12 @@ __device__ __forceinline__ void duo_disp(const Grid& g, const F2 (&ri)[3], const
 //             duo inside the run: 16-byte word c of the skin row lives at
 //             sl16[row_run0 * lmax / 8 + c * nr + k], 8-byte word c of the exact row at
 //             xl8[row_run0 * lmax / 4 + c * nr + k]
-template <int DIM, class P, bool INTERIOR, bool FILTER>
+// SPLIT lanes share a duo (CONSUME only): lane `part` takes the words part, part + SPLIT, ... of
+// the exact row; the caller sums the accumulators over the lanes.
+template <int DIM, class P, bool INTERIOR, bool FILTER, int SPLIT>
 __device__ __forceinline__ void duo_consume(const Grid& g, const Consts& c, const Extra& ex,
                                             const DuoList& dl, const float4* sq, int cap,
-                                            int row_run0, int nr, int k, int nn, bool has1,
+                                            int row_run0, int nr, int k, int part, int nn, bool has1,
                                             const float (&rA)[3], const float (&rB)[3],
                                             const typename Duo<P>::OwnD& own,
                                             typename Duo<P>::AccD& acc, int& n_exact) {
@@ -202,16 +217,18 @@ __device__ __forceinline__ void duo_consume(const Grid& g, const Consts& c, cons
   } else {
     // exact list: a zero entry (unused slot of the last word) has no membership bit set
     // (words are fetched two trips ahead: a trip is shorter than a round trip to HBM)
+    const int nwords = (nn + 3) >> 2, step = SPLIT * nr;
     unsigned long long nxt = 0ull, nxt2 = 0ull;
-    if (nn > 0) nxt = __ldg(xp);
-    if (nn > 4) nxt2 = __ldg(xp + nr);
-    xp += nr;
+    xp += part * nr;
+    if (part < nwords) nxt = __ldg(xp);
+    if (part + SPLIT < nwords) nxt2 = __ldg(xp + step);
+    xp += step;
 #pragma unroll 1
-    for (int kk = 0; kk < nn; kk += 4) {
+    for (int w = part; w < nwords; w += SPLIT) {
       const unsigned long long cur = nxt;
       nxt = nxt2;
-      xp += nr;
-      if (kk + 8 < nn) nxt2 = __ldg(xp);
+      xp += step;
+      if (w + 2 * SPLIT < nwords) nxt2 = __ldg(xp);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const unsigned e = (unsigned)(cur >> (16 * u)) & 0xffffu;
@@ -282,7 +299,7 @@ struct Walk2 {
   // appends the candidates near either particle to the thread's shared-memory column; returns
   // true when the window is exhausted, false when some lane's column cannot take the next chunk
   __device__ __forceinline__ bool run(const Grid& g, const float4* sq, unsigned short* list, int tid,
-                                      int lcap, int& cnt, const int* soff, int E, int nxs,
+                                      int ls, int lcap, int& cnt, const int* soff, int E, int nxs,
                                       int slen1, const int (&sa0)[3], const float (&rA)[3],
                                       const float (&rB)[3], bool act, float thr) {
     for (;;) {
@@ -319,24 +336,23 @@ struct Walk2 {
       const int want = rem > 0 ? min(rem, SWEEP_CHUNK) : 0;
       if (__any_sync(FULL_MASK, want > lcap - cnt)) return false;  // drain first
       const int e = j + want;
-      int lo_ = cnt * DUO_LS + tid;
+      unsigned short* col = list + tid;
       // four candidates per trip, loaded before the first append (see sweep.cuh, Walk::run)
       for (; j + 4 <= e; j += 4) {
         const float4 p0 = sq[j], p1 = sq[j + 1], p2 = sq[j + 2], p3 = sq[j + 3];
         const bool n0 = near(p0, thr), n1 = near(p1, thr), n2 = near(p2, thr), n3 = near(p3, thr);
-        if (n0) { list[lo_] = (unsigned short)j; lo_ += DUO_LS; }
-        if (n1) { list[lo_] = (unsigned short)(j + 1); lo_ += DUO_LS; }
-        if (n2) { list[lo_] = (unsigned short)(j + 2); lo_ += DUO_LS; }
-        if (n3) { list[lo_] = (unsigned short)(j + 3); lo_ += DUO_LS; }
+        if (n0) { col[cnt * ls] = (unsigned short)j; ++cnt; }
+        if (n1) { col[cnt * ls] = (unsigned short)(j + 1); ++cnt; }
+        if (n2) { col[cnt * ls] = (unsigned short)(j + 2); ++cnt; }
+        if (n3) { col[cnt * ls] = (unsigned short)(j + 3); ++cnt; }
       }
 #pragma unroll 1
       for (; j < e; ++j) {
         if (near(sq[j], thr)) {
-          list[lo_] = (unsigned short)j;
-          lo_ += DUO_LS;
+          col[cnt * ls] = (unsigned short)j;
+          ++cnt;
         }
       }
-      cnt = lo_ / DUO_LS;
     }
   }
 };
@@ -363,8 +379,9 @@ __host__ __device__ inline int duo_desc_ints(int rows) { return (DD_JOBS + 2 * 3
 
 // (register cap per policy: sweeps with a small staged record run two blocks of up to 384
 // threads per SM, P::DUO_MINB == 2; the block size itself is a run-time choice up to DUO_MAXT)
-template <int DIM, class P, int ROLE>
-__global__ void __maxnreg__(P::DUO_MINB > 1 ? 80 : 128)
+// SPLIT (DUO_CONSUME): lanes per duo, see duo_consume.
+template <int DIM, class P, int ROLE, int SPLIT = 1>
+__global__ void __maxnreg__(SPLIT > 1 ? 80 : (P::DUO_MINB > 1 ? 80 : 128))
     k_duo(const Grid g, const Consts c, const Frame f, const int* __restrict__ cs,
           const SweepDims sd, const Extra ex, unsigned* __restrict__ err, const DuoList dl) {
   if (sd.gate != nullptr && *sd.gate != sd.gate_want) return;
@@ -375,7 +392,7 @@ __global__ void __maxnreg__(P::DUO_MINB > 1 ? 80 : 128)
   float4* sq = reinterpret_cast<float4*>(smem_raw);
   unsigned short* list = reinterpret_cast<unsigned short*>(smem_raw + (size_t)sd.sb * sd.cap);
   // BUILD: tile tables built from the cell table; FILTER / CONSUME: the tile's descriptor
-  int* soff = reinterpret_cast<int*>(list + (size_t)sd.lcap * DUO_LS);
+  int* soff = reinterpret_cast<int*>(list + (size_t)sd.lcap * TPB);
   int* own_start = soff + (DUO_SOFF + 1);
   int* own_off = own_start + (DUO_RUNS + 1);
   int* duo_off = own_off + (DUO_RUNS + 1);
@@ -572,9 +589,9 @@ __global__ void __maxnreg__(P::DUO_MINB > 1 ? 80 : 128)
     }
     bool staged = false;  // the wait for the staged data comes after the thread's own loads
 
-    for (int ib = 0; ib < tile_duos; ib += TPB) {
+    for (int ib = 0; ib < tile_duos; ib += TPB / SPLIT) {
       // ---- the thread's duo ----------------------------------------------------
-      const int t = ib + tid;
+      const int t = ib + tid / SPLIT, part = tid % SPLIT;
       const bool have = t < tile_duos;
       int run = 0, k = 0, p0 = 0, nr = 1;
       bool has1 = false;
@@ -631,15 +648,15 @@ __global__ void __maxnreg__(P::DUO_MINB > 1 ? 80 : 128)
         const bool rows_fit = row_run0 + nr <= dl.rows_cap;  // (holds by construction of rows_cap)
         if (have && !rows_fit) s_bad = 1;
         for (;;) {
-          const bool fin = wk.run(g, sq, list, tid, sd.lcap, cnt, soff, E, nxs, slen[1], sa0, rA, rB,
-                                  have, g.c2_hi);
+          const bool fin = wk.run(g, sq, list, tid, TPB, sd.lcap, cnt, soff, E, nxs, slen[1], sa0, rA,
+                                  rB, have, g.c2_hi);
           int w = 0;
           for (; cnt - w >= 8; w += 8) {
             uint4 v;
-            v.x = (unsigned)col[(w + 0) * DUO_LS] | ((unsigned)col[(w + 1) * DUO_LS] << 16);
-            v.y = (unsigned)col[(w + 2) * DUO_LS] | ((unsigned)col[(w + 3) * DUO_LS] << 16);
-            v.z = (unsigned)col[(w + 4) * DUO_LS] | ((unsigned)col[(w + 5) * DUO_LS] << 16);
-            v.w = (unsigned)col[(w + 6) * DUO_LS] | ((unsigned)col[(w + 7) * DUO_LS] << 16);
+            v.x = (unsigned)col[(w + 0) * TPB] | ((unsigned)col[(w + 1) * TPB] << 16);
+            v.y = (unsigned)col[(w + 2) * TPB] | ((unsigned)col[(w + 3) * TPB] << 16);
+            v.z = (unsigned)col[(w + 4) * TPB] | ((unsigned)col[(w + 5) * TPB] << 16);
+            v.w = (unsigned)col[(w + 6) * TPB] | ((unsigned)col[(w + 7) * TPB] << 16);
             if (gk + 8 <= dl.lmax && rows_fit) {
               *gp = v;
               gp += nr;
@@ -650,7 +667,7 @@ __global__ void __maxnreg__(P::DUO_MINB > 1 ? 80 : 128)
           }
           const int r = cnt - w;
           if (w > 0)
-            for (int i = 0; i < r; ++i) col[i * DUO_LS] = col[(w + i) * DUO_LS];
+            for (int i = 0; i < r; ++i) col[i * TPB] = col[(w + i) * TPB];
           cnt = r;
           if (fin) break;
         }
@@ -658,7 +675,7 @@ __global__ void __maxnreg__(P::DUO_MINB > 1 ? 80 : 128)
           if (cnt > 0) {  // tail chunk, padded with the index of the far sentinel (see duo_consume)
             unsigned e8[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) e8[i] = i < cnt ? (unsigned)col[i * DUO_LS] : (unsigned)total_staged;
+            for (int i = 0; i < 8; ++i) e8[i] = i < cnt ? (unsigned)col[i * TPB] : (unsigned)total_staged;
             if (gk + 8 <= dl.lmax && rows_fit)
               *gp = make_uint4(e8[0] | (e8[1] << 16), e8[2] | (e8[3] << 16), e8[4] | (e8[5] << 16),
                                e8[6] | (e8[7] << 16));
@@ -706,20 +723,26 @@ __global__ void __maxnreg__(P::DUO_MINB > 1 ? 80 : 128)
           D::init(ad);
           int n_exact = 0;
           if (interior)
-            duo_consume<DIM, P, true, ROLE == DUO_FILTER>(g, c, ex, dl, sq, sd.cap, row_run0, nr, k,
-                                                          nn, has1, rA, rB, od, ad, n_exact);
+            duo_consume<DIM, P, true, ROLE == DUO_FILTER, SPLIT>(g, c, ex, dl, sq, sd.cap, row_run0,
+                                                                 nr, k, part, nn, has1, rA, rB, od, ad,
+                                                                 n_exact);
           else
-            duo_consume<DIM, P, false, ROLE == DUO_FILTER>(g, c, ex, dl, sq, sd.cap, row_run0, nr,
-                                                           k, nn, has1, rA, rB, od, ad, n_exact);
+            duo_consume<DIM, P, false, ROLE == DUO_FILTER, SPLIT>(g, c, ex, dl, sq, sd.cap, row_run0,
+                                                                  nr, k, part, nn, has1, rA, rB, od,
+                                                                  ad, n_exact);
+          if (SPLIT > 1) D::xsum(ad);
           D::fold(ad, aA, aB);
-          if (ROLE == DUO_FILTER && have) dl.xcnt[row] = n_exact;
+          if (ROLE == DUO_FILTER && have && part == 0) dl.xcnt[row] = n_exact;
         }
         if (have) {
           // the epilogue re-reads the own values (nothing of them has to stay in registers
-          // across the pair loop beyond what the packed body keeps)
-          P::load_own(c, f, ex, p0, qA, oA);
-          P::finish(c, f, ex, p0, oA, aA);
-          if (has1) {
+          // across the pair loop beyond what the packed body keeps); lanes that share a duo
+          // take one particle each
+          if (SPLIT == 1 || part == 0) {
+            P::load_own(c, f, ex, p0, qA, oA);
+            P::finish(c, f, ex, p0, oA, aA);
+          }
+          if (has1 && (SPLIT == 1 || part == 1)) {
             P::load_own(c, f, ex, p1, qB, oB);
             P::finish(c, f, ex, p1, oB, aB);
           }

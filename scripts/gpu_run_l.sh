@@ -1,8 +1,9 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"k_duo.*PhysForce" -s 0 -c 1 -f -o gpurun_out/r2l_prof python bench.py --nx 128 --steps 3 --warmup 3 --e2e-steps 1 --cpu-steps 1 --no-configs > gpurun_out/r2l_ncu.log 2>&1
-tail -2 gpurun_out/r2l_ncu.log | cut -c1-300
+timeout 300 python scripts/duo_check.py 48 40 > gpurun_out/r2l_duo_check.log 2>&1
+grep -v "plan" gpurun_out/r2l_duo_check.log | tail -12
+python -m pytest tests/test_gpu_api.py -m gpu -q -x -k "advance_host" -p no:cacheprovider 2>&1 | tail -3
 run() { tag=$1; shift; env "${ENVV[@]}" python bench.py --steps 20 --warmup 3 --e2e-steps 1 --cpu-steps 1 --no-configs "$@" > gpurun_out/r2l_$tag.json 2> gpurun_out/r2l_$tag.err
 python - <<PY
 import json
@@ -14,10 +15,7 @@ except Exception as e:
     print("$tag", "FAILED", e)
 PY
 }
-ENVV=(SPHB200_DUO_TPB=288); run t644_288 --tile-x 6 --tile-y 4 --tile-z 4
-ENVV=(SPHB200_DUO_TPB=256); run t544_256 --tile-x 5 --tile-y 4 --tile-z 4
-ENVV=(SPHB200_DUO_TPB=384); run t844_384 --tile-x 8 --tile-y 4 --tile-z 4
-ENVV=(SPHB200_DUO_TPB=512); run t844_512 --tile-x 8 --tile-y 4 --tile-z 4
-ENVV=(SPHB200_DUO_TPB=352); run t853_352 --tile-x 8 --tile-y 5 --tile-z 3
-ENVV=(SPHB200_DUO_TPB=352); run t844_s12 --skin 0.12
-ENVV=(SPHB200_DUO_TPB=352); run t844_s15 --skin 0.15
+ENVV=(A=1); run base
+ENVV=(A=1); run s12 --skin 0.12
+ENVV=(A=1); run s14 --skin 0.14
+ENVV=(SPHB200_DUO_TPB=320); run t744_320 --tile-x 7 --tile-y 4 --tile-z 4

@@ -287,25 +287,34 @@ def test_advance_host_overlapped_download_is_bit_exact(kw):
     """sphb200_engine_advance_host sends r (and u, v where nothing rewrites them after the
     reorder pass) back to the host while the sweeps run, and rho, p while the force sweep runs
     (unless a bc table sets p afterwards): the result must equal, bit for bit,
-    upload + step + download of the same entries on a second engine (same upload order, so the
-    sums run in the same order), over several steps and with pinned host buffers."""
+    refresh + step + download of the same entries on a second engine -- the same sequence without
+    the overlap (both engines keep their cell sort and neighbour lists between the steps, so the
+    sums run in the same order) -- over several steps and with pinned host buffers.  A third
+    engine that uploads from scratch every step (and therefore sorts and searches every step:
+    another summation order) must agree within the parity tolerance."""
     import torch
 
     from jax_sph_b200 import Engine, config_from_setup
 
     setup = _case(**kw)
     n = len(setup.state["r"])
-    a, b = Engine(config_from_setup(setup), n), Engine(config_from_setup(setup), n)
+    a, b, c = (Engine(config_from_setup(setup), n) for _ in range(3))
     read, written = a.live_fields()
     pin = lambda v: torch.from_numpy(np.ascontiguousarray(v)).pin_memory()  # noqa: E731
     sa = {k: pin(v) for k, v in setup.state.items()}
     sb = {k: pin(v) for k, v in setup.state.items()}
+    sc = {k: pin(v) for k, v in setup.state.items()}
     for step in range(4):
         sa = a.advance_host(setup.dt, sa)
-        b.upload({k: sb[k] for k in read})
+        b.refresh({k: sb[k] for k in read})
         b.step(setup.dt, 1)
         b.download(out={k: sb[k] for k in written})
+        c.upload({k: sc[k] for k in read})
+        c.step(setup.dt, 1)
+        c.download(out={k: sc[k] for k in written})
         torch.cuda.synchronize()
         for k in written:
             assert torch.equal(sa[k], sb[k]), (step, k)
+            assert_close(k, sa[k].numpy(), sc[k].numpy(), setup, factor=3.0,
+                         what="frozen sort vs sort every step")
     assert a.error() == 0 and b.error() == 0
