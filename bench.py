@@ -41,12 +41,13 @@ UNIT = "particle-updates/s"
 # Algorithmic HBM bytes per particle-step, float32: what the pass must
 # move if every array crossed HBM once -- integrate 144 (R pt um vv du dv rb, W pt um vv),
 # density 24 (R pt, W rho p), force 76 (R pt um vv st, W dudt dvdt).  `lists` = what the engine
-# adds on top by keeping neighbour lists in HBM: the density pass reads
-# the skin row (147 / 37 entries on the 3D / 2D lattice, 2 B each, in 16-byte chunks) and writes
-# the exact row (123 / 29), the force pass reads the exact row.
+# adds on top by keeping neighbour lists in HBM, per particle: the density
+# pass reads the skin row of its duo (about 190 / 45 entries per TWO particles on the 3D / 2D
+# lattice, 2 B each) and writes the exact row (about 120 / 32 per two particles), the force pass
+# reads the exact row and the compact force records (52 B written + read per particle).
 BYTES = {
-    3: dict(cells=144, density=24, force=76, lists=dict(density=304 + 4 + 246 + 4, force=246 + 4)),
-    2: dict(cells=144, density=24, force=76, lists=dict(density=80 + 4 + 58 + 4, force=58 + 4)),
+    3: dict(cells=144, density=24, force=76, lists=dict(density=190 + 2 + 120 + 2, force=120 + 2 + 104)),
+    2: dict(cells=144, density=24, force=76, lists=dict(density=45 + 2 + 32 + 2, force=32 + 2 + 104)),
 }
 # useful flops per directed in-range edge, SURVEY.md section 8d
 FLOPS_EDGE = {3: dict(density=58 + 1, force=58 + 103 + 16), 2: dict(density=50 + 1, force=50 + 63 + 14)}
@@ -105,15 +106,21 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def roofline_of(acc, dim, n, edges, peaks, which, fp32=None, searches_per_step=None):
+def roofline_of(acc, dim, n, edges, peaks, which, fp32=None, searches_per_step=None, duo=True):
     """`roofline` object: the DOMINANT kernel of the step (largest CUDA-event time) against the
     roofline that bounds it -- FP32 issue: the sweeps do 20 useful flop per algorithmic byte, the
     ridge of this device is at 11 -- with the measured FMA peak as the
     denominator; its HBM figure, the other sweep and the HBM-bound integrate pass beside it."""
-    names = {"density": "k_sweep<PhysDensity, LIST_FILTER> (exact membership test + density sweep"
+    names = {"density": "k_duo<PhysDensity, DUO_FILTER> (exact membership test + density sweep"
                         " + exact list of the step; on sorting steps preceded by the search "
-                        "k_sweep<PhysNone, LIST_BUILD>, included in ms)",
-             "force": "k_sweep<PhysForce, LIST_CONSUME> (force sweep)"}
+                        "k_duo<PhysNone, DUO_BUILD>, included in ms)",
+             "force": "k_duo<PhysForce, DUO_CONSUME, 2> (force sweep; k_force_rec, the compact "
+                      "records it stages by bulk copy, included in ms)"}
+    if not duo:
+        names = {"density": "k_sweep<PhysDensity, LIST_FILTER> (exact membership test + density "
+                            "sweep + exact list of the step; on sorting steps preceded by the "
+                            "search k_sweep<PhysNone, LIST_BUILD>, included in ms)",
+                 "force": "k_sweep<PhysForce, LIST_CONSUME> (force sweep)"}
     peak_tf = fp32["ffma"] if fp32 else FP32_NOMINAL_TFLOPS
     peak_src = "measured: sphb200_fp32_peak (FFMA chains) on this device" if fp32 else "nominal"
     per = {}
@@ -143,7 +150,8 @@ def roofline_of(acc, dim, n, edges, peaks, which, fp32=None, searches_per_step=N
         "hbm_peak_source": which,
         "note": "achieved = useful flops (SURVEY.md 8d: per in-range directed edge, "
                 f"{edges} edges per lattice particle) / CUDA-event time of the pass; the sweeps "
-                "are bound by instruction issue and shared-memory wavefronts (ncu: profiles/), "
+                "are bound by the FP32 pipes (the packed f32x2 instructions halve the issue "
+                "slots, not the pipe cycles) and by latency at one block per SM (ncu: profiles/), "
                 "not by HBM; `cells` is the HBM-bound integrate pass (plus the cell sort on the "
                 "steps that sort)",
         "kernels": per,
@@ -505,7 +513,7 @@ def stateless_advance(args, eng_cfg, state, meta, steps):
     ms = timed(call(lib.sphb200_advance_persistent), steps)
     lib.sphb200_workspace_release(C.c_void_p(ws.data_ptr()))
     ms_scratch = timed(call(lib.sphb200_advance), min(steps, 3))
-    return {"value": n * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+    return {"value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "device_error_word": int(err.item()),
             "what": "sphb200_advance_persistent on device pointers, the caller's workspace handed "
                     "in again call after call (the engine in it keeps the particles cell-sorted "
@@ -617,7 +625,7 @@ def run_ours(args):
     value = world * n * args.steps / (ms * 1e-3)
     edges = 93 if dim == 3 else 25  # directed in-range edges per lattice particle incl. self
     roof = roofline_of(acc, dim, n, edges, peaks, which, fp32,
-                       counters["searches"] / max(counters["steps"], 1))
+                       counters["searches"] / max(counters["steps"], 1), counters.get("duo", False))
     # the C-ABI drop-in call and the other BASELINE configurations (resident engine freed first)
     cfg_copy = config_of(args, meta)
     plan = eng.plan()

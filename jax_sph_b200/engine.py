@@ -398,12 +398,14 @@ class Engine:
 
     def counters(self):
         """steps run, searches (cell sort + candidate walk) among them, list row length, skin /
-        cutoff, tiles, tiles swept without lists (sphb200_engine_counters)."""
+        cutoff, tiles, tiles swept without lists, whether the duo sweeps (csrc/sweep2.cuh: two
+        particles per thread on one union list) serve this solver variant
+        (sphb200_engine_counters)."""
         out = (C.c_int64 * 8)()
         _lib.check(self.lib.sphb200_engine_counters(self._h, C.byref(out), _stream_ptr()))
         v = list(out)
         return dict(steps=v[0], searches=v[1], list_rows=v[2], skin=v[3] * 1e-6, tiles=v[4],
-                    tiles_without_lists=v[5])
+                    tiles_without_lists=v[5], duo=bool(v[6]))
 
     def plan(self):
         out = (C.c_int32 * 16)()

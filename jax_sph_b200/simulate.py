@@ -45,7 +45,7 @@ def defaults(**overrides) -> Dict:
     cfg = {
         "seed": 123, "dtype": "float32",
         "case": dict(name="tgv", mode="sim", dim=3, dx=0.05, r0_type="cartesian", state0_path=None,
-                     r0_noise_factor=0.0, g_ext_magnitude=0.0, viscosity=0.01, u_ref=1.0,
+                     state0_keys=["r"], special=dict(), r0_noise_factor=0.0, g_ext_magnitude=0.0, viscosity=0.01, u_ref=1.0,
                      c_ref_factor=10.0, rho_ref=1.0, T_ref=1.0, kappa_ref=0.0, Cp_ref=0.0),
         "solver": dict(name="SPH", tvf=0.0, cfl=0.25, density_evolution=False,
                        density_renormalize=False, dt=None, t_end=0.2, artificial_alpha=0.0,
@@ -126,15 +126,24 @@ def _prepare_tgv(cfg) -> _Prepared:
         artificial_alpha=g(cfg, "solver.artificial_alpha"),
         diff_delta=g(cfg, "solver.diff_delta"), diff_alpha=g(cfg, "solver.diff_alpha"))
     state = case_setup.init_lattice(lat)
-    if r0_type == "relaxed" and mode == "sim":
-        # TGV.__init__ (cases/tgv.py:20-23) + _get_relaxed_r0 (case_setup.py:274-294): positions
-        # of the relaxed state, velocities evaluated there
-        import os
+    # SimulationSetup.initialize() (jax_sph/case_setup.py:126-194), in its order: positions (the
+    # lattice, or for r0_type == "relaxed" those of data_relaxed/<name>.h5, cases/tgv.py:20-23 +
+    # case_setup.py:274-294), noise on the fluid particles, the velocity field AT those positions,
+    # and last -- for ANY r0_type -- the fluid entries named by case.state0_keys taken from the
+    # snapshot case.state0_path (:184-194; restarts list every key).
+    import os
 
-        path = g(cfg, "case.state0_path") if _has(cfg, "case.state0_path") else None
-        if path is None:
-            stem = case_setup.relaxed_state_name(g(cfg, "case.name"), dim, dx, g(cfg, "seed"))
-            path = os.path.join("data_relaxed", stem + ".h5")
+    path0 = g(cfg, "case.state0_path") if _has(cfg, "case.state0_path") else None
+    keys0 = list(g(cfg, "case.state0_keys")) if _has(cfg, "case.state0_keys") else ["r"]
+    moved = False
+    if r0_type == "relaxed" and mode == "sim":
+        if path0 is None or "r" not in keys0:  # case_setup.py:38-39
+            raise _lib.Sphb200Error("case.r0_type='relaxed' needs case.state0_path and 'r' in "
+                                    "case.state0_keys")
+        stem = case_setup.relaxed_state_name(g(cfg, "case.name"), dim, dx, g(cfg, "seed"))
+        path = os.path.join("data_relaxed", stem + ".h5")
+        if not os.path.isfile(path):
+            path = path0  # (a driver without the data_relaxed/ tree: the snapshot itself)
         if not os.path.isfile(path):
             raise FileNotFoundError(
                 f"{path}: first run the relaxation (case.mode='rlx', solver.tvf=1, "
@@ -144,11 +153,16 @@ def _prepare_tgv(cfg) -> _Prepared:
             raise _lib.Sphb200Error(f"{path}: {tuple(snap['r'].shape)} positions, the case has "
                                     f"{tuple(state['r'].shape)}")
         state["r"] = snap["r"].contiguous()
-        case_setup.eval_velocity(state, field)
-    elif g(cfg, "case.r0_noise_factor") != 0.0:
-        # case_setup.py:138-150: noise on the fluid particles, wrapped, THEN the velocity field
+        moved = True
+    if g(cfg, "case.r0_noise_factor") != 0.0:
         case_setup.add_noise(state, g(cfg, "case.r0_noise_factor") * dx, g(cfg, "seed"), box)
+        moved = True
+    if moved:
         case_setup.eval_velocity(state, field)
+    if path0 is not None:
+        if not os.path.isfile(path0):
+            raise FileNotFoundError(f"case.state0_path: {path0}")
+        case_setup.apply_state0(state, io_state.read_h5(path0, array_type="torch"), keys0)
     return _Prepared(ecfg, state, dt, seq, dx, case_setup.lattice_rows(lat))
 
 
@@ -171,7 +185,23 @@ def channel_case(cfg) -> Dict:
     name = str(g(cfg, "case.name")).lower()
     special, depth = _CHANNEL_SPECIAL[name]
     dim, dx, n_walls = g(cfg, "case.dim"), g(cfg, "case.dx"), g(cfg, "solver.n_walls")
-    sp = {k: (g(cfg, "special." + k) if _has(cfg, "special." + k) else v) for k, v in special.items()}
+    # `cfg.case.special` as in the reference's YAML files (cases/ht.yaml, pf.yaml; read by
+    # SimulationSetup.__init__, case_setup.py:36); a top-level `special` section is accepted too
+    sp = {}
+    for k, v in special.items():
+        if _has(cfg, "case.special." + k):
+            sp[k] = g(cfg, "case.special." + k)
+        elif _has(cfg, "special." + k):
+            sp[k] = g(cfg, "special." + k)
+        else:
+            sp[k] = v
+    for section in ("case.special", "special"):
+        if _has(cfg, section):
+            given = g(cfg, section)
+            unknown = [k for k in (given.keys() if hasattr(given, "keys") else []) if k not in special]
+            if unknown:
+                raise _lib.Sphb200Error(f"{section}: unknown key(s) {unknown} for case '{name}' "
+                                        f"(known: {sorted(special)})")
     box = [sp["L"], sp["H"] + 2 * n_walls * dx] + ([depth] if dim == 3 else [])
     nxyz = [int(round(sp["L"] / dx)), int(round(sp["H"] / dx)) + 2 * n_walls] + (
         [int(round(depth / dx))] if dim == 3 else [])

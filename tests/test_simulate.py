@@ -348,3 +348,65 @@ def test_poiseuille_tables_equal_the_oracle_case(dim, dx):
     wall_ref = setup.state["tag"] == 1
     assert np.array_equal(wall_ref, (q[:, 1] < 3) | (q[:, 1] >= n[1] - 3))
 
+
+
+def test_channel_geometry_is_read_from_case_special():
+    """cases/ht.yaml keeps the channel geometry under `case.special` (SimulationSetup.__init__,
+    jax_sph/case_setup.py:36): a config keyed like the reference's changes the box, the hot patch
+    and its temperature; a misspelt key is an error, not a silent default."""
+    from jax_sph_b200 import _lib
+
+    base = dict(name="ht", dim=2, dx=0.02, g_ext_magnitude=2.3, kappa_ref=7.313, Cp_ref=305.27)
+    ref = sim.channel_case(sim.defaults(case=base))
+    cfg = sim.defaults(case=dict(base, special=dict(L=2.0, hot_wall_temperature=1.5,
+                                                    hot_wall_half_width=0.5)))
+    ht = sim.channel_case(cfg)
+    assert ht["box"][0] == 2.0 and ref["box"][0] == 1.0 and ht["box"][1] == ref["box"][1]
+    assert ht["T_hot"] == 1.5 and ht["hot"] == (0.5, 1.5)
+    assert ht["nxyz"][0] == 2 * ref["nxyz"][0]
+    # the older top-level section still works, the case section wins
+    top = sim.defaults(case=base, special=dict(L=3.0))
+    assert sim.channel_case(top)["box"][0] == 3.0
+    both = sim.defaults(case=dict(base, special=dict(L=2.0)), special=dict(L=3.0))
+    assert sim.channel_case(both)["box"][0] == 2.0
+    with pytest.raises(_lib.Sphb200Error):
+        sim.channel_case(sim.defaults(case=dict(base, special=dict(hot_wall_temp=1.5))))
+
+
+@pytest.mark.gpu
+def test_state0_path_applies_to_a_cartesian_start(tmp_path):
+    """validation/tgv2d.sh passes case.state0_path with case.r0_type=cartesian: initialize()
+    (jax_sph/case_setup.py:184-194) then overwrites the fluid entries named by
+    case.state0_keys AFTER the velocities were evaluated on the lattice -- positions of the
+    snapshot, lattice velocities; with every key listed the run restarts from the snapshot."""
+    from jax_sph_b200 import io_state
+
+    dx = 0.05
+    n = int(round(1 / dx)) ** 2
+    first = sim.defaults(seed=3, case=dict(name="tgv", dim=2, dx=dx, r0_noise_factor=0.25),
+                         solver=dict(tvf=1.0, t_end=0.02),
+                         io=dict(write_type=["h5"], write_every=1000, data_path=str(tmp_path)))
+    sim.simulate(first, log=lambda s: None)
+    # (simulation runs write into a run directory below io.data_path, io_state.io_setup)
+    snaps = sorted(os.path.join(d, f) for d, _, fs in os.walk(tmp_path) for f in fs if f.endswith(".h5"))
+    assert snaps
+    path = snaps[-1]
+    snap = io_state.read_h5(path)
+
+    def start(keys):
+        cfg = sim.defaults(seed=3, case=dict(name="tgv", dim=2, dx=dx, state0_path=path,
+                                             state0_keys=keys),
+                           solver=dict(tvf=1.0, t_end=1e-9), io=dict(data_path=str(tmp_path)))
+        prep = sim._prepare_tgv(cfg)
+        return {k: (v.cpu().numpy() if hasattr(v, "cpu") else np.asarray(v)) for k, v in prep.state.items()}
+
+    only_r = start(["r"])
+    assert only_r["r"].shape == (n, 2) and np.array_equal(only_r["r"], snap["r"])
+    lattice = (np.arange(int(round(1 / dx))) + 0.5) * dx
+    gx, gy = np.meshgrid(lattice, lattice, indexing="ij")
+    # the velocity is the TGV field of the LATTICE positions (evaluated before the overwrite)
+    u_lat = -np.cos(2 * np.pi * gx) * np.sin(2 * np.pi * gy)
+    assert np.allclose(np.sort(only_r["u"][:, 0]), np.sort(u_lat.ravel()), atol=1e-5)
+    restart = start(["r", "u", "v", "rho", "p", "dudt", "dvdt"])
+    for k in ("r", "u", "v", "rho", "p", "dudt", "dvdt"):
+        assert np.array_equal(restart[k], snap[k]), k
