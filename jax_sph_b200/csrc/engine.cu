@@ -199,10 +199,13 @@ int max_stage_bytes(const sphb200_config& c) {
 
 // Cell grid, stencil and tiling (host).  nranks > 1: the local view of rank `rank`.
 // skin / cutoff of an engine for this config
+bool duo_variant(const sphb200_config& c);
 double plan_skin(const sphb200_config& c) {
   if (c.nl_cap < 0 || c.skin < 0.f) return 0.0;
   if (c.skin > 0.f) return c.skin > 1.f ? 1.0 : (double)c.skin;
-  return 0.10;  // tuned on B200 (profiles/r02_skin_*.txt)
+  // tuned on B200 (profiles/r02_plan_tuning_*): the cheaper search + filter of the 3D duo sweeps
+  // move the optimum out a little
+  return (c.dim == 3 && duo_variant(c)) ? 0.12 : 0.10;
 }
 
 void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nranks = 1,
@@ -333,6 +336,9 @@ void plan_consts(const sphb200_config& c, Consts& k) {
   k.ooh = (float)ooh;
   k.sigma = (float)sigma;
   k.sigma_ooh = k.sigma * k.ooh;
+  k.gwk[0] = k.sigma_ooh * -5.0f;
+  k.gwk[1] = k.sigma_ooh * 30.0f;
+  k.gwk[2] = k.sigma_ooh * -75.0f;
   k.dt_s = (float)c.dt;
   k.p_ref = (float)c.p_ref; k.rho_ref = (float)c.rho_ref; k.p_bg = (float)c.p_bg;
   k.gamma = (float)c.gamma;

@@ -1,10 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 300 python scripts/duo_check.py 48 40 > gpurun_out/r2l_duo_check.log 2>&1
-grep -v "plan" gpurun_out/r2l_duo_check.log | tail -12
-python -m pytest tests/test_gpu_api.py -m gpu -q -x -k "advance_host" -p no:cacheprovider 2>&1 | tail -3
-run() { tag=$1; shift; env "${ENVV[@]}" python bench.py --steps 20 --warmup 3 --e2e-steps 1 --cpu-steps 1 --no-configs "$@" > gpurun_out/r2l_$tag.json 2> gpurun_out/r2l_$tag.err
+python -m pytest tests/test_gpu_duo.py tests/test_gpu_parity3d.py tests/test_gpu_reference.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
+run() { tag=$1; shift; env "${ENVV[@]}" python bench.py --steps 60 --warmup 3 --e2e-steps 1 --cpu-steps 1 --no-configs "$@" > gpurun_out/r2l_$tag.json 2> gpurun_out/r2l_$tag.err
 python - <<PY
 import json
 f="gpurun_out/r2l_$tag.json"
@@ -17,5 +15,4 @@ PY
 }
 ENVV=(A=1); run base
 ENVV=(A=1); run s12 --skin 0.12
-ENVV=(A=1); run s14 --skin 0.14
-ENVV=(SPHB200_DUO_TPB=320); run t744_320 --tile-x 7 --tile-y 4 --tile-z 4
+ENVV=(A=1); run s08 --skin 0.08

@@ -1,7 +1,7 @@
 """Turn ncu output into the text summaries committed under profiles/.
 
   python scripts/ncu_summary.py raw      <report.ncu-rep> <out.txt> ["header comment"]
-  python scripts/ncu_summary.py traffic  <report.ncu-rep> <out.json> ["source note"]
+  python scripts/ncu_summary.py traffic  <report.ncu-rep> <out.json> <particles> ["source note"]
   python scripts/ncu_summary.py launches <launches.csv>   <out.txt> <steps> ["header comment"]
 
 `raw`: the metrics the roofline discussion of DESIGN.md section 3 quotes, one row per metric,
@@ -60,7 +60,15 @@ def cmd_raw(report, dst, note=""):
     open(dst, "w").write("\n".join(lines) + "\n")
 
 
-def cmd_traffic(report, dst, note=""):
+def cmd_traffic(report, dst, n, note=""):
+    """n: particles of the captured run; the file also carries bench.source_sha(), the hash of
+    the CUDA sources, so that bench.py only quotes it for the build it describes."""
+    import os
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    n = int(n)
     hdr, units, data = raw_rows(report)
     col = {h: i for i, h in enumerate(hdr)}
 
@@ -78,8 +86,10 @@ def cmd_traffic(report, dst, note=""):
         wr = to_bytes(d[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
         out[key] = {"kernel": name.replace("sphb200::", "").replace("(int)", ""),
                     "dram_bytes_read": rd, "dram_bytes_write": wr,
-                    "dram_bytes_per_launch": rd + wr}
+                    "dram_bytes_per_launch": rd + wr, "particles": n,
+                    "dram_bytes_per_particle": (rd + wr) / n}
     out["_source"] = note
+    out["source_sha"] = bench.source_sha()
     json.dump(out, open(dst, "w"), indent=1)
 
 
@@ -103,6 +113,6 @@ if __name__ == "__main__":
     if mode == "raw":
         cmd_raw(*sys.argv[2:5])
     elif mode == "traffic":
-        cmd_traffic(*sys.argv[2:5])
+        cmd_traffic(*sys.argv[2:6])
     elif mode == "launches":
         cmd_launches(sys.argv[2], sys.argv[3], int(sys.argv[4]), *sys.argv[5:6])

@@ -40,14 +40,23 @@ def engine_for(setup, **tuning):
     return Engine(config_from_setup(setup, **tuning), len(setup.state["r"]))
 
 
-def row(case, what, key, got, ref32, ref64, setup, factor):
+def row(case, what, key, got, ref32, ref64, setup, factor, same_start=True):
     err = periodic_err(got, ref32, setup.box_size) if key == "r" else max_err(got, ref32)
     tol = factor * tolerance(key, ref32, setup)
-    e64 = periodic_err(got, ref64, setup.box_size) if key == "r" else max_err(got, ref64)
-    d3264 = periodic_err(ref32, ref64, setup.box_size) if key == "r" else max_err(ref32, ref64)
-    print(f"{case:16s} {what:9s} {key:7s} err {err:10.3e}  tol {tol:10.3e}  err/tol {err / tol:6.3f}  "
-          f"|e-64| {e64:10.3e}  |32-64| {d3264:10.3e}")
+    line = f"{case:16s} {what:9s} {key:7s} err {err:10.3e}  tol {tol:10.3e}  err/tol {err / tol:6.3f}  "
+    if same_start:
+        e64 = periodic_err(got, ref64, setup.box_size) if key == "r" else max_err(got, ref64)
+        d3264 = periodic_err(ref32, ref64, setup.box_size) if key == "r" else max_err(ref32, ref64)
+        line += f"|e-64| {e64:10.3e}  |32-64| {d3264:10.3e}"
+    else:
+        # the reference draws its position noise per dtype: its float64 run starts elsewhere
+        line += "|e-64|        n/a  |32-64|        n/a  (float64 run: another noise sample)"
+    print(line)
     return err / tol
+
+
+def same_start(z):
+    return float(np.abs(z["state0_f32_r"].astype(np.float64) - z["state0_f64_r"]).max()) < 1e-5
 
 
 def main():
@@ -70,14 +79,14 @@ def main():
         got = eng.download(host=True)
         for k in FWD_KEYS:
             worst = max(worst, row(name, "forward", k, got[k].numpy(), z[f"forward_f32_{k}"],
-                                   z[f"forward_f64_{k}"], setup, 1.0))
+                                   z[f"forward_f64_{k}"], setup, 1.0, same_start(z)))
         eng.upload(state0)
         eng.step(meta["dt"], meta["nsteps"])
         got = eng.download(host=True)
         cnt = eng.counters()
         for k in ADV_KEYS:
             worst = max(worst, row(name, f"{meta['nsteps']} steps", k, got[k].numpy(),
-                                   z[f"advance_f32_{k}"], z[f"advance_f64_{k}"], setup, 5.0))
+                                   z[f"advance_f32_{k}"], z[f"advance_f64_{k}"], setup, 5.0, same_start(z)))
         print(f"{name:16s} searches {cnt['searches']} of {cnt['steps']} steps, device error {eng.error()}")
         eng.close()
     print("# 200-step trajectories (tests/golden/ref200_*.npz), tolerance factor 15")
@@ -95,7 +104,7 @@ def main():
         cnt = eng.counters()
         for k in ("r", "u", "v", "rho", "T"):
             worst = max(worst, row(name, "200 steps", k, got[k].numpy(), z[f"advance_f32_{k}"],
-                                   z[f"advance_f64_{k}"], setup, 15.0))
+                                   z[f"advance_f64_{k}"], setup, 15.0, same_start(z)))
         print(f"{name:16s} searches {cnt['searches']} of {cnt['steps']} steps, device error {eng.error()}")
         eng.close()
     print("# oracle-based 3D case with interior tiles and frozen steps (tests/test_gpu_parity3d.py)")
