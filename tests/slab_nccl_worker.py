@@ -26,7 +26,9 @@ def main():
     nsteps = 40
     for kw in (dict(case="tgv", dim=2, dx=0.0125, tvf=1.0),
                dict(case="tgv", dim=3, dx=2 * np.pi / 32, tvf=1.0, viscosity=0.02),
-               dict(case="ht", dim=3, dx=0.02),
+               # (a slab must be two cutoffs thick: the channel is 0.5 deep, 15 cell layers at
+               # dx = 0.02 with the list skin -- enough for two ranks, not for four)
+               dict(case="ht", dim=3, dx=0.02 if world <= 2 else 0.0125),
                # Delta-SPH density diffusion: five exchanges per step
                dict(case="tgv", dim=3, dx=2 * np.pi / 32, solver="DELTA", density_evolution=True,
                     viscosity=0.02)):
