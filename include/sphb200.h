@@ -218,6 +218,21 @@ int sphb200_engine_advance_host(sphb200_engine *e, double dt, const sphb200_stat
                                 sphb200_state *out, uint32_t flags, void *stream);
 /* Write the state back in the ORIGINAL particle order (index-stable API). NULL members are skipped. */
 int sphb200_engine_download(sphb200_engine *e, sphb200_state *out, int on_host, void *stream);
+/* Vector-Jacobian product of the step the engine ran LAST -- one advance(dt) with `flags` as
+ * in sphb200_engine_step (SPHB200_STEP_INTEGRATE) or one forward() (flags 0) -- at the state it
+ * holds: what jax.grad / jax.vjp give for `advance` of jax_sph/integrator.py:22-56 in
+ * notebooks/iclr24_grads.ipynb (cell 5), by hand-written adjoint sweeps over the same cell-sorted
+ * particles (csrc/adjoint.cuh).
+ *   cot_out  cotangents of the step's outputs r, u, v, dudt, rho, p (DEVICE pointers, the
+ *            caller's particle order, NULL = zero)
+ *   cot_in   receives the cotangents of the step's inputs r, u, v, dudt, dvdt, rho, p (non-NULL
+ *            members; rho and p are overwritten by the step: zero)
+ * Supported: solver SPH, density by summation, tvf = 0, no wall / bc sweep, no artificial
+ * viscosity, constant external force, Quintic or Wendland C2 kernel; otherwise SPHB200_EUNSUP.
+ * A gradient through K steps is K calls in reverse order, each after re-running the step from
+ * its saved input state (jax_sph_b200.engine.grad_through_steps). */
+int sphb200_engine_vjp(sphb200_engine *e, double dt, uint32_t flags, const sphb200_state *cot_out,
+                       sphb200_state *cot_in, void *stream);
 /* sync: read and clear the device error word. */
 int sphb200_engine_error(sphb200_engine *e, uint32_t *code, void *stream);
 /* Sparse neighbour list of the CURRENT resident positions in original indices:

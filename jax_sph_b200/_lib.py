@@ -89,6 +89,7 @@ SYMBOLS = {
     "sphb200_engine_advance_host": (C.c_int, [_P, C.c_double, C.POINTER(State), C.POINTER(State),
                                              C.c_uint32, _P]),
     "sphb200_engine_download": (C.c_int, [_P, C.POINTER(State), C.c_int, _P]),
+    "sphb200_engine_vjp": (C.c_int, [_P, C.c_double, C.c_uint32, C.POINTER(State), C.POINTER(State), _P]),
     "sphb200_engine_error": (C.c_int, [_P, C.POINTER(C.c_uint32), _P]),
     "sphb200_engine_neighbor_list": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P]),
     "sphb200_engine_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), _P]),

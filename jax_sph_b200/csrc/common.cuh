@@ -84,6 +84,14 @@ struct Consts {
   int any_walls;    // 0 when no particle carries a wall tag (host-known hint)
 };
 
+// Work arrays of the vector-Jacobian product (adjoint.cuh), one entry per slot.
+struct AdjBufs {
+  float4* am;    // abar / m (xyz): the cotangent of dudt over the particle's mass
+  float4* rbar;  // position cotangent, accumulated by the two adjoint sweeps
+  float4* ubar;  // velocity cotangent from the force sweep
+  float4* rp;    // (rhobar_force, pbar_force, q = m (rhobar + pbar dp/drho), -)
+};
+
 // Per-launch switches of the sweep policies (phys.cuh).
 struct Extra {
   float4* st_out;  // destination of the (rho, p, T, dTdt) quad (ping-pong, see engine.cu)
@@ -98,6 +106,7 @@ struct Extra {
   // compact force records of every slot (duo force sweep: staged by bulk copies, sweep2.cuh)
   float4 *rec0, *rec1, *rec2;
   float* rec_e;
+  AdjBufs adj;     // adjoint sweeps
   // neighbour-list materialiser
   int* nl_counts;
   const int* nl_offsets;

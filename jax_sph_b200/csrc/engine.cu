@@ -28,6 +28,7 @@
 #include "slab.cuh"
 #include "sweep.cuh"
 #include "sweep2.cuh"
+#include "adjoint.cuh"
 
 using namespace sphb200;
 
@@ -138,6 +139,7 @@ struct sphb200_engine {
   bool stage_more;    // forward_stage ran only part of the stage (another halo refresh first)
   // wall-normal recomputation for moving walls (utils.py:197-277): the static one-layer
   // discretisation of the wall surface; wl_n == 0: normals are an input that never changes
+  float4* adj_mem;  // work arrays of sphb200_engine_vjp (4 n quads), allocated on first use
   float4* wl_pts;
   int wl_n;
   float wl_off[3];
@@ -1443,6 +1445,7 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
     slab_range(g.ng[ax], sp->rank, sp->nranks, e->slab_z0, e->slab_z1);
   }
   e->cur = 0;
+  e->adj_mem = nullptr;
   e->cells_valid = false;
   e->launches = 0;
   e->profile = false;
@@ -1616,6 +1619,7 @@ int sphb200_engine_destroy(sphb200_engine* e) {
     for (int i = 0; i < 8; ++i) cudaEventDestroy(e->ev[i]);
   if (e->hstage) cudaFree(e->hstage);
   if (e->wl_pts) cudaFree(e->wl_pts);
+  if (e->adj_mem) cudaFree(e->adj_mem);
   if (e->overlap) {
     cudaStreamDestroy(e->side);
     cudaEventDestroy(e->ev_main);
@@ -1910,6 +1914,60 @@ int sphb200_engine_step(sphb200_engine* e, double dt, int nsteps, uint32_t flags
     if (rc) return rc;
     if (e->profile) cudaEventRecord(e->ev[5], st);
   }
+  return SPHB200_OK;
+}
+
+int sphb200_engine_vjp(sphb200_engine* e, double dt, uint32_t flags, const sphb200_state* cot_out,
+                       sphb200_state* cot_in, void* stream) {
+  if (!e || !cot_out || !cot_in) return SPHB200_EINVAL;
+  const sphb200_config& c = e->cfg;
+  // the variant adjoint.cuh differentiates (the setting of notebooks/iclr24_grads.ipynb, cell 5)
+  if (e->slab_on || c.solver != SPHB200_SOLVER_SPH || c.tvf != 0.0 || c.artificial_alpha != 0.0 ||
+      (c.flags & (SPHB200_F_BC_TRICK | SPHB200_F_RHO_EVOL | SPHB200_F_HEAT | SPHB200_F_FREE_SLIP)) ||
+      bc_table_on(c) || (c.g_mode != SPHB200_G_NONE && c.g_mode != SPHB200_G_CONST) ||
+      (c.kernel != SPHB200_KERNEL_QSK && c.kernel != SPHB200_KERNEL_WC2K))
+    return SPHB200_EUNSUP;
+  if (!e->cells_valid) return SPHB200_EINVAL;  // no step has been run: nothing to linearise about
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = e->n;
+  if (!e->adj_mem) CK(cudaMalloc((void**)&e->adj_mem, (size_t)n * 64));
+  AdjBufs ab{e->adj_mem, e->adj_mem + n, e->adj_mem + 2 * (size_t)n, e->adj_mem + 3 * (size_t)n};
+  CotPtrs ct{cot_out->r, cot_out->u, cot_out->v, cot_out->dudt, cot_out->rho, cot_out->p};
+  CotOut out{cot_in->r, cot_in->u, cot_in->v, cot_in->dudt, cot_in->dvdt, cot_in->rho, cot_in->p};
+  Frame& F = e->fr[e->cur];
+  const int nb = (n + 255) / 256;
+  const int integrate = (flags & SPHB200_STEP_INTEGRATE) ? 1 : 0;
+  if (e->dim == 2) k_adj_begin<2><<<nb, 256, 0, st>>>(n, F, ab, ct);
+  else k_adj_begin<3><<<nb, 256, 0, st>>>(n, F, ab, ct);
+  CK(cudaGetLastError());
+  Extra ex = make_extra();
+  ex.adj = ab;
+  ex.nq = 4;
+  int rc = SPHB200_OK;
+  const SweepPlan pf = plan_sweep(e, 4, e->lcap), pd = plan_sweep(e, 1, e->lcap);
+  const bool qsk = c.kernel == SPHB200_KERNEL_QSK;
+#define ADJ(P, PLAN)                                                                                 \
+  do {                                                                                               \
+    if (e->dim == 2) {                                                                               \
+      if (qsk) rc = launch_sweep(e, k_sweep<2, P<2, SPHB200_KERNEL_QSK>, LIST_NONE>, PLAN, F, ex, st); \
+      else rc = launch_sweep(e, k_sweep<2, P<2, SPHB200_KERNEL_WC2K>, LIST_NONE>, PLAN, F, ex, st);   \
+    } else {                                                                                         \
+      if (qsk) rc = launch_sweep(e, k_sweep<3, P<3, SPHB200_KERNEL_QSK>, LIST_NONE>, PLAN, F, ex, st); \
+      else rc = launch_sweep(e, k_sweep<3, P<3, SPHB200_KERNEL_WC2K>, LIST_NONE>, PLAN, F, ex, st);   \
+    }                                                                                                \
+  } while (0)
+  ADJ(PhysForceAdj, pf);
+  if (rc) return rc;
+  k_adj_eos<<<nb, 256, 0, st>>>(n, e->consts, F, ab, ct);
+  CK(cudaGetLastError());
+  ex.nq = 1;
+  ADJ(PhysDensAdj, pd);
+#undef ADJ
+  if (rc) return rc;
+  if (e->dim == 2) k_adj_finish<2><<<nb, 256, 0, st>>>(n, F, ab, ct, out, (float)dt, integrate);
+  else k_adj_finish<3><<<nb, 256, 0, st>>>(n, F, ab, ct, out, (float)dt, integrate);
+  CK(cudaGetLastError());
+  e->launches += 3;
   return SPHB200_OK;
 }
 

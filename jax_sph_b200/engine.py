@@ -351,6 +351,27 @@ class Engine:
         res.update({k: dst[k] for k in written})
         return res
 
+    def vjp(self, dt: float, cot: Dict, integrate: bool = True) -> Dict:
+        """Vector-Jacobian product of the step this engine ran LAST (`step(dt, 1)`, or
+        `step(0, 1, integrate=False)` for forward() alone) at the state it holds: `cot` maps
+        output names (r, u, v, dudt, rho, p) to cotangent CUDA tensors in the caller's particle
+        order, the result maps the step's inputs (r, u, v, dudt, dvdt, rho, p) to theirs
+        (sphb200_engine_vjp, csrc/adjoint.cuh).  The counterpart of jax.vjp on `advance`
+        (jax_sph/integrator.py:22-56); SPH with summation density and tvf = 0."""
+        torch = _torch()
+        names = ("r", "u", "v", "dudt", "dvdt", "rho", "p")
+        cin = {k: cot[k].to(device="cuda", dtype=torch.float32).contiguous()
+               for k in names if k in cot and cot[k] is not None}
+        out = {k: torch.zeros((self.n, self.dim) if k in _lib.VECTOR_FIELDS else (self.n,),
+                              dtype=torch.float32, device="cuda") for k in names}
+        st_in, _, keep_in = self._state_struct(cin, writable=False)
+        st_out, _, keep_out = self._state_struct(out, writable=True)
+        self._keep = (keep_in, keep_out, cin)
+        flags = _lib.STEP_INTEGRATE if integrate else 0
+        _lib.check(self.lib.sphb200_engine_vjp(self._h, float(dt), flags, C.byref(st_in),
+                                               C.byref(st_out), _stream_ptr()))
+        return out
+
     def error(self) -> int:
         code = C.c_uint32()
         _lib.check(self.lib.sphb200_engine_error(self._h, C.byref(code), _stream_ptr()))
@@ -414,3 +435,33 @@ class Engine:
         return dict(cells=v[0:3], sub=v[3:6], tile=v[6:9], threads=v[9], list_cap=v[10],
                     stage_cap=dict(density=v[11], wall=v[12], force=v[13]), exact_all=v[14],
                     ncells=v[15])
+
+
+def grad_through_steps(cfg, state: Dict, dt: float, nsteps: int, loss_cotangent):
+    """Gradient of a scalar function of the state after `nsteps` x advance(dt) with respect to
+    the initial state -- what `jax.grad` of the loop in notebooks/iclr24_grads.ipynb (cell 5)
+    computes -- by checkpointing every step's input state and calling `Engine.vjp` in reverse.
+
+    loss_cotangent(final_state) -> {name: d loss / d final_state[name]} (CUDA tensors).
+    Returns (final_state, {name: d loss / d state[name]}) for r, u, v, dudt, dvdt."""
+    torch = _torch()
+    n = len(state["r"])
+    eng = Engine(cfg, n)
+    keys = ("r", "u", "v", "dudt", "dvdt", "rho", "p")
+    cur = {k: torch.as_tensor(np.ascontiguousarray(v)).cuda() if not hasattr(v, "is_cuda") else v
+           for k, v in state.items()}
+    saved = []
+    for _ in range(nsteps):
+        saved.append({k: v.clone() for k, v in cur.items()})
+        eng.upload(cur)
+        eng.step(dt, 1)
+        new = eng.download()
+        cur = dict(cur, **new)
+    final = cur
+    cot = {k: v for k, v in loss_cotangent(final).items() if k in keys}
+    for s in reversed(saved):
+        eng.upload(s)
+        eng.step(dt, 1)  # the linearisation point of this step
+        cot = eng.vjp(dt, cot)
+    eng.close()
+    return final, cot

@@ -1,5 +1,5 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 1700 python -m pytest tests/ -m gpu -q --maxfail=30 -p no:cacheprovider > gpurun_out/r2_tests.log 2>&1
-tail -30 gpurun_out/r2_tests.log | cut -c1-220
+timeout 900 python -m pytest tests/test_gpu_vjp.py -m gpu -q -x -p no:cacheprovider > gpurun_out/r2_tests_vjp.log 2>&1
+tail -30 gpurun_out/r2_tests_vjp.log | cut -c1-250
