@@ -406,6 +406,8 @@ def config_of(args, meta):
                        threads=args.threads, list_cap=args.list_cap,
                        tile=[args.tile_x, args.tile_y, args.tile_z] if args.tile_x else None,
                        skin=args.skin,
+                       # every generated state has one eta (verified on the device every step)
+                       uniform_eta=not args.no_uniform_eta,
                        **meta.get("cfg_kwargs", {}))
 
 
@@ -903,6 +905,8 @@ def main():
     ap.add_argument("--tile-z", type=int, default=0)
     ap.add_argument("--skin", type=float, default=0.0,
                     help="neighbour-list skin / cutoff (0 = engine default, < 0 = search every step)")
+    ap.add_argument("--no-uniform-eta", action="store_true",
+                    help="do not promise a uniform viscosity (SPHB200_HINT_UNIFORM_ETA off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -58,6 +58,7 @@ extern "C" {
 #define SPHB200_ERR_OUTSIDE_BOX (1u << 4)       /* a position outside [0, box]: the periodic    *
                                                  * fold assumes shift_fn-wrapped positions       */
 #define SPHB200_ERR_SLAB_OVERFLOW (1u << 5)     /* slab engine: own / halo / migration capacity  */
+#define SPHB200_ERR_HINT (1u << 7)           /* a SPHB200_HINT_* promise of the config does not hold  */
 #define SPHB200_ERR_SLAB_MIGRATION (1u << 6)    /* slab engine: a particle crossed more than the *
                                                  * halo width in one step                        */
 
@@ -164,7 +165,10 @@ typedef struct sphb200_config {
                         * skin since the last one; the exact d^2 < cutoff^2 membership test of
                         * jax_md/partition.py:897 still runs for every pair on every step, so the
                         * neighbour sets are the reference's.  0 = automatic, < 0 = search every step */
-  int32_t reserved[4];
+  uint32_t hints;      /* SPHB200_HINT_*: promises about the state the engine may exploit; each is
+                        * verified on the device every step, a broken one raises
+                        * SPHB200_ERR_HINT in the device error word */
+  int32_t reserved[3];
 } sphb200_config;
 
 /* State dict of the reference (solver.py:930-947), device or host pointers.
@@ -177,6 +181,12 @@ typedef struct sphb200_state {
 } sphb200_state;
 
 typedef struct sphb200_engine sphb200_engine;
+
+/* config hints */
+#define SPHB200_HINT_UNIFORM_ETA (1u << 0) /* state.eta is the same for every particle (every case of
+                                            * the reference sets eta = viscosity, case_setup.py:152-181):
+                                            * eta_ij of solver.py:243 is a constant of the run and the
+                                            * force sweep does not stage eta */
 
 /* step flags */
 #define SPHB200_STEP_INTEGRATE (1u << 0) /* si_euler kick+drift before forward (advance); unset = forward only */

@@ -16,6 +16,8 @@ ABI_VERSION = 3
 OK, EINVAL, ENOMEM, ECUDA, EDTYPE, EUNSUP, ENODEV = 0, -1, -2, -3, -4, -5, -6
 ERR_NEIGHBOR_OVERFLOW, ERR_CELL_OVERFLOW, ERR_STAGE_OVERFLOW, ERR_NONFINITE = 1, 2, 4, 8
 ERR_OUTSIDE_BOX = 16
+ERR_HINT = 128
+HINT_UNIFORM_ETA = 1
 SOLVER = {"SPH": 0, "RIE": 1, "DELTA": 2}
 KERNEL = {"QSK": 0, "WC2K": 1, "CSK": 2, "WC4K": 3, "WC6K": 4, "GK": 5, "SGK": 6}
 EOS_TAIT, EOS_RIEMANN = 0, 1
@@ -52,7 +54,7 @@ class Config(C.Structure):
         ("cell_sub", C.c_int32 * 3), ("tile", C.c_int32 * 3), ("threads", C.c_int32),
         ("list_cap", C.c_int32), ("stage_cap", C.c_int32), ("nl_cap", C.c_int32),
         ("diff_delta", C.c_float), ("diff_alpha", C.c_float), ("skin", C.c_float),
-        ("reserved", C.c_int32 * 4),
+        ("hints", C.c_uint32), ("reserved", C.c_int32 * 3),
     ]
 
 

@@ -106,6 +106,8 @@ struct Extra {
   // compact force records of every slot (duo force sweep: staged by bulk copies, sweep2.cuh)
   float4 *rec0, *rec1, *rec2;
   float* rec_e;
+  const float4* eta_ref;  // SPHB200_HINT_UNIFORM_ETA: the (v, eta) quad of the first own slot
+  unsigned* err_word;     // device error word (a broken hint)
   AdjBufs adj;     // adjoint sweeps
   // neighbour-list materialiser
   int* nl_counts;

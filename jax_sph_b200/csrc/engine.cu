@@ -181,6 +181,7 @@ void slab_range(int ng, int r, int p, int& z0, int& z1) {
 
 // Largest record (bytes per staged particle) any sweep of this solver variant stages: the
 // records of phys.cuh (PhysDensity / PhysDelta / PhysRenorm / PhysWall / PhysForce).
+bool duo_variant(const sphb200_config& c);
 int max_stage_bytes(const sphb200_config& c) {
   const bool rie = c.solver == SPHB200_SOLVER_RIE, delta = c.solver == SPHB200_SOLVER_DELTA;
   const bool bc_trick = c.flags & SPHB200_F_BC_TRICK, evol = c.flags & SPHB200_F_RHO_EVOL,
@@ -192,7 +193,9 @@ int max_stage_bytes(const sphb200_config& c) {
   const int force_nq = 3 + ((!rie && c.tvf != 0.0) ? 1 : 0) + (heat ? 1 : 0) + (rie ? 1 : 0) +
                        (has_ut ? 1 : 0);
   const bool generic = rie || heat || c.artificial_alpha != 0.0 || delta;
-  const int force = generic ? 16 * force_nq : (c.tvf != 0.0 ? 52 : 40);
+  // (the duo force sweep under SPHB200_HINT_UNIFORM_ETA stages three quads, no eta column)
+  const bool eta_u = (c.hints & SPHB200_HINT_UNIFORM_ETA) && duo_variant(c);
+  const int force = generic ? 16 * force_nq : (c.tvf != 0.0 ? (eta_u ? 48 : 52) : (duo_variant(c) ? 48 : 40));
   if (force > m) m = force;
   if (bc_trick && !rie && 64 > m) m = 64;  // PhysWall
   if (evol && renorm && 32 > m) m = 32;    // PhysRenorm
@@ -886,7 +889,9 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
   int* const nbad = e->ctl + 4;
   // bytes of the duo force record in shared memory (phys.cuh, PhysForce: FORCE_PLAIN keeps eta and
   // (m/rho)^2 in a third quad there)
-  const int duo_force_sb = force_feat == FORCE_TVF ? 52 : 48;
+  const int duo_feat = (force_feat == FORCE_TVF && (c.hints & SPHB200_HINT_UNIFORM_ETA)) ? FORCE_TVF_U
+                                                                                         : force_feat;
+  const int duo_force_sb = duo_feat == FORCE_TVF ? 52 : 48;
   if (e->duo) {
     planDF = plan_duo(e, duo_force_sb, 0);
     int mc = e->planDB.cap < e->planDA.cap ? e->planDB.cap : e->planDA.cap;
@@ -1053,16 +1058,22 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
       Extra exd = ex;
       exd.sb = duo_force_sb;
       exd.rec0 = e->rec0; exd.rec1 = e->rec1; exd.rec2 = e->rec2; exd.rec_e = e->rec_e;
+      exd.eta_ref = F.vv + e->slab.base;
+      exd.err_word = e->err;
       {
         const int mode = !e->slab_on ? 0 : (part == 1 ? 1 : (part == 2 ? 2 : 0));
         const int nb = stream_blocks(e, e->n);
+#define REC(D, FEAT) k_force_rec<PhysForce<D, SPHB200_KERNEL_QSK, SPHB200_SOLVER_SPH, FEAT>><<<nb, 256, 0, st>>>(e->n, e->slab, mode, F, exd)
         if (e->dim == 2) {
-          if (force_feat == FORCE_PLAIN) k_force_rec<PhysForce<2, SPHB200_KERNEL_QSK, SPHB200_SOLVER_SPH, FORCE_PLAIN>><<<nb, 256, 0, st>>>(e->n, e->slab, mode, F, exd);
-          else k_force_rec<PhysForce<2, SPHB200_KERNEL_QSK, SPHB200_SOLVER_SPH, FORCE_TVF>><<<nb, 256, 0, st>>>(e->n, e->slab, mode, F, exd);
+          if (duo_feat == FORCE_PLAIN) REC(2, FORCE_PLAIN);
+          else if (duo_feat == FORCE_TVF) REC(2, FORCE_TVF);
+          else REC(2, FORCE_TVF_U);
         } else {
-          if (force_feat == FORCE_PLAIN) k_force_rec<PhysForce<3, SPHB200_KERNEL_QSK, SPHB200_SOLVER_SPH, FORCE_PLAIN>><<<nb, 256, 0, st>>>(e->n, e->slab, mode, F, exd);
-          else k_force_rec<PhysForce<3, SPHB200_KERNEL_QSK, SPHB200_SOLVER_SPH, FORCE_TVF>><<<nb, 256, 0, st>>>(e->n, e->slab, mode, F, exd);
+          if (duo_feat == FORCE_PLAIN) REC(3, FORCE_PLAIN);
+          else if (duo_feat == FORCE_TVF) REC(3, FORCE_TVF);
+          else REC(3, FORCE_TVF_U);
         }
+#undef REC
         e->launches++;
         CK(cudaGetLastError());
       }
@@ -1072,6 +1083,14 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
 #undef CALL
         if (rc) return rc;
 #define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>, LIST_CONSUME>, sp, F, ex, st, nlb, nbad, true, false, -1)
+        DISPATCH_DK(e, CALL);
+#undef CALL
+      } else if (duo_feat == FORCE_TVF_U) {
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF_U>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, false, 2)
+        DISPATCH_DK(e, CALL);
+#undef CALL
+        if (rc) return rc;
+#define CALL(D, K) rc = launch_sweep(e, k_sweep<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF>, LIST_CONSUME>, sp, F, ex, st, nlb, nbad, true, false, -1)
         DISPATCH_DK(e, CALL);
 #undef CALL
       } else {
@@ -1277,10 +1296,11 @@ void plan_all(const sphb200_config& c, int64_t n, int rank, int nranks, Grid& g,
   dp.tpb = dp.lmax = dp.rows = dp.desc_stride = 0;
   if (dp.on) {
     // tuned on B200 (profiles/r02_duo_*): one block per SM holds the force record of the stencil
-    dp.tpb = c.dim == 3 ? 352 : 256;
+    // (48-byte force records leave room for a ninth cell along x: 384 threads hold its duos)
+    dp.tpb = c.dim == 3 ? (((c.hints & SPHB200_HINT_UNIFORM_ETA) && c.tvf != 0.0) ? 384 : 352) : 256;
     if (const char* env = getenv("SPHB200_DUO_TPB")) {
       const int v = atoi(env);
-      if (v >= 32 && v <= DUO_MAXT) dp.tpb = (v + 31) / 32 * 32;
+      if (v >= 32 && v <= 384) dp.tpb = (v + 31) / 32 * 32;  // (two lanes per duo in the force sweep)
     }
   }
   plan_grid(c, g, tpb > 512 ? 512 : tpb, rank, nranks, skin, dp.tpb);

@@ -620,7 +620,9 @@ struct PhysWall {
 // is accumulated as  a_i += -(c p_ij) r + (c eta_ij) u_ij + (c (rho_j/2 (v_j-u_j)).r) u_j  and the
 // A_i term is factored out of the sum: 1/2 rho_i u_i ((v_i-u_i) . sum_j c r); sum_j c r is the
 // transport-velocity sum the sweep keeps anyway (dvdt = p_bg sum_j c r, solver.py:199-213).
-enum { FORCE_PLAIN = 0, FORCE_TVF = 1, FORCE_GENERIC = 2 };
+// FORCE_TVF_U: FORCE_TVF under SPHB200_HINT_UNIFORM_ETA (duo sweeps only): eta is not staged, eta_ij
+// is a constant of the duo
+enum { FORCE_PLAIN = 0, FORCE_TVF = 1, FORCE_GENERIC = 2, FORCE_TVF_U = 3 };
 
 template <int DIM, int KERN, int SOLVER, int FEAT>
 struct PhysForce {
@@ -639,6 +641,7 @@ struct PhysForce {
     float dT;
   };
   static constexpr bool COMPACT = SOLVER == SPHB200_SOLVER_SPH && FEAT != FORCE_GENERIC;
+  static constexpr bool TVF = FEAT == FORCE_TVF || FEAT == FORCE_TVF_U;
   template <class F>
   __device__ static void each_acc(Acc& a, F f) {
 #pragma unroll
@@ -719,7 +722,7 @@ struct PhysForce {
   // Extra::rec*): three quads by bulk copy, and for FORCE_TVF the eta column through registers.
   //   quad 2 of FORCE_PLAIN there: (eta, (m/rho)^2, 0, 0)
   static constexpr int DUO_COPIES = COMPACT ? 3 : 0;
-  static constexpr bool DUO_REST = COMPACT && FEAT == FORCE_TVF;
+  static constexpr bool DUO_REST = COMPACT && FEAT == FORCE_TVF;  // (FORCE_TVF_U: no eta column)
   __device__ static void duo_sources(const Frame&, const Extra& ex, const float4* (&a)[COMPACT ? 3 : 1]) {
     if (COMPACT) {
       a[0] = ex.rec0; a[1] = ex.rec1; a[2] = ex.rec2;
@@ -735,17 +738,19 @@ struct PhysForce {
     const float vol = um.w / st.x;
     ex.rec0[gp] = make_float4(pt.x, pt.y, pt.z, st.x);
     ex.rec1[gp] = make_float4(um.x, um.y, um.z, st.y);
-    if (FEAT == FORCE_TVF) {
+    if (TVF) {
       const float hr = 0.5f * st.x;
       ex.rec2[gp] = make_float4(hr * (vv.x - um.x), hr * (vv.y - um.y), hr * (vv.z - um.z), vol * vol);
-      ex.rec_e[gp] = vv.w;
+      if (FEAT == FORCE_TVF) ex.rec_e[gp] = vv.w;
+      else if (vv.w != ex.eta_ref[0].w) atomicOr(ex.err_word, SPHB200_ERR_HINT);  // the promise
     } else {
       ex.rec2[gp] = make_float4(vv.w, vol * vol, 0.f, 0.f);
     }
   }
   struct OwnD {
     F2 u[3];
-    F2 rho, p, eta_e, eta2, inv_m, V2m;  // eta_e = eta + EPS, V2m = (m/rho)^2 / m
+    // eta_e = eta + EPS, V2m = (m/rho)^2 / m; FORCE_TVF_U: eta2 holds eta_ij itself
+    F2 rho, p, eta_e, eta2, inv_m, V2m;
   };
   struct AccD {
     F2 a[3], tv[3];
@@ -757,6 +762,8 @@ struct PhysForce {
     d.p = f2(o0.p, o1.p);
     d.eta_e = f2(o0.eta + 1.1920928955078125e-07f, o1.eta + 1.1920928955078125e-07f);
     d.eta2 = f2(o0.eta2, o1.eta2);
+    if (FEAT == FORCE_TVF_U)  // every eta_j equals the own eta: the pair value, same operations
+      d.eta2 = mul2(mul2(d.eta2, f2(o0.eta, o1.eta)), frcp2(add2(d.eta_e, f2(o0.eta, o1.eta))));
     d.inv_m = f2(o0.inv_m, o1.inv_m);
     d.V2m = f2(o0.V2 * o0.inv_m, o1.V2 * o1.inv_m);
   }
@@ -769,12 +776,12 @@ struct PhysForce {
                                   F2 d2, bool v0, bool v1) {
     const float4 q = sq[cap + j];  // (u_j, p_j)
     const float rho_j = pj.w, p_j = q.w;
-    float eta_j, V2_j, hx = 0.f, hy = 0.f, hz = 0.f;
-    if (FEAT == FORCE_TVF) {
+    float eta_j = 0.f, V2_j, hx = 0.f, hy = 0.f, hz = 0.f;
+    if (TVF) {
       const float4 r = sq[2 * cap + j];
       hx = r.x; hy = r.y; hz = r.z;
       V2_j = r.w;
-      eta_j = reinterpret_cast<const float*>(sq + 3 * cap)[j];
+      if (FEAT == FORCE_TVF) eta_j = reinterpret_cast<const float*>(sq + 3 * cap)[j];
     } else {
       const float4 ev = sq[2 * cap + j];  // duo layout of FORCE_PLAIN: (eta, (m/rho)^2, -, -)
       eta_j = ev.x;
@@ -788,13 +795,14 @@ struct PhysForce {
     const F2 id = frcp2(add2(dist, f2(c.eps)));
     const F2 wv = fma2(f2(V2_j), o.inv_m, o.V2m);                           // :205 / :247
     const F2 cc = sel2(v0, v1, mul2(mul2(wv, gw), id));                     // :206 / :248
-    const F2 eta_ij = mul2(mul2(o.eta2, f2(eta_j)),
-                           frcp2(add2(o.eta_e, f2(eta_j))));                 // :243
+    const F2 eta_ij = FEAT == FORCE_TVF_U ? o.eta2
+                                          : mul2(mul2(o.eta2, f2(eta_j)),
+                                                 frcp2(add2(o.eta_e, f2(eta_j))));  // :243
     const F2 p_ij = mul2(fma2(f2(rho_j), o.p, mul2(o.rho, f2(p_j))),
                          frcp2(add2(o.rho, f2(rho_j))));                     // :244
     const F2 ncp = mul2(cc, neg2(p_ij)), ce = mul2(cc, eta_ij);
     F2 cj = f2(0.0f);
-    if (FEAT == FORCE_TVF) {  // c (A_j r)_k = cj u_j[k]   (:250-251)
+    if (TVF) {  // c (A_j r)_k = cj u_j[k]   (:250-251)
       F2 d = mul2(f2(hx), dr[0]);
       d = fma2(f2(hy), dr[1], d);
       if (DIM == 3) d = fma2(f2(hz), dr[2], d);
@@ -806,7 +814,7 @@ struct PhysForce {
       fma2_into(a.tv[k], cc, dr[k]);                       // sum_j c r  (:199-213, :912-921)
       fma2_into(a.a[k], ncp, dr[k]);                       // -c p_ij r
       fma2_into(a.a[k], ce, sub2(o.u[k], f2(uj[k])));      // c eta_ij u_ij
-      if (FEAT == FORCE_TVF) fma2_into(a.a[k], cj, f2(uj[k]));
+      if (TVF) fma2_into(a.a[k], cj, f2(uj[k]));
     }
   }
   __device__ static void fold_duo(const AccD& d, Acc& a0, Acc& a1) {
@@ -1022,7 +1030,7 @@ struct PhysForce {
     float du[3], dv[3];
     // A_i term of the standard acceleration, factored out of the pair sum (see the header)
     float ai = 0.f;
-    if (SOLVER == SPHB200_SOLVER_SPH && (COMPACT ? FEAT == FORCE_TVF : qv(ex) >= 0))
+    if (SOLVER == SPHB200_SOLVER_SPH && (COMPACT ? TVF : qv(ex) >= 0))
       ai = 0.5f * o.rho * dot3(o.dvu, a.tv, DIM);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {

@@ -22,7 +22,7 @@ def make_config(
     is_bc_trick=False, is_rho_evol=False, is_rho_renorm=False, is_free_slip=False,
     is_heat_conduction=False, artificial_alpha=0.0, g_ext_spec=None, bc_table=None,
     cell_sub=None, tile=None, threads=0, list_cap=0, stage_cap=0, nl_cap=0, g_ext_array=False,
-    r_cutoff=0.0, wall_layer=None, diff_delta=0.1, diff_alpha=0.01, skin=0.0,
+    r_cutoff=0.0, wall_layer=None, diff_delta=0.1, diff_alpha=0.01, skin=0.0, uniform_eta=False,
 ):
     """Build a `sphb200_config` from the WCSPH constructor arguments
     (jax_sph/solver.py:616-637) plus the table forms of the case callables."""
@@ -44,6 +44,8 @@ def make_config(
         cfg.box[a] = float(box[a])
     cfg.dx = dx
     cfg.h = h_fac * dx
+    # promises about the state (verified on the device every step: SPHB200_ERR_HINT)
+    cfg.hints = _lib.HINT_UNIFORM_ETA if uniform_eta else 0
     cfg.dt = dt
     cfg.tvf = tvf
     cfg.c_ref = c_ref
@@ -165,7 +167,11 @@ def live_fields(cfg):
 def config_from_setup(setup, **tuning):
     """`setup` is anything exposing the fields of the reference's
     SimulationSetup / WCSPH call (jax_sph/simulate.py:49-69): used by tests and
-    bench with the oracle's case objects -- only plain attributes are read."""
+    bench with the oracle's case objects -- only plain attributes are read.  The uniform-viscosity
+    hint is set when the setup's state says so (every reference case: eta = viscosity)."""
+    if "uniform_eta" not in tuning:
+        eta = getattr(setup, "state", {}).get("eta") if isinstance(getattr(setup, "state", None), dict) else None
+        tuning = dict(tuning, uniform_eta=bool(eta is not None and len(eta) and np.ptp(np.asarray(eta)) == 0.0))
     return make_config(
         setup.dim, setup.box_size, setup.dx, setup.dt, solver=setup.solver, kernel=setup.kernel,
         h_fac=setup.h_factor, tvf=setup.tvf, p_ref=setup.p_ref, rho_ref=setup.rho_ref,

@@ -124,7 +124,8 @@ def _prepare_tgv(cfg) -> _Prepared:
         is_rho_renorm=g(cfg, "solver.density_renormalize"), is_free_slip=g(cfg, "solver.free_slip"),
         is_heat_conduction=g(cfg, "solver.heat_conduction"),
         artificial_alpha=g(cfg, "solver.artificial_alpha"),
-        diff_delta=g(cfg, "solver.diff_delta"), diff_alpha=g(cfg, "solver.diff_alpha"))
+        diff_delta=g(cfg, "solver.diff_delta"), diff_alpha=g(cfg, "solver.diff_alpha"),
+        uniform_eta=_uniform_eta(cfg))
     state = case_setup.init_lattice(lat)
     # SimulationSetup.initialize() (jax_sph/case_setup.py:126-194), in its order: positions (the
     # lattice, or for r0_type == "relaxed" those of data_relaxed/<name>.h5, cases/tgv.py:20-23 +
@@ -258,6 +259,7 @@ def _prepare_channel(cfg) -> _Prepared:
         is_heat_conduction=g(cfg, "solver.heat_conduction"),
         artificial_alpha=g(cfg, "solver.artificial_alpha"),
         diff_delta=g(cfg, "solver.diff_delta"), diff_alpha=g(cfg, "solver.diff_alpha"),
+        uniform_eta=_uniform_eta(cfg),
         g_ext_spec=ht["g_ext_spec"], bc_table=ht["bc_table"])
     state = case_setup.init_lattice(lat)
     if g(cfg, "case.r0_noise_factor") != 0.0:  # case_setup.py:138-144 (velocities stay zero)
@@ -279,6 +281,14 @@ def _prepare_setup(cfg, setup, tuning) -> _Prepared:
         seq = int(io_state._get(cfg, "solver.t_end") / dt)
     return _Prepared(config_from_setup(setup, **tuning), setup.state, dt, int(seq), setup.dx,
                      len(setup.state["r"]))
+
+
+def _uniform_eta(cfg) -> bool:
+    """The state the driver builds carries eta = case.viscosity for every particle
+    (case_setup.py:152-181) unless a restart file overwrites it."""
+    keys = io_state._get(cfg, "case.state0_keys") if _has(cfg, "case.state0_keys") else ()
+    path = io_state._get(cfg, "case.state0_path") if _has(cfg, "case.state0_path") else None
+    return not (path and "eta" in (keys or ()))
 
 
 def log_line(step: int, sequence_length: int, dt: float, stats: Dict) -> str:

@@ -175,3 +175,45 @@ def test_duo_vs_oracle_on_clustered_particles(name):
     assert eng.error() == 0 and eng.counters()["duo"]
     for k in ADV_KEYS:
         assert_close(k, got[k].numpy(), ref[k], setup, factor=4.0, what=f"{name} clustered vs oracle")
+
+
+@pytest.mark.parametrize("name", ["tgv3d_tvf", "tgv2d_tvf"])
+def test_uniform_viscosity_hint(name):
+    """SPHB200_HINT_UNIFORM_ETA (every reference case sets eta = viscosity, case_setup.py:152-181):
+    the duo force sweep stages no eta column and keeps eta_ij of solver.py:243 per duo.  Same
+    operations on the same values per pair; the smaller record buys a wider tile (384 threads), so
+    the pair sums run in another order and the results agree to rounding, not to the bit.  A state that breaks the promise raises SPHB200_ERR_HINT, and a particle-wise viscosity without
+    the hint still follows the oracle."""
+    from jax_sph_b200 import _lib
+    from oracle import cases, integrator
+
+    kw = dict(CASES[name])
+    if kw["dim"] == 3:
+        kw["dx"] = 2 * np.pi / 32
+    setup = cases.make_case(dtype=np.float32, **kw)
+    setup.state = _clustered(setup, seed=5)
+    out = {}
+    for hint in (False, True):
+        eng = _engine(setup, uniform_eta=hint)
+        eng.upload(setup.state)
+        eng.step(setup.dt, 6)
+        assert eng.error() == 0 and eng.counters()["duo"]
+        out[hint] = {k: v.numpy().copy() for k, v in eng.download(host=True).items()}
+    for k in ADV_KEYS:
+        assert_close(k, out[True][k], out[False][k], setup, factor=2.0, what=f"{name}: hint vs staged eta")
+    # particle-wise viscosity: the promise is broken -> error bit; without the hint -> the oracle
+    rng = np.random.default_rng(11)
+    eta = setup.state["eta"] * rng.uniform(0.5, 1.5, len(setup.state["eta"])).astype(np.float32)
+    setup.state = dict(setup.state, eta=eta)
+    eng = _engine(setup, uniform_eta=True)
+    eng.upload(setup.state)
+    eng.step(setup.dt, 1)
+    assert eng.error() & _lib.ERR_HINT
+    eng = _engine(setup)  # config_from_setup reads the state: no hint
+    eng.upload(setup.state)
+    eng.step(setup.dt, 4)
+    assert eng.error() == 0 and eng.counters()["duo"]
+    got = eng.download(host=True)
+    ref = integrator.simulate(setup, 4, fast_segment_sum=True)
+    for k in ADV_KEYS:
+        assert_close(k, got[k].numpy(), ref[k], setup, factor=3.0, what=f"{name} particle-wise eta vs oracle")

@@ -109,13 +109,15 @@ def test_engine_bytes_scale_with_features():
     heat = nbytes(cases.make_case("ht", dim=3, dx=0.05, dtype=np.float32), nl_cap=-1)
     assert 200 * 100000 < plain < 260 * 100000  # ~212 B / particle + cell tables
     assert heat > plain  # kappa / Cp carried only when heat conduction is on
-    # neighbour lists: the skin list and the exact list of the step, rows of 1.3 x 150 + 8 -> 208
-    # uint16 entries (150 = particles within 1.1 cutoffs: default skin) + a count per particle each
+    # neighbour lists: the skin list and the exact list of the step, rows of 1.3 x 159 + 8 -> 216
+    # uint16 entries (159 = particles within 1.12 cutoffs: default skin of the 3D duo sweeps) + a
+    # count per particle each, + the tile descriptors, compact force records and duo rows of
+    # sweep2.cuh (a few tens of bytes per particle)
     lists = nbytes(tgv) - plain
-    assert 2 * 208 * 2 * 100000 - 65536 <= lists < 2 * (208 * 2 + 4 + 1) * 100000 + 4096
+    assert 2 * 216 * 2 * 100000 - 65536 <= lists < 2 * (216 * 2 + 40) * 100000 + 4096
     # without a skin the rows hold the 113 neighbours of the cutoff sphere: 160 entries
     lists = nbytes(tgv, skin=-1.0) - plain
-    assert 2 * 160 * 2 * 100000 <= lists < 2 * (160 * 2 + 4 + 1) * 100000 + 4096
+    assert 2 * 160 * 2 * 100000 <= lists < 2 * (160 * 2 + 40) * 100000 + 4096
 
 
 def test_bench_ht3d_lattice_is_the_reference_case():

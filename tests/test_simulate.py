@@ -78,7 +78,7 @@ def test_heated_channel_tables_equal_the_oracle_case(dim, dx):
     # the engine config the driver builds == the one built from the oracle's case object
     a = make_config(dim, ht["box"], dx, sim.time_step(cfg), p_ref=100.0, p_bg=5.0, c_ref=10.0,
                     is_bc_trick=True, is_heat_conduction=True, g_ext_spec=ht["g_ext_spec"],
-                    bc_table=ht["bc_table"])
+                    bc_table=ht["bc_table"], uniform_eta=True)
     b = config_from_setup(setup)
     import ctypes as C
 
@@ -338,7 +338,7 @@ def test_poiseuille_tables_equal_the_oracle_case(dim, dx):
     assert abs(g1["lo"] - g2["lo"]) < 1e-12 and abs(g1["hi"] - g2["hi"]) < 1e-12
     a = make_config(dim, ch["box"], dx, setup.dt, p_ref=setup.p_ref, p_bg=setup.p_bg,
                     c_ref=setup.c_ref, u_ref=1.25, is_bc_trick=True, g_ext_spec=ch["g_ext_spec"],
-                    bc_table=ch["bc_table"])
+                    bc_table=ch["bc_table"], uniform_eta=True)
     b = config_from_setup(setup)
     raw = lambda c: bytes((C.c_char * C.sizeof(type(c))).from_buffer_copy(c))  # noqa: E731
     assert raw(a) == raw(b)
