@@ -514,6 +514,20 @@ def stateless_advance(args, eng_cfg, state, meta, steps):
 
     ms = timed(call(lib.sphb200_advance_persistent), steps)
     lib.sphb200_workspace_release(C.c_void_p(ws.data_ptr()))
+    # the same with the arrays kept in engine order (sphb200_advance_ordered): outputs and order of
+    # one call are the inputs of the next
+    order = [torch.arange(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")]
+
+    def call_ordered(i):
+        _lib.check(lib.sphb200_advance_ordered(
+            C.byref(eng_cfg), n, float(meta["dt"]), C.byref(sts[i % 2]), C.c_void_p(order[i % 2].data_ptr()),
+            C.byref(sts[(i + 1) % 2]), C.c_void_p(order[(i + 1) % 2].data_ptr()), C.c_void_p(err.data_ptr()),
+            C.c_void_p(ws.data_ptr()), nbytes.value, stream))
+
+    timed.i = 0
+    ms_ordered = timed(call_ordered, steps)
+    err_ordered = int(err.item())
+    lib.sphb200_workspace_release(C.c_void_p(ws.data_ptr()))
     ms_scratch = timed(call(lib.sphb200_advance), min(steps, 3))
     return {"value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
             "device_error_word": int(err.item()),
@@ -521,6 +535,12 @@ def stateless_advance(args, eng_cfg, state, meta, steps):
                     "in again call after call (the engine in it keeps the particles cell-sorted "
                     "and the neighbour lists; every call copies the full state in and the full "
                     "state out in the caller's particle order)",
+            "engine_order": {"value": n / (ms_ordered * 1e-3), "unit": UNIT, "ms_per_step": ms_ordered,
+                             "steps": steps, "device_error_word": err_ordered,
+                             "what": "sphb200_advance_ordered: the caller keeps its arrays in the engine's "
+                                     "slot order and an int32 order array carries the particle labels "
+                                     "through the sorts; every call streams the full state (16 entries) "
+                                     "in and out without a permutation"},
             "scratch_workspace": {"value": n / (ms_scratch * 1e-3), "unit": UNIT,
                                   "ms_per_step": ms_scratch,
                                   "what": "sphb200_advance: nothing kept between calls (pack, "
@@ -781,7 +801,11 @@ def run_slab(args, world, rank, local, saved_stdout):
         "config": {"workload": workload_name(args, n_total),
                    "particles_per_gpu": n_own0, "particles_total_after_run": int(tot.item()),
                    "parallelism": f"slab{world}: 1-D slabs of cell layers along axis {eng.axis}, "
-                                  f"halo (one cutoff) + migration every step, NCCL send/recv ring",
+                                  f"halo (one cutoff) + migration every step, transport: " +
+                                  ("pack kernels store into the ring neighbours' symmetric-memory buffers "
+                                   "over NVLink + signal flags (no collective on the data path)"
+                                   if eng.transport == "direct" else "NCCL send/recv ring + all_reduce"),
+                   "transport": eng.transport,
                    "slab": {"layers": [eng.z0, eng.z1], "of": eng.layers, "own_cap": eng.own_cap,
                             "halo_cap": eng.halo_cap, "mig_cap": eng.mig_cap,
                             "message_bytes_per_step_per_rank": int(xbytes),

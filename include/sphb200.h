@@ -339,6 +339,17 @@ int sphb200_slab_counts(sphb200_engine *e, int32_t out[8], void *stream);
 int sphb200_slab_run(sphb200_engine *e, int phase, double dt, uint32_t flags, void *send_lo,
                      void *send_hi, const void *recv_lo, const void *recv_hi, void *stream,
                      int64_t *xbytes);
+/* Transport without collectives (ranks that map each other's device memory: CUDA IPC / symmetric
+ * memory over NVLink).  The engine only ever WRITES the send buffers, and only the live part of
+ * a message (counts travel in the header), so send_lo / send_hi of sphb200_slab_run may be the
+ * ring neighbours' receive buffers themselves: the pack kernels then store straight into the
+ * neighbour's memory and an exchange is a pair of flags (jax_sph_b200/slab.py, DirectRing).
+ * sphb200_slab_set_agree does the same for the re-sort agreement: flag_arrays[r] is rank r's
+ * int32[2][nranks] array as mapped into THIS process (flag_arrays[rank] the local one); phase 0
+ * then stores this rank's word into slot [step parity][rank] of every array and the transport
+ * answers nbytes == -4 with a barrier over all ranks instead of the max-reduction; phase 1 takes
+ * the maximum of the local array.  nranks <= 16; flag_arrays == NULL switches back. */
+int sphb200_slab_set_agree(sphb200_engine *e, int32_t *const *flag_arrays, int nranks);
 
 /* ---- on-device case initialisation ----------
  * Replaces the host-side lattice generators pos_init_cartesian_2d / _3d
@@ -414,6 +425,22 @@ int sphb200_advance(const sphb200_config *cfg, int64_t n, double dt, const sphb2
 int sphb200_advance_persistent(const sphb200_config *cfg, int64_t n, double dt,
                                const sphb200_state *in, sphb200_state *out, uint32_t *err,
                                void *workspace, size_t workspace_bytes, void *stream);
+/* sphb200_advance_persistent for a caller that lets the ENGINE choose the row order of its state
+ * arrays: row p of `in` is taken as the particle in slot p, row p of `out` is the particle the
+ * step left in slot p, and in_order / out_order (int32[n]) carry the particles' labels through
+ * the cell sorts (in_order == NULL: rows are labelled 0 .. n-1 as given; out_order is required).
+ * The reference keeps the caller's order for ever (jax_sph/simulate.py:110-134 carries `state`
+ * from advance() to advance()); a caller that feeds `out` / `out_order` of one call to the next
+ * and un-permutes only where it looks at particles by index (io_state.write_state every
+ * write_every steps: state[k][argsort(order)]) saves the two permuted copies of every step: the
+ * copies in and out are then plain streaming passes and the call costs about what a resident
+ * step costs.  Any row order is accepted -- out = f(in) row for row whatever the workspace held;
+ * rows that do not lie where the workspace's cells expect them simply trigger a sort.  All
+ * sixteen entries of `out` the caller wants must be non-NULL: a step that sorted has moved
+ * every row, including the entries advance() does not change. */
+int sphb200_advance_ordered(const sphb200_config *cfg, int64_t n, double dt, const sphb200_state *in,
+                            const int32_t *in_order, sphb200_state *out, int32_t *out_order,
+                            uint32_t *err, void *workspace, size_t workspace_bytes, void *stream);
 void sphb200_workspace_release(void *workspace);
 
 #ifdef __cplusplus

@@ -111,6 +111,7 @@ SYMBOLS = {
     "sphb200_slab_counts": (C.c_int, [_P, C.POINTER(C.c_int32 * 8), _P]),
     "sphb200_slab_run": (C.c_int, [_P, C.c_int, C.c_double, C.c_uint32, _P, _P, _P, _P, _P,
                                    C.POINTER(C.c_int64)]),
+    "sphb200_slab_set_agree": (C.c_int, [_P, C.POINTER(_P), C.c_int]),
     "sphb200_lattice_rows": (C.c_int64, [C.POINTER(Lattice)]),
     "sphb200_init_lattice": (C.c_int, [C.POINTER(Lattice), C.POINTER(State), _P, _P]),
     "sphb200_eval_velocity": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P]),
@@ -127,6 +128,9 @@ SYMBOLS = {
     "sphb200_advance_persistent": (C.c_int, [C.POINTER(Config), C.c_int64, C.c_double,
                                              C.POINTER(State), C.POINTER(State), _P, _P,
                                              C.c_size_t, _P]),
+    "sphb200_advance_ordered": (C.c_int, [C.POINTER(Config), C.c_int64, C.c_double,
+                                          C.POINTER(State), _P, C.POINTER(State), _P, _P, _P,
+                                          C.c_size_t, _P]),
 }
 
 _lib = None

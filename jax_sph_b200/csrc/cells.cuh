@@ -345,6 +345,21 @@ __global__ void k_gate(int* flag_cur, int* flag_next, int force) {
 // the transport max-reduces the word over the ranks, every rank takes the result.
 __global__ void k_flag_out(const int* flag, int* word) { *word = *flag; }
 __global__ void k_flag_in(const int* word, int* flag) { *flag = *word != 0 ? 1 : 0; }
+// The same agreement without a collective (slab engines whose ranks map each other's memory):
+// every rank stores its word into slot [rank] of every rank's array, the transport runs a
+// barrier, every rank takes the maximum of its own array.
+struct AgreePtrs {
+  int* p[16];
+  int n;
+};
+__global__ void k_flag_bcast(const int* flag, AgreePtrs a, int rank, int off) {
+  if ((int)threadIdx.x < a.n) a.p[threadIdx.x][off + rank] = *flag;
+}
+__global__ void k_flag_in_max(const int* words, int n, int* flag) {
+  int m = 0;
+  for (int i = 0; i < n; ++i) m |= words[i] != 0 ? 1 : 0;
+  *flag = m;
+}
 
 // After a re-sort (k_reorder: frame a -> frame b) the sorted particles go back to frame a, so
 // that the host always launches on the same frame whether or not the device decided to re-sort.

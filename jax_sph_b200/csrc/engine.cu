@@ -81,6 +81,7 @@ struct sphb200_engine {
   float4* rb;               // [n] positions at the last sort
   int* ctl;                 // [0], [1] re-sort flag of even / odd steps, [2] searches so far
   unsigned long long step_no;
+  AgreePtrs agree;  // sphb200_slab_set_agree: every rank's flag array (peer-mapped), n = 0: off
   const int* gate_cur;      // flag word of the step being enqueued (nullptr: ungated)
   bool force_rebuild;       // the next step must sort + search (new state, lists stale)
   bool maybe_drifted;       // particles may have left the cells of the frozen table
@@ -606,7 +607,8 @@ SweepPlan plan_duo(const sphb200_engine* e, int sb, int lcap, int blocks_per_sm 
   // (a block's share of the SM's shared memory when several are to be resident: 1 KB each is
   // the system's)
   const long long room = ((long long)e->max_smem + 1024) / blocks_per_sm - 1024 - 64;
-  const long long fit = (room - (long long)duo_smem_bytes(0, 0, lcap, e->duo_tpb)) / sb;
+  const int desc_ints = lcap > 0 ? 0 : e->duo_desc_stride;  // (lcap > 0: the search, DUO_BUILD)
+  const long long fit = (room - (long long)duo_smem_bytes(0, 0, lcap, e->duo_tpb, desc_ints)) / sb;
   if (want > fit) want = fit;
   if (want > DUO_IDX + 1) want = DUO_IDX + 1;
   want = want / 32 * 32;
@@ -615,7 +617,7 @@ SweepPlan plan_duo(const sphb200_engine* e, int sb, int lcap, int blocks_per_sm 
   p.sb = sb;
   p.cap = (int)want;
   p.lcap = lcap;
-  p.smem = duo_smem_bytes(sb, p.cap, lcap, e->duo_tpb);
+  p.smem = duo_smem_bytes(sb, p.cap, lcap, e->duo_tpb, desc_ints);
   return p;
 }
 
@@ -916,7 +918,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
     ex.finalT = false;
     ex.st_out = e->fr[1 - e->cur].st;
     ex.nq = 1;
-#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysDensity<D, K, DENS_SUM>, DUO_FILTER>, e->planDA, F, ex, st, dl)
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysDensity<D, K, DENS_SUM>, DUO_FILTER>, e->planDA, F, ex, st, dl, nullptr, true)
     DISPATCH_DK(e, CALL);
 #undef CALL
     if (rc) return rc;
@@ -1078,7 +1080,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
         CK(cudaGetLastError());
       }
       if (force_feat == FORCE_PLAIN) {
-#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, false, 2)
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, true, 2)
         DISPATCH_DK(e, CALL);
 #undef CALL
         if (rc) return rc;
@@ -1086,7 +1088,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
         DISPATCH_DK(e, CALL);
 #undef CALL
       } else if (duo_feat == FORCE_TVF_U) {
-#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF_U>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, false, 2)
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF_U>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, true, 2)
         DISPATCH_DK(e, CALL);
 #undef CALL
         if (rc) return rc;
@@ -1094,7 +1096,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
         DISPATCH_DK(e, CALL);
 #undef CALL
       } else {
-#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, false, 2)
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, true, 2)
         DISPATCH_DK(e, CALL);
 #undef CALL
         if (rc) return rc;
@@ -1380,6 +1382,7 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   // half the skin, minus a margin for the rounding of positions and of the accumulated path
   e->path_limit = e->skin_frac > 0.0 ? (float)(0.5 * e->skin_frac * kernel_cutoff(*cfg) * (1.0 - 1e-3)) : -1.0f;
   e->step_no = 0;
+  e->agree.n = 0;
   e->gate_cur = nullptr;
   e->force_rebuild = true;
   e->maybe_drifted = false;
@@ -1692,8 +1695,10 @@ static int ensure_hstage(sphb200_engine* e) {
 }
 
 // rows: particles in *s (slab mode: this rank's own particles, ids = their global indices)
+// in_place (stateless calls in engine order): row p of *s goes into slot p and ids[p] is the
+// particle's label; the cells and lists stay valid as far as the positions allow (k_drift).
 static int upload_impl(sphb200_engine* e, const sphb200_state* s, int rows, const int32_t* ids,
-                       int on_host, void* stream, bool keep_order = false) {
+                       int on_host, void* stream, bool keep_order = false, bool in_place = false) {
   if (!e || !s || !s->r) return SPHB200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const int n = rows, d = e->dim;
@@ -1732,7 +1737,8 @@ static int upload_impl(sphb200_engine* e, const sphb200_state* s, int rows, cons
   // keep_order: the same particles as the resident ones go into the slots they occupy; the
   // cells and lists survive if the new positions are close to the sorted ones (k_drift)
   keep_order = keep_order && e->cells_valid && !e->slab_on && !ids;
-  if (keep_order) {
+  in_place = in_place && e->cells_valid && !e->slab_on && !keep_order;
+  if (keep_order || in_place) {
     e->positions_replaced = true;
   } else {
     e->cur = 0;
@@ -2451,6 +2457,21 @@ static int prelaunch_interior(sphb200_engine* e, int stage, cudaStream_t st) {
   return SPHB200_OK;
 }
 
+int sphb200_slab_set_agree(sphb200_engine* e, int32_t* const* flag_arrays, int nranks) {
+  if (!e || !e->slab_on) return SPHB200_EINVAL;
+  if (!flag_arrays || nranks <= 0) {
+    e->agree.n = 0;
+    return SPHB200_OK;
+  }
+  if (nranks != e->slab_nranks || nranks > 16) return SPHB200_EINVAL;
+  for (int r = 0; r < nranks; ++r) {
+    if (!flag_arrays[r]) return SPHB200_EINVAL;
+    e->agree.p[r] = flag_arrays[r];
+  }
+  e->agree.n = nranks;
+  return SPHB200_OK;
+}
+
 int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, void* send_lo,
                      void* send_hi, const void* recv_lo, const void* recv_hi, void* stream,
                      int64_t* xbytes) {
@@ -2477,7 +2498,11 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
     if (e->profile) cudaEventRecord(e->ev[0], st);
     int rc = drift_step(e, k, st);
     if (rc) return rc;
-    k_flag_out<<<1, 1, 0, st>>>(e->gate_cur, (int*)send_lo);
+    if (e->agree.n > 0)
+      k_flag_bcast<<<1, 32, 0, st>>>(e->gate_cur, e->agree, e->slab_rank,
+                                     (int)((e->step_no - 1ull) & 1ull) * e->agree.n);
+    else
+      k_flag_out<<<1, 1, 0, st>>>(e->gate_cur, (int*)send_lo);
     e->launches++;
     CK(cudaGetLastError());
     *xbytes = -4;
@@ -2485,7 +2510,11 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
   }
   int* fc = e->ctl + ((e->step_no - 1ull) & 1ull);  // the flag word of this step (drift_step)
   if (phase == 1) {
-    k_flag_in<<<1, 1, 0, st>>>((const int*)send_lo, fc);
+    if (e->agree.n > 0)
+      k_flag_in_max<<<1, 1, 0, st>>>(e->agree.p[e->slab_rank] + (int)((e->step_no - 1ull) & 1ull) * e->agree.n,
+                                     e->agree.n, fc);
+    else
+      k_flag_in<<<1, 1, 0, st>>>((const int*)send_lo, fc);
     int rc = hash_cells(e, off, st, fc);  // emigrants -> send buffers (on the steps that sort)
     if (rc) return rc;
     k_mig_header<<<1, 1, 0, st>>>(sl);
@@ -2623,10 +2652,16 @@ static unsigned written_mask(const sphb200_engine* e, bool* rest_some) {
   return DL_R | DL_U | DL_V | DL_RHO | DL_P | DL_DUDT | DL_DVDT;
 }
 
+// ordered: the caller keeps its arrays in ENGINE order (sphb200_advance_ordered): row p goes
+// into slot p and comes back from slot p, in_order / out_order carry the particle labels through
+// the sorts -- no permuted copy on either side of the step.
 static int stateless_step(const sphb200_config* cfg, int64_t n, double dt, uint32_t flags,
                           const sphb200_state* in, sphb200_state* out, uint32_t* err, void* ws,
-                          size_t ws_bytes, void* stream, bool persistent = false) {
+                          size_t ws_bytes, void* stream, bool persistent = false,
+                          bool ordered = false, const int32_t* in_order = nullptr,
+                          int32_t* out_order = nullptr) {
   if (!in || !out || !cfg || !ws) return SPHB200_EINVAL;
+  if (ordered && (!persistent || !out_order)) return SPHB200_EINVAL;
   if (!persistent) {  // scratch workspace: nothing survives the call
     sphb200_engine* e = nullptr;
     int rc = with_engine(cfg, n, ws, ws_bytes, &e);
@@ -2669,9 +2704,16 @@ static int stateless_step(const sphb200_config* cfg, int64_t n, double dt, uint3
   }
   slot->stamp = ++g_stamp;
   sphb200_engine* e = slot->e;
-  rc = hit ? sphb200_engine_refresh(e, in, 0, stream) : sphb200_engine_upload(e, in, 0, stream);
-  if (!rc) rc = sphb200_engine_step(e, dt, 1, flags, stream);
-  if (!rc) {
+  if (ordered) {
+    rc = upload_impl(e, in, (int)n, in_order, 0, stream, false, hit);
+    if (!rc) rc = sphb200_engine_step(e, dt, 1, flags, stream);
+    // every entry comes back from the frame: a step that sorted has moved the rows
+    if (!rc) rc = download_impl(e, out, (int)n, out_order, 0, stream);
+  } else {
+    rc = hit ? sphb200_engine_refresh(e, in, 0, stream) : sphb200_engine_upload(e, in, 0, stream);
+    if (!rc) rc = sphb200_engine_step(e, dt, 1, flags, stream);
+  }
+  if (!rc && !ordered) {
     // entries the step changes come back through the permutation (k_unpack scatters by particle
     // id); the others are the caller's own values: straight copies in -> out
     bool rest_some = false;
@@ -2739,6 +2781,13 @@ int sphb200_advance_persistent(const sphb200_config* cfg, int64_t n, double dt,
                                size_t ws_bytes, void* stream) {
   return stateless_step(cfg, n, dt, SPHB200_STEP_INTEGRATE | SPHB200_STEP_BC, in, out, err, ws,
                         ws_bytes, stream, true);
+}
+
+int sphb200_advance_ordered(const sphb200_config* cfg, int64_t n, double dt, const sphb200_state* in,
+                            const int32_t* in_order, sphb200_state* out, int32_t* out_order,
+                            uint32_t* err, void* ws, size_t ws_bytes, void* stream) {
+  return stateless_step(cfg, n, dt, SPHB200_STEP_INTEGRATE | SPHB200_STEP_BC, in, out, err, ws,
+                        ws_bytes, stream, true, true, in_order, out_order);
 }
 
 }  // extern "C"

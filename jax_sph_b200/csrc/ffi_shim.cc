@@ -36,11 +36,22 @@ ffi::Error Status(int rc) {
   return ffi::Error(ffi::ErrorCode::kInternal, sphb200_strerror(rc));
 }
 
-// The config travels as one opaque attribute (bytes of sphb200_config).
+// The config travels as one string attribute: the bytes of sphb200_config as lower-case hex
+// (a str attribute decodes as std::string_view; an ndarray one would decode as a Span).
 ffi::Error LoadConfig(std::string_view blob, sphb200_config* cfg) {
-  if (blob.size() != sizeof(sphb200_config))
+  if (blob.size() != 2 * sizeof(sphb200_config))
     return ffi::Error(ffi::ErrorCode::kInvalidArgument, "sphb200_config size mismatch");
-  std::memcpy(cfg, blob.data(), sizeof(*cfg));
+  auto nib = [](char ch) -> int {
+    if (ch >= '0' && ch <= '9') return ch - '0';
+    if (ch >= 'a' && ch <= 'f') return ch - 'a' + 10;
+    return -1;
+  };
+  unsigned char* dst = reinterpret_cast<unsigned char*>(cfg);
+  for (size_t i = 0; i < sizeof(*cfg); ++i) {
+    const int hi = nib(blob[2 * i]), lo = nib(blob[2 * i + 1]);
+    if (hi < 0 || lo < 0) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "sphb200_config: not hex");
+    dst[i] = static_cast<unsigned char>(hi * 16 + lo);
+  }
   return ffi::Error::Success();
 }
 

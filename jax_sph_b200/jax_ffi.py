@@ -31,7 +31,7 @@ def register():  # pragma: no cover
 def advance_fn(cfg):  # pragma: no cover
     """`advance(dt, state, neighbors)` as one XLA custom call (drop-in for the jitted
     closure of integrator.py:22-56)."""
-    blob = bytes(cfg)
+    blob = bytes(cfg).hex()  # a str attribute: what the shim's Attr<std::string_view> decodes
 
     def advance(dt, state, neighbors):
         args = [state[k] for k in STATE_ORDER]
@@ -39,7 +39,7 @@ def advance_fn(cfg):  # pragma: no cover
         outs.append(jax.ShapeDtypeStruct((1,), jnp.uint32))
         res = jax.ffi.ffi_call("sphb200_ffi_advance", outs,
                                input_output_aliases={i: i for i in range(len(args))})(
-            *args, config=np.frombuffer(blob, dtype=np.uint8), dt=float(dt))
+            *args, config=blob, dt=float(dt))
         new_state = dict(zip(STATE_ORDER, res[:-1]))
         return new_state, neighbors
 

@@ -76,11 +76,74 @@ def ring_exchange(send_lo, send_hi, recv_lo, recv_hi, rank: int, nranks: int, gr
         w.wait()
 
 
+SIGNAL_TIMEOUT_MS = 20000  # a neighbour that never answers traps the kernel instead of hanging it
+
+
+class DirectRing:
+    """The ring transport without collectives: every rank's receive buffers live in symmetric
+    memory (torch.distributed._symmetric_memory: device memory mapped into all ranks of the node
+    over NVLink / NVSwitch), the engine's pack kernels are handed the ring NEIGHBOURS' receive
+    buffers as their send buffers (include/sphb200.h, sphb200_slab_set_agree) and store the live
+    part of a message straight into them; an exchange is then two flags up and two flags down
+    (put_signal / wait_signal on the signal pads), no copy and no NCCL launch.
+
+    Two sets of receive buffers alternate from exchange to exchange: a rank that signals
+    exchange x has, in stream order, consumed exchange x - 1, so when its neighbour -- which
+    waited for that signal -- stores exchange x + 1 into the same set, nobody reads it any more.
+    The re-sort agreement uses int32[2][nranks] flag arrays (one per step parity) and a barrier.
+    """
+
+    def __init__(self, msg_bytes: int, rank: int, nranks: int, group=None):
+        torch = _torch()
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.rank, self.nranks = rank, nranks
+        self.group = group if group is not None else dist.group.WORLD
+        self.mb = (int(msg_bytes) + 255) // 256 * 256
+        self.flag_off = 4 * self.mb
+        total = self.flag_off + 4096
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.mem = symm_mem.empty(total, dtype=torch.uint8, device=dev)
+        self.mem.zero_()
+        self.hdl = symm_mem.rendezvous(self.mem, group=self.group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        lo, hi = ring_neighbours(rank, nranks)
+        self.lo, self.hi = lo, hi
+        # set s: [recv_lo | recv_hi] at s * 2 mb; my downward message is the lower rank's recv_hi
+        self.recv = [(ptrs[rank] + s * 2 * self.mb, ptrs[rank] + s * 2 * self.mb + self.mb) for s in (0, 1)]
+        self.send = [(ptrs[lo] + s * 2 * self.mb + self.mb, ptrs[hi] + s * 2 * self.mb) for s in (0, 1)]
+        self.flag_ptrs = (C.c_void_p * nranks)(*[p + self.flag_off for p in ptrs])
+        self.x = 0  # exchanges so far
+        torch.cuda.current_stream().synchronize()
+        self.hdl.barrier(3, SIGNAL_TIMEOUT_MS)  # every rank's buffers are zeroed before anyone stores
+
+    def buffers(self):
+        """(send_lo, send_hi, recv_lo, recv_hi) device addresses for the next run_phase: it packs
+        exchange x into the neighbours' set x % 2 and unpacks exchange x - 1 from the local other set."""
+        s = self.x & 1
+        return self.send[s] + self.recv[1 - s]
+
+    def exchange(self):
+        h = self.hdl
+        h.put_signal(self.lo, 0, SIGNAL_TIMEOUT_MS)   # my downward message is complete
+        h.put_signal(self.hi, 1, SIGNAL_TIMEOUT_MS)   # my upward message is complete
+        h.wait_signal(self.hi, 0, SIGNAL_TIMEOUT_MS)  # the upper rank's downward message
+        h.wait_signal(self.lo, 1, SIGNAL_TIMEOUT_MS)  # the lower rank's upward message
+        self.x += 1
+
+    def agree(self):
+        self.hdl.barrier(2, SIGNAL_TIMEOUT_MS)
+
+
 class SlabEngine:
-    """The slab of one rank, resident on the current CUDA device."""
+    """The slab of one rank, resident on the current CUDA device.  `transport`: "nccl"
+    (batch_isend_irecv + all_reduce), "direct" (DirectRing: peer stores + flags), or "auto"
+    (direct when the ranks can map each other's memory, else nccl; SPHB200_SLAB_TRANSPORT
+    overrides)."""
 
     def __init__(self, cfg, rank: Optional[int] = None, nranks: Optional[int] = None, group=None,
-                 own_cap: int = 0, halo_cap: int = 0, mig_cap: int = 0):
+                 own_cap: int = 0, halo_cap: int = 0, mig_cap: int = 0, transport: str = "auto"):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.Sphb200Error("no CUDA device: the engine has no CPU fallback")
@@ -112,6 +175,32 @@ class SlabEngine:
 
             set_wall_layer(self.lib, self._h, self.dim, **cfg.wall_layer)
         self._xev = []
+        import os
+
+        transport = os.environ.get("SPHB200_SLAB_TRANSPORT", transport)
+        self.ring = None
+        if transport not in ("nccl", "direct", "auto"):
+            raise ValueError(f"transport {transport!r}")
+        if transport == "auto":  # (a ring of engines inside one process has no transport at all)
+            import torch.distributed as dist
+
+            if not (dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl"
+                    and dist.get_world_size(group) == self.nranks):
+                transport = "nccl"
+        if transport != "nccl" and self.nranks > 1:
+            try:
+                if self.nranks > 16:
+                    raise RuntimeError("more than 16 ranks")
+                self.ring = DirectRing(self.msg_bytes, self.rank, self.nranks, group)
+                _lib.check(self.lib.sphb200_slab_set_agree(self._h, self.ring.flag_ptrs, self.nranks))
+            except Exception as exc:  # no peer mapping here: the collectives still work
+                if transport == "direct":
+                    raise
+                import warnings
+
+                warnings.warn(f"sphb200 slab transport: symmetric memory unavailable ({exc}); using NCCL")
+                self.ring = None
+        self.transport = "direct" if self.ring is not None else "nccl"
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -191,8 +280,11 @@ class SlabEngine:
             torch = _torch()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        ring_exchange(b["send_lo"][:nbytes], b["send_hi"][:nbytes], b["recv_lo"][:nbytes],
-                      b["recv_hi"][:nbytes], self.rank, self.nranks, self.group)
+        if self.ring is not None:
+            self.ring.exchange()
+        else:
+            ring_exchange(b["send_lo"][:nbytes], b["send_hi"][:nbytes], b["recv_lo"][:nbytes],
+                          b["recv_hi"][:nbytes], self.rank, self.nranks, self.group)
         if self.time_exchanges:
             e1.record()
             self._xev.append((phase, nbytes, e0, e1))
@@ -212,17 +304,23 @@ class SlabEngine:
     def run_phase(self, phase: int, dt: float, flags: int) -> int:
         """Enqueue one phase of the step; returns the bytes of the send buffers the ring
         neighbours need before the next phase (0: the step is complete)."""
-        b = self._buf
+        if self.ring is not None:
+            ptrs = self.ring.buffers()
+        else:
+            b = self._buf
+            ptrs = tuple(b[k].data_ptr() for k in ("send_lo", "send_hi", "recv_lo", "recv_hi"))
         nb = C.c_int64()
         _lib.check(self.lib.sphb200_slab_run(
-            self._h, phase, float(dt), flags, C.c_void_p(b["send_lo"].data_ptr()),
-            C.c_void_p(b["send_hi"].data_ptr()), C.c_void_p(b["recv_lo"].data_ptr()),
-            C.c_void_p(b["recv_hi"].data_ptr()), _stream_ptr(), C.byref(nb)))
+            self._h, phase, float(dt), flags, C.c_void_p(ptrs[0]), C.c_void_p(ptrs[1]),
+            C.c_void_p(ptrs[2]), C.c_void_p(ptrs[3]), _stream_ptr(), C.byref(nb)))
         return int(nb.value)
 
     def _agree(self):
         """The ranks' re-sort decisions (one int32 word each, written by phase 0 into the head of
         the send buffer) -> their maximum, in place: all ranks sort and search, or none does."""
+        if self.ring is not None:
+            self.ring.agree()
+            return
         import torch.distributed as dist
 
         word = self._buf["send_lo"][:4].view(_torch().int32)

@@ -1,5 +1,5 @@
 """Worker of test_gpu_slab_nccl.py: launched with torch.distributed.run, one rank per GPU.
-Every rank steps its slab (NCCL ring transport); rank 0 gathers the global state and checks
+Every rank steps its slab (ring transport chosen by SPHB200_SLAB_TRANSPORT); rank 0 gathers the global state and checks
 it against a single-engine run of the same state."""
 
 import os
@@ -35,6 +35,8 @@ def main():
         setup = cases.make_case(dtype=np.float32, **kw)
         n = len(setup.state["r"])
         eng = SlabEngine(config_from_setup(setup))
+        transport = eng.transport
+        assert transport == os.environ.get("SPHB200_SLAB_TRANSPORT", transport)
         eng.upload(setup.state)
         eng.step(setup.dt, nsteps)
         err = eng.error()
@@ -53,7 +55,7 @@ def main():
             print(f"case {kw['case']}{kw['dim']}d N={n} P={world}: ok", flush=True)
         dist.barrier()
     if rank == 0:
-        print("SLAB_NCCL_OK", flush=True)
+        print(f"SLAB_NCCL_OK transport={transport}", flush=True)
     dist.destroy_process_group()
 
 

@@ -169,6 +169,78 @@ def test_persistent_workspace_advance_is_the_resident_engine():
         assert_close(k, out[k].cpu().numpy(), one[k][p], setup, what="unrelated state, same workspace")
 
 
+def test_ordered_advance_is_the_resident_engine_in_engine_order():
+    """sphb200_advance_ordered: the caller's arrays stay in the engine's slot order from call to
+    call, `order` carries the labels through the sorts.  Un-permuted by `order`, the result is
+    bitwise the resident engine's trajectory (every entry, the constant ones included); a state
+    handed in with rows in an unrelated order still gives that state's own result."""
+    import torch
+
+    from jax_sph_b200 import Engine, _lib, config_from_setup
+    from oracle import integrator as oint
+
+    setup = _case(case="tgv", dim=3, dx=2 * np.pi / 16, tvf=1.0, viscosity=0.02, r0_noise_factor=0.25)
+    # (labels that differ from row numbers, masses that differ from particle to particle: the
+    # constant entries have to travel with their rows)
+    rng = np.random.default_rng(7)
+    setup.state = dict(setup.state, mass=(setup.state["mass"] * rng.uniform(0.99, 1.01, len(setup.state["mass"]))).astype(np.float32))
+    n = len(setup.state["r"])
+    cfg = config_from_setup(setup)
+    nsteps = 12
+    eng = Engine(cfg, n)
+    eng.upload(setup.state)
+    eng.step(setup.dt, nsteps)
+    ref = eng.download()
+    assert 1 <= eng.counters()["searches"] < nsteps
+    lib = _lib.load()
+    nbytes = C.c_size_t()
+    _lib.check(lib.sphb200_workspace_bytes(C.byref(cfg), n, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+    bufs = [_to_cuda(setup.state), {k: torch.empty_like(v) for k, v in _to_cuda(setup.state).items()}]
+    order = [torch.arange(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")]
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def struct(d):
+        st = _lib.State()
+        for k, v in d.items():
+            setattr(st, k, v.data_ptr())
+        return st
+
+    def call(src, o_in, dst, o_out):
+        _lib.check(lib.sphb200_advance_ordered(
+            C.byref(cfg), n, float(setup.dt), C.byref(struct(src)),
+            C.c_void_p(o_in.data_ptr() if o_in is not None else None), C.byref(struct(dst)),
+            C.c_void_p(o_out.data_ptr()), C.c_void_p(err.data_ptr()), C.c_void_p(ws.data_ptr()),
+            nbytes.value, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    moved = 0
+    for i in range(nsteps):
+        call(bufs[i % 2], order[i % 2] if i else None, bufs[(i + 1) % 2], order[(i + 1) % 2])
+        moved += int(not torch.equal(order[0], order[1]))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    assert moved >= 1  # the sorts did move rows
+    got, o = bufs[nsteps % 2], order[nsteps % 2].long()
+    assert torch.equal(torch.sort(o).values, torch.arange(n, device="cuda"))
+    for k in ("r", "u", "v", "rho", "p", "dudt", "dvdt", "tag", "mass", "eta", "T"):
+        back = torch.empty_like(got[k])
+        back[o] = got[k]
+        assert torch.equal(back, ref[k]), k
+    # same workspace, rows in an unrelated order with their labels
+    perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    shuffled = {k: v[perm].contiguous() for k, v in _to_cuda(setup.state).items()}
+    out = {k: torch.empty_like(v) for k, v in shuffled.items()}
+    o_out = torch.empty(n, dtype=torch.int32, device="cuda")
+    call(shuffled, perm.int().contiguous(), out, o_out)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    lib.sphb200_workspace_release(C.c_void_p(ws.data_ptr()))
+    one = oint.simulate(setup, 1, fast_segment_sum=True)
+    oo = o_out.long().cpu().numpy()
+    for k in ("r", "u", "v", "rho", "p", "dudt", "dvdt", "mass"):
+        assert_close(k, out[k].cpu().numpy(), one[k][oo], setup, what="unrelated order, same workspace")
+
+
 def test_determinism_and_host_pointer_path():
     import torch
 

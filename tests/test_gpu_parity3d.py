@@ -6,7 +6,7 @@ walk) and the frozen-sort steps between two searches were never compared with th
 physics there.  Here the oracle (oracle/, the CPU restatement of solver.py:705-949 and
 integrator.py:22-56) runs beside the engine on noisy 3D lattices large enough that
 
-* interior tiles exist (asserted from the engine's own plan: 9 of 100 at 32^3, 48 of 168 for the
+* interior tiles exist (asserted from the engine's own plan: 16 of 108 at 40^3, 48 of 168 for the
   channel),
 * the step sequence contains searches AND frozen steps (asserted from the device counters),
 
@@ -62,8 +62,9 @@ def _oracle_forward(setup, dtype):
 
 
 CASES_3D = {
-    # BASELINE configs[3] (validation/tgv3d.sh) at 32^3 with the lattice noise of case_setup.py:139-144
-    "tgv3d_tvf_32": (dict(case="tgv", dim=3, dx=2 * np.pi / 32, tvf=1.0, viscosity=0.02,
+    # BASELINE configs[3] (validation/tgv3d.sh) at 40^3 with the lattice noise of case_setup.py:139-144
+    # (23 cells per axis: the 9 x 4 x 4 tiles of the uniform-viscosity duo sweeps leave 16 interior)
+    "tgv3d_tvf_40": (dict(case="tgv", dim=3, dx=2 * np.pi / 40, tvf=1.0, viscosity=0.02,
                           r0_noise_factor=0.25), 12),
     # BASELINE configs[4] (cases/ht.yaml, case.dim=3): walls + heat + band force, 89 600 particles
     "ht3d_80": (dict(case="ht", dim=3, dx=0.0125), 4),
