@@ -399,7 +399,8 @@ __device__ __forceinline__ void duo_tiles(const Grid& g, const Consts& c, const 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = TPB >> 5;
   const int nd = dl.desc_stride;
   unsigned bar_parity = 0;
-  int* dbuf[2] = {dbuf0, dbuf1};
+  const int dstride = (int)(dbuf1 - dbuf0);
+  auto dbuf_of = [&](int b) { return dbuf0 + b * dstride; };
 
   auto load_desc = [&](int tq, int* dst) {
     const int tile = tq + g.block0;
@@ -443,18 +444,18 @@ __device__ __forceinline__ void duo_tiles(const Grid& g, const Consts& c, const 
 
   int tq = blockIdx.x, buf = 0;
   if (tq >= g.ntl) return;
-  load_desc(tq, dbuf[0]);
+  load_desc(tq, dbuf0);
   __syncthreads();
-  issue(dbuf[0]);
+  issue(dbuf0);
   for (; tq < g.ntl; tq += gridDim.x) {
-    const int* dsc = dbuf[buf];
+    const int* dsc = dbuf_of(buf);
     const int tq_next = tq + (int)gridDim.x;
     const bool has_next = tq_next < g.ntl;
-    if (has_next) load_desc(tq_next, dbuf[buf ^ 1]);  // complete at the next barrier
+    if (has_next) load_desc(tq_next, dbuf_of(buf ^ 1));  // complete at the next barrier
     const bool live = dsc[DD_OK] != 0 && dsc[1] != 0;
     if (!live) {
       __syncthreads();
-      if (has_next) issue(dbuf[buf ^ 1]);
+      if (has_next) issue(dbuf_of(buf ^ 1));
       buf ^= 1;
       continue;
     }
@@ -562,7 +563,7 @@ __device__ __forceinline__ void duo_tiles(const Grid& g, const Consts& c, const 
         // the last warp has left the pair loop: the staging buffer is free for the next tile,
         // whose copies run under this tile's epilogue and the next tile's own loads
         __syncthreads();
-        if (has_next) issue(dbuf[buf ^ 1]);
+        if (has_next) issue(dbuf_of(buf ^ 1));
       }
       if (have) {
         // the epilogue re-reads the own values (nothing of them has to stay in registers
@@ -580,7 +581,7 @@ __device__ __forceinline__ void duo_tiles(const Grid& g, const Consts& c, const 
     }
     if (tile_duos <= 0) {  // (own particles without duos cannot happen; keep the protocol whole)
       __syncthreads();
-      if (has_next) issue(dbuf[buf ^ 1]);
+      if (has_next) issue(dbuf_of(buf ^ 1));
     }
     buf ^= 1;
   }
@@ -589,7 +590,8 @@ __device__ __forceinline__ void duo_tiles(const Grid& g, const Consts& c, const 
 // (register cap per policy: sweeps with a small staged record run two blocks of up to 384
 // threads per SM, P::DUO_MINB == 2; the block size itself is a run-time choice up to DUO_MAXT)
 // SPLIT (DUO_CONSUME): lanes per duo, see duo_consume.
-template <int DIM, class P, int ROLE, int SPLIT = 1>
+// PIPE (FILTER / CONSUME): persistent blocks with the pipelined tile loop (duo_tiles).
+template <int DIM, class P, int ROLE, int SPLIT = 1, bool PIPE = false>
 __global__ void __maxnreg__(SPLIT > 1 ? 80 : (P::DUO_MINB > 1 ? 80 : 128))
     k_duo(const Grid g, const Consts c, const Frame f, const int* __restrict__ cs,
           const SweepDims sd, const Extra ex, unsigned* __restrict__ err, const DuoList dl) {
@@ -616,15 +618,22 @@ __global__ void __maxnreg__(SPLIT > 1 ? 80 : (P::DUO_MINB > 1 ? 80 : 128))
     fence_mbar_init();
   }
   __syncthreads();
-  if constexpr (ROLE != DUO_BUILD) {
-    // FILTER / CONSUME: the pipelined tile loop (two descriptor buffers behind the staging buffer)
+  if constexpr (ROLE != DUO_BUILD && PIPE) {
+    // two descriptor buffers behind the staging buffer
     duo_tiles<DIM, P, ROLE, SPLIT>(g, c, f, sd, ex, dl, sq, dsc, dsc + (dl.desc_stride + 3) / 4 * 4, &s_bar);
     return;
+  }
+  if (ROLE != DUO_BUILD) {
+    own_off = dsc + DD_OWN_OFF;
+    own_start = dsc + DD_OWN_START;
+    duo_off = dsc + DD_DUO_OFF;
+    row0 = dsc + DD_ROW0;
   }
 
   for (int tq = blockIdx.x; tq < g.ntl; tq += gridDim.x) {
     int b = tq + g.block0;
     const int tile_id = b;
+    if (ROLE != DUO_BUILD && dl.ok[tile_id] == 0) continue;  // swept by sweep.cuh
     if (tq != (int)blockIdx.x) __syncthreads();  // readers of the previous tile's tables are done
 
     // ---- tile geometry (uniform), as in sweep.cuh ----------------------------
@@ -753,6 +762,46 @@ __global__ void __maxnreg__(SPLIT > 1 ? 80 : (P::DUO_MINB > 1 ? 80 : 128))
         // the search stages positions only: one bulk copy per job
         if (len > 0) bulk_g2s(sq + dst, f.pt + src, (unsigned)len * 16u, &s_bar);
       }
+    } else {
+      // ---- descriptor -> shared memory, then one bulk copy per job and staged array ----
+      const int nd = dl.desc_stride;
+      for (int i = tid; i < nd; i += TPB) dsc[i] = __ldg(gdsc + i);
+      __syncthreads();
+      total_staged = dsc[0];
+      tile_n = dsc[1];
+      tile_duos = dsc[2];
+      if (tile_n == 0) continue;
+      const int njobs = dsc[3];
+      const float4* src_arr[P::DUO_COPIES > 0 ? P::DUO_COPIES : 1];
+      P::duo_sources(f, ex, src_arr);
+      if (P::DUO_COPIES > 0) {
+        // every thread issues the copies of its jobs (a copy is issued by one lane at a time, so
+        // the issue is spread over all warps); the arrival that arms the barrier may come after
+        // some copies have completed: the transaction count is signed
+        if (tid == 0) mbar_expect_tx(&s_bar, (unsigned)total_staged * 16u * P::DUO_COPIES);
+        fence_proxy_async();  // the previous tile's reads of the buffer precede the copies
+        for (int job = tid; job < njobs; job += TPB) {
+          const int src = dsc[DD_JOBS + 2 * job], dlen = dsc[DD_JOBS + 2 * job + 1];
+          const int dst = dlen & 0xffff, len = dlen >> 16;
+          if (len > 0) {
+#pragma unroll
+            for (int a = 0; a < P::DUO_COPIES; ++a)
+              bulk_g2s(sq + (size_t)a * sd.cap + dst, src_arr[a] + src, (unsigned)len * 16u, &s_bar);
+          }
+        }
+      }
+      // what the bulk copies do not cover: a 4-byte column (asynchronous 4-byte copies, a warp per
+      // job), or -- a policy without source arrays -- everything, through registers
+      if (P::DUO_COPIES == 0 || P::DUO_REST) {
+        for (int job = warp; job < njobs; job += nwarps) {
+          const int src = dsc[DD_JOBS + 2 * job], dlen = dsc[DD_JOBS + 2 * job + 1];
+          const int dst = dlen & 0xffff, len = dlen >> 16;
+          for (int m = lane; m < len; m += 32) {
+            if (P::DUO_COPIES == 0) P::stage(c, f, ex, src + m, sq, sd.cap, dst + m);
+            else P::stage_rest(c, f, ex, src + m, sq, sd.cap, dst + m);
+          }
+        }
+      }
     }
     bool staged = false;  // the wait for the staged data comes after the thread's own loads
 
@@ -850,6 +899,69 @@ __global__ void __maxnreg__(SPLIT > 1 ? 80 : (P::DUO_MINB > 1 ? 80 : 128))
               s_bad = 1;
           }
           if (rows_fit) dl.scnt[row_run0 + k] = gk + cnt;
+        }
+      } else {
+        // ---------------- list consumer (FILTER: exact test + exact list of the step) ------
+        typename P::Own oA, oB;
+        bool actA = false, actB = false;
+        if (have) {
+          P::load_own(c, f, ex, p0, qA, oA);
+          P::load_own(c, f, ex, p1, qB, oB);
+          actA = P::active(c, oA);
+          actB = has1 && P::active(c, oB);
+        } else {
+          oA = typename P::Own();
+          oB = oA;
+        }
+        typename P::Acc aA, aB;
+        P::init(aA);
+        P::init(aB);
+        const bool any_act = P::SPARSE ? (__syncthreads_or(actA || actB) != 0) : true;
+        const int row = row_run0 + k;
+        int nn = 0;
+        if (any_act && have && (actA || actB)) nn = ROLE == DUO_FILTER ? dl.scnt[row] : dl.xcnt[row];
+        if (!staged) {  // (uniform) the stencil has arrived
+          if (ROLE == DUO_BUILD || P::DUO_COPIES > 0) {
+            mbar_wait(&s_bar, bar_parity);
+            bar_parity ^= 1u;
+          }
+          if (ROLE != DUO_BUILD && P::DUO_REST) cp_async_wait_all();
+          // the far sentinel behind the stencil: what the padding of the skin rows points at
+          if (ROLE == DUO_FILTER && tid == 0)
+            sq[total_staged] = make_float4(DUO_FAR, DUO_FAR, DUO_FAR, 0.f);
+          __syncthreads();
+          staged = true;
+        }
+        if (any_act) {
+          typename D::OwnD od;
+          typename D::AccD ad;
+          D::load(oA, oB, od);
+          D::init(ad);
+          int n_exact = 0;
+          if (interior)
+            duo_consume<DIM, P, true, ROLE == DUO_FILTER, SPLIT>(g, c, ex, dl, sq, sd.cap, row_run0,
+                                                                 nr, k, part, nn, has1, rA, rB, od, ad,
+                                                                 n_exact);
+          else
+            duo_consume<DIM, P, false, ROLE == DUO_FILTER, SPLIT>(g, c, ex, dl, sq, sd.cap, row_run0,
+                                                                  nr, k, part, nn, has1, rA, rB, od,
+                                                                  ad, n_exact);
+          if (SPLIT > 1) D::xsum(ad);
+          D::fold(ad, aA, aB);
+          if (ROLE == DUO_FILTER && have && part == 0) dl.xcnt[row] = n_exact;
+        }
+        if (have) {
+          // the epilogue re-reads the own values (nothing of them has to stay in registers
+          // across the pair loop beyond what the packed body keeps); lanes that share a duo
+          // take one particle each
+          if (SPLIT == 1 || part == 0) {
+            P::load_own(c, f, ex, p0, qA, oA);
+            P::finish(c, f, ex, p0, oA, aA);
+          }
+          if (has1 && (SPLIT == 1 || part == 1)) {
+            P::load_own(c, f, ex, p1, qB, oB);
+            P::finish(c, f, ex, p1, oB, aB);
+          }
         }
       }
     }

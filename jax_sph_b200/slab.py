@@ -143,7 +143,7 @@ class SlabEngine:
     overrides)."""
 
     def __init__(self, cfg, rank: Optional[int] = None, nranks: Optional[int] = None, group=None,
-                 own_cap: int = 0, halo_cap: int = 0, mig_cap: int = 0, transport: str = "auto"):
+                 own_cap: int = 0, halo_cap: int = 0, mig_cap: int = 0, transport: str = "nccl"):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.Sphb200Error("no CUDA device: the engine has no CPU fallback")
