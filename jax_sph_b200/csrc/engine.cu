@@ -887,8 +887,6 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
   SweepPlan planDF = planF;
   DuoList dl{e->duo_desc, e->duo_desc_stride, e->sl_list, e->pl_list, e->sl_cnt, e->pl_cnt,
              e->pl_ok,    e->duo_lmax,        0,          e->duo_rows};
-  // persistent blocks with the pipelined tile loop (sweep2.cuh, duo_tiles): SPHB200_DUO_PIPE=0 / 1
-  static const bool duo_pipe = [] { const char* v = getenv("SPHB200_DUO_PIPE"); return v && v[0] == '1'; }();
   NList nlb{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, e->pl_ok};
   int* const nbad = e->ctl + 4;
   // bytes of the duo force record in shared memory (phys.cuh, PhysForce: FORCE_PLAIN keeps eta and
@@ -920,8 +918,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
     ex.finalT = false;
     ex.st_out = e->fr[1 - e->cur].st;
     ex.nq = 1;
-#define CALL(D, K) rc = duo_pipe ? launch_duo(e, k_duo<D, PhysDensity<D, K, DENS_SUM>, DUO_FILTER, 1, true>, e->planDA, F, ex, st, dl, nullptr, true) \
-                             : launch_duo(e, k_duo<D, PhysDensity<D, K, DENS_SUM>, DUO_FILTER>, e->planDA, F, ex, st, dl)
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysDensity<D, K, DENS_SUM>, DUO_FILTER>, e->planDA, F, ex, st, dl)
     DISPATCH_DK(e, CALL);
 #undef CALL
     if (rc) return rc;
@@ -1083,8 +1080,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
         CK(cudaGetLastError());
       }
       if (force_feat == FORCE_PLAIN) {
-#define CALL(D, K) rc = duo_pipe ? launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>, DUO_CONSUME, 2, true>, planDF, F, exd, st, dl, nullptr, true, 2) \
-                             : launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, false, 2)
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_PLAIN>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, false, 2)
         DISPATCH_DK(e, CALL);
 #undef CALL
         if (rc) return rc;
@@ -1092,8 +1088,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
         DISPATCH_DK(e, CALL);
 #undef CALL
       } else if (duo_feat == FORCE_TVF_U) {
-#define CALL(D, K) rc = duo_pipe ? launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF_U>, DUO_CONSUME, 2, true>, planDF, F, exd, st, dl, nullptr, true, 2) \
-                             : launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF_U>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, false, 2)
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF_U>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, false, 2)
         DISPATCH_DK(e, CALL);
 #undef CALL
         if (rc) return rc;
@@ -1101,8 +1096,7 @@ int forward_stage(sphb200_engine* e, int stage, uint32_t flags, bool v_is_u, cud
         DISPATCH_DK(e, CALL);
 #undef CALL
       } else {
-#define CALL(D, K) rc = duo_pipe ? launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF>, DUO_CONSUME, 2, true>, planDF, F, exd, st, dl, nullptr, true, 2) \
-                             : launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, false, 2)
+#define CALL(D, K) rc = launch_duo(e, k_duo<D, PhysForce<D, K, SPHB200_SOLVER_SPH, FORCE_TVF>, DUO_CONSUME, 2>, planDF, F, exd, st, dl, nullptr, false, 2)
         DISPATCH_DK(e, CALL);
 #undef CALL
         if (rc) return rc;

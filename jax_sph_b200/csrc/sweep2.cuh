@@ -59,7 +59,7 @@ enum { DUO_BUILD = 1, DUO_CONSUME = 2, DUO_FILTER = 3 };
 // (the per-thread columns of DUO_BUILD are strided by the block size; FILTER / CONSUME keep the
 // tile's descriptor, desc_ints > 0, where DUO_BUILD keeps its tile tables)
 __host__ __device__ inline size_t duo_smem_bytes(int sb, int cap, int lcap, int tpb, int desc_ints = 0) {
-  const size_t tables = desc_ints > 0 ? 2 * (((size_t)desc_ints * 4 + 15) / 16 * 16)  // two tiles'
+  const size_t tables = desc_ints > 0 ? ((size_t)desc_ints * 4 + 15) / 16 * 16
                                       : (size_t)(DUO_SOFF + 1 + 4 * (DUO_RUNS + 1)) * 4;
   return (size_t)sb * cap + (size_t)lcap * tpb * 2 + tables;
 }
@@ -380,218 +380,10 @@ constexpr int DD_ROW0 = DD_DUO_OFF + DUO_RUNS + 1;
 constexpr int DD_JOBS = (DD_ROW0 + DUO_RUNS + 3) / 4 * 4;
 __host__ __device__ inline int duo_desc_ints(int rows) { return (DD_JOBS + 2 * 3 * rows + 3) / 4 * 4; }
 
-// ---------------------------------------------------------------------------
-// FILTER / CONSUME: the tile loop of a persistent block, software-pipelined over tiles.
-// One staging buffer cannot hold two stencils, so what overlaps is everything around the pair
-// loop: the NEXT tile's descriptor is fetched into a second descriptor buffer while this tile's
-// pairs run, and its bulk copies are issued as soon as the last warp leaves the pair loop --
-// before this tile's epilogue (global loads and stores of finish()) and the next tile's own
-// loads, which then run under the copies instead of in front of them.
-//   dsc[DD_OK]: the tile's ok byte (dl.ok) travels with the descriptor
-constexpr int DD_OK = 5;
-template <int DIM, class P, int ROLE, int SPLIT>
-__device__ __forceinline__ void duo_tiles(const Grid& g, const Consts& c, const Frame& f,
-                                          const SweepDims& sd, const Extra& ex, const DuoList& dl,
-                                          float4* sq, int* dbuf0, int* dbuf1,
-                                          unsigned long long* s_bar) {
-  using D = Duo<P>;
-  const int TPB = blockDim.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = TPB >> 5;
-  const int nd = dl.desc_stride;
-  unsigned bar_parity = 0;
-  const int dstride = (int)(dbuf1 - dbuf0);
-  auto dbuf_of = [&](int b) { return dbuf0 + b * dstride; };
-
-  auto load_desc = [&](int tq, int* dst) {
-    const int tile = tq + g.block0;
-    const int* gdsc = dl.desc + (size_t)tile * dl.desc_stride;
-    for (int i = tid; i < nd; i += TPB) dst[i] = i == DD_OK ? (int)dl.ok[tile] : __ldg(gdsc + i);
-  };
-  // the copies of a tile whose descriptor is complete in shared memory (after a barrier that also
-  // ends every read of the staging buffer); false: nothing to sweep in this tile
-  auto issue = [&](const int* dsc) -> bool {
-    if (dsc[DD_OK] == 0 || dsc[1] == 0) return false;
-    const int total_staged = dsc[0], njobs = dsc[3];
-    const float4* src_arr[P::DUO_COPIES > 0 ? P::DUO_COPIES : 1];
-    P::duo_sources(f, ex, src_arr);
-    if (P::DUO_COPIES > 0) {
-      // every thread issues the copies of its jobs; the arrival that arms the barrier may come
-      // after some copies have completed: the transaction count is signed
-      if (tid == 0) mbar_expect_tx(s_bar, (unsigned)total_staged * 16u * P::DUO_COPIES);
-      fence_proxy_async();  // the previous tile's reads of the buffer precede the copies
-      for (int job = tid; job < njobs; job += TPB) {
-        const int src = dsc[DD_JOBS + 2 * job], dlen = dsc[DD_JOBS + 2 * job + 1];
-        const int dst = dlen & 0xffff, len = dlen >> 16;
-        if (len > 0) {
-#pragma unroll
-          for (int a = 0; a < P::DUO_COPIES; ++a)
-            bulk_g2s(sq + (size_t)a * sd.cap + dst, src_arr[a] + src, (unsigned)len * 16u, s_bar);
-        }
-      }
-    }
-    if (P::DUO_COPIES == 0 || P::DUO_REST) {
-      for (int job = warp; job < njobs; job += nwarps) {
-        const int src = dsc[DD_JOBS + 2 * job], dlen = dsc[DD_JOBS + 2 * job + 1];
-        const int dst = dlen & 0xffff, len = dlen >> 16;
-        for (int m = lane; m < len; m += 32) {
-          if (P::DUO_COPIES == 0) P::stage(c, f, ex, src + m, sq, sd.cap, dst + m);
-          else P::stage_rest(c, f, ex, src + m, sq, sd.cap, dst + m);
-        }
-      }
-    }
-    return true;
-  };
-
-  int tq = blockIdx.x, buf = 0;
-  if (tq >= g.ntl) return;
-  load_desc(tq, dbuf0);
-  __syncthreads();
-  issue(dbuf0);
-  for (; tq < g.ntl; tq += gridDim.x) {
-    const int* dsc = dbuf_of(buf);
-    const int tq_next = tq + (int)gridDim.x;
-    const bool has_next = tq_next < g.ntl;
-    if (has_next) load_desc(tq_next, dbuf_of(buf ^ 1));  // complete at the next barrier
-    const bool live = dsc[DD_OK] != 0 && dsc[1] != 0;
-    if (!live) {
-      __syncthreads();
-      if (has_next) issue(dbuf_of(buf ^ 1));
-      buf ^= 1;
-      continue;
-    }
-    const int* own_off = dsc + DD_OWN_OFF;
-    const int* own_start = dsc + DD_OWN_START;
-    const int* duo_off = dsc + DD_DUO_OFF;
-    const int* row0 = dsc + DD_ROW0;
-    const int total_staged = dsc[0], tile_duos = dsc[2];
-    // ---- tile geometry (uniform): is there a periodic image inside the stencil? ----
-    int b = tq + g.block0;
-    const int tx = b % g.nt[0];
-    b /= g.nt[0];
-    const int ty = b % g.nt[1];
-    const int tz = b / g.nt[1];
-    const int c0[3] = {g.own_lo[0] + tx * g.T[0], g.own_lo[1] + ty * g.T[1], g.own_lo[2] + tz * g.T[2]};
-    bool interior = true;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const int no = min(g.T[a], g.own_hi[a] - c0[a]);
-      int sa0 = 0, slen = g.n[a];
-      if (g.n[a] >= 2 * g.S[a] + 1) {
-        sa0 = c0[a] - g.S[a];
-        slen = no + 2 * g.S[a];
-      }
-      interior = interior && (a >= DIM || (sa0 + g.goff[a] >= 0 && sa0 + g.goff[a] + slen <= g.ng[a] &&
-                                           g.n[a] >= 2 * g.S[a] + 2));
-    }
-    bool staged = false;
-    for (int ib = 0; ib < tile_duos; ib += TPB / SPLIT) {
-      const bool last_round = ib + TPB / SPLIT >= tile_duos;
-      // ---- the thread's duo ----------------------------------------------------
-      const int t = ib + tid / SPLIT, part = tid % SPLIT;
-      const bool have = t < tile_duos;
-      int run = 0, k = 0, p0 = 0, nr = 1;
-      bool has1 = false;
-      if (have) {
-        while (t >= duo_off[run + 1]) ++run;
-        k = t - duo_off[run];
-        nr = duo_off[run + 1] - duo_off[run];
-        p0 = own_start[run] + 2 * k;
-        has1 = 2 * k + 1 < own_off[run + 1] - own_off[run];
-      }
-      const int p1 = has1 ? p0 + 1 : p0;
-      const int row_run0 = row0[run];
-      float rA[3] = {0.f, 0.f, 0.f}, rB[3] = {0.f, 0.f, 0.f};
-      float4 qA = make_float4(0.f, 0.f, 0.f, 0.f), qB = qA;
-      if (have) {
-        qA = f.pt[p0];
-        qB = f.pt[p1];
-        rA[0] = qA.x; rA[1] = qA.y; rA[2] = qA.z;
-        rB[0] = qB.x; rB[1] = qB.y; rB[2] = qB.z;
-        // no second particle: a position no neighbour is near (every distance overflows to +inf,
-        // which fails the FILTER's test without a special case)
-        if (!has1) rB[0] = rB[1] = rB[2] = DUO_FAR_OWN;
-      }
-      typename P::Own oA, oB;
-      bool actA = false, actB = false;
-      if (have) {
-        P::load_own(c, f, ex, p0, qA, oA);
-        P::load_own(c, f, ex, p1, qB, oB);
-        actA = P::active(c, oA);
-        actB = has1 && P::active(c, oB);
-      } else {
-        oA = typename P::Own();
-        oB = oA;
-      }
-      typename P::Acc aA, aB;
-      P::init(aA);
-      P::init(aB);
-      const bool any_act = P::SPARSE ? (__syncthreads_or(actA || actB) != 0) : true;
-      const int row = row_run0 + k;
-      int nn = 0;
-      if (any_act && have && (actA || actB)) nn = ROLE == DUO_FILTER ? dl.scnt[row] : dl.xcnt[row];
-      if (!staged) {  // (uniform) the stencil has arrived
-        if (P::DUO_COPIES > 0) {
-          mbar_wait(s_bar, bar_parity);
-          bar_parity ^= 1u;
-        }
-        if (P::DUO_REST) cp_async_wait_all();
-        // the far sentinel behind the stencil: what the padding of the skin rows points at
-        if (ROLE == DUO_FILTER && tid == 0)
-          sq[total_staged] = make_float4(DUO_FAR, DUO_FAR, DUO_FAR, 0.f);
-        __syncthreads();
-        staged = true;
-      }
-      if (any_act) {
-        typename D::OwnD od;
-        typename D::AccD ad;
-        D::load(oA, oB, od);
-        D::init(ad);
-        int n_exact = 0;
-        if (interior)
-          duo_consume<DIM, P, true, ROLE == DUO_FILTER, SPLIT>(g, c, ex, dl, sq, sd.cap, row_run0, nr,
-                                                               k, part, nn, has1, rA, rB, od, ad,
-                                                               n_exact);
-        else
-          duo_consume<DIM, P, false, ROLE == DUO_FILTER, SPLIT>(g, c, ex, dl, sq, sd.cap, row_run0, nr,
-                                                                k, part, nn, has1, rA, rB, od, ad,
-                                                                n_exact);
-        if (SPLIT > 1) D::xsum(ad);
-        D::fold(ad, aA, aB);
-        if (ROLE == DUO_FILTER && have && part == 0) dl.xcnt[row] = n_exact;
-      }
-      if (last_round) {
-        // the last warp has left the pair loop: the staging buffer is free for the next tile,
-        // whose copies run under this tile's epilogue and the next tile's own loads
-        __syncthreads();
-        if (has_next) issue(dbuf_of(buf ^ 1));
-      }
-      if (have) {
-        // the epilogue re-reads the own values (nothing of them has to stay in registers
-        // across the pair loop beyond what the packed body keeps); lanes that share a duo
-        // take one particle each
-        if (SPLIT == 1 || part == 0) {
-          P::load_own(c, f, ex, p0, qA, oA);
-          P::finish(c, f, ex, p0, oA, aA);
-        }
-        if (has1 && (SPLIT == 1 || part == 1)) {
-          P::load_own(c, f, ex, p1, qB, oB);
-          P::finish(c, f, ex, p1, oB, aB);
-        }
-      }
-    }
-    if (tile_duos <= 0) {  // (own particles without duos cannot happen; keep the protocol whole)
-      __syncthreads();
-      if (has_next) issue(dbuf_of(buf ^ 1));
-    }
-    buf ^= 1;
-  }
-}
-
 // (register cap per policy: sweeps with a small staged record run two blocks of up to 384
 // threads per SM, P::DUO_MINB == 2; the block size itself is a run-time choice up to DUO_MAXT)
 // SPLIT (DUO_CONSUME): lanes per duo, see duo_consume.
-// PIPE (FILTER / CONSUME): persistent blocks with the pipelined tile loop (duo_tiles).
-template <int DIM, class P, int ROLE, int SPLIT = 1, bool PIPE = false>
+template <int DIM, class P, int ROLE, int SPLIT = 1>
 __global__ void __maxnreg__(SPLIT > 1 ? 80 : (P::DUO_MINB > 1 ? 80 : 128))
     k_duo(const Grid g, const Consts c, const Frame f, const int* __restrict__ cs,
           const SweepDims sd, const Extra ex, unsigned* __restrict__ err, const DuoList dl) {
@@ -618,11 +410,6 @@ __global__ void __maxnreg__(SPLIT > 1 ? 80 : (P::DUO_MINB > 1 ? 80 : 128))
     fence_mbar_init();
   }
   __syncthreads();
-  if constexpr (ROLE != DUO_BUILD && PIPE) {
-    // two descriptor buffers behind the staging buffer
-    duo_tiles<DIM, P, ROLE, SPLIT>(g, c, f, sd, ex, dl, sq, dsc, dsc + (dl.desc_stride + 3) / 4 * 4, &s_bar);
-    return;
-  }
   if (ROLE != DUO_BUILD) {
     own_off = dsc + DD_OWN_OFF;
     own_start = dsc + DD_OWN_START;
@@ -979,7 +766,10 @@ __global__ void __maxnreg__(SPLIT > 1 ? 80 : (P::DUO_MINB > 1 ? 80 : 128))
 template <class P>
 __global__ void __launch_bounds__(256) k_force_rec(int n, Slab sl, int mode, Frame f, Extra ex) {
   int lo = 0, hi = n, lo2 = 0, hi2 = 0;
-  if (sl.dn != nullptr && mode != 0) {
+  if (sl.dn != nullptr && mode == 0) {  // slab engines: the live slots only (halo + own + halo)
+    lo = sl.base - sl.dn[DN_HALO_LO];
+    hi = sl.base + sl.dn[DN_OWN] + sl.dn[DN_HALO_HI];
+  } else if (sl.dn != nullptr) {
     const int own = sl.dn[DN_OWN];
     if (mode == 1) {
       lo = sl.base;

@@ -79,6 +79,21 @@ def ring_exchange(send_lo, send_hi, recv_lo, recv_hi, rank: int, nranks: int, gr
 SIGNAL_TIMEOUT_MS = 20000  # a neighbour that never answers traps the kernel instead of hanging it
 
 
+def direct_ring_layout(ptrs, rank: int, nranks: int, msg_bytes: int):
+    """Addresses of the direct transport.  Every rank's symmetric allocation (base `ptrs[r]` as
+    mapped into THIS process) holds two sets of receive buffers, set s at `s * 2 * mb`:
+    `[recv_lo | recv_hi]`, and the agreement flags behind them.  Returns (mb, recv, send, flags):
+    recv[s] = (recv_lo, recv_hi) of this rank, send[s] = (send_lo, send_hi) = the lower
+    neighbour's recv_hi and the upper neighbour's recv_lo of set s (my downward message is what
+    the rank below receives from above), flags[r] = rank r's flag array."""
+    mb = (int(msg_bytes) + 255) // 256 * 256
+    lo, hi = ring_neighbours(rank, nranks)
+    recv = [(ptrs[rank] + s * 2 * mb, ptrs[rank] + s * 2 * mb + mb) for s in (0, 1)]
+    send = [(ptrs[lo] + s * 2 * mb + mb, ptrs[hi] + s * 2 * mb) for s in (0, 1)]
+    flags = [p + 4 * mb for p in ptrs]
+    return mb, recv, send, flags
+
+
 class DirectRing:
     """The ring transport without collectives: every rank's receive buffers live in symmetric
     memory (torch.distributed._symmetric_memory: device memory mapped into all ranks of the node
@@ -101,19 +116,15 @@ class DirectRing:
         self.rank, self.nranks = rank, nranks
         self.group = group if group is not None else dist.group.WORLD
         self.mb = (int(msg_bytes) + 255) // 256 * 256
-        self.flag_off = 4 * self.mb
-        total = self.flag_off + 4096
+        total = 4 * self.mb + 4096
         dev = torch.device("cuda", torch.cuda.current_device())
         self.mem = symm_mem.empty(total, dtype=torch.uint8, device=dev)
         self.mem.zero_()
         self.hdl = symm_mem.rendezvous(self.mem, group=self.group)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        lo, hi = ring_neighbours(rank, nranks)
-        self.lo, self.hi = lo, hi
-        # set s: [recv_lo | recv_hi] at s * 2 mb; my downward message is the lower rank's recv_hi
-        self.recv = [(ptrs[rank] + s * 2 * self.mb, ptrs[rank] + s * 2 * self.mb + self.mb) for s in (0, 1)]
-        self.send = [(ptrs[lo] + s * 2 * self.mb + self.mb, ptrs[hi] + s * 2 * self.mb) for s in (0, 1)]
-        self.flag_ptrs = (C.c_void_p * nranks)(*[p + self.flag_off for p in ptrs])
+        self.lo, self.hi = ring_neighbours(rank, nranks)
+        _, self.recv, self.send, flags = direct_ring_layout(ptrs, rank, nranks, msg_bytes)
+        self.flag_ptrs = (C.c_void_p * nranks)(*flags)
         self.x = 0  # exchanges so far
         torch.cuda.current_stream().synchronize()
         self.hdl.barrier(3, SIGNAL_TIMEOUT_MS)  # every rank's buffers are zeroed before anyone stores

@@ -65,7 +65,7 @@ CASES_3D = {
     # BASELINE configs[3] (validation/tgv3d.sh) at 40^3 with the lattice noise of case_setup.py:139-144
     # (23 cells per axis: the 9 x 4 x 4 tiles of the uniform-viscosity duo sweeps leave 16 interior)
     "tgv3d_tvf_40": (dict(case="tgv", dim=3, dx=2 * np.pi / 40, tvf=1.0, viscosity=0.02,
-                          r0_noise_factor=0.25), 12),
+                          r0_noise_factor=0.25), 8),
     # BASELINE configs[4] (cases/ht.yaml, case.dim=3): walls + heat + band force, 89 600 particles
     "ht3d_80": (dict(case="ht", dim=3, dx=0.0125), 4),
 }

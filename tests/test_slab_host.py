@@ -103,3 +103,29 @@ def test_ring_exchange_over_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert all(res[r] for r in range(world)), res
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 4, 8])
+def test_direct_ring_layout_pairs_senders_with_receivers(nranks):
+    """The direct transport (slab.py, DirectRing): what rank r packs as its downward / upward
+    message of exchange x is exactly the buffer its lower / upper ring neighbour unpacks as
+    recv_hi / recv_lo after that exchange; the two sets alternate, nothing overlaps, and the
+    agreement flags lie behind the buffers of every rank."""
+    from jax_sph_b200.slab import direct_ring_layout, ring_neighbours
+
+    msg = 1000  # not a multiple of 256: the layout rounds up
+    bases = [0x10000000 * (r + 1) for r in range(nranks)]
+    lay = [direct_ring_layout(bases, r, nranks, msg) for r in range(nranks)]
+    mb = lay[0][0]
+    assert mb % 256 == 0 and mb >= msg
+    for r in range(nranks):
+        lo, hi = ring_neighbours(r, nranks)
+        _, recv, send, flags = lay[r]
+        for x in range(4):
+            s = x & 1
+            # run_phase before exchange x packs into set s; the phase after it unpacks set s
+            assert send[s][0] == lay[lo][1][s][1]  # my send_lo == lower rank's recv_hi
+            assert send[s][1] == lay[hi][1][s][0]  # my send_hi == upper rank's recv_lo
+        spans = sorted((a, a + mb) for s in (0, 1) for a in recv[s])
+        assert all(spans[i][1] <= spans[i + 1][0] for i in range(3))
+        assert flags[r] >= spans[-1][1] and flags == [b + 4 * mb for b in bases]
