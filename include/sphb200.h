@@ -58,6 +58,8 @@ extern "C" {
 #define SPHB200_ERR_OUTSIDE_BOX (1u << 4)       /* a position outside [0, box]: the periodic    *
                                                  * fold assumes shift_fn-wrapped positions       */
 #define SPHB200_ERR_SLAB_OVERFLOW (1u << 5)     /* slab engine: own / halo / migration capacity  */
+#define SPHB200_ERR_SLAB_TIMEOUT (1u << 8)       /* slab engine, direct transport: a ring neighbour's  *
+                                                 * signal did not arrive within 20 s                   */
 #define SPHB200_ERR_HINT (1u << 7)           /* a SPHB200_HINT_* promise of the config does not hold  */
 #define SPHB200_ERR_SLAB_MIGRATION (1u << 6)    /* slab engine: a particle crossed more than the *
                                                  * halo width in one step                        */
@@ -344,12 +346,21 @@ int sphb200_slab_run(sphb200_engine *e, int phase, double dt, uint32_t flags, vo
  * a message (counts travel in the header), so send_lo / send_hi of sphb200_slab_run may be the
  * ring neighbours' receive buffers themselves: the pack kernels then store straight into the
  * neighbour's memory and an exchange is a pair of flags (jax_sph_b200/slab.py, DirectRing).
- * sphb200_slab_set_agree does the same for the re-sort agreement: flag_arrays[r] is rank r's
- * int32[2][nranks] array as mapped into THIS process (flag_arrays[rank] the local one); phase 0
- * then stores this rank's word into slot [step parity][rank] of every array and the transport
- * answers nbytes == -4 with a barrier over all ranks instead of the max-reduction; phase 1 takes
- * the maximum of the local array.  nranks <= 16; flag_arrays == NULL switches back. */
+ * sphb200_slab_set_agree hands the engine every rank's CONTROL BLOCK -- flag_arrays[r] is rank
+ * r's zero-initialised int32[3 * nranks + 2] as mapped into THIS process (flag_arrays[rank] the
+ * local one): agreement words [step parity][source rank], agreement arrivals [source rank],
+ * and the two exchange signals (from above, from below); all signals are sequence numbers that
+ * only grow.  Phase 0 then stores this rank's re-sort word and the step number into every block
+ * and phase 1 waits for all ranks' step numbers and takes the maximum of the local words: the
+ * transport answers nbytes == -4 with nothing at all.  After every phase that returns nbytes > 0
+ * the transport calls sphb200_slab_signal(e, stream) instead of moving bytes: one kernel on the
+ * step's stream that tells both ring neighbours "my messages are complete" (system-scope release
+ * behind the pack kernels' stores) and waits for theirs.  The caller alternates two sets of
+ * receive buffers from exchange to exchange (a rank that signals exchange x has consumed x - 1).
+ * A signal that does not arrive within 20 s raises SPHB200_ERR_SLAB_TIMEOUT instead of hanging.
+ * nranks <= 16; flag_arrays == NULL switches back to the message transport. */
 int sphb200_slab_set_agree(sphb200_engine *e, int32_t *const *flag_arrays, int nranks);
+int sphb200_slab_signal(sphb200_engine *e, void *stream);
 
 /* ---- on-device case initialisation ----------
  * Replaces the host-side lattice generators pos_init_cartesian_2d / _3d

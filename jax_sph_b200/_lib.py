@@ -17,6 +17,7 @@ OK, EINVAL, ENOMEM, ECUDA, EDTYPE, EUNSUP, ENODEV = 0, -1, -2, -3, -4, -5, -6
 ERR_NEIGHBOR_OVERFLOW, ERR_CELL_OVERFLOW, ERR_STAGE_OVERFLOW, ERR_NONFINITE = 1, 2, 4, 8
 ERR_OUTSIDE_BOX = 16
 ERR_HINT = 128
+ERR_SLAB_TIMEOUT = 256
 HINT_UNIFORM_ETA = 1
 SOLVER = {"SPH": 0, "RIE": 1, "DELTA": 2}
 KERNEL = {"QSK": 0, "WC2K": 1, "CSK": 2, "WC4K": 3, "WC6K": 4, "GK": 5, "SGK": 6}
@@ -112,6 +113,7 @@ SYMBOLS = {
     "sphb200_slab_run": (C.c_int, [_P, C.c_int, C.c_double, C.c_uint32, _P, _P, _P, _P, _P,
                                    C.POINTER(C.c_int64)]),
     "sphb200_slab_set_agree": (C.c_int, [_P, C.POINTER(_P), C.c_int]),
+    "sphb200_slab_signal": (C.c_int, [_P, _P]),
     "sphb200_lattice_rows": (C.c_int64, [C.POINTER(Lattice)]),
     "sphb200_init_lattice": (C.c_int, [C.POINTER(Lattice), C.POINTER(State), _P, _P]),
     "sphb200_eval_velocity": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P]),

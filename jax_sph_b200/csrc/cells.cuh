@@ -345,20 +345,72 @@ __global__ void k_gate(int* flag_cur, int* flag_next, int force) {
 // the transport max-reduces the word over the ranks, every rank takes the result.
 __global__ void k_flag_out(const int* flag, int* word) { *word = *flag; }
 __global__ void k_flag_in(const int* word, int* flag) { *flag = *word != 0 ? 1 : 0; }
-// The same agreement without a collective (slab engines whose ranks map each other's memory):
-// every rank stores its word into slot [rank] of every rank's array, the transport runs a
-// barrier, every rank takes the maximum of its own array.
+// The same agreement, and the ring exchange, without a collective (slab engines whose ranks map
+// each other's memory, include/sphb200.h: sphb200_slab_set_agree).  Every rank owns a control
+// block of int32 words, mapped into all ranks:
+//   [0, 2n)    agreement words [step parity][source rank]
+//   [2n, 3n)   agreement arrivals [source rank]: the step number of the last word stored
+//   [3n]       exchange signal from the rank above (its downward message is complete)
+//   [3n + 1]   exchange signal from the rank below
+// Signals are sequence numbers that only grow: a waiter spins until the word reaches the number it
+// expects (system-scope acquire), a producer stores it after a system-scope fence behind its
+// data.  A wait that lasts longer than `timeout_ns` gives up and raises SPHB200_ERR_SLAB_TIMEOUT.
 struct AgreePtrs {
   int* p[16];
   int n;
 };
-__global__ void k_flag_bcast(const int* flag, AgreePtrs a, int rank, int off) {
-  if ((int)threadIdx.x < a.n) a.p[threadIdx.x][off + rank] = *flag;
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
-__global__ void k_flag_in_max(const int* words, int n, int* flag) {
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool wait_reach(const int* p, int want, unsigned long long timeout_ns) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (ld_acquire_sys(p) - want < 0) {  // (difference: wrap-safe)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) return false;
+    __nanosleep(200);
+  }
+  return true;
+}
+__global__ void k_flag_bcast(const int* flag, AgreePtrs a, int rank, int off, int seq) {
+  if ((int)threadIdx.x < a.n) {
+    int* blk = a.p[threadIdx.x];
+    blk[off + rank] = *flag;
+    __threadfence_system();
+    st_release_sys(blk + 2 * a.n + rank, seq);
+  }
+}
+__global__ void k_flag_in_max(const int* blk, int n, int off, int seq, int* flag,
+                              unsigned* __restrict__ err, unsigned long long timeout_ns) {
   int m = 0;
-  for (int i = 0; i < n; ++i) m |= words[i] != 0 ? 1 : 0;
-  *flag = m;
+  if ((int)threadIdx.x < n) {
+    if (!wait_reach(blk + 2 * n + threadIdx.x, seq, timeout_ns)) atomicOr(err, SPHB200_ERR_SLAB_TIMEOUT);
+    m = blk[off + threadIdx.x] != 0 ? 1 : 0;
+  }
+  m = __any_sync(0xffffffffu, m != 0) ? 1 : 0;
+  if (threadIdx.x == 0) *flag = m;
+}
+// one exchange of the direct ring: my two messages are complete (the pack kernels ran earlier on
+// this stream) -> tell both neighbours, then wait for theirs
+__global__ void k_ring_signal(AgreePtrs a, int lo, int hi, int rank, int seq,
+                              unsigned* __restrict__ err, unsigned long long timeout_ns) {
+  const int n = a.n;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    st_release_sys(a.p[lo] + 3 * n, seq);      // the rank below: "from above"
+  } else if (threadIdx.x == 1) {
+    __threadfence_system();
+    st_release_sys(a.p[hi] + 3 * n + 1, seq);  // the rank above: "from below"
+  } else if (threadIdx.x == 2 || threadIdx.x == 3) {
+    const int* w = a.p[rank] + 3 * n + (threadIdx.x - 2);
+    if (!wait_reach(w, seq, timeout_ns)) atomicOr(err, SPHB200_ERR_SLAB_TIMEOUT);
+  }
 }
 
 // After a re-sort (k_reorder: frame a -> frame b) the sorted particles go back to frame a, so

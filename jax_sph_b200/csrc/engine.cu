@@ -81,7 +81,8 @@ struct sphb200_engine {
   float4* rb;               // [n] positions at the last sort
   int* ctl;                 // [0], [1] re-sort flag of even / odd steps, [2] searches so far
   unsigned long long step_no;
-  AgreePtrs agree;  // sphb200_slab_set_agree: every rank's flag array (peer-mapped), n = 0: off
+  AgreePtrs agree;  // sphb200_slab_set_agree: every rank's control block (peer-mapped), n = 0: off
+  int ring_seq;     // exchanges signalled so far (sphb200_slab_signal)
   const int* gate_cur;      // flag word of the step being enqueued (nullptr: ungated)
   bool force_rebuild;       // the next step must sort + search (new state, lists stale)
   bool maybe_drifted;       // particles may have left the cells of the frozen table
@@ -1383,6 +1384,7 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
   e->path_limit = e->skin_frac > 0.0 ? (float)(0.5 * e->skin_frac * kernel_cutoff(*cfg) * (1.0 - 1e-3)) : -1.0f;
   e->step_no = 0;
   e->agree.n = 0;
+  e->ring_seq = 0;
   e->gate_cur = nullptr;
   e->force_rebuild = true;
   e->maybe_drifted = false;
@@ -2457,6 +2459,19 @@ static int prelaunch_interior(sphb200_engine* e, int stage, cudaStream_t st) {
   return SPHB200_OK;
 }
 
+// a neighbour that never answers costs this long, then the error word says so
+static const unsigned long long SLAB_SIGNAL_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+
+int sphb200_slab_signal(sphb200_engine* e, void* stream) {
+  if (!e || !e->slab_on || e->agree.n <= 0) return SPHB200_EINVAL;
+  const int n = e->agree.n, r = e->slab_rank;
+  k_ring_signal<<<1, 32, 0, (cudaStream_t)stream>>>(e->agree, (r + n - 1) % n, (r + 1) % n, r, ++e->ring_seq,
+                                                    e->err, SLAB_SIGNAL_TIMEOUT_NS);
+  e->launches++;
+  CK(cudaGetLastError());
+  return SPHB200_OK;
+}
+
 int sphb200_slab_set_agree(sphb200_engine* e, int32_t* const* flag_arrays, int nranks) {
   if (!e || !e->slab_on) return SPHB200_EINVAL;
   if (!flag_arrays || nranks <= 0) {
@@ -2500,7 +2515,7 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
     if (rc) return rc;
     if (e->agree.n > 0)
       k_flag_bcast<<<1, 32, 0, st>>>(e->gate_cur, e->agree, e->slab_rank,
-                                     (int)((e->step_no - 1ull) & 1ull) * e->agree.n);
+                                     (int)((e->step_no - 1ull) & 1ull) * e->agree.n, (int)e->step_no);
     else
       k_flag_out<<<1, 1, 0, st>>>(e->gate_cur, (int*)send_lo);
     e->launches++;
@@ -2511,8 +2526,9 @@ int sphb200_slab_run(sphb200_engine* e, int phase, double dt, uint32_t flags, vo
   int* fc = e->ctl + ((e->step_no - 1ull) & 1ull);  // the flag word of this step (drift_step)
   if (phase == 1) {
     if (e->agree.n > 0)
-      k_flag_in_max<<<1, 1, 0, st>>>(e->agree.p[e->slab_rank] + (int)((e->step_no - 1ull) & 1ull) * e->agree.n,
-                                     e->agree.n, fc);
+      k_flag_in_max<<<1, 32, 0, st>>>(e->agree.p[e->slab_rank], e->agree.n,
+                                      (int)((e->step_no - 1ull) & 1ull) * e->agree.n, (int)e->step_no, fc,
+                                      e->err, SLAB_SIGNAL_TIMEOUT_NS);
     else
       k_flag_in<<<1, 1, 0, st>>>((const int*)send_lo, fc);
     int rc = hash_cells(e, off, st, fc);  // emigrants -> send buffers (on the steps that sort)

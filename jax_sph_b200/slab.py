@@ -99,13 +99,15 @@ class DirectRing:
     memory (torch.distributed._symmetric_memory: device memory mapped into all ranks of the node
     over NVLink / NVSwitch), the engine's pack kernels are handed the ring NEIGHBOURS' receive
     buffers as their send buffers (include/sphb200.h, sphb200_slab_set_agree) and store the live
-    part of a message straight into them; an exchange is then two flags up and two flags down
-    (put_signal / wait_signal on the signal pads), no copy and no NCCL launch.
+    part of a message straight into them; an exchange is then two flags out and two flags in
+    (sequence numbers in every rank's control block, one kernel: sphb200_slab_signal), no copy and
+    no NCCL launch.
 
     Two sets of receive buffers alternate from exchange to exchange: a rank that signals
     exchange x has, in stream order, consumed exchange x - 1, so when its neighbour -- which
     waited for that signal -- stores exchange x + 1 into the same set, nobody reads it any more.
-    The re-sort agreement uses int32[2][nranks] flag arrays (one per step parity) and a barrier.
+    The re-sort agreement is part of the same control block (words per step parity + arrival
+    numbers): the phase kernels store and wait themselves.
     """
 
     def __init__(self, msg_bytes: int, rank: int, nranks: int, group=None):
@@ -136,15 +138,9 @@ class DirectRing:
         return self.send[s] + self.recv[1 - s]
 
     def exchange(self):
-        h = self.hdl
-        h.put_signal(self.lo, 0, SIGNAL_TIMEOUT_MS)   # my downward message is complete
-        h.put_signal(self.hi, 1, SIGNAL_TIMEOUT_MS)   # my upward message is complete
-        h.wait_signal(self.hi, 0, SIGNAL_TIMEOUT_MS)  # the upper rank's downward message
-        h.wait_signal(self.lo, 1, SIGNAL_TIMEOUT_MS)  # the lower rank's upward message
+        """The pack kernels of the last phase have stored exchange x into the neighbours' set
+        x % 2; the engine's signal kernel (one launch: two flags out, two flags in) does the rest."""
         self.x += 1
-
-    def agree(self):
-        self.hdl.barrier(2, SIGNAL_TIMEOUT_MS)
 
 
 class SlabEngine:
@@ -154,7 +150,7 @@ class SlabEngine:
     overrides)."""
 
     def __init__(self, cfg, rank: Optional[int] = None, nranks: Optional[int] = None, group=None,
-                 own_cap: int = 0, halo_cap: int = 0, mig_cap: int = 0, transport: str = "nccl"):
+                 own_cap: int = 0, halo_cap: int = 0, mig_cap: int = 0, transport: str = "auto"):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.Sphb200Error("no CUDA device: the engine has no CPU fallback")
@@ -292,6 +288,7 @@ class SlabEngine:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         if self.ring is not None:
+            _lib.check(self.lib.sphb200_slab_signal(self._h, _stream_ptr()))
             self.ring.exchange()
         else:
             ring_exchange(b["send_lo"][:nbytes], b["send_hi"][:nbytes], b["recv_lo"][:nbytes],
@@ -329,8 +326,7 @@ class SlabEngine:
     def _agree(self):
         """The ranks' re-sort decisions (one int32 word each, written by phase 0 into the head of
         the send buffer) -> their maximum, in place: all ranks sort and search, or none does."""
-        if self.ring is not None:
-            self.ring.agree()
+        if self.ring is not None:  # (the agreement travels with the phase kernels' own flags)
             return
         import torch.distributed as dist
 
