@@ -137,20 +137,23 @@ struct Duo<P, true> {
 };
 
 // Reference displacement r_i - r_j (space.py:170-181) of one staged neighbour for both particles
-// of the duo (INTERIOR: no periodic image inside the tile's stencil, see sweep.cuh pair_disp).
+// of the duo.  INTERIOR: no periodic image inside the tile's stencil (see sweep.cuh pair_disp);
+// otherwise `wrap` says along which axes there is one (uniform per tile: a tile on a face of the
+// box folds along one axis only, the others keep the three packed operations).
 template <int DIM, bool INTERIOR>
 __device__ __forceinline__ void duo_disp(const Grid& g, const F2 (&ri)[3], const float (&rA)[3],
-                                         const float (&rB)[3], const float4 pj, F2 (&dr)[3]) {
-  if (INTERIOR) {
-    dr[0] = disp2_nowrap2(ri[0], pj.x, g.half[0]);
-    dr[1] = disp2_nowrap2(ri[1], pj.y, g.half[1]);
-    dr[2] = (DIM == 3) ? disp2_nowrap2(ri[2], pj.z, g.half[2]) : f2(0.0f);
-  } else {
-    dr[0] = f2(disp1(rA[0], pj.x, g.half[0], g.box[0]), disp1(rB[0], pj.x, g.half[0], g.box[0]));
-    dr[1] = f2(disp1(rA[1], pj.y, g.half[1], g.box[1]), disp1(rB[1], pj.y, g.half[1], g.box[1]));
-    dr[2] = (DIM == 3) ? f2(disp1(rA[2], pj.z, g.half[2], g.box[2]),
-                            disp1(rB[2], pj.z, g.half[2], g.box[2]))
-                       : f2(0.0f);
+                                         const float (&rB)[3], const float4 pj, F2 (&dr)[3],
+                                         unsigned wrap) {
+  const float pc[3] = {pj.x, pj.y, pj.z};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (a >= DIM) {
+      dr[a] = f2(0.0f);
+    } else if (INTERIOR || !(wrap & (1u << a))) {
+      dr[a] = disp2_nowrap2(ri[a], pc[a], g.half[a]);
+    } else {
+      dr[a] = f2(disp1(rA[a], pc[a], g.half[a], g.box[a]), disp1(rB[a], pc[a], g.half[a], g.box[a]));
+    }
   }
 }
 
@@ -166,7 +169,7 @@ template <int DIM, class P, bool INTERIOR, bool FILTER, int SPLIT>
 __device__ __forceinline__ void duo_consume(const Grid& g, const Consts& c, const Extra& ex,
                                             const DuoList& dl, const float4* sq, int cap,
                                             int row_run0, int nr, int k, int part, int nn, bool has1,
-                                            const float (&rA)[3], const float (&rB)[3],
+                                            unsigned wrap, const float (&rA)[3], const float (&rB)[3],
                                             const typename Duo<P>::OwnD& own,
                                             typename Duo<P>::AccD& acc, int& n_exact) {
   using D = Duo<P>;
@@ -194,7 +197,7 @@ __device__ __forceinline__ void duo_consume(const Grid& g, const Consts& c, cons
         const int j = (int)e;
         const float4 pj = sq[j];
         F2 dr[3];
-        duo_disp<DIM, INTERIOR>(g, ri, rA, rB, pj, dr);
+        duo_disp<DIM, INTERIOR>(g, ri, rA, rB, pj, dr, wrap);
         const F2 d2 = sumsq2<DIM>(dr);
         const bool v0 = lo(d2) < g.c2;
         const bool v1 = hi(d2) < g.c2;
@@ -239,7 +242,7 @@ __device__ __forceinline__ void duo_consume(const Grid& g, const Consts& c, cons
         const bool v0 = (e & 0x4000u) != 0u, v1 = (e & 0x8000u) != 0u;
         const float4 pj = sq[j];
         F2 dr[3];
-        duo_disp<DIM, INTERIOR>(g, ri, rA, rB, pj, dr);
+        duo_disp<DIM, INTERIOR>(g, ri, rA, rB, pj, dr, wrap);
         // (membership was decided by the FILTER sweep on the unfused sum: here d^2 only feeds
         // the physics and may keep the extra bits of the fused form)
         F2 d2 = fma2(dr[1], dr[1], mul2(dr[0], dr[0]));
@@ -430,7 +433,7 @@ __global__ void __maxnreg__(SPLIT > 1 ? 80 : (P::DUO_MINB > 1 ? 80 : 128))
     const int tz = b / g.nt[1];
     int c0[3] = {g.own_lo[0] + tx * g.T[0], g.own_lo[1] + ty * g.T[1], g.own_lo[2] + tz * g.T[2]};
     int no[3], sa0[3], slen[3];
-    bool interior = true;
+    unsigned wrap = 0u;  // axes along which the stencil holds a periodic image
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       no[a] = min(g.T[a], g.own_hi[a] - c0[a]);
@@ -441,10 +444,11 @@ __global__ void __maxnreg__(SPLIT > 1 ? 80 : (P::DUO_MINB > 1 ? 80 : 128))
         sa0[a] = 0;
         slen[a] = g.n[a];
       }
-      interior = interior && (a >= DIM || (sa0[a] + g.goff[a] >= 0 &&
-                                           sa0[a] + g.goff[a] + slen[a] <= g.ng[a] &&
-                                           g.n[a] >= 2 * g.S[a] + 2));
+      if (a < DIM && !(sa0[a] + g.goff[a] >= 0 && sa0[a] + g.goff[a] + slen[a] <= g.ng[a] &&
+                       g.n[a] >= 2 * g.S[a] + 2))
+        wrap |= 1u << a;
     }
+    const bool interior = wrap == 0u;
     const int nxs = slen[0];
     const int nrows = slen[1] * slen[2];
     const int E = nrows * nxs;
@@ -727,11 +731,11 @@ __global__ void __maxnreg__(SPLIT > 1 ? 80 : (P::DUO_MINB > 1 ? 80 : 128))
           int n_exact = 0;
           if (interior)
             duo_consume<DIM, P, true, ROLE == DUO_FILTER, SPLIT>(g, c, ex, dl, sq, sd.cap, row_run0,
-                                                                 nr, k, part, nn, has1, rA, rB, od, ad,
+                                                                 nr, k, part, nn, has1, wrap, rA, rB, od, ad,
                                                                  n_exact);
           else
             duo_consume<DIM, P, false, ROLE == DUO_FILTER, SPLIT>(g, c, ex, dl, sq, sd.cap, row_run0,
-                                                                  nr, k, part, nn, has1, rA, rB, od,
+                                                                  nr, k, part, nn, has1, wrap, rA, rB, od,
                                                                   ad, n_exact);
           if (SPLIT > 1) D::xsum(ad);
           D::fold(ad, aA, aB);

@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_slab.py -m gpu -x -q 2>&1 | tail -3
+
 timeout 900 python -m pytest tests/test_gpu_slab_nccl.py -m gpu -x -q -k "${N}-" > gpurun_out/r3p_tests_$N.log 2>&1; tail -5 gpurun_out/r3p_tests_$N.log
 for tr in direct nccl; do
   SPHB200_SLAB_TRANSPORT=$tr timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 40 --warmup 3 --e2e-steps 1 --cpu-steps 1 > gpurun_out/r3p_bench${N}_$tr.json 2> gpurun_out/r3p_bench${N}_$tr.err
