@@ -111,7 +111,7 @@ def main():
     from oracle import integrator
     from test_gpu_parity3d import CASES_3D, _oracle_forward, interior_tiles
 
-    kw, nsteps = CASES_3D["tgv3d_tvf_32"]
+    kw, nsteps = CASES_3D["tgv3d_tvf_40"]
     setup = cases.make_case(dtype=np.float32, **kw)
     setup64 = cases.make_case(dtype=np.float64, **kw)
     for k, v in setup.state.items():
@@ -123,7 +123,7 @@ def main():
     eng.step(0.0, 1, integrate=False, bc=False)
     got = eng.download(host=True)
     for k in FWD_KEYS:
-        worst = max(worst, row("tgv3d_tvf_32", "forward", k, got[k].numpy(), ref[k], ref64[k], setup, 1.0))
+        worst = max(worst, row("tgv3d_tvf_40", "forward", k, got[k].numpy(), ref[k], ref64[k], setup, 1.0))
     ref = integrator.simulate(setup, nsteps, fast_segment_sum=True)
     ref64 = integrator.simulate(setup64, nsteps, fast_segment_sum=True)
     eng.upload(setup.state)
@@ -131,9 +131,9 @@ def main():
     got = eng.download(host=True)
     cnt = eng.counters()
     for k in ADV_KEYS:
-        worst = max(worst, row("tgv3d_tvf_32", f"{nsteps} steps", k, got[k].numpy(), ref[k], ref64[k],
+        worst = max(worst, row("tgv3d_tvf_40", f"{nsteps} steps", k, got[k].numpy(), ref[k], ref64[k],
                                setup, 4.0))
-    print(f"tgv3d_tvf_32     {inner} of {total} tiles interior, searches {cnt['searches']} of "
+    print(f"tgv3d_tvf_40     {inner} of {total} tiles interior, searches {cnt['searches']} of "
           f"{cnt['steps']} steps, device error {eng.error()}")
     print(f"# worst err/tol over all rows: {worst:.3f}")
 
