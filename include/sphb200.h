@@ -288,7 +288,9 @@ int sphb200_engine_last_times(sphb200_engine *e, float ms[8]);
 int sphb200_engine_plan(const sphb200_engine *e, int32_t out[16]);
 /* sync: [0] steps run since creation, [1] searches (cell sort + candidate walk) among them,
  * [2] row length of the neighbour lists, [3] skin in 1e-6 of the cutoff, [4] tiles,
- * [5] tiles whose lists do not exist (swept by their own search), [6..7] reserved. */
+ * [5] tiles whose lists do not exist (swept by their own search), [6] 1 when the duo sweeps serve
+ * this variant, [7] directed pairs (self pairs included) in the exact neighbour lists of the last
+ * step -- duo engines whose every tile has lists, else -1. */
 int sphb200_engine_counters(sphb200_engine *e, int64_t out[8], void *stream);
 /* sync: measured FP32 throughput of this device in TFLOP/s (2 flop per lane-FMA): a grid of
  * independent FMA chains, `packed` = 0: FFMA, 1: FFMA2 (fma.rn.f32x2).  The roofline denominator

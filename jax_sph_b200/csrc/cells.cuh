@@ -297,15 +297,20 @@ __global__ void __launch_bounds__(256) k_reorder(int n, Grid g, Kick k, Slab sl,
 // particles (the stateless entry points do): if it is not close to the sorted one, the step sorts.
 // The flag words alternate between steps: this launch also clears the next step's word.
 template <int DIM>
+// `maybe` (engines with the relative criterion, k_drift_box below): exceeding `limit` only asks
+// for the relative test (word maybe[0], maybe[1] is cleared for the next step), exceeding
+// `guard2` raises the flag at once.
 __global__ void __launch_bounds__(256) k_drift(int n, Grid g, Kick k, Slab sl, Frame f,
                                                const float4* __restrict__ rb, int* flag_cur,
                                                int* flag_next, int force, float limit2,
-                                               unsigned* __restrict__ err) {
+                                               unsigned* __restrict__ err, int* maybe_cur = nullptr,
+                                               int* maybe_next = nullptr, float guard2 = 0.f) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *flag_next = 0;
+    if (maybe_next) *maybe_next = 0;
     if (force) atomicOr(flag_cur, 1);
   }
-  bool over = false;
+  bool over = false, over_guard = false;
   const int n_own = sl.dn ? sl.dn[DN_OWN] : n;  // slab engines: own particles only
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_own; t += gridDim.x * blockDim.x) {
     const int p = sl.base + t;
@@ -330,7 +335,122 @@ __global__ void __launch_bounds__(256) k_drift(int n, Grid g, Kick k, Slab sl, F
                     DIM == 3 ? disp1(r[2], q.z, g.half[2], g.box[2]) : 0.f};
       const float d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
       over = over || !(d2 <= limit2);
+      over_guard = over_guard || !(d2 <= guard2);
     }
+  }
+  if (maybe_cur == nullptr) {
+    if (__syncthreads_or(over) && threadIdx.x == 0) atomicOr(flag_cur, 1);
+  } else {
+    const int any = __syncthreads_or(over), anyg = __syncthreads_or(over_guard);
+    if (threadIdx.x == 0) {
+      if (anyg) atomicOr(flag_cur, 1);
+      else if (any) atomicOr(maybe_cur, 1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The re-sort criterion by RELATIVE drift (single-GPU duo engines).  A pair inside the cutoff now
+// was inside cutoff + skin at the last search as long as the two particles have moved less than
+// `skin` RELATIVE to each other since then -- and neighbours move almost together: in a smooth
+// flow the relative drift is the strain rate times the pair distance, an order of magnitude below
+// the particles' own drift.  The bound is taken per block of S x S x S cells of the frozen table
+// (slot ranges): k_drift_box makes the component-wise box [min, max] of the minimum-image drift
+// r - rb of a block's particles, k_drift_window joins the boxes of every block whose cells lie
+// within S cells of the block's own (any pair of the skin list lies in one such window) and
+// raises the step's flag when the diagonal of the joined box exceeds the limit.  Either bound is
+// sufficient, so the boxes are made only on the steps where some particle is further than half
+// the skin from where it was sorted (k_drift's `maybe` word).  k_drift keeps an absolute guard
+// (most of a cutoff): what it protects is the "interior" shortcut of the sweeps, whose tiles
+// keep S more cells away from the periodic seam in these engines (Grid::imargin).
+struct DriftBlocks {
+  int nb[3];       // blocks per axis
+  float4* bmin;    // [blocks]
+  float4* bmax;
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(128) k_drift_box(Grid g, DriftBlocks db, const int* __restrict__ start,
+                                                   const float4* __restrict__ pt,
+                                                   const float4* __restrict__ rb,
+                                                   const int* __restrict__ flag_cur,
+                                                   const int* __restrict__ maybe_cur) {
+  // the step sorts anyway, or no particle is further than half the skin from where it was sorted
+  // (the absolute criterion already proves the lists complete)
+  if (*flag_cur != 0 || *maybe_cur == 0) return;
+  const int nblocks = db.nb[0] * db.nb[1] * db.nb[2];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const int bx = b % db.nb[0], by = (b / db.nb[0]) % db.nb[1], bz = b / (db.nb[0] * db.nb[1]);
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  const int x0 = bx * g.S[0], x1 = min(x0 + g.S[0], g.n[0]);
+  const int z0 = DIM == 3 ? bz * g.S[2] : 0, z1 = DIM == 3 ? min((bz + 1) * g.S[2], g.n[2]) : 1;
+  for (int cz = z0; cz < z1; ++cz) {
+    for (int cy = by * g.S[1]; cy < min((by + 1) * g.S[1], g.n[1]); ++cy) {
+      const int row = (cz * g.n[1] + cy) * g.n[0];
+      const int s0 = start[row + x0], s1 = start[row + x1];
+      for (int p = s0; p < s1; ++p) {
+        const float4 a = pt[p], q = rb[p];
+        const float d[3] = {disp1(a.x, q.x, g.half[0], g.box[0]), disp1(a.y, q.y, g.half[1], g.box[1]),
+                            DIM == 3 ? disp1(a.z, q.z, g.half[2], g.box[2]) : 0.f};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          lo[k] = fminf(lo[k], d[k]);
+          hi[k] = fmaxf(hi[k], d[k]);
+        }
+      }
+    }
+  }
+  db.bmin[b] = make_float4(lo[0], lo[1], lo[2], 0.f);
+  db.bmax[b] = make_float4(hi[0], hi[1], hi[2], 0.f);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128) k_drift_window(Grid g, DriftBlocks db, float limit2, int* flag_cur,
+                                                      const int* __restrict__ maybe_cur) {
+  if (*flag_cur != 0 || *maybe_cur == 0) return;
+  const int nblocks = db.nb[0] * db.nb[1] * db.nb[2];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  bool over = false;
+  if (b < nblocks) {
+    const int bc[3] = {b % db.nb[0], (b / db.nb[0]) % db.nb[1], b / (db.nb[0] * db.nb[1])};
+    // blocks that hold the cells [S b - S, S b + 2 S) of every axis (periodic in CELLS: the last
+    // block of an axis may be a partial one, so up to four blocks per axis)
+    int nbr[3][6], cnt[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      cnt[a] = 0;
+      if (a >= DIM) {
+        nbr[a][cnt[a]++] = 0;
+        continue;
+      }
+      const int S = g.S[a], n = g.n[a];
+      for (int off = -S; off < 2 * S; ++off) {
+        int cc = S * bc[a] + off;
+        cc = cc < 0 ? cc + n : (cc >= n ? cc - n : cc);
+        const int nbk = cc / S;
+        bool seen = false;
+        for (int j = 0; j < cnt[a]; ++j) seen = seen || nbr[a][j] == nbk;
+        if (!seen && cnt[a] < 6) nbr[a][cnt[a]++] = nbk;
+      }
+    }
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int iz = 0; iz < cnt[2]; ++iz)
+      for (int iy = 0; iy < cnt[1]; ++iy)
+        for (int ix = 0; ix < cnt[0]; ++ix) {
+          const int q = (nbr[2][iz] * db.nb[1] + nbr[1][iy]) * db.nb[0] + nbr[0][ix];
+          const float4 mn = db.bmin[q], mx = db.bmax[q];
+          lo[0] = fminf(lo[0], mn.x); lo[1] = fminf(lo[1], mn.y); lo[2] = fminf(lo[2], mn.z);
+          hi[0] = fmaxf(hi[0], mx.x); hi[1] = fmaxf(hi[1], mx.y); hi[2] = fmaxf(hi[2], mx.z);
+        }
+    // (an empty window leaves lo = +inf, hi = -inf: spread -inf, clamped to 0)
+    float d2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float w = fmaxf(hi[k] - lo[k], 0.f);
+      d2 += w * w;
+    }
+    over = !(d2 <= limit2);
   }
   if (__syncthreads_or(over) && threadIdx.x == 0) atomicOr(flag_cur, 1);
 }

@@ -56,6 +56,9 @@ struct Grid {
   int own_lo[3], own_hi[3];  // local cell range this rank owns (sweeps tile exactly this range)
   int block0;    // first tile of this launch (a sweep may be launched over a sub-range of tiles)
   int ntl;       // tiles of this launch: [block0, block0 + ntl)
+  int imargin;   // 1: a tile is "interior" only if its stencil keeps S more cells away from the
+                 // periodic seam (engines whose re-sort criterion is the RELATIVE drift of
+                 // neighbours, cells.cuh k_drift_box: particles may be far from where they were sorted)
 };
 
 // Derived float32 constants, rounded where the reference rounds them.

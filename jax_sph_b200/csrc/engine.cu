@@ -78,6 +78,11 @@ struct sphb200_engine {
   bool inplace;
   double skin_frac;         // skin / cutoff
   float path_limit;         // < 0: sort + search every step
+  bool rel_drift;           // re-sort criterion: relative drift of neighbours (cells.cuh, k_drift_box)
+  float rel_limit;          // ... its limit (the skin); path_limit (half the skin, absolute) stays
+                            // sufficient on its own, rel_guard is the absolute guard of the seam
+  float rel_guard;
+  DriftBlocks dblocks;
   float4* rb;               // [n] positions at the last sort
   int* ctl;                 // [0], [1] re-sort flag of even / odd steps, [2] searches so far
   unsigned long long step_no;
@@ -220,6 +225,7 @@ void plan_grid(const sphb200_config& c, Grid& g, int tpb, int rank = 0, int nran
   const double cutoff = kernel_cutoff(c) * (1.0 + skin_frac);  // what the cells and the search cover
   double pop = 1.0;
   g.exact_all = 0;
+  g.imargin = 0;
   g.ncells = 1;
   for (int a = 0; a < 3; ++a) {
     if (a < c.dim) {
@@ -391,6 +397,7 @@ struct Layout {
   size_t pl_list, pl_cnt, pl_ok, sl_list, sl_cnt, path, ctl;
   size_t dl, dg;  // Delta-SPH density diffusion (PhysDelta)
   size_t rec, desc;  // duo sweeps: compact force records (52 B per slot), tile descriptors
+  size_t dbox;       // duo engines: drift boxes of the S^3-cell blocks (cells.cuh, k_drift_box)
   int pl_lmax;
   size_t dn;
   size_t total;
@@ -462,10 +469,13 @@ void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, double skin_
   } else {
     L.pl_list = L.pl_cnt = L.pl_ok = L.sl_list = L.sl_cnt = (size_t)-1;
   }
-  L.rec = L.desc = (size_t)-1;
+  L.rec = L.desc = L.dbox = (size_t)-1;
   if (dp.on) {
     L.rec = take((size_t)n * 52);
     L.desc = take((size_t)g.nt[0] * g.nt[1] * g.nt[2] * dp.desc_stride * 4);
+    size_t blocks = 1;
+    for (int a = 0; a < c.dim; ++a) blocks *= (size_t)((g.n[a] + g.S[a] - 1) / g.S[a]);
+    L.dbox = take(blocks * 32);
   }
   L.total = off;
 }
@@ -787,12 +797,29 @@ int drift_step(sphb200_engine* e, const Kick& k, cudaStream_t st) {
   const int force = (e->force_rebuild || !e->cells_valid) ? 1 : 0;
   Frame& F = e->fr[e->cur];
   const float lim2 = e->path_limit < 0.f ? -1.0f : e->path_limit * e->path_limit;
+  // relative criterion: ctl[5], ctl[6] are the alternating `maybe` words of k_drift
+  int* mc = e->rel_drift ? e->ctl + 5 + (e->step_no & 1ull) : nullptr;
+  int* mn = e->rel_drift ? e->ctl + 5 + ((e->step_no + 1ull) & 1ull) : nullptr;
+  const float guard2 = e->rel_guard * e->rel_guard;
   if (k.on || e->positions_replaced) {  // (a forward-only call on a re-uploaded state tests it too)
     const int nb = stream_blocks(e, e->slab_on ? e->sgeom.own_cap : e->n);
     if (e->dim == 2)
-      k_drift<2><<<nb, 256, 0, st>>>(e->n, e->grid, k, e->slab, F, e->rb, fc, fn, force, lim2, e->err);
+      k_drift<2><<<nb, 256, 0, st>>>(e->n, e->grid, k, e->slab, F, e->rb, fc, fn, force, lim2, e->err, mc, mn, guard2);
     else
-      k_drift<3><<<nb, 256, 0, st>>>(e->n, e->grid, k, e->slab, F, e->rb, fc, fn, force, lim2, e->err);
+      k_drift<3><<<nb, 256, 0, st>>>(e->n, e->grid, k, e->slab, F, e->rb, fc, fn, force, lim2, e->err, mc, mn, guard2);
+    if (e->rel_drift && !force) {
+      const int blocks = e->dblocks.nb[0] * e->dblocks.nb[1] * e->dblocks.nb[2];
+      const int nbk = (blocks + 127) / 128;
+      const float rl2 = e->rel_limit * e->rel_limit;
+      if (e->dim == 2) {
+        k_drift_box<2><<<nbk, 128, 0, st>>>(e->grid, e->dblocks, e->start, F.pt, e->rb, fc, mc);
+        k_drift_window<2><<<nbk, 128, 0, st>>>(e->grid, e->dblocks, rl2, fc, mc);
+      } else {
+        k_drift_box<3><<<nbk, 128, 0, st>>>(e->grid, e->dblocks, e->start, F.pt, e->rb, fc, mc);
+        k_drift_window<3><<<nbk, 128, 0, st>>>(e->grid, e->dblocks, rl2, fc, mc);
+      }
+      e->launches += 2;
+    }
     e->maybe_drifted = true;
     e->positions_replaced = false;
   } else {
@@ -1449,6 +1476,33 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
     e->rec2 = e->rec1 + n;
     e->rec_e = (float*)(e->rec2 + n);
     e->duo_desc = (int*)(e->arena + L.desc);
+  }
+  // Relative-drift criterion: single-GPU duo engines on a grid with room for the wider seam
+  // margin of the interior shortcut (SPHB200_REL_DRIFT=0 keeps the absolute criterion alone).
+  e->rel_drift = false;
+  e->rel_guard = 0.f;
+  e->grid.imargin = 0;
+  if (dp.on && !sp && e->skin_frac > 0.0 && !e->grid.exact_all) {
+    const char* env = getenv("SPHB200_REL_DRIFT");
+    bool on = !(env && env[0] == '0');
+    for (int a = 0; a < e->dim; ++a) on = on && e->grid.n[a] >= 6 * e->grid.S[a];
+    if (on) {
+      e->rel_drift = true;
+      e->grid.imargin = 1;
+      size_t blocks = 1;
+      for (int a = 0; a < 3; ++a) {
+        e->dblocks.nb[a] = a < e->dim ? (e->grid.n[a] + e->grid.S[a] - 1) / e->grid.S[a] : 1;
+        blocks *= (size_t)e->dblocks.nb[a];
+      }
+      e->dblocks.bmin = (float4*)(e->arena + L.dbox);
+      e->dblocks.bmax = e->dblocks.bmin + blocks;
+      const double rc = kernel_cutoff(*cfg);
+      // pairs: relative drift below the skin; particles: the interior tiles keep 2 S cells (two
+      // cutoffs + skins) between their own particles and the periodic seam, a particle that has
+      // moved less than 0.9 cutoffs cannot meet one that crossed the seam
+      e->rel_limit = (float)(e->skin_frac * rc * (1.0 - 1e-3));
+      e->rel_guard = (float)(0.9 * rc);
+    }
   }
   e->dn = (int*)(e->arena + L.dn);
   memset(&e->slab, 0, sizeof(e->slab));
@@ -2264,6 +2318,20 @@ int sphb200_engine_counters(sphb200_engine* e, int64_t out[8], void* stream) {
   out[3] = (int64_t)(e->skin_frac * 1e6 + 0.5);
   out[4] = tiles;
   out[5] = e->pl_ok ? h[3] : tiles;
+  out[7] = -1;
+  if (e->duo && e->cells_valid && e->pl_ok && h[3] == 0 && e->step_no > 0) {
+    // directed pairs in the exact lists of the last step (diagnostics: k_duo_pair_count)
+    unsigned long long* dcount = reinterpret_cast<unsigned long long*>(e->stats);
+    unsigned long long hc = 0ull;
+    CK(cudaMemsetAsync(dcount, 0, 8, st));
+    DuoList dl{e->duo_desc, e->duo_desc_stride, e->sl_list, e->pl_list, e->sl_cnt, e->pl_cnt,
+               e->pl_ok,    e->duo_lmax,        0,          e->duo_rows};
+    k_duo_pair_count<<<tiles, 256, 0, st>>>(dl, dcount);
+    e->launches++;
+    CK(cudaMemcpyAsync(&hc, dcount, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out[7] = (int64_t)hc;
+  }
   return SPHB200_OK;
 }
 

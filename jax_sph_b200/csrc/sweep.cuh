@@ -358,8 +358,9 @@ __global__ void __launch_bounds__(SWEEP_MAXT, P::MINB)
         sa0[a] = 0;
         slen[a] = g.n[a];
       }
-      interior = interior && (a >= DIM || (sa0[a] + g.goff[a] >= 0 &&
-                                           sa0[a] + g.goff[a] + slen[a] <= g.ng[a] &&
+      const int im = g.imargin ? g.S[a] : 0;
+      interior = interior && (a >= DIM || (sa0[a] + g.goff[a] - im >= 0 &&
+                                           sa0[a] + g.goff[a] + slen[a] + im <= g.ng[a] &&
                                            g.n[a] >= 2 * g.S[a] + 2));
     }
     if (g.exact_all) interior = false;

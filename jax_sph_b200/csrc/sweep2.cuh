@@ -444,7 +444,8 @@ __global__ void __maxnreg__(SPLIT > 1 ? 80 : (P::DUO_MINB > 1 ? 80 : 128))
         sa0[a] = 0;
         slen[a] = g.n[a];
       }
-      if (a < DIM && !(sa0[a] + g.goff[a] >= 0 && sa0[a] + g.goff[a] + slen[a] <= g.ng[a] &&
+      const int im = g.imargin ? g.S[a] : 0;
+      if (a < DIM && !(sa0[a] + g.goff[a] - im >= 0 && sa0[a] + g.goff[a] + slen[a] + im <= g.ng[a] &&
                        g.n[a] >= 2 * g.S[a] + 2))
         wrap |= 1u << a;
     }
@@ -788,6 +789,39 @@ __global__ void __launch_bounds__(256) k_force_rec(int n, Slab sl, int mode, Fra
   const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   for (int p = lo + t0; p < hi; p += stride) P::make_record(f, ex, p);
   for (int p = lo2 + t0; p < hi2; p += stride) P::make_record(f, ex, p);
+}
+
+// Diagnostics (sphb200_engine_counters): directed pairs in the exact lists of the last step -- the
+// membership bits of every duo row of every tile that has lists.  Equal to the brute-force count
+// of pairs (i, j) with d^2 < cutoff^2 at the step's positions, self pairs included, whenever the
+// lists are complete (tests/test_gpu_duo.py).
+__global__ void __launch_bounds__(256) k_duo_pair_count(DuoList dl, unsigned long long* out) {
+  const int tile = blockIdx.x;
+  unsigned long long cnt = 0ull;
+  if (dl.ok[tile] != 0) {
+    const int* d = dl.desc + (size_t)tile * dl.desc_stride;
+    const int duos = d[1] > 0 ? d[2] : 0;
+    for (int t = threadIdx.x; t < duos; t += blockDim.x) {
+      int run = 0;
+      while (t >= d[DD_DUO_OFF + run + 1]) ++run;
+      const int k = t - d[DD_DUO_OFF + run], nr = d[DD_DUO_OFF + run + 1] - d[DD_DUO_OFF + run];
+      const int row_run0 = d[DD_ROW0 + run];
+      const int nwords = (dl.xcnt[row_run0 + k] + 3) >> 2;
+      const unsigned long long* xp =
+          reinterpret_cast<const unsigned long long*>(dl.xl) + (size_t)row_run0 * (dl.lmax / 4) + k;
+      for (int w = 0; w < nwords; ++w) {
+        const unsigned long long cur = xp[(size_t)w * nr];
+        // bits 14 / 15 of every 16-bit entry
+        cnt += __popcll(cur & 0xC000C000C000C000ull);
+      }
+    }
+  }
+  __shared__ unsigned long long s;
+  if (threadIdx.x == 0) s = 0ull;
+  __syncthreads();
+  if (cnt) atomicAdd(&s, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0 && s) atomicAdd(out, s);
 }
 
 // number of tiles the duo sweeps leave to sweep.cuh -> *nbad (the gate of those launches)

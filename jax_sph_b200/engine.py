@@ -432,7 +432,7 @@ class Engine:
         _lib.check(self.lib.sphb200_engine_counters(self._h, C.byref(out), _stream_ptr()))
         v = list(out)
         return dict(steps=v[0], searches=v[1], list_rows=v[2], skin=v[3] * 1e-6, tiles=v[4],
-                    tiles_without_lists=v[5], duo=bool(v[6]))
+                    tiles_without_lists=v[5], duo=bool(v[6]), pairs=v[7])
 
     def plan(self):
         out = (C.c_int32 * 16)()

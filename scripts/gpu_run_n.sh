@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 run() { # name, env..., -- bench args
   name=$1; shift
   envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
-  env "${envs[@]}" timeout 300 python bench.py --steps 40 --warmup 3 --e2e-steps 1 --cpu-steps 1 --no-configs "$@" > gpurun_out/r3n_$name.json 2> gpurun_out/r3n_$name.err
+  env "${envs[@]}" timeout 300 python bench.py --steps 100 --warmup 3 --e2e-steps 1 --cpu-steps 1 --no-configs "$@" > gpurun_out/r3n_$name.json 2> gpurun_out/r3n_$name.err
   python - "$name" <<'PY'
 import json,sys
 f="gpurun_out/r3n_%s.json"%sys.argv[1]

@@ -217,3 +217,70 @@ def test_uniform_viscosity_hint(name):
     ref = integrator.simulate(setup, 4, fast_segment_sum=True)
     for k in ADV_KEYS:
         assert_close(k, got[k].numpy(), ref[k], setup, factor=3.0, what=f"{name} particle-wise eta vs oracle")
+
+
+def _brute_force_pairs(r, box, cutoff):
+    """Directed pairs (i, j), self pairs included, with the reference's float32 test
+    d^2 < cutoff^2 on the periodic displacement of space.py:170-181 (torch on the GPU: float32
+    add / sub / mul / fmod with the same roundings, no fused multiply-add across statements)."""
+    import torch
+
+    r = torch.as_tensor(np.asarray(r, dtype=np.float32), device="cuda")
+    box = torch.as_tensor(np.asarray(box, dtype=np.float32), device="cuda")
+    half = box * 0.5
+    c2 = torch.tensor(np.float32(cutoff) * np.float32(cutoff), device="cuda")
+    total = 0
+    for i0 in range(0, len(r), 1024):
+        d = r[i0:i0 + 1024, None, :] - r[None, :, :]
+        d = torch.remainder(d + half, box) - half
+        d2 = d * d
+        s = d2[..., 0] + d2[..., 1]
+        if r.shape[1] == 3:
+            s = s + d2[..., 2]
+        total += int((s < c2).sum().item())
+    return total
+
+
+def _engine_rel(setup, rel):
+    old = os.environ.get("SPHB200_REL_DRIFT")
+    os.environ["SPHB200_REL_DRIFT"] = rel
+    try:
+        return _engine(setup)
+    finally:
+        if old is None:
+            os.environ.pop("SPHB200_REL_DRIFT")
+        else:
+            os.environ["SPHB200_REL_DRIFT"] = old
+
+
+@pytest.mark.parametrize("rel", ["0", "1"])
+@pytest.mark.parametrize("name", ["tgv3d_tvf", "tgv2d_tvf"])
+def test_frozen_lists_hold_every_pair(name, rel):
+    """The exact lists of a step taken long after the last search hold exactly the pairs of a
+    brute-force search at that step's positions (membership bits counted on the device,
+    sphb200_engine_counters), with the absolute re-sort criterion alone (a particle further than
+    half the skin from where it was sorted) and with the relative one beside it (cells.cuh,
+    k_drift_box: no block of neighbours has drifted apart by more than the skin), which never
+    searches more often."""
+    from oracle import cases
+
+    kw = dict(CASES[name])
+    kw["dx"] = 2 * np.pi / 28 if kw["dim"] == 3 else 1.0 / 120
+    setup = cases.make_case(dtype=np.float32, r0_noise_factor=0.1, **kw)
+    eng = _engine_rel(setup, rel)
+    eng.upload(setup.state)
+    cutoff = 3.0 * setup.dx
+    done = 0
+    for nsteps in (1, 9, 30, 40):
+        eng.step(setup.dt, nsteps)
+        done += nsteps
+        cnt = eng.counters()
+        assert eng.error() == 0 and cnt["duo"] and cnt["tiles_without_lists"] == 0
+        r_now = eng.download(host=True)["r"].numpy()
+        assert cnt["pairs"] == _brute_force_pairs(r_now, setup.box_size, cutoff), (name, rel, done, cnt)
+    assert cnt["searches"] < done
+    if rel == "1":
+        other = _engine_rel(setup, "0")
+        other.upload(setup.state)
+        other.step(setup.dt, done)
+        assert cnt["searches"] <= other.counters()["searches"], (cnt, other.counters())
