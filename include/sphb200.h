@@ -213,8 +213,10 @@ int sphb200_engine_upload(sphb200_engine *e, const sphb200_state *s, int on_host
 /* Copy a state of the SAME particles (row i is still particle i) into the slots they occupy in
  * the cell-sorted frame.  Unlike sphb200_engine_upload this keeps the cell table and the
  * neighbour lists: the next step tests every position against the one the particle had when the
- * cells were made and sorts again only if one moved further than half the list skin -- the
- * result is the same either way.  Before the first step it is an ordinary upload. */
+ * cells were made and sorts again only if the skin lists may have become incomplete (a particle
+ * further than half the list skin from there AND a block of neighbouring cells whose particles
+ * drifted apart by more than the skin, csrc/cells.cuh k_drift / k_drift_box) -- the result is
+ * the same either way.  Before the first step it is an ordinary upload. */
 int sphb200_engine_refresh(sphb200_engine *e, const sphb200_state *s, int on_host, void *stream);
 /* nsteps x advance(dt) (integrator.py:22-56) or forward only, per `flags`. */
 int sphb200_engine_step(sphb200_engine *e, double dt, int nsteps, uint32_t flags, void *stream);
@@ -430,8 +432,9 @@ int sphb200_advance(const sphb200_config *cfg, int64_t n, double dt, const sphb2
  * workspace held.  But when it is handed in again with the same cfg and n, the particles are
  * found cell-sorted in it with their neighbour lists: the new state goes into the slots its
  * particles occupy (sphb200_engine_refresh), every position is tested against the sorted one, and
- * the cell sort + neighbour search run only if a particle moved further than half the list skin
- * -- a state that has nothing to do with the previous call simply sorts again.  The call then
+ * the cell sort + neighbour search run only if the lists may have become incomplete (see
+ * sphb200_engine_refresh) -- a state that has nothing to do with the previous call simply sorts
+ * again.  The call then
  * costs a resident step plus the two state copies.  The library keeps a table workspace pointer
  * -> engine for this (mutex-protected, at most 8 workspaces); call
  * sphb200_workspace_release(ws) before the memory is freed or reused (NULL: all). */
