@@ -209,7 +209,42 @@ def snapshot_name(step: int, cfg) -> Optional[str]:
     return "traj_" + str(step).zfill(len(str(step_max)))
 
 
-def _write_files(state: Dict, dir: str, name: str, write_type: Sequence[str]):
+REFERENCE_KEYS = ("r", "tag", "u", "v", "dudt", "dvdt", "drhodt", "rho", "p", "mass", "eta", "dTdt", "T",
+                  "kappa", "Cp", "nw")  # the state dict of case_setup.py:152-181 / solver.py:930-947
+
+
+def complete_state(state: Dict, cfg=None) -> Dict:
+    """The reference's snapshots always hold all sixteen state entries (read_h5 with state0_keys,
+    visualisation and validation scripts index them); an engine that does not carry `nw`
+    (no Riemann / free-slip walls) or `kappa` / `Cp` (no heat conduction) downloads a state
+    without them.  Fill those in as the reference's own initial state has them: zeros for `nw`,
+    the case constants (case.kappa_ref / case.Cp_ref when `cfg` has them, else zeros) for the
+    heat entries.  Entries that are present are never touched; a dict that lacks any other
+    reference key is not an engine download and is written as it is."""
+    optional = ("nw", "kappa", "Cp")
+    if any(k not in state for k in REFERENCE_KEYS if k not in optional) or all(k in state for k in optional):
+        return state  # not an engine download (a partial dict is written as it is), or complete
+    r = state["r"]
+    n, dim = int(r.shape[0]), int(r.shape[1])
+
+    def const(path):
+        try:
+            return float(_get(cfg, path)) if cfg is not None else 0.0
+        except (KeyError, AttributeError, TypeError):
+            return 0.0
+
+    out = dict(state)
+    fill = {"nw": np.zeros((n, dim), dtype=np.float32),
+            "kappa": np.full(n, const("case.kappa_ref"), dtype=np.float32),
+            "Cp": np.full(n, const("case.Cp_ref"), dtype=np.float32)}
+    for k, v in fill.items():
+        if k not in out:
+            out[k] = v
+    return out
+
+
+def _write_files(state: Dict, dir: str, name: str, write_type: Sequence[str], cfg=None):
+    state = complete_state(state, cfg)
     if "h5" in write_type:
         write_h5(state, os.path.join(dir, name + ".h5"))
     if "vtk" in write_type:
@@ -220,7 +255,7 @@ def write_state(step: int, state: Dict, dir: str, cfg):
     """io_state.py:44-66: write `state` (host or device arrays) if this step is a write step."""
     name = snapshot_name(step, cfg)
     if name is not None:
-        _write_files(state, dir, name, _get(cfg, "io.write_type"))
+        _write_files(state, dir, name, _get(cfg, "io.write_type"), cfg)
 
 
 class TrajectoryWriter:
@@ -287,7 +322,7 @@ class TrajectoryWriter:
             try:
                 done.synchronize()
                 state = {k: v.numpy() for k, v in self.host[slot].items()}
-                _write_files(state, self.dir, name, self.write_type)
+                _write_files(state, self.dir, name, self.write_type, self.cfg)
                 self.written.append(name)
             except Exception as exc:  # surfaced on the next write() / close()
                 self.error = exc

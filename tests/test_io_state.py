@@ -79,6 +79,26 @@ def test_write_state_round_trips(tmp_path, dim):
     assert head.startswith(b"# vtk DataFile Version 3.0\n") and b"BINARY\nDATASET POLYDATA" in head
 
 
+def test_snapshots_hold_all_sixteen_reference_keys(tmp_path):
+    """An engine without wall normals / heat conduction downloads no `nw`, `kappa`, `Cp`; the
+    snapshot still has the reference's sixteen entries (zeros / the case constants), and entries
+    that are present pass through untouched."""
+    cfg = _cfg(write_type=("h5",))
+    full = _state(dim=3)
+    n = len(full["r"])
+    full.update(drhodt=np.zeros(n, np.float32), dTdt=np.zeros(n, np.float32),
+                kappa=np.full(n, 7.0, np.float32), Cp=np.full(n, 3.0, np.float32))
+    part = {k: v for k, v in full.items() if k not in ("nw", "kappa", "Cp")}
+    io_state.write_state(0, part, str(tmp_path), cfg)
+    back = io_state.read_h5(str(tmp_path / "traj_00.h5"))
+    assert sorted(back) == sorted(io_state.REFERENCE_KEYS)
+    for k in part:
+        assert np.array_equal(back[k], part[k]), k
+    assert back["nw"].shape == full["r"].shape and not back["nw"].any()
+    assert back["kappa"].shape == (len(full["r"]),) and back["Cp"].dtype == np.float32
+    assert io_state.complete_state(full) is full
+
+
 @pytest.mark.gpu
 def test_trajectory_writer_equals_synchronous_downloads(tmp_path):
     """The loop of jax_sph/simulate.py:113-134 with the asynchronous writer: every snapshot
