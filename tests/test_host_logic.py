@@ -221,3 +221,59 @@ def test_bench_db2d_generator_is_the_reference_case():
     dxn = 3 * 0.00071
     n_w = 2 * round(dxn / 0.00071) * round((2.0 + 2 * dxn) / 0.00071) + 2 * round(5.366 / 0.00071) * 3
     assert n_f + n_w == 4028622
+
+
+@pytest.mark.parametrize("n_cells,S", [((13, 12, 14), 2), ((12, 13, 1), 2), ((19, 20, 21), 3)])
+def test_relative_drift_window_bounds_every_pair(n_cells, S):
+    """NumPy model of the relative re-sort criterion (csrc/cells.cuh: k_drift_box / k_drift_window):
+    particles are binned into the cells of the frozen table, cells into blocks of S^dim cells (the
+    last block of an axis may be partial), every block joins the drift boxes of the blocks that
+    hold a cell within S cells of its own (periodic in cells).  For EVERY pair that was within one
+    stencil (S cells) at the sort, |disp_i - disp_j| must not exceed the diagonal of the joined box
+    of either particle's block -- that inequality is what lets the engine keep its skin lists."""
+    rng = np.random.default_rng(sum(n_cells) + S)
+    dim = 3 if n_cells[2] > 1 else 2
+    n_cells = np.array(n_cells[:dim])
+    box = np.array([1.0, 0.9, 1.1][:dim])
+    cell = box / n_cells
+    reach = S * cell.min()  # pairs closer than this lie within S cells along every axis
+    npart = 1500
+    rb = rng.uniform(0, 1, (npart, dim)) * box
+    disp = 0.05 * reach * np.sin(2 * np.pi * rb / box + rng.uniform(0, 6, dim)) + rng.normal(0, 0.01 * reach, (npart, dim))
+    cidx = np.minimum((rb / cell).astype(int), n_cells - 1)
+    nb = (n_cells + S - 1) // S
+    bidx = cidx // S
+    lo = np.full(tuple(nb) + (dim,), np.inf)
+    hi = np.full(tuple(nb) + (dim,), -np.inf)
+    for p in range(npart):
+        b = tuple(bidx[p])
+        lo[b] = np.minimum(lo[b], disp[p])
+        hi[b] = np.maximum(hi[b], disp[p])
+
+    def window_blocks(bc, a):  # the kernel's rule, one axis
+        out = []
+        for off in range(-S, 2 * S):
+            cc = (S * bc + off) % n_cells[a]
+            if cc // S not in out:
+                out.append(int(cc // S))
+        assert len(out) <= 6
+        return out
+
+    spread = np.zeros(tuple(nb))
+    for b in np.ndindex(*nb):
+        wl, wh = np.full(dim, np.inf), np.full(dim, -np.inf)
+        axes = [window_blocks(b[a], a) for a in range(dim)]
+        for q in np.ndindex(*[len(x) for x in axes]):
+            qq = tuple(axes[a][q[a]] for a in range(dim))
+            wl, wh = np.minimum(wl, lo[qq]), np.maximum(wh, hi[qq])
+        spread[b] = np.sqrt((np.maximum(wh - wl, 0.0) ** 2).sum())
+    d = rb[:, None, :] - rb[None, :, :]
+    d = np.mod(d + box / 2, box) - box / 2
+    near = (d ** 2).sum(-1) < reach ** 2
+    rel = np.sqrt(((disp[:, None, :] - disp[None, :, :]) ** 2).sum(-1))
+    i, j = np.nonzero(near)
+    assert len(i) > npart
+    bound = spread[tuple(bidx[i].T)]
+    assert (rel[i, j] <= bound + 1e-12).all()
+    # and it is not vacuous: the bound stays within a small multiple of the largest relative drift
+    assert bound.max() < 6 * rel[i, j].max()
