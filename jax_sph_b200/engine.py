@@ -426,7 +426,10 @@ class Engine:
     def counters(self):
         """steps run, searches (cell sort + candidate walk) among them, list row length, skin /
         cutoff, tiles, tiles swept without lists, whether the duo sweeps (csrc/sweep2.cuh: two
-        particles per thread on one union list) serve this solver variant
+        particles per thread on one union list) serve this solver variant, and `pairs`: the
+        directed pairs (self pairs included) in the exact neighbour lists of the last step,
+        counted on the device from the lists' membership bits (duo engines whose every tile has
+        lists, else -1) -- what a brute-force search at the step's positions finds
         (sphb200_engine_counters)."""
         out = (C.c_int64 * 8)()
         _lib.check(self.lib.sphb200_engine_counters(self._h, C.byref(out), _stream_ptr()))
