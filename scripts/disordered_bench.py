@@ -18,13 +18,13 @@ from jax_sph_b200 import Engine, make_config  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nx", type=int, default=256)
-    ap.add_argument("--pre", type=int, nargs="*", default=[0, 200, 600])
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--pre", type=int, nargs="*", default=[0, 600, 2000])
+    ap.add_argument("--steps", type=int, default=60)
     a = ap.parse_args()
     state, meta = lattice_state("tgv3d", a.nx)
     n = len(state["r"])
     cfg = make_config(3, meta["box"], meta["dx"], meta["dt"], tvf=meta["tvf"], c_ref=meta["c_ref"],
-                      p_ref=meta["p_ref"])
+                      p_ref=meta["p_ref"], uniform_eta=True)
     eng = Engine(cfg, n)
     eng.upload({k: torch.from_numpy(v).pin_memory() for k, v in state.items()})
     done = 0
@@ -32,19 +32,29 @@ def main():
         eng.step(meta["dt"], pre - done + 3)
         done = pre + 3
         torch.cuda.synchronize()
+        c0 = eng.counters()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.step(meta["dt"], a.steps)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.steps
+        c1 = eng.counters()
+        done += a.steps
         eng.profile(True)
         acc = {}
-        for _ in range(a.steps):
+        for _ in range(10):
             eng.step(meta["dt"], 1)
             for k, v in eng.last_times().items():
-                acc[k] = acc.get(k, 0.0) + v / a.steps
+                acc[k] = acc.get(k, 0.0) + v / 10
         eng.profile(False)
-        done += a.steps
+        done += 10
         ek, um = eng.stats()
         cnt = eng.neighbor_list(0)[1] if n <= 2**22 else -1
         print(f"after {pre:5d} steps (t = {pre * meta['dt']:.3f}): "
               + " ".join(f"{k}={v:.3f}" for k, v in acc.items())
-              + f" | {n / acc['total'] / 1e3:.1f} M upd/s  err={eng.error()} ekin={ek:.5e} "
+              + f" | {ms:.3f} ms/step over {a.steps} steps ({c1['searches'] - c0['searches']} searches) = "
+              + f"{n / ms / 1e3:.1f} M upd/s  err={eng.error()} ekin={ek:.5e} "
               + (f"edges/particle={cnt / n:.1f}" if cnt >= 0 else ""), flush=True)
 
 
