@@ -355,17 +355,26 @@ __global__ void __launch_bounds__(256) k_drift(int n, Grid g, Kick k, Slab sl, F
 // `skin` RELATIVE to each other since then -- and neighbours move almost together: in a smooth
 // flow the relative drift is the strain rate times the pair distance, an order of magnitude below
 // the particles' own drift.  The bound is taken per block of S x S x S cells of the frozen table
-// (slot ranges): k_drift_box makes the component-wise box [min, max] of the minimum-image drift
-// r - rb of a block's particles, k_drift_window joins the boxes of every block whose cells lie
-// within S cells of the block's own (any pair of the skin list lies in one such window) and
-// raises the step's flag when the diagonal of the joined box exceeds the limit.  Either bound is
-// sufficient, so the boxes are made only on the steps where some particle is further than half
-// the skin from where it was sorted (k_drift's `maybe` word).  k_drift keeps an absolute guard
-// (most of a cutoff): what it protects is the "interior" shortcut of the sweeps, whose tiles
-// keep S more cells away from the periodic seam in these engines (Grid::imargin).
+// (slot ranges; a block edge is at least one cutoff + skin):
+//   k_drift_box   the component-wise box [min, max] of the minimum-image drift r - rb of a block's
+//                 particles;
+//   k_drift_join  joins, axis after axis (min / max are separable), the boxes of every block that
+//                 holds a cell within 2 S cells of the block's own cells, and -- last axis --
+//                 raises the step's flag when the diagonal of the joined box exceeds the skin.
+// Why this is sufficient.  Take any two particles.  If their sort-time cells are within 2 S cells
+// of each other's BLOCK on every axis, both lie in one window: their relative drift is below the
+// skin, so a pair inside the cutoff now was inside cutoff + skin at the search and is in the skin
+// list.  Otherwise their sort-time cells are 2 S cells = two (cutoff + skin) apart along some axis,
+// and with every particle's own drift below `guard` = (2 (cutoff + skin) - cutoff) / 2 (k_drift
+// raises the flag at once beyond it) they are still further apart than the cutoff.  Either bound
+// -- this one, or "no particle further than half the skin from where it was sorted" -- suffices,
+// so the boxes are made only on the steps where the second one fails (k_drift's `maybe` word).
+// The same guard keeps the "interior" shortcut of the sweeps valid: their tiles keep S more cells
+// away from the periodic seam in these engines (Grid::imargin), so a particle that crossed the
+// seam stays more than a cutoff away from every own particle of an interior tile.
 struct DriftBlocks {
   int nb[3];       // blocks per axis
-  float4* bmin;    // [blocks]
+  float4* bmin;    // [3][blocks]: the blocks' own boxes, then two buffers of the axis passes
   float4* bmax;
 };
 
@@ -405,54 +414,50 @@ __global__ void __launch_bounds__(128) k_drift_box(Grid g, DriftBlocks db, const
   db.bmax[b] = make_float4(hi[0], hi[1], hi[2], 0.f);
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(128) k_drift_window(Grid g, DriftBlocks db, float limit2, int* flag_cur,
-                                                      const int* __restrict__ maybe_cur) {
+// One axis of the window join: dst[b] = join of src over the blocks that hold a cell of
+// [S b - 2 S, S b + 3 S) along AXIS (periodic in CELLS: the last block of an axis may be a partial
+// one).  LAST: nothing is stored, the diagonal of the result is tested against the limit.
+template <int AXIS, bool LAST>
+__global__ void __launch_bounds__(128) k_drift_join(Grid g, DriftBlocks db, int src, int dst, float limit2,
+                                                    int* flag_cur, const int* __restrict__ maybe_cur) {
   if (*flag_cur != 0 || *maybe_cur == 0) return;
   const int nblocks = db.nb[0] * db.nb[1] * db.nb[2];
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   bool over = false;
   if (b < nblocks) {
-    const int bc[3] = {b % db.nb[0], (b / db.nb[0]) % db.nb[1], b / (db.nb[0] * db.nb[1])};
-    // blocks that hold the cells [S b - S, S b + 2 S) of every axis (periodic in CELLS: the last
-    // block of an axis may be a partial one, so up to four blocks per axis)
-    int nbr[3][6], cnt[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      cnt[a] = 0;
-      if (a >= DIM) {
-        nbr[a][cnt[a]++] = 0;
-        continue;
-      }
-      const int S = g.S[a], n = g.n[a];
-      for (int off = -S; off < 2 * S; ++off) {
-        int cc = S * bc[a] + off;
-        cc = cc < 0 ? cc + n : (cc >= n ? cc - n : cc);
-        const int nbk = cc / S;
-        bool seen = false;
-        for (int j = 0; j < cnt[a]; ++j) seen = seen || nbr[a][j] == nbk;
-        if (!seen && cnt[a] < 6) nbr[a][cnt[a]++] = nbk;
-      }
-    }
+    int bc[3] = {b % db.nb[0], (b / db.nb[0]) % db.nb[1], b / (db.nb[0] * db.nb[1])};
+    const int S = g.S[AXIS], n = g.n[AXIS], own = bc[AXIS];
+    const float4* smin = db.bmin + (size_t)src * nblocks;
+    const float4* smax = db.bmax + (size_t)src * nblocks;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int iz = 0; iz < cnt[2]; ++iz)
-      for (int iy = 0; iy < cnt[1]; ++iy)
-        for (int ix = 0; ix < cnt[0]; ++ix) {
-          const int q = (nbr[2][iz] * db.nb[1] + nbr[1][iy]) * db.nb[0] + nbr[0][ix];
-          const float4 mn = db.bmin[q], mx = db.bmax[q];
-          lo[0] = fminf(lo[0], mn.x); lo[1] = fminf(lo[1], mn.y); lo[2] = fminf(lo[2], mn.z);
-          hi[0] = fmaxf(hi[0], mx.x); hi[1] = fmaxf(hi[1], mx.y); hi[2] = fmaxf(hi[2], mx.z);
-        }
-    // (an empty window leaves lo = +inf, hi = -inf: spread -inf, clamped to 0)
-    float d2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float w = fmaxf(hi[k] - lo[k], 0.f);
-      d2 += w * w;
+    int last = -1;
+    for (int off = -2 * S; off < 3 * S; ++off) {
+      int cc = S * own + off;
+      cc = cc < 0 ? cc + n : (cc >= n ? cc - n : cc);
+      const int nbk = cc / S;
+      if (nbk == last) continue;  // (joining a block twice after a wrap is harmless)
+      last = nbk;
+      bc[AXIS] = nbk;
+      const int q = (bc[2] * db.nb[1] + bc[1]) * db.nb[0] + bc[0];
+      const float4 mn = smin[q], mx = smax[q];
+      lo[0] = fminf(lo[0], mn.x); lo[1] = fminf(lo[1], mn.y); lo[2] = fminf(lo[2], mn.z);
+      hi[0] = fmaxf(hi[0], mx.x); hi[1] = fmaxf(hi[1], mx.y); hi[2] = fmaxf(hi[2], mx.z);
     }
-    over = !(d2 <= limit2);
+    if (LAST) {
+      // (an empty window leaves lo = +inf, hi = -inf: spread -inf, clamped to 0)
+      float d2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float w = fmaxf(hi[k] - lo[k], 0.f);
+        d2 += w * w;
+      }
+      over = !(d2 <= limit2);
+    } else {
+      db.bmin[(size_t)dst * nblocks + b] = make_float4(lo[0], lo[1], lo[2], 0.f);
+      db.bmax[(size_t)dst * nblocks + b] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
   }
-  if (__syncthreads_or(over) && threadIdx.x == 0) atomicOr(flag_cur, 1);
+  if (LAST && __syncthreads_or(over) && threadIdx.x == 0) atomicOr(flag_cur, 1);
 }
 
 // forward-only steps (no integration): just the flag protocol of k_drift

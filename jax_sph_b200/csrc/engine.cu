@@ -475,7 +475,7 @@ void plan_layout(const sphb200_config& c, int64_t n, const Grid& g, double skin_
     L.desc = take((size_t)g.nt[0] * g.nt[1] * g.nt[2] * dp.desc_stride * 4);
     size_t blocks = 1;
     for (int a = 0; a < c.dim; ++a) blocks *= (size_t)((g.n[a] + g.S[a] - 1) / g.S[a]);
-    L.dbox = take(blocks * 32);
+    L.dbox = take(blocks * 32 * 3);  // the blocks' boxes + two buffers of the axis passes
   }
   L.total = off;
 }
@@ -811,14 +811,18 @@ int drift_step(sphb200_engine* e, const Kick& k, cudaStream_t st) {
       const int blocks = e->dblocks.nb[0] * e->dblocks.nb[1] * e->dblocks.nb[2];
       const int nbk = (blocks + 127) / 128;
       const float rl2 = e->rel_limit * e->rel_limit;
+      // boxes -> buffer 0; joins along x (0 -> 1), y (1 -> 2, or the test in 2D), z (the test)
       if (e->dim == 2) {
         k_drift_box<2><<<nbk, 128, 0, st>>>(e->grid, e->dblocks, e->start, F.pt, e->rb, fc, mc);
-        k_drift_window<2><<<nbk, 128, 0, st>>>(e->grid, e->dblocks, rl2, fc, mc);
+        k_drift_join<0, false><<<nbk, 128, 0, st>>>(e->grid, e->dblocks, 0, 1, rl2, fc, mc);
+        k_drift_join<1, true><<<nbk, 128, 0, st>>>(e->grid, e->dblocks, 1, 2, rl2, fc, mc);
       } else {
         k_drift_box<3><<<nbk, 128, 0, st>>>(e->grid, e->dblocks, e->start, F.pt, e->rb, fc, mc);
-        k_drift_window<3><<<nbk, 128, 0, st>>>(e->grid, e->dblocks, rl2, fc, mc);
+        k_drift_join<0, false><<<nbk, 128, 0, st>>>(e->grid, e->dblocks, 0, 1, rl2, fc, mc);
+        k_drift_join<1, false><<<nbk, 128, 0, st>>>(e->grid, e->dblocks, 1, 2, rl2, fc, mc);
+        k_drift_join<2, true><<<nbk, 128, 0, st>>>(e->grid, e->dblocks, 2, 0, rl2, fc, mc);
       }
-      e->launches += 2;
+      e->launches += 1 + e->dim;
     }
     e->maybe_drifted = true;
     e->positions_replaced = false;
@@ -1495,13 +1499,14 @@ int init_engine(sphb200_engine* e, const sphb200_config* cfg, int64_t n, void* w
         blocks *= (size_t)e->dblocks.nb[a];
       }
       e->dblocks.bmin = (float4*)(e->arena + L.dbox);
-      e->dblocks.bmax = e->dblocks.bmin + blocks;
+      e->dblocks.bmax = e->dblocks.bmin + 3 * blocks;
       const double rc = kernel_cutoff(*cfg);
-      // pairs: relative drift below the skin; particles: the interior tiles keep 2 S cells (two
-      // cutoffs + skins) between their own particles and the periodic seam, a particle that has
-      // moved less than 0.9 cutoffs cannot meet one that crossed the seam
+      // pairs that share a window of 2 S cells: relative drift below the skin; all others were two
+      // (cutoff + skin) apart at the sort and stay a cutoff apart while every particle's own drift
+      // is below (2 (cutoff + skin) - cutoff) / 2 (cells.cuh, k_drift_join); the same guard keeps
+      // a particle that crossed the periodic seam a cutoff away from the interior tiles
       e->rel_limit = (float)(e->skin_frac * rc * (1.0 - 1e-3));
-      e->rel_guard = (float)(0.9 * rc);
+      e->rel_guard = (float)(0.5 * (2.0 * rc * (1.0 + e->skin_frac) - rc) * (1.0 - 1e-3));
     }
   }
   e->dn = (int*)(e->arena + L.dn);

@@ -225,21 +225,22 @@ def test_bench_db2d_generator_is_the_reference_case():
 
 @pytest.mark.parametrize("n_cells,S", [((13, 12, 14), 2), ((12, 13, 1), 2), ((19, 20, 21), 3)])
 def test_relative_drift_window_bounds_every_pair(n_cells, S):
-    """NumPy model of the relative re-sort criterion (csrc/cells.cuh: k_drift_box / k_drift_window):
+    """NumPy model of the relative re-sort criterion (csrc/cells.cuh: k_drift_box / k_drift_join):
     particles are binned into the cells of the frozen table, cells into blocks of S^dim cells (the
-    last block of an axis may be partial), every block joins the drift boxes of the blocks that
-    hold a cell within S cells of its own (periodic in cells).  For EVERY pair that was within one
-    stencil (S cells) at the sort, |disp_i - disp_j| must not exceed the diagonal of the joined box
-    of either particle's block -- that inequality is what lets the engine keep its skin lists."""
+    last block of an axis may be partial), every block joins -- axis after axis -- the drift boxes
+    of the blocks that hold a cell within 2 S cells of its own cells (periodic in cells).  Then for
+    EVERY pair of particles either (a) |disp_i - disp_j| is at most the diagonal of the joined box
+    of i's block, or (b) the two were at least 2 S cells apart along some axis at the sort -- the
+    two cases of the sufficiency argument in cells.cuh."""
     rng = np.random.default_rng(sum(n_cells) + S)
     dim = 3 if n_cells[2] > 1 else 2
     n_cells = np.array(n_cells[:dim])
     box = np.array([1.0, 0.9, 1.1][:dim])
     cell = box / n_cells
-    reach = S * cell.min()  # pairs closer than this lie within S cells along every axis
-    npart = 1500
+    npart = 1200
     rb = rng.uniform(0, 1, (npart, dim)) * box
-    disp = 0.05 * reach * np.sin(2 * np.pi * rb / box + rng.uniform(0, 6, dim)) + rng.normal(0, 0.01 * reach, (npart, dim))
+    amp = 0.05 * S * cell.min()
+    disp = amp * np.sin(2 * np.pi * rb / box + rng.uniform(0, 6, dim)) + rng.normal(0, 0.2 * amp, (npart, dim))
     cidx = np.minimum((rb / cell).astype(int), n_cells - 1)
     nb = (n_cells + S - 1) // S
     bidx = cidx // S
@@ -251,29 +252,35 @@ def test_relative_drift_window_bounds_every_pair(n_cells, S):
         hi[b] = np.maximum(hi[b], disp[p])
 
     def window_blocks(bc, a):  # the kernel's rule, one axis
-        out = []
-        for off in range(-S, 2 * S):
-            cc = (S * bc + off) % n_cells[a]
-            if cc // S not in out:
-                out.append(int(cc // S))
-        assert len(out) <= 6
+        out, last = [], -1
+        for off in range(-2 * S, 3 * S):
+            blk = int(((S * bc + off) % n_cells[a]) // S)
+            if blk != last:
+                out.append(blk)
+            last = blk
         return out
 
-    spread = np.zeros(tuple(nb))
-    for b in np.ndindex(*nb):
-        wl, wh = np.full(dim, np.inf), np.full(dim, -np.inf)
-        axes = [window_blocks(b[a], a) for a in range(dim)]
-        for q in np.ndindex(*[len(x) for x in axes]):
-            qq = tuple(axes[a][q[a]] for a in range(dim))
-            wl, wh = np.minimum(wl, lo[qq]), np.maximum(wh, hi[qq])
-        spread[b] = np.sqrt((np.maximum(wh - wl, 0.0) ** 2).sum())
-    d = rb[:, None, :] - rb[None, :, :]
-    d = np.mod(d + box / 2, box) - box / 2
-    near = (d ** 2).sum(-1) < reach ** 2
+    for a in range(dim):  # the separable passes of k_drift_join
+        lo2, hi2 = np.empty_like(lo), np.empty_like(hi)
+        for b in np.ndindex(*nb):
+            src = [tuple(b[:a]) + (q,) + tuple(b[a + 1:]) for q in window_blocks(b[a], a)]
+            lo2[b] = np.min([lo[s] for s in src], axis=0)
+            hi2[b] = np.max([hi[s] for s in src], axis=0)
+        lo, hi = lo2, hi2
+    spread = np.sqrt((np.maximum(hi - lo, 0.0) ** 2).sum(-1))
     rel = np.sqrt(((disp[:, None, :] - disp[None, :, :]) ** 2).sum(-1))
-    i, j = np.nonzero(near)
-    assert len(i) > npart
-    bound = spread[tuple(bidx[i].T)]
-    assert (rel[i, j] <= bound + 1e-12).all()
-    # and it is not vacuous: the bound stays within a small multiple of the largest relative drift
-    assert bound.max() < 6 * rel[i, j].max()
+    # cell gap of j from the cells [S b, S b + S) of i's block, periodic, per axis
+    b0 = (bidx * S)[:, None, :]
+    cj = cidx[None, :, :]
+    fwd = np.mod(cj - b0, n_cells)              # 0 .. S-1 inside the block
+    gap = np.minimum(np.maximum(fwd - (S - 1), 0), np.mod(b0 - cj, n_cells))
+    in_window = (gap <= 2 * S).all(-1)
+    bound = spread[tuple(bidx.T)][:, None]
+    assert (rel[in_window] <= np.broadcast_to(bound, rel.shape)[in_window] + 1e-12).all()
+    # pairs outside the window were 2 S cells apart along some axis: distance >= 2 S cells
+    d = rb[:, None, :] - rb[None, :, :]
+    d = np.abs(np.mod(d + box / 2, box) - box / 2)
+    far = ~in_window
+    assert far.any() and ((d / cell)[far].max(-1) >= 2 * S - 1e-9).all()
+    # and the bound is not vacuous
+    assert bound.max() < 8 * rel[in_window].max()
